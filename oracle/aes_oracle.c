@@ -1,0 +1,501 @@
+/*
+ * aes_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY, see aes_oracle.h).
+ *
+ * A from-scratch restatement of the hot path of polfosol/micro-AES: the Rijndael
+ * block cipher and the ECB / CTR / XTS / GCM chaining loops.  Each function cites
+ * the micro_aes.c lines whose behaviour it restates.  It is written for clarity
+ * and for being pinned against the reference, not for speed; the only liberties
+ * taken are a run-time key length and no static state.
+ */
+#include "aes_oracle.h"
+#include <string.h>
+
+/* ------------------------------------------------------------------------ */
+/* GF(2^8) and the S-boxes (values of micro_aes.c:41-65, derived not copied) */
+/* ------------------------------------------------------------------------ */
+
+static uint8_t SBOX[256], INV_SBOX[256];
+
+/* multiply by x modulo x^8+x^4+x^3+x+1 (micro_aes.c:115-118 `xtime`) */
+static uint8_t gf8_double(uint8_t a)
+{
+    return (uint8_t)((a << 1) ^ ((a >> 7) * 0x1b));
+}
+
+static uint8_t gf8_mul(uint8_t a, uint8_t b)
+{
+    uint8_t r = 0;
+    while (b) {
+        if (b & 1) r ^= a;
+        a = gf8_double(a);
+        b >>= 1;
+    }
+    return r;
+}
+
+/* FIPS-197 5.1.1: S(a) = affine(a^-1) */
+__attribute__((constructor)) static void build_sboxes(void)
+{
+    int a;
+    for (a = 0; a < 256; ++a) {
+        uint8_t inv = 0, s;
+        int b;
+        if (a)
+            for (b = 1; b < 256; ++b)
+                if (gf8_mul((uint8_t)a, (uint8_t)b) == 1) { inv = (uint8_t)b; break; }
+        s = inv;
+        s ^= (uint8_t)((inv << 1) | (inv >> 7));
+        s ^= (uint8_t)((inv << 2) | (inv >> 6));
+        s ^= (uint8_t)((inv << 3) | (inv >> 5));
+        s ^= (uint8_t)((inv << 4) | (inv >> 4));
+        s ^= 0x63;
+        SBOX[a] = s;
+        INV_SBOX[s] = (uint8_t)a;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* key schedule and the block cipher                                        */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+    int rounds;             /* Nk + 6  (micro_aes.c:16-27) */
+    uint8_t rk[240];        /* round r at offset 16*r, FIPS-197 byte order */
+} aes_ctx;
+
+/* micro_aes.c:144-178 (KeyExpansion) */
+static void key_setup(aes_ctx *c, int keybits, const uint8_t *key)
+{
+    const int nk = keybits == 256 ? 8 : keybits == 192 ? 6 : 4;
+    const int total = 4 * (nk + 7);        /* 4 * (rounds + 1) words */
+    uint8_t rcon = 1;
+    int i;
+
+    c->rounds = nk + 6;
+    memcpy(c->rk, key, (size_t)(4 * nk));
+    for (i = nk; i < total; ++i) {
+        uint8_t t[4];
+        memcpy(t, c->rk + 4 * (i - 1), 4);
+        if (i % nk == 0) {
+            /* RotWord, SubWord, rcon */
+            const uint8_t t0 = t[0];
+            t[0] = SBOX[t[1]] ^ rcon;
+            t[1] = SBOX[t[2]];
+            t[2] = SBOX[t[3]];
+            t[3] = SBOX[t0];
+            rcon = gf8_double(rcon);
+        } else if (nk == 8 && i % nk == 4) {
+            /* AES-256 extra SubWord (micro_aes.c:165-172) */
+            t[0] = SBOX[t[0]]; t[1] = SBOX[t[1]];
+            t[2] = SBOX[t[2]]; t[3] = SBOX[t[3]];
+        }
+        c->rk[4 * i + 0] = c->rk[4 * (i - nk) + 0] ^ t[0];
+        c->rk[4 * i + 1] = c->rk[4 * (i - nk) + 1] ^ t[1];
+        c->rk[4 * i + 2] = c->rk[4 * (i - nk) + 2] ^ t[2];
+        c->rk[4 * i + 3] = c->rk[4 * (i - nk) + 3] ^ t[3];
+    }
+}
+
+static void xor16(uint8_t *dst, const uint8_t *src)   /* micro_aes.c:105-112 */
+{
+    int i;
+    for (i = 0; i < 16; ++i) dst[i] ^= src[i];
+}
+
+/* state byte i = column i/4, row i%4 (micro_aes.c:74-77) */
+static void shift_rows(uint8_t s[16], int inverse)     /* micro_aes.c:198-218, 278-298 */
+{
+    uint8_t t[16];
+    int col, row;
+    for (col = 0; col < 4; ++col)
+        for (row = 0; row < 4; ++row) {
+            const int from = inverse ? (col - row + 4) % 4 : (col + row) % 4;
+            t[4 * col + row] = s[4 * from + row];
+        }
+    memcpy(s, t, 16);
+}
+
+static void mix_columns(uint8_t s[16])                 /* micro_aes.c:221-239 */
+{
+    int c;
+    for (c = 0; c < 16; c += 4) {
+        const uint8_t a0 = s[c], a1 = s[c + 1], a2 = s[c + 2], a3 = s[c + 3];
+        const uint8_t all = a0 ^ a1 ^ a2 ^ a3;
+        s[c + 0] = a0 ^ all ^ gf8_double(a0 ^ a1);
+        s[c + 1] = a1 ^ all ^ gf8_double(a1 ^ a2);
+        s[c + 2] = a2 ^ all ^ gf8_double(a2 ^ a3);
+        s[c + 3] = a3 ^ all ^ gf8_double(a3 ^ a0);
+    }
+}
+
+static void inv_mix_columns(uint8_t s[16])             /* micro_aes.c:301-312 */
+{
+    int c;
+    for (c = 0; c < 16; c += 4) {
+        const uint8_t a0 = s[c], a1 = s[c + 1], a2 = s[c + 2], a3 = s[c + 3];
+        s[c + 0] = gf8_mul(a0, 14) ^ gf8_mul(a1, 11) ^ gf8_mul(a2, 13) ^ gf8_mul(a3, 9);
+        s[c + 1] = gf8_mul(a0, 9) ^ gf8_mul(a1, 14) ^ gf8_mul(a2, 11) ^ gf8_mul(a3, 13);
+        s[c + 2] = gf8_mul(a0, 13) ^ gf8_mul(a1, 9) ^ gf8_mul(a2, 14) ^ gf8_mul(a3, 11);
+        s[c + 3] = gf8_mul(a0, 11) ^ gf8_mul(a1, 13) ^ gf8_mul(a2, 9) ^ gf8_mul(a3, 14);
+    }
+}
+
+/* micro_aes.c:242-259 (rijndaelEncrypt); in may alias out */
+static void encrypt_block(const aes_ctx *c, const uint8_t *in, uint8_t *out)
+{
+    uint8_t s[16];
+    int r, i;
+    memcpy(s, in, 16);
+    for (r = 0; r < c->rounds; ++r) {
+        xor16(s, c->rk + 16 * r);
+        for (i = 0; i < 16; ++i) s[i] = SBOX[s[i]];
+        shift_rows(s, 0);
+        if (r + 1 < c->rounds) mix_columns(s);
+    }
+    xor16(s, c->rk + 16 * c->rounds);
+    memcpy(out, s, 16);
+}
+
+/* micro_aes.c:315-332 (rijndaelDecrypt): the straight inverse cipher */
+static void decrypt_block(const aes_ctx *c, const uint8_t *in, uint8_t *out)
+{
+    uint8_t s[16];
+    int r, i;
+    memcpy(s, in, 16);
+    xor16(s, c->rk + 16 * c->rounds);
+    for (r = c->rounds - 1; r >= 0; --r) {
+        shift_rows(s, 1);
+        for (i = 0; i < 16; ++i) s[i] = INV_SBOX[s[i]];
+        xor16(s, c->rk + 16 * r);
+        if (r) inv_mix_columns(s);
+    }
+    memcpy(out, s, 16);
+}
+
+int oracle_key_expansion(int keybits, const uint8_t *key, uint8_t *roundkeys)
+{
+    aes_ctx c;
+    key_setup(&c, keybits, key);
+    memcpy(roundkeys, c.rk, (size_t)(16 * (c.rounds + 1)));
+    return c.rounds;
+}
+
+void oracle_encrypt_block(int keybits, const uint8_t *key, const uint8_t in[16], uint8_t out[16])
+{
+    aes_ctx c;
+    key_setup(&c, keybits, key);
+    encrypt_block(&c, in, out);
+}
+
+void oracle_decrypt_block(int keybits, const uint8_t *key, const uint8_t in[16], uint8_t out[16])
+{
+    aes_ctx c;
+    key_setup(&c, keybits, key);
+    decrypt_block(&c, in, out);
+}
+
+/* ------------------------------------------------------------------------ */
+/* ECB                                                                      */
+/* ------------------------------------------------------------------------ */
+
+/* micro_aes.c:636-653 with AES_PADDING == 0: the partial tail block is
+ * zero-filled and encrypted (padBlock, micro_aes.c:610-621) */
+void oracle_ecb_encrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    const uint8_t *x = (const uint8_t *)in;
+    uint8_t *y = (uint8_t *)out;
+    size_t n = len / 16, tail = len % 16;
+
+    key_setup(&c, keybits, key);
+    for (; n--; x += 16, y += 16) encrypt_block(&c, x, y);
+    if (tail) {
+        uint8_t last[16] = {0};
+        memcpy(last, x, tail);
+        encrypt_block(&c, last, y);
+    }
+}
+
+/* micro_aes.c:663-680: full blocks are decrypted, the tail bytes are copied
+ * through untouched (the initial memcpy), and a ragged length is an error */
+int oracle_ecb_decrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    const uint8_t *x = (const uint8_t *)in;
+    uint8_t *y = (uint8_t *)out;
+    size_t n = len / 16, tail = len % 16;
+
+    key_setup(&c, keybits, key);
+    for (; n--; x += 16, y += 16) decrypt_block(&c, x, y);
+    if (tail) memmove(y, x, tail);
+    return tail ? ORACLE_DECRYPTION_ERROR : ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
+/* CTR                                                                      */
+/* ------------------------------------------------------------------------ */
+
+/* counter += n on the 56-bit big-endian field in bytes 9..15; byte 8 and below
+ * never change (incBlock with index = LAST, micro_aes.c:421-427) */
+static void ctr_add(uint8_t ctr[16], uint64_t n)
+{
+    uint64_t v = 0;
+    int i;
+    for (i = 9; i < 16; ++i) v = v << 8 | ctr[i];
+    v += n;                                   /* bits above 55 are discarded */
+    for (i = 15; i >= 9; --i, v >>= 8) ctr[i] = (uint8_t)v;
+}
+
+/* the shared loop of micro_aes.c:943-949 (CTR_cipher): ctr is consumed */
+static void ctr_stream(const aes_ctx *c, uint8_t ctr[16],
+                       const uint8_t *x, size_t len, uint8_t *y)
+{
+    uint8_t ks[16];
+    size_t i;
+    for (; len >= 16; len -= 16, x += 16, y += 16) {
+        encrypt_block(c, ctr, ks);
+        for (i = 0; i < 16; ++i) y[i] = x[i] ^ ks[i];
+        ctr_add(ctr, 1);
+    }
+    if (len) {                                /* mixThenXor, micro_aes.c:534-544 */
+        encrypt_block(c, ctr, ks);
+        for (i = 0; i < len; ++i) y[i] = x[i] ^ ks[i];
+    }
+}
+
+/* micro_aes.c:962-976 with PRESET_COUNTER == 0, CTR_IV_LENGTH == 12,
+ * CTR_START_VALUE == 1 */
+void oracle_ctr_crypt_at(int keybits, const uint8_t *key, const uint8_t iv[12],
+                         uint64_t first_block, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t ctr[16] = {0};
+    memcpy(ctr, iv, 12);
+    ctr[15] ^= 1;                             /* xorBEint(ctr, 1, LAST), :971 */
+    ctr_add(ctr, first_block);
+    key_setup(&c, keybits, key);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+}
+
+void oracle_ctr_crypt(int keybits, const uint8_t *key, const uint8_t iv[12],
+                      const void *in, size_t len, void *out)
+{
+    oracle_ctr_crypt_at(keybits, key, iv, 0, in, len, out);
+}
+
+/* ------------------------------------------------------------------------ */
+/* XTS                                                                      */
+/* ------------------------------------------------------------------------ */
+
+/* micro_aes.c:449-458 (doubleLblock): little-endian shift left, 0x87 fold */
+void oracle_xts_double(uint8_t t[16])
+{
+    unsigned carry = 0;
+    int i;
+    for (i = 0; i < 16; ++i) {
+        const unsigned v = (unsigned)t[i] << 1 | carry;
+        carry = v >> 8;
+        t[i] = (uint8_t)v;
+    }
+    if (carry) t[0] ^= 0x87;
+}
+
+static void xex_block(const aes_ctx *c, int encrypt, const uint8_t T[16],
+                      const uint8_t *x, uint8_t *y)
+{
+    uint8_t b[16];
+    memcpy(b, x, 16);
+    xor16(b, T);
+    if (encrypt) encrypt_block(c, b, b); else decrypt_block(c, b, b);
+    xor16(b, T);
+    memcpy(y, b, 16);
+}
+
+/* micro_aes.c:1008-1055 (XTS_cipher) */
+static int xts_unit(int keybits, const uint8_t *keys, const uint8_t *tweak,
+                    const uint8_t *x, size_t len, uint8_t *y, int encrypt)
+{
+    const int keysize = keybits / 8;
+    aes_ctx k1, k2;
+    uint8_t T[16] = {0};
+    size_t r = len % 16, n;
+
+    if (len < 16) return ORACLE_DATALENGTH_ERROR;       /* :1069, :1088 */
+    n = len / 16 - (r > 0);
+    if (tweak) memcpy(T, tweak, 16);                    /* NULL -> sector 0, :1017 */
+    key_setup(&k2, keybits, keys + keysize);            /* key2 = second half */
+    key_setup(&k1, keybits, keys);
+    encrypt_block(&k2, T, T);
+
+    for (; n--; x += 16, y += 16) {
+        xex_block(&k1, encrypt, T, x, y);
+        oracle_xts_double(T);
+    }
+    if (r) {                                            /* stealing, :1037-1053 */
+        uint8_t Tn[16], first[16], cc[16], pp[16];
+        size_t i;
+        memcpy(Tn, T, 16);
+        oracle_xts_double(Tn);
+        /* encrypt: block m-1 under T, stolen block under alpha*T; decrypt: swapped */
+        memcpy(first, x, 16);
+        xex_block(&k1, encrypt, encrypt ? T : Tn, first, cc);
+        for (i = 0; i < 16; ++i) pp[i] = i < r ? x[16 + i] : cc[i];
+        for (i = 0; i < r; ++i) first[i] = cc[i];       /* keep before y is written */
+        xex_block(&k1, encrypt, encrypt ? Tn : T, pp, y);
+        memcpy(y + 16, first, r);
+    }
+    return ORACLE_SUCCESS;
+}
+
+int oracle_xts_encrypt(int keybits, const uint8_t *keys, const uint8_t *tweak,
+                       const void *in, size_t len, void *out)
+{
+    return xts_unit(keybits, keys, tweak, (const uint8_t *)in, len, (uint8_t *)out, 1);
+}
+
+int oracle_xts_decrypt(int keybits, const uint8_t *keys, const uint8_t *tweak,
+                       const void *in, size_t len, void *out)
+{
+    return xts_unit(keybits, keys, tweak, (const uint8_t *)in, len, (uint8_t *)out, 0);
+}
+
+int oracle_xts_sectors(int keybits, const uint8_t *keys, uint64_t first_sector,
+                       size_t sector_bytes, const void *in, size_t len, void *out,
+                       int encrypt)
+{
+    const uint8_t *x = (const uint8_t *)in;
+    uint8_t *y = (uint8_t *)out;
+    uint64_t s = first_sector;
+    if (sector_bytes < 16 || len % sector_bytes) return ORACLE_DATALENGTH_ERROR;
+    for (; len; len -= sector_bytes, x += sector_bytes, y += sector_bytes, ++s) {
+        uint8_t tweak[16] = {0};
+        int i;
+        for (i = 0; i < 8; ++i) tweak[i] = (uint8_t)(s >> (8 * i));  /* copyLint, :399 */
+        xts_unit(keybits, keys, tweak, x, sector_bytes, y, encrypt);
+    }
+    return ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
+/* GCM                                                                      */
+/* ------------------------------------------------------------------------ */
+
+/* micro_aes.c:464-473 (divideBblock): big-endian shift right, 0xE1 fold */
+static void gcm_halve(uint8_t y[16])
+{
+    const unsigned lsb = y[15] & 1;
+    int i;
+    for (i = 15; i > 0; --i) y[i] = (uint8_t)(y[i] >> 1 | y[i - 1] << 7);
+    y[0] >>= 1;
+    if (lsb) y[0] ^= 0xe1;
+}
+
+/* micro_aes.c:476-493 (mulGF128): y <- x*y, bits of x MSB first */
+void oracle_gf128_mul(const uint8_t x[16], uint8_t y[16])
+{
+    uint8_t acc[16] = {0};
+    int i, b;
+    for (i = 0; i < 16; ++i)
+        for (b = 0x80; b; b >>= 1) {
+            if (x[i] & b) xor16(acc, y);
+            gcm_halve(y);
+        }
+    memcpy(y, acc, 16);
+}
+
+/* micro_aes.c:551-570 (xMac with mix = mulGF128) */
+static void ghash_absorb(const uint8_t H[16], const uint8_t *x, size_t len, uint8_t g[16])
+{
+    size_t i;
+    for (; len >= 16; len -= 16, x += 16) {
+        xor16(g, x);
+        oracle_gf128_mul(H, g);
+    }
+    if (len) {
+        for (i = 0; i < len; ++i) g[i] ^= x[i];
+        oracle_gf128_mul(H, g);
+    }
+}
+
+/* micro_aes.c:1127-1137 (gHash) */
+void oracle_ghash(const uint8_t H[16], const void *aad, size_t aadlen,
+                  const void *ct, size_t ctlen, uint8_t out[16])
+{
+    uint8_t lens[16];
+    uint64_t abits = (uint64_t)aadlen * 8, cbits = (uint64_t)ctlen * 8;
+    int i;
+    for (i = 7; i >= 0; --i, abits >>= 8) lens[i] = (uint8_t)abits;
+    for (i = 15; i >= 8; --i, cbits >>= 8) lens[i] = (uint8_t)cbits;
+    memset(out, 0, 16);
+    ghash_absorb(H, (const uint8_t *)aad, aadlen, out);
+    ghash_absorb(H, (const uint8_t *)ct, ctlen, out);
+    ghash_absorb(H, lens, 16, out);
+}
+
+/* micro_aes.c:1140-1152 (GCMsetup) with GCM_NONCE_LEN == 12 */
+static void gcm_setup(aes_ctx *c, int keybits, const uint8_t *key, const uint8_t nonce[12],
+                      uint8_t H[16], uint8_t j0[16])
+{
+    key_setup(c, keybits, key);
+    memset(H, 0, 16);
+    encrypt_block(c, H, H);
+    memcpy(j0, nonce, 12);
+    j0[12] = j0[13] = j0[14] = 0;
+    j0[15] = 1;
+}
+
+/* micro_aes.c:1164-1179 */
+void oracle_gcm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t H[16], j0[16], ctr[16], ekj0[16], g[16];
+    gcm_setup(&c, keybits, key, nonce, H, j0);
+    memcpy(ctr, j0, 16);
+    ctr_add(ctr, 1);                          /* CCM_GCM pre-increment, :939-941 */
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+    encrypt_block(&c, j0, ekj0);
+    oracle_ghash(H, aad, aadlen, out, len, g);
+    xor16(g, ekj0);
+    memcpy((uint8_t *)out + len, g, 16);
+}
+
+/* micro_aes.c:1192-1212: verify first, leave `out` untouched on failure */
+int oracle_gcm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t H[16], j0[16], ctr[16], ekj0[16], g[16];
+    gcm_setup(&c, keybits, key, nonce, H, j0);
+    oracle_ghash(H, aad, aadlen, in, len, g);
+    encrypt_block(&c, j0, ekj0);
+    xor16(g, ekj0);
+    if (memcmp(g, (const uint8_t *)in + len, 16)) return ORACLE_AUTHENTICATION_ERROR;
+    memcpy(ctr, j0, 16);
+    ctr_add(ctr, 1);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+    return ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
+/* synthetic data                                                           */
+/* ------------------------------------------------------------------------ */
+
+static uint64_t splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords)
+{
+    uint8_t *p = (uint8_t *)dst;
+    size_t w;
+    int i;
+    for (w = 0; w < nwords; ++w) {
+        uint64_t v = splitmix64(seed + first_word + w);
+        for (i = 0; i < 8; ++i, v >>= 8) *p++ = (uint8_t)v;
+    }
+}

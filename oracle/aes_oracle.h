@@ -1,0 +1,88 @@
+/*
+ * aes_oracle.h -- CPU oracle for the AES ECB/CTR/XTS/GCM hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the algorithms in
+ * polfosol/micro-AES (micro_aes.c) for the one hot path this repository
+ * accelerates.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it; the product library (libuaes_b200.so) never
+ * links, loads or calls anything in oracle/.
+ *
+ * Parity is PINNED: tests/test_oracle.py checks every function below against
+ *   - the reference's own known-answer vectors (main.c, testvectors/ .rsp files;
+ *     committed as tests/golden/ JSON files by tests/golden/make_golden.py), and
+ *   - the unmodified reference compiled from /root/reference into oracle/_ref/
+ *     (see oracle/Makefile), on random inputs.
+ *
+ * Unlike the reference, key length is a run-time argument (keybits = 128|192|256;
+ * the reference fixes it with the AES___ macro, micro_aes.h:17) and nothing is
+ * kept in static storage (the reference keeps RoundKey static, micro_aes.c:72),
+ * so tests may call it from several threads/processes.
+ */
+#ifndef AES_ORACLE_H_
+#define AES_ORACLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* return codes: same values as micro_aes.h:469-476 */
+enum {
+    ORACLE_SUCCESS              = 0,
+    ORACLE_DATALENGTH_ERROR     = 0x1,
+    ORACLE_AUTHENTICATION_ERROR = 0x1A,
+    ORACLE_DECRYPTION_ERROR     = 0x1D
+};
+
+/* FIPS-197 single block (micro_aes.c:242-259 / 315-332) */
+void oracle_encrypt_block(int keybits, const uint8_t *key, const uint8_t in[16], uint8_t out[16]);
+void oracle_decrypt_block(int keybits, const uint8_t *key, const uint8_t in[16], uint8_t out[16]);
+/* key schedule, FIPS-197 order, 16*(rounds+1) bytes (micro_aes.c:144-178); returns rounds */
+int  oracle_key_expansion(int keybits, const uint8_t *key, uint8_t *roundkeys);
+
+/* ECB with the default zero padding, out holds ceil16(len) (micro_aes.c:636-680) */
+void oracle_ecb_encrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out);
+int  oracle_ecb_decrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out);
+
+/* CTR, 12-byte IV, counter starts at 1, 56-bit big-endian carry (micro_aes.c:919-976).
+ * first_block skips that many keystream blocks (counter-range extension). */
+void oracle_ctr_crypt(int keybits, const uint8_t *key, const uint8_t iv[12],
+                      const void *in, size_t len, void *out);
+void oracle_ctr_crypt_at(int keybits, const uint8_t *key, const uint8_t iv[12],
+                         uint64_t first_block, const void *in, size_t len, void *out);
+
+/* XTS, one data unit per call, keys = K1 || K2, tweak NULL -> sector 0
+ * (micro_aes.c:1008-1093) */
+int  oracle_xts_encrypt(int keybits, const uint8_t *keys, const uint8_t *tweak,
+                        const void *in, size_t len, void *out);
+int  oracle_xts_decrypt(int keybits, const uint8_t *keys, const uint8_t *tweak,
+                        const void *in, size_t len, void *out);
+/* caller loop over fixed-size sectors, tweak_j = LE128(first_sector + j)
+ * (the copyLint convention of micro_aes.c:1017-1021).  len % sector_bytes == 0. */
+int  oracle_xts_sectors(int keybits, const uint8_t *keys, uint64_t first_sector,
+                        size_t sector_bytes, const void *in, size_t len, void *out,
+                        int encrypt);
+
+/* GCM, 12-byte nonce, 16-byte tag appended at out+len (micro_aes.c:1127-1212) */
+void oracle_gcm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+int  oracle_gcm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+/* GHASH(H; aad, ct) including the length block (micro_aes.c:1127-1137) */
+void oracle_ghash(const uint8_t H[16], const void *aad, size_t aadlen,
+                  const void *ct, size_t ctlen, uint8_t out[16]);
+/* y <- x*y in GCM's GF(2^128) (micro_aes.c:476-493) */
+void oracle_gf128_mul(const uint8_t x[16], uint8_t y[16]);
+/* T <- alpha*T in XTS's GF(2^128) (micro_aes.c:449-458) */
+void oracle_xts_double(uint8_t t[16]);
+
+/* splitmix64 synthetic-data generator shared by tests and bench: 64-bit word w of
+ * the buffer (byte offset 8w, little-endian) = splitmix64(seed + first_word + w) */
+void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,210 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.json from the reference's own known-answer material.
+
+Run in the BUILD container only (needs /root/reference); the outputs are committed
+so that the GPU box, which has no /root/reference, can run every parity test.
+
+Sources (all under /root/reference):
+  main.c:16-88           the 57-byte demo vectors, for ECB / CTR / XTS / GCM
+  main.c:19-21           FIPS-197 C.1 hidden in the key constants (main.c:124-134)
+  testvectors/XTSGenAES{128,256}.rsp    filtered as aes_testvectors_XTS.h:84 does
+                         (whole-byte data units only) -> 800 / 600 cases
+  testvectors/GcmEncryptExtIV{128,192,256}.rsp  filtered as aes_testvectors_GCM.h:86
+                         does (IVlen = 96, Taglen = 128) -> 375 cases each
+
+Additionally writes oracle_ref_samples.json: outputs of the UNMODIFIED reference
+(oracle/_ref/libref*.so) on seeded inputs that no in-tree vector pins (long CTR,
+counter carries, multi-sector XTS, XTS-256 stealing, big GCM) so that the oracle
+stays pinned to the reference on the GPU box as well.
+"""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import sys
+
+REF = os.environ.get("UAES_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+def c_strings(src):
+    """name -> concatenated hex of every `*name = "..." "..."` initialiser, in order of
+    appearance (a name can appear several times under different #if branches)."""
+    out = {}
+    for m in re.finditer(r'\*(\w+)\s*=\s*((?:"[^"]*"\s*(?:/\*.*?\*/\s*)*|#.*\n\s*)+)', src):
+        name, body = m.group(1), m.group(2)
+        # split the initialiser on preprocessor lines so #if/#else alternatives stay apart
+        parts, cur = [], []
+        for line in body.splitlines():
+            if line.strip().startswith("#"):
+                if cur:
+                    parts.append("".join(cur))
+                    cur = []
+                continue
+            cur += re.findall(r'"([^"]*)"', line)
+        if cur:
+            parts.append("".join(cur))
+        out.setdefault(name, []).extend(p.replace(" ", "").lower() for p in parts)
+    return out
+
+
+def main_c_vectors():
+    src = open(os.path.join(REF, "main.c"), encoding="utf-8").read()
+    s = c_strings(src)
+    key_pool = s["cipherKey"][0] + s["secondKey"][0]          # main.c:119-120
+    pt = s["plainText"][0]
+    assert len(pt) == 114
+    # order of appearance in main.c: AES-256 block first, then AES-128, then AES-192
+    gcm256, gcm128 = s["gcmcipher"][0], s["gcmcipher"][1]
+    xts256, xts128 = s["xtscipher"][0], s["xtscipher"][1]
+    ecb128 = s["ecbcipher"][0]
+    ctr128_preset, ctr128 = s["ctrcipher"][0], s["ctrcipher"][1]
+    assert len(ecb128) == 128 and len(ctr128) == 114 and len(gcm128) == 114 + 32
+    return {
+        "source": "main.c:16-88 (57-byte demo vectors) and main.c:19-21 (FIPS-197 C.1)",
+        "plaintext": pt,
+        "iv16": s["iVec"][0],
+        "key_pool": key_pool,
+        "aad": s["secretKey"][0][2:],                          # authKey + 1, 31 bytes
+        "fips197_c1": {"key": s["secretKey"][0][:32], "pt": s["secondKey"][0][:32],
+                       "ct": s["cipherKey"][0][32:]},
+        "ecb128": ecb128, "ctr128": ctr128, "ctr128_preset_counter": ctr128_preset,
+        "xts128": xts128, "xts256": xts256, "gcm128": gcm128, "gcm256": gcm256,
+    }
+
+
+def parse_xts(path, keybits):
+    cases, cur, direction = [], {}, None
+    for line in open(path):
+        line = line.strip()
+        if line in ("[ENCRYPT]", "[DECRYPT]"):
+            direction = line[1:-1].lower()
+        elif " = " in line or line.endswith(" ="):
+            k, _, v = line.partition(" =")
+            cur[k.strip()] = v.strip()
+            if "PT" in cur and "CT" in cur:
+                if (len(cur["Key"]) == keybits // 4
+                        and int(cur["DataUnitLen"]) == 4 * len(cur["PT"])):
+                    cases.append({"dir": direction, "key": cur["Key"], "i": cur["i"],
+                                  "pt": cur["PT"], "ct": cur["CT"]})
+                cur = {}
+    return cases
+
+
+def parse_gcm(path, keybits):
+    cases, cur, hdr = [], {}, {}
+    for line in open(path):
+        line = line.strip()
+        m = re.match(r"\[(\w+) = (\d+)\]", line)
+        if m:
+            hdr[m.group(1)] = int(m.group(2))
+        elif " = " in line or line.endswith(" ="):
+            k, _, v = line.partition(" =")
+            cur[k.strip()] = v.strip()
+            if "Tag" in cur:
+                if hdr["Keylen"] == keybits and hdr["IVlen"] == 96 and hdr["Taglen"] == 128:
+                    cases.append({"key": cur["Key"], "iv": cur["IV"], "pt": cur["PT"],
+                                  "aad": cur["AAD"], "ct": cur["CT"], "tag": cur["Tag"]})
+                cur = {}
+    return cases
+
+
+def rnd(tag, n):
+    """deterministic pseudo-random bytes: SHA-256 in counter mode over a tag"""
+    out = b""
+    i = 0
+    while len(out) < n:
+        out += hashlib.sha256(f"{tag}:{i}".encode()).digest()
+        i += 1
+    return out[:n]
+
+
+def ref_samples():
+    """outputs of the unmodified reference on inputs no in-tree vector covers"""
+    libs = {b: ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libref{b}.so"))
+            for b in (128, 192, 256)}
+    pc = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref128pc.so"))
+    out = {"source": "oracle/_ref/libref*.so = unmodified /root/reference/micro_aes.c, "
+                     "gcc -O2 -fno-strict-aliasing; inputs = SHA-256 counter streams (rnd())",
+           "ctr": [], "ctr_preset_counter": [], "ecb": [], "xts": [], "xts_sectors": [],
+           "gcm": []}
+    sha = lambda b: hashlib.sha256(b).hexdigest()
+    for bits, lib in libs.items():
+        ks = bits // 8
+        for n in (0, 1, 15, 16, 17, 255, 4096, 65536 + 5, 1 << 20):
+            key, iv, pt = rnd(f"ctrk{bits}{n}", ks), rnd(f"ctri{bits}{n}", 12), rnd(f"ctrp{bits}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.AES_CTR_encrypt(key, iv, pt, ctypes.c_size_t(n), ct)
+            out["ctr"].append({"bits": bits, "n": n, "key": key.hex(), "iv": iv.hex(),
+                               "pt_tag": f"ctrp{bits}{n}", "ct_sha256": sha(ct.raw[:n]),
+                               "ct_head": ct.raw[:min(n, 64)].hex()})
+        for n in (0, 5, 16, 48, 100, 4096 + 7):
+            key, pt = rnd(f"ecbk{bits}{n}", ks), rnd(f"ecbp{bits}{n}", n)
+            m = (n + 15) // 16 * 16
+            ct = ctypes.create_string_buffer(m + 16)
+            lib.AES_ECB_encrypt(key, pt, ctypes.c_size_t(n), ct)
+            out["ecb"].append({"bits": bits, "n": n, "key": key.hex(), "pt_tag": f"ecbp{bits}{n}",
+                               "ct_sha256": sha(ct.raw[:m])})
+        if bits != 192:      # XTS-192 is not defined (testvectors/aes_testvectors.h:57-62)
+            for n in (16, 17, 31, 32, 33, 57, 512, 4096, 4096 + 9, 65536 + 15):
+                keys, tw, pt = rnd(f"xtsk{bits}{n}", 2 * ks), rnd(f"xtst{bits}{n}", 16), rnd(f"xtsp{bits}{n}", n)
+                ct = ctypes.create_string_buffer(n + 16)
+                rc = lib.AES_XTS_encrypt(keys, tw, pt, ctypes.c_size_t(n), ct)
+                assert rc == 0
+                out["xts"].append({"bits": bits, "n": n, "keys": keys.hex(), "tweak": tw.hex(),
+                                   "pt_tag": f"xtsp{bits}{n}", "ct_sha256": sha(ct.raw[:n])})
+            for first, sb, ns in ((0, 512, 40), ((1 << 32) - 3, 512, 8), (7, 4096, 3), (123456789012, 528, 5)):
+                keys, pt = rnd(f"xsk{bits}{first}", 2 * ks), rnd(f"xsp{bits}{first}", sb * ns)
+                ct = ctypes.create_string_buffer(sb * ns)
+                for j in range(ns):
+                    tw = (first + j).to_bytes(16, "little")
+                    o = ctypes.create_string_buffer(sb)
+                    lib.AES_XTS_encrypt(keys, tw, pt[j * sb:(j + 1) * sb], ctypes.c_size_t(sb), o)
+                    ct[j * sb:(j + 1) * sb] = o.raw
+                out["xts_sectors"].append({"bits": bits, "first_sector": first, "sector_bytes": sb,
+                                           "sectors": ns, "keys": keys.hex(),
+                                           "pt_tag": f"xsp{bits}{first}", "ct_sha256": sha(ct.raw)})
+        for n, a in ((0, 0), (1, 0), (16, 16), (57, 31), (1000, 20), (4096, 0), (65536 + 3, 129), (1 << 18, 7)):
+            key, nonce = rnd(f"gcmk{bits}{n}", ks), rnd(f"gcmn{bits}{n}", 12)
+            aad, pt = rnd(f"gcma{bits}{n}", a), rnd(f"gcmp{bits}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.AES_GCM_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            out["gcm"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                               "aad_tag": f"gcma{bits}{n}", "pt_tag": f"gcmp{bits}{n}",
+                               "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    # counter carries: the PRESET_COUNTER build takes the caller's 16-byte block as counter 0
+    for name, ctr_hex in (("byte15", "00112233445566778899aabbccddeeff"),
+                          ("into_nonce_byte11", "000102030405060708090a0bfffffffe"),
+                          ("wrap56", "a0a1a2a3a4a5a6a7a8fffffffffffffd")):
+        key, pt = rnd("pck" + name, 16), rnd("pcp" + name, 16 * 8)
+        ct = ctypes.create_string_buffer(16 * 8)
+        pc.AES_CTR_encrypt(key, bytes.fromhex(ctr_hex), pt, ctypes.c_size_t(16 * 8), ct)
+        out["ctr_preset_counter"].append({"name": name, "key": key.hex(), "counter0": ctr_hex,
+                                          "pt_tag": "pcp" + name, "ct": ct.raw.hex()})
+    return out
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit(f"{REF} not found: golden vectors can only be regenerated in the build container")
+    w = lambda name, obj: json.dump(obj, open(os.path.join(HERE, name), "w"), indent=0, separators=(",", ":"))
+    w("main_c.json", main_c_vectors())
+    tv = os.path.join(REF, "testvectors")
+    for bits in (128, 256):
+        c = parse_xts(os.path.join(tv, f"XTSGenAES{bits}.rsp"), 2 * bits)
+        w(f"xts{bits}.json", {"source": f"testvectors/XTSGenAES{bits}.rsp, filter of aes_testvectors_XTS.h:84",
+                              "cases": c})
+        print(f"xts{bits}: {len(c)} cases")
+    for bits in (128, 192, 256):
+        c = parse_gcm(os.path.join(tv, f"GcmEncryptExtIV{bits}.rsp"), bits)
+        w(f"gcm{bits}.json", {"source": f"testvectors/GcmEncryptExtIV{bits}.rsp, filter of aes_testvectors_GCM.h:86",
+                              "cases": c})
+        print(f"gcm{bits}: {len(c)} cases")
+    w("oracle_ref_samples.json", ref_samples())
+    print("ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,222 @@
+"""Pins the CPU oracle (oracle/aes_oracle.c) before anything trusts it.
+
+1. every known-answer vector the reference holds for the hot path
+   (main.c demo vectors, FIPS-197 C.1, XTSGenAES{128,256}.rsp 800/600
+   executed cases, GcmEncryptExtIV{128,192,256}.rsp 375 executed cases each), from the
+   committed fixtures tests/golden/*.json;
+2. outputs of the UNMODIFIED reference recorded in tests/golden/oracle_ref_samples.json
+   (long CTR, counter carries, multi-sector XTS, XTS-256 stealing, big GCM);
+3. when oracle/_ref/libref*.so is present (built from /root/reference in the build
+   container and shipped to the GPU box as a binary): live differential runs.
+
+CPU only.
+"""
+import pytest
+
+from util import Oracle, Reference, golden, rnd, sha256
+
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+# ---------------------------------------------------------------- main.c vectors
+
+def test_fips197_block(orc):
+    v = golden("main_c.json")["fips197_c1"]
+    assert orc.encrypt_block(H(v["key"]), H(v["pt"])) == H(v["ct"])
+    assert orc.decrypt_block(H(v["key"]), H(v["ct"])) == H(v["pt"])
+    # config 1 of BASELINE.json: AES-128-ECB single block through the mode API
+    assert orc.ecb_encrypt(H(v["key"]), H(v["pt"])) == H(v["ct"])
+
+
+def test_key_expansion_fips197_a1(orc):
+    # FIPS-197 appendix A.1: last round key of 2b7e1516...
+    rk = orc.key_expansion(H("2b7e151628aed2a6abf7158809cf4f3c"))
+    assert rk[-16:] == H("d014f9a8c9ee2589e13f0cc8b6630ca6")
+    rk = orc.key_expansion(H("603deb1015ca71be2b73aef0857d77811f352c073b6108d72d9810a30914dff4"))
+    assert rk[-16:] == H("fe4890d1e6188d0b046df344706c631e")
+    rk = orc.key_expansion(H("8e73b0f7da0e6452c810f32b809079e562f8ead2522c6b7b"))
+    assert rk[-16:] == H("e98ba06f448c773c8ecc720401002202")
+
+
+def test_main_c_ecb(orc):
+    m = golden("main_c.json")
+    key, pt = H(m["key_pool"])[:16], H(m["plaintext"])
+    ct = orc.ecb_encrypt(key, pt)                      # main.c:139-145, zero padded to 64
+    assert ct == H(m["ecb128"])
+    rc, back = orc.ecb_decrypt(key, ct)
+    assert rc == 0 and back[:57] == pt and back[57:] == bytes(7)
+
+
+def test_main_c_ctr(orc):
+    m = golden("main_c.json")
+    key, iv, pt = H(m["key_pool"])[:16], H(m["iv16"])[:12], H(m["plaintext"])
+    assert orc.ctr(key, iv, pt) == H(m["ctr128"])      # main.c:167-173
+    assert orc.ctr(key, iv, H(m["ctr128"])) == pt
+
+
+@pytest.mark.parametrize("bits", [128, 256])
+def test_main_c_xts(orc, bits):
+    m = golden("main_c.json")
+    keys, tw, pt = H(m["key_pool"])[:bits // 4], H(m["iv16"]), H(m["plaintext"])
+    rc, ct = orc.xts(keys, tw, pt)                     # main.c:174-180 (57 B: stealing)
+    assert rc == 0 and ct == H(m[f"xts{bits}"])
+    rc, back = orc.xts(keys, tw, ct, encrypt=False)
+    assert rc == 0 and back == pt
+
+
+@pytest.mark.parametrize("bits", [128, 256])
+def test_main_c_gcm(orc, bits):
+    m = golden("main_c.json")
+    key, nonce = H(m["key_pool"])[:bits // 8], H(m["iv16"])[:12]
+    aad, pt = H(m["aad"]), H(m["plaintext"])
+    out = orc.gcm_encrypt(key, nonce, aad, pt)         # main.c:191-197
+    assert out == H(m[f"gcm{bits}"])
+    rc, back = orc.gcm_decrypt(key, nonce, aad, out)
+    assert rc == 0 and back == pt
+    bad = bytearray(out)
+    bad[-1] ^= 1
+    rc, _ = orc.gcm_decrypt(key, nonce, aad, bytes(bad))
+    assert rc == 0x1A                                  # M_AUTHENTICATION_ERROR
+
+
+# ---------------------------------------------------------------- NIST .rsp vectors
+
+@pytest.mark.parametrize("bits,expected", [(128, 800), (256, 600)])
+def test_xts_rsp(orc, bits, expected):
+    cases = golden(f"xts{bits}.json")["cases"]
+    assert len(cases) == expected
+    for c in cases:
+        rc, ct = orc.xts(H(c["key"]), H(c["i"]), H(c["pt"]))
+        assert rc == 0 and ct == H(c["ct"])
+        rc, pt = orc.xts(H(c["key"]), H(c["i"]), H(c["ct"]), encrypt=False)
+        assert rc == 0 and pt == H(c["pt"])
+
+
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_gcm_rsp(orc, bits):
+    cases = golden(f"gcm{bits}.json")["cases"]
+    assert len(cases) == 375
+    for c in cases:
+        out = orc.gcm_encrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["pt"]))
+        assert out == H(c["ct"]) + H(c["tag"])
+        rc, pt = orc.gcm_decrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), out)
+        assert rc == 0 and pt == H(c["pt"])
+
+
+# ---------------------------------------------------------------- recorded reference outputs
+
+def test_ref_samples_ctr(orc):
+    s = golden("oracle_ref_samples.json")
+    for c in s["ctr"]:
+        ct = orc.ctr(H(c["key"]), H(c["iv"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(ct) == c["ct_sha256"], c
+        assert ct[:64].hex() == c["ct_head"]
+
+
+def test_ref_samples_counter_carry(orc):
+    """the 56-bit big-endian counter: recorded with the PRESET_COUNTER build
+    of the reference, reproduced by the oracle block by block"""
+    s = golden("oracle_ref_samples.json")
+    for c in s["ctr_preset_counter"]:
+        key, ctr, pt = H(c["key"]), bytearray(H(c["counter0"])), rnd(c["pt_tag"], 128)
+        out = bytearray()
+        for b in range(8):
+            ks = orc.encrypt_block(key, bytes(ctr))
+            out += bytes(x ^ y for x, y in zip(ks, pt[16 * b:16 * b + 16]))
+            v = (int.from_bytes(ctr[9:], "big") + 1) % (1 << 56)
+            ctr[9:] = v.to_bytes(7, "big")
+        assert out.hex() == c["ct"], c["name"]
+    # and through the mode API: iv||00000000 ^ 1 then +first_block must hit the same blocks
+    c = next(x for x in s["ctr_preset_counter"] if x["name"] == "into_nonce_byte11")
+    key, pt = H(c["key"]), rnd(c["pt_tag"], 128)
+    iv = H(c["counter0"])[:12]                         # 00..0b, counter field = fffffffe
+    first = 0xFFFFFFFE - 1                             # counter(k) = 1 + k
+    assert orc.ctr(key, iv, pt, first_block=first).hex() == c["ct"]
+
+
+def test_ref_samples_ecb_xts_gcm(orc):
+    s = golden("oracle_ref_samples.json")
+    for c in s["ecb"]:
+        assert sha256(orc.ecb_encrypt(H(c["key"]), rnd(c["pt_tag"], c["n"]))) == c["ct_sha256"], c
+    for c in s["xts"]:
+        rc, ct = orc.xts(H(c["keys"]), H(c["tweak"]), rnd(c["pt_tag"], c["n"]))
+        assert rc == 0 and sha256(ct) == c["ct_sha256"], c
+        rc, pt = orc.xts(H(c["keys"]), H(c["tweak"]), ct, encrypt=False)
+        assert pt == rnd(c["pt_tag"], c["n"])
+    for c in s["xts_sectors"]:
+        pt = rnd(c["pt_tag"], c["sector_bytes"] * c["sectors"])
+        rc, ct = orc.xts_sectors(H(c["keys"]), c["first_sector"], c["sector_bytes"], pt)
+        assert rc == 0 and sha256(ct) == c["ct_sha256"], c
+        rc, back = orc.xts_sectors(H(c["keys"]), c["first_sector"], c["sector_bytes"], ct, encrypt=False)
+        assert back == pt
+    for c in s["gcm"]:
+        out = orc.gcm_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]),
+                              rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+
+
+# ---------------------------------------------------------------- edge cases
+
+def test_edge_cases(orc):
+    key = rnd("edge-key", 16)
+    assert orc.ctr(key, bytes(12), b"") == b""
+    assert orc.ecb_encrypt(key, b"") == b""
+    rc, _ = orc.xts(rnd("edge-keys", 32), bytes(16), b"123456789012345")
+    assert rc == 1                                      # M_DATALENGTH_ERROR, micro_aes.c:1069
+    rc, out = orc.ecb_decrypt(key, bytes(20))
+    assert rc == 0x1D and out[16:] == bytes(4)          # micro_aes.c:679
+    # NULL tweak = sector 0 (micro_aes.c:1017-1021)
+    keys, pt = rnd("edge-keys", 32), rnd("edge-pt", 64)
+    assert orc.xts(keys, None, pt) == orc.xts(keys, bytes(16), pt)
+    # GHASH identity element is 0x80 00..00
+    x = rnd("edge-x", 16)
+    assert orc.gf128_mul(b"\x80" + bytes(15), x) == x
+    assert orc.gf128_mul(x, b"\x80" + bytes(15)) == x
+
+
+def test_splitmix_generator(orc):
+    # splitmix64(0) first output is the published constant e220a8397b1dcdaf
+    assert orc.splitmix(0, 0, 1) == (0xE220A8397B1DCDAF).to_bytes(8, "little")
+    a = orc.splitmix(7, 0, 64)
+    assert orc.splitmix(7, 16, 8) == a[128:192]
+
+
+# ---------------------------------------------------------------- live differential vs reference
+
+need_ref = pytest.mark.skipif(not Reference.available(128), reason="oracle/_ref not built")
+
+
+@need_ref
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_live_reference_differential(orc, bits):
+    ref = Reference(bits)
+    ks = bits // 8
+    for i, n in enumerate([0, 1, 16, 31, 32, 100, 1000, 4099, 70001]):
+        key, iv, data = rnd(f"lk{bits}{i}", ks), rnd(f"li{bits}{i}", 12), rnd(f"ld{bits}{i}", n)
+        assert orc.ctr(key, iv, data) == ref.ctr(key, iv, data)
+        assert orc.ecb_encrypt(key, data) == ref.ecb_encrypt(key, data)
+        assert orc.ecb_decrypt(key, data) == ref.ecb_decrypt(key, data)
+        aad = rnd(f"la{bits}{i}", (7 * i) % 50)
+        enc = ref.gcm_encrypt(key, iv, aad, data)
+        assert orc.gcm_encrypt(key, iv, aad, data) == enc
+        assert orc.gcm_decrypt(key, iv, aad, enc) == ref.gcm_decrypt(key, iv, aad, enc) == (0, data)
+        if bits != 192 and n >= 16:
+            keys, tw = rnd(f"lx{bits}{i}", 2 * ks), rnd(f"lt{bits}{i}", 16)
+            e = ref.xts(keys, tw, data)
+            assert orc.xts(keys, tw, data) == e
+            assert orc.xts(keys, tw, e[1], encrypt=False) == ref.xts(keys, tw, e[1], encrypt=False) == (0, data)
+
+
+@need_ref
+def test_live_reference_gcm_auth_failure(orc):
+    ref = Reference(128)
+    key, nonce, aad, pt = rnd("af-k", 16), rnd("af-n", 12), rnd("af-a", 20), rnd("af-p", 100)
+    enc = bytearray(ref.gcm_encrypt(key, nonce, aad, pt))
+    enc[5] ^= 0x40
+    assert ref.gcm_decrypt(key, nonce, aad, bytes(enc))[0] == 0x1A
+    assert orc.gcm_decrypt(key, nonce, aad, bytes(enc))[0] == 0x1A

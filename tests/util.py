@@ -1,0 +1,179 @@
+"""Shared helpers for the tests: deterministic inputs, the checker bindings, golden files."""
+import ctypes
+import hashlib
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_u8p = ctypes.c_char_p
+_sz = ctypes.c_size_t
+_u64 = ctypes.c_uint64
+_int = ctypes.c_int
+
+
+def rnd(tag, n):
+    """deterministic bytes: SHA-256 in counter mode over `tag` (same as golden/make_golden.py)"""
+    out = bytearray()
+    i = 0
+    while len(out) < n:
+        out += hashlib.sha256(f"{tag}:{i}".encode()).digest()
+        i += 1
+    return bytes(out[:n])
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def sha256(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+class Oracle:
+    """ctypes binding of oracle/liboracle.so (our C restatement of the reference path)"""
+
+    def __init__(self):
+        L = self.lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        L.oracle_encrypt_block.argtypes = [_int, _u8p, _u8p, _u8p]
+        L.oracle_decrypt_block.argtypes = [_int, _u8p, _u8p, _u8p]
+        L.oracle_key_expansion.argtypes = [_int, _u8p, _u8p]
+        L.oracle_ecb_encrypt.argtypes = [_int, _u8p, _u8p, _sz, _u8p]
+        L.oracle_ecb_decrypt.argtypes = [_int, _u8p, _u8p, _sz, _u8p]
+        L.oracle_ctr_crypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
+        L.oracle_ctr_crypt_at.argtypes = [_int, _u8p, _u8p, _u64, _u8p, _sz, _u8p]
+        for f in (L.oracle_xts_encrypt, L.oracle_xts_decrypt):
+            f.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
+        L.oracle_xts_sectors.argtypes = [_int, _u8p, _u64, _sz, _u8p, _sz, _u8p, _int]
+        L.oracle_gcm_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_gcm_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_ghash.argtypes = [_u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_gf128_mul.argtypes = [_u8p, _u8p]
+        L.oracle_xts_double.argtypes = [_u8p]
+        L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
+
+    @staticmethod
+    def _buf(n):
+        return ctypes.create_string_buffer(max(n, 1))
+
+    def encrypt_block(self, key, blk):
+        o = self._buf(16)
+        self.lib.oracle_encrypt_block(len(key) * 8, key, blk, o)
+        return o.raw[:16]
+
+    def decrypt_block(self, key, blk):
+        o = self._buf(16)
+        self.lib.oracle_decrypt_block(len(key) * 8, key, blk, o)
+        return o.raw[:16]
+
+    def key_expansion(self, key):
+        o = self._buf(240)
+        r = self.lib.oracle_key_expansion(len(key) * 8, key, o)
+        return o.raw[:16 * (r + 1)]
+
+    def ecb_encrypt(self, key, pt):
+        m = (len(pt) + 15) // 16 * 16
+        o = self._buf(m)
+        self.lib.oracle_ecb_encrypt(len(key) * 8, key, pt, len(pt), o)
+        return o.raw[:m]
+
+    def ecb_decrypt(self, key, ct):
+        o = self._buf(len(ct))
+        rc = self.lib.oracle_ecb_decrypt(len(key) * 8, key, ct, len(ct), o)
+        return rc, o.raw[:len(ct)]
+
+    def ctr(self, key, iv, data, first_block=0):
+        o = self._buf(len(data))
+        self.lib.oracle_ctr_crypt_at(len(key) * 8, key, iv, first_block, data, len(data), o)
+        return o.raw[:len(data)]
+
+    def xts(self, keys, tweak, data, encrypt=True):
+        o = self._buf(len(data))
+        f = self.lib.oracle_xts_encrypt if encrypt else self.lib.oracle_xts_decrypt
+        rc = f(len(keys) * 4, keys, tweak, data, len(data), o)
+        return rc, o.raw[:len(data)]
+
+    def xts_sectors(self, keys, first_sector, sector_bytes, data, encrypt=True):
+        o = self._buf(len(data))
+        rc = self.lib.oracle_xts_sectors(len(keys) * 4, keys, first_sector, sector_bytes, data,
+                                         len(data), o, 1 if encrypt else 0)
+        return rc, o.raw[:len(data)]
+
+    def gcm_encrypt(self, key, nonce, aad, pt):
+        o = self._buf(len(pt) + 16)
+        self.lib.oracle_gcm_encrypt(len(key) * 8, key, nonce, aad, len(aad), pt, len(pt), o)
+        return o.raw[:len(pt) + 16]
+
+    def gcm_decrypt(self, key, nonce, aad, ct_and_tag):
+        n = len(ct_and_tag) - 16
+        o = self._buf(n)
+        rc = self.lib.oracle_gcm_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
+        return rc, o.raw[:n]
+
+    def ghash(self, H, aad, ct):
+        o = self._buf(16)
+        self.lib.oracle_ghash(H, aad, len(aad), ct, len(ct), o)
+        return o.raw[:16]
+
+    def gf128_mul(self, x, y):
+        o = ctypes.create_string_buffer(y, 16)
+        self.lib.oracle_gf128_mul(x, o)
+        return o.raw[:16]
+
+    def splitmix(self, seed, first_word, nwords):
+        o = self._buf(8 * nwords)
+        self.lib.oracle_fill_splitmix64(seed, first_word, o, nwords)
+        return o.raw[:8 * nwords]
+
+
+class Reference:
+    """ctypes binding of oracle/_ref/libref<bits>.so: the UNMODIFIED micro_aes.c.  The key
+    length is baked into each library (AES___, micro_aes.h:17)."""
+
+    def __init__(self, bits, preset_counter=False):
+        name = f"libref{bits}{'pc' if preset_counter else ''}.so"
+        self.path = os.path.join(ROOT, "oracle", "_ref", name)
+        self.bits = bits
+        self.lib = ctypes.CDLL(self.path)
+        for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt"):
+            getattr(self.lib, f).restype = ctypes.c_char
+
+    @staticmethod
+    def available(bits=128, preset_counter=False):
+        return os.path.exists(os.path.join(ROOT, "oracle", "_ref",
+                                           f"libref{bits}{'pc' if preset_counter else ''}.so"))
+
+    def ecb_encrypt(self, key, pt):
+        m = (len(pt) + 15) // 16 * 16
+        o = ctypes.create_string_buffer(m + 16)
+        self.lib.AES_ECB_encrypt(key, pt, _sz(len(pt)), o)
+        return o.raw[:m]
+
+    def ecb_decrypt(self, key, ct):
+        o = ctypes.create_string_buffer(len(ct) + 16)
+        rc = self.lib.AES_ECB_decrypt(key, ct, _sz(len(ct)), o)
+        return ord(rc), o.raw[:len(ct)]
+
+    def ctr(self, key, iv, data):
+        o = ctypes.create_string_buffer(len(data) + 16)
+        self.lib.AES_CTR_encrypt(key, iv, data, _sz(len(data)), o)
+        return o.raw[:len(data)]
+
+    def xts(self, keys, tweak, data, encrypt=True):
+        o = ctypes.create_string_buffer(len(data) + 16)
+        f = self.lib.AES_XTS_encrypt if encrypt else self.lib.AES_XTS_decrypt
+        rc = f(keys, tweak, data, _sz(len(data)), o)
+        return ord(rc), o.raw[:len(data)]
+
+    def gcm_encrypt(self, key, nonce, aad, pt):
+        o = ctypes.create_string_buffer(len(pt) + 16)
+        self.lib.AES_GCM_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
+        return o.raw[:len(pt) + 16]
+
+    def gcm_decrypt(self, key, nonce, aad, ct_and_tag):
+        n = len(ct_and_tag) - 16
+        o = ctypes.create_string_buffer(n + 16)
+        rc = self.lib.AES_GCM_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
+        return ord(rc), o.raw[:n]
