@@ -1,0 +1,142 @@
+/*
+ * micro_aes.h -- the hot-path subset of the micro-AES C API, served by the
+ * B200 (sm_100a) engine in libuaes_b200.so.
+ *
+ * This header declares, with the reference's names, argument order and return
+ * codes, exactly the eight entry points the reference exports when only
+ * ECB, CTR (CTR_NA), XEX/XTS and GCM are enabled:
+ *
+ *     function            replaces (polfosol/micro-AES)
+ *     ------------------  ---------------------------------------------
+ *     AES_ECB_encrypt     micro_aes.h:173-176, micro_aes.c:636-653
+ *     AES_ECB_decrypt     micro_aes.h:178-181, micro_aes.c:663-680
+ *     AES_CTR_encrypt     micro_aes.h:256-260, micro_aes.c:962-976
+ *     AES_CTR_decrypt     micro_aes.h:262-266, micro_aes.c:986-990
+ *     AES_XTS_encrypt     micro_aes.h:239-243, micro_aes.c:1066-1074
+ *     AES_XTS_decrypt     micro_aes.h:245-249, micro_aes.c:1085-1093
+ *     AES_GCM_encrypt     micro_aes.h:294-300, micro_aes.c:1164-1179
+ *     AES_GCM_decrypt     micro_aes.h:302-308, micro_aes.c:1192-1212
+ *
+ * A program written against the reference keeps its `#include "micro_aes.h"`,
+ * drops micro_aes.c from its build and links one of
+ *     -lmicro_aes_128   -lmicro_aes_192   -lmicro_aes_256
+ * (the reference fixes the key size at compile time with AES___, micro_aes.h:17;
+ * each shim library is that choice).  All other modes of the reference are out
+ * of scope and their feature macros are 0 here, so code
+ * guarded by `#if CBC`, `#if CCM`, ... compiles away exactly as it does with
+ * the reference's own switches.
+ *
+ * Buffers may be ordinary host memory, pinned host memory, or CUDA device /
+ * managed memory (detected per call); device buffers are processed in place in
+ * HBM with no copies.  The `void` functions cannot report CUDA failures: query
+ * uaes_last_error() from uaes_b200.h.
+ *
+ * Plain ANSI C; no CUDA types appear in any signature.
+ */
+#ifndef MICRO_AES_H_
+#define MICRO_AES_H_
+
+#ifndef AES___
+#define AES___          128     /* 128, 192 or 256: must match the linked shim */
+#endif
+
+/* feature switches, named as in the reference (micro_aes.h:23-69) */
+#define BLOCKCIPHERS    1
+#define AEAD_MODES      1
+#define ECB             1
+#define CTR             1
+#define CTR_NA          1
+#define XEX             1
+#define XTS             1
+#define GCM             1
+#define CBC             0
+#define CFB             0
+#define OFB             0
+#define KWA             0
+#define FPE             0
+#define CMAC            0
+#define CCM             0
+#define EAX             0
+#define EAXP            0
+#define SIV             0
+#define GCM_SIV         0
+#define OCB             0
+#define POLY1305        0
+#define CTS             0
+#define MICRO_RJNDL     0
+
+#define AES_PADDING     0       /* ECB tail block is zero padded (micro_aes.h:78-80) */
+#define DECRYPTION      1
+#define PRESET_COUNTER  0       /* CTR takes a 12-byte IV, counter field starts at 1 */
+
+enum constant_parameters_of_modes
+{
+    CTR_START_VALUE = 1,        /* micro_aes.h:98  */
+    CTR_IV_LENGTH   = 12,       /* micro_aes.h:99  */
+    GCM_NONCE_LEN   = 12,       /* micro_aes.h:108 */
+    GCM_TAG_LEN     = 16,       /* micro_aes.h:109 */
+#if AES___ != 256 && AES___ != 192
+    AES_KEYLENGTH   = 16
+#else
+    AES_KEYLENGTH   = AES___ / 8
+#endif
+};
+
+#include <stddef.h>
+#include <limits.h>
+#if defined(__STDC_VERSION__) && __STDC_VERSION__ >= 199901L || defined(__cplusplus)
+#include <stdint.h>
+#elif CHAR_BIT == 8 && !defined(UINT8_MAX)
+typedef unsigned char uint8_t;
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ECB: output holds ceil16(ptextLen) bytes, the tail block is zero padded */
+void AES_ECB_encrypt(const uint8_t *key, const void *pntxt, const size_t ptextLen, void *crtxt);
+/* returns M_DECRYPTION_ERROR when crtxtLen is not a multiple of 16 (full blocks are
+ * still decrypted, tail bytes copied through) */
+char AES_ECB_decrypt(const uint8_t *key, const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* CTR: iv = CTR_IV_LENGTH bytes; counter block = iv || BE32(1), incremented as a
+ * 56-bit big-endian integer in bytes 9..15 (micro_aes.c:421-427) */
+void AES_CTR_encrypt(const uint8_t *key, const uint8_t *iv,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+void AES_CTR_decrypt(const uint8_t *key, const uint8_t *iv,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* XTS: keys = K1 || K2 (2 * AES_KEYLENGTH bytes), one data unit per call, tweak = 16
+ * bytes or NULL for sector 0; ciphertext stealing when the length is ragged;
+ * returns M_DATALENGTH_ERROR below 16 bytes */
+char AES_XTS_encrypt(const uint8_t *keys, const uint8_t *tweak,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+char AES_XTS_decrypt(const uint8_t *keys, const uint8_t *tweak,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* GCM: 12-byte nonce; crtxt holds ptextLen + GCM_TAG_LEN bytes (tag appended) */
+void AES_GCM_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+/* verifies the tag at crtxt + crtxtLen first; on mismatch returns
+ * M_AUTHENTICATION_ERROR and leaves pntxt untouched */
+char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* result codes, values as in the reference (micro_aes.h:469-476) */
+enum function_result_codes
+{
+    M_ENCRYPTION_ERROR     = 0x1E,
+    M_DECRYPTION_ERROR     = 0x1D,
+    M_AUTHENTICATION_ERROR = 0x1A,
+    M_DATALENGTH_ERROR     = 0x01,
+    M_RESULT_SUCCESS       = 0
+};
+
+#endif /* MICRO_AES_H_ */

@@ -1,0 +1,121 @@
+/*
+ * uaes_b200.h -- C ABI of libuaes_b200.so, the B200 (sm_100a) AES bulk engine.
+ *
+ * micro_aes.h is the drop-in contract (the reference's eight hot-path functions,
+ * key size fixed per shim library).  This header is what those shims call, plus
+ * the extensions a GPU deployment needs and the reference API cannot express
+ * (SURVEY.md section 8b):
+ *
+ *   - run-time key length (the reference bakes it in with AES___, micro_aes.h:17);
+ *   - an error latch, because AES_CTR_encrypt / AES_GCM_encrypt / AES_ECB_encrypt
+ *     return void (micro_aes.h:173,256,294) and cannot report a CUDA failure;
+ *   - counter-range CTR (resume / shard at keystream block k), the multi-GPU
+ *     partitioning of micro_aes.c:943-948;
+ *   - batched-sector XTS, i.e. the caller loop over AES_XTS_encrypt with
+ *     tweak = LE128(sector) (micro_aes.c:1017-1021) as ONE launch;
+ *   - stream selection and asynchronous completion for device-resident buffers.
+ *
+ * Every data pointer may be host memory (pageable or pinned) or CUDA device /
+ * managed memory; the library classifies it per call.  Device buffers are processed
+ * in HBM with no copies; host buffers are staged through pinned chunks with copies
+ * overlapped against the kernels.  key / iv / nonce / tweak / aad are always small
+ * HOST arrays, as in the reference.
+ *
+ * All functions return 0 (UAES_OK) or a micro_aes.h result code (1, 0x1A, 0x1D) or
+ * a negative UAES_E_* value; the failure is also latched for uaes_last_error().
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * UAES_E_NO_DEVICE.
+ *
+ * Plain C89; no CUDA or torch types in any signature (streams travel as void*).
+ */
+#ifndef UAES_B200_H_
+#define UAES_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef unsigned char      uaes_u8;
+typedef unsigned long long uaes_u64;
+
+enum uaes_status
+{
+    UAES_OK                 = 0,
+    UAES_DATALENGTH_ERROR   = 0x01,   /* = M_DATALENGTH_ERROR     (micro_aes.h:474) */
+    UAES_AUTH_ERROR         = 0x1A,   /* = M_AUTHENTICATION_ERROR (micro_aes.h:473) */
+    UAES_DECRYPTION_ERROR   = 0x1D,   /* = M_DECRYPTION_ERROR     (micro_aes.h:472) */
+    UAES_E_NO_DEVICE        = -1,     /* no CUDA device / driver: nothing was computed */
+    UAES_E_CUDA             = -2,     /* a CUDA runtime call or kernel failed */
+    UAES_E_BAD_ARGUMENT     = -3,     /* key size not 128/192/256, XTS-192, ragged sectors */
+    UAES_E_NO_MEMORY        = -4
+};
+
+/* ---- library state -------------------------------------------------------- */
+
+/* most recent failure on the calling thread's device context (0 = none) */
+int         uaes_last_error(void);
+const char *uaes_last_error_string(void);
+void        uaes_clear_error(void);
+
+/* number of usable CUDA devices (0 when there is no driver) */
+int  uaes_device_count(void);
+/* stream used by subsequent calls from this thread (a cudaStream_t passed as void*;
+ * NULL = the legacy default stream).  The device is the caller's current device. */
+void uaes_set_stream(void *stream);
+/* 0 (default): every call returns after the result is complete (reference semantics).
+ * 1: calls whose data buffers are all device memory only ENQUEUE work on the stream
+ *    set above and return; GCM decrypt still waits for the tag check. */
+void uaes_set_async(int enable);
+/* pinned host memory, for callers that want full-speed host<->device staging */
+void *uaes_host_alloc(size_t bytes);
+void  uaes_host_free(void *p);
+/* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
+uaes_u64 uaes_kernel_launches(void);
+
+/* ---- the hot path, run-time key length ------------------------------------- */
+/* keybits = 128, 192 or 256 everywhere (XTS: 128 or 256, keys = K1 || K2). */
+
+/* micro_aes.c:636-653; out holds ceil16(len) */
+int uaes_ecb_encrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out);
+/* micro_aes.c:663-680; UAES_DECRYPTION_ERROR when len % 16 (blocks still decrypted) */
+int uaes_ecb_decrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out);
+
+/* micro_aes.c:962-990; iv = 12 bytes, counter block k = iv || BE32(1) plus k as a 56-bit
+ * big-endian add over bytes 9..15 (micro_aes.c:421-427) */
+int uaes_ctr_crypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
+                   const void *in, size_t len, void *out);
+/* the same keystream starting at block `first_block`: bytes [16*first_block, +len) of the
+ * stream AES_CTR_encrypt would produce.  This is how a buffer shards over GPUs. */
+int uaes_ctr_crypt_range(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
+                         uaes_u64 first_block, const void *in, size_t len, void *out);
+
+/* micro_aes.c:1066-1093: one data unit, tweak = 16 bytes or NULL (sector 0), stealing */
+int uaes_xts_encrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak,
+                     const void *in, size_t len, void *out);
+int uaes_xts_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak,
+                     const void *in, size_t len, void *out);
+/* len / sector_bytes consecutive data units, unit j tweaked with LE128(first_sector + j);
+ * sector_bytes must be a multiple of 16, len a multiple of sector_bytes.  Equals a loop of
+ * AES_XTS_encrypt / AES_XTS_decrypt calls over the sectors. */
+int uaes_xts_sectors(int keybits, const uaes_u8 *keys, uaes_u64 first_sector,
+                     size_t sector_bytes, const void *in, size_t len, void *out, int encrypt);
+
+/* micro_aes.c:1164-1179; nonce = 12 bytes; out holds len + 16 (tag appended) */
+int uaes_gcm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+/* micro_aes.c:1192-1212; in holds len + 16; UAES_AUTH_ERROR leaves out untouched */
+int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
+/* ---- synthetic data (bench / tests) ----------------------------------------- */
+/* 64-bit word w of dst (little-endian) = splitmix64(seed + first_word + w); dst is DEVICE memory */
+int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords);
+/* XOR-fold of a DEVICE buffer of nwords 64-bit words into one word written to *result (host) */
+int uaes_xor_fold64(const void *src, size_t nwords, uaes_u64 *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAES_B200_H_ */

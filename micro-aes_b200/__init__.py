@@ -1,0 +1,241 @@
+"""micro-aes_b200: Python mirror of the micro-AES hot-path API over the B200 engine.
+
+The product is the C-ABI shared library `lib/libuaes_b200.so` (CUDA kernels for sm_100a plus an
+ANSI-C host side) and the per-key-size shims `lib/libmicro_aes_{128,192,256}.so` that export the
+reference's own symbol names (include/micro_aes.h).  This package is only a thin ctypes binding
+used by the tests and bench.py; it mirrors the reference interface (same function names,
+argument order and return codes, micro_aes.h:173-308) and adds the extensions of
+include/uaes_b200.h (device pointers, counter ranges, sector batches).
+
+There is no CPU fallback: importing works anywhere (so the CPU test-suite can check the ABI),
+but every compute call needs a CUDA device and raises UaesError otherwise.
+
+The directory name contains a hyphen, so import it with
+    importlib.import_module("micro-aes_b200")
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(_HERE, "lib")
+
+M_RESULT_SUCCESS = 0
+M_DATALENGTH_ERROR = 0x01
+M_AUTHENTICATION_ERROR = 0x1A
+M_DECRYPTION_ERROR = 0x1D
+M_ENCRYPTION_ERROR = 0x1E
+
+_vp, _sz, _u64, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int
+_cp = ctypes.c_char_p
+
+# every symbol include/uaes_b200.h declares: name -> (restype, argtypes)
+UAES_ABI = {
+    "uaes_last_error": (_int, []),
+    "uaes_last_error_string": (_cp, []),
+    "uaes_clear_error": (None, []),
+    "uaes_device_count": (_int, []),
+    "uaes_set_stream": (None, [_vp]),
+    "uaes_set_async": (None, [_int]),
+    "uaes_host_alloc": (_vp, [_sz]),
+    "uaes_host_free": (None, [_vp]),
+    "uaes_kernel_launches": (_u64, []),
+    "uaes_ecb_encrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
+    "uaes_ecb_decrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
+    "uaes_ctr_crypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
+    "uaes_ctr_crypt_range": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp]),
+    "uaes_xts_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
+    "uaes_xts_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
+    "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
+    "uaes_gcm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_gcm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_fill_splitmix64": (_int, [_u64, _u64, _vp, _sz]),
+    "uaes_xor_fold64": (_int, [_vp, _sz, ctypes.POINTER(_u64)]),
+}
+
+# the eight reference symbols of include/micro_aes.h: name -> (restype, argtypes)
+MICRO_AES_ABI = {
+    "AES_ECB_encrypt": (None, [_cp, _vp, _sz, _vp]),
+    "AES_ECB_decrypt": (ctypes.c_char, [_cp, _vp, _sz, _vp]),
+    "AES_CTR_encrypt": (None, [_cp, _cp, _vp, _sz, _vp]),
+    "AES_CTR_decrypt": (None, [_cp, _cp, _vp, _sz, _vp]),
+    "AES_XTS_encrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
+    "AES_XTS_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
+    "AES_GCM_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_GCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+}
+
+
+class UaesError(RuntimeError):
+    pass
+
+
+def _bind(lib, table):
+    for name, (res, args) in table.items():
+        f = getattr(lib, name)          # AttributeError if the library does not export it
+        f.restype, f.argtypes = res, args
+    return lib
+
+
+_core = None
+_shims = {}
+
+
+def core():
+    """libuaes_b200.so, bound.  Raises UaesError if it was not built (run __graft_entry__.build())."""
+    global _core
+    if _core is None:
+        path = os.path.join(LIBDIR, "libuaes_b200.so")
+        if not os.path.exists(path):
+            raise UaesError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _core = _bind(ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL), UAES_ABI)
+    return _core
+
+
+def shim(bits):
+    """libmicro_aes_<bits>.so: the reference's symbol names for one key size."""
+    if bits not in _shims:
+        core()
+        _shims[bits] = _bind(ctypes.CDLL(os.path.join(LIBDIR, f"libmicro_aes_{bits}.so")), MICRO_AES_ABI)
+    return _shims[bits]
+
+
+def _ptr(x):
+    """bytes / bytearray / ctypes buffer / int device pointer / torch tensor -> address"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, (bytes, bytearray)):
+        return ctypes.cast((ctypes.c_char * len(x)).from_buffer(x) if isinstance(x, bytearray)
+                           else ctypes.c_char_p(x), ctypes.c_void_p).value
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return ctypes.addressof(x)
+
+
+def check(rc):
+    """raise on engine failures (negative codes); pass reference result codes through"""
+    if rc < 0:
+        raise UaesError(f"uaes error {rc}: {core().uaes_last_error_string().decode()}")
+    return rc
+
+
+class MicroAES:
+    """The reference API for one key size, on host `bytes` (the way main.c uses it).
+
+    Method names, argument order and return values follow micro_aes.h; every call goes through
+    the reference-named symbol of libmicro_aes_<bits>.so, i.e. through the same entry points a C
+    program linked against the shim would use."""
+
+    def __init__(self, bits=128):
+        self.bits = bits
+        self.lib = shim(bits)
+
+    def _after(self):
+        e = core().uaes_last_error()
+        if e < 0:
+            msg = core().uaes_last_error_string().decode()
+            core().uaes_clear_error()
+            raise UaesError(f"uaes error {e}: {msg}")
+
+    def AES_ECB_encrypt(self, key, pntxt):
+        out = ctypes.create_string_buffer(max((len(pntxt) + 15) // 16 * 16, 1))
+        self.lib.AES_ECB_encrypt(key, pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:(len(pntxt) + 15) // 16 * 16]
+
+    def AES_ECB_decrypt(self, key, crtxt):
+        out = ctypes.create_string_buffer(max(len(crtxt), 1))
+        rc = ord(self.lib.AES_ECB_decrypt(key, crtxt, len(crtxt), out))
+        self._after()
+        return rc, out.raw[:len(crtxt)]
+
+    def AES_CTR_encrypt(self, key, iv, pntxt):
+        out = ctypes.create_string_buffer(max(len(pntxt), 1))
+        self.lib.AES_CTR_encrypt(key, iv, pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:len(pntxt)]
+
+    def AES_CTR_decrypt(self, key, iv, crtxt):
+        out = ctypes.create_string_buffer(max(len(crtxt), 1))
+        self.lib.AES_CTR_decrypt(key, iv, crtxt, len(crtxt), out)
+        self._after()
+        return out.raw[:len(crtxt)]
+
+    def AES_XTS_encrypt(self, keys, tweak, pntxt):
+        out = ctypes.create_string_buffer(max(len(pntxt), 1))
+        rc = ord(self.lib.AES_XTS_encrypt(keys, tweak, pntxt, len(pntxt), out))
+        self._after()
+        return rc, out.raw[:len(pntxt)]
+
+    def AES_XTS_decrypt(self, keys, tweak, crtxt):
+        out = ctypes.create_string_buffer(max(len(crtxt), 1))
+        rc = ord(self.lib.AES_XTS_decrypt(keys, tweak, crtxt, len(crtxt), out))
+        self._after()
+        return rc, out.raw[:len(crtxt)]
+
+    def AES_GCM_encrypt(self, key, nonce, aData, pntxt):
+        out = ctypes.create_string_buffer(len(pntxt) + 16)
+        self.lib.AES_GCM_encrypt(key, nonce, aData, len(aData), pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:len(pntxt) + 16]
+
+    def AES_GCM_decrypt(self, key, nonce, aData, crtxt_and_tag):
+        n = len(crtxt_and_tag) - 16
+        out = ctypes.create_string_buffer(b"\xcc" * max(n, 1), max(n, 1))
+        rc = ord(self.lib.AES_GCM_decrypt(key, nonce, aData, len(aData), crtxt_and_tag, n, out))
+        self._after()
+        return rc, out.raw[:n]
+
+
+# ---- extensions of include/uaes_b200.h on raw pointers (device or host) ----
+
+def ctr_crypt_range(bits, key, iv, first_block, src, nbytes, dst):
+    return check(core().uaes_ctr_crypt_range(bits, key, iv, first_block, _ptr(src), nbytes, _ptr(dst)))
+
+
+def ecb(bits, key, src, nbytes, dst, encrypt=True):
+    f = core().uaes_ecb_encrypt if encrypt else core().uaes_ecb_decrypt
+    return check(f(bits, key, _ptr(src), nbytes, _ptr(dst)))
+
+
+def xts_unit(bits, keys, tweak, src, nbytes, dst, encrypt=True):
+    f = core().uaes_xts_encrypt if encrypt else core().uaes_xts_decrypt
+    return check(f(bits, keys, tweak, _ptr(src), nbytes, _ptr(dst)))
+
+
+def xts_sectors(bits, keys, first_sector, sector_bytes, src, nbytes, dst, encrypt=True):
+    return check(core().uaes_xts_sectors(bits, keys, first_sector, sector_bytes, _ptr(src), nbytes,
+                                         _ptr(dst), 1 if encrypt else 0))
+
+
+def gcm_encrypt(bits, key, nonce, aad, src, nbytes, dst):
+    return check(core().uaes_gcm_encrypt(bits, key, nonce, _ptr(aad), len(aad) if aad else 0,
+                                         _ptr(src), nbytes, _ptr(dst)))
+
+
+def gcm_decrypt(bits, key, nonce, aad, src, nbytes, dst):
+    return check(core().uaes_gcm_decrypt(bits, key, nonce, _ptr(aad), len(aad) if aad else 0,
+                                         _ptr(src), nbytes, _ptr(dst)))
+
+
+def fill_splitmix64(seed, first_word, dst, nwords):
+    return check(core().uaes_fill_splitmix64(seed, first_word, _ptr(dst), nwords))
+
+
+def xor_fold64(src, nwords):
+    r = _u64(0)
+    check(core().uaes_xor_fold64(_ptr(src), nwords, ctypes.byref(r)))
+    return r.value
+
+
+def set_stream(stream_handle):
+    core().uaes_set_stream(stream_handle)
+
+
+def set_async(flag):
+    core().uaes_set_async(1 if flag else 0)
+
+
+def kernel_launches():
+    return core().uaes_kernel_launches()

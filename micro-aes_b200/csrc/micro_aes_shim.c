@@ -1,0 +1,71 @@
+/*
+ * micro_aes_shim.c -- the reference's symbol names on top of libuaes_b200.so.  ANSI C.
+ *
+ * Compiled once per key size (-DAES___=128 / 192 / 256) into libmicro_aes_<bits>.so, mirroring
+ * the reference's compile-time choice (micro_aes.h:17).  A program built against the reference
+ * keeps its source and its `#include "micro_aes.h"`, and links one of these libraries in place
+ * of micro_aes.c.  Each function forwards to the run-time-key-length entry point of
+ * uaes_b200.h; return codes are the reference's (micro_aes.h:469-476).  The void functions
+ * latch failures for uaes_last_error().
+ */
+#include "../../include/micro_aes.h"
+#include "../../include/uaes_b200.h"
+
+#define BITS (AES_KEYLENGTH * 8)
+
+/* a failure below zero is a device/runtime problem, not a reference result code: report it as the
+ * closest reference code so that callers which test `!= 0` still see an error */
+static char code(int rc, char fallback)
+{
+    if (rc >= 0) return (char)rc;
+    return fallback;
+}
+
+void AES_ECB_encrypt(const uint8_t *key, const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_ecb_encrypt(BITS, key, pntxt, ptextLen, crtxt);
+}
+
+char AES_ECB_decrypt(const uint8_t *key, const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_ecb_decrypt(BITS, key, crtxt, crtxtLen, pntxt), M_DECRYPTION_ERROR);
+}
+
+void AES_CTR_encrypt(const uint8_t *key, const uint8_t *iv,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_ctr_crypt(BITS, key, iv, pntxt, ptextLen, crtxt);
+}
+
+void AES_CTR_decrypt(const uint8_t *key, const uint8_t *iv,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    uaes_ctr_crypt(BITS, key, iv, crtxt, crtxtLen, pntxt);     /* micro_aes.c:986-990 */
+}
+
+char AES_XTS_encrypt(const uint8_t *keys, const uint8_t *tweak,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    return code(uaes_xts_encrypt(BITS, keys, tweak, pntxt, ptextLen, crtxt), M_ENCRYPTION_ERROR);
+}
+
+char AES_XTS_decrypt(const uint8_t *keys, const uint8_t *tweak,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_xts_decrypt(BITS, keys, tweak, crtxt, crtxtLen, pntxt), M_DECRYPTION_ERROR);
+}
+
+void AES_GCM_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_gcm_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+}
+
+char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_gcm_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+                M_DECRYPTION_ERROR);
+}

@@ -1,0 +1,418 @@
+// uaes_gcm.cuh -- GCM kernels (included by uaes_kernels.cu).
+//
+// Restates AES_GCM_encrypt / gHash / xMac / mulGF128 (micro_aes.c:1164-1179, 1127-1137,
+// 551-570, 476-493).  The reference makes two serial passes (CTR, then a bit-serial GHASH chain
+// G <- H*(G ^ X_i)).  Here ONE pass reads the plaintext once and writes the ciphertext once:
+//
+//   GHASH(X_0..X_{n-1}) = sum_i X_i * H^(n-i)  is split into chunks of CB = 32 * 2^kr blocks,
+//   aligned to the END of the message (a short first chunk is a full one with leading zeros).
+//   Inside a chunk lane l of the warp owns blocks = l (mod 32) in counter space and runs
+//   Horner with the fixed multiplier C = H^32:   y_l <- y_l * C ^ X.
+//   The multiply-by-constant is a byte-serial table walk (Shoup): 16 lookups of M[b] = b(x)*C
+//   (256 x 16 B, replicated 8x so the 8 lanes of a quarter-warp hit 8 different bank groups)
+//   and 15 lookups of the key-independent reduction R[d] = d(x)*x^128 (lane replicated).
+//   At the end of a chunk lane l scales y_l by H^(distance to the chunk end) in 1..32 (one
+//   generic product per chunk) and the warp XOR-reduces by shuffle into one 16-byte partial.
+//   A last small kernel folds the partials pairwise with P = H^CB, P^2, P^4, ... , absorbs the
+//   ragged tail block and the length block and writes  tag = E_K(J0) ^ GHASH.
+//
+//   The AAD enters as the initial GHASH state, which is simply XORed into block 0.
+#pragma once
+
+namespace uaes {
+
+struct GcmWork {
+    uint4 H;             // E_K(0), as the four memory words of the block
+    uint4 EJ0;           // E_K(J0)
+    uint4 C32;           // H^32
+    uint4 aad_state;     // GHASH state after the (zero padded) AAD
+    uint4 lanepow[32];   // lanepow[e-1] = H^e
+    uint4 partials[1];   // NC entries, stored in reverse chunk order
+};
+
+__device__ __forceinline__ Gf gf_load(const uint4 &v) { return gf_from_words(v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ uint4 gf_store(Gf g)
+{
+    uint4 v;
+    gf_to_words(g, v.x, v.y, v.z, v.w);
+    return v;
+}
+
+__device__ inline uint4 load_block_bytes(const uint8_t *p, uint32_t n)   // zero padded, n <= 16
+{
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < n; ++i) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---------------------------------------------------------------- per-call constants
+
+struct GcmSetupArgs {
+    uaes_keysched ks;
+    uint32_t j0[4];              // nonce || 00000001 as words (micro_aes.c:1150-1151)
+    const uint8_t *aad;
+    uint64_t aadlen;
+    GcmWork *work;
+};
+
+// one warp: H and E_K(J0) on two lanes, the squarings H^2..H^32 on lane 0, then lane l
+// assembles H^(l+1) from its binary digits; lane 0 finally absorbs the AAD (xMac over the AAD,
+// micro_aes.c:1134)
+__global__ void gcm_setup_kernel(const __grid_constant__ GcmSetupArgs a)
+{
+    __shared__ Gf sq[6];                                      // H^(2^i)
+    const uint32_t lane = threadIdx.x;
+    if (lane < 2) {
+        uint32_t s[4] = {0, 0, 0, 0};
+        if (lane == 1) { s[0] = a.j0[0]; s[1] = a.j0[1]; s[2] = a.j0[2]; s[3] = a.j0[3]; }
+        small_encrypt(a.ks.w, a.ks.rounds, s);
+        const uint4 v = make_uint4(s[0], s[1], s[2], s[3]);
+        if (lane == 0) { a.work->H = v; sq[0] = gf_load(v); } else a.work->EJ0 = v;
+    }
+    __syncwarp();
+    if (lane == 0)
+        for (int i = 1; i < 6; ++i) sq[i] = gf_mul(sq[i - 1], sq[i - 1]);
+    __syncwarp();
+    {
+        const uint32_t e = lane + 1;                         // H^e
+        Gf p{0x8000000000000000ull, 0};                      // the field's 1
+        for (int i = 0; i < 6; ++i)
+            if (e >> i & 1) p = gf_mul(p, sq[i]);
+        a.work->lanepow[lane] = gf_store(p);
+        if (e == 32) a.work->C32 = gf_store(p);
+    }
+    if (lane == 0) {
+        Gf g{0, 0};
+        const Gf H = sq[0];
+        for (uint64_t off = 0; off < a.aadlen; off += 16) {
+            const uint64_t left = a.aadlen - off;
+            const Gf x = gf_load(load_block_bytes(a.aad + off, left < 16 ? (uint32_t)left : 16));
+            g.hi ^= x.hi; g.lo ^= x.lo;
+            g = gf_mul(H, g);
+        }
+        a.work->aad_state = gf_store(g);
+    }
+}
+
+// ---------------------------------------------------------------- the fused bulk pass
+
+struct GcmBulkArgs {
+    uaes_keysched ks;
+    uint32_t w0, w1, b8;
+    uint64_t v0;                 // counter of data block 0 = J0 + 1
+    const uint4 *in;
+    uint4 *out;
+    uint64_t nblocks;            // FULL blocks only; the ragged tail is done by the finish kernel
+    uint32_t kr;                 // chunk = 32 << kr blocks
+    uint64_t nchunks;
+    GcmWork *work;
+};
+
+constexpr uint32_t kGhashRegion = 32768;                 // M table and R table, 32 KiB each
+
+// y <- y * C, y as four memory-order words; mb = M base | (lane&7)*16, rb = R base | lane*4
+__device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t rb, uint32_t &y0, uint32_t &y1,
+                                                uint32_t &y2, uint32_t &y3)
+{
+    auto m_at = [&](uint32_t word, int byte) -> uint4 {
+        const int sh = 8 * byte - 7;                         // ((word >> 8*byte) & 0xff) << 7
+        const uint32_t idx = (sh >= 0 ? word >> sh : word << -sh) & 0x7f80u;
+        uint4 v;
+        asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(idx | mb));
+        return v;
+    };
+    uint4 acc = m_at(y3, 3);                                 // byte 15 first
+    const uint32_t yw[4] = {y0, y1, y2, y3};
+#pragma unroll
+    for (int i = 14; i >= 0; --i) {
+        uint32_t r;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(((acc.w >> 17) & 0x7f80u) | rb));
+        const uint4 m = m_at(yw[i >> 2], i & 3);
+        // acc <- acc * x^8 (bytes move one place up), reduce the byte that fell off, add M[z_i]
+        acc.w = __byte_perm(acc.z, acc.w, 0x6543) ^ m.w;
+        acc.z = __byte_perm(acc.y, acc.z, 0x6543) ^ m.z;
+        acc.y = __byte_perm(acc.x, acc.y, 0x6543) ^ m.y;
+        acc.x = (acc.x << 8) ^ r ^ m.x;
+    }
+    y0 = acc.x; y1 = acc.y; y2 = acc.z; y3 = acc.w;
+}
+
+template <int NR, bool HASH_ONLY>
+__global__ void __launch_bounds__(kThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    // ---- shared memory map: AES tables 64 KiB aligned, GHASH tables in the 32 KiB-aligned gaps
+    const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
+    const uint32_t tbase = align_table_base(dyn);
+    uint32_t mbase, rbase;
+    if (tbase >= win0 + kGhashRegion) { mbase = tbase - kGhashRegion; rbase = tbase + kEncTableBytes; }
+    else                              { mbase = tbase + kEncTableBytes; rbase = mbase + kGhashRegion; }
+    if (rbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1) __trap();
+
+    if (!HASH_ONLY) init_enc_tables(tbase);
+    {
+        // M[b] = b(x) * C: bit 7 of b is the coefficient of x^0 (micro_aes.c:476-493 bit order)
+        const Gf C = gf_load(a.work->C32);
+        if (threadIdx.x < 256) {
+            Gf acc{0, 0}, t = C;
+            for (int j = 0; j < 8; ++j) {
+                if (threadIdx.x & (0x80u >> j)) { acc.hi ^= t.hi; acc.lo ^= t.lo; }
+                t = gf_mulx(t);
+            }
+            const uint4 v = gf_store(acc);
+            for (int rep = 0; rep < 8; ++rep) {
+                const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+        for (uint32_t w = threadIdx.x; w < 256u * 32u; w += blockDim.x)
+            sts32(rbase + w * 4, c_ghash_reduce.v[w >> 5]);
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4), rb = rbase | (lane << 2);
+    asm volatile("" : "+r"(lb), "+r"(mb), "+r"(rb)::"memory");
+
+    const uint32_t *rk = a.ks.w;
+    const uint64_t CB = 32ull << a.kr;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint4 aad_state = a.work->aad_state;
+
+    uint64_t cur_group = ~0ull;
+    uint32_t s3 = 0, K0 = 0, D0 = 0, D1 = 0, D2 = 0, D3 = 0;
+
+    for (uint64_t c = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); c < a.nchunks; c += nwarps) {
+        // chunk c ends (NC-1-c) chunks before the end of the message
+        const uint64_t b1 = a.nblocks - (a.nchunks - 1 - c) * CB;
+        const uint64_t b0 = b1 > CB ? b1 - CB : 0;
+        const uint64_t vfirst = (a.v0 + b0) & ~31ull, vend = a.v0 + b1;      // counter space rows
+        uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+        uint64_t klast = 0;
+        bool any = false;
+
+        auto valid_k = [&](uint64_t vrow, uint64_t &k) -> bool {
+            const uint64_t v = vrow + lane;
+            k = v - a.v0;
+            return v >= a.v0 + b0 && v < vend;
+        };
+        uint64_t kk;
+        uint4 cur = valid_k(vfirst, kk) ? ld_stream(a.in + kk) : make_uint4(0, 0, 0, 0);
+        for (uint64_t vrow = vfirst; vrow < vend; vrow += 32) {
+            uint64_t k, kn;
+            const bool ok = valid_k(vrow, k);
+            const uint4 nxt = (vrow + 32 < vend && valid_k(vrow + 32, kn)) ? ld_stream(a.in + kn) : make_uint4(0, 0, 0, 0);
+            uint32_t o0 = cur.x, o1 = cur.y, o2 = cur.z, o3 = cur.w;
+            if (!HASH_ONLY) {
+                if ((vrow >> 8) != cur_group) {              // same hoisting as ctr_kernel
+                    cur_group = vrow >> 8;
+                    uint32_t w2, w3;
+                    ctr_words(a.b8, (cur_group << 8) & kMask56, w2, w3);
+                    const uint32_t s0 = a.w0 ^ rk[0], s1 = a.w1 ^ rk[1], s2 = w2 ^ rk[2];
+                    s3 = w3 ^ rk[3];
+                    K0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ rk[4];
+                    const uint32_t C1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<2, kOffT2>(lb, s3) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
+                    const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
+                    const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
+                    D0 = lut<1, kOffT1>(lb, C1) ^ lut<2, kOffT2>(lb, C2) ^ lut<3, kOffT3>(lb, C3) ^ rk[8];
+                    D1 = lut<0, kOffT0>(lb, C1) ^ lut<1, kOffT1>(lb, C2) ^ lut<2, kOffT2>(lb, C3) ^ rk[9];
+                    D2 = lut<0, kOffT0>(lb, C2) ^ lut<1, kOffT1>(lb, C3) ^ lut<3, kOffT3>(lb, C1) ^ rk[10];
+                    D3 = lut<0, kOffT0>(lb, C3) ^ lut<2, kOffT2>(lb, C1) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+                }
+                const uint32_t c0 = K0 ^ lut<3, kOffT3>(lb, s3 ^ ((((uint32_t)vrow & 255u) + lane) << 24));
+                uint32_t t0 = D0 ^ lut<0, kOffT0>(lb, c0), t1 = D1 ^ lut<3, kOffT3>(lb, c0);
+                uint32_t t2 = D2 ^ lut<2, kOffT2>(lb, c0), t3 = D3 ^ lut<1, kOffT1>(lb, c0);
+                enc_finish<NR, 3>(lb, t0, t1, t2, t3, rk, o0, o1, o2, o3);
+                o0 = t0; o1 = t1; o2 = t2; o3 = t3;
+                if (ok) st_stream(a.out + k, make_uint4(o0, o1, o2, o3));
+            }
+            if (ok) {
+                if (k == 0) { o0 ^= aad_state.x; o1 ^= aad_state.y; o2 ^= aad_state.z; o3 ^= aad_state.w; }
+                if (any) ghash_mul_const(mb, rb, y0, y1, y2, y3);
+                y0 ^= o0; y1 ^= o1; y2 ^= o2; y3 ^= o3;
+                any = true;
+                klast = k;
+            }
+            cur = nxt;
+        }
+
+        // lane l holds sum_j X_(l+32j) * C^(J-j); scale by H^(b1 - klast) and reduce over the warp
+        Gf z{0, 0};
+        if (any) z = gf_mul(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]), gf_from_words(y0, y1, y2, y3));
+        for (int o = 16; o; o >>= 1) {
+            z.hi ^= __shfl_xor_sync(0xffffffffu, z.hi, o);
+            z.lo ^= __shfl_xor_sync(0xffffffffu, z.lo, o);
+        }
+        if (lane == 0) a.work->partials[a.nchunks - 1 - c] = gf_store(z);
+    }
+}
+
+// ---------------------------------------------------------------- fold, tail, tag
+
+struct GcmFinishArgs {
+    uaes_keysched ks;
+    uint32_t w0, w1, b8;
+    uint64_t v0;
+    const uint8_t *in;
+    uint8_t *out;
+    uint64_t len, aadlen;
+    uint32_t kr;
+    uint64_t nchunks;
+    int hash_only;
+    uint8_t *tag_out;            // 16 bytes, any alignment
+    GcmWork *work;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gcm_finish_kernel(const __grid_constant__ GcmFinishArgs a)
+{
+    uint4 *slot = a.work->partials;
+    // P = H^CB = (H^32)^(2^kr); every thread squares along (no broadcast needed)
+    Gf P = gf_load(a.work->C32);
+    for (uint32_t i = 0; i < a.kr; ++i) P = gf_mul(P, P);
+
+    // slot[i] = partial of the i-th chunk counted from the end; total = sum_i slot[i] * P^i
+    for (uint64_t n = a.nchunks; n > 1; n = (n + 1) / 2) {
+        const uint64_t half = (n + 1) / 2;
+        for (uint64_t base = 0; base < half; base += kThreads) {
+            const uint64_t m = base + threadIdx.x;
+            Gf f{0, 0};
+            if (m < half) {
+                f = gf_load(slot[2 * m]);
+                if (2 * m + 1 < n) {
+                    const Gf g = gf_mul(P, gf_load(slot[2 * m + 1]));
+                    f.hi ^= g.hi; f.lo ^= g.lo;
+                }
+            }
+            __syncthreads();
+            if (m < half) slot[m] = gf_store(f);
+            __syncthreads();
+        }
+        P = gf_mul(P, P);
+    }
+
+    if (threadIdx.x != 0) return;
+    const Gf H = gf_load(a.work->H);
+    Gf S = a.nchunks ? gf_load(slot[0]) : gf_load(a.work->aad_state);
+
+    const uint64_t nfull = a.len / 16;
+    const uint32_t tail = (uint32_t)(a.len % 16);
+    if (tail) {
+        uint4 ct = load_block_bytes(a.in + 16 * nfull, tail);
+        if (!a.hash_only) {                                   // mixThenXor, micro_aes.c:949
+            uint32_t w2, w3;
+            ctr_words(a.b8, (a.v0 + nfull) & kMask56, w2, w3);
+            uint32_t s[4] = {a.w0, a.w1, w2, w3};
+            small_encrypt(a.ks.w, a.ks.rounds, s);
+            const uint32_t keep[4] = {tail >= 4 ? 0xffffffffu : (1u << (8 * tail)) - 1,
+                                      tail >= 8 ? 0xffffffffu : tail > 4 ? (1u << (8 * (tail - 4))) - 1 : 0,
+                                      tail >= 12 ? 0xffffffffu : tail > 8 ? (1u << (8 * (tail - 8))) - 1 : 0,
+                                      tail > 12 ? (1u << (8 * (tail - 12))) - 1 : 0};
+            ct.x = (ct.x ^ s[0]) & keep[0]; ct.y = (ct.y ^ s[1]) & keep[1];
+            ct.z = (ct.z ^ s[2]) & keep[2]; ct.w = (ct.w ^ s[3]) & keep[3];
+            const uint32_t cw[4] = {ct.x, ct.y, ct.z, ct.w};
+            for (uint32_t i = 0; i < tail; ++i) a.out[16 * nfull + i] = (uint8_t)(cw[i >> 2] >> (8 * (i & 3)));
+        }
+        const Gf x = gf_load(ct);
+        S.hi ^= x.hi; S.lo ^= x.lo;
+        S = gf_mul(H, S);
+    }
+    // length block: BE64(8*aadlen) || BE64(8*len)   (micro_aes.c:1130-1132)
+    S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
+    S = gf_mul(H, S);
+    const uint4 ej0 = a.work->EJ0;
+    uint4 tag = gf_store(S);
+    tag.x ^= ej0.x; tag.y ^= ej0.y; tag.z ^= ej0.z; tag.w ^= ej0.w;
+    const uint32_t tw[4] = {tag.x, tag.y, tag.z, tag.w};
+    for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
+}
+
+template <int NR, bool HASH_ONLY>
+static cudaError_t launch_gcm_bulk_nr(const GcmBulkArgs &a, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(gcm_bulk_kernel<NR, HASH_ONLY>);
+    if (e != cudaSuccess) return e;
+    gcm_bulk_kernel<NR, HASH_ONLY><<<grid_for(a.nchunks), kThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// rows per chunk = 2^kr: big enough to amortise the per-chunk scaling (one generic product),
+// small enough that every warp of the grid gets at least two chunks
+static uint32_t gcm_pick_kr(uint64_t nblocks)
+{
+    const uint64_t rows = (nblocks + 31) / 32;
+    const uint64_t warps = (uint64_t)sm_count() * kWarpsPerCta;
+    uint32_t kr = 0;
+    while (kr < 8 && (rows >> (kr + 1)) >= 2 * warps) ++kr;
+    return kr;
+}
+
+}  // namespace uaes
+
+extern "C" size_t uaes_gcm_work_bytes(u64 len)
+{
+    using namespace uaes;
+    const uint64_t nblocks = len / 16;
+    const uint32_t kr = gcm_pick_kr(nblocks);
+    const uint64_t CB = 32ull << kr;
+    const uint64_t nchunks = (nblocks + CB - 1) / CB;
+    return sizeof(GcmWork) + (size_t)nchunks * sizeof(uint4);
+}
+
+extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+                               u64 aadlen, const void *in, void *out, u64 len, int hash_only,
+                               void *tag_out, void *work, void *stream)
+{
+    using namespace uaes;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t nblocks = len / 16;
+    const uint32_t kr = gcm_pick_kr(nblocks);
+    const uint64_t CB = 32ull << kr;
+    const uint64_t nchunks = (nblocks + CB - 1) / CB;
+
+    uint32_t j0[4];
+    for (int c = 0; c < 3; ++c)
+        j0[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
+    j0[3] = 0x01000000u;                                   // bytes 12..15 = 00 00 00 01
+
+    GcmSetupArgs s;
+    s.ks = *ks;
+    for (int c = 0; c < 4; ++c) s.j0[c] = j0[c];
+    s.aad = (const uint8_t *)aad_dev; s.aadlen = aadlen; s.work = (GcmWork *)work;
+    gcm_setup_kernel<<<1, 32, 0, st>>>(s);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+
+    // counter field of J0 = bytes 9..11 of the nonce, then 00 00 00 01; data starts at J0 + 1
+    // (CCM_GCM pre-increment, micro_aes.c:939-941)
+    const uint64_t vj0 = (uint64_t)nonce[9] << 48 | (uint64_t)nonce[10] << 40 | (uint64_t)nonce[11] << 32 | 1u;
+    const uint32_t b8 = nonce[8];
+
+    if (nchunks) {
+        GcmBulkArgs b;
+        b.ks = *ks;
+        b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = (vj0 + 1) & kMask56;
+        b.in = (const uint4 *)in; b.out = (uint4 *)out;
+        b.nblocks = nblocks; b.kr = kr; b.nchunks = nchunks; b.work = (GcmWork *)work;
+        switch (ks->rounds * 2 + (hash_only ? 1 : 0)) {
+        case 20: e = launch_gcm_bulk_nr<10, false>(b, st); break;
+        case 21: e = launch_gcm_bulk_nr<10, true>(b, st); break;
+        case 24: e = launch_gcm_bulk_nr<12, false>(b, st); break;
+        case 25: e = launch_gcm_bulk_nr<12, true>(b, st); break;
+        case 28: e = launch_gcm_bulk_nr<14, false>(b, st); break;
+        case 29: e = launch_gcm_bulk_nr<14, true>(b, st); break;
+        default: e = cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return (int)e;
+    }
+
+    GcmFinishArgs f;
+    f.ks = *ks;
+    f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1) & kMask56;
+    f.in = (const uint8_t *)in; f.out = (uint8_t *)out;
+    f.len = len; f.aadlen = aadlen; f.kr = kr; f.nchunks = nchunks; f.hash_only = hash_only;
+    f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
+    gcm_finish_kernel<<<1, kThreads, 0, st>>>(f);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}

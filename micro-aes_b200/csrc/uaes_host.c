@@ -1,0 +1,579 @@
+/*
+ * uaes_host.c -- host side of libuaes_b200.so, plain C.
+ *
+ * What stays on the host is what the reference does ONCE per call: KeyExpansion
+ * (micro_aes.c:144-178), building the initial counter block (micro_aes.c:962-971) and argument
+ * checks with the reference's return codes.  Every per-block operation -- Cipher(), the CTR /
+ * XTS / GCM chaining, GHASH, even E_K(0) and E_K(J0) -- runs in the CUDA kernels of
+ * uaes_kernels.cu.  There is no CPU implementation of the data path in this library: without a
+ * CUDA device every entry point fails with UAES_E_NO_DEVICE.
+ *
+ * Buffers are classified per call (cudaPointerGetAttributes):
+ *   device / managed, 16-byte aligned  -> kernels run directly on them, zero copies;
+ *   anything else (pageable or pinned host memory, misaligned device memory) -> staged through
+ *   three device chunks on three streams so that H2D, kernel and D2H of consecutive chunks
+ *   overlap (CTR, ECB, XTS sectors), or through one full-size device buffer (GCM, single XTS
+ *   data unit, which cannot be cut).
+ */
+#include <cuda_runtime_api.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/uaes_b200.h"
+#include "uaes_launch.h"
+
+#if defined(__GNUC__)
+#define UAES_TLS __thread
+#else
+#define UAES_TLS
+#endif
+
+#define NSLOT       3
+#define CHUNK_BYTES ((size_t)32 << 20)      /* multiple of every sector size we accept per chunk */
+#define MAX_DEV     64
+
+typedef unsigned char u8;
+
+/* ------------------------------------------------------------------ error latch */
+
+static UAES_TLS int  tls_err;
+static UAES_TLS char tls_msg[160];
+static UAES_TLS void *tls_stream;
+static UAES_TLS int  tls_async;
+
+static int fail(int code, const char *what, int cuda_err)
+{
+    tls_err = code;
+    if (cuda_err)
+        snprintf(tls_msg, sizeof tls_msg, "%s: %s", what, cudaGetErrorString((cudaError_t)cuda_err));
+    else
+        snprintf(tls_msg, sizeof tls_msg, "%s", what);
+    return code;
+}
+
+int uaes_last_error(void) { return tls_err; }
+const char *uaes_last_error_string(void) { return tls_err ? tls_msg : ""; }
+void uaes_clear_error(void) { tls_err = 0; tls_msg[0] = 0; }
+void uaes_set_stream(void *stream) { tls_stream = stream; }
+void uaes_set_async(int enable) { tls_async = enable; }
+uaes_u64 uaes_kernel_launches(void) { return uaes_launch_count(); }
+
+int uaes_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void *uaes_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(UAES_E_NO_MEMORY, "cudaHostAlloc", (int)cudaGetLastError());
+        return NULL;
+    }
+    return p;
+}
+
+void uaes_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(UAES_E_CUDA, #call, (int)e_); goto done; } } while (0)
+#define LAUNCH(call) do { int e_ = (call); if (e_) { rc = fail(UAES_E_CUDA, #call, e_); goto done; } } while (0)
+
+/* ------------------------------------------------------------------ key schedules */
+
+static u8 g_sbox[256];
+static pthread_once_t g_sbox_once = PTHREAD_ONCE_INIT;
+
+static u8 xtime(u8 a) { return (u8)((a << 1) ^ ((a >> 7) * 0x1b)); }   /* micro_aes.c:115-118 */
+
+static u8 gmul(u8 a, u8 b)
+{
+    u8 r = 0;
+    while (b) { if (b & 1) r ^= a; a = xtime(a); b >>= 1; }
+    return r;
+}
+
+/* S(a) = affine(a^-1), FIPS-197 5.1.1 (the values of micro_aes.c:41-51) */
+static void build_sbox(void)
+{
+    int a, b;
+    for (a = 0; a < 256; ++a) {
+        u8 inv = 0, s;
+        if (a) for (b = 1; b < 256; ++b) if (gmul((u8)a, (u8)b) == 1) { inv = (u8)b; break; }
+        s = (u8)(inv ^ (u8)(inv << 1 | inv >> 7) ^ (u8)(inv << 2 | inv >> 6) ^
+                 (u8)(inv << 3 | inv >> 5) ^ (u8)(inv << 4 | inv >> 4) ^ 0x63);
+        g_sbox[a] = s;
+    }
+}
+
+/* KeyExpansion (micro_aes.c:144-178) into little-endian column words */
+static int expand_key(int keybits, const u8 *key, uaes_keysched *ks)
+{
+    int nk, total, i;
+    u8 rk[240], rcon = 1;
+
+    if (keybits != 128 && keybits != 192 && keybits != 256) return -1;
+    pthread_once(&g_sbox_once, build_sbox);
+    nk = keybits / 32;
+    total = 4 * (nk + 7);
+    memcpy(rk, key, (size_t)(4 * nk));
+    for (i = nk; i < total; ++i) {
+        u8 t0 = rk[4 * i - 4], t1 = rk[4 * i - 3], t2 = rk[4 * i - 2], t3 = rk[4 * i - 1];
+        if (i % nk == 0) {
+            const u8 first = t0;
+            t0 = (u8)(g_sbox[t1] ^ rcon); t1 = g_sbox[t2]; t2 = g_sbox[t3]; t3 = g_sbox[first];
+            rcon = xtime(rcon);
+        } else if (nk == 8 && i % nk == 4) {                  /* micro_aes.c:165-172 */
+            t0 = g_sbox[t0]; t1 = g_sbox[t1]; t2 = g_sbox[t2]; t3 = g_sbox[t3];
+        }
+        rk[4 * i + 0] = (u8)(rk[4 * (i - nk) + 0] ^ t0);
+        rk[4 * i + 1] = (u8)(rk[4 * (i - nk) + 1] ^ t1);
+        rk[4 * i + 2] = (u8)(rk[4 * (i - nk) + 2] ^ t2);
+        rk[4 * i + 3] = (u8)(rk[4 * (i - nk) + 3] ^ t3);
+    }
+    memset(ks, 0, sizeof *ks);
+    ks->rounds = nk + 6;
+    for (i = 0; i < total; ++i)
+        ks->w[i] = (u32)rk[4 * i] | (u32)rk[4 * i + 1] << 8 | (u32)rk[4 * i + 2] << 16 | (u32)rk[4 * i + 3] << 24;
+    return 0;
+}
+
+/* InvMixColumns of one column word (micro_aes.c:301-312) */
+static u32 inv_mix_word(u32 w)
+{
+    const u8 a0 = (u8)w, a1 = (u8)(w >> 8), a2 = (u8)(w >> 16), a3 = (u8)(w >> 24);
+    const u8 b0 = (u8)(gmul(a0, 14) ^ gmul(a1, 11) ^ gmul(a2, 13) ^ gmul(a3, 9));
+    const u8 b1 = (u8)(gmul(a0, 9) ^ gmul(a1, 14) ^ gmul(a2, 11) ^ gmul(a3, 13));
+    const u8 b2 = (u8)(gmul(a0, 13) ^ gmul(a1, 9) ^ gmul(a2, 14) ^ gmul(a3, 11));
+    const u8 b3 = (u8)(gmul(a0, 11) ^ gmul(a1, 13) ^ gmul(a2, 9) ^ gmul(a3, 14));
+    return (u32)b0 | (u32)b1 << 8 | (u32)b2 << 16 | (u32)b3 << 24;
+}
+
+/* The reference decrypts with the encryption schedule read backwards (micro_aes.c:315-332).
+ * The table-driven kernel uses the equivalent inverse cipher, which needs InvMixColumns applied
+ * to round keys 1..rounds-1; both produce the same plaintext (FIPS-197 5.3.5). */
+static void invert_schedule(const uaes_keysched *enc, uaes_keysched *dec)
+{
+    int r, c;
+    const int nr = enc->rounds;
+    memset(dec, 0, sizeof *dec);
+    dec->rounds = nr;
+    for (r = 0; r <= nr; ++r)
+        for (c = 0; c < 4; ++c) {
+            const u32 w = enc->w[4 * (nr - r) + c];
+            dec->w[4 * r + c] = (r == 0 || r == nr) ? w : inv_mix_word(w);
+        }
+}
+
+/* counter block of keystream block `first` for a 12-byte IV whose counter field starts at
+ * `start` (1 for CTR: micro_aes.c:968-971) */
+static void make_ctrblock(const u8 *iv, u64 start, u64 first, uaes_ctrblock *cb)
+{
+    u64 v = (u64)iv[9] << 48 | (u64)iv[10] << 40 | (u64)iv[11] << 32;
+    v ^= start;                                   /* xorBEint into a zeroed field */
+    cb->w0 = (u32)iv[0] | (u32)iv[1] << 8 | (u32)iv[2] << 16 | (u32)iv[3] << 24;
+    cb->w1 = (u32)iv[4] | (u32)iv[5] << 8 | (u32)iv[6] << 16 | (u32)iv[7] << 24;
+    cb->b8 = iv[8];
+    cb->v0 = (v + first) & (((u64)1 << 56) - 1);  /* 56-bit carry, micro_aes.c:421-427 */
+}
+
+/* ------------------------------------------------------------------ per-device resources */
+
+typedef struct {
+    int ready;
+    void *slot[NSLOT];
+    cudaStream_t st[NSLOT];
+    void *big;  size_t big_bytes;       /* grow-only full-size staging (GCM / XTS unit) */
+    void *work; size_t work_bytes;      /* grow-only GCM scratch + AAD copy */
+} devctx;
+
+static devctx g_dev[MAX_DEV];
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static int get_ctx(devctx **out)
+{
+    int dev = 0, i, n = 0;
+    devctx *c;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(UAES_E_NO_DEVICE, "no CUDA device: libuaes_b200 has no CPU fallback", 0);
+    }
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV)
+        return fail(UAES_E_NO_DEVICE, "cudaGetDevice failed", (int)cudaGetLastError());
+    c = &g_dev[dev];
+    if (!c->ready) {
+        for (i = 0; i < NSLOT; ++i)
+            if (cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking) != cudaSuccess)
+                return fail(UAES_E_CUDA, "cudaStreamCreate", (int)cudaGetLastError());
+        c->ready = 1;
+    }
+    *out = c;
+    return 0;
+}
+
+static int need_slots(devctx *c)
+{
+    int i;
+    for (i = 0; i < NSLOT; ++i)
+        if (!c->slot[i] && cudaMalloc(&c->slot[i], CHUNK_BYTES + 16) != cudaSuccess)
+            return fail(UAES_E_NO_MEMORY, "cudaMalloc(staging chunk)", (int)cudaGetLastError());
+    return 0;
+}
+
+static int grow(void **p, size_t *have, size_t want, const char *what)
+{
+    if (*have >= want) return 0;
+    if (*p) { cudaFree(*p); *p = NULL; *have = 0; }
+    want += want / 8 + 4096;
+    if (cudaMalloc(p, want) != cudaSuccess) return fail(UAES_E_NO_MEMORY, what, (int)cudaGetLastError());
+    *have = want;
+    return 0;
+}
+
+/* device (or managed) memory that the kernels may touch directly with 128-bit accesses */
+static int is_direct(const void *p)
+{
+    struct cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return 0;
+    return ((size_t)p & 15) == 0;
+}
+
+static int finish_direct(void)
+{
+    if (!tls_async) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)tls_stream);
+        if (e != cudaSuccess) return fail(UAES_E_CUDA, "cudaStreamSynchronize", (int)e);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ chunked staging pipeline */
+
+typedef int (*chunk_fn)(void *user, u64 offset, void *dev, size_t bytes, size_t out_bytes, void *stream);
+
+/* in/out may be any mix of host and device memory.  `unit` = granularity a chunk must respect.
+ * out_extra = bytes the LAST chunk writes beyond its input size (ECB padding). */
+static int run_chunked(devctx *c, const void *in, void *out, size_t len, size_t unit, size_t out_extra,
+                       chunk_fn fn, void *user)
+{
+    int rc = 0, i;
+    size_t off = 0, chunk = CHUNK_BYTES - CHUNK_BYTES % unit;
+    unsigned n = 0;
+
+    if ((rc = need_slots(c)) != 0) return rc;
+    /* inputs produced on the caller's stream (mixed host/device calls) must be complete */
+    CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+    while (off < len) {
+        const size_t bytes = len - off < chunk ? len - off : chunk;
+        const size_t obytes = bytes + (off + bytes == len ? out_extra : 0);
+        const int s = (int)(n++ % NSLOT);
+        CU(cudaMemcpyAsync(c->slot[s], (const u8 *)in + off, bytes, cudaMemcpyDefault, c->st[s]));
+        rc = fn(user, off, c->slot[s], bytes, obytes, c->st[s]);
+        if (rc) goto done;
+        CU(cudaMemcpyAsync((u8 *)out + off, c->slot[s], obytes, cudaMemcpyDefault, c->st[s]));
+        off += bytes;
+    }
+done:
+    for (i = 0; i < NSLOT; ++i) {
+        cudaError_t e = cudaStreamSynchronize(c->st[i]);
+        if (e != cudaSuccess && !rc) rc = fail(UAES_E_CUDA, "cudaStreamSynchronize(staging)", (int)e);
+    }
+    return rc;
+}
+
+/* ------------------------------------------------------------------ CTR */
+
+typedef struct { uaes_keysched ks; const u8 *iv; u64 first; } ctr_job;
+
+static int ctr_chunk(void *user, u64 offset, void *dev, size_t bytes, size_t obytes, void *stream)
+{
+    ctr_job *j = (ctr_job *)user;
+    uaes_ctrblock cb;
+    int e;
+    (void)obytes;
+    make_ctrblock(j->iv, 1, j->first + offset / 16, &cb);
+    e = uaes_launch_ctr(&j->ks, &cb, dev, dev, bytes, stream);
+    return e ? fail(UAES_E_CUDA, "ctr kernel launch", e) : 0;
+}
+
+int uaes_ctr_crypt_range(int keybits, const uaes_u8 *key, const uaes_u8 *iv, uaes_u64 first_block,
+                         const void *in, size_t len, void *out)
+{
+    devctx *c;
+    ctr_job j;
+    int rc;
+    if (expand_key(keybits, key, &j.ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (len == 0) return 0;                         /* NULL data is fine when there is none */
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    j.iv = iv; j.first = first_block;
+    if (is_direct(in) && is_direct(out)) {
+        uaes_ctrblock cb;
+        make_ctrblock(iv, 1, first_block, &cb);
+        LAUNCH(uaes_launch_ctr(&j.ks, &cb, in, out, len, tls_stream));
+        rc = finish_direct();
+    } else {
+        rc = run_chunked(c, in, out, len, 16, 0, ctr_chunk, &j);
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_ctr_crypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out)
+{
+    return uaes_ctr_crypt_range(keybits, key, iv, 0, in, len, out);
+}
+
+/* ------------------------------------------------------------------ ECB */
+
+typedef struct { uaes_keysched ks; int encrypt; } ecb_job;
+
+static int ecb_chunk(void *user, u64 offset, void *dev, size_t bytes, size_t obytes, void *stream)
+{
+    ecb_job *j = (ecb_job *)user;
+    int e;
+    (void)offset; (void)obytes;
+    e = uaes_launch_ecb(&j->ks, j->encrypt, dev, dev, bytes, stream);
+    return e ? fail(UAES_E_CUDA, "ecb kernel launch", e) : 0;
+}
+
+static int ecb_common(int keybits, const u8 *key, const void *in, size_t len, void *out, int encrypt)
+{
+    devctx *c;
+    ecb_job j;
+    uaes_keysched enc;
+    int rc;
+    if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (encrypt) j.ks = enc; else invert_schedule(&enc, &j.ks);
+    j.encrypt = encrypt;
+    if (len == 0) return 0;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if (is_direct(in) && is_direct(out)) {
+        LAUNCH(uaes_launch_ecb(&j.ks, encrypt, in, out, len, tls_stream));
+        rc = finish_direct();
+    } else {
+        /* encrypt pads the ragged tail to a whole block: the last chunk returns up to 15 more bytes */
+        const size_t extra = (encrypt && len % 16) ? 16 - len % 16 : 0;
+        rc = run_chunked(c, in, out, len, 16, extra, ecb_chunk, &j);
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_ecb_encrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out)
+{
+    return ecb_common(keybits, key, in, len, out, 1);
+}
+
+int uaes_ecb_decrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out)
+{
+    const int rc = ecb_common(keybits, key, in, len, out, 0);
+    if (rc) return rc;
+    return len % 16 ? UAES_DECRYPTION_ERROR : UAES_OK;       /* micro_aes.c:679 */
+}
+
+/* ------------------------------------------------------------------ XTS */
+
+typedef struct { uaes_keysched k1, k1e, k2; int encrypt; u64 first_sector; size_t sector_bytes; } xts_job;
+
+static int xts_keys(int keybits, const u8 *keys, int encrypt, xts_job *j)
+{
+    if (keybits != 128 && keybits != 256)
+        return fail(UAES_E_BAD_ARGUMENT, "XTS is defined for 128- and 256-bit keys only", 0);
+    expand_key(keybits, keys, &j->k1e);                       /* key1 = first half: data key   */
+    expand_key(keybits, keys + keybits / 8, &j->k2);          /* key2 = second half: tweak key */
+    if (encrypt) j->k1 = j->k1e; else invert_schedule(&j->k1e, &j->k1);
+    j->encrypt = encrypt;
+    return 0;
+}
+
+static int xts_chunk(void *user, u64 offset, void *dev, size_t bytes, size_t obytes, void *stream)
+{
+    xts_job *j = (xts_job *)user;
+    int e;
+    (void)obytes;
+    e = uaes_launch_xts_sectors(&j->k1, &j->k2, j->encrypt, j->first_sector + offset / j->sector_bytes,
+                                j->sector_bytes / 16, bytes / j->sector_bytes, dev, dev, stream);
+    return e ? fail(UAES_E_CUDA, "xts kernel launch", e) : 0;
+}
+
+int uaes_xts_sectors(int keybits, const uaes_u8 *keys, uaes_u64 first_sector, size_t sector_bytes,
+                     const void *in, size_t len, void *out, int encrypt)
+{
+    devctx *c;
+    xts_job j;
+    int rc;
+    if ((rc = xts_keys(keybits, keys, encrypt, &j)) != 0) return rc;
+    if (sector_bytes < 16 || sector_bytes % 16 || sector_bytes > CHUNK_BYTES || len % sector_bytes)
+        return fail(UAES_E_BAD_ARGUMENT, "sector size must be a multiple of 16 and divide the length", 0);
+    if (len == 0) return 0;
+    j.first_sector = first_sector; j.sector_bytes = sector_bytes;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if (is_direct(in) && is_direct(out)) {
+        LAUNCH(uaes_launch_xts_sectors(&j.k1, &j.k2, encrypt, first_sector, sector_bytes / 16,
+                                       len / sector_bytes, in, out, tls_stream));
+        rc = finish_direct();
+    } else {
+        rc = run_chunked(c, in, out, len, sector_bytes, 0, xts_chunk, &j);
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+static int xts_unit(int keybits, const u8 *keys, const u8 *tweak, const void *in, size_t len, void *out,
+                    int encrypt)
+{
+    static const u8 sector0[16] = {0};
+    devctx *c;
+    xts_job j;
+    int rc;
+    if (len < 16) return UAES_DATALENGTH_ERROR;               /* micro_aes.c:1069, 1088 */
+    if ((rc = xts_keys(keybits, keys, encrypt, &j)) != 0) return rc;
+    if (!tweak) tweak = sector0;                              /* micro_aes.c:1017-1021 */
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if (is_direct(in) && is_direct(out)) {
+        LAUNCH(uaes_launch_xts_unit(&j.k1, &j.k1e, &j.k2, encrypt, tweak, in, out, len, tls_stream));
+        rc = finish_direct();
+    } else {
+        /* one data unit cannot be cut at chunk borders without the tweak chain: stage it whole */
+        if ((rc = grow(&c->big, &c->big_bytes, len + 16, "cudaMalloc(XTS unit staging)")) != 0) goto done;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        CU(cudaMemcpyAsync(c->big, in, len, cudaMemcpyDefault, c->st[0]));
+        LAUNCH(uaes_launch_xts_unit(&j.k1, &j.k1e, &j.k2, encrypt, tweak, c->big, c->big, len, c->st[0]));
+        CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, c->st[0]));
+        CU(cudaStreamSynchronize(c->st[0]));
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_xts_encrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, const void *in, size_t len, void *out)
+{
+    return xts_unit(keybits, keys, tweak, in, len, out, 1);
+}
+
+int uaes_xts_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, const void *in, size_t len, void *out)
+{
+    return xts_unit(keybits, keys, tweak, in, len, out, 0);
+}
+
+/* ------------------------------------------------------------------ GCM */
+
+#define GCM_WORK_HEAD 1024   /* tag scratch lives in front of the kernels' work area */
+
+/* common part: returns with data resident on the device (din/dout), AAD on the device, work ready */
+static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
+                      const void *in, size_t len, void *out, int decrypt)
+{
+    devctx *c;
+    uaes_keysched ks;
+    int rc, direct;
+    const void *din, *daad;
+    void *dout;
+    u8 *work, *dtag;
+    size_t wbytes;
+    cudaStream_t st;
+
+    if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+
+    direct = len == 0 || (is_direct(in) && is_direct(out));
+    st = direct ? (cudaStream_t)tls_stream : c->st[0];
+    wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + aadlen + 64;
+    if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM work)")) != 0) goto done;
+    dtag = (u8 *)c->work;
+    work = (u8 *)c->work + GCM_WORK_HEAD;
+    daad = NULL;
+    if (aadlen) {
+        u8 *a = work + uaes_gcm_work_bytes(len);
+        a += (16 - ((size_t)a & 15)) & 15;
+        CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
+        daad = a;
+    }
+    if (direct) {
+        din = in; dout = out;
+    } else {
+        if ((rc = grow(&c->big, &c->big_bytes, len + 32, "cudaMalloc(GCM staging)")) != 0) goto done;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
+        din = c->big; dout = c->big;
+    }
+
+    if (!decrypt) {
+        /* one fused pass: CTR + GHASH, tag appended at out + len (micro_aes.c:1168,1178) */
+        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, dout, len, 0, (u8 *)dout + len, work, st));
+        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
+        if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
+    } else {
+        /* verify first, decrypt only on success; `out` stays untouched otherwise (micro_aes.c:1199-1209) */
+        u8 t1[16], t2[16];
+        uaes_ctrblock cb;
+        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, NULL, len, 1, dtag, work, st));
+        CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(t2, (const u8 *)din + len, 16, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));
+        if (memcmp(t1, t2, 16)) { rc = UAES_AUTH_ERROR; goto done; }
+        if (len) {
+            make_ctrblock(nonce, 1, 1, &cb);                  /* J0 = nonce || 1, data from J0 + 1 */
+            LAUNCH(uaes_launch_ctr(&ks, &cb, din, dout, len, st));
+            if (!direct) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
+            if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
+        }
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_gcm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return gcm_common(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+}
+
+int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return gcm_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+}
+
+/* ------------------------------------------------------------------ synthetic data */
+
+int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords)
+{
+    devctx *c;
+    int rc;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    LAUNCH(uaes_launch_fill(seed, first_word, dst, nwords, tls_stream));
+    rc = finish_direct();
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_xor_fold64(const void *src, size_t nwords, uaes_u64 *result)
+{
+    devctx *c;
+    int rc;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD, "cudaMalloc(work)")) != 0) goto done;
+    LAUNCH(uaes_launch_xor_fold(src, nwords, c->work, tls_stream));
+    CU(cudaMemcpyAsync(result, c->work, 8, cudaMemcpyDefault, (cudaStream_t)tls_stream));
+    CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}

@@ -1,0 +1,76 @@
+/*
+ * uaes_launch.h -- internal boundary between the ANSI-C host side (uaes_host.c) and the CUDA
+ * translation unit (uaes_kernels.cu).  Plain C: structs of words and the launcher prototypes.
+ * Nothing here is public; the public ABI is include/uaes_b200.h.
+ */
+#ifndef UAES_LAUNCH_H_
+#define UAES_LAUNCH_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef unsigned int       u32;
+typedef unsigned long long u64;
+
+/* An expanded key as the kernels consume it: 4*(rounds+1) little-endian column words.
+ * For encryption w[] is the FIPS-197 schedule (micro_aes.c:144-178).  For the table-driven
+ * decryption rounds w[] is the equivalent-inverse-cipher schedule: round keys in reverse
+ * order with InvMixColumns applied to all but the first and last. */
+typedef struct {
+    u32 w[60];
+    int rounds;              /* 10, 12 or 14 */
+} uaes_keysched;
+
+/* CTR / GCM counter block (micro_aes.c:962-971, 1150-1151): bytes 0..8 are fixed, bytes 9..15
+ * are a 56-bit big-endian counter (micro_aes.c:421-427). */
+typedef struct {
+    u32 w0, w1;              /* counter-block bytes 0..7 as little-endian words */
+    u32 b8;                  /* byte 8 */
+    u64 v0;                  /* 56-bit counter value of keystream block 0 */
+} uaes_ctrblock;
+
+/* all launchers return a cudaError_t value as int (0 = success); `stream` is a cudaStream_t */
+
+/* out[i] = in[i] ^ E_K(counter(i)); len in bytes, tail block handled in-kernel */
+int uaes_launch_ctr(const uaes_keysched *ks, const uaes_ctrblock *cb, const void *in, void *out,
+                    u64 len, void *stream);
+
+/* ECB over len/16 full blocks; encrypt additionally zero-pads and encrypts a len%16 tail */
+int uaes_launch_ecb(const uaes_keysched *ks, int encrypt, const void *in, void *out, u64 len,
+                    void *stream);
+
+/* XTS over nsectors data units of sector_blocks*16 bytes; unit j uses tweak LE128(first_sector+j).
+ * ks1 = data key schedule (inverse schedule when !encrypt), ks2 = tweak key (always encryption) */
+int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keysched *ks2, int encrypt,
+                            u64 first_sector, u64 sector_blocks, u64 nsectors, const void *in,
+                            void *out, void *stream);
+
+/* XTS over ONE data unit of len bytes (len >= 16) with an explicit 16-byte tweak, including
+ * ciphertext stealing.  ks1e = data key encryption schedule (needed by the stealing path and
+ * the small cipher), ks1 = schedule for the bulk direction. */
+int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysched *ks1e,
+                         const uaes_keysched *ks2, int encrypt, const unsigned char tweak[16],
+                         const void *in, void *out, u64 len, void *stream);
+
+/* GCM.  `work` is a device scratch area of at least uaes_gcm_work_bytes(len) bytes.
+ * encrypt: CTR over in -> out, GHASH over aad and out, tag written to out + len.
+ * hash_only: GHASH over aad and in, tag (E_K(J0) ^ GHASH) written to tag_out (device, 16 B). */
+size_t uaes_gcm_work_bytes(u64 len);
+int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+                    u64 aadlen, const void *in, void *out, u64 len, int hash_only, void *tag_out,
+                    void *work, void *stream);
+
+/* synthetic data + checksum helpers */
+int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
+int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);
+
+/* kernels launched so far by this process */
+u64 uaes_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

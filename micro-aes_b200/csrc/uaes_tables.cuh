@@ -1,0 +1,178 @@
+// uaes_tables.cuh -- AES lookup tables for sm_100a: generated at compile time, expanded
+// into bank-conflict-free shared-memory layouts at kernel start.
+//
+// What the reference does per byte with sbox[] / rsbox[] (micro_aes.c:41-65), xtime
+// (micro_aes.c:115-118) and MixColumns / InvMixColumns (micro_aes.c:221-239, 301-312) is
+// folded into four 32-bit "T-tables" per direction:
+//     Te0[x] = { 2*S(x), S(x), S(x), 3*S(x) }   (byte 0 = row 0), Te_k = Te0 rotated left 8k bits
+//     Td0[x] = { 14*Si(x), 9*Si(x), 13*Si(x), 11*Si(x) },        Td_k = Td0 rotated left 8k bits
+// so that one round of a column is four lookups and four XORs.
+//
+// Shared-memory layout (the part that matters on B200): shared memory has 32 banks x 4 B and
+// serves one 4-byte word per bank per clock, i.e. at most 32 table lookups / clk / SM.  Random
+// S-box indices hit random banks, so every table is stored 32 times, once per lane, with lane l's
+// copy living entirely in bank l:
+//     address(table pair p, table t in {0,1}, entry x, lane l) = base + p*65536 + x*256 + t*128 + l*4
+// A lookup is then ONE byte-permute (PRMT builds  x<<8 | lane*4  straight from the state word,
+// no shift/mask) plus ONE conflict-free LDS with an immediate table offset.  `base` must be
+// 64 KiB aligned inside the CTA's shared window for the PRMT trick; kernels over-allocate and
+// align at run time (the window starts at a driver-chosen offset).
+#pragma once
+#include <stdint.h>
+
+namespace uaes {
+
+// ---------------------------------------------------------------- compile-time generation
+
+struct ByteTable { uint8_t v[256]; };
+struct WordTable { uint32_t v[256]; };
+
+constexpr uint8_t gf_double(uint8_t a) { return (uint8_t)((a << 1) ^ ((a >> 7) * 0x1b)); }
+
+constexpr uint8_t gf_mul(uint8_t a, uint8_t b)
+{
+    uint8_t r = 0;
+    for (int i = 0; i < 8; ++i) {
+        if (b & 1) r ^= a;
+        a = gf_double(a);
+        b >>= 1;
+    }
+    return r;
+}
+
+// FIPS-197 5.1.1: multiplicative inverse in GF(2^8) followed by the affine map
+constexpr ByteTable make_sbox()
+{
+    ByteTable t{};
+    // generator 3 walks the whole multiplicative group: p = 3^i, q = 3^-i
+    uint8_t p = 1, q = 1;
+    do {
+        p = (uint8_t)(p ^ gf_double(p));                       // p *= 3
+        q ^= (uint8_t)(q << 1); q ^= (uint8_t)(q << 2); q ^= (uint8_t)(q << 4);
+        if (q & 0x80) q ^= 0x09;                               // q /= 3
+        uint8_t x = (uint8_t)(q ^ (uint8_t)((q << 1) | (q >> 7)) ^ (uint8_t)((q << 2) | (q >> 6))
+                              ^ (uint8_t)((q << 3) | (q >> 5)) ^ (uint8_t)((q << 4) | (q >> 4)));
+        t.v[p] = (uint8_t)(x ^ 0x63);
+    } while (p != 1);
+    t.v[0] = 0x63;
+    return t;
+}
+
+constexpr ByteTable make_inv_sbox()
+{
+    ByteTable s = make_sbox(), t{};
+    for (int i = 0; i < 256; ++i) t.v[s.v[i]] = (uint8_t)i;
+    return t;
+}
+
+constexpr WordTable make_te0()
+{
+    ByteTable s = make_sbox();
+    WordTable t{};
+    for (int i = 0; i < 256; ++i) {
+        const uint32_t x = s.v[i], x2 = gf_double((uint8_t)x), x3 = x2 ^ x;
+        t.v[i] = x2 | x << 8 | x << 16 | x3 << 24;
+    }
+    return t;
+}
+
+constexpr WordTable make_td0()
+{
+    ByteTable s = make_inv_sbox();
+    WordTable t{};
+    for (int i = 0; i < 256; ++i) {
+        const uint8_t x = s.v[i];
+        t.v[i] = (uint32_t)gf_mul(x, 14) | (uint32_t)gf_mul(x, 9) << 8
+               | (uint32_t)gf_mul(x, 13) << 16 | (uint32_t)gf_mul(x, 11) << 24;
+    }
+    return t;
+}
+
+// inverse S-box replicated into all four bytes: the last decryption round picks bytes from it
+constexpr WordTable make_td4()
+{
+    ByteTable s = make_inv_sbox();
+    WordTable t{};
+    for (int i = 0; i < 256; ++i) t.v[i] = 0x01010101u * s.v[i];
+    return t;
+}
+
+// 1 KiB each, read once per CTA (warp-uniform index -> constant-cache broadcast)
+__constant__ WordTable c_te0 = make_te0();
+__constant__ WordTable c_td0 = make_td0();
+__constant__ WordTable c_td4 = make_td4();
+// byte tables for the one-off blocks (GCM subkeys, XTS stealing) that run on a single thread
+__constant__ ByteTable c_sbox = make_sbox();
+__constant__ ByteTable c_inv_sbox = make_inv_sbox();
+
+// ---------------------------------------------------------------- shared-memory layout
+
+constexpr uint32_t kTablePairBytes = 65536;            // 256 entries x (2 tables x 32 lanes x 4 B)
+constexpr uint32_t kTableAlign     = 65536;
+constexpr uint32_t kOffT0 = 0, kOffT1 = 128, kOffT2 = kTablePairBytes, kOffT3 = kTablePairBytes + 128;
+constexpr uint32_t kEncTableBytes  = 2 * kTablePairBytes;   // Te0|Te1, Te2|Te3
+constexpr uint32_t kDecTableBytes  = 2 * kTablePairBytes;   // Td0|Td1, Td4|(unused)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int n)   // n in {0,8,16,24}
+{
+    return n ? __funnelshift_l(x, x, n) : x;
+}
+
+// Fill one 64 KiB pair region: table A in the low 128 B of each 256 B row, table B in the high
+// 128 B, each word replicated for the 32 lanes.  src is a __constant__ table, rotA / rotB are
+// left rotations in bits.  Called by all threads of the CTA.
+__device__ __forceinline__ void fill_pair(uint32_t region, const WordTable &srcA, int rotA,
+                                          const WordTable &srcB, int rotB)
+{
+    // 256 rows x 64 words; consecutive threads write consecutive words (conflict free)
+    for (uint32_t w = threadIdx.x; w < 256u * 64u; w += blockDim.x) {
+        const uint32_t row = w >> 6, col = w & 63;
+        const uint32_t v = col < 32 ? rotl32(srcA.v[row], rotA) : rotl32(srcB.v[row], rotB);
+        sts32(region + row * 256 + col * 4, v);
+    }
+}
+
+// returns the 64 KiB-aligned base of the encryption tables inside the dynamic smem window
+__device__ __forceinline__ uint32_t align_table_base(const void *dyn_smem)
+{
+    return (smem_u32(dyn_smem) + (kTableAlign - 1)) & ~(kTableAlign - 1);
+}
+
+__device__ __forceinline__ void init_enc_tables(uint32_t base)
+{
+    fill_pair(base, c_te0, 0, c_te0, 8);
+    fill_pair(base + kTablePairBytes, c_te0, 16, c_te0, 24);
+}
+
+// decryption keeps Td0|Td1 and derives Td2/Td3 by a 16-bit rotate of the looked-up word, so
+// that the second pair region can hold Td4 (inverse S-box) for the last round
+__device__ __forceinline__ void init_dec_tables(uint32_t base)
+{
+    fill_pair(base, c_td0, 0, c_td0, 8);
+    fill_pair(base + kTablePairBytes, c_td4, 0, c_td4, 0);
+}
+
+// ---------------------------------------------------------------- the lookup primitive
+
+// lanebase = table base + lane*4 (byte 0 = lane*4 < 128, byte 1 = 0, bytes 2..3 = base >> 16).
+// PRMT builds  { lanebase.b0, w.b[BYTE], lanebase.b2, lanebase.b3 }  =  base + x*256 + lane*4.
+template <int BYTE, uint32_t OFF>
+__device__ __forceinline__ uint32_t lut(uint32_t lanebase, uint32_t w)
+{
+    const uint32_t a = __byte_perm(w, lanebase, 0x7604 | (BYTE << 4));
+    uint32_t r;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(a), "n"(OFF));
+    return r;
+}
+
+}  // namespace uaes

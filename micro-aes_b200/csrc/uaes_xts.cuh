@@ -1,0 +1,257 @@
+// uaes_xts.cuh -- XTS kernels (included by uaes_kernels.cu).
+//
+// Restates XTS_cipher (micro_aes.c:1008-1055): Y_j = T_j ^ Cipher_K1(T_j ^ X_j) with
+// T_0 = E_K2(tweak), T_{j+1} = alpha * T_j, plus ciphertext stealing for ragged units.  The
+// reference's serial tweak chain becomes T_0 * alpha^j computed from the block index.
+#pragma once
+
+namespace uaes {
+
+// Encryption with ONLY Te0 available at table offset OFF (decrypt kernels keep Te0 next to the
+// inverse tables so that they can still encrypt sector tweaks): Te_k = Te0 rotated by 8k bits.
+template <int NR, uint32_t OFF>
+__device__ __forceinline__ void enc_block_te0(uint32_t lb, uint32_t &s0, uint32_t &s1, uint32_t &s2,
+                                              uint32_t &s3, const uint32_t *rk)
+{
+    s0 ^= rk[0]; s1 ^= rk[1]; s2 ^= rk[2]; s3 ^= rk[3];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) {
+        const uint32_t t0 = lut<0, OFF>(lb, s0) ^ rotl32(lut<1, OFF>(lb, s1), 8) ^ rotl32(lut<2, OFF>(lb, s2), 16) ^ rotl32(lut<3, OFF>(lb, s3), 24) ^ rk[4 * r + 0];
+        const uint32_t t1 = lut<0, OFF>(lb, s1) ^ rotl32(lut<1, OFF>(lb, s2), 8) ^ rotl32(lut<2, OFF>(lb, s3), 16) ^ rotl32(lut<3, OFF>(lb, s0), 24) ^ rk[4 * r + 1];
+        const uint32_t t2 = lut<0, OFF>(lb, s2) ^ rotl32(lut<1, OFF>(lb, s3), 8) ^ rotl32(lut<2, OFF>(lb, s0), 16) ^ rotl32(lut<3, OFF>(lb, s1), 24) ^ rk[4 * r + 2];
+        const uint32_t t3 = lut<0, OFF>(lb, s3) ^ rotl32(lut<1, OFF>(lb, s0), 8) ^ rotl32(lut<2, OFF>(lb, s1), 16) ^ rotl32(lut<3, OFF>(lb, s2), 24) ^ rk[4 * r + 3];
+        s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+    }
+    // Te0 = {2S, S, S, 3S}: S(x) sits in bytes 1 and 2
+    auto last = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        const uint32_t lo = __byte_perm(lut<0, OFF>(lb, a), lut<1, OFF>(lb, b), 0x0051);
+        const uint32_t hi = __byte_perm(lut<2, OFF>(lb, c), lut<3, OFF>(lb, d), 0x6200);
+        return __byte_perm(lo, hi, 0x7610);
+    };
+    const uint32_t o0 = last(s0, s1, s2, s3) ^ rk[4 * NR + 0], o1 = last(s1, s2, s3, s0) ^ rk[4 * NR + 1];
+    const uint32_t o2 = last(s2, s3, s0, s1) ^ rk[4 * NR + 2], o3 = last(s3, s0, s1, s2) ^ rk[4 * NR + 3];
+    s0 = o0; s1 = o1; s2 = o2; s3 = o3;
+}
+
+// decrypt kernels: pair 0 = Td0|Td1, pair 1 = Td4|Te0
+__device__ __forceinline__ void init_xts_dec_tables(uint32_t base)
+{
+    fill_pair(base, c_td0, 0, c_td0, 8);
+    fill_pair(base + kTablePairBytes, c_td4, 0, c_te0, 0);
+}
+
+template <bool ENC>
+__device__ __forceinline__ uint32_t setup_xts_tables(const void *dyn)
+{
+    const uint32_t base = align_table_base(dyn);
+    if (base + kEncTableBytes > smem_u32(dyn) + dyn_smem_size()) __trap();
+    if (ENC) init_enc_tables(base); else init_xts_dec_tables(base);
+    __syncthreads();
+    uint32_t lanebase = base + (threadIdx.x & 31) * 4;
+    asm volatile("" : "+r"(lanebase)::"memory");
+    return lanebase;
+}
+
+// one XEX block: s = Cipher(s ^ T) ^ T
+template <int NR, bool ENC>
+__device__ __forceinline__ void xex_block(uint32_t lb, uint32_t &s0, uint32_t &s1, uint32_t &s2,
+                                          uint32_t &s3, const uint32_t *k1, Tweak t)
+{
+    uint32_t t0, t1, t2, t3;
+    tweak_words(t, t0, t1, t2, t3);
+    s0 ^= t0; s1 ^= t1; s2 ^= t2; s3 ^= t3;
+    if (ENC) enc_block<NR>(lb, s0, s1, s2, s3, k1, t0, t1, t2, t3);
+    else     dec_block<NR>(lb, s0, s1, s2, s3, k1, t0, t1, t2, t3);
+}
+
+// ---------------------------------------------------------------- batched sectors
+
+struct XtsSectorArgs {
+    uaes_keysched k1, k2;
+    uint64_t first_sector, sector_blocks, nsectors;
+    const uint4 *in;
+    uint4 *out;
+};
+
+// A warp takes a tile of 32 consecutive sectors: lane l encrypts the tweak of sector l (one AES
+// per 32 sectors per lane), then the warp walks the sectors; for each one the sector's T_0 is
+// broadcast by shuffle and lane l takes block 32*row + l with tweak T_0 * alpha^(32*row + l).
+// A 512-byte sector is exactly one coalesced row.
+template <int NR, bool ENC>
+__global__ void __launch_bounds__(kThreads, 1) xts_sectors_kernel(const __grid_constant__ XtsSectorArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_xts_tables<ENC>(dyn);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t ntiles = (a.nsectors + 31) / 32;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint64_t sb = a.sector_blocks;
+
+    for (uint64_t tile = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        // T_0 of sector tile*32 + lane: E_K2(LE128(sector)), micro_aes.c:1017-1027
+        const uint64_t sec = a.first_sector + tile * 32 + lane;
+        uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
+        if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.k2.w);
+        else     enc_block_te0<NR, kOffT3>(lb, e0, e1, e2, e3, a.k2.w);
+
+        const uint64_t left = a.nsectors - tile * 32;
+        const int nsec = left < 32 ? (int)left : 32;
+        for (int s = 0; s < nsec; ++s) {
+            Tweak t0;
+            t0.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, s) << 32 | __shfl_sync(0xffffffffu, e0, s);
+            t0.hi = (uint64_t)__shfl_sync(0xffffffffu, e3, s) << 32 | __shfl_sync(0xffffffffu, e2, s);
+            Tweak t = xts_shl(t0, lane);                        // alpha^lane
+            const uint64_t base = (tile * 32 + s) * sb;
+            for (uint64_t j = lane; j < sb; j += 32) {
+                uint4 v = ld_stream(a.in + base + j);
+                xex_block<NR, ENC>(lb, v.x, v.y, v.z, v.w, a.k1.w, t);
+                st_stream(a.out + base + j, v);
+                t = xts_shl(t, 32);                             // next row of this sector
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- one data unit
+
+struct XtsUnitArgs {
+    uaes_keysched k1, k1e, k2;   // bulk-direction schedule, K1 encryption schedule, K2 schedule
+    uint32_t tweak[4];
+    const uint4 *in;
+    uint4 *out;
+    uint64_t nblocks;            // blocks handled by the plain loop: len/16 - (len%16 != 0)
+    uint32_t tail;               // len % 16 (stealing when non-zero)
+};
+
+// The unit is cut into rows of 32 blocks; every warp owns a contiguous run of rows, jumps to
+// T_0 * alpha^(first block) once (ladder of squarings of alpha^128) and then steps alpha^32 per row.
+template <int NR, bool ENC>
+__global__ void __launch_bounds__(kThreads, 1) xts_unit_kernel(const __grid_constant__ XtsUnitArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    __shared__ uint32_t t0s[4];
+    if (threadIdx.x == 0) {                                   // T_0 = E_K2(tweak), micro_aes.c:1026-1027
+        uint32_t s[4] = {a.tweak[0], a.tweak[1], a.tweak[2], a.tweak[3]};
+        small_encrypt(a.k2.w, a.k2.rounds, s);
+        t0s[0] = s[0]; t0s[1] = s[1]; t0s[2] = s[2]; t0s[3] = s[3];
+    }
+    const uint32_t lb = setup_xts_tables<ENC>(dyn);           // contains __syncthreads()
+    const uint32_t lane = threadIdx.x & 31;
+    Tweak T0;
+    T0.lo = (uint64_t)t0s[1] << 32 | t0s[0];
+    T0.hi = (uint64_t)t0s[3] << 32 | t0s[2];
+
+    const uint64_t rows = (a.nblocks + 31) / 32;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint64_t rpw = (rows + nwarps - 1) / nwarps;
+    const uint64_t warp = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const uint64_t r0 = warp * rpw, r1 = r0 + rpw < rows ? r0 + rpw : rows;
+
+    if (r0 < r1) {
+        Tweak t = xts_jump(T0, r0 * 32 + lane);
+        uint64_t k = r0 * 32 + lane;
+        uint4 cur = k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
+        for (uint64_t r = r0; r < r1; ++r, k += 32) {
+            const uint4 nxt = (r + 1 < r1 && k + 32 < a.nblocks) ? ld_stream(a.in + k + 32) : make_uint4(0, 0, 0, 0);
+            uint4 v = cur;
+            xex_block<NR, ENC>(lb, v.x, v.y, v.z, v.w, a.k1.w, t);
+            if (k < a.nblocks) st_stream(a.out + k, v);
+            t = xts_shl(t, 32);
+            cur = nxt;
+        }
+    }
+
+    // ciphertext stealing (micro_aes.c:1037-1053) on one thread with the byte-wise cipher
+    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint64_t m = a.nblocks;                          // index of the last full block
+        const Tweak Tm = xts_jump(T0, m), Tn = xts_shl(Tm, 1);
+        const uint8_t *x = (const uint8_t *)(a.in + m);
+        uint8_t *y = (uint8_t *)(a.out + m);
+        uint8_t first[16], part[16];
+        for (int i = 0; i < 16; ++i) first[i] = x[i];
+        for (uint32_t i = 0; i < a.tail; ++i) part[i] = x[16 + i];
+        auto xex = [&](uint8_t b[16], Tweak t) {
+            uint32_t tw[4], s[4];
+            tweak_words(t, tw[0], tw[1], tw[2], tw[3]);
+            for (int c = 0; c < 4; ++c)
+                s[c] = ((uint32_t)b[4 * c] | (uint32_t)b[4 * c + 1] << 8 | (uint32_t)b[4 * c + 2] << 16 | (uint32_t)b[4 * c + 3] << 24) ^ tw[c];
+            if (ENC) small_encrypt(a.k1e.w, a.k1e.rounds, s); else small_decrypt(a.k1e.w, a.k1e.rounds, s);
+            for (int c = 0; c < 4; ++c) {
+                s[c] ^= tw[c];
+                for (int i = 0; i < 4; ++i) b[4 * c + i] = (uint8_t)(s[c] >> (8 * i));
+            }
+        };
+        // encrypt: block m under T_m, the stolen block under alpha*T_m; decrypt: the other way round
+        xex(first, ENC ? Tm : Tn);
+        for (uint32_t i = a.tail; i < 16; ++i) part[i] = first[i];
+        xex(part, ENC ? Tn : Tm);
+        for (int i = 0; i < 16; ++i) y[i] = part[i];
+        for (uint32_t i = 0; i < a.tail; ++i) y[16 + i] = first[i];
+    }
+}
+
+template <int NR, bool ENC>
+static cudaError_t launch_xts_sectors_nr(const XtsSectorArgs &a, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(xts_sectors_kernel<NR, ENC>);
+    if (e != cudaSuccess) return e;
+    xts_sectors_kernel<NR, ENC><<<grid_for((a.nsectors + 31) / 32), kThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+template <int NR, bool ENC>
+static cudaError_t launch_xts_unit_nr(const XtsUnitArgs &a, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(xts_unit_kernel<NR, ENC>);
+    if (e != cudaSuccess) return e;
+    // at least 8 rows per warp so that the jump-ahead amortises
+    xts_unit_kernel<NR, ENC><<<grid_for((a.nblocks + 255) / 256), kThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace uaes
+
+extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keysched *ks2, int encrypt,
+                                       u64 first_sector, u64 sector_blocks, u64 nsectors,
+                                       const void *in, void *out, void *stream)
+{
+    using namespace uaes;
+    if (nsectors == 0 || sector_blocks == 0) return 0;
+    XtsSectorArgs a;
+    a.k1 = *ks1; a.k2 = *ks2;
+    a.first_sector = first_sector; a.sector_blocks = sector_blocks; a.nsectors = nsectors;
+    a.in = (const uint4 *)in; a.out = (uint4 *)out;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
+    case 21: return (int)launch_xts_sectors_nr<10, true>(a, st);
+    case 20: return (int)launch_xts_sectors_nr<10, false>(a, st);
+    case 29: return (int)launch_xts_sectors_nr<14, true>(a, st);
+    case 28: return (int)launch_xts_sectors_nr<14, false>(a, st);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysched *ks1e,
+                                    const uaes_keysched *ks2, int encrypt, const unsigned char tweak[16],
+                                    const void *in, void *out, u64 len, void *stream)
+{
+    using namespace uaes;
+    if (len < 16) return (int)cudaErrorInvalidValue;
+    XtsUnitArgs a;
+    a.k1 = *ks1; a.k1e = *ks1e; a.k2 = *ks2;
+    for (int c = 0; c < 4; ++c)
+        a.tweak[c] = (uint32_t)tweak[4 * c] | (uint32_t)tweak[4 * c + 1] << 8 | (uint32_t)tweak[4 * c + 2] << 16 | (uint32_t)tweak[4 * c + 3] << 24;
+    a.in = (const uint4 *)in; a.out = (uint4 *)out;
+    a.tail = (uint32_t)(len % 16);
+    a.nblocks = len / 16 - (a.tail ? 1 : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
+    case 21: return (int)launch_xts_unit_nr<10, true>(a, st);
+    case 20: return (int)launch_xts_unit_nr<10, false>(a, st);
+    case 29: return (int)launch_xts_unit_nr<14, true>(a, st);
+    case 28: return (int)launch_xts_unit_nr<14, false>(a, st);
+    }
+    return (int)cudaErrorInvalidValue;
+}

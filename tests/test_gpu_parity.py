@@ -1,0 +1,306 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmicro_aes_<bits>.so with the
+reference's symbol names, and the uaes_* extensions of libuaes_b200.so), against
+
+  * the reference's own known-answer vectors (tests/golden/*.json), bit-exact;
+  * the pinned CPU oracle on seeded inputs, including the edge cases the reference exercises
+    (empty / ragged inputs, stealing, auth failure) and the ones it cannot (counter carries,
+    device pointers, in-place, misaligned pointers);
+  * size-independent properties at BASELINE.json's full sizes (test_gpu_fullsize.py).
+
+Everything here is integer/byte work: the bar is bit-exact, no tolerance.
+"""
+import ctypes
+import importlib
+
+import pytest
+
+from util import Oracle, golden, rnd, sha256
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def uaes():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    mod = importlib.import_module("micro-aes_b200")
+    assert mod.core().uaes_device_count() >= 1
+    return mod
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    return pytest.importorskip("torch")
+
+
+def dev(torch, data, pad=0, offset=0):
+    """device uint8 tensor holding `data` at byte offset `offset` of an over-allocated buffer"""
+    import numpy as np
+    t = torch.zeros(offset + len(data) + pad + 16, dtype=torch.uint8, device="cuda")
+    if data:
+        t[offset:offset + len(data)] = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+    return t
+
+
+def host(t, a, b):
+    return bytes(t[a:b].cpu().numpy())
+
+
+# ---------------------------------------------------------------- the reference's own vectors
+
+def test_fips197_and_main_c(uaes):
+    m = golden("main_c.json")
+    a = uaes.MicroAES(128)
+    v = m["fips197_c1"]
+    assert a.AES_ECB_encrypt(H(v["key"]), H(v["pt"])) == H(v["ct"])          # BASELINE config 1
+    assert a.AES_ECB_decrypt(H(v["key"]), H(v["ct"])) == (0, H(v["pt"]))
+    key, iv16, pt = H(m["key_pool"]), H(m["iv16"]), H(m["plaintext"])
+    assert a.AES_ECB_encrypt(key[:16], pt) == H(m["ecb128"])                  # main.c:139-145
+    rc, back = a.AES_ECB_decrypt(key[:16], H(m["ecb128"]))
+    assert rc == 0 and back == pt + bytes(7)
+    assert a.AES_CTR_encrypt(key[:16], iv16[:12], pt) == H(m["ctr128"])       # main.c:167-173
+    assert a.AES_CTR_decrypt(key[:16], iv16[:12], H(m["ctr128"])) == pt
+    for bits in (128, 256):
+        b = uaes.MicroAES(bits)
+        assert b.AES_XTS_encrypt(key[:bits // 4], iv16, pt) == (0, H(m[f"xts{bits}"]))   # main.c:174-180
+        assert b.AES_XTS_decrypt(key[:bits // 4], iv16, H(m[f"xts{bits}"])) == (0, pt)
+        out = b.AES_GCM_encrypt(key[:bits // 8], iv16[:12], H(m["aad"]), pt)  # main.c:191-197
+        assert out == H(m[f"gcm{bits}"])
+        assert b.AES_GCM_decrypt(key[:bits // 8], iv16[:12], H(m["aad"]), out) == (0, pt)
+
+
+@pytest.mark.parametrize("bits,expected", [(128, 800), (256, 600)])
+def test_xts_rsp(uaes, bits, expected):
+    a = uaes.MicroAES(bits)
+    cases = golden(f"xts{bits}.json")["cases"]
+    assert len(cases) == expected
+    for c in cases:
+        assert a.AES_XTS_encrypt(H(c["key"]), H(c["i"]), H(c["pt"])) == (0, H(c["ct"])), c
+        assert a.AES_XTS_decrypt(H(c["key"]), H(c["i"]), H(c["ct"])) == (0, H(c["pt"])), c
+
+
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_gcm_rsp(uaes, bits):
+    a = uaes.MicroAES(bits)
+    cases = golden(f"gcm{bits}.json")["cases"]
+    assert len(cases) == 375
+    for c in cases:
+        out = a.AES_GCM_encrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["pt"]))
+        assert out == H(c["ct"]) + H(c["tag"]), c
+        assert a.AES_GCM_decrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), out) == (0, H(c["pt"])), c
+
+
+def test_recorded_reference_outputs(uaes):
+    """outputs of the unmodified reference recorded by tests/golden/make_golden.py"""
+    s = golden("oracle_ref_samples.json")
+    lib = {b: uaes.MicroAES(b) for b in (128, 192, 256)}
+    for c in s["ctr"]:
+        ct = lib[c["bits"]].AES_CTR_encrypt(H(c["key"]), H(c["iv"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(ct) == c["ct_sha256"], c
+    for c in s["ecb"]:
+        assert sha256(lib[c["bits"]].AES_ECB_encrypt(H(c["key"]), rnd(c["pt_tag"], c["n"]))) == c["ct_sha256"], c
+    for c in s["xts"]:
+        rc, ct = lib[c["bits"]].AES_XTS_encrypt(H(c["keys"]), H(c["tweak"]), rnd(c["pt_tag"], c["n"]))
+        assert rc == 0 and sha256(ct) == c["ct_sha256"], c
+        assert lib[c["bits"]].AES_XTS_decrypt(H(c["keys"]), H(c["tweak"]), ct) == (0, rnd(c["pt_tag"], c["n"]))
+    for c in s["gcm"]:
+        out = lib[c["bits"]].AES_GCM_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]),
+                                             rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+    for c in s["xts_sectors"]:
+        n = c["sector_bytes"] * c["sectors"]
+        pt = rnd(c["pt_tag"], n)
+        out = ctypes.create_string_buffer(n)
+        uaes.xts_sectors(c["bits"], H(c["keys"]), c["first_sector"], c["sector_bytes"], pt, n, out)
+        assert sha256(out.raw) == c["ct_sha256"], c
+
+
+def test_counter_carries(uaes, orc):
+    """56-bit big-endian counter (micro_aes.c:421-427): carry out of byte 12 into the nonce bytes
+    and the wrap at 2^56 that leaves byte 8 alone; pinned by the PRESET_COUNTER reference run"""
+    s = golden("oracle_ref_samples.json")
+    c = next(x for x in s["ctr_preset_counter"] if x["name"] == "into_nonce_byte11")
+    key, pt, iv = H(c["key"]), rnd(c["pt_tag"], 128), H(c["counter0"])[:12]
+    out = ctypes.create_string_buffer(128)
+    uaes.ctr_crypt_range(128, key, iv, 0xFFFFFFFE - 1, pt, 128, out)
+    assert out.raw.hex() == c["ct"]
+    c = next(x for x in s["ctr_preset_counter"] if x["name"] == "wrap56")
+    key, pt, blk = H(c["key"]), rnd(c["pt_tag"], 128), H(c["counter0"])
+    iv = blk[:9] + b"\xff\xff\xff"                     # field = ffffff|00000001 after the ^1
+    first = (int.from_bytes(blk[9:], "big") - ((0xFFFFFF << 32) | 1)) % (1 << 56)
+    uaes.ctr_crypt_range(128, key, iv, first, pt, 128, out)
+    assert out.raw.hex() == c["ct"]
+    # and against the oracle across a group (256-counter) boundary and the 2^32 boundary
+    key, iv = rnd("cc-k", 32), rnd("cc-i", 12)
+    for first in (0, 200, 254, 255, 256, 0xFFFFFF00, 0xFFFFFFFF - 40, (1 << 40) - 3, (1 << 56) - 300):
+        data = rnd(f"cc-d{first}", 16 * 600 + 7)
+        o = ctypes.create_string_buffer(len(data))
+        uaes.ctr_crypt_range(256, key, iv, first, data, len(data), o)
+        assert o.raw == orc.ctr(key, iv, data, first_block=first), first
+
+
+# ---------------------------------------------------------------- seeded differential vs oracle
+
+SIZES = [0, 1, 15, 16, 17, 31, 32, 33, 255, 256, 257, 511, 512, 513, 4095, 4096, 4097,
+         16 * 255, 16 * 256 + 9, 65536 - 1, 65536, (1 << 20) + 5]
+
+
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_ctr_ecb_sizes(uaes, orc, bits):
+    a = uaes.MicroAES(bits)
+    for n in SIZES:
+        key, iv, data = rnd(f"s-k{bits}{n}", bits // 8), rnd(f"s-i{bits}{n}", 12), rnd(f"s-d{bits}{n}", n)
+        assert a.AES_CTR_encrypt(key, iv, data) == orc.ctr(key, iv, data), n
+        assert a.AES_ECB_encrypt(key, data) == orc.ecb_encrypt(key, data), n
+        assert a.AES_ECB_decrypt(key, data) == orc.ecb_decrypt(key, data), n
+
+
+@pytest.mark.parametrize("bits", [128, 256])
+def test_xts_sizes(uaes, orc, bits):
+    a = uaes.MicroAES(bits)
+    for n in [s for s in SIZES if s >= 16] + [16 * 1024 * 40 + 3, (1 << 22) + 15]:
+        keys, tw, data = rnd(f"x-k{bits}{n}", bits // 4), rnd(f"x-t{bits}{n}", 16), rnd(f"x-d{bits}{n}", n)
+        want = orc.xts(keys, tw, data)
+        assert a.AES_XTS_encrypt(keys, tw, data) == want, n
+        assert a.AES_XTS_decrypt(keys, tw, want[1]) == (0, data), n
+    assert a.AES_XTS_encrypt(rnd("x-k", bits // 4), bytes(16), b"short") == (1, b"\0" * 5)   # M_DATALENGTH_ERROR
+    keys, data = rnd("x-k0", bits // 4), rnd("x-d0", 80)
+    assert a.AES_XTS_encrypt(keys, None, data) == orc.xts(keys, None, data)    # NULL tweak = sector 0
+
+
+@pytest.mark.parametrize("bits", [128, 256])
+def test_xts_sectors(uaes, orc, bits):
+    for first, sb, ns in ((0, 512, 100), ((1 << 32) - 5, 512, 70), (3, 4096, 33), (99, 16, 1000),
+                          (1 << 60, 528, 65), (7, 8192, 5)):
+        keys, data = rnd(f"xs-k{bits}{first}", bits // 4), rnd(f"xs-d{bits}{first}", sb * ns)
+        out = ctypes.create_string_buffer(len(data))
+        uaes.xts_sectors(bits, keys, first, sb, data, len(data), out, True)
+        assert (0, out.raw) == orc.xts_sectors(keys, first, sb, data), (first, sb, ns)
+        back = ctypes.create_string_buffer(len(data))
+        uaes.xts_sectors(bits, keys, first, sb, out.raw, len(data), back, False)
+        assert back.raw == data
+
+
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_gcm_sizes(uaes, orc, bits):
+    a = uaes.MicroAES(bits)
+    for n, alen in [(0, 0), (0, 13), (1, 0), (15, 1), (16, 16), (17, 90), (511, 20), (512, 0), (513, 31),
+                    (4096, 7), (16 * 255, 0), (16 * 257 + 3, 129), (65536 + 3, 20), ((1 << 20) + 5, 20),
+                    (3 * (1 << 20) + 1, 0)]:
+        key, nonce = rnd(f"g-k{bits}{n}", bits // 8), rnd(f"g-n{bits}{n}", 12)
+        aad, data = rnd(f"g-a{bits}{n}", alen), rnd(f"g-d{bits}{n}", n)
+        want = orc.gcm_encrypt(key, nonce, aad, data)
+        got = a.AES_GCM_encrypt(key, nonce, aad, data)
+        assert got[-16:] == want[-16:], (n, alen)
+        assert got == want, (n, alen)
+        assert a.AES_GCM_decrypt(key, nonce, aad, want) == (0, data), (n, alen)
+
+
+def test_gcm_auth_failure_leaves_output_untouched(uaes, orc):
+    a = uaes.MicroAES(128)
+    key, nonce, aad, data = rnd("af-k", 16), rnd("af-n", 12), rnd("af-a", 20), rnd("af-d", 1000)
+    enc = bytearray(orc.gcm_encrypt(key, nonce, aad, data))
+    for pos in (0, 500, len(enc) - 1):
+        bad = bytearray(enc)
+        bad[pos] ^= 0x10
+        rc, out = a.AES_GCM_decrypt(key, nonce, aad, bytes(bad))
+        assert rc == 0x1A and out == b"\xcc" * 1000            # micro_aes.c:1204-1208
+    rc, _ = a.AES_GCM_decrypt(key, nonce, aad + b"x", bytes(enc))
+    assert rc == 0x1A
+
+
+# ---------------------------------------------------------------- device pointers
+
+def test_device_pointers_inplace_and_misaligned(uaes, orc, torch):
+    key, iv = rnd("dp-k", 16), rnd("dp-i", 12)
+    n = 100000 + 7
+    data = rnd("dp-d", n)
+    want = orc.ctr(key, iv, data, first_block=5)
+    # aligned, out of place; bytes after the end must stay zero
+    src, dst = dev(torch, data), dev(torch, b"", pad=n)
+    uaes.ctr_crypt_range(128, key, iv, 5, src, n, dst)
+    torch.cuda.synchronize()
+    assert host(dst, 0, n) == want and host(dst, n, n + 16) == bytes(16)
+    # in place (micro_aes.h:520-526: in == out must work)
+    uaes.ctr_crypt_range(128, key, iv, 5, src, n, src)
+    assert host(src, 0, n) == want
+    # misaligned device pointers go through the staging path and still match
+    src = dev(torch, data, offset=3)
+    dst = dev(torch, b"", pad=n, offset=9)
+    uaes.ctr_crypt_range(128, key, iv, 5, src.data_ptr() + 3, n, dst.data_ptr() + 9)
+    assert host(dst, 9, 9 + n) == want and host(dst, 0, 9) == bytes(9)
+    # mixed: host in, device out
+    dst = dev(torch, b"", pad=n)
+    uaes.ctr_crypt_range(128, key, iv, 5, data, n, dst)
+    assert host(dst, 0, n) == want
+
+
+def test_device_gcm_xts_ecb(uaes, orc, torch):
+    key, nonce, aad = rnd("dg-k", 32), rnd("dg-n", 12), rnd("dg-a", 33)
+    n = (1 << 21) + 11
+    data = rnd("dg-d", n)
+    want = orc.gcm_encrypt(key, nonce, aad, data)
+    src, dst = dev(torch, data), dev(torch, b"", pad=n + 16)
+    uaes.gcm_encrypt(256, key, nonce, aad, src, n, dst)
+    assert host(dst, 0, n + 16) == want
+    back = dev(torch, b"", pad=n)
+    assert uaes.gcm_decrypt(256, key, nonce, aad, dst, n, back) == 0
+    assert host(back, 0, n) == data
+    dst[n + 3] ^= 1                                            # corrupt the tag on the device
+    untouched = dev(torch, b"\xaa" * n)
+    assert uaes.gcm_decrypt(256, key, nonce, aad, dst, n, untouched) == 0x1A
+    assert host(untouched, 0, n) == b"\xaa" * n
+
+    keys, tw = rnd("dx-k", 64), rnd("dx-t", 16)
+    want = orc.xts(keys, tw, data)[1]
+    src = dev(torch, data)
+    uaes.xts_unit(256, keys, tw, src, n, src, True)            # in place, with stealing
+    assert host(src, 0, n) == want
+    uaes.xts_unit(256, keys, tw, src, n, src, False)
+    assert host(src, 0, n) == data
+
+    m = n - n % 512
+    want = orc.xts_sectors(keys, 77, 512, data[:m])[1]
+    uaes.xts_sectors(256, keys, 77, 512, src, m, src, True)
+    assert host(src, 0, m) == want
+
+    src = dev(torch, data)
+    dst = dev(torch, b"", pad=n + 16)
+    uaes.ecb(192, key[:24], src, n, dst, True)
+    assert host(dst, 0, (n + 15) // 16 * 16) == orc.ecb_encrypt(key[:24], data)
+
+
+def test_large_host_buffers_use_chunked_pipeline(uaes, orc):
+    """> 3 staging chunks of 32 MiB, ragged: exercises slot reuse and the counter offset per chunk"""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    n = 100 * (1 << 20) + 13
+    data = orc.splitmix(0xABCDEF, 0, (n + 7) // 8)[:n]
+    key, iv = rnd("lh-k", 16), rnd("lh-i", 12)
+    got = uaes.MicroAES(128).AES_CTR_encrypt(key, iv, data)
+    piece = 1 << 20
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        parts = list(ex.map(lambda o: orc.ctr(key, iv, data[o:o + piece], first_block=o // 16), range(0, n, piece)))
+    assert got == b"".join(parts)
+
+
+def test_async_stream_api(uaes, orc, torch):
+    key, iv, data = rnd("as-k", 16), rnd("as-i", 12), rnd("as-d", 1 << 16)
+    s = torch.cuda.Stream()
+    src, dst = dev(torch, data), dev(torch, b"", pad=len(data))
+    uaes.set_stream(s.cuda_stream)
+    uaes.set_async(True)
+    try:
+        uaes.ctr_crypt_range(128, key, iv, 0, src, len(data), dst)
+        s.synchronize()
+    finally:
+        uaes.set_async(False)
+        uaes.set_stream(None)
+    assert host(dst, 0, len(data)) == orc.ctr(key, iv, data)
