@@ -206,8 +206,23 @@ def run_gpu(args):
     uaes.set_stream(stream.cuda_stream)
     uaes.fill_splitmix64(SEED, first_block * 2, src, nbytes // 8)
 
+    wl = args.workload
+    key32 = key + bytes(range(16))
+    keys64 = key32 + bytes(range(32, 64))
+    if wl == "gcm128":
+        dst = torch.empty(nbytes + 16, dtype=torch.uint8, device="cuda")
+
     def step():
-        uaes.ctr_crypt_range(128, key, iv, first_block, src, nbytes, dst)
+        if wl == "ctr128":
+            uaes.ctr_crypt_range(128, key, iv, first_block, src, nbytes, dst)
+        elif wl == "ctr256":
+            uaes.ctr_crypt_range(256, key32, iv, first_block, src, nbytes, dst)
+        elif wl == "ecb128":
+            uaes.ecb(128, key, src, nbytes, dst, True)
+        elif wl == "xts256":        # BASELINE config 3: 512-byte sectors, sector numbers follow the shard
+            uaes.xts_sectors(256, keys64, first_block // 32, 512, src, nbytes, dst, True)
+        elif wl == "gcm128":        # BASELINE config 4: one message per rank
+            uaes.gcm_encrypt(128, key, iv, b"", src, nbytes, dst)
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,6 +257,8 @@ def run_gpu(args):
     # ---- spot parity inside the bench: first and last 64 KiB of this rank's shard vs the oracle
     parity = None
     try:
+        if wl != "ctr128":
+            raise RuntimeError("spot check implemented for the headline workload only (see tests/)")
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from util import Oracle
         orc = Oracle()
@@ -257,6 +274,8 @@ def run_gpu(args):
     # ---- e2e: the reference-facing C ABI with HOST buffers, copies inside the timed region
     e2e = None
     try:
+        if args.no_e2e or wl != "ctr128":
+            raise RuntimeError("skipped (--no-e2e or secondary workload)")
         avail = mem_available_gib()
         e2e_gib = args.e2e_gib if args.e2e_gib else (args.gib_per_gpu if world == 1 else min(args.gib_per_gpu, 4))
         while e2e_gib > 0.25 and e2e_gib * world * 1.5 + 8 > avail:
@@ -298,16 +317,17 @@ def run_gpu(args):
         achieved = 2 * nbytes / (kernel_ms / 1e3) / 1e9        # 32 algorithmic bytes per 16-byte block
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ctr_traffic.json")))["dram_bytes_per_launch_16GiB"]
+            if wl == "ctr128" and nbytes == 16 * GIB:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ctr_traffic.json")))["dram_bytes_per_launch_16GiB"]
         except Exception:
             pass
-        cpu = cpu_throughput(slice_mib=args.cpu_slice_mib, reps=1) if world == 1 and not args.no_cpu else None
+        cpu = cpu_throughput(slice_mib=args.cpu_slice_mib, reps=1) if world == 1 and not args.no_cpu and wl == "ctr128" else None
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC if wl == "ctr128" else f"{wl} throughput, {args.gib_per_gpu:g} GiB per B200", "value": round(value, 2), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"AES-128-CTR, {args.gib_per_gpu:g} GiB per GPU, out of place, device resident "
+            "config": {"workload": f"{'AES-128-CTR' if wl == 'ctr128' else wl}, {args.gib_per_gpu:g} GiB per GPU, out of place, device resident "
                                    f"(BASELINE config {'4 (16 GiB, 1 B200)' if world == 1 else '5 (sharded by counter range)'})",
                        "bytes_per_gpu": nbytes, "total_bytes": nbytes * world,
                        "sharding": "contiguous keystream-block range per rank; NCCL broadcast of key||iv only",
@@ -315,7 +335,9 @@ def run_gpu(args):
                        "input": f"splitmix64(seed=0x{SEED:x}) generated on device"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "uaes::ctr_kernel<10>", "kernel_ms": round(kernel_ms, 4),
+                         "kernel": {"ctr128": "uaes::ctr_kernel<10>", "ctr256": "uaes::ctr_kernel<14>", "ecb128": "uaes::ecb_kernel<10,true>",
+                                    "xts256": "uaes::xts_sectors_kernel<14,true>", "gcm128": "uaes::gcm_bulk_kernel<10,false>"}[wl],
+                         "kernel_ms": round(kernel_ms, 4),
                          "algorithmic_bytes_per_launch": 2 * nbytes},
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "parity_spot_check": parity,
@@ -335,7 +357,10 @@ def main():
     ap.add_argument("--e2e-gib", type=float, default=0.0, help="host buffer for the e2e leg (default: auto)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-slice-mib", type=int, default=256)
+    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "xts256", "gcm128"],
+                    help="ctr128 is the headline (BASELINE.json metric); the others are the secondary configs")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

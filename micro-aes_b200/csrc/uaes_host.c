@@ -488,7 +488,10 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *a
     pthread_mutex_lock(&g_lock);
     if ((rc = get_ctx(&c)) != 0) goto done;
 
-    direct = len == 0 || (is_direct(in) && is_direct(out));
+    /* the kernels write ciphertext and tag through `out` and read `in`: both must be device memory
+     * for the zero-copy path (an empty message still has a tag to write when encrypting) */
+    if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
+    else         direct = is_direct(out) && (len == 0 || is_direct(in));
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
     wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + aadlen + 64;
     if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM work)")) != 0) goto done;

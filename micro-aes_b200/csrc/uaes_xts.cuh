@@ -129,7 +129,9 @@ template <int NR, bool ENC>
 __global__ void __launch_bounds__(kThreads, 1) xts_unit_kernel(const __grid_constant__ XtsUnitArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
-    __shared__ uint32_t t0s[4];
+    // T_0 is handed to the other warps through the last 16 bytes of the dynamic window (the tables
+    // end at least 35 KB earlier); static shared memory would push the launch over the 227 KB limit
+    volatile uint32_t *t0s = (volatile uint32_t *)(dyn + dyn_smem_size() - 16);
     if (threadIdx.x == 0) {                                   // T_0 = E_K2(tweak), micro_aes.c:1026-1027
         uint32_t s[4] = {a.tweak[0], a.tweak[1], a.tweak[2], a.tweak[3]};
         small_encrypt(a.k2.w, a.k2.rounds, s);

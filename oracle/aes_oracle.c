@@ -417,6 +417,11 @@ static void ghash_absorb(const uint8_t H[16], const uint8_t *x, size_t len, uint
     }
 }
 
+void oracle_ghash_absorb(const uint8_t H[16], const void *data, size_t len, uint8_t state[16])
+{
+    ghash_absorb(H, (const uint8_t *)data, len, state);
+}
+
 /* micro_aes.c:1127-1137 (gHash) */
 void oracle_ghash(const uint8_t H[16], const void *aad, size_t aadlen,
                   const void *ct, size_t ctlen, uint8_t out[16])

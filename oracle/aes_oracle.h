@@ -73,6 +73,9 @@ int  oracle_gcm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12]
 /* GHASH(H; aad, ct) including the length block (micro_aes.c:1127-1137) */
 void oracle_ghash(const uint8_t H[16], const void *aad, size_t aadlen,
                   const void *ct, size_t ctlen, uint8_t out[16]);
+/* state <- xMac(data) with mix = mulGF128(H, .): the absorb loop alone (micro_aes.c:551-570),
+ * so a long message can be hashed in pieces and recombined with powers of H */
+void oracle_ghash_absorb(const uint8_t H[16], const void *data, size_t len, uint8_t state[16]);
 /* y <- x*y in GCM's GF(2^128) (micro_aes.c:476-493) */
 void oracle_gf128_mul(const uint8_t x[16], uint8_t y[16]);
 /* T <- alpha*T in XTS's GF(2^128) (micro_aes.c:449-458) */

@@ -1,0 +1,23 @@
+"""Drop-in acceptance on the GPU: the reference's own self-test program (main.c), built in the
+build container against include/micro_aes.h and linked against libmicro_aes_<bits>.so in place of
+micro_aes.c (oracle/Makefile target `dropin`), must print PASSED for every hot-path mode."""
+import os
+import subprocess
+
+import pytest
+
+from util import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("bits,modes", [(128, ["ECB", "CTR", "XTS", "GCM"]), (256, ["XTS", "GCM"])])
+def test_reference_main_c_passes_against_our_library(bits, modes):
+    exe = os.path.join(ROOT, "oracle", "_ref", f"dropin_main_{bits}")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_main_* not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    assert "FAILED" not in out, out
+    for m in modes:
+        assert f"AES-{bits} {m} encryption: PASSED!" in out, out
+        assert f"AES-{bits} {m} decryption: PASSED!" in out, out

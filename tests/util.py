@@ -51,6 +51,7 @@ class Oracle:
         L.oracle_gcm_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_ghash.argtypes = [_u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_gf128_mul.argtypes = [_u8p, _u8p]
+        L.oracle_ghash_absorb.argtypes = [_u8p, ctypes.c_void_p, _sz, _u8p]
         L.oracle_xts_double.argtypes = [_u8p]
         L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
 
@@ -116,6 +117,24 @@ class Oracle:
         o = self._buf(16)
         self.lib.oracle_ghash(H, aad, len(aad), ct, len(ct), o)
         return o.raw[:16]
+
+    def ghash_absorb(self, H, data_ptr, nbytes, state=bytes(16)):
+        """data_ptr: address (int) or bytes"""
+        o = ctypes.create_string_buffer(state, 16)
+        if isinstance(data_ptr, (bytes, bytearray)):
+            data_ptr = ctypes.cast(ctypes.c_char_p(bytes(data_ptr)), ctypes.c_void_p).value
+        self.lib.oracle_ghash_absorb(H, data_ptr, nbytes, o)
+        return o.raw[:16]
+
+    def gf128_pow(self, x, e):
+        """x^e by square and multiply with the oracle's mulGF128"""
+        r, b = b"\x80" + bytes(15), x
+        while e:
+            if e & 1:
+                r = self.gf128_mul(b, r)
+            b = self.gf128_mul(b, b)
+            e >>= 1
+        return r
 
     def gf128_mul(self, x, y):
         o = ctypes.create_string_buffer(y, 16)
