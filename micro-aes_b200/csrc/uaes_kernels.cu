@@ -10,6 +10,7 @@
 //   * round keys are kernel arguments (constant bank), no per-launch symbol copies.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "uaes_core.cuh"
 #include "uaes_gf128.cuh"
@@ -84,14 +85,25 @@ struct CtrArgs {
 };
 
 // Work unit = a "group": the 256 counter values that share bytes 0..14 of the counter block.
-// Inside a group only byte 15 changes, so AddRoundKey(0), 15/16 of round 1 and 12/16 of round 2
-// are the same for all 256 blocks: the warp computes them once per group (27 lookups) and every
-// block then needs 1 + 4 lookups for rounds 1-2 instead of 32.  Rounds 3..NR are the plain
-// 16-lookup rounds.  Lane l takes counters with low byte = 32*it + l, it = 0..7, i.e. 8 coalesced
-// 512-byte rows per group.
-template <int NR>
-__global__ void __launch_bounds__(kThreads, 1) ctr_kernel(const __grid_constant__ CtrArgs a)
+// Inside a group only byte 15 changes, and the cipher's first two rounds factor accordingly:
+//
+//   round 1: column 0 = K0 ^ Te3[S-box input of byte 15]; columns 1..3 (C1..C3) do not see byte 15.
+//            K0 depends on counter bytes 0, 5, 10 only -> constant for 2^40 consecutive blocks.
+//   round 2: column j = D_j ^ Te_x[one byte of column 0].  The Te_x term is a function of byte 15
+//            (and K0) alone, so a lane that always serves the same byte-15 values keeps those four
+//            words per value in REGISTERS for the whole launch (U[it][0..3] below).
+//            D_j = E_j ^ Te_y[a byte of C1]; C1 follows counter byte 14 (one lookup per group), the
+//            E_j follow bytes 12..13 (recomputed every 256 groups).
+//
+// So rounds 1-2 cost 5 lookups per GROUP HALF (4 rows) instead of 32 per block, and every block
+// pays only the 16 x (NR-2) lookups of rounds 3..NR -- the shared-memory pipe is the roof
+// (profiles/), so lookups are what is worth saving.  A warp serves one half of a group (rows
+// it = 0..3: byte 15 = 128*half + 32*it + lane) and walks a CONTIGUOUS run of groups so that the
+// slow-changing constants really are constant; its partner warp serves the other half.
+template <int NR, int kCtrThreads>
+__global__ void __launch_bounds__(kCtrThreads, 1) ctr_kernel(const __grid_constant__ CtrArgs a)
 {
+    constexpr int kCtrWarps = kCtrThreads / 32;
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_tables<true>(dyn);
     const uint32_t *rk = a.ks.w;
@@ -100,45 +112,65 @@ __global__ void __launch_bounds__(kThreads, 1) ctr_kernel(const __grid_constant_
     const uint32_t lowoff = (uint32_t)a.v0 & 255u;
     const uint64_t g0 = a.v0 >> 8;
     const uint64_t ngroups = (lowoff + a.nblocks + 255) >> 8;
-    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerCta;
-    uint64_t j = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const uint64_t wg = (uint64_t)blockIdx.x * kCtrWarps + (threadIdx.x >> 5);
+    const uint32_t half = (uint32_t)wg & 1u;
+    const uint64_t npairs = (uint64_t)gridDim.x * (kCtrWarps / 2);
+    const uint64_t per = (ngroups + npairs - 1) / npairs;
+    const uint64_t j0 = (wg >> 1) * per;
+    const uint64_t j1 = j0 + per < ngroups ? j0 + per : ngroups;
+    const uint32_t b15 = half * 128 + lane;                   // + 32 * it
 
     // block index handled by this lane in row `it` of group j; valid iff 0 <= k < nblocks
     auto kof = [&](uint64_t grp, int it) -> int64_t {
-        return (int64_t)(grp << 8) + it * 32 + (int64_t)lane - (int64_t)lowoff;
+        return (int64_t)(grp << 8) + (int64_t)(b15 + 32 * it) - (int64_t)lowoff;
     };
     auto fetch = [&](uint64_t grp, int it) -> uint4 {
         const int64_t k = kof(grp, it);
-        if (grp < ngroups && k >= 0 && (uint64_t)k < a.nblocks) return ld_stream(a.in + k);
+        if (grp < j1 && k >= 0 && (uint64_t)k < a.nblocks) return ld_stream(a.in + k);
         return make_uint4(0, 0, 0, 0);
     };
 
-    uint4 cur = fetch(j, 0);
-    for (; j < ngroups; j += nwarps) {
-        // ---- per-group constants
-        uint32_t w2, w3;
-        ctr_words(a.b8, ((g0 + j) << 8) & kMask56, w2, w3);
-        const uint32_t s0 = a.w0 ^ rk[0], s1 = a.w1 ^ rk[1], s2 = w2 ^ rk[2], s3 = w3 ^ rk[3];
-        const uint32_t K0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ rk[4];
-        const uint32_t C1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<2, kOffT2>(lb, s3) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
-        const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
-        const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
-        const uint32_t D0 = lut<1, kOffT1>(lb, C1) ^ lut<2, kOffT2>(lb, C2) ^ lut<3, kOffT3>(lb, C3) ^ rk[8];
-        const uint32_t D1 = lut<0, kOffT0>(lb, C1) ^ lut<1, kOffT1>(lb, C2) ^ lut<2, kOffT2>(lb, C3) ^ rk[9];
-        const uint32_t D2 = lut<0, kOffT0>(lb, C2) ^ lut<1, kOffT1>(lb, C3) ^ lut<3, kOffT3>(lb, C1) ^ rk[10];
-        const uint32_t D3 = lut<0, kOffT0>(lb, C3) ^ lut<2, kOffT2>(lb, C1) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+    uint64_t tag40 = ~0ull, tag16 = ~0ull;
+    uint32_t U[4][4], Cp1 = 0, E0 = 0, E1 = 0, E2 = 0, E3 = 0;
+    const uint32_t s0 = a.w0 ^ rk[0], s1 = a.w1 ^ rk[1];
 
-#pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-            const uint4 nxt = it < 7 ? fetch(j, it + 1) : fetch(j + nwarps, 0);
+    uint4 cur = fetch(j0, 0);
+    for (uint64_t j = j0; j < j1; ++j) {
+        const uint64_t vg = ((g0 + j) << 8) & kMask56;
+        uint32_t w2, w3;
+        ctr_words(a.b8, vg, w2, w3);
+        const uint32_t s2 = w2 ^ rk[2], s3 = w3 ^ rk[3];         // byte 15 of the counter is 0 here
+        if ((vg >> 40) != tag40) {                               // once per launch in practice
+            tag40 = vg >> 40;
+            const uint32_t K0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ rk[4];
+            Cp1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t c0 = K0 ^ lut<3, kOffT3>(lb, s3 ^ ((b15 + 32 * it) << 24));
+                U[it][0] = lut<0, kOffT0>(lb, c0); U[it][1] = lut<3, kOffT3>(lb, c0);
+                U[it][2] = lut<2, kOffT2>(lb, c0); U[it][3] = lut<1, kOffT1>(lb, c0);
+            }
+            tag16 = ~0ull;
+        }
+        if ((vg >> 16) != tag16) {                               // every 256 groups
+            tag16 = vg >> 16;
+            const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
+            const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
+            E0 = lut<2, kOffT2>(lb, C2) ^ lut<3, kOffT3>(lb, C3) ^ rk[8];
+            E1 = lut<1, kOffT1>(lb, C2) ^ lut<2, kOffT2>(lb, C3) ^ rk[9];
+            E2 = lut<0, kOffT0>(lb, C2) ^ lut<1, kOffT1>(lb, C3) ^ rk[10];
+            E3 = lut<0, kOffT0>(lb, C3) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+        }
+        // per group: counter byte 14 enters through column 1 of round 1
+        const uint32_t C1 = Cp1 ^ lut<2, kOffT2>(lb, s3);
+        const uint32_t D0 = E0 ^ lut<1, kOffT1>(lb, C1), D1 = E1 ^ lut<0, kOffT0>(lb, C1);
+        const uint32_t D2 = E2 ^ lut<3, kOffT3>(lb, C1), D3 = E3 ^ lut<2, kOffT2>(lb, C1);
+
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const uint4 nxt = it < 3 ? fetch(j, it + 1) : fetch(j + 1, 0);
             const int64_t k = kof(j, it);
-            // round 1, column 0: the only column that sees byte 15 of the counter
-            const uint32_t c0 = K0 ^ lut<3, kOffT3>(lb, s3 ^ ((uint32_t)(it * 32 + lane) << 24));
-            // round 2: one varying byte per column
-            uint32_t t0 = D0 ^ lut<0, kOffT0>(lb, c0);
-            uint32_t t1 = D1 ^ lut<3, kOffT3>(lb, c0);
-            uint32_t t2 = D2 ^ lut<2, kOffT2>(lb, c0);
-            uint32_t t3 = D3 ^ lut<1, kOffT1>(lb, c0);
+            uint32_t t0 = D0 ^ U[it][0], t1 = D1 ^ U[it][1], t2 = D2 ^ U[it][2], t3 = D3 ^ U[it][3];
             enc_finish<NR, 3>(lb, t0, t1, t2, t3, rk, cur.x, cur.y, cur.z, cur.w);
             if (k >= 0 && (uint64_t)k < a.nblocks) st_stream(a.out + k, make_uint4(t0, t1, t2, t3));
             cur = nxt;
@@ -256,15 +288,38 @@ static unsigned grid_for(uint64_t warp_units)
     return (unsigned)(need < 1 ? 1 : need < sms ? need : sms);
 }
 
+template <int NR, int kCtrThreads>
+static cudaError_t launch_ctr_nt(const CtrArgs &a, cudaStream_t st)
+{
+    constexpr int kCtrWarps = kCtrThreads / 32;
+    cudaError_t e = opt_in_smem(ctr_kernel<NR, kCtrThreads>);
+    if (e != cudaSuccess) return e;
+    const uint64_t ngroups = (((uint32_t)a.v0 & 255u) + a.nblocks + 255) >> 8;
+    // a pair of warps per group; at least 4 groups per pair before another CTA is worth its table fill
+    const uint64_t ctas = (ngroups + 4 * (kCtrWarps / 2) - 1) / (4 * (kCtrWarps / 2));
+    const uint64_t sms = (uint64_t)sm_count();
+    ctr_kernel<NR, kCtrThreads><<<(unsigned)(ctas < 1 ? 1 : ctas < sms ? ctas : sms), kCtrThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// CTA size of the CTR kernel: registers per thread trade against warps per SM (768 threads = 80
+// registers, no spills).  UAES_CTR_THREADS overrides it for tuning runs.
 template <int NR>
 static cudaError_t launch_ctr_nr(const CtrArgs &a, cudaStream_t st)
 {
-    cudaError_t e = opt_in_smem(ctr_kernel<NR>);
-    if (e != cudaSuccess) return e;
-    const uint64_t ngroups = (((uint32_t)a.v0 & 255u) + a.nblocks + 255) >> 8;
-    ctr_kernel<NR><<<grid_for(ngroups), kThreads, kDynSmem, st>>>(a);
-    ++g_launches;
-    return cudaGetLastError();
+    static int threads = 0;
+    if (!threads) {
+        const char *e = getenv("UAES_CTR_THREADS");
+        threads = e ? atoi(e) : 768;
+    }
+    switch (threads) {
+    case 1024: return launch_ctr_nt<NR, 1024>(a, st);
+    case 896:  return launch_ctr_nt<NR, 896>(a, st);
+    case 640:  return launch_ctr_nt<NR, 640>(a, st);
+    case 512:  return launch_ctr_nt<NR, 512>(a, st);
+    default:   return launch_ctr_nt<NR, 768>(a, st);
+    }
 }
 
 template <int NR, bool ENC>
