@@ -17,7 +17,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(_HERE, "lib")
+LIBDIR = os.environ.get("UAES_LIBDIR") or os.path.join(_HERE, "lib")   # override: tuning builds only
 
 M_RESULT_SUCCESS = 0
 M_DATALENGTH_ERROR = 0x01

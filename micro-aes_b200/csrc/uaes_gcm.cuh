@@ -4,8 +4,9 @@
 // 551-570, 476-493).  The reference makes two serial passes (CTR, then a bit-serial GHASH chain
 // G <- H*(G ^ X_i)).  Here ONE pass reads the plaintext once and writes the ciphertext once:
 //
-//   GHASH(X_0..X_{n-1}) = sum_i X_i * H^(n-i)  is split into chunks of CB = 32 * 2^kr blocks,
-//   aligned to the END of the message (a short first chunk is a full one with leading zeros).
+//   GHASH(X_0..X_{n-1}) = sum_i X_i * H^(n-i)  is split into one chunk of CB = 32*R blocks per warp
+//   of the persistent grid (R rows, sized so that every warp gets the same share), aligned to the
+//   END of the message (a short first chunk is a full one with leading zeros).
 //   Inside a chunk lane l of the warp owns blocks = l (mod 32) in counter space and runs
 //   Horner with the fixed multiplier C = H^32:   y_l <- y_l * C ^ X.
 //   The multiply-by-constant is a byte-serial table walk (Shoup): 16 lookups of M[b] = b(x)*C
@@ -13,7 +14,8 @@
 //   and 15 lookups of the key-independent reduction R[d] = d(x)*x^128 (lane replicated).
 //   At the end of a chunk lane l scales y_l by H^(distance to the chunk end) in 1..32 (one
 //   generic product per chunk) and the warp XOR-reduces by shuffle into one 16-byte partial.
-//   A last small kernel folds the partials pairwise with P = H^CB, P^2, P^4, ... , absorbs the
+//   A last small kernel folds the partials pairwise with P = H^CB, P^2, P^4, ... (carry-less
+//   multiplies built from integer multiplies, gf_mul_fast), absorbs the
 //   ragged tail block and the length block and writes  tag = E_K(J0) ^ GHASH.
 //
 //   The AAD enters as the initial GHASH state, which is simply XORed into block 0.
@@ -71,13 +73,13 @@ __global__ void gcm_setup_kernel(const __grid_constant__ GcmSetupArgs a)
     }
     __syncwarp();
     if (lane == 0)
-        for (int i = 1; i < 6; ++i) sq[i] = gf_mul(sq[i - 1], sq[i - 1]);
+        for (int i = 1; i < 6; ++i) sq[i] = gf_mul_fast(sq[i - 1], sq[i - 1]);
     __syncwarp();
     {
         const uint32_t e = lane + 1;                         // H^e
         Gf p{0x8000000000000000ull, 0};                      // the field's 1
         for (int i = 0; i < 6; ++i)
-            if (e >> i & 1) p = gf_mul(p, sq[i]);
+            if (e >> i & 1) p = gf_mul_fast(p, sq[i]);
         a.work->lanepow[lane] = gf_store(p);
         if (e == 32) a.work->C32 = gf_store(p);
     }
@@ -88,7 +90,7 @@ __global__ void gcm_setup_kernel(const __grid_constant__ GcmSetupArgs a)
             const uint64_t left = a.aadlen - off;
             const Gf x = gf_load(load_block_bytes(a.aad + off, left < 16 ? (uint32_t)left : 16));
             g.hi ^= x.hi; g.lo ^= x.lo;
-            g = gf_mul(H, g);
+            g = gf_mul_fast(H, g);
         }
         a.work->aad_state = gf_store(g);
     }
@@ -103,12 +105,14 @@ struct GcmBulkArgs {
     const uint4 *in;
     uint4 *out;
     uint64_t nblocks;            // FULL blocks only; the ragged tail is done by the finish kernel
-    uint32_t kr;                 // chunk = 32 << kr blocks
+    uint64_t chunk_blocks;       // CB = 32 * rows per chunk
     uint64_t nchunks;
     GcmWork *work;
 };
 
 constexpr uint32_t kGhashRegion = 32768;                 // M table and R table, 32 KiB each
+constexpr int kGcmThreads = 768;                         // 85 registers per thread: no spills; the
+constexpr int kGcmWarps = kGcmThreads / 32;              // lookup pipe saturates from 16 warps up
 
 // y <- y * C, y as four memory-order words; mb = M base | (lane&7)*16, rb = R base | lane*4
 __device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t rb, uint32_t &y0, uint32_t &y1,
@@ -138,7 +142,7 @@ __device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t rb, uint32
 }
 
 template <int NR, bool HASH_ONLY>
-__global__ void __launch_bounds__(kThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
+__global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
     // ---- shared memory map: AES tables 64 KiB aligned, GHASH tables in the 32 KiB-aligned gaps
@@ -174,14 +178,14 @@ __global__ void __launch_bounds__(kThreads, 1) gcm_bulk_kernel(const __grid_cons
     asm volatile("" : "+r"(lb), "+r"(mb), "+r"(rb)::"memory");
 
     const uint32_t *rk = a.ks.w;
-    const uint64_t CB = 32ull << a.kr;
-    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerCta;
+    const uint64_t CB = a.chunk_blocks;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kGcmWarps;
     const uint4 aad_state = a.work->aad_state;
 
     uint64_t cur_group = ~0ull;
     uint32_t s3 = 0, K0 = 0, D0 = 0, D1 = 0, D2 = 0, D3 = 0;
 
-    for (uint64_t c = (uint64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); c < a.nchunks; c += nwarps) {
+    for (uint64_t c = (uint64_t)blockIdx.x * kGcmWarps + (threadIdx.x >> 5); c < a.nchunks; c += nwarps) {
         // chunk c ends (NC-1-c) chunks before the end of the message
         const uint64_t b1 = a.nblocks - (a.nchunks - 1 - c) * CB;
         const uint64_t b0 = b1 > CB ? b1 - CB : 0;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcm_bulk_kernel(const __grid_cons
 
         // lane l holds sum_j X_(l+32j) * C^(J-j); scale by H^(b1 - klast) and reduce over the warp
         Gf z{0, 0};
-        if (any) z = gf_mul(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]), gf_from_words(y0, y1, y2, y3));
+        if (any) z = gf_mul_fast(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]), gf_from_words(y0, y1, y2, y3));
         for (int o = 16; o; o >>= 1) {
             z.hi ^= __shfl_xor_sync(0xffffffffu, z.hi, o);
             z.lo ^= __shfl_xor_sync(0xffffffffu, z.lo, o);
@@ -255,30 +259,31 @@ struct GcmFinishArgs {
     const uint8_t *in;
     uint8_t *out;
     uint64_t len, aadlen;
-    uint32_t kr;
-    uint64_t nchunks;
+    uint64_t nparts, chunk_rows; // partials left by the bulk kernel; neighbours are H^(32*rows) apart
     int hash_only;
     uint8_t *tag_out;            // 16 bytes, any alignment
     GcmWork *work;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) gcm_finish_kernel(const __grid_constant__ GcmFinishArgs a)
+constexpr int kFinThreads = 256;     // latency-bound tree over <= one partial per warp of the grid
+
+__global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid_constant__ GcmFinishArgs a)
 {
     uint4 *slot = a.work->partials;
-    // P = H^CB = (H^32)^(2^kr); every thread squares along (no broadcast needed)
-    Gf P = gf_load(a.work->C32);
-    for (uint32_t i = 0; i < a.kr; ++i) P = gf_mul(P, P);
+    // multiplier between neighbouring partials: H^(chunk blocks) = (H^32)^rows; every thread
+    // computes it for itself (no broadcast needed)
+    Gf P = gf_pow_fast(gf_load(a.work->C32), a.chunk_rows);
 
-    // slot[i] = partial of the i-th chunk counted from the end; total = sum_i slot[i] * P^i
-    for (uint64_t n = a.nchunks; n > 1; n = (n + 1) / 2) {
+    // slot[i] = partial of the i-th run counted from the end; total = sum_i slot[i] * P^i
+    for (uint64_t n = a.nparts; n > 1; n = (n + 1) / 2) {
         const uint64_t half = (n + 1) / 2;
-        for (uint64_t base = 0; base < half; base += kThreads) {
+        for (uint64_t base = 0; base < half; base += kFinThreads) {
             const uint64_t m = base + threadIdx.x;
             Gf f{0, 0};
             if (m < half) {
                 f = gf_load(slot[2 * m]);
                 if (2 * m + 1 < n) {
-                    const Gf g = gf_mul(P, gf_load(slot[2 * m + 1]));
+                    const Gf g = gf_mul_fast(P, gf_load(slot[2 * m + 1]));
                     f.hi ^= g.hi; f.lo ^= g.lo;
                 }
             }
@@ -286,12 +291,12 @@ __global__ void __launch_bounds__(kThreads, 1) gcm_finish_kernel(const __grid_co
             if (m < half) slot[m] = gf_store(f);
             __syncthreads();
         }
-        P = gf_mul(P, P);
+        P = gf_mul_fast(P, P);
     }
 
     if (threadIdx.x != 0) return;
     const Gf H = gf_load(a.work->H);
-    Gf S = a.nchunks ? gf_load(slot[0]) : gf_load(a.work->aad_state);
+    Gf S = a.nparts ? gf_load(slot[0]) : gf_load(a.work->aad_state);
 
     const uint64_t nfull = a.len / 16;
     const uint32_t tail = (uint32_t)(a.len % 16);
@@ -313,11 +318,11 @@ __global__ void __launch_bounds__(kThreads, 1) gcm_finish_kernel(const __grid_co
         }
         const Gf x = gf_load(ct);
         S.hi ^= x.hi; S.lo ^= x.lo;
-        S = gf_mul(H, S);
+        S = gf_mul_fast(H, S);
     }
     // length block: BE64(8*aadlen) || BE64(8*len)   (micro_aes.c:1130-1132)
     S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
-    S = gf_mul(H, S);
+    S = gf_mul_fast(H, S);
     const uint4 ej0 = a.work->EJ0;
     uint4 tag = gf_store(S);
     tag.x ^= ej0.x; tag.y ^= ej0.y; tag.z ^= ej0.z; tag.w ^= ej0.w;
@@ -325,25 +330,30 @@ __global__ void __launch_bounds__(kThreads, 1) gcm_finish_kernel(const __grid_co
     for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
 }
 
+static unsigned gcm_grid(uint64_t nchunks)
+{
+    const uint64_t need = (nchunks + kGcmWarps - 1) / kGcmWarps, sms = (uint64_t)sm_count();
+    return (unsigned)(need < 1 ? 1 : need < sms ? need : sms);
+}
+
 template <int NR, bool HASH_ONLY>
 static cudaError_t launch_gcm_bulk_nr(const GcmBulkArgs &a, cudaStream_t st)
 {
     cudaError_t e = opt_in_smem(gcm_bulk_kernel<NR, HASH_ONLY>);
     if (e != cudaSuccess) return e;
-    gcm_bulk_kernel<NR, HASH_ONLY><<<grid_for(a.nchunks), kThreads, kDynSmem, st>>>(a);
+    gcm_bulk_kernel<NR, HASH_ONLY><<<gcm_grid(a.nchunks), kGcmThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
 
-// rows per chunk = 2^kr: big enough to amortise the per-chunk scaling (one generic product),
-// small enough that every warp of the grid gets at least two chunks
-static uint32_t gcm_pick_kr(uint64_t nblocks)
+// One chunk per warp of the persistent grid: R rows each, so that all warps get the same share
+// (the first chunk in message order is the short one).  Small messages get one row per chunk.
+static void gcm_plan(uint64_t nblocks, uint64_t &rows_per_chunk, uint64_t &nchunks)
 {
     const uint64_t rows = (nblocks + 31) / 32;
-    const uint64_t warps = (uint64_t)sm_count() * kWarpsPerCta;
-    uint32_t kr = 0;
-    while (kr < 8 && (rows >> (kr + 1)) >= 2 * warps) ++kr;
-    return kr;
+    const uint64_t warps = (uint64_t)sm_count() * kGcmWarps;
+    rows_per_chunk = rows ? (rows + warps - 1) / warps : 1;
+    nchunks = rows ? (nblocks + 32 * rows_per_chunk - 1) / (32 * rows_per_chunk) : 0;
 }
 
 }  // namespace uaes
@@ -351,10 +361,8 @@ static uint32_t gcm_pick_kr(uint64_t nblocks)
 extern "C" size_t uaes_gcm_work_bytes(u64 len)
 {
     using namespace uaes;
-    const uint64_t nblocks = len / 16;
-    const uint32_t kr = gcm_pick_kr(nblocks);
-    const uint64_t CB = 32ull << kr;
-    const uint64_t nchunks = (nblocks + CB - 1) / CB;
+    uint64_t rows_per_chunk, nchunks;
+    gcm_plan(len / 16, rows_per_chunk, nchunks);
     return sizeof(GcmWork) + (size_t)nchunks * sizeof(uint4);
 }
 
@@ -365,9 +373,8 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     using namespace uaes;
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t nblocks = len / 16;
-    const uint32_t kr = gcm_pick_kr(nblocks);
-    const uint64_t CB = 32ull << kr;
-    const uint64_t nchunks = (nblocks + CB - 1) / CB;
+    uint64_t rows_per_chunk, nchunks;
+    gcm_plan(nblocks, rows_per_chunk, nchunks);
 
     uint32_t j0[4];
     for (int c = 0; c < 3; ++c)
@@ -393,7 +400,7 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
         b.ks = *ks;
         b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = (vj0 + 1) & kMask56;
         b.in = (const uint4 *)in; b.out = (uint4 *)out;
-        b.nblocks = nblocks; b.kr = kr; b.nchunks = nchunks; b.work = (GcmWork *)work;
+        b.nblocks = nblocks; b.chunk_blocks = 32 * rows_per_chunk; b.nchunks = nchunks; b.work = (GcmWork *)work;
         switch (ks->rounds * 2 + (hash_only ? 1 : 0)) {
         case 20: e = launch_gcm_bulk_nr<10, false>(b, st); break;
         case 21: e = launch_gcm_bulk_nr<10, true>(b, st); break;
@@ -410,9 +417,9 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     f.ks = *ks;
     f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1) & kMask56;
     f.in = (const uint8_t *)in; f.out = (uint8_t *)out;
-    f.len = len; f.aadlen = aadlen; f.kr = kr; f.nchunks = nchunks; f.hash_only = hash_only;
+    f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.hash_only = hash_only;
     f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
-    gcm_finish_kernel<<<1, kThreads, 0, st>>>(f);
+    gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
     ++g_launches;
     return (int)cudaGetLastError();
 }

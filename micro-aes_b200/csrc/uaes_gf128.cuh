@@ -127,6 +127,67 @@ __device__ __forceinline__ void gf_to_words(Gf g, uint32_t &w0, uint32_t &w1, ui
     w0 = (uint32_t)a; w1 = (uint32_t)(a >> 32); w2 = (uint32_t)b; w3 = (uint32_t)(b >> 32);
 }
 
+// ---- fast generic product for the one-off multiplications (setup, chunk scaling, final fold).
+// gf_mul above is a 128-step dependent chain (~8 us on one thread); this one is a carry-less
+// 128x128 multiply built from integer multiplies on operands whose bits are spread 4 apart
+// ("holes": column sums stay below 16, so no carry crosses into a neighbouring coefficient),
+// Karatsuba 128 -> 64 -> 32, then a fold by x^128 = x^7 + x^2 + x + 1.  It works on the natural
+// bit order (bit i = coefficient of x^i), i.e. the bit reversal of GHASH's serialisation.
+__device__ __forceinline__ uint64_t clmul32(uint32_t x, uint32_t y)
+{
+    const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
+    const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
+    auto m = [](uint32_t a, uint32_t b) { return (uint64_t)a * b; };
+    const uint64_t z0 = m(x0, y0) ^ m(x1, y3) ^ m(x2, y2) ^ m(x3, y1);
+    const uint64_t z1 = m(x0, y1) ^ m(x1, y0) ^ m(x2, y3) ^ m(x3, y2);
+    const uint64_t z2 = m(x0, y2) ^ m(x1, y1) ^ m(x2, y0) ^ m(x3, y3);
+    const uint64_t z3 = m(x0, y3) ^ m(x1, y2) ^ m(x2, y1) ^ m(x3, y0);
+    return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) |
+           (z2 & 0x4444444444444444ull) | (z3 & 0x8888888888888888ull);
+}
+
+__device__ __forceinline__ void clmul64(uint64_t a, uint64_t b, uint64_t &lo, uint64_t &hi)
+{
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const uint64_t z0 = clmul32(a0, b0), z2 = clmul32(a1, b1);
+    const uint64_t z1 = clmul32(a0 ^ a1, b0 ^ b1) ^ z0 ^ z2;
+    lo = z0 ^ (z1 << 32);
+    hi = z2 ^ (z1 >> 32);
+}
+
+__device__ inline Gf gf_mul_fast(Gf x, Gf y)
+{
+    // natural order: n.lo = coefficients x^0..x^63
+    const uint64_t al = __brevll(x.hi), ah = __brevll(x.lo), bl = __brevll(y.hi), bh = __brevll(y.lo);
+    uint64_t z0l, z0h, z2l, z2h, z1l, z1h;
+    clmul64(al, bl, z0l, z0h);
+    clmul64(ah, bh, z2l, z2h);
+    clmul64(al ^ ah, bl ^ bh, z1l, z1h);
+    z1l ^= z0l ^ z2l; z1h ^= z0h ^ z2h;
+    const uint64_t r0 = z0l, r1 = z0h ^ z1l, h0 = z2l ^ z1h, h1 = z2h;
+    // fold the upper 128 bits: H * (1 + x + x^2 + x^7), then the <= 7 bits that overflow again
+    const uint64_t t0 = h0 ^ (h0 << 1) ^ (h0 << 2) ^ (h0 << 7);
+    const uint64_t t1 = h1 ^ (h1 << 1 | h0 >> 63) ^ (h1 << 2 | h0 >> 62) ^ (h1 << 7 | h0 >> 57);
+    const uint64_t t2 = (h1 >> 63) ^ (h1 >> 62) ^ (h1 >> 57);
+    const uint64_t lo = r0 ^ t0 ^ t2 ^ (t2 << 1) ^ (t2 << 2) ^ (t2 << 7);
+    const uint64_t hi = r1 ^ t1;
+    Gf r;
+    r.hi = __brevll(lo);
+    r.lo = __brevll(hi);
+    return r;
+}
+
+// x^e by square and multiply
+__device__ inline Gf gf_pow_fast(Gf x, uint64_t e)
+{
+    Gf r{0x8000000000000000ull, 0};
+    for (; e; e >>= 1) {
+        if (e & 1) r = gf_mul_fast(r, x);
+        if (e > 1) x = gf_mul_fast(x, x);
+    }
+    return r;
+}
+
 // R[d] = d(x) * x^128 mod p as the first two bytes of a block (little-endian 16-bit value):
 // what falls off the end when a block is multiplied by x^8.  Key independent.
 struct GhashReduce { uint16_t v[256]; };

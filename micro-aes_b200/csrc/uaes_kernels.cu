@@ -25,17 +25,25 @@ static unsigned long long g_launches = 0;
 
 // ---------------------------------------------------------------- small device helpers
 
+// cache operators of the bulk loads/stores (every byte is touched once); overridable for tuning
+#ifndef UAES_LD
+#define UAES_LD "ld.global.cs.v4.u32"
+#endif
+#ifndef UAES_ST
+#define UAES_ST "st.global.cs.v4.u32"
+#endif
+
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
     uint4 v;
-    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile(UAES_LD " {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
 __device__ __forceinline__ void st_stream(uint4 *p, uint4 v)
 {
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+    asm volatile(UAES_ST " [%0], {%1,%2,%3,%4};"
                  ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
