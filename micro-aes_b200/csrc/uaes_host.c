@@ -18,6 +18,7 @@
 #include <cuda_runtime_api.h>
 #include <pthread.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/uaes_b200.h"
@@ -29,9 +30,16 @@
 #define UAES_TLS
 #endif
 
-#define NSLOT       3
-#define CHUNK_BYTES ((size_t)32 << 20)      /* multiple of every sector size we accept per chunk */
+#define MAX_SLOT    8
+#define MAX_CHUNK   ((size_t)256 << 20)
 #define MAX_DEV     64
+
+/* staging geometry: g_nslot device chunks of g_chunk bytes, one stream each (defaults measured on
+ * B200/PCIe gen5, see profiles/); UAES_STAGE_SLOTS / UAES_STAGE_CHUNK_MIB override for tuning */
+static int    g_nslot = 3;
+static size_t g_chunk = (size_t)64 << 20;
+#define NSLOT       g_nslot
+#define CHUNK_BYTES g_chunk
 
 typedef unsigned char u8;
 
@@ -183,8 +191,8 @@ static void make_ctrblock(const u8 *iv, u64 start, u64 first, uaes_ctrblock *cb)
 
 typedef struct {
     int ready;
-    void *slot[NSLOT];
-    cudaStream_t st[NSLOT];
+    void *slot[MAX_SLOT];
+    cudaStream_t st[MAX_SLOT];
     void *big;  size_t big_bytes;       /* grow-only full-size staging (GCM / XTS unit) */
     void *work; size_t work_bytes;      /* grow-only GCM scratch + AAD copy */
 } devctx;
@@ -204,7 +212,11 @@ static int get_ctx(devctx **out)
         return fail(UAES_E_NO_DEVICE, "cudaGetDevice failed", (int)cudaGetLastError());
     c = &g_dev[dev];
     if (!c->ready) {
-        for (i = 0; i < NSLOT; ++i)
+        const char *e;
+        if ((e = getenv("UAES_STAGE_SLOTS")) != NULL && atoi(e) >= 1 && atoi(e) <= MAX_SLOT) g_nslot = atoi(e);
+        if ((e = getenv("UAES_STAGE_CHUNK_MIB")) != NULL && atoi(e) >= 1 && (size_t)atoi(e) <= (MAX_CHUNK >> 20))
+            g_chunk = (size_t)atoi(e) << 20;
+        for (i = 0; i < MAX_SLOT; ++i)
             if (cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking) != cudaSuccess)
                 return fail(UAES_E_CUDA, "cudaStreamCreate", (int)cudaGetLastError());
         c->ready = 1;
