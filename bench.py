@@ -41,6 +41,23 @@ def shard_plan(total_blocks, world):
     return [(r * per, per if r < world - 1 else total_blocks - r * per) for r in range(world)]
 
 
+def gcm_shards(total_bytes, world):
+    """byte ranges [(offset, nbytes)] of one GCM message over `world` ranks: whole 16-byte blocks
+    per rank, the last rank owns the ragged tail"""
+    blocks = total_bytes // 16
+    plan = shard_plan(blocks, world)
+    out = [(f * 16, n * 16) for f, n in plan]
+    off, n = out[-1]
+    out[-1] = (off, total_bytes - off)
+    return out
+
+
+def gcm_blocks_after(shards, total_bytes):
+    """GHASH blocks after the end of each shard (the exponents of H in the combine step)"""
+    total_blocks = (total_bytes + 15) // 16
+    return [total_blocks - (off + n + 15) // 16 for off, n in shards]
+
+
 # --------------------------------------------------------------------------- CPU baseline
 
 def _ref_lib():
@@ -221,8 +238,19 @@ def run_gpu(args):
             uaes.ecb(128, key, src, nbytes, dst, True)
         elif wl == "xts256":        # BASELINE config 3: 512-byte sectors, sector numbers follow the shard
             uaes.xts_sectors(256, keys64, first_block // 32, 512, src, nbytes, dst, True)
-        elif wl == "gcm128":        # BASELINE config 4: one message per rank
+        elif wl == "gcm128" and world == 1:   # BASELINE config 4: one 4 GiB message, one GPU
             uaes.gcm_encrypt(128, key, iv, b"", src, nbytes, dst)
+        elif wl == "gcm128":
+            # one message of world * nbytes sharded by block range: fused pass per rank, ONE 16-byte
+            # all-gather, rank 0 folds the contributions into the tag
+            part = uaes.gcm_shard(128, key, iv, first_block, src, nbytes, dst)
+            mine = torch.from_numpy(np.frombuffer(part, dtype=np.uint8).copy()).cuda()
+            allp = [torch.empty(16, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allp, mine)
+            if rank == 0:
+                shards = gcm_shards(nbytes * world, world)
+                uaes.gcm_combine(128, key, iv, b"", [bytes(p.cpu().numpy()) for p in allp],
+                                 gcm_blocks_after(shards, nbytes * world), nbytes * world)
 
     def barrier():
         torch.cuda.synchronize()

@@ -109,6 +109,21 @@ int uaes_gcm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
 int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                      const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* One GCM message sharded over several GPUs (or calls).  Each shard holds a contiguous byte range
+ * starting at block `first_block` of the message; all shards but the last are multiples of 16
+ * bytes.  uaes_gcm_shard runs the fused CTR + GHASH pass over the shard (encrypt: GHASH over the
+ * output; decrypt: GHASH over the input, plaintext written in the same pass) and returns the
+ * shard's 16-byte GHASH contribution in partial[] (host memory).  Gather the contributions (the
+ * one 16-byte-per-rank exchange of the path) and let uaes_gcm_combine fold them with the AAD and the
+ * lengths into the tag: blocks_after[r] = number of 16-byte blocks of the message after shard r's
+ * end (0 for the last shard).  A decrypting caller compares that tag with the received one and
+ * discards the shards' output on mismatch (the single-call API does this itself). */
+int uaes_gcm_shard(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, uaes_u64 first_block,
+                   const void *in, size_t len, void *out, int decrypt, uaes_u8 *partial);
+int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const uaes_u8 *partials, const uaes_u64 *blocks_after, int nshards,
+                     uaes_u64 total_len, uaes_u8 *tag);
+
 /* ---- synthetic data (bench / tests) ----------------------------------------- */
 /* 64-bit word w of dst (little-endian) = splitmix64(seed + first_word + w); dst is DEVICE memory */
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords);

@@ -48,6 +48,8 @@ UAES_ABI = {
     "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
     "uaes_gcm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_gcm_shard": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp, _int, _vp]),
+    "uaes_gcm_combine": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _vp, _int, _u64, _vp]),
     "uaes_fill_splitmix64": (_int, [_u64, _u64, _vp, _sz]),
     "uaes_xor_fold64": (_int, [_vp, _sz, ctypes.POINTER(_u64)]),
 }
@@ -217,6 +219,25 @@ def gcm_encrypt(bits, key, nonce, aad, src, nbytes, dst):
 def gcm_decrypt(bits, key, nonce, aad, src, nbytes, dst):
     return check(core().uaes_gcm_decrypt(bits, key, nonce, _ptr(aad), len(aad) if aad else 0,
                                          _ptr(src), nbytes, _ptr(dst)))
+
+
+def gcm_shard(bits, key, nonce, first_block, src, nbytes, dst, decrypt=False):
+    """fused CTR+GHASH over one shard of a message; returns the shard's 16-byte GHASH contribution"""
+    part = ctypes.create_string_buffer(16)
+    check(core().uaes_gcm_shard(bits, key, nonce, first_block, _ptr(src), nbytes, _ptr(dst),
+                                1 if decrypt else 0, ctypes.addressof(part)))
+    return part.raw
+
+
+def gcm_combine(bits, key, nonce, aad, partials, blocks_after, total_len):
+    """tag of a sharded message from the gathered contributions"""
+    tag = ctypes.create_string_buffer(16)
+    ps = b"".join(partials)
+    after = (ctypes.c_uint64 * max(len(blocks_after), 1))(*blocks_after)
+    check(core().uaes_gcm_combine(bits, key, nonce, _ptr(aad) if aad else None, len(aad) if aad else 0,
+                                  _ptr(ps) if ps else None, ctypes.addressof(after), len(partials), total_len,
+                                  ctypes.addressof(tag)))
+    return tag.raw
 
 
 def fill_splitmix64(seed, first_word, dst, nwords):

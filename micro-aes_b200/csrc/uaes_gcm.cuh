@@ -141,7 +141,10 @@ __device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t rb, uint32
     y0 = acc.x; y1 = acc.y; y2 = acc.z; y3 = acc.w;
 }
 
-template <int NR, bool HASH_ONLY>
+// MODE 0: encrypt (CTR, hash the OUTPUT)   MODE 1: hash only (GCM decrypt's verify pass)
+// MODE 2: decrypt shard (CTR, hash the INPUT in the same pass; multi-GPU shards, where the caller
+//         compares the combined tag afterwards)
+template <int NR, int MODE>
 __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
     else                              { mbase = tbase + kEncTableBytes; rbase = mbase + kGhashRegion; }
     if (rbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1) __trap();
 
-    if (!HASH_ONLY) init_enc_tables(tbase);
+    if (MODE != 1) init_enc_tables(tbase);
     {
         // M[b] = b(x) * C: bit 7 of b is the coefficient of x^0 (micro_aes.c:476-493 bit order)
         const Gf C = gf_load(a.work->C32);
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
             const bool ok = valid_k(vrow, k);
             const uint4 nxt = (vrow + 32 < vend && valid_k(vrow + 32, kn)) ? ld_stream(a.in + kn) : make_uint4(0, 0, 0, 0);
             uint32_t o0 = cur.x, o1 = cur.y, o2 = cur.z, o3 = cur.w;
-            if (!HASH_ONLY) {
+            if (MODE != 1) {
                 if ((vrow >> 8) != cur_group) {              // same hoisting as ctr_kernel
                     cur_group = vrow >> 8;
                     uint32_t w2, w3;
@@ -226,8 +229,8 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
                 uint32_t t0 = D0 ^ lut<0, kOffT0>(lb, c0), t1 = D1 ^ lut<3, kOffT3>(lb, c0);
                 uint32_t t2 = D2 ^ lut<2, kOffT2>(lb, c0), t3 = D3 ^ lut<1, kOffT1>(lb, c0);
                 enc_finish<NR, 3>(lb, t0, t1, t2, t3, rk, o0, o1, o2, o3);
-                o0 = t0; o1 = t1; o2 = t2; o3 = t3;
-                if (ok) st_stream(a.out + k, make_uint4(o0, o1, o2, o3));
+                if (ok) st_stream(a.out + k, make_uint4(t0, t1, t2, t3));
+                if (MODE == 0) { o0 = t0; o1 = t1; o2 = t2; o3 = t3; }     // GHASH runs over ciphertext
             }
             if (ok) {
                 if (k == 0) { o0 ^= aad_state.x; o1 ^= aad_state.y; o2 ^= aad_state.z; o3 ^= aad_state.w; }
@@ -260,7 +263,8 @@ struct GcmFinishArgs {
     uint8_t *out;
     uint64_t len, aadlen;
     uint64_t nparts, chunk_rows; // partials left by the bulk kernel; neighbours are H^(32*rows) apart
-    int hash_only;
+    int mode;                    // as gcm_bulk_kernel's MODE
+    int partial_only;            // write the GHASH state of this shard instead of a tag
     uint8_t *tag_out;            // 16 bytes, any alignment
     GcmWork *work;
 };
@@ -301,8 +305,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
     const uint64_t nfull = a.len / 16;
     const uint32_t tail = (uint32_t)(a.len % 16);
     if (tail) {
-        uint4 ct = load_block_bytes(a.in + 16 * nfull, tail);
-        if (!a.hash_only) {                                   // mixThenXor, micro_aes.c:949
+        uint4 ct = load_block_bytes(a.in + 16 * nfull, tail);   // what GHASH absorbs (zero padded)
+        if (a.mode != 1) {                                    // mixThenXor, micro_aes.c:949
             uint32_t w2, w3;
             ctr_words(a.b8, (a.v0 + nfull) & kMask56, w2, w3);
             uint32_t s[4] = {a.w0, a.w1, w2, w3};
@@ -311,14 +315,20 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
                                       tail >= 8 ? 0xffffffffu : tail > 4 ? (1u << (8 * (tail - 4))) - 1 : 0,
                                       tail >= 12 ? 0xffffffffu : tail > 8 ? (1u << (8 * (tail - 8))) - 1 : 0,
                                       tail > 12 ? (1u << (8 * (tail - 12))) - 1 : 0};
-            ct.x = (ct.x ^ s[0]) & keep[0]; ct.y = (ct.y ^ s[1]) & keep[1];
-            ct.z = (ct.z ^ s[2]) & keep[2]; ct.w = (ct.w ^ s[3]) & keep[3];
-            const uint32_t cw[4] = {ct.x, ct.y, ct.z, ct.w};
+            const uint32_t cw[4] = {(ct.x ^ s[0]) & keep[0], (ct.y ^ s[1]) & keep[1],
+                                    (ct.z ^ s[2]) & keep[2], (ct.w ^ s[3]) & keep[3]};
             for (uint32_t i = 0; i < tail; ++i) a.out[16 * nfull + i] = (uint8_t)(cw[i >> 2] >> (8 * (i & 3)));
+            if (a.mode == 0) ct = make_uint4(cw[0], cw[1], cw[2], cw[3]);
         }
         const Gf x = gf_load(ct);
         S.hi ^= x.hi; S.lo ^= x.lo;
         S = gf_mul_fast(H, S);
+    }
+    if (a.partial_only) {                                     // shard: hand the state to the combiner
+        const uint4 sv = gf_store(S);
+        const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+        for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(sw[i >> 2] >> (8 * (i & 3)));
+        return;
     }
     // length block: BE64(8*aadlen) || BE64(8*len)   (micro_aes.c:1130-1132)
     S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
@@ -336,12 +346,12 @@ static unsigned gcm_grid(uint64_t nchunks)
     return (unsigned)(need < 1 ? 1 : need < sms ? need : sms);
 }
 
-template <int NR, bool HASH_ONLY>
+template <int NR, int MODE>
 static cudaError_t launch_gcm_bulk_nr(const GcmBulkArgs &a, cudaStream_t st)
 {
-    cudaError_t e = opt_in_smem(gcm_bulk_kernel<NR, HASH_ONLY>);
+    cudaError_t e = opt_in_smem(gcm_bulk_kernel<NR, MODE>);
     if (e != cudaSuccess) return e;
-    gcm_bulk_kernel<NR, HASH_ONLY><<<gcm_grid(a.nchunks), kGcmThreads, kDynSmem, st>>>(a);
+    gcm_bulk_kernel<NR, MODE><<<gcm_grid(a.nchunks), kGcmThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -356,6 +366,63 @@ static void gcm_plan(uint64_t nblocks, uint64_t &rows_per_chunk, uint64_t &nchun
     nchunks = rows ? (nblocks + 32 * rows_per_chunk - 1) / (32 * rows_per_chunk) : 0;
 }
 
+// ---------------------------------------------------------------- multi-shard combine
+
+// A message sharded over GPUs: shard r returns Z_r = sum over its blocks of
+// X_i * H^(shard end - i).  GHASH of the whole = aad_state * H^(all blocks) ^ sum_r Z_r * H^(blocks
+// after shard r), then the length block and E_K(J0) as usual.  <= 32 shards, one lane each.
+struct GcmCombineArgs {
+    uaes_keysched ks;
+    uint32_t j0[4];
+    const uint8_t *aad;
+    uint64_t aadlen, len;
+    const uint8_t *partials;     // nshards x 16 bytes (device)
+    const uint64_t *after;       // GHASH blocks after the end of shard r (device)
+    uint32_t nshards;
+    uint64_t total_blocks;       // ceil(len / 16)
+    uint8_t *tag_out;
+};
+
+__global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
+{
+    __shared__ Gf sh_H, sh_ej0;
+    const uint32_t lane = threadIdx.x;
+    if (lane < 2) {
+        uint32_t s[4] = {0, 0, 0, 0};
+        if (lane == 1) { s[0] = a.j0[0]; s[1] = a.j0[1]; s[2] = a.j0[2]; s[3] = a.j0[3]; }
+        small_encrypt(a.ks.w, a.ks.rounds, s);
+        (lane == 0 ? sh_H : sh_ej0) = gf_from_words(s[0], s[1], s[2], s[3]);
+    }
+    __syncwarp();
+    const Gf H = sh_H;
+    Gf term{0, 0};
+    if (lane < a.nshards) {
+        const uint4 z = load_block_bytes(a.partials + 16 * lane, 16);
+        term = gf_mul_fast(gf_load(z), gf_pow_fast(H, a.after[lane]));
+    } else if (lane == 31) {                                  // the AAD rides in front of block 0
+        Gf g{0, 0};
+        for (uint64_t off = 0; off < a.aadlen; off += 16) {
+            const uint64_t left = a.aadlen - off;
+            const Gf x = gf_load(load_block_bytes(a.aad + off, left < 16 ? (uint32_t)left : 16));
+            g.hi ^= x.hi; g.lo ^= x.lo;
+            g = gf_mul_fast(H, g);
+        }
+        term = gf_mul_fast(g, gf_pow_fast(H, a.total_blocks));
+    }
+    for (int o = 16; o; o >>= 1) {
+        term.hi ^= __shfl_xor_sync(0xffffffffu, term.hi, o);
+        term.lo ^= __shfl_xor_sync(0xffffffffu, term.lo, o);
+    }
+    if (lane) return;
+    Gf S = term;
+    S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
+    S = gf_mul_fast(H, S);
+    S.hi ^= sh_ej0.hi; S.lo ^= sh_ej0.lo;
+    const uint4 t = gf_store(S);
+    const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+    for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
+}
+
 }  // namespace uaes
 
 extern "C" size_t uaes_gcm_work_bytes(u64 len)
@@ -367,8 +434,8 @@ extern "C" size_t uaes_gcm_work_bytes(u64 len)
 }
 
 extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
-                               u64 aadlen, const void *in, void *out, u64 len, int hash_only,
-                               void *tag_out, void *work, void *stream)
+                               u64 aadlen, const void *in, void *out, u64 len, int mode, u64 first_block,
+                               int partial_only, void *tag_out, void *work, void *stream)
 {
     using namespace uaes;
     cudaStream_t st = (cudaStream_t)stream;
@@ -398,16 +465,19 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     if (nchunks) {
         GcmBulkArgs b;
         b.ks = *ks;
-        b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = (vj0 + 1) & kMask56;
+        b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = (vj0 + 1 + first_block) & kMask56;
         b.in = (const uint4 *)in; b.out = (uint4 *)out;
         b.nblocks = nblocks; b.chunk_blocks = 32 * rows_per_chunk; b.nchunks = nchunks; b.work = (GcmWork *)work;
-        switch (ks->rounds * 2 + (hash_only ? 1 : 0)) {
-        case 20: e = launch_gcm_bulk_nr<10, false>(b, st); break;
-        case 21: e = launch_gcm_bulk_nr<10, true>(b, st); break;
-        case 24: e = launch_gcm_bulk_nr<12, false>(b, st); break;
-        case 25: e = launch_gcm_bulk_nr<12, true>(b, st); break;
-        case 28: e = launch_gcm_bulk_nr<14, false>(b, st); break;
-        case 29: e = launch_gcm_bulk_nr<14, true>(b, st); break;
+        switch (ks->rounds * 4 + mode) {
+        case 40: e = launch_gcm_bulk_nr<10, 0>(b, st); break;
+        case 41: e = launch_gcm_bulk_nr<10, 1>(b, st); break;
+        case 42: e = launch_gcm_bulk_nr<10, 2>(b, st); break;
+        case 48: e = launch_gcm_bulk_nr<12, 0>(b, st); break;
+        case 49: e = launch_gcm_bulk_nr<12, 1>(b, st); break;
+        case 50: e = launch_gcm_bulk_nr<12, 2>(b, st); break;
+        case 56: e = launch_gcm_bulk_nr<14, 0>(b, st); break;
+        case 57: e = launch_gcm_bulk_nr<14, 1>(b, st); break;
+        case 58: e = launch_gcm_bulk_nr<14, 2>(b, st); break;
         default: e = cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return (int)e;
@@ -415,11 +485,30 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
 
     GcmFinishArgs f;
     f.ks = *ks;
-    f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1) & kMask56;
+    f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1 + first_block) & kMask56;
     f.in = (const uint8_t *)in; f.out = (uint8_t *)out;
-    f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.hash_only = hash_only;
+    f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.mode = mode; f.partial_only = partial_only;
     f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+                                       u64 aadlen, u64 len, const void *partials_dev, const void *after_dev,
+                                       unsigned nshards, void *tag_out, void *stream)
+{
+    using namespace uaes;
+    if (nshards > 31) return (int)cudaErrorInvalidValue;
+    GcmCombineArgs a;
+    a.ks = *ks;
+    for (int c = 0; c < 3; ++c)
+        a.j0[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
+    a.j0[3] = 0x01000000u;
+    a.aad = (const uint8_t *)aad_dev; a.aadlen = aadlen; a.len = len;
+    a.partials = (const uint8_t *)partials_dev; a.after = (const uint64_t *)after_dev;
+    a.nshards = nshards; a.total_blocks = (len + 15) / 16; a.tag_out = (uint8_t *)tag_out;
+    gcm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
     return (int)cudaGetLastError();
 }

@@ -527,14 +527,14 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *a
 
     if (!decrypt) {
         /* one fused pass: CTR + GHASH, tag appended at out + len (micro_aes.c:1168,1178) */
-        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, dout, len, 0, (u8 *)dout + len, work, st));
+        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, dout, len, 0, 0, 0, (u8 *)dout + len, work, st));
         if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
         if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
     } else {
         /* verify first, decrypt only on success; `out` stays untouched otherwise (micro_aes.c:1199-1209) */
         u8 t1[16], t2[16];
         uaes_ctrblock cb;
-        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, NULL, len, 1, dtag, work, st));
+        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, NULL, len, 1, 0, 0, dtag, work, st));
         CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
         CU(cudaMemcpyAsync(t2, (const u8 *)din + len, 16, cudaMemcpyDefault, st));
         CU(cudaStreamSynchronize(st));
@@ -561,6 +561,75 @@ int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
                      const void *in, size_t len, void *out)
 {
     return gcm_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+}
+
+/* ---- a GCM message sharded over several GPUs / calls ---------------------------
+ * Every shard runs the fused CTR+GHASH pass over its own byte range and returns 16 bytes; one
+ * caller gathers them (an all-gather of 16 B per rank) and folds them into the tag. */
+int uaes_gcm_shard(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, uaes_u64 first_block,
+                   const void *in, size_t len, void *out, int decrypt, uaes_u8 *partial)
+{
+    devctx *c;
+    uaes_keysched ks;
+    int rc, direct;
+    const void *din;
+    void *dout;
+    u8 *work, *dpart;
+    cudaStream_t st;
+
+    if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    direct = len == 0 || (is_direct(in) && is_direct(out));
+    st = direct ? (cudaStream_t)tls_stream : c->st[0];
+    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + 64, "cudaMalloc(GCM work)")) != 0) goto done;
+    dpart = (u8 *)c->work;
+    work = (u8 *)c->work + GCM_WORK_HEAD;
+    if (direct) {
+        din = in; dout = out;
+    } else {
+        if ((rc = grow(&c->big, &c->big_bytes, len + 32, "cudaMalloc(GCM staging)")) != 0) goto done;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        CU(cudaMemcpyAsync(c->big, in, len, cudaMemcpyDefault, st));
+        din = c->big; dout = c->big;
+    }
+    LAUNCH(uaes_launch_gcm(&ks, nonce, NULL, 0, din, dout, len, decrypt ? 2 : 0, first_block, 1, dpart, work, st));
+    if (!direct) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(partial, dpart, 16, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));                            /* the 16 bytes are a host result */
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const uaes_u8 *partials, const uaes_u64 *blocks_after, int nshards,
+                     uaes_u64 total_len, uaes_u8 *tag)
+{
+    devctx *c;
+    uaes_keysched ks;
+    int rc;
+    u8 *w;
+    cudaStream_t st = (cudaStream_t)tls_stream;
+
+    if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (nshards < 0 || nshards > 31) return fail(UAES_E_BAD_ARGUMENT, "at most 31 shards", 0);
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + 32 * 24 + aadlen + 64, "cudaMalloc(GCM work)")) != 0) goto done;
+    w = (u8 *)c->work;                                        /* [tag 16][pad][partials][after][aad] */
+    if (nshards) {
+        CU(cudaMemcpyAsync(w + 64, partials, (size_t)nshards * 16, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(w + 64 + 32 * 16, blocks_after, (size_t)nshards * 8, cudaMemcpyDefault, st));
+    }
+    if (aadlen) CU(cudaMemcpyAsync(w + GCM_WORK_HEAD, aad, aadlen, cudaMemcpyDefault, st));
+    LAUNCH(uaes_launch_gcm_combine(&ks, nonce, aadlen ? w + GCM_WORK_HEAD : NULL, aadlen, total_len,
+                                   w + 64, w + 64 + 32 * 16, (unsigned)nshards, w, st));
+    CU(cudaMemcpyAsync(tag, w, 16, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
 }
 
 /* ------------------------------------------------------------------ synthetic data */

@@ -56,12 +56,20 @@ int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysched *ks1e,
                          const void *in, void *out, u64 len, void *stream);
 
 /* GCM.  `work` is a device scratch area of at least uaes_gcm_work_bytes(len) bytes.
- * encrypt: CTR over in -> out, GHASH over aad and out, tag written to out + len.
- * hash_only: GHASH over aad and in, tag (E_K(J0) ^ GHASH) written to tag_out (device, 16 B). */
+ * mode 0: CTR over in -> out, GHASH over aad and out;  mode 1: GHASH over aad and in only;
+ * mode 2: CTR over in -> out, GHASH over in (decrypting shard).
+ * first_block: keystream/GHASH position of in[0] inside a larger message (0 for a whole message).
+ * partial_only = 0: tag = E_K(J0) ^ GHASH(aad, data, lengths) written to tag_out (16 B, device);
+ * partial_only = 1: the shard's GHASH contribution sum X_i * H^(shard end - i) written instead. */
 size_t uaes_gcm_work_bytes(u64 len);
 int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
-                    u64 aadlen, const void *in, void *out, u64 len, int hash_only, void *tag_out,
-                    void *work, void *stream);
+                    u64 aadlen, const void *in, void *out, u64 len, int mode, u64 first_block,
+                    int partial_only, void *tag_out, void *work, void *stream);
+/* tag of a sharded message from the shards' contributions: partials_dev = nshards x 16 B,
+ * after_dev = nshards x u64 (GHASH blocks after the end of each shard), both device memory */
+int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+                            u64 aadlen, u64 len, const void *partials_dev, const void *after_dev,
+                            unsigned nshards, void *tag_out, void *stream);
 
 /* synthetic data + checksum helpers */
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);

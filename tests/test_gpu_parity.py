@@ -304,3 +304,41 @@ def test_async_stream_api(uaes, orc, torch):
         uaes.set_async(False)
         uaes.set_stream(None)
     assert host(dst, 0, len(data)) == orc.ctr(key, iv, data)
+
+
+def test_gcm_sharded_message(uaes, orc, torch):
+    """one GCM message cut into shards (as over several GPUs), each shard one fused
+    pass returning 16 bytes, folded by uaes_gcm_combine: ciphertext and tag == the unsharded oracle"""
+    for bits, n, alen, cuts in [(128, 3 * (1 << 20) + 7, 20, [1 << 20, (2 << 20) + 4096]),
+                                (256, 100000, 0, [16, 32, 48, 99968]),
+                                (192, 4096, 33, []),
+                                (128, 5, 7, []),
+                                (128, 0, 13, [])]:
+        key, nonce = rnd(f"sh-k{bits}{n}", bits // 8), rnd(f"sh-n{bits}{n}", 12)
+        aad, data = rnd(f"sh-a{bits}{n}", alen), rnd(f"sh-d{bits}{n}", n)
+        want = orc.gcm_encrypt(key, nonce, aad, data)
+        edges = [0] + cuts + [n]
+        total_blocks = (n + 15) // 16
+        for device in (False, True):
+            parts, after, out = [], [], b""
+            for a, b in zip(edges[:-1], edges[1:]):
+                if device:
+                    src, dst = dev(torch, data[a:b]), dev(torch, b"", pad=b - a)
+                    parts.append(uaes.gcm_shard(bits, key, nonce, a // 16, src, b - a, dst))
+                    out += host(dst, 0, b - a)
+                else:
+                    dst = ctypes.create_string_buffer(max(b - a, 1))
+                    parts.append(uaes.gcm_shard(bits, key, nonce, a // 16, data[a:b], b - a, dst))
+                    out += dst.raw[:b - a]
+                after.append(total_blocks - (b + 15) // 16)
+            tag = uaes.gcm_combine(bits, key, nonce, aad, parts, after, n)
+            assert out == want[:-16], (bits, n, device)
+            assert tag == want[-16:], (bits, n, device)
+        # decrypting shards: plaintext back, same tag from the INPUT ciphertext
+        parts, after, back = [], [], b""
+        for a, b in zip(edges[:-1], edges[1:]):
+            dst = ctypes.create_string_buffer(max(b - a, 1))
+            parts.append(uaes.gcm_shard(bits, key, nonce, a // 16, want[a:b], b - a, dst, decrypt=True))
+            back += dst.raw[:b - a]
+            after.append(total_blocks - (b + 15) // 16)
+        assert back == data and uaes.gcm_combine(bits, key, nonce, aad, parts, after, n) == want[-16:]

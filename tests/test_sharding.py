@@ -62,3 +62,51 @@ def test_shard_plan_covers_and_crosses_2_32():
     assert plan[3][0] < (1 << 32) - 1 <= plan[3][0] + plan[3][1]
     plan = bench.shard_plan(1003, 4)
     assert [f for f, _ in plan] == [0, 250, 500, 750] and plan[-1][1] == 253
+
+
+def _gcm_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    orc = Oracle()
+    key, nonce, aad = rnd("gs-key", 16), rnd("gs-nonce", 12), rnd("gs-aad", 20)
+    total = 16 * 1000 + 5                                    # ragged: the last shard owns the tail
+    shards = bench.gcm_shards(total, world)
+    off, n = shards[rank]
+    data = rnd("gs-data", total)[off:off + n]
+    # what uaes_gcm_shard does on a GPU, restated with the checker: CTR from J0 + 1 + first_block,
+    # then the shard's GHASH contribution from a zero state
+    ct = orc.ctr(key, nonce, data, first_block=1 + off // 16)
+    H = orc.encrypt_block(key, bytes(16))
+    part = torch.tensor(list(orc.ghash_absorb(H, ct, len(ct))), dtype=torch.uint8)
+    gathered = [torch.zeros(16, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(gathered, part)                          # the path's one exchange: 16 B per rank
+    cts = [None] * world
+    dist.all_gather_object(cts, ct)
+    if rank == 0:
+        # what uaes_gcm_combine does: sum Z_r * H^(blocks after shard r), AAD in front, lengths, E(J0)
+        after = bench.gcm_blocks_after(shards, total)
+        state = orc.gf128_mul(orc.gf128_pow(H, (total + 15) // 16), orc.ghash_absorb(H, aad, len(aad)))
+        for z, a in zip(gathered, after):
+            term = orc.gf128_mul(orc.gf128_pow(H, a), bytes(z.tolist()))
+            state = bytes(x ^ y for x, y in zip(state, term))
+        lens = (len(aad) * 8).to_bytes(8, "big") + (total * 8).to_bytes(8, "big")
+        state = orc.ghash_absorb(H, lens, 16, state)
+        ej0 = orc.encrypt_block(key, nonce + b"\0\0\0\1")
+        q.put((b"".join(cts), bytes(x ^ y for x, y in zip(state, ej0))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gcm_shards_and_16_byte_gather():
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = tmp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_gcm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ct, tag = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = Oracle().gcm_encrypt(rnd("gs-key", 16), rnd("gs-nonce", 12), rnd("gs-aad", 20), rnd("gs-data", 16 * 1000 + 5))
+    assert ct == want[:-16] and tag == want[-16:]

@@ -11,6 +11,48 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
+__constant__ uint32_t c_tab[1024];
+
+// LDS gathers next to indexed constant-bank loads (LDC with a per-lane index): does the constant
+// cache offer a second lookup path?
+template <int NLDS, int NLDC>
+__global__ void __launch_bounds__(1024, 1) ldc_kernel(uint32_t *out, int iters, uint32_t smem_bytes)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t base0 = (uint32_t)__cvta_generic_to_shared(dyn);
+    const uint32_t base = (base0 + 65535u) & ~65535u;
+    if (NLDS) {
+        if (base + 65536u > base0 + smem_bytes) __trap();
+        for (uint32_t w = threadIdx.x; w < 16384; w += blockDim.x)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + w * 4), "r"(w * 2654435761u) : "memory");
+    }
+    __syncthreads();
+    uint32_t lb = base + (threadIdx.x & 31) * 4;
+    uint32_t s0 = threadIdx.x * 0x9E3779B9u, s1 = s0 ^ 0x12345678u, s2 = s0 + 77, s3 = ~s0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t a = 0, b = 0, c = 0, d = 0;
+#pragma unroll
+        for (int k = 0; k < NLDS; ++k) {
+            const uint32_t w = (k & 3) == 0 ? s0 : (k & 3) == 1 ? s1 : (k & 3) == 2 ? s2 : s3;
+            const uint32_t ad = __byte_perm(w, lb, 0x7604 | (((k >> 2) & 3) << 4));
+            uint32_t r;
+            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(ad), "n"(0));
+            if ((k & 3) == 0) a ^= r; else if ((k & 3) == 1) b ^= r; else if ((k & 3) == 2) c ^= r; else d ^= r;
+        }
+#pragma unroll
+        for (int k = 0; k < NLDC; ++k) {
+            const uint32_t w = (k & 3) == 0 ? s1 : (k & 3) == 1 ? s2 : (k & 3) == 2 ? s3 : s0;
+            const uint32_t r = c_tab[(w >> (8 * ((k >> 2) & 3))) & 0xff];
+            if ((k & 3) == 0) a ^= r; else if ((k & 3) == 1) b ^= r; else if ((k & 3) == 2) c ^= r; else d ^= r;
+        }
+        s0 = a + it; s1 = b ^ s0; s2 = c + s1; s3 = d ^ s2;
+    }
+    if ((s0 ^ s1 ^ s2 ^ s3) == 0x1234567) out[1 + (threadIdx.x & 1)] = s0;
+}
+
+template <int NLDS, int NLDC>
+static void run_ldc(uint32_t *out, int sms, double mhz, uint32_t smem);
+
 template <int NLDS, int NTEX>
 __global__ void __launch_bounds__(1024, 1) gather_kernel(cudaTextureObject_t tex, uint32_t *out, int iters, uint32_t smem_bytes)
 {
@@ -96,6 +138,18 @@ static void run_gather(cudaTextureObject_t tex, uint32_t *out, int sms, double m
            NLDS, NTEX, smem >> 10, ms, lookups / clk, clk / iters / 32.0, NLDS + NTEX);
 }
 
+template <int NLDS, int NLDC>
+static void run_ldc(uint32_t *out, int sms, double mhz, uint32_t smem)
+{
+    const int iters = 2000;
+    CK(cudaFuncSetAttribute(ldc_kernel<NLDS, NLDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double ms = time_ms([&] { ldc_kernel<NLDS, NLDC><<<sms, 1024, smem>>>(out, iters, smem); });
+    CK(cudaGetLastError());
+    const double clk = ms * 1e-3 * mhz * 1e6;
+    printf("gather  LDS=%2d LDC=%2d smem=%3u KB: %8.3f ms  %6.2f lookups/clk/SM  (%.1f clk per %d-lookup step per warp-row)\n",
+           NLDS, NLDC, smem >> 10, ms, (double)iters * 1024 * (NLDS + NLDC) / clk, clk / iters / 32.0, NLDS + NLDC);
+}
+
 int main()
 {
     cudaDeviceProp p;
@@ -132,6 +186,18 @@ int main()
     run_gather<16, 8>(tex, out, sms, mhz, 130 * 1024);
     run_gather<12, 4>(tex, out, sms, mhz, 130 * 1024);
     run_gather<16, 4>(tex, out, sms, mhz, 227 * 1024);
+
+    {
+        uint32_t hc[1024];
+        for (int i = 0; i < 1024; ++i) hc[i] = i * 2246822519u;
+        CK(cudaMemcpyToSymbol(c_tab, hc, sizeof hc));
+    }
+    run_ldc<0, 16>(out, sms, mhz, 1024);
+    run_ldc<0, 4>(out, sms, mhz, 1024);
+    run_ldc<16, 1>(out, sms, mhz, 227 * 1024);
+    run_ldc<16, 2>(out, sms, mhz, 227 * 1024);
+    run_ldc<16, 4>(out, sms, mhz, 227 * 1024);
+    run_ldc<14, 2>(out, sms, mhz, 227 * 1024);
 
     const int iters = 20000;
     const char *names[3] = {"LOP3", "PRMT", "LOP3+IMAD"};
