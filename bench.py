@@ -226,7 +226,7 @@ def run_gpu(args):
     wl = args.workload
     key32 = key + bytes(range(16))
     keys64 = key32 + bytes(range(32, 64))
-    if wl == "gcm128":
+    if wl in ("gcm128", "gcmsiv128"):
         dst = torch.empty(nbytes + 16, dtype=torch.uint8, device="cuda")
 
     def step():
@@ -236,6 +236,12 @@ def run_gpu(args):
             uaes.ctr_crypt_range(256, key32, iv, first_block, src, nbytes, dst)
         elif wl == "ecb128":
             uaes.ecb(128, key, src, nbytes, dst, True)
+        elif wl == "ecb128dec":
+            uaes.ecb(128, key, src, nbytes, dst, False)
+        elif wl == "xts256dec":
+            uaes.xts_sectors(256, keys64, first_block // 32, 512, src, nbytes, dst, False)
+        elif wl == "gcmsiv128":     # two passes (POLYVAL, then CTR)
+            uaes.gcmsiv(128, key, iv, b"", src, nbytes, dst, True)
         elif wl == "xts256":        # BASELINE config 3: 512-byte sectors, sector numbers follow the shard
             uaes.xts_sectors(256, keys64, first_block // 32, 512, src, nbytes, dst, True)
         elif wl == "gcm128" and world == 1:   # BASELINE config 4: one 4 GiB message, one GPU
@@ -364,7 +370,9 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel": {"ctr128": "uaes::ctr_kernel<10>", "ctr256": "uaes::ctr_kernel<14>", "ecb128": "uaes::ecb_kernel<10,true>",
-                                    "xts256": "uaes::xts_sectors_kernel<14,true>", "gcm128": "uaes::gcm_bulk_kernel<10,false>"}[wl],
+                                    "xts256": "uaes::xts_sectors_kernel<14,true>", "gcm128": "uaes::gcm_bulk_kernel<10,0>",
+                                    "ecb128dec": "uaes::ecb_kernel<10,false>", "xts256dec": "uaes::xts_sectors_kernel<14,false>",
+                                    "gcmsiv128": "uaes::gcm_bulk_kernel<10,1,true> + uaes::ctr32_kernel<10>"}[wl],
                          "kernel_ms": round(kernel_ms, 4),
                          "algorithmic_bytes_per_launch": 2 * nbytes},
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -385,7 +393,7 @@ def main():
     ap.add_argument("--e2e-gib", type=float, default=0.0, help="host buffer for the e2e leg (default: auto)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-slice-mib", type=int, default=256)
-    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "xts256", "gcm128"],
+    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "ecb128dec", "xts256", "xts256dec", "gcm128", "gcmsiv128"],
                     help="ctr128 is the headline (BASELINE.json metric); the others are the secondary configs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")

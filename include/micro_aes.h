@@ -3,8 +3,8 @@
  * B200 (sm_100a) engine in libuaes_b200.so.
  *
  * This header declares, with the reference's names, argument order and return
- * codes, exactly the eight entry points the reference exports when only
- * ECB, CTR (CTR_NA), XEX/XTS and GCM are enabled:
+ * codes, the entry points the reference exports when only ECB, CTR (CTR_NA),
+ * XEX/XTS, GCM and GCM_SIV are enabled:
  *
  *     function            replaces (polfosol/micro-AES)
  *     ------------------  ---------------------------------------------
@@ -16,6 +16,8 @@
  *     AES_XTS_decrypt     micro_aes.h:245-249, micro_aes.c:1085-1093
  *     AES_GCM_encrypt     micro_aes.h:294-300, micro_aes.c:1164-1179
  *     AES_GCM_decrypt     micro_aes.h:302-308, micro_aes.c:1192-1212
+ *     GCM_SIV_encrypt     micro_aes.h:386-392, micro_aes.c:1474-1487   (SURVEY 8f "next" row 1)
+ *     GCM_SIV_decrypt     micro_aes.h:394-400, micro_aes.c:1499-1516
  *
  * A program written against the reference keeps its `#include "micro_aes.h"`,
  * drops micro_aes.c from its build and links one of
@@ -59,7 +61,7 @@
 #define EAX             0
 #define EAXP            0
 #define SIV             0
-#define GCM_SIV         0
+#define GCM_SIV         1
 #define OCB             0
 #define POLY1305        0
 #define CTS             0
@@ -75,6 +77,8 @@ enum constant_parameters_of_modes
     CTR_IV_LENGTH   = 12,       /* micro_aes.h:99  */
     GCM_NONCE_LEN   = 12,       /* micro_aes.h:108 */
     GCM_TAG_LEN     = 16,       /* micro_aes.h:109 */
+    SIVGCM_NONCE_LEN = 12,      /* micro_aes.h:112 */
+    SIVGCM_TAG_LEN  = 16,       /* micro_aes.h:113 */
 #if AES___ != 256 && AES___ != 192
     AES_KEYLENGTH   = 16
 #else
@@ -122,6 +126,15 @@ void AES_GCM_encrypt(const uint8_t *key, const uint8_t *nonce,
 /* verifies the tag at crtxt + crtxtLen first; on mismatch returns
  * M_AUTHENTICATION_ERROR and leaves pntxt untouched */
 char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* GCM-SIV (RFC 8452): 12-byte nonce; crtxt holds ptextLen + SIVGCM_TAG_LEN bytes */
+void GCM_SIV_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+/* decrypts, then authenticates: M_AUTHENTICATION_ERROR means pntxt must be discarded */
+char GCM_SIV_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 

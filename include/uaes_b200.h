@@ -109,6 +109,15 @@ int uaes_gcm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
 int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                      const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* ---- AES-GCM-SIV (RFC 8452), micro_aes.c:1474-1516 ------------- */
+/* nonce = 12 bytes; out holds len + 16 (tag appended).  Two passes (POLYVAL, then CTR). */
+int uaes_gcmsiv_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+/* in holds len + 16.  As in the reference the plaintext is produced before the tag is checked;
+ * UAES_AUTH_ERROR means it must be discarded. */
+int uaes_gcmsiv_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
 /* One GCM message sharded over several GPUs (or calls).  Each shard holds a contiguous byte range
  * starting at block `first_block` of the message; all shards but the last are multiples of 16
  * bytes.  uaes_gcm_shard runs the fused CTR + GHASH pass over the shard (encrypt: GHASH over the

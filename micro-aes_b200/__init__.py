@@ -48,6 +48,8 @@ UAES_ABI = {
     "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
     "uaes_gcm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_gcmsiv_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_gcmsiv_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_shard": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp, _int, _vp]),
     "uaes_gcm_combine": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _vp, _int, _u64, _vp]),
     "uaes_fill_splitmix64": (_int, [_u64, _u64, _vp, _sz]),
@@ -64,6 +66,8 @@ MICRO_AES_ABI = {
     "AES_XTS_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
     "AES_GCM_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_GCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "GCM_SIV_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "GCM_SIV_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
 }
 
 
@@ -190,6 +194,20 @@ class MicroAES:
         return rc, out.raw[:n]
 
 
+    def GCM_SIV_encrypt(self, key, nonce, aData, pntxt):
+        out = ctypes.create_string_buffer(len(pntxt) + 16)
+        self.lib.GCM_SIV_encrypt(key, nonce, aData, len(aData), pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:len(pntxt) + 16]
+
+    def GCM_SIV_decrypt(self, key, nonce, aData, crtxt_and_tag):
+        n = len(crtxt_and_tag) - 16
+        out = ctypes.create_string_buffer(max(n, 1))
+        rc = ord(self.lib.GCM_SIV_decrypt(key, nonce, aData, len(aData), crtxt_and_tag, n, out))
+        self._after()
+        return rc, out.raw[:n]
+
+
 # ---- extensions of include/uaes_b200.h on raw pointers (device or host) ----
 
 def ctr_crypt_range(bits, key, iv, first_block, src, nbytes, dst):
@@ -219,6 +237,11 @@ def gcm_encrypt(bits, key, nonce, aad, src, nbytes, dst):
 def gcm_decrypt(bits, key, nonce, aad, src, nbytes, dst):
     return check(core().uaes_gcm_decrypt(bits, key, nonce, _ptr(aad), len(aad) if aad else 0,
                                          _ptr(src), nbytes, _ptr(dst)))
+
+
+def gcmsiv(bits, key, nonce, aad, src, nbytes, dst, encrypt=True):
+    f = core().uaes_gcmsiv_encrypt if encrypt else core().uaes_gcmsiv_decrypt
+    return check(f(bits, key, nonce, _ptr(aad), len(aad) if aad else 0, _ptr(src), nbytes, _ptr(dst)))
 
 
 def gcm_shard(bits, key, nonce, first_block, src, nbytes, dst, decrypt=False):

@@ -69,3 +69,18 @@ char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
     return code(uaes_gcm_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
                 M_DECRYPTION_ERROR);
 }
+
+void GCM_SIV_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_gcmsiv_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+}
+
+char GCM_SIV_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_gcmsiv_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+                M_DECRYPTION_ERROR);
+}

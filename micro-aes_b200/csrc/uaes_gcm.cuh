@@ -40,6 +40,14 @@ __device__ __forceinline__ uint4 gf_store(Gf g)
     return v;
 }
 
+// POLYVAL (GCM-SIV, micro_aes.c:498-528) is GHASH on byte-reversed blocks with the key
+// mulX_GHASH(ByteReverse(H)) (RFC 8452 appendix A); ByteReverse of a block held as memory words:
+__device__ __forceinline__ uint4 rev_block(uint4 v)
+{
+    return make_uint4(__byte_perm(v.w, 0, 0x0123), __byte_perm(v.z, 0, 0x0123),
+                      __byte_perm(v.y, 0, 0x0123), __byte_perm(v.x, 0, 0x0123));
+}
+
 __device__ inline uint4 load_block_bytes(const uint8_t *p, uint32_t n)   // zero padded, n <= 16
 {
     uint32_t w[4] = {0, 0, 0, 0};
@@ -54,6 +62,8 @@ struct GcmSetupArgs {
     uint32_t j0[4];              // nonce || 00000001 as words (micro_aes.c:1150-1151)
     const uint8_t *aad;
     uint64_t aadlen;
+    int polyval;                 // 1: H comes from auth[] (GCM-SIV message-authentication key)
+    uint32_t auth[4];
     GcmWork *work;
 };
 
@@ -68,7 +78,9 @@ __global__ void gcm_setup_kernel(const __grid_constant__ GcmSetupArgs a)
         uint32_t s[4] = {0, 0, 0, 0};
         if (lane == 1) { s[0] = a.j0[0]; s[1] = a.j0[1]; s[2] = a.j0[2]; s[3] = a.j0[3]; }
         small_encrypt(a.ks.w, a.ks.rounds, s);
-        const uint4 v = make_uint4(s[0], s[1], s[2], s[3]);
+        uint4 v = make_uint4(s[0], s[1], s[2], s[3]);
+        if (lane == 0 && a.polyval)                           // H' = mulX_GHASH(ByteReverse(auth key))
+            v = gf_store(gf_mulx(gf_load(rev_block(make_uint4(a.auth[0], a.auth[1], a.auth[2], a.auth[3])))));
         if (lane == 0) { a.work->H = v; sq[0] = gf_load(v); } else a.work->EJ0 = v;
     }
     __syncwarp();
@@ -88,7 +100,9 @@ __global__ void gcm_setup_kernel(const __grid_constant__ GcmSetupArgs a)
         const Gf H = sq[0];
         for (uint64_t off = 0; off < a.aadlen; off += 16) {
             const uint64_t left = a.aadlen - off;
-            const Gf x = gf_load(load_block_bytes(a.aad + off, left < 16 ? (uint32_t)left : 16));
+            uint4 blk = load_block_bytes(a.aad + off, left < 16 ? (uint32_t)left : 16);
+            if (a.polyval) blk = rev_block(blk);
+            const Gf x = gf_load(blk);
             g.hi ^= x.hi; g.lo ^= x.lo;
             g = gf_mul_fast(H, g);
         }
@@ -144,7 +158,8 @@ __device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t rb, uint32
 // MODE 0: encrypt (CTR, hash the OUTPUT)   MODE 1: hash only (GCM decrypt's verify pass)
 // MODE 2: decrypt shard (CTR, hash the INPUT in the same pass; multi-GPU shards, where the caller
 //         compares the combined tag afterwards)
-template <int NR, int MODE>
+// REV: absorb byte-reversed blocks (POLYVAL)
+template <int NR, int MODE, bool REV = false>
 __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
@@ -233,6 +248,7 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
                 if (MODE == 0) { o0 = t0; o1 = t1; o2 = t2; o3 = t3; }     // GHASH runs over ciphertext
             }
             if (ok) {
+                if (REV) { const uint4 r = rev_block(make_uint4(o0, o1, o2, o3)); o0 = r.x; o1 = r.y; o2 = r.z; o3 = r.w; }
                 if (k == 0) { o0 ^= aad_state.x; o1 ^= aad_state.y; o2 ^= aad_state.z; o3 ^= aad_state.w; }
                 if (any) ghash_mul_const(mb, rb, y0, y1, y2, y3);
                 y0 ^= o0; y1 ^= o1; y2 ^= o2; y3 ^= o3;
@@ -265,6 +281,7 @@ struct GcmFinishArgs {
     uint64_t nparts, chunk_rows; // partials left by the bulk kernel; neighbours are H^(32*rows) apart
     int mode;                    // as gcm_bulk_kernel's MODE
     int partial_only;            // write the GHASH state of this shard instead of a tag
+    int siv;                     // POLYVAL + GCM-SIV tag (micro_aes.c:1454-1462); j0[] = nonce words
     uint8_t *tag_out;            // 16 bytes, any alignment
     GcmWork *work;
 };
@@ -306,6 +323,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
     const uint32_t tail = (uint32_t)(a.len % 16);
     if (tail) {
         uint4 ct = load_block_bytes(a.in + 16 * nfull, tail);   // what GHASH absorbs (zero padded)
+        if (a.siv) ct = rev_block(ct);
         if (a.mode != 1) {                                    // mixThenXor, micro_aes.c:949
             uint32_t w2, w3;
             ctr_words(a.b8, (a.v0 + nfull) & kMask56, w2, w3);
@@ -330,6 +348,16 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
         for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(sw[i >> 2] >> (8 * (i & 3)));
         return;
     }
+    if (a.siv) {
+        // length block LE64(8*aadlen) || LE64(8*len) (micro_aes.c:1427-1429), byte-reversed
+        S.hi ^= a.len * 8; S.lo ^= a.aadlen * 8;
+        S = gf_mul_fast(H, S);
+        const uint4 pv = rev_block(gf_store(S));              // = POLYVAL
+        uint32_t t[4] = {pv.x ^ a.w0, pv.y ^ a.w1, pv.z ^ a.b8, pv.w & 0x7fffffffu};   // ^ nonce, clear bit 127
+        small_encrypt(a.ks.w, a.ks.rounds, t);
+        for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(t[i >> 2] >> (8 * (i & 3)));
+        return;
+    }
     // length block: BE64(8*aadlen) || BE64(8*len)   (micro_aes.c:1130-1132)
     S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
     S = gf_mul_fast(H, S);
@@ -346,12 +374,12 @@ static unsigned gcm_grid(uint64_t nchunks)
     return (unsigned)(need < 1 ? 1 : need < sms ? need : sms);
 }
 
-template <int NR, int MODE>
+template <int NR, int MODE, bool REV = false>
 static cudaError_t launch_gcm_bulk_nr(const GcmBulkArgs &a, cudaStream_t st)
 {
-    cudaError_t e = opt_in_smem(gcm_bulk_kernel<NR, MODE>);
+    cudaError_t e = opt_in_smem(gcm_bulk_kernel<NR, MODE, REV>);
     if (e != cudaSuccess) return e;
-    gcm_bulk_kernel<NR, MODE><<<gcm_grid(a.nchunks), kGcmThreads, kDynSmem, st>>>(a);
+    gcm_bulk_kernel<NR, MODE, REV><<<gcm_grid(a.nchunks), kGcmThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -364,6 +392,73 @@ static void gcm_plan(uint64_t nblocks, uint64_t &rows_per_chunk, uint64_t &nchun
     const uint64_t warps = (uint64_t)sm_count() * kGcmWarps;
     rows_per_chunk = rows ? (rows + warps - 1) / warps : 1;
     nchunks = rows ? (nblocks + 32 * rows_per_chunk - 1) / (32 * rows_per_chunk) : 0;
+}
+
+// ---------------------------------------------------------------- GCM-SIV pieces
+
+struct SivDeriveArgs {
+    uaes_keysched master;
+    uint32_t nonce[3];
+    uint8_t *out;                // 8 bytes per derived half block, (2 + Nk/2) of them
+};
+
+// GCM_SIVsetup (micro_aes.c:1437-1451): E_K(LE32(i) || nonce), the first 8 bytes of each
+__global__ void gcmsiv_derive_kernel(const __grid_constant__ SivDeriveArgs a)
+{
+    const uint32_t n = 2 + (a.master.rounds - 6) / 2;
+    if (threadIdx.x >= n) return;
+    uint32_t s[4] = {threadIdx.x, a.nonce[0], a.nonce[1], a.nonce[2]};
+    small_encrypt(a.master.w, a.master.rounds, s);
+    for (uint32_t i = 0; i < 8; ++i) a.out[8 * threadIdx.x + i] = (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
+}
+
+struct Ctr32Args {
+    uaes_keysched ks;
+    const uint8_t *tag;          // 16 bytes in device memory: the initial counter block
+    const uint4 *in;
+    uint4 *out;
+    uint64_t nblocks;
+    uint32_t tail;
+};
+
+// CTR_cipher with mode SIVGCM_CTR (micro_aes.c:935-938): bit 7 of byte 15 forced, the counter is
+// the little-endian 32-bit word in bytes 0..3 and wraps modulo 2^32
+template <int NR>
+__global__ void __launch_bounds__(kThreads, 1) ctr32_kernel(const __grid_constant__ Ctr32Args a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.ks.w;
+    const uint4 c = load_block_bytes(a.tag, 16);
+    const uint32_t c3 = c.w | 0x80000000u;
+    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+    uint64_t k = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+
+    uint4 cur = k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
+    for (; k < a.nblocks; k += stride) {
+        const uint4 nxt = k + stride < a.nblocks ? ld_stream(a.in + k + stride) : make_uint4(0, 0, 0, 0);
+        uint32_t s0 = c.x + (uint32_t)k, s1 = c.y, s2 = c.z, s3 = c3;
+        enc_block<NR>(lb, s0, s1, s2, s3, rk, cur.x, cur.y, cur.z, cur.w);
+        st_stream(a.out + k, make_uint4(s0, s1, s2, s3));
+        cur = nxt;
+    }
+    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t s[4] = {c.x + (uint32_t)a.nblocks, c.y, c.z, c3};
+        enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
+        const uint8_t *x = (const uint8_t *)(a.in + a.nblocks);
+        uint8_t *y = (uint8_t *)(a.out + a.nblocks);
+        for (uint32_t i = 0; i < a.tail; ++i) y[i] = x[i] ^ (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
+template <int NR>
+static cudaError_t launch_ctr32_nr(const Ctr32Args &a, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(ctr32_kernel<NR>);
+    if (e != cudaSuccess) return e;
+    ctr32_kernel<NR><<<grid_for((a.nblocks + 31) / 32), kThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- multi-shard combine
@@ -452,6 +547,8 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     s.ks = *ks;
     for (int c = 0; c < 4; ++c) s.j0[c] = j0[c];
     s.aad = (const uint8_t *)aad_dev; s.aadlen = aadlen; s.work = (GcmWork *)work;
+    s.polyval = 0;
+    s.auth[0] = s.auth[1] = s.auth[2] = s.auth[3] = 0;
     gcm_setup_kernel<<<1, 32, 0, st>>>(s);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -487,7 +584,7 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     f.ks = *ks;
     f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1 + first_block) & kMask56;
     f.in = (const uint8_t *)in; f.out = (uint8_t *)out;
-    f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.mode = mode; f.partial_only = partial_only;
+    f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.mode = mode; f.partial_only = partial_only; f.siv = 0;
     f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
     ++g_launches;
@@ -511,4 +608,84 @@ extern "C" int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned c
     gcm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
     return (int)cudaGetLastError();
+}
+
+extern "C" int uaes_launch_gcmsiv_derive(const uaes_keysched *master, const unsigned char nonce[12],
+                                         void *out_dev, void *stream)
+{
+    using namespace uaes;
+    SivDeriveArgs a;
+    a.master = *master;
+    for (int c = 0; c < 3; ++c)
+        a.nonce[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
+    a.out = (uint8_t *)out_dev;
+    gcmsiv_derive_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+// POLYVAL(auth; aad, data) -> GCM-SIV tag = E_enc((POLYVAL ^ nonce) with bit 127 cleared)
+extern "C" int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned char auth[16],
+                                      const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
+                                      const void *data, u64 len, void *tag_out, void *work, void *stream)
+{
+    using namespace uaes;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t nblocks = len / 16;
+    uint64_t rows_per_chunk, nchunks;
+    gcm_plan(nblocks, rows_per_chunk, nchunks);
+    uint32_t nw[3];
+    for (int c = 0; c < 3; ++c)
+        nw[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
+
+    GcmSetupArgs s;
+    s.ks = *enc;
+    s.j0[0] = s.j0[1] = s.j0[2] = s.j0[3] = 0;
+    s.aad = (const uint8_t *)aad_dev; s.aadlen = aadlen; s.work = (GcmWork *)work;
+    s.polyval = 1;
+    for (int c = 0; c < 4; ++c)
+        s.auth[c] = (uint32_t)auth[4 * c] | (uint32_t)auth[4 * c + 1] << 8 | (uint32_t)auth[4 * c + 2] << 16 | (uint32_t)auth[4 * c + 3] << 24;
+    gcm_setup_kernel<<<1, 32, 0, st>>>(s);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+
+    if (nchunks) {
+        GcmBulkArgs b;
+        b.ks = *enc;
+        b.w0 = b.w1 = b.b8 = 0; b.v0 = 0;
+        b.in = (const uint4 *)data; b.out = nullptr;
+        b.nblocks = nblocks; b.chunk_blocks = 32 * rows_per_chunk; b.nchunks = nchunks; b.work = (GcmWork *)work;
+        e = launch_gcm_bulk_nr<10, 1, true>(b, st);          // hash only: NR is irrelevant
+        if (e != cudaSuccess) return (int)e;
+    }
+    GcmFinishArgs f;
+    f.ks = *enc;
+    f.w0 = nw[0]; f.w1 = nw[1]; f.b8 = nw[2]; f.v0 = 0;      // the nonce words ride in the counter fields
+    f.in = (const uint8_t *)data; f.out = nullptr;
+    f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk;
+    f.mode = 1; f.partial_only = 0; f.siv = 1;
+    f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
+    gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int uaes_launch_ctr32(const uaes_keysched *enc, const void *tag_dev, const void *in, void *out,
+                                 u64 len, void *stream)
+{
+    using namespace uaes;
+    if (len == 0) return 0;
+    Ctr32Args a;
+    a.ks = *enc;
+    a.tag = (const uint8_t *)tag_dev;
+    a.in = (const uint4 *)in; a.out = (uint4 *)out;
+    a.nblocks = len / 16; a.tail = (uint32_t)(len % 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (enc->rounds) {
+    case 10: return (int)launch_ctr32_nr<10>(a, st);
+    case 12: return (int)launch_ctr32_nr<12>(a, st);
+    case 14: return (int)launch_ctr32_nr<14>(a, st);
+    }
+    return (int)cudaErrorInvalidValue;
 }

@@ -632,6 +632,96 @@ done:
     return rc;
 }
 
+/* ------------------------------------------------------------------ GCM-SIV */
+
+/* micro_aes.c:1474-1516.  Two passes by construction (the tag is the CTR seed): encrypt =
+ * POLYVAL over the plaintext, tag, then CTR; decrypt = CTR seeded by the received tag, POLYVAL
+ * over the result, compare (like the reference, the plaintext is written before the check). */
+static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
+                         const void *in, size_t len, void *out, int decrypt)
+{
+    devctx *c;
+    uaes_keysched master, enc;
+    int rc, direct;
+    const void *din, *daad;
+    void *dout;
+    u8 *work, *dtag, *dderived, derived[48];
+    size_t wbytes;
+    cudaStream_t st;
+
+    if (expand_key(keybits, key, &master)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+
+    if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
+    else         direct = is_direct(out) && (len == 0 || is_direct(in));
+    st = direct ? (cudaStream_t)tls_stream : c->st[0];
+    wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + aadlen + 64;
+    if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM-SIV work)")) != 0) goto done;
+    dtag = (u8 *)c->work;                 /* [0,16) computed tag, [64,112) derived key material */
+    dderived = (u8 *)c->work + 64;
+    work = (u8 *)c->work + GCM_WORK_HEAD;
+
+    /* message keys: E_K(LE32(i) || nonce) on the device, KeyExpansion of the result on the host */
+    LAUNCH(uaes_launch_gcmsiv_derive(&master, nonce, dderived, st));
+    CU(cudaMemcpyAsync(derived, dderived, 48, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    expand_key(keybits, derived + 16, &enc);
+
+    daad = NULL;
+    if (aadlen) {
+        u8 *a = work + uaes_gcm_work_bytes(len);
+        a += (16 - ((size_t)a & 15)) & 15;
+        CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
+        daad = a;
+    }
+    if (direct) {
+        din = in; dout = out;
+    } else {
+        if ((rc = grow(&c->big, &c->big_bytes, len + 32, "cudaMalloc(GCM-SIV staging)")) != 0) goto done;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
+        din = c->big; dout = c->big;
+    }
+
+    if (!decrypt) {
+        u8 *tagpos = (u8 *)dout + len;
+        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, daad, aadlen, din, len, dtag, work, st));
+        LAUNCH(uaes_launch_ctr32(&enc, dtag, din, dout, len, st));
+        CU(cudaMemcpyAsync(tagpos, dtag, 16, cudaMemcpyDefault, st));
+        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
+        if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
+    } else {
+        u8 t1[16], t2[16];
+        const u8 *rtag = (const u8 *)din + len;
+        /* the received tag seeds the counter; keep a copy, in-place decryption may overwrite nothing
+         * beyond len but the staging buffer is shared */
+        CU(cudaMemcpyAsync(dtag + 16, rtag, 16, cudaMemcpyDefault, st));
+        LAUNCH(uaes_launch_ctr32(&enc, dtag + 16, din, dout, len, st));
+        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, daad, aadlen, dout, len, dtag, work, st));
+        if (!direct && len) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(t2, dtag + 16, 16, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));
+        if (memcmp(t1, t2, 16)) rc = UAES_AUTH_ERROR;         /* micro_aes.c:1510-1514 */
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_gcmsiv_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out)
+{
+    return gcmsiv_common(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+}
+
+int uaes_gcmsiv_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out)
+{
+    return gcmsiv_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords)

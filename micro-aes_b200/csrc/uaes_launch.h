@@ -71,6 +71,17 @@ int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char nonce[1
                             u64 aadlen, u64 len, const void *partials_dev, const void *after_dev,
                             unsigned nshards, void *tag_out, void *stream);
 
+/* GCM-SIV (micro_aes.c:1418-1516): key derivation blocks (8 bytes each, 2 + Nk/2 of them) into
+ * device memory; POLYVAL + tag; CTR with the 32-bit little-endian counter seeded by a tag that
+ * lives in device memory */
+int uaes_launch_gcmsiv_derive(const uaes_keysched *master, const unsigned char nonce[12],
+                              void *out_dev, void *stream);
+int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned char auth[16],
+                           const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
+                           const void *data, u64 len, void *tag_out, void *work, void *stream);
+int uaes_launch_ctr32(const uaes_keysched *enc, const void *tag_dev, const void *in, void *out,
+                      u64 len, void *stream);
+
 /* synthetic data + checksum helpers */
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
 int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);

@@ -483,6 +483,136 @@ int oracle_gcm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
 }
 
 /* ------------------------------------------------------------------------ */
+/* GCM-SIV                                                                  */
+/* ------------------------------------------------------------------------ */
+
+/* micro_aes.c:498-508 (divideLblock): little-endian shift right, 0xE1 into byte 15 */
+static void polyval_halve(uint8_t y[16])
+{
+    const unsigned lsb = y[0] & 1;
+    int i;
+    for (i = 0; i < 15; ++i) y[i] = (uint8_t)(y[i] >> 1 | y[i + 1] << 7);
+    y[15] >>= 1;
+    if (lsb) y[15] ^= 0xe1;
+}
+
+/* micro_aes.c:511-528 (dotGF128): bytes of x from last to first, bits MSB first, halve BEFORE use */
+void oracle_dot128(const uint8_t x[16], uint8_t y[16])
+{
+    uint8_t acc[16] = {0};
+    int i, b;
+    for (i = 15; i >= 0; --i)
+        for (b = 0x80; b; b >>= 1) {
+            polyval_halve(y);
+            if (x[i] & b) xor16(acc, y);
+        }
+    memcpy(y, acc, 16);
+}
+
+static void polyval_absorb(const uint8_t H[16], const uint8_t *x, size_t len, uint8_t g[16])
+{
+    size_t i;
+    for (; len >= 16; len -= 16, x += 16) {
+        xor16(g, x);
+        oracle_dot128(H, g);
+    }
+    if (len) {
+        for (i = 0; i < len; ++i) g[i] ^= x[i];
+        oracle_dot128(H, g);
+    }
+}
+
+/* micro_aes.c:1423-1434 (polyval) */
+void oracle_polyval(const uint8_t H[16], const void *aad, size_t aadlen,
+                    const void *pt, size_t ptlen, uint8_t out[16])
+{
+    uint8_t lens[16];
+    uint64_t abits = (uint64_t)aadlen * 8, pbits = (uint64_t)ptlen * 8;
+    int i;
+    for (i = 0; i < 8; ++i, abits >>= 8) lens[i] = (uint8_t)abits;       /* copyLint(len, .., 0)  */
+    for (i = 8; i < 16; ++i, pbits >>= 8) lens[i] = (uint8_t)pbits;      /* copyLint(len, .., HB) */
+    memset(out, 0, 16);
+    polyval_absorb(H, (const uint8_t *)aad, aadlen, out);
+    polyval_absorb(H, (const uint8_t *)pt, ptlen, out);
+    polyval_absorb(H, lens, 16, out);
+}
+
+/* micro_aes.c:1437-1451 (GCM_SIVsetup): E_K(LE32(i) || nonce), first 8 bytes of each */
+static void gcmsiv_setup(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                         uint8_t auth[16], aes_ctx *enc)
+{
+    aes_ctx master;
+    uint8_t blk[16], out[16], derived[48];
+    const int n = 2 + keybits / 64;
+    int i;
+    key_setup(&master, keybits, key);
+    memset(blk, 0, 4);
+    memcpy(blk + 4, nonce, 12);
+    for (i = 0; i < n; ++i) {
+        blk[0] = (uint8_t)i;
+        encrypt_block(&master, blk, out);
+        memcpy(derived + 8 * i, out, 8);
+    }
+    memcpy(auth, derived, 16);
+    key_setup(enc, keybits, derived + 16);
+}
+
+/* micro_aes.c:1454-1462 (GCM_SIVtag) */
+static void gcmsiv_tag(const aes_ctx *enc, const uint8_t nonce[12], uint8_t pv[16], uint8_t tag[16])
+{
+    int i;
+    for (i = 0; i < 12; ++i) pv[i] ^= nonce[i];
+    pv[15] &= 0x7f;
+    encrypt_block(enc, pv, tag);
+}
+
+/* CTR_cipher with mode SIVGCM_CTR (micro_aes.c:935-938, 943-949): bit 7 of byte 15 set, the
+ * counter is the little-endian 32-bit word in bytes 0..3 and wraps modulo 2^32 */
+static void gcmsiv_ctr(const aes_ctx *enc, const uint8_t tag[16], const uint8_t *x, size_t len, uint8_t *y)
+{
+    uint8_t c[16], ks[16];
+    uint32_t ctr;
+    size_t i;
+    memcpy(c, tag, 16);
+    c[15] |= 0x80;
+    ctr = (uint32_t)c[0] | (uint32_t)c[1] << 8 | (uint32_t)c[2] << 16 | (uint32_t)c[3] << 24;
+    for (; len; x += 16, y += 16, ++ctr) {
+        const size_t n = len < 16 ? len : 16;
+        c[0] = (uint8_t)ctr; c[1] = (uint8_t)(ctr >> 8); c[2] = (uint8_t)(ctr >> 16); c[3] = (uint8_t)(ctr >> 24);
+        encrypt_block(enc, c, ks);
+        for (i = 0; i < n; ++i) y[i] = x[i] ^ ks[i];
+        len -= n;
+    }
+}
+
+/* micro_aes.c:1474-1487 */
+void oracle_gcmsiv_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx enc;
+    uint8_t auth[16], pv[16], tag[16];
+    gcmsiv_setup(keybits, key, nonce, auth, &enc);
+    oracle_polyval(auth, aad, aadlen, in, len, pv);
+    gcmsiv_tag(&enc, nonce, pv, tag);
+    gcmsiv_ctr(&enc, tag, (const uint8_t *)in, len, (uint8_t *)out);
+    memcpy((uint8_t *)out + len, tag, 16);
+}
+
+/* micro_aes.c:1499-1516: decrypt first, then authenticate the plaintext */
+int oracle_gcmsiv_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                          const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx enc;
+    uint8_t auth[16], pv[16], tag[16], got[16];
+    memcpy(got, (const uint8_t *)in + len, 16);
+    gcmsiv_setup(keybits, key, nonce, auth, &enc);
+    gcmsiv_ctr(&enc, got, (const uint8_t *)in, len, (uint8_t *)out);
+    oracle_polyval(auth, aad, aadlen, out, len, pv);
+    gcmsiv_tag(&enc, nonce, pv, tag);
+    return memcmp(tag, got, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
 /* synthetic data                                                           */
 /* ------------------------------------------------------------------------ */
 

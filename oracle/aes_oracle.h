@@ -81,6 +81,19 @@ void oracle_gf128_mul(const uint8_t x[16], uint8_t y[16]);
 /* T <- alpha*T in XTS's GF(2^128) (micro_aes.c:449-458) */
 void oracle_xts_double(uint8_t t[16]);
 
+/* ---- SURVEY.md 8f "next" row 1: AES-GCM-SIV (RFC 8452), micro_aes.c:1418-1516 ---- */
+/* POLYVAL(H; aad, pt) including the little-endian length block (micro_aes.c:1423-1434) */
+void oracle_polyval(const uint8_t H[16], const void *aad, size_t aadlen,
+                    const void *pt, size_t ptlen, uint8_t out[16]);
+/* y <- dot(x, y), POLYVAL's field product (micro_aes.c:511-528) */
+void oracle_dot128(const uint8_t x[16], uint8_t y[16]);
+/* 12-byte nonce, 16-byte tag appended at out+len */
+void oracle_gcmsiv_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+/* in holds len+16; like the reference the plaintext is written BEFORE the tag is checked */
+int  oracle_gcmsiv_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
 /* splitmix64 synthetic-data generator shared by tests and bench: 64-bit word w of
  * the buffer (byte offset 8w, little-endian) = splitmix64(seed + first_word + w) */
 void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords);

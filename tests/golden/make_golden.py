@@ -72,6 +72,14 @@ def main_c_vectors():
                        "ct": s["cipherKey"][0][32:]},
         "ecb128": ecb128, "ctr128": ctr128, "ctr128_preset_counter": ctr128_preset,
         "xts128": xts128, "xts256": xts256, "gcm128": gcm128, "gcm256": gcm256,
+        # GCM-SIV, main.c:61-63 (same inputs) and the two RFC 8452 cases main.c:275-299
+        "gcmsiv128": s["gsvcipher"][0],
+        "gcmsiv_rfc8452": [
+            {"key": "ee8e1ed9ff2540ae8f2ba9f50bc2f27c", "iv": "752abad3e0afb5f434dc4310", "aad": "6578616d706c65",
+             "pt": "48656c6c6f20776f726c64", "ct": "5d349ead175ef6b1def6fd4fbcdeb7e4793f4a1d7e4faa70100af1"},
+            {"key": "01000000000000000000000000000000", "iv": "030000000000000000000000", "aad": "01",
+             "pt": "0200000000000000000000000000000003000000000000000000000000000000",
+             "ct": "620048ef3c1e73e57e02bb8562c416a319e73e4caac8e96a1ecb2933145a1d71e6af6a7f87287da059a71684ed3498e1"}],
     }
 
 
@@ -111,6 +119,22 @@ def parse_gcm(path, keybits):
     return cases
 
 
+def parse_gcmsiv(path, keybits):
+    """testvectors/SIV_GCM_ACVP.tv, kept when the key has the build's size
+    (aes_testvectors_GCMSIV.h:84)"""
+    cases, cur = [], {}
+    for line in open(path):
+        line = line.strip()
+        if " = " in line or line.endswith(" ="):
+            k, _, v = line.partition(" =")
+            cur[k.strip()] = v.strip().lower()
+            if "pt" in cur and "ct" in cur and "key" in cur and "iv" in cur and "aad" in cur:
+                if len(cur["key"]) == keybits // 4:
+                    cases.append({k2: cur[k2] for k2 in ("key", "iv", "aad", "pt", "ct")})
+                cur = {}
+    return cases
+
+
 def rnd(tag, n):
     """deterministic pseudo-random bytes: SHA-256 in counter mode over a tag"""
     out = b""
@@ -129,7 +153,7 @@ def ref_samples():
     out = {"source": "oracle/_ref/libref*.so = unmodified /root/reference/micro_aes.c, "
                      "gcc -O2 -fno-strict-aliasing; inputs = SHA-256 counter streams (rnd())",
            "ctr": [], "ctr_preset_counter": [], "ecb": [], "xts": [], "xts_sectors": [],
-           "gcm": []}
+           "gcm": [], "gcmsiv": []}
     sha = lambda b: hashlib.sha256(b).hexdigest()
     for bits, lib in libs.items():
         ks = bits // 8
@@ -174,6 +198,30 @@ def ref_samples():
             out["gcm"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
                                "aad_tag": f"gcma{bits}{n}", "pt_tag": f"gcmp{bits}{n}",
                                "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    for bits, lib in libs.items():
+        ks = bits // 8
+        for n, a in ((0, 0), (1, 0), (16, 16), (57, 31), (1000, 20), (4096 + 3, 129), (1 << 18, 7)):
+            key, nonce = rnd(f"gsk{bits}{n}", ks), rnd(f"gsn{bits}{n}", 12)
+            aad, pt = rnd(f"gsa{bits}{n}", a), rnd(f"gsp{bits}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.GCM_SIV_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            out["gcmsiv"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                                  "aad_tag": f"gsa{bits}{n}", "pt_tag": f"gsp{bits}{n}",
+                                  "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    # The 32-bit little-endian counter of GCM-SIV wraps (micro_aes.c:935-938).  The counter starts at
+    # the tag, and GCM_SIV_decrypt runs CTR with the RECEIVED tag before it authenticates
+    # (micro_aes.c:1505-1515), so a forged tag ff ff ff f8 .. pins the wrap: the call fails with
+    # M_AUTHENTICATION_ERROR but the output buffer holds input ^ keystream across the wrap.
+    out["gcmsiv_forged_tag_decrypt"] = []
+    for bits, lib in libs.items():
+        lib.GCM_SIV_decrypt.restype = ctypes.c_char
+        key, nonce, ct = rnd(f"gsfk{bits}", bits // 8), rnd(f"gsfn{bits}", 12), rnd(f"gsfc{bits}", 16 * 40 + 3)
+        tag = bytes.fromhex("f8ffffff") + rnd(f"gsft{bits}", 12)
+        o = ctypes.create_string_buffer(len(ct) + 16)
+        rc = lib.GCM_SIV_decrypt(key, nonce, b"", ctypes.c_size_t(0), ct + tag, ctypes.c_size_t(len(ct)), o)
+        out["gcmsiv_forged_tag_decrypt"].append({"bits": bits, "key": key.hex(), "nonce": nonce.hex(),
+                                                 "ct_tag": f"gsfc{bits}", "n": len(ct), "tag": tag.hex(),
+                                                 "rc": ord(rc), "out_sha256": sha(o.raw[:len(ct)])})
     # counter carries: the PRESET_COUNTER build takes the caller's 16-byte block as counter 0
     for name, ctr_hex in (("byte15", "00112233445566778899aabbccddeeff"),
                           ("into_nonce_byte11", "000102030405060708090a0bfffffffe"),
@@ -202,6 +250,10 @@ def main():
         w(f"gcm{bits}.json", {"source": f"testvectors/GcmEncryptExtIV{bits}.rsp, filter of aes_testvectors_GCM.h:86",
                               "cases": c})
         print(f"gcm{bits}: {len(c)} cases")
+    c = parse_gcmsiv(os.path.join(tv, "SIV_GCM_ACVP.tv"), 128)
+    w("gcmsiv128.json", {"source": "testvectors/SIV_GCM_ACVP.tv (102 AES-128 cases, aes_testvectors_GCMSIV.h)",
+                         "cases": c})
+    print(f"gcmsiv128: {len(c)} cases")
     w("oracle_ref_samples.json", ref_samples())
     print("ok")
 

@@ -342,3 +342,54 @@ def test_gcm_sharded_message(uaes, orc, torch):
             back += dst.raw[:b - a]
             after.append(total_blocks - (b + 15) // 16)
         assert back == data and uaes.gcm_combine(bits, key, nonce, aad, parts, after, n) == want[-16:]
+
+
+# ---------------------------------------------------------------- GCM-SIV
+
+def test_gcmsiv_reference_vectors(uaes):
+    m = golden("main_c.json")
+    a = uaes.MicroAES(128)
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"])[:12], H(m["aad"]), H(m["plaintext"])
+    out = a.GCM_SIV_encrypt(key, nonce, aad, pt)               # main.c:219-224
+    assert out == H(m["gcmsiv128"])
+    assert a.GCM_SIV_decrypt(key, nonce, aad, out) == (0, pt)
+    for v in m["gcmsiv_rfc8452"]:                              # main.c:275-299
+        assert a.GCM_SIV_encrypt(H(v["key"]), H(v["iv"]), H(v["aad"]), H(v["pt"])) == H(v["ct"])
+    cases = golden("gcmsiv128.json")["cases"]                  # testvectors/SIV_GCM_ACVP.tv
+    assert len(cases) == 102
+    for c in cases:
+        assert a.GCM_SIV_encrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+        assert a.GCM_SIV_decrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"])), c
+
+
+def test_gcmsiv_recorded_reference_and_oracle(uaes, orc, torch):
+    s = golden("oracle_ref_samples.json")
+    lib = {b: uaes.MicroAES(b) for b in (128, 192, 256)}
+    for c in s["gcmsiv"]:
+        out = lib[c["bits"]].GCM_SIV_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]),
+                                             rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+    for c in s["gcmsiv_forged_tag_decrypt"]:                   # 32-bit LE counter wrap; auth must fail
+        rc, out = lib[c["bits"]].GCM_SIV_decrypt(H(c["key"]), H(c["nonce"]), b"", rnd(c["ct_tag"], c["n"]) + H(c["tag"]))
+        assert rc == 0x1A and sha256(out) == c["out_sha256"], c
+    for bits in (128, 256):
+        for n, alen in [(0, 0), (0, 5), (15, 0), (16, 1), (33, 100), (4095, 7), ((1 << 20) + 9, 20), (3 * (1 << 20), 0)]:
+            key, nonce = rnd(f"gv-k{bits}{n}", bits // 8), rnd(f"gv-n{bits}{n}", 12)
+            aad, data = rnd(f"gv-a{bits}{n}", alen), rnd(f"gv-d{bits}{n}", n)
+            want = orc.gcmsiv_encrypt(key, nonce, aad, data)
+            assert lib[bits].GCM_SIV_encrypt(key, nonce, aad, data) == want, (bits, n)
+            assert lib[bits].GCM_SIV_decrypt(key, nonce, aad, want) == (0, data), (bits, n)
+            if n:
+                bad = bytearray(want)
+                bad[n // 2] ^= 1
+                assert lib[bits].GCM_SIV_decrypt(key, nonce, aad, bytes(bad))[0] == 0x1A
+    # device pointers, in place
+    key, nonce, aad = rnd("gv-dk", 16), rnd("gv-dn", 12), rnd("gv-da", 33)
+    n = (1 << 21) + 5
+    data = rnd("gv-dd", n)
+    want = orc.gcmsiv_encrypt(key, nonce, aad, data)
+    buf = dev(torch, data, pad=16)
+    uaes.gcmsiv(128, key, nonce, aad, buf, n, buf, True)
+    assert host(buf, 0, n + 16) == want
+    assert uaes.gcmsiv(128, key, nonce, aad, buf, n, buf, False) == 0
+    assert host(buf, 0, n) == data

@@ -160,6 +160,33 @@ def test_ref_samples_ecb_xts_gcm(orc):
         assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
 
 
+# ---------------------------------------------------------------- GCM-SIV
+
+def test_gcmsiv_vectors(orc):
+    m = golden("main_c.json")
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"])[:12], H(m["aad"]), H(m["plaintext"])
+    out = orc.gcmsiv_encrypt(key, nonce, aad, pt)           # main.c:219-224
+    assert out == H(m["gcmsiv128"])
+    assert orc.gcmsiv_decrypt(key, nonce, aad, out) == (0, pt)
+    for v in m["gcmsiv_rfc8452"]:                           # main.c:275-299
+        assert orc.gcmsiv_encrypt(H(v["key"]), H(v["iv"]), H(v["aad"]), H(v["pt"])) == H(v["ct"])
+    cases = golden("gcmsiv128.json")["cases"]
+    assert len(cases) == 102
+    for c in cases:
+        assert orc.gcmsiv_encrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+        assert orc.gcmsiv_decrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"]))
+
+
+def test_gcmsiv_recorded_reference_outputs(orc):
+    s = golden("oracle_ref_samples.json")
+    for c in s["gcmsiv"]:
+        out = orc.gcmsiv_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+    for c in s["gcmsiv_forged_tag_decrypt"]:               # 32-bit LE counter wrap, micro_aes.c:935-938
+        rc, out = orc.gcmsiv_decrypt(H(c["key"]), H(c["nonce"]), b"", rnd(c["ct_tag"], c["n"]) + H(c["tag"]))
+        assert rc == c["rc"] == 0x1A and sha256(out) == c["out_sha256"]
+
+
 # ---------------------------------------------------------------- edge cases
 
 def test_edge_cases(orc):

@@ -53,6 +53,9 @@ class Oracle:
         L.oracle_gf128_mul.argtypes = [_u8p, _u8p]
         L.oracle_ghash_absorb.argtypes = [_u8p, ctypes.c_void_p, _sz, _u8p]
         L.oracle_xts_double.argtypes = [_u8p]
+        L.oracle_gcmsiv_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_gcmsiv_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_polyval.argtypes = [_u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
 
     @staticmethod
@@ -113,6 +116,22 @@ class Oracle:
         rc = self.lib.oracle_gcm_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
         return rc, o.raw[:n]
 
+    def gcmsiv_encrypt(self, key, nonce, aad, pt):
+        o = self._buf(len(pt) + 16)
+        self.lib.oracle_gcmsiv_encrypt(len(key) * 8, key, nonce, aad, len(aad), pt, len(pt), o)
+        return o.raw[:len(pt) + 16]
+
+    def gcmsiv_decrypt(self, key, nonce, aad, ct_and_tag):
+        n = len(ct_and_tag) - 16
+        o = self._buf(n)
+        rc = self.lib.oracle_gcmsiv_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
+        return rc, o.raw[:n]
+
+    def polyval(self, H, aad, pt):
+        o = self._buf(16)
+        self.lib.oracle_polyval(H, aad, len(aad), pt, len(pt), o)
+        return o.raw[:16]
+
     def ghash(self, H, aad, ct):
         o = self._buf(16)
         self.lib.oracle_ghash(H, aad, len(aad), ct, len(ct), o)
@@ -156,7 +175,7 @@ class Reference:
         self.path = os.path.join(ROOT, "oracle", "_ref", name)
         self.bits = bits
         self.lib = ctypes.CDLL(self.path)
-        for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt"):
+        for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt", "GCM_SIV_decrypt"):
             getattr(self.lib, f).restype = ctypes.c_char
 
     @staticmethod
@@ -190,6 +209,17 @@ class Reference:
         o = ctypes.create_string_buffer(len(pt) + 16)
         self.lib.AES_GCM_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
         return o.raw[:len(pt) + 16]
+
+    def gcmsiv_encrypt(self, key, nonce, aad, pt):
+        o = ctypes.create_string_buffer(len(pt) + 16)
+        self.lib.GCM_SIV_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
+        return o.raw[:len(pt) + 16]
+
+    def gcmsiv_decrypt(self, key, nonce, aad, ct_and_tag):
+        n = len(ct_and_tag) - 16
+        o = ctypes.create_string_buffer(n + 16)
+        rc = self.lib.GCM_SIV_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
+        return ord(rc), o.raw[:n]
 
     def gcm_decrypt(self, key, nonce, aad, ct_and_tag):
         n = len(ct_and_tag) - 16
