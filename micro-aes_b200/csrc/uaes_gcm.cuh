@@ -62,6 +62,7 @@ struct GcmSetupArgs {
     uint32_t j0[4];              // nonce || 00000001 as words (micro_aes.c:1150-1151)
     const uint8_t *aad;
     uint64_t aadlen;
+    const uint4 *aad_state_in;   // non-null: GHASH state of the AAD computed by a bulk pass (large AAD)
     int polyval;                 // 1: H comes from auth[] (GCM-SIV message-authentication key)
     uint32_t auth[4];
     GcmWork *work;
@@ -95,7 +96,9 @@ __global__ void gcm_setup_kernel(const __grid_constant__ GcmSetupArgs a)
         a.work->lanepow[lane] = gf_store(p);
         if (e == 32) a.work->C32 = gf_store(p);
     }
-    if (lane == 0) {
+    if (lane == 0 && a.aad_state_in) {
+        a.work->aad_state = *a.aad_state_in;
+    } else if (lane == 0) {
         Gf g{0, 0};
         const Gf H = sq[0];
         for (uint64_t off = 0; off < a.aadlen; off += 16) {
@@ -529,8 +532,9 @@ extern "C" size_t uaes_gcm_work_bytes(u64 len)
 }
 
 extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
-                               u64 aadlen, const void *in, void *out, u64 len, int mode, u64 first_block,
-                               int partial_only, void *tag_out, void *work, void *stream)
+                               u64 aadlen, const void *aad_state_dev, const void *in, void *out, u64 len,
+                               int mode, u64 first_block, int partial_only, void *tag_out, void *work,
+                               void *stream)
 {
     using namespace uaes;
     cudaStream_t st = (cudaStream_t)stream;
@@ -547,6 +551,7 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     s.ks = *ks;
     for (int c = 0; c < 4; ++c) s.j0[c] = j0[c];
     s.aad = (const uint8_t *)aad_dev; s.aadlen = aadlen; s.work = (GcmWork *)work;
+    s.aad_state_in = (const uint4 *)aad_state_dev;
     s.polyval = 0;
     s.auth[0] = s.auth[1] = s.auth[2] = s.auth[3] = 0;
     gcm_setup_kernel<<<1, 32, 0, st>>>(s);
@@ -627,7 +632,8 @@ extern "C" int uaes_launch_gcmsiv_derive(const uaes_keysched *master, const unsi
 // POLYVAL(auth; aad, data) -> GCM-SIV tag = E_enc((POLYVAL ^ nonce) with bit 127 cleared)
 extern "C" int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned char auth[16],
                                       const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
-                                      const void *data, u64 len, void *tag_out, void *work, void *stream)
+                                      const void *aad_state_dev, const void *data, u64 len, int partial_only,
+                                      void *tag_out, void *work, void *stream)
 {
     using namespace uaes;
     cudaStream_t st = (cudaStream_t)stream;
@@ -642,6 +648,7 @@ extern "C" int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned c
     s.ks = *enc;
     s.j0[0] = s.j0[1] = s.j0[2] = s.j0[3] = 0;
     s.aad = (const uint8_t *)aad_dev; s.aadlen = aadlen; s.work = (GcmWork *)work;
+    s.aad_state_in = (const uint4 *)aad_state_dev;
     s.polyval = 1;
     for (int c = 0; c < 4; ++c)
         s.auth[c] = (uint32_t)auth[4 * c] | (uint32_t)auth[4 * c + 1] << 8 | (uint32_t)auth[4 * c + 2] << 16 | (uint32_t)auth[4 * c + 3] << 24;
@@ -664,7 +671,7 @@ extern "C" int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned c
     f.w0 = nw[0]; f.w1 = nw[1]; f.b8 = nw[2]; f.v0 = 0;      // the nonce words ride in the counter fields
     f.in = (const uint8_t *)data; f.out = nullptr;
     f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk;
-    f.mode = 1; f.partial_only = 0; f.siv = 1;
+    f.mode = 1; f.partial_only = partial_only; f.siv = 1;
     f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
     ++g_launches;

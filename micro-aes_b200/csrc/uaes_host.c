@@ -482,6 +482,8 @@ int uaes_xts_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, con
 /* ------------------------------------------------------------------ GCM */
 
 #define GCM_WORK_HEAD 1024   /* tag scratch lives in front of the kernels' work area */
+#define AAD_STATE_OFF 128    /* 16 bytes inside the head: GHASH state of a bulk-hashed AAD */
+#define AAD_BULK_MIN  4096   /* larger AADs are hashed by the bulk kernel instead of one lane */
 
 /* common part: returns with data resident on the device (din/dout), AAD on the device, work ready */
 static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
@@ -492,7 +494,7 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *a
     int rc, direct;
     const void *din, *daad;
     void *dout;
-    u8 *work, *dtag;
+    u8 *work, *dtag, *dstate;
     size_t wbytes;
     cudaStream_t st;
 
@@ -505,13 +507,13 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *a
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
     else         direct = is_direct(out) && (len == 0 || is_direct(in));
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
-    wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + aadlen + 64;
+    wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len > aadlen ? len : aadlen) + aadlen + 64;
     if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM work)")) != 0) goto done;
     dtag = (u8 *)c->work;
     work = (u8 *)c->work + GCM_WORK_HEAD;
     daad = NULL;
     if (aadlen) {
-        u8 *a = work + uaes_gcm_work_bytes(len);
+        u8 *a = work + uaes_gcm_work_bytes(len > aadlen ? len : aadlen);
         a += (16 - ((size_t)a & 15)) & 15;
         CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
         daad = a;
@@ -524,17 +526,22 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *a
         CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
         din = c->big; dout = c->big;
     }
+    dstate = NULL;
+    if (aadlen >= AAD_BULK_MIN) {                             /* xMac over the AAD (micro_aes.c:1134) in bulk */
+        dstate = (u8 *)c->work + AAD_STATE_OFF;
+        LAUNCH(uaes_launch_gcm(&ks, nonce, NULL, 0, NULL, daad, NULL, aadlen, 1, 0, 1, dstate, work, st));
+    }
 
     if (!decrypt) {
         /* one fused pass: CTR + GHASH, tag appended at out + len (micro_aes.c:1168,1178) */
-        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, dout, len, 0, 0, 0, (u8 *)dout + len, work, st));
+        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, dstate, din, dout, len, 0, 0, 0, (u8 *)dout + len, work, st));
         if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
         if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
     } else {
         /* verify first, decrypt only on success; `out` stays untouched otherwise (micro_aes.c:1199-1209) */
         u8 t1[16], t2[16];
         uaes_ctrblock cb;
-        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, din, NULL, len, 1, 0, 0, dtag, work, st));
+        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, dstate, din, NULL, len, 1, 0, 0, dtag, work, st));
         CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
         CU(cudaMemcpyAsync(t2, (const u8 *)din + len, 16, cudaMemcpyDefault, st));
         CU(cudaStreamSynchronize(st));
@@ -593,7 +600,7 @@ int uaes_gcm_shard(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, uaes_u
         CU(cudaMemcpyAsync(c->big, in, len, cudaMemcpyDefault, st));
         din = c->big; dout = c->big;
     }
-    LAUNCH(uaes_launch_gcm(&ks, nonce, NULL, 0, din, dout, len, decrypt ? 2 : 0, first_block, 1, dpart, work, st));
+    LAUNCH(uaes_launch_gcm(&ks, nonce, NULL, 0, NULL, din, dout, len, decrypt ? 2 : 0, first_block, 1, dpart, work, st));
     if (!direct) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(partial, dpart, 16, cudaMemcpyDefault, st));
     CU(cudaStreamSynchronize(st));                            /* the 16 bytes are a host result */
@@ -645,7 +652,7 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
     int rc, direct;
     const void *din, *daad;
     void *dout;
-    u8 *work, *dtag, *dderived, derived[48];
+    u8 *work, *dtag, *dderived, *dstate, derived[48];
     size_t wbytes;
     cudaStream_t st;
 
@@ -656,7 +663,7 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
     else         direct = is_direct(out) && (len == 0 || is_direct(in));
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
-    wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + aadlen + 64;
+    wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len > aadlen ? len : aadlen) + aadlen + 64;
     if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM-SIV work)")) != 0) goto done;
     dtag = (u8 *)c->work;                 /* [0,16) computed tag, [64,112) derived key material */
     dderived = (u8 *)c->work + 64;
@@ -670,7 +677,7 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
 
     daad = NULL;
     if (aadlen) {
-        u8 *a = work + uaes_gcm_work_bytes(len);
+        u8 *a = work + uaes_gcm_work_bytes(len > aadlen ? len : aadlen);
         a += (16 - ((size_t)a & 15)) & 15;
         CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
         daad = a;
@@ -683,10 +690,15 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
         CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
         din = c->big; dout = c->big;
     }
+    dstate = NULL;
+    if (aadlen >= AAD_BULK_MIN) {                             /* POLYVAL state of a large AAD, in bulk */
+        dstate = (u8 *)c->work + AAD_STATE_OFF;
+        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, NULL, 0, NULL, daad, aadlen, 1, dstate, work, st));
+    }
 
     if (!decrypt) {
         u8 *tagpos = (u8 *)dout + len;
-        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, daad, aadlen, din, len, dtag, work, st));
+        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, daad, aadlen, dstate, din, len, 0, dtag, work, st));
         LAUNCH(uaes_launch_ctr32(&enc, dtag, din, dout, len, st));
         CU(cudaMemcpyAsync(tagpos, dtag, 16, cudaMemcpyDefault, st));
         if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
@@ -698,7 +710,7 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
          * beyond len but the staging buffer is shared */
         CU(cudaMemcpyAsync(dtag + 16, rtag, 16, cudaMemcpyDefault, st));
         LAUNCH(uaes_launch_ctr32(&enc, dtag + 16, din, dout, len, st));
-        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, daad, aadlen, dout, len, dtag, work, st));
+        LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, daad, aadlen, dstate, dout, len, 0, dtag, work, st));
         if (!direct && len) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
         CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
         CU(cudaMemcpyAsync(t2, dtag + 16, 16, cudaMemcpyDefault, st));

@@ -62,9 +62,13 @@ int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysched *ks1e,
  * partial_only = 0: tag = E_K(J0) ^ GHASH(aad, data, lengths) written to tag_out (16 B, device);
  * partial_only = 1: the shard's GHASH contribution sum X_i * H^(shard end - i) written instead. */
 size_t uaes_gcm_work_bytes(u64 len);
+/* aad_state_dev: NULL, or 16 bytes of device memory holding the GHASH state after the AAD (from a
+ * mode-1 partial_only pass over a large AAD); aad_dev is then not read, aadlen still feeds the
+ * length block */
 int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
-                    u64 aadlen, const void *in, void *out, u64 len, int mode, u64 first_block,
-                    int partial_only, void *tag_out, void *work, void *stream);
+                    u64 aadlen, const void *aad_state_dev, const void *in, void *out, u64 len,
+                    int mode, u64 first_block, int partial_only, void *tag_out, void *work,
+                    void *stream);
 /* tag of a sharded message from the shards' contributions: partials_dev = nshards x 16 B,
  * after_dev = nshards x u64 (GHASH blocks after the end of each shard), both device memory */
 int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
@@ -78,7 +82,8 @@ int uaes_launch_gcmsiv_derive(const uaes_keysched *master, const unsigned char n
                               void *out_dev, void *stream);
 int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned char auth[16],
                            const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
-                           const void *data, u64 len, void *tag_out, void *work, void *stream);
+                           const void *aad_state_dev, const void *data, u64 len, int partial_only,
+                           void *tag_out, void *work, void *stream);
 int uaes_launch_ctr32(const uaes_keysched *enc, const void *tag_dev, const void *in, void *out,
                       u64 len, void *stream);
 

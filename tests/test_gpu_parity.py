@@ -193,7 +193,7 @@ def test_gcm_sizes(uaes, orc, bits):
     a = uaes.MicroAES(bits)
     for n, alen in [(0, 0), (0, 13), (1, 0), (15, 1), (16, 16), (17, 90), (511, 20), (512, 0), (513, 31),
                     (4096, 7), (16 * 255, 0), (16 * 257 + 3, 129), (65536 + 3, 20), ((1 << 20) + 5, 20),
-                    (3 * (1 << 20) + 1, 0)]:
+                    (3 * (1 << 20) + 1, 0), (1000, 70000 + 5), (0, 4096), (100, 1 << 20)]:   # last three: bulk-hashed AAD
         key, nonce = rnd(f"g-k{bits}{n}", bits // 8), rnd(f"g-n{bits}{n}", 12)
         aad, data = rnd(f"g-a{bits}{n}", alen), rnd(f"g-d{bits}{n}", n)
         want = orc.gcm_encrypt(key, nonce, aad, data)
@@ -373,7 +373,8 @@ def test_gcmsiv_recorded_reference_and_oracle(uaes, orc, torch):
         rc, out = lib[c["bits"]].GCM_SIV_decrypt(H(c["key"]), H(c["nonce"]), b"", rnd(c["ct_tag"], c["n"]) + H(c["tag"]))
         assert rc == 0x1A and sha256(out) == c["out_sha256"], c
     for bits in (128, 256):
-        for n, alen in [(0, 0), (0, 5), (15, 0), (16, 1), (33, 100), (4095, 7), ((1 << 20) + 9, 20), (3 * (1 << 20), 0)]:
+        for n, alen in [(0, 0), (0, 5), (15, 0), (16, 1), (33, 100), (4095, 7), ((1 << 20) + 9, 20), (3 * (1 << 20), 0),
+                        (500, 70000 + 5), (0, 4096 + 16)]:
             key, nonce = rnd(f"gv-k{bits}{n}", bits // 8), rnd(f"gv-n{bits}{n}", 12)
             aad, data = rnd(f"gv-a{bits}{n}", alen), rnd(f"gv-d{bits}{n}", n)
             want = orc.gcmsiv_encrypt(key, nonce, aad, data)
