@@ -129,6 +129,15 @@ char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 
+/* only the block-parallel DEcrypt directions of CBC (CS3 stealing, as with the
+ * reference's CTS = 1) and CFB exist on the GPU; CBC / CFB stay 0 above because the serial
+ * encrypt directions (micro_aes.c:697-733, 826-830) are not provided.
+ * Replaces micro_aes.h:194-198 / micro_aes.c:746-782 and micro_aes.h:211-215 / micro_aes.c:840-845. */
+char AES_CBC_decrypt(const uint8_t *key, const uint8_t iVec[16],
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+void AES_CFB_decrypt(const uint8_t *key, const uint8_t iVec[16],
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
 /* GCM-SIV (RFC 8452): 12-byte nonce; crtxt holds ptextLen + SIVGCM_TAG_LEN bytes */
 void GCM_SIV_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,

@@ -118,6 +118,16 @@ int uaes_gcmsiv_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
 int uaes_gcmsiv_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                         const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* ---- the block-parallel decrypt directions of CBC and CFB ---------- */
+/* micro_aes.c:746-782 with the reference's default CS3 ciphertext stealing (CTS = 1): any
+ * len >= 16; UAES_DATALENGTH_ERROR below that.  iv = 16 bytes.  (CBC/CFB ENcryption is a serial
+ * chain and is not provided.)  A staged copy is made when in == out. */
+int uaes_cbc_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
+                     const void *in, size_t len, void *out);
+/* micro_aes.c:799-845, any length */
+int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
+                     const void *in, size_t len, void *out);
+
 /* One GCM message sharded over several GPUs (or calls).  Each shard holds a contiguous byte range
  * starting at block `first_block` of the message; all shards but the last are multiples of 16
  * bytes.  uaes_gcm_shard runs the fused CTR + GHASH pass over the shard (encrypt: GHASH over the

@@ -48,6 +48,8 @@ UAES_ABI = {
     "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
     "uaes_gcm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_cbc_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
+    "uaes_cfb_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_gcmsiv_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcmsiv_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_shard": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp, _int, _vp]),
@@ -66,6 +68,8 @@ MICRO_AES_ABI = {
     "AES_XTS_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
     "AES_GCM_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_GCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_CBC_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
+    "AES_CFB_decrypt": (None, [_cp, _cp, _vp, _sz, _vp]),
     "GCM_SIV_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "GCM_SIV_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
 }
@@ -194,6 +198,18 @@ class MicroAES:
         return rc, out.raw[:n]
 
 
+    def AES_CBC_decrypt(self, key, iVec, crtxt):
+        out = ctypes.create_string_buffer(b"\xcc" * max(len(crtxt), 1), max(len(crtxt), 1))
+        rc = ord(self.lib.AES_CBC_decrypt(key, iVec, crtxt, len(crtxt), out))
+        self._after()
+        return rc, out.raw[:len(crtxt)]
+
+    def AES_CFB_decrypt(self, key, iVec, crtxt):
+        out = ctypes.create_string_buffer(max(len(crtxt), 1))
+        self.lib.AES_CFB_decrypt(key, iVec, crtxt, len(crtxt), out)
+        self._after()
+        return out.raw[:len(crtxt)]
+
     def GCM_SIV_encrypt(self, key, nonce, aData, pntxt):
         out = ctypes.create_string_buffer(len(pntxt) + 16)
         self.lib.GCM_SIV_encrypt(key, nonce, aData, len(aData), pntxt, len(pntxt), out)
@@ -237,6 +253,11 @@ def gcm_encrypt(bits, key, nonce, aad, src, nbytes, dst):
 def gcm_decrypt(bits, key, nonce, aad, src, nbytes, dst):
     return check(core().uaes_gcm_decrypt(bits, key, nonce, _ptr(aad), len(aad) if aad else 0,
                                          _ptr(src), nbytes, _ptr(dst)))
+
+
+def chain_decrypt(bits, key, iv, src, nbytes, dst, cbc=True):
+    f = core().uaes_cbc_decrypt if cbc else core().uaes_cfb_decrypt
+    return check(f(bits, key, iv, _ptr(src), nbytes, _ptr(dst)))
 
 
 def gcmsiv(bits, key, nonce, aad, src, nbytes, dst, encrypt=True):

@@ -84,3 +84,15 @@ char GCM_SIV_decrypt(const uint8_t *key, const uint8_t *nonce,
     return code(uaes_gcmsiv_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
                 M_DECRYPTION_ERROR);
 }
+
+char AES_CBC_decrypt(const uint8_t *key, const uint8_t iVec[16],
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_cbc_decrypt(BITS, key, iVec, crtxt, crtxtLen, pntxt), M_DECRYPTION_ERROR);
+}
+
+void AES_CFB_decrypt(const uint8_t *key, const uint8_t iVec[16],
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    uaes_cfb_decrypt(BITS, key, iVec, crtxt, crtxtLen, pntxt);
+}

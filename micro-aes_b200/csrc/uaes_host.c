@@ -734,6 +734,59 @@ int uaes_gcmsiv_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, c
     return gcmsiv_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
 }
 
+/* ------------------------------------------------------------------ CBC / CFB decrypt (8f, row 2) */
+
+/* Both directions read two input blocks per output block, so in and out must be different
+ * buffers on the device: the staged path uses the two halves of the full-size staging area. */
+static int chain_common(int keybits, const u8 *key, const u8 *iv, const void *in, size_t len, void *out, int cbc)
+{
+    devctx *c;
+    uaes_keysched enc, dec;
+    int rc;
+    size_t n = len / 16, r = len % 16;
+    cudaStream_t st;
+
+    if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (cbc) {                                                /* CS3 rules of micro_aes.c:751-760 */
+        if (n > 1 && !r) { --n; r = 16; }
+        if (n == 0) return UAES_DATALENGTH_ERROR;
+        n -= r > 0;
+        invert_schedule(&enc, &dec);
+    } else if (len == 0) {
+        return 0;
+    }
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if (is_direct(in) && is_direct(out) && in != out) {
+        LAUNCH(uaes_launch_chain_dec(cbc ? &dec : &enc, &enc, cbc, iv, in, out, n, (unsigned)r, tls_stream));
+        rc = finish_direct();
+    } else {
+        const size_t half = (len + 255) & ~(size_t)255;
+        u8 *din, *dout;
+        if ((rc = grow(&c->big, &c->big_bytes, 2 * half + 32, "cudaMalloc(CBC/CFB staging)")) != 0) goto done;
+        din = (u8 *)c->big; dout = din + half;
+        st = c->st[0];
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        CU(cudaMemcpyAsync(din, in, len, cudaMemcpyDefault, st));
+        LAUNCH(uaes_launch_chain_dec(cbc ? &dec : &enc, &enc, cbc, iv, din, dout, n, (unsigned)r, st));
+        CU(cudaMemcpyAsync(out, dout, len, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_cbc_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out)
+{
+    return chain_common(keybits, key, iv, in, len, out, 1);
+}
+
+int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out)
+{
+    return chain_common(keybits, key, iv, in, len, out, 0);
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords)

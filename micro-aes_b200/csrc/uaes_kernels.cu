@@ -346,6 +346,7 @@ using namespace uaes;
 
 #include "uaes_xts.cuh"
 #include "uaes_gcm.cuh"
+#include "uaes_chain.cuh"
 
 extern "C" {
 

@@ -87,6 +87,13 @@ int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned char auth[16
 int uaes_launch_ctr32(const uaes_keysched *enc, const void *tag_dev, const void *in, void *out,
                       u64 len, void *stream);
 
+/* CBC / CFB decrypt (block-parallel directions).  cbc: ks = inverse schedule, kse = encryption
+ * schedule (one-thread CS3 pair); cfb: ks = kse = encryption schedule.  tail: CBC = bytes of the
+ * short member of the CTS pair (1..16, 0 = no pair), CFB = len % 16. */
+int uaes_launch_chain_dec(const uaes_keysched *ks, const uaes_keysched *kse, int cbc,
+                          const unsigned char iv[16], const void *in, void *out, u64 nblocks,
+                          unsigned tail, void *stream);
+
 /* synthetic data + checksum helpers */
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
 int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);

@@ -613,6 +613,104 @@ int oracle_gcmsiv_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[1
 }
 
 /* ------------------------------------------------------------------------ */
+/* CBC with CS3 stealing, CFB                                               */
+/* ------------------------------------------------------------------------ */
+
+/* micro_aes.c:697-733 (AES_CBC_encrypt, CTS == 1).  out must not alias in. */
+int oracle_cbc_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                       const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    const uint8_t *x = (const uint8_t *)in, *chain = iv;
+    uint8_t *y = (uint8_t *)out;
+    size_t n = len / 16, r = len % 16;
+    if (n > 1 && !r) { --n; r = 16; }                  /* CS3: the last two blocks always swap */
+    if (n == 0) return ORACLE_DATALENGTH_ERROR;
+    key_setup(&c, keybits, key);
+    for (; n--; x += 16, y += 16) {
+        memcpy(y, x, 16);
+        xor16(y, chain);
+        encrypt_block(&c, y, y);
+        chain = y;
+    }
+    if (r) {
+        /* y - 16 holds C_(m-1); the final plaintext chunk P_m (r bytes) is zero padded, chained
+         * with C_(m-1) and encrypted into the second-to-last position; C_(m-1)[0..r) moves last */
+        uint8_t last[16] = {0}, head[16];
+        memcpy(last, x, r);
+        memcpy(head, y - 16, 16);
+        xor16(last, head);
+        encrypt_block(&c, last, y - 16);
+        memcpy(y, head, r);
+    }
+    return ORACLE_SUCCESS;
+}
+
+/* micro_aes.c:746-782 (AES_CBC_decrypt, CTS == 1).  out must not alias in (the reference chains
+ * through the input buffer, micro_aes.c:766). */
+int oracle_cbc_decrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                       const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    const uint8_t *x = (const uint8_t *)in, *chain = iv;
+    uint8_t *y = (uint8_t *)out;
+    size_t n = len / 16, r = len % 16, i;
+    if (n > 1 && !r) { --n; r = 16; }
+    if (n == 0) return ORACLE_DATALENGTH_ERROR;
+    n -= r > 0;                                        /* the last two blocks are the CTS pair */
+    key_setup(&c, keybits, key);
+    for (; n--; x += 16, y += 16) {
+        decrypt_block(&c, x, y);
+        xor16(y, chain);
+        chain = x;
+    }
+    if (r) {
+        const uint8_t *z = x + 16;                     /* {X, Z}: X full, Z has r bytes */
+        uint8_t dx[16], blk[16];
+        decrypt_block(&c, x, dx);
+        for (i = 0; i < r; ++i) y[16 + i] = dx[i] ^ z[i];      /* P2 = Z ^ Dec(X) */
+        memcpy(blk, dx, 16);
+        memcpy(blk, z, r);
+        decrypt_block(&c, blk, y);                     /* P1 = IV ^ Dec(Z | tail of Dec(X)) */
+        xor16(y, chain);
+    }
+    return ORACLE_SUCCESS;
+}
+
+/* micro_aes.c:799-818 (CFB_cipher) */
+static void cfb_cipher(int keybits, const uint8_t *key, const uint8_t iv[16], int encrypt,
+                       const uint8_t *x, size_t len, uint8_t *y)
+{
+    aes_ctx c;
+    uint8_t fb[16], ks[16];
+    size_t i;
+    key_setup(&c, keybits, key);
+    memcpy(fb, iv, 16);
+    for (; len; ) {
+        const size_t n = len < 16 ? len : 16;
+        encrypt_block(&c, fb, ks);
+        for (i = 0; i < n; ++i) {
+            const uint8_t ct = encrypt ? (uint8_t)(x[i] ^ ks[i]) : x[i];
+            y[i] = x[i] ^ ks[i];
+            fb[i] = ct;                                /* IV_next = ciphertext */
+        }
+        x += n; y += n; len -= n;
+    }
+}
+
+void oracle_cfb_decrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                        const void *in, size_t len, void *out)
+{
+    cfb_cipher(keybits, key, iv, 0, (const uint8_t *)in, len, (uint8_t *)out);
+}
+
+void oracle_cfb_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                        const void *in, size_t len, void *out)
+{
+    cfb_cipher(keybits, key, iv, 1, (const uint8_t *)in, len, (uint8_t *)out);
+}
+
+/* ------------------------------------------------------------------------ */
 /* synthetic data                                                           */
 /* ------------------------------------------------------------------------ */
 

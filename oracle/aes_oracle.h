@@ -94,6 +94,19 @@ void oracle_gcmsiv_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[
 int  oracle_gcmsiv_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
                            const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* ---- SURVEY.md 8f "next" row 2: the block-parallel DEcrypt directions of CBC (with the
+ * reference's default CS3 ciphertext stealing, micro_aes.c:746-782) and CFB (micro_aes.c:799-845).
+ * The encrypt directions are serial chains and stay out of scope; oracle_cbc_encrypt /
+ * oracle_cfb_encrypt exist only so that tests can build valid ciphertexts (micro_aes.c:697-733). */
+int  oracle_cbc_decrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                        const void *in, size_t len, void *out);
+int  oracle_cbc_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                        const void *in, size_t len, void *out);
+void oracle_cfb_decrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                        const void *in, size_t len, void *out);
+void oracle_cfb_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
+                        const void *in, size_t len, void *out);
+
 /* splitmix64 synthetic-data generator shared by tests and bench: 64-bit word w of
  * the buffer (byte offset 8w, little-endian) = splitmix64(seed + first_word + w) */
 void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords);

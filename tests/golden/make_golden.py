@@ -72,6 +72,8 @@ def main_c_vectors():
                        "ct": s["cipherKey"][0][32:]},
         "ecb128": ecb128, "ctr128": ctr128, "ctr128_preset_counter": ctr128_preset,
         "xts128": xts128, "xts256": xts256, "gcm128": gcm128, "gcm256": gcm256,
+        # CBC with CS3 stealing (CTS = 1, main.c:35-37,146-152) and CFB (main.c:41-42,153-159)
+        "cbc128_cts": s["cbccipher"][0] + s["cbccipher"][1], "cfb128": s["cfbcipher"][0],
         # GCM-SIV, main.c:61-63 (same inputs) and the two RFC 8452 cases main.c:275-299
         "gcmsiv128": s["gsvcipher"][0],
         "gcmsiv_rfc8452": [
@@ -208,6 +210,21 @@ def ref_samples():
             out["gcmsiv"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
                                   "aad_tag": f"gsa{bits}{n}", "pt_tag": f"gsp{bits}{n}",
                                   "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    out["cbc_decrypt"], out["cfb_decrypt"] = [], []
+    for bits, lib in libs.items():
+        lib.AES_CBC_decrypt.restype = ctypes.c_char
+        for n in (15, 16, 17, 31, 32, 33, 48, 57, 4096, 4096 + 5, 65536 + 15, 1 << 18):
+            key, iv, ct = rnd(f"cbk{bits}{n}", bits // 8), rnd(f"cbi{bits}{n}", 16), rnd(f"cbc{bits}{n}", n)
+            o = ctypes.create_string_buffer(n + 16)
+            rc = lib.AES_CBC_decrypt(key, iv, ct, ctypes.c_size_t(n), o)
+            out["cbc_decrypt"].append({"bits": bits, "n": n, "key": key.hex(), "iv": iv.hex(), "ct_tag": f"cbc{bits}{n}",
+                                       "rc": ord(rc), "pt_sha256": sha(o.raw[:n]) if ord(rc) == 0 else None})
+        for n in (0, 1, 16, 17, 57, 4096, 4096 + 5, 1 << 18):
+            key, iv, ct = rnd(f"cfk{bits}{n}", bits // 8), rnd(f"cfi{bits}{n}", 16), rnd(f"cfc{bits}{n}", n)
+            o = ctypes.create_string_buffer(n + 16)
+            lib.AES_CFB_decrypt(key, iv, ct, ctypes.c_size_t(n), o)
+            out["cfb_decrypt"].append({"bits": bits, "n": n, "key": key.hex(), "iv": iv.hex(), "ct_tag": f"cfc{bits}{n}",
+                                       "pt_sha256": sha(o.raw[:n])})
     # The 32-bit little-endian counter of GCM-SIV wraps (micro_aes.c:935-938).  The counter starts at
     # the tag, and GCM_SIV_decrypt runs CTR with the RECEIVED tag before it authenticates
     # (micro_aes.c:1505-1515), so a forged tag ff ff ff f8 .. pins the wrap: the call fails with

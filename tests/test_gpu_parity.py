@@ -394,3 +394,43 @@ def test_gcmsiv_recorded_reference_and_oracle(uaes, orc, torch):
     assert host(buf, 0, n + 16) == want
     assert uaes.gcmsiv(128, key, nonce, aad, buf, n, buf, False) == 0
     assert host(buf, 0, n) == data
+
+
+# ---------------------------------------------------------------- CBC / CFB decrypt
+
+def test_cbc_cfb_decrypt(uaes, orc, torch):
+    m = golden("main_c.json")
+    a = uaes.MicroAES(128)
+    key, iv, pt = H(m["key_pool"])[:16], H(m["iv16"]), H(m["plaintext"])
+    assert a.AES_CBC_decrypt(key, iv, H(m["cbc128_cts"])) == (0, pt)         # main.c:146-152 (CTS)
+    assert a.AES_CFB_decrypt(key, iv, H(m["cfb128"])) == pt                  # main.c:153-159
+    s = golden("oracle_ref_samples.json")
+    lib = {b: uaes.MicroAES(b) for b in (128, 192, 256)}
+    for c in s["cbc_decrypt"]:                                               # unmodified reference runs
+        rc, out = lib[c["bits"]].AES_CBC_decrypt(H(c["key"]), H(c["iv"]), rnd(c["ct_tag"], c["n"]))
+        assert rc == c["rc"], c
+        if rc == 0:
+            assert sha256(out) == c["pt_sha256"], c
+        else:
+            assert out == b"\xcc" * c["n"]                                   # M_DATALENGTH_ERROR: nothing written
+    for c in s["cfb_decrypt"]:
+        assert sha256(lib[c["bits"]].AES_CFB_decrypt(H(c["key"]), H(c["iv"]), rnd(c["ct_tag"], c["n"]))) == c["pt_sha256"], c
+    for bits in (128, 192, 256):
+        for n in [16, 17, 31, 32, 33, 47, 48, 49, 511, 512, 513, 4096, 4097, 65536 + 15, (1 << 20) + 16, (1 << 20) + 7]:
+            key, iv, ct = rnd(f"cb-k{bits}{n}", bits // 8), rnd(f"cb-i{bits}{n}", 16), rnd(f"cb-c{bits}{n}", n)
+            assert lib[bits].AES_CBC_decrypt(key, iv, ct) == orc.cbc(key, iv, ct), (bits, n)
+            assert lib[bits].AES_CFB_decrypt(key, iv, ct) == orc.cfb(key, iv, ct), (bits, n)
+    # valid ciphertexts made by the oracle's serial encrypt come back as the plaintext
+    key, iv, pt = rnd("cb-rk", 32), rnd("cb-ri", 16), rnd("cb-rp", 100000 + 3)
+    assert lib[256].AES_CBC_decrypt(key, iv, orc.cbc(key, iv, pt, encrypt=True)[1]) == (0, pt)
+    assert lib[256].AES_CFB_decrypt(key, iv, orc.cfb(key, iv, pt, encrypt=True)) == pt
+    # device pointers (out of place) and the in == out request (staged copy)
+    n = (1 << 21) + 9
+    ct = rnd("cb-dc", n)
+    src, dst = dev(torch, ct), dev(torch, b"", pad=n)
+    uaes.chain_decrypt(128, key[:16], iv, src, n, dst, cbc=True)
+    assert host(dst, 0, n) == orc.cbc(key[:16], iv, ct)[1] and host(dst, n, n + 16) == bytes(16)
+    uaes.chain_decrypt(128, key[:16], iv, src, n, dst, cbc=False)
+    assert host(dst, 0, n) == orc.cfb(key[:16], iv, ct)
+    uaes.chain_decrypt(128, key[:16], iv, src, n, src, cbc=True)
+    assert host(src, 0, n) == orc.cbc(key[:16], iv, ct)[1]

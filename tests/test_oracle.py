@@ -187,6 +187,23 @@ def test_gcmsiv_recorded_reference_outputs(orc):
         assert rc == c["rc"] == 0x1A and sha256(out) == c["out_sha256"]
 
 
+# ---------------------------------------------------------------- CBC / CFB decrypt
+
+def test_cbc_cfb_vectors_and_recorded_reference(orc):
+    m = golden("main_c.json")
+    key, iv, pt = H(m["key_pool"])[:16], H(m["iv16"]), H(m["plaintext"])
+    assert orc.cbc(key, iv, H(m["cbc128_cts"])) == (0, pt)          # main.c:146-152, CTS
+    assert orc.cbc(key, iv, pt, encrypt=True) == (0, H(m["cbc128_cts"]))
+    assert orc.cfb(key, iv, H(m["cfb128"])) == pt                   # main.c:153-159
+    assert orc.cfb(key, iv, pt, encrypt=True) == H(m["cfb128"])
+    s = golden("oracle_ref_samples.json")
+    for c in s["cbc_decrypt"]:
+        rc, out = orc.cbc(H(c["key"]), H(c["iv"]), rnd(c["ct_tag"], c["n"]))
+        assert rc == c["rc"] and (rc or sha256(out) == c["pt_sha256"]), c
+    for c in s["cfb_decrypt"]:
+        assert sha256(orc.cfb(H(c["key"]), H(c["iv"]), rnd(c["ct_tag"], c["n"]))) == c["pt_sha256"], c
+
+
 # ---------------------------------------------------------------- edge cases
 
 def test_edge_cases(orc):

@@ -56,6 +56,8 @@ class Oracle:
         L.oracle_gcmsiv_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_gcmsiv_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_polyval.argtypes = [_u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        for f in (L.oracle_cbc_decrypt, L.oracle_cbc_encrypt, L.oracle_cfb_decrypt, L.oracle_cfb_encrypt):
+            f.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
         L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
 
     @staticmethod
@@ -127,6 +129,18 @@ class Oracle:
         rc = self.lib.oracle_gcmsiv_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
         return rc, o.raw[:n]
 
+    def cbc(self, key, iv, data, encrypt=False):
+        o = self._buf(len(data))
+        f = self.lib.oracle_cbc_encrypt if encrypt else self.lib.oracle_cbc_decrypt
+        rc = f(len(key) * 8, key, iv, data, len(data), o)
+        return rc, o.raw[:len(data)]
+
+    def cfb(self, key, iv, data, encrypt=False):
+        o = self._buf(len(data))
+        f = self.lib.oracle_cfb_encrypt if encrypt else self.lib.oracle_cfb_decrypt
+        f(len(key) * 8, key, iv, data, len(data), o)
+        return o.raw[:len(data)]
+
     def polyval(self, H, aad, pt):
         o = self._buf(16)
         self.lib.oracle_polyval(H, aad, len(aad), pt, len(pt), o)
@@ -175,7 +189,8 @@ class Reference:
         self.path = os.path.join(ROOT, "oracle", "_ref", name)
         self.bits = bits
         self.lib = ctypes.CDLL(self.path)
-        for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt", "GCM_SIV_decrypt"):
+        for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt", "GCM_SIV_decrypt",
+                  "AES_CBC_encrypt", "AES_CBC_decrypt"):
             getattr(self.lib, f).restype = ctypes.c_char
 
     @staticmethod
@@ -209,6 +224,18 @@ class Reference:
         o = ctypes.create_string_buffer(len(pt) + 16)
         self.lib.AES_GCM_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
         return o.raw[:len(pt) + 16]
+
+    def cbc(self, key, iv, data, encrypt=False):
+        o = ctypes.create_string_buffer(b"\xcc" * (len(data) + 16), len(data) + 16)
+        f = self.lib.AES_CBC_encrypt if encrypt else self.lib.AES_CBC_decrypt
+        rc = f(key, iv, data, _sz(len(data)), o)
+        return ord(rc), o.raw[:len(data)]
+
+    def cfb(self, key, iv, data, encrypt=False):
+        o = ctypes.create_string_buffer(len(data) + 16)
+        f = self.lib.AES_CFB_encrypt if encrypt else self.lib.AES_CFB_decrypt
+        f(key, iv, data, _sz(len(data)), o)
+        return o.raw[:len(data)]
 
     def gcmsiv_encrypt(self, key, nonce, aad, pt):
         o = ctypes.create_string_buffer(len(pt) + 16)
