@@ -1,12 +1,12 @@
 // uaes_kernels.cu -- sm_100a kernels for the AES bulk path and their C launchers.
 //
 // Kernel shape shared by every mode ("Kernels"):
-//   * persistent grid: one 1024-thread CTA per SM (148 on B200), 227 KB of dynamic shared memory
-//     holding the lane-replicated T-tables (uaes_tables.cuh);
+//   * persistent grid: one 768- or 1024-thread CTA per SM (148 on B200), 227 KB of dynamic shared
+//     memory holding the lane-replicated T-tables (uaes_tables.cuh);
 //   * one 16-byte block per thread per step, a warp covers 32 consecutive blocks = 512
 //     contiguous bytes, moved with one 128-bit load and one 128-bit store per thread;
-//   * the next step's input is requested before the current step's rounds start, so 32 warps
-//     keep 16 KB of loads in flight per SM;
+//   * the next step's input is requested before the current step's rounds start, so the warps
+//     keep 12-16 KB of loads in flight per SM;
 //   * round keys are kernel arguments (constant bank), no per-launch symbol copies.
 #include <cuda_runtime.h>
 #include <stdint.h>
