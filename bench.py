@@ -226,7 +226,7 @@ def run_gpu(args):
     wl = args.workload
     key32 = key + bytes(range(16))
     keys64 = key32 + bytes(range(32, 64))
-    if wl in ("gcm128", "gcmsiv128"):
+    if wl in ("gcm128", "gcmsiv128", "ocb128"):
         dst = torch.empty(nbytes + 16, dtype=torch.uint8, device="cuda")
 
     def step():
@@ -240,6 +240,8 @@ def run_gpu(args):
             uaes.ecb(128, key, src, nbytes, dst, False)
         elif wl == "xts256dec":
             uaes.xts_sectors(256, keys64, first_block // 32, 512, src, nbytes, dst, False)
+        elif wl == "ocb128":
+            uaes.ocb(128, key, iv, b"", src, nbytes, dst, True)
         elif wl == "cbc128dec":
             uaes.chain_decrypt(128, key, key, src, nbytes, dst, cbc=True)
         elif wl == "cfb128dec":
@@ -377,7 +379,7 @@ def run_gpu(args):
                                     "xts256": "uaes::xts_sectors_kernel<14,true>", "gcm128": "uaes::gcm_bulk_kernel<10,0>",
                                     "ecb128dec": "uaes::ecb_kernel<10,false>", "xts256dec": "uaes::xts_sectors_kernel<14,false>",
                                     "gcmsiv128": "uaes::gcm_bulk_kernel<10,1,true> + uaes::ctr32_kernel<10>",
-                                    "cbc128dec": "uaes::chain_dec_kernel<10,true>", "cfb128dec": "uaes::chain_dec_kernel<10,false>"}[wl],
+                                    "ocb128": "uaes::ocb_bulk_kernel<10,true>", "cbc128dec": "uaes::chain_dec_kernel<10,true>", "cfb128dec": "uaes::chain_dec_kernel<10,false>"}[wl],
                          "kernel_ms": round(kernel_ms, 4),
                          "algorithmic_bytes_per_launch": 2 * nbytes},
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -398,7 +400,7 @@ def main():
     ap.add_argument("--e2e-gib", type=float, default=0.0, help="host buffer for the e2e leg (default: auto)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-slice-mib", type=int, default=256)
-    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "ecb128dec", "xts256", "xts256dec", "gcm128", "gcmsiv128", "cbc128dec", "cfb128dec"],
+    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "ecb128dec", "xts256", "xts256dec", "gcm128", "gcmsiv128", "cbc128dec", "cfb128dec", "ocb128"],
                     help="ctr128 is the headline (BASELINE.json metric); the others are the secondary configs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")

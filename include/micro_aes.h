@@ -4,7 +4,7 @@
  *
  * This header declares, with the reference's names, argument order and return
  * codes, the entry points the reference exports when only ECB, CTR (CTR_NA),
- * XEX/XTS, GCM and GCM_SIV are enabled:
+ * XEX/XTS, GCM, GCM_SIV and OCB are enabled:
  *
  *     function            replaces (polfosol/micro-AES)
  *     ------------------  ---------------------------------------------
@@ -18,6 +18,8 @@
  *     AES_GCM_decrypt     micro_aes.h:302-308, micro_aes.c:1192-1212
  *     GCM_SIV_encrypt     micro_aes.h:386-392, micro_aes.c:1474-1487   (SURVEY 8f "next" row 1)
  *     GCM_SIV_decrypt     micro_aes.h:394-400, micro_aes.c:1499-1516
+ *     AES_OCB_encrypt     micro_aes.h:336-342, micro_aes.c:1779-1789   (SURVEY 8f "next" row 3)
+ *     AES_OCB_decrypt     micro_aes.h:344-350, micro_aes.c:1802-1813
  *
  * A program written against the reference keeps its `#include "micro_aes.h"`,
  * drops micro_aes.c from its build and links one of
@@ -62,7 +64,7 @@
 #define EAXP            0
 #define SIV             0
 #define GCM_SIV         1
-#define OCB             0
+#define OCB             1
 #define POLY1305        0
 #define CTS             0
 #define MICRO_RJNDL     0
@@ -79,6 +81,8 @@ enum constant_parameters_of_modes
     GCM_TAG_LEN     = 16,       /* micro_aes.h:109 */
     SIVGCM_NONCE_LEN = 12,      /* micro_aes.h:112 */
     SIVGCM_TAG_LEN  = 16,       /* micro_aes.h:113 */
+    OCB_NONCE_LEN   = 12,       /* micro_aes.h:116 */
+    OCB_TAG_LEN     = 16,       /* micro_aes.h:117 */
 #if AES___ != 256 && AES___ != 192
     AES_KEYLENGTH   = 16
 #else
@@ -136,6 +140,14 @@ char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
 char AES_CBC_decrypt(const uint8_t *key, const uint8_t iVec[16],
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 void AES_CFB_decrypt(const uint8_t *key, const uint8_t iVec[16],
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* OCB (RFC 7253): 12-byte nonce; crtxt holds ptextLen + OCB_TAG_LEN bytes */
+void AES_OCB_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+char AES_OCB_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 
 /* GCM-SIV (RFC 8452): 12-byte nonce; crtxt holds ptextLen + SIVGCM_TAG_LEN bytes */

@@ -128,6 +128,14 @@ int uaes_cbc_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
 int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
                      const void *in, size_t len, void *out);
 
+/* ---- AES-OCB (RFC 7253), micro_aes.c:1779-1813 ------------------- */
+/* nonce = 12 bytes, 16-byte tag appended at out + len.  One pass. */
+int uaes_ocb_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+/* in holds len + 16; the plaintext is written, then the tag is compared (UAES_AUTH_ERROR) */
+int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
 /* One GCM message sharded over several GPUs (or calls).  Each shard holds a contiguous byte range
  * starting at block `first_block` of the message; all shards but the last are multiples of 16
  * bytes.  uaes_gcm_shard runs the fused CTR + GHASH pass over the shard (encrypt: GHASH over the

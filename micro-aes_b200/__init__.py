@@ -48,6 +48,8 @@ UAES_ABI = {
     "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
     "uaes_gcm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_ocb_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_ocb_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_cbc_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_cfb_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_gcmsiv_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
@@ -68,6 +70,8 @@ MICRO_AES_ABI = {
     "AES_XTS_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
     "AES_GCM_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_GCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_OCB_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_OCB_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_CBC_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
     "AES_CFB_decrypt": (None, [_cp, _cp, _vp, _sz, _vp]),
     "GCM_SIV_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
@@ -198,6 +202,19 @@ class MicroAES:
         return rc, out.raw[:n]
 
 
+    def AES_OCB_encrypt(self, key, nonce, aData, pntxt):
+        out = ctypes.create_string_buffer(len(pntxt) + 16)
+        self.lib.AES_OCB_encrypt(key, nonce, aData, len(aData), pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:len(pntxt) + 16]
+
+    def AES_OCB_decrypt(self, key, nonce, aData, crtxt_and_tag):
+        n = len(crtxt_and_tag) - 16
+        out = ctypes.create_string_buffer(max(n, 1))
+        rc = ord(self.lib.AES_OCB_decrypt(key, nonce, aData, len(aData), crtxt_and_tag, n, out))
+        self._after()
+        return rc, out.raw[:n]
+
     def AES_CBC_decrypt(self, key, iVec, crtxt):
         out = ctypes.create_string_buffer(b"\xcc" * max(len(crtxt), 1), max(len(crtxt), 1))
         rc = ord(self.lib.AES_CBC_decrypt(key, iVec, crtxt, len(crtxt), out))
@@ -253,6 +270,11 @@ def gcm_encrypt(bits, key, nonce, aad, src, nbytes, dst):
 def gcm_decrypt(bits, key, nonce, aad, src, nbytes, dst):
     return check(core().uaes_gcm_decrypt(bits, key, nonce, _ptr(aad), len(aad) if aad else 0,
                                          _ptr(src), nbytes, _ptr(dst)))
+
+
+def ocb(bits, key, nonce, aad, src, nbytes, dst, encrypt=True):
+    f = core().uaes_ocb_encrypt if encrypt else core().uaes_ocb_decrypt
+    return check(f(bits, key, nonce, _ptr(aad), len(aad) if aad else 0, _ptr(src), nbytes, _ptr(dst)))
 
 
 def chain_decrypt(bits, key, iv, src, nbytes, dst, cbc=True):

@@ -96,3 +96,18 @@ void AES_CFB_decrypt(const uint8_t *key, const uint8_t iVec[16],
 {
     uaes_cfb_decrypt(BITS, key, iVec, crtxt, crtxtLen, pntxt);
 }
+
+void AES_OCB_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_ocb_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+}
+
+char AES_OCB_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_ocb_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+                M_DECRYPTION_ERROR);
+}

@@ -787,6 +787,76 @@ int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const v
     return chain_common(keybits, key, iv, in, len, out, 0);
 }
 
+/* ------------------------------------------------------------------ OCB */
+
+/* micro_aes.c:1779-1813.  One pass; decrypt writes the plaintext and then reports the tag
+ * comparison, exactly like the reference (micro_aes.c:1806-1812). */
+static int ocb_common(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
+                      const void *in, size_t len, void *out, int decrypt)
+{
+    devctx *c;
+    uaes_keysched enc, dec;
+    int rc, direct;
+    const void *din, *daad;
+    void *dout;
+    u8 *work, *dtag;
+    cudaStream_t st;
+
+    if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (decrypt) invert_schedule(&enc, &dec);
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
+    else         direct = is_direct(out) && (len == 0 || is_direct(in));
+    st = direct ? (cudaStream_t)tls_stream : c->st[0];
+    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + uaes_ocb_work_bytes() + aadlen + 64,
+                   "cudaMalloc(OCB work)")) != 0) goto done;
+    dtag = (u8 *)c->work;
+    work = (u8 *)c->work + GCM_WORK_HEAD;
+    daad = NULL;
+    if (aadlen) {
+        u8 *a = work + ((uaes_ocb_work_bytes() + 15) & ~(size_t)15);
+        CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
+        daad = a;
+    }
+    if (direct) {
+        din = in; dout = out;
+    } else {
+        if ((rc = grow(&c->big, &c->big_bytes, len + 32, "cudaMalloc(OCB staging)")) != 0) goto done;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
+        din = c->big; dout = c->big;
+    }
+    if (!decrypt) {
+        LAUNCH(uaes_launch_ocb(&enc, &enc, 1, nonce, daad, aadlen, din, dout, len, (u8 *)dout + len, work, st));
+        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
+        if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
+    } else {
+        u8 t1[16], t2[16];
+        CU(cudaMemcpyAsync(t2, (const u8 *)din + len, 16, cudaMemcpyDefault, st));   /* before it can be overwritten */
+        LAUNCH(uaes_launch_ocb(&enc, &dec, 0, nonce, daad, aadlen, din, dout, len, dtag, work, st));
+        if (!direct && len) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));
+        if (memcmp(t1, t2, 16)) rc = UAES_AUTH_ERROR;
+    }
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_ocb_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+}
+
+int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords)

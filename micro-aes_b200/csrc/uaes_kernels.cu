@@ -347,6 +347,7 @@ using namespace uaes;
 #include "uaes_xts.cuh"
 #include "uaes_gcm.cuh"
 #include "uaes_chain.cuh"
+#include "uaes_ocb.cuh"
 
 extern "C" {
 

@@ -94,6 +94,14 @@ int uaes_launch_chain_dec(const uaes_keysched *ks, const uaes_keysched *kse, int
                           const unsigned char iv[16], const void *in, void *out, u64 nblocks,
                           unsigned tail, void *stream);
 
+/* OCB (micro_aes.c:1693-1814): setup + bulk + finish on one stream.  enc = encryption schedule,
+ * bulk = enc when encrypting, the inverse schedule when decrypting.  The 16-byte tag is written to
+ * tag_out (device); when decrypting it is the tag computed over the produced plaintext. */
+size_t uaes_ocb_work_bytes(void);
+int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int encrypt,
+                    const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
+                    const void *in, void *out, u64 len, void *tag_out, void *work, void *stream);
+
 /* synthetic data + checksum helpers */
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
 int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);

@@ -711,6 +711,127 @@ void oracle_cfb_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
 }
 
 /* ------------------------------------------------------------------------ */
+/* OCB                                                                      */
+/* ------------------------------------------------------------------------ */
+
+/* micro_aes.c:433-443 (doubleBblock): big-endian shift left, 0x87 into the last byte */
+static void ocb_double(uint8_t b[16])
+{
+    const unsigned msb = b[0] >> 7;
+    int i;
+    for (i = 0; i < 15; ++i) b[i] = (uint8_t)(b[i] << 1 | b[i + 1] >> 7);
+    b[15] = (uint8_t)(b[15] << 1);
+    if (msb) b[15] ^= 0x87;
+}
+
+/* micro_aes.c:1662-1680 (getDelta): delta = delta0 ^ XOR of the L_k selected by index; the
+ * reference's mask arithmetic picks exactly the bits of the Gray code index ^ (index >> 1),
+ * i.e. Offset_i = Offset_(i-1) ^ L_ntz(i) of RFC 7253 unrolled */
+static void ocb_delta(uint64_t index, const uint8_t Ldollar[16], const uint8_t delta0[16], uint8_t delta[16])
+{
+    uint8_t L[16];
+    uint64_t gray = index ^ (index >> 1);
+    memcpy(L, Ldollar, 16);
+    memcpy(delta, delta0, 16);
+    for (; gray; gray >>= 1) {
+        ocb_double(L);                                 /* L_0 = double(L_$), L_k = double(L_(k-1)) */
+        if (gray & 1) xor16(delta, L);
+    }
+}
+
+/* micro_aes.c:1693-1767 (OCB_cipher) */
+static void ocb_cipher(int keybits, const uint8_t *key, const uint8_t nonce[12], int encrypt,
+                       const uint8_t *aad, size_t aadlen, const uint8_t *x, size_t len,
+                       uint8_t *y, uint8_t tag[16])
+{
+    aes_ctx c;
+    uint8_t Lstar[16] = {0}, Ldollar[16], ktop[16] = {0}, stretch[24], off0[16], delta[16], sum[16] = {0};
+    uint8_t blk[16], acc[16];
+    const unsigned bottom = nonce[11] % 64;
+    size_t n = len / 16, r = len % 16, i, j;
+
+    key_setup(&c, keybits, key);
+    encrypt_block(&c, Lstar, Lstar);                   /* L_* = Enc(0), L_$ = double(L_*): getSubkeys */
+    memcpy(Ldollar, Lstar, 16);
+    ocb_double(Ldollar);
+    /* nonce block: tag length (128 mod 128 = 0) in the top 7 bits, then 0..01, then the nonce with
+     * its last six bits cleared (micro_aes.c:1709-1712) */
+    memcpy(ktop + 4, nonce, 12);
+    ktop[3] |= 1;
+    ktop[15] &= 0xC0;
+    encrypt_block(&c, ktop, ktop);
+    memcpy(stretch, ktop, 16);
+    for (i = 0; i < 8; ++i) stretch[16 + i] = ktop[i] ^ ktop[i + 1];
+    for (i = 0; i < 16; ++i)                           /* Offset_0 = Stretch[bottom .. bottom+128) */
+        off0[i] = (uint8_t)(((unsigned)stretch[i + bottom / 8] << 8 | stretch[i + bottom / 8 + 1]) >> (8 - bottom % 8));
+
+    for (i = 0; i < n; ++i) {
+        const uint8_t *p = encrypt ? x + 16 * i : NULL;
+        ocb_delta(i + 1, Ldollar, off0, delta);
+        memcpy(blk, x + 16 * i, 16);
+        xor16(blk, delta);
+        if (encrypt) encrypt_block(&c, blk, blk); else decrypt_block(&c, blk, blk);
+        xor16(blk, delta);
+        if (p) xor16(sum, p);                          /* checksum of the PLAINtext */
+        memcpy(y + 16 * i, blk, 16);
+        if (!encrypt) xor16(sum, blk);
+    }
+    if (n) ocb_delta(n, Ldollar, off0, delta); else memcpy(delta, off0, 16);
+    if (r) {                                           /* Y_* = Enc(L_* ^ delta_n) ^ X_*, pad the checksum */
+        uint8_t pad[16];
+        xor16(delta, Lstar);
+        encrypt_block(&c, delta, pad);
+        for (j = 0; j < r; ++j) {
+            const uint8_t in = x[16 * n + j], out = in ^ pad[j];
+            y[16 * n + j] = out;
+            sum[j] ^= encrypt ? in : out;
+        }
+        sum[r] ^= 0x80;
+    }
+    xor16(sum, delta);
+    xor16(sum, Ldollar);
+    encrypt_block(&c, sum, tag);                       /* tag = Enc(checksum ^ delta ^ L_$) so far */
+
+    /* PMAC of the associated data (micro_aes.c:1750-1765) */
+    memset(acc, 0, 16);
+    n = aadlen / 16; r = aadlen % 16;
+    for (i = 0; i < n; ++i) {
+        ocb_delta(i + 1, Ldollar, aad + 16 * i, blk);
+        encrypt_block(&c, blk, blk);
+        xor16(acc, blk);
+    }
+    if (r) {
+        uint8_t zero[16] = {0};
+        ocb_delta(n, Ldollar, zero, blk);
+        for (j = 0; j < r; ++j) blk[j] ^= aad[16 * n + j];
+        blk[r] ^= 0x80;
+        xor16(blk, Lstar);
+        encrypt_block(&c, blk, blk);
+        xor16(acc, blk);
+    }
+    xor16(tag, acc);
+}
+
+/* micro_aes.c:1779-1789 */
+void oracle_ocb_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    uint8_t tag[16];
+    ocb_cipher(keybits, key, nonce, 1, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, (uint8_t *)out, tag);
+    memcpy((uint8_t *)out + len, tag, 16);
+}
+
+/* micro_aes.c:1802-1813 */
+int oracle_ocb_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    uint8_t tag[16], got[16];
+    memcpy(got, (const uint8_t *)in + len, 16);
+    ocb_cipher(keybits, key, nonce, 0, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, (uint8_t *)out, tag);
+    return memcmp(tag, got, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
 /* synthetic data                                                           */
 /* ------------------------------------------------------------------------ */
 

@@ -107,6 +107,14 @@ void oracle_cfb_decrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
 void oracle_cfb_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
                         const void *in, size_t len, void *out);
 
+/* ---- SURVEY.md 8f "next" row 3: AES-OCB (RFC 7253, 12-byte nonce, 16-byte tag),
+ * micro_aes.c:1655-1814 ---- */
+void oracle_ocb_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+/* like the reference, the plaintext is written before the tag is checked */
+int  oracle_ocb_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
 /* splitmix64 synthetic-data generator shared by tests and bench: 64-bit word w of
  * the buffer (byte offset 8w, little-endian) = splitmix64(seed + first_word + w) */
 void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords);

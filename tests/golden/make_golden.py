@@ -72,6 +72,12 @@ def main_c_vectors():
                        "ct": s["cipherKey"][0][32:]},
         "ecb128": ecb128, "ctr128": ctr128, "ctr128_preset_counter": ctr128_preset,
         "xts128": xts128, "xts256": xts256, "gcm128": gcm128, "gcm256": gcm256,
+        # OCB, main.c:69-71 (same inputs as GCM) and the RFC 7253 case main.c:262-274
+        "ocb128": s["ocbcipher"][0],
+        "ocb_rfc7253": {"key": "000102030405060708090a0b0c0d0e0f", "iv": "bbaa99887766554433221107",
+                        "aad": "000102030405060708090a0b0c0d0e0f1011121314151617",
+                        "pt": "000102030405060708090a0b0c0d0e0f1011121314151617",
+                        "ct": "1ca2207308c87c010756104d8840ce1952f09673a448a122c92c62241051f57356d7f3c90bb0e07f"},
         # CBC with CS3 stealing (CTS = 1, main.c:35-37,146-152) and CFB (main.c:41-42,153-159)
         "cbc128_cts": s["cbccipher"][0] + s["cbccipher"][1], "cfb128": s["cfbcipher"][0],
         # GCM-SIV, main.c:61-63 (same inputs) and the two RFC 8452 cases main.c:275-299
@@ -134,6 +140,28 @@ def parse_gcmsiv(path, keybits):
                 if len(cur["key"]) == keybits // 4:
                     cases.append({k2: cur[k2] for k2 in ("key", "iv", "aad", "pt", "ct")})
                 cur = {}
+    return cases
+
+
+def parse_ocb(path, keybits):
+    """testvectors/OCB_AES128.tv (OpenSSL evp test format): blank-line separated cases; kept when the
+    key has the build's size, the IV 12 bytes and the tag 16 bytes and no error is expected
+    (aes_testvectors_OCB.h:88-93)"""
+    cases, cur = [], {}
+    for line in list(open(path)) + [""]:
+        line = line.strip()
+        if line.startswith("#"):
+            continue
+        if not line:
+            if cur.get("Cipher", "").lower().endswith("-ocb") and "Result" not in cur:
+                if len(cur["Key"]) == keybits // 4 and len(cur["IV"]) == 24 and len(cur["Tag"]) == 32:
+                    cases.append({"key": cur["Key"].lower(), "iv": cur["IV"].lower(), "aad": cur.get("AAD", "").lower(),
+                                  "pt": cur.get("Plaintext", "").lower(),
+                                  "ct": (cur.get("Ciphertext", "") + cur["Tag"]).lower()})
+            cur = {}
+        elif " = " in line or line.endswith(" ="):
+            k, _, v = line.partition(" =")
+            cur[k.strip()] = v.strip()
     return cases
 
 
@@ -210,6 +238,16 @@ def ref_samples():
             out["gcmsiv"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
                                   "aad_tag": f"gsa{bits}{n}", "pt_tag": f"gsp{bits}{n}",
                                   "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    out["ocb"] = []
+    for bits, lib in libs.items():
+        for n, a in ((0, 0), (0, 5), (1, 0), (16, 16), (57, 31), (1000, 20), (4096 + 3, 129), (1 << 18, 7), (100, 70000 + 5)):
+            key, nonce = rnd(f"ock{bits}{n}", bits // 8), rnd(f"ocn{bits}{n}", 12)
+            aad, pt = rnd(f"oca{bits}{n}{a}", a), rnd(f"ocp{bits}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.AES_OCB_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            out["ocb"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                               "aad_tag": f"oca{bits}{n}{a}", "pt_tag": f"ocp{bits}{n}",
+                               "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
     out["cbc_decrypt"], out["cfb_decrypt"] = [], []
     for bits, lib in libs.items():
         lib.AES_CBC_decrypt.restype = ctypes.c_char
@@ -271,6 +309,18 @@ def main():
     w("gcmsiv128.json", {"source": "testvectors/SIV_GCM_ACVP.tv (102 AES-128 cases, aes_testvectors_GCMSIV.h)",
                          "cases": c})
     print(f"gcmsiv128: {len(c)} cases")
+    c = parse_ocb(os.path.join(tv, "OCB_AES128.tv"), 128)
+    ref128 = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref128.so"))
+    for case in c:                      # the file is only trusted through the reference itself
+        pt, aad = bytes.fromhex(case["pt"]), bytes.fromhex(case["aad"])
+        o = ctypes.create_string_buffer(len(pt) + 16)
+        ref128.AES_OCB_encrypt(bytes.fromhex(case["key"]), bytes.fromhex(case["iv"]), aad, ctypes.c_size_t(len(aad)),
+                               pt, ctypes.c_size_t(len(pt)), o)
+        assert o.raw.hex() == case["ct"], case
+    w("ocb128.json", {"source": "testvectors/OCB_AES128.tv, cases the reference harness runs "
+                                "(aes_testvectors_OCB.h:88-93); each re-checked against oracle/_ref/libref128.so",
+                      "cases": c})
+    print(f"ocb128: {len(c)} cases")
     w("oracle_ref_samples.json", ref_samples())
     print("ok")
 

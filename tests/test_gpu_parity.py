@@ -434,3 +434,52 @@ def test_cbc_cfb_decrypt(uaes, orc, torch):
     assert host(dst, 0, n) == orc.cfb(key[:16], iv, ct)
     uaes.chain_decrypt(128, key[:16], iv, src, n, src, cbc=True)
     assert host(src, 0, n) == orc.cbc(key[:16], iv, ct)[1]
+
+
+# ---------------------------------------------------------------- OCB
+
+def test_ocb(uaes, orc, torch):
+    m = golden("main_c.json")
+    a = uaes.MicroAES(128)
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"])[:12], H(m["aad"]), H(m["plaintext"])
+    out = a.AES_OCB_encrypt(key, nonce, aad, pt)                  # main.c:204-210
+    assert out == H(m["ocb128"])
+    assert a.AES_OCB_decrypt(key, nonce, aad, out) == (0, pt)
+    v = m["ocb_rfc7253"]                                          # main.c:262-274
+    assert a.AES_OCB_encrypt(H(v["key"]), H(v["iv"]), H(v["aad"]), H(v["pt"])) == H(v["ct"])
+    cases = golden("ocb128.json")["cases"]                        # testvectors/OCB_AES128.tv
+    assert len(cases) == 16
+    for c in cases:
+        assert a.AES_OCB_encrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+        assert a.AES_OCB_decrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"])), c
+    lib = {b: uaes.MicroAES(b) for b in (128, 192, 256)}
+    for c in golden("oracle_ref_samples.json")["ocb"]:            # unmodified reference runs
+        out = lib[c["bits"]].AES_OCB_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+    for bits in (128, 256):
+        for n, alen in [(0, 0), (0, 5), (1, 0), (15, 16), (16, 0), (17, 1), (511, 33), (512, 0), (513, 100), (4096, 7),
+                        (16 * 1024 + 3, 20), ((1 << 20) + 9, 20), (3 * (1 << 20), 5000 + 7)]:
+            key, nonce = rnd(f"oc-k{bits}{n}", bits // 8), rnd(f"oc-n{bits}{n}", 12)
+            aad, data = rnd(f"oc-a{bits}{n}", alen), rnd(f"oc-d{bits}{n}", n)
+            want = orc.ocb_encrypt(key, nonce, aad, data)
+            assert lib[bits].AES_OCB_encrypt(key, nonce, aad, data) == want, (bits, n, alen)
+            assert lib[bits].AES_OCB_decrypt(key, nonce, aad, want) == (0, data), (bits, n, alen)
+            if n:
+                bad = bytearray(want)
+                bad[n // 2] ^= 1
+                assert lib[bits].AES_OCB_decrypt(key, nonce, aad, bytes(bad)) == orc.ocb_decrypt(key, nonce, aad, bytes(bad))
+    # every value of "bottom" (the last six nonce bits select the Stretch window)
+    key, data = rnd("oc-bk", 16), rnd("oc-bd", 100)
+    for b in range(64):
+        nonce = rnd("oc-bn", 11) + bytes([0x40 | b])
+        assert a.AES_OCB_encrypt(key, nonce, b"", data) == orc.ocb_encrypt(key, nonce, b"", data), b
+    # device pointers, in place
+    key, nonce, aad = rnd("oc-dk", 16), rnd("oc-dn", 12), rnd("oc-da", 33)
+    n = (1 << 21) + 5
+    data = rnd("oc-dd", n)
+    want = orc.ocb_encrypt(key, nonce, aad, data)
+    buf = dev(torch, data, pad=16)
+    uaes.ocb(128, key, nonce, aad, buf, n, buf, True)
+    assert host(buf, 0, n + 16) == want
+    assert uaes.ocb(128, key, nonce, aad, buf, n, buf, False) == 0
+    assert host(buf, 0, n) == data

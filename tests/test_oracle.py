@@ -204,6 +204,26 @@ def test_cbc_cfb_vectors_and_recorded_reference(orc):
         assert sha256(orc.cfb(H(c["key"]), H(c["iv"]), rnd(c["ct_tag"], c["n"]))) == c["pt_sha256"], c
 
 
+# ---------------------------------------------------------------- OCB
+
+def test_ocb_vectors_and_recorded_reference(orc):
+    m = golden("main_c.json")
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"])[:12], H(m["aad"]), H(m["plaintext"])
+    out = orc.ocb_encrypt(key, nonce, aad, pt)                      # main.c:204-210
+    assert out == H(m["ocb128"])
+    assert orc.ocb_decrypt(key, nonce, aad, out) == (0, pt)
+    v = m["ocb_rfc7253"]                                            # main.c:262-274
+    assert orc.ocb_encrypt(H(v["key"]), H(v["iv"]), H(v["aad"]), H(v["pt"])) == H(v["ct"])
+    cases = golden("ocb128.json")["cases"]
+    assert len(cases) == 16
+    for c in cases:
+        assert orc.ocb_encrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+        assert orc.ocb_decrypt(H(c["key"]), H(c["iv"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"]))
+    for c in golden("oracle_ref_samples.json")["ocb"]:
+        out = orc.ocb_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+
+
 # ---------------------------------------------------------------- edge cases
 
 def test_edge_cases(orc):
