@@ -7,7 +7,8 @@ measured HBM roofline, next to micro_aes.c timed on the box's host cores.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        the reference's own CPU code on all host cores
 
-One step = one pass of the hot path (one ctr_kernel launch) over this rank's 16 GiB shard of the
+One step = one pass of the hot path (one ctr_kernel launch: table-driven warps plus the bitsliced
+ALU co-runner warps) over this rank's 16 GiB shard of the
 N*16 GiB buffer; rank r owns keystream blocks [r*2^30, (r+1)*2^30) (counter-range sharding, no
 data-path collective; the key and IV are broadcast once over NCCL).  Scaling is therefore weak.
 torch is used for device memory, streams/events and torch.distributed only; the encryption is
@@ -375,7 +376,7 @@ def run_gpu(args):
                        "input": f"splitmix64(seed=0x{SEED:x}) generated on device"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": {"ctr128": "uaes::ctr_kernel<10>", "ctr256": "uaes::ctr_kernel<14>", "ecb128": "uaes::ecb_kernel<10,true>",
+                         "kernel": {"ctr128": "uaes::ctr_kernel<10,384,true,2> (384 table-driven + 128 bitsliced threads per CTA)", "ctr256": "uaes::ctr_kernel<14,384,true,2>", "ecb128": "uaes::ecb_kernel<10,true>",
                                     "xts256": "uaes::xts_sectors_kernel<14,true>", "gcm128": "uaes::gcm_bulk_kernel<10,0>",
                                     "ecb128dec": "uaes::ecb_kernel<10,false>", "xts256dec": "uaes::xts_sectors_kernel<14,false>",
                                     "gcmsiv128": "uaes::gcm_bulk_kernel<10,1,true> + uaes::ctr32_kernel<10>",

@@ -73,6 +73,15 @@ void *uaes_host_alloc(size_t bytes);
 void  uaes_host_free(void *p);
 /* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
 uaes_u64 uaes_kernel_launches(void);
+/* CTR kernel geometry (tuning and tests; the defaults are the measured optimum on B200):
+ *   tt_threads       geometry code: 385 (default) = 384 table-driven threads with two blocks in
+ *                    flight each + 128 bitsliced co-runner threads; 384 = the same with one block
+ *                    in flight; 512 / 768 / 1024 = table-driven warps only
+ *   bs_permille      share of the blocks, in 1/1024, given to the bitsliced ALU co-runner warps
+ *                    (0 = co-runner off)
+ *   bs_min_blocks    calls shorter than this many 16-byte blocks never use the co-runner
+ * A negative value leaves that setting unchanged.  Results do not depend on any of them. */
+void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks);
 
 /* ---- the hot path, run-time key length ------------------------------------- */
 /* keybits = 128, 192 or 256 everywhere (XTS: 128 or 256, keys = K1 || K2). */

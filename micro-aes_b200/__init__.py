@@ -39,6 +39,7 @@ UAES_ABI = {
     "uaes_host_alloc": (_vp, [_sz]),
     "uaes_host_free": (None, [_vp]),
     "uaes_kernel_launches": (_u64, []),
+    "uaes_ctr_tuning": (None, [_int, _int, ctypes.c_longlong]),
     "uaes_ecb_encrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
     "uaes_ecb_decrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
     "uaes_ctr_crypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
@@ -326,3 +327,8 @@ def set_async(flag):
 
 def kernel_launches():
     return core().uaes_kernel_launches()
+
+
+def ctr_tuning(tt_threads=-1, bs_permille=-1, bs_min_blocks=-1):
+    """CTR kernel geometry (uaes_ctr_tuning in include/uaes_b200.h); negative = leave unchanged"""
+    core().uaes_ctr_tuning(tt_threads, bs_permille, bs_min_blocks)

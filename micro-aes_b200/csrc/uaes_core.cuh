@@ -57,6 +57,26 @@ __device__ __forceinline__ void enc_finish(uint32_t lb, uint32_t &s0, uint32_t &
     s0 = o0; s1 = o1; s2 = o2; s3 = o3;
 }
 
+// the same for N independent blocks, rounds interleaved: N x 16 lookups in flight per warp, which
+// is what keeps the lookup pipe fed when few table-driven warps share the SM with the co-runner
+template <int NR, int FIRST, int N>
+__device__ __forceinline__ void enc_finish_n(uint32_t lb, uint32_t (&s)[N][4], const uint32_t *rk,
+                                             const uint4 (&x)[N])
+{
+#pragma unroll
+    for (int r = FIRST; r < NR; ++r)
+#pragma unroll
+        for (int i = 0; i < N; ++i) enc_round(lb, s[i][0], s[i][1], s[i][2], s[i][3], rk + 4 * r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t o0 = enc_last_col(lb, s[i][0], s[i][1], s[i][2], s[i][3]) ^ rk[4 * NR + 0] ^ x[i].x;
+        const uint32_t o1 = enc_last_col(lb, s[i][1], s[i][2], s[i][3], s[i][0]) ^ rk[4 * NR + 1] ^ x[i].y;
+        const uint32_t o2 = enc_last_col(lb, s[i][2], s[i][3], s[i][0], s[i][1]) ^ rk[4 * NR + 2] ^ x[i].z;
+        const uint32_t o3 = enc_last_col(lb, s[i][3], s[i][0], s[i][1], s[i][2]) ^ rk[4 * NR + 3] ^ x[i].w;
+        s[i][0] = o0; s[i][1] = o1; s[i][2] = o2; s[i][3] = o3;
+    }
+}
+
 // whole block: out = E_K(s) ^ x
 template <int NR>
 __device__ __forceinline__ void enc_block(uint32_t lb, uint32_t &s0, uint32_t &s1, uint32_t &s2,

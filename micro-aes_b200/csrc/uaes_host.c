@@ -66,6 +66,10 @@ void uaes_clear_error(void) { tls_err = 0; tls_msg[0] = 0; }
 void uaes_set_stream(void *stream) { tls_stream = stream; }
 void uaes_set_async(int enable) { tls_async = enable; }
 uaes_u64 uaes_kernel_launches(void) { return uaes_launch_count(); }
+void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks)
+{
+    uaes_launch_ctr_tuning(tt_threads, bs_permille, bs_min_blocks);
+}
 
 int uaes_device_count(void)
 {

@@ -14,6 +14,7 @@
 
 #include "uaes_core.cuh"
 #include "uaes_gf128.cuh"
+#include "uaes_bitslice.cuh"
 
 namespace uaes {
 
@@ -90,6 +91,12 @@ struct CtrArgs {
     uint4 *out;
     uint64_t nblocks;            // full blocks
     uint32_t tail;               // len % 16
+    // split between the table-driven warps and the bitsliced ALU co-runner warps (below)
+    uint64_t tt_blocks;          // blocks [0, tt_blocks) belong to the table-driven warps
+    uint64_t bs_u0;              // v0 + tt_blocks: first counter (not reduced mod 2^56) of the
+                                 // bitsliced range, a multiple of 1024 unless bs_passes == 0
+    uint64_t bs_passes;          // 1024-counter passes covering blocks [tt_blocks, nblocks)
+    BsKeyPlanes bs;
 };
 
 // Work unit = a "group": the 256 counter values that share bytes 0..14 of the counter block.
@@ -108,8 +115,81 @@ struct CtrArgs {
 // (profiles/), so lookups are what is worth saving.  A warp serves one half of a group (rows
 // it = 0..3: byte 15 = 128*half + 32*it + lane) and walks a CONTIGUOUS run of groups so that the
 // slow-changing constants really are constant; its partner warp serves the other half.
-template <int NR, int kCtrThreads>
-__global__ void __launch_bounds__(kCtrThreads, 1) ctr_kernel(const __grid_constant__ CtrArgs a)
+// ---- the ALU co-runner: one warpgroup (4 warps, one per scheduler) of bitsliced AES -------------
+// The table-driven warps keep the shared-memory pipe at its roof and, with their lookup addresses
+// built on the FMA pipe, use less than half of the ALU pipe; these four warps turn the rest into
+// keystream with no lookups at all (uaes_bitslice.cuh).  Register budgets differ by 2x, so the two
+// roles re-balance the CTA's register file with setmaxnreg right after the table fill.
+constexpr int kBsThreads = 128;
+
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <int NR, int BATCH>
+__device__ __forceinline__ void ctr_bitsliced_warp(const CtrArgs &a, uint32_t lb, uint32_t *um,
+                                                   uint64_t p0, uint64_t p1)
+{
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t tag16 = ~0ull;
+    for (uint64_t p = p0; p < p1; ++p) {
+        const uint64_t u0 = a.bs_u0 + (p << 10);
+        const uint64_t vc = u0 & kMask56;
+        {   // pull this pass's 16 KiB of input towards L2 while the rounds run (4 lines per lane)
+            const uint64_t kb = u0 - a.v0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint64_t k = kb + (uint64_t)(lane * 4 + i) * 8;
+                if (k < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + k));
+            }
+        }
+        if ((vc >> 16) != tag16) {              // counter bytes <= 13 changed: every 64 passes
+            tag16 = vc >> 16;
+            uint32_t w2, w3, uw[6];
+            ctr_words(a.b8, vc, w2, w3);
+            bs_uniform_words([&](int t, uint32_t x) { return lut_index(lb, t == 0 ? kOffT0 : t == 1 ? kOffT1 : t == 2 ? kOffT2 : kOffT3, x); },
+                             a.w0 ^ rk[0], a.w1 ^ rk[1], w2 ^ rk[2], w3 ^ rk[3], rk, uw);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 6; ++j) um[32 * j + lane] = bs_mask(uw[j], (int)lane);
+            __syncwarp();
+        }
+        uint32_t s[128];
+        bs_first_rounds(s, lane, (uint32_t)(vc >> 8) & 0xfcu, a.bs.k0, um);
+#pragma unroll 1
+        for (int r = 3; r < NR; ++r) bs_round(s, a.bs.k[r - 3]);
+        bs_last_round(s, a.bs.k[NR - 3]);
+        // XOR with the data: slot t of all lanes = one coalesced 512-byte row.  The loads are
+        // software-pipelined one batch ahead (the first batch goes out before the transposes).
+        const int64_t k0 = (int64_t)(u0 - a.v0) + lane;      // block index of slot 0; >= tt_blocks
+        auto load_batch = [&](int t0, uint4 (&x)[BATCH]) {
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int64_t k = k0 + 32 * (t0 + i);
+                x[i] = (uint64_t)k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
+            }
+        };
+        uint4 x[BATCH], y[BATCH];
+        load_batch(0, x);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+#pragma unroll
+        for (int t0 = 0; t0 < 32; t0 += BATCH) {
+            if (t0 + BATCH < 32) load_batch(t0 + BATCH, y);
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int64_t k = k0 + 32 * (t0 + i);
+                const int t = t0 + i;
+                x[i].x ^= s[t]; x[i].y ^= s[32 + t]; x[i].z ^= s[64 + t]; x[i].w ^= s[96 + t];
+                if ((uint64_t)k < a.nblocks) st_stream(a.out + k, x[i]);
+                x[i] = y[i];
+            }
+        }
+    }
+}
+
+template <int NR, int kCtrThreads, bool BS, int ILP>
+__global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_kernel(const __grid_constant__ CtrArgs a)
 {
     constexpr int kCtrWarps = kCtrThreads / 32;
     extern __shared__ __align__(16) uint8_t dyn[];
@@ -117,9 +197,34 @@ __global__ void __launch_bounds__(kCtrThreads, 1) ctr_kernel(const __grid_consta
     const uint32_t *rk = a.ks.w;
     const uint32_t lane = threadIdx.x & 31;
 
+    if (BS) {
+        // launch allocation is 65536 / threads rounded down to 8; hand the table warps' surplus to
+        // the bitsliced warpgroup (whose 128-plane state needs it)
+        constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
+        constexpr int kTtRegs = ILP == 1 ? 80 : 104;
+        constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
+        constexpr int kBsRegs = (kBsRegs0 > 232 ? 232 : kBsRegs0) / 8 * 8;
+        if (threadIdx.x >= kCtrThreads) {
+            reg_inc<kBsRegs>();
+            const uint32_t tbase = align_table_base(dyn);
+            const uint32_t bw = (threadIdx.x - kCtrThreads) >> 5;
+            const uint32_t off = tbase + kEncTableBytes + bw * (kBsUniformMasks * 4) - smem_u32(dyn);
+            if (off + kBsUniformMasks * 4 > dyn_smem_size()) __trap();
+            const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + bw;
+            const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+            const uint64_t per = (a.bs_passes + nw - 1) / nw;
+            const uint64_t p0 = gw * per < a.bs_passes ? gw * per : a.bs_passes;
+            const uint64_t p1 = p0 + per < a.bs_passes ? p0 + per : a.bs_passes;
+            ctr_bitsliced_warp<NR, 4>(a, lb, (uint32_t *)(dyn + off), p0, p1);
+            return;
+        }
+        reg_dec<kTtRegs>();
+    }
+
+    const uint64_t tt_blocks = BS ? a.tt_blocks : a.nblocks;
     const uint32_t lowoff = (uint32_t)a.v0 & 255u;
     const uint64_t g0 = a.v0 >> 8;
-    const uint64_t ngroups = (lowoff + a.nblocks + 255) >> 8;
+    const uint64_t ngroups = (lowoff + tt_blocks + 255) >> 8;
     const uint64_t wg = (uint64_t)blockIdx.x * kCtrWarps + (threadIdx.x >> 5);
     const uint32_t half = (uint32_t)wg & 1u;
     const uint64_t npairs = (uint64_t)gridDim.x * (kCtrWarps / 2);
@@ -134,7 +239,7 @@ __global__ void __launch_bounds__(kCtrThreads, 1) ctr_kernel(const __grid_consta
     };
     auto fetch = [&](uint64_t grp, int it) -> uint4 {
         const int64_t k = kof(grp, it);
-        if (grp < j1 && k >= 0 && (uint64_t)k < a.nblocks) return ld_stream(a.in + k);
+        if (grp < j1 && k >= 0 && (uint64_t)k < tt_blocks) return ld_stream(a.in + k);
         return make_uint4(0, 0, 0, 0);
     };
 
@@ -142,7 +247,9 @@ __global__ void __launch_bounds__(kCtrThreads, 1) ctr_kernel(const __grid_consta
     uint32_t U[4][4], Cp1 = 0, E0 = 0, E1 = 0, E2 = 0, E3 = 0;
     const uint32_t s0 = a.w0 ^ rk[0], s1 = a.w1 ^ rk[1];
 
-    uint4 cur = fetch(j0, 0);
+    uint4 cur[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) cur[i] = fetch(j0, i);
     for (uint64_t j = j0; j < j1; ++j) {
         const uint64_t vg = ((g0 + j) << 8) & kMask56;
         uint32_t w2, w3;
@@ -175,13 +282,23 @@ __global__ void __launch_bounds__(kCtrThreads, 1) ctr_kernel(const __grid_consta
         const uint32_t D2 = E2 ^ lut<3, kOffT3>(lb, C1), D3 = E3 ^ lut<2, kOffT2>(lb, C1);
 
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const uint4 nxt = it < 3 ? fetch(j, it + 1) : fetch(j + 1, 0);
-            const int64_t k = kof(j, it);
-            uint32_t t0 = D0 ^ U[it][0], t1 = D1 ^ U[it][1], t2 = D2 ^ U[it][2], t3 = D3 ^ U[it][3];
-            enc_finish<NR, 3>(lb, t0, t1, t2, t3, rk, cur.x, cur.y, cur.z, cur.w);
-            if (k >= 0 && (uint64_t)k < a.nblocks) st_stream(a.out + k, make_uint4(t0, t1, t2, t3));
-            cur = nxt;
+        for (int it = 0; it < 4; it += ILP) {
+            uint4 nxt[ILP];
+            uint32_t t[ILP][4];
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                const int n = it + ILP + i;
+                nxt[i] = n < 4 ? fetch(j, n) : fetch(j + 1, n - 4);
+                t[i][0] = D0 ^ U[it + i][0]; t[i][1] = D1 ^ U[it + i][1];
+                t[i][2] = D2 ^ U[it + i][2]; t[i][3] = D3 ^ U[it + i][3];
+            }
+            enc_finish_n<NR, 3, ILP>(lb, t, rk, cur);
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                const int64_t k = kof(j, it + i);
+                if (k >= 0 && (uint64_t)k < tt_blocks) st_stream(a.out + k, make_uint4(t[i][0], t[i][1], t[i][2], t[i][3]));
+                cur[i] = nxt[i];
+            }
         }
     }
 
@@ -296,37 +413,75 @@ static unsigned grid_for(uint64_t warp_units)
     return (unsigned)(need < 1 ? 1 : need < sms ? need : sms);
 }
 
-template <int NR, int kCtrThreads>
+template <int NR, int kCtrThreads, bool BS, int ILP = 1>
 static cudaError_t launch_ctr_nt(const CtrArgs &a, cudaStream_t st)
 {
     constexpr int kCtrWarps = kCtrThreads / 32;
-    cudaError_t e = opt_in_smem(ctr_kernel<NR, kCtrThreads>);
+    cudaError_t e = opt_in_smem(ctr_kernel<NR, kCtrThreads, BS, ILP>);
     if (e != cudaSuccess) return e;
-    const uint64_t ngroups = (((uint32_t)a.v0 & 255u) + a.nblocks + 255) >> 8;
+    const uint64_t ngroups = (((uint32_t)a.v0 & 255u) + a.tt_blocks + 255) >> 8;
     // a pair of warps per group; at least 4 groups per pair before another CTA is worth its table fill
-    const uint64_t ctas = (ngroups + 4 * (kCtrWarps / 2) - 1) / (4 * (kCtrWarps / 2));
+    uint64_t ctas = (ngroups + 4 * (kCtrWarps / 2) - 1) / (4 * (kCtrWarps / 2));
+    if (BS && ctas < (a.bs_passes + 3) / 4) ctas = (a.bs_passes + 3) / 4;    // one pass per co-runner warp
     const uint64_t sms = (uint64_t)sm_count();
-    ctr_kernel<NR, kCtrThreads><<<(unsigned)(ctas < 1 ? 1 : ctas < sms ? ctas : sms), kCtrThreads, kDynSmem, st>>>(a);
+    ctr_kernel<NR, kCtrThreads, BS, ILP><<<(unsigned)(ctas < 1 ? 1 : ctas < sms ? ctas : sms), kCtrThreads + (BS ? kBsThreads : 0), kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
 
-// CTA size of the CTR kernel: registers per thread trade against warps per SM (768 threads = 80
-// registers, no spills).  UAES_CTR_THREADS overrides it for tuning runs.
-template <int NR>
-static cudaError_t launch_ctr_nr(const CtrArgs &a, cudaStream_t st)
+// CTR geometry: share of the blocks given to the bitsliced warps in 1/1024 (tuned on B200,
+// profiles/; 0 turns the co-runner off), threads of the table-driven warps, and the call size
+// below which one kernel flavour is simpler and as fast.  Environment variables set the initial
+// values, uaes_ctr_tuning() changes them at run time (tests sweep them).
+static int env_int(const char *name, int dflt)
 {
-    static int threads = 0;
-    if (!threads) {
-        const char *e = getenv("UAES_CTR_THREADS");
-        threads = e ? atoi(e) : 768;
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+static int g_ctr_threads = 0, g_ctr_share = -1;
+static long long g_ctr_bs_min = 1ll << 20;
+
+// Measured on B200, AES-128, 16 GiB (profiles/r1_ctr_hybrid_sweep.txt): table-driven warps alone
+// 942-946 GiB/s; with the co-runner 1000 / 1006 / 1004 / 980 GiB/s at 170 / 185 / 200 / 215 per
+// 1024, falling off quickly once the bitsliced warps become the tail.  Geometry codes:
+//   384  = 384 table-driven threads, one block per thread in flight (+128 co-runner threads)
+//   385  = the same with two blocks per thread in flight (default; the co-runner's instructions
+//          lengthen every lookup round trip, the second block hides it: 968 -> 1006 GiB/s)
+//   512 / 768 / 1024 = table-driven warps only
+constexpr int kCtrDefaultGeometry = 385, kCtrDefaultShare = 190;
+
+static void ctr_tuning_init()
+{
+    if (g_ctr_threads) return;
+    g_ctr_threads = env_int("UAES_CTR_THREADS", kCtrDefaultGeometry);
+    g_ctr_share = env_int("UAES_CTR_BS_PERMILLE", kCtrDefaultShare);
+}
+
+template <int NR>
+static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
+{
+    ctr_tuning_init();
+    const int threads = g_ctr_threads, share = g_ctr_share;
+    a.tt_blocks = a.nblocks; a.bs_u0 = 0; a.bs_passes = 0;
+    if (share > 0 && (threads == 384 || threads == 385) && (long long)a.nblocks >= g_ctr_bs_min) {
+        // bitsliced range = [S, v0 + nblocks) with S a multiple of 1024 in counter space
+        const uint64_t want = a.nblocks / 1024 * (uint64_t)share;           // blocks for the co-runner
+        const uint64_t end = a.v0 + a.nblocks;
+        uint64_t s0 = (end - want) & ~1023ull;
+        if (s0 < a.v0) s0 = (a.v0 + 1023) & ~1023ull;
+        if (s0 < end) {
+            a.tt_blocks = s0 - a.v0; a.bs_u0 = s0; a.bs_passes = (end - s0 + 1023) >> 10;
+            bs_make_key_planes(a.ks.w, NR, &a.bs);
+            return threads == 384 ? launch_ctr_nt<NR, 384, true, 1>(a, st) : launch_ctr_nt<NR, 384, true, 2>(a, st);
+        }
     }
     switch (threads) {
-    case 1024: return launch_ctr_nt<NR, 1024>(a, st);
-    case 896:  return launch_ctr_nt<NR, 896>(a, st);
-    case 640:  return launch_ctr_nt<NR, 640>(a, st);
-    case 512:  return launch_ctr_nt<NR, 512>(a, st);
-    default:   return launch_ctr_nt<NR, 768>(a, st);
+    case 384:  return launch_ctr_nt<NR, 384, false, 1>(a, st);
+    case 385:  return launch_ctr_nt<NR, 384, false, 2>(a, st);
+    case 1024: return launch_ctr_nt<NR, 1024, false>(a, st);
+    case 512:  return launch_ctr_nt<NR, 512, false>(a, st);
+    default:   return launch_ctr_nt<NR, 768, false>(a, st);
     }
 }
 
@@ -352,6 +507,14 @@ using namespace uaes;
 extern "C" {
 
 u64 uaes_launch_count(void) { return g_launches; }
+
+void uaes_launch_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks)
+{
+    ctr_tuning_init();
+    if (tt_threads > 0) g_ctr_threads = tt_threads;
+    if (bs_permille >= 0) g_ctr_share = bs_permille > 1024 ? 1024 : bs_permille;
+    if (bs_min_blocks >= 0) g_ctr_bs_min = bs_min_blocks;
+}
 
 int uaes_launch_ctr(const uaes_keysched *ks, const uaes_ctrblock *cb, const void *in, void *out,
                     u64 len, void *stream)

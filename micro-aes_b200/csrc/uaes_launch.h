@@ -108,6 +108,8 @@ int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *st
 
 /* kernels launched so far by this process */
 u64 uaes_launch_count(void);
+/* CTR kernel geometry, see uaes_ctr_tuning() in uaes_b200.h */
+void uaes_launch_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks);
 
 #ifdef __cplusplus
 }

@@ -12,11 +12,14 @@
 // serves one 4-byte word per bank per clock, i.e. at most 32 table lookups / clk / SM.  Random
 // S-box indices hit random banks, so every table is stored 32 times, once per lane, with lane l's
 // copy living entirely in bank l:
-//     address(table pair p, table t in {0,1}, entry x, lane l) = base + p*65536 + x*256 + t*128 + l*4
-// A lookup is then ONE byte-permute (PRMT builds  x<<8 | lane*4  straight from the state word,
-// no shift/mask) plus ONE conflict-free LDS with an immediate table offset.  `base` must be
-// 64 KiB aligned inside the CTA's shared window for the PRMT trick; kernels over-allocate and
-// align at run time (the window starts at a driver-chosen offset).
+//     address(table t in 0..3, entry x, lane l) = base + t*32768 + x*128 + l*4
+// A lookup is then ONE integer dot product (IDP.4A with a one-hot selector computes
+// byte*128 + lanebase straight from the state word -- on the FMA pipe, which is otherwise idle,
+// leaving the ALU pipe to the XORs and to the bitsliced co-runner of the CTR kernel) plus ONE
+// conflict-free LDS with an immediate table offset.  -DUAES_LUT_PRMT selects the first-generation
+// layout (x*256 + t*128 + l*4, address by one PRMT on the ALU pipe; same speed stand-alone,
+// measured in profiles/r1_idp_vs_prmt.txt).  Kernels over-allocate and align `base` to 64 KiB at
+// run time (needed by the PRMT variant; the window starts at a driver-chosen offset).
 #pragma once
 #include <stdint.h>
 
@@ -109,7 +112,12 @@ __constant__ ByteTable c_inv_sbox = make_inv_sbox();
 
 constexpr uint32_t kTablePairBytes = 65536;            // 256 entries x (2 tables x 32 lanes x 4 B)
 constexpr uint32_t kTableAlign     = 65536;
+#ifndef UAES_LUT_PRMT
+// IDP.4A addressing: entry stride 128 B, table A in the low 32 KiB of a pair region, B in the high
+constexpr uint32_t kOffT0 = 0, kOffT1 = 32768, kOffT2 = kTablePairBytes, kOffT3 = kTablePairBytes + 32768;
+#else
 constexpr uint32_t kOffT0 = 0, kOffT1 = 128, kOffT2 = kTablePairBytes, kOffT3 = kTablePairBytes + 128;
+#endif
 constexpr uint32_t kEncTableBytes  = 2 * kTablePairBytes;   // Te0|Te1, Te2|Te3
 constexpr uint32_t kDecTableBytes  = 2 * kTablePairBytes;   // Td0|Td1, Td4|(unused)
 
@@ -138,7 +146,11 @@ __device__ __forceinline__ void fill_pair(uint32_t region, const WordTable &srcA
     for (uint32_t w = threadIdx.x; w < 256u * 64u; w += blockDim.x) {
         const uint32_t row = w >> 6, col = w & 63;
         const uint32_t v = col < 32 ? rotl32(srcA.v[row], rotA) : rotl32(srcB.v[row], rotB);
+#ifndef UAES_LUT_PRMT
+        sts32(region + (col >> 5) * 32768 + row * 128 + (col & 31) * 4, v);
+#else
         sts32(region + row * 256 + col * 4, v);
+#endif
     }
 }
 
@@ -169,9 +181,28 @@ __device__ __forceinline__ void init_dec_tables(uint32_t base)
 template <int BYTE, uint32_t OFF>
 __device__ __forceinline__ uint32_t lut(uint32_t lanebase, uint32_t w)
 {
+#ifndef UAES_LUT_PRMT
+    // one integer dot product on the FMA pipe: w.b[BYTE] * 128 + lanebase (selector is one-hot)
+    const uint32_t a = __dp4a(w, 0x80u << (8 * BYTE), lanebase);
+#else
     const uint32_t a = __byte_perm(w, lanebase, 0x7604 | (BYTE << 4));
+#endif
     uint32_t r;
     asm("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(a), "n"(OFF));
+    return r;
+}
+
+// lookup by an already extracted index x (0..255) and a run-time table offset: rare, warp-uniform
+// set-up work only
+__device__ __forceinline__ uint32_t lut_index(uint32_t lanebase, uint32_t off, uint32_t x)
+{
+    uint32_t r;
+#ifndef UAES_LUT_PRMT
+    const uint32_t a = lanebase + off + x * 128u;
+#else
+    const uint32_t a = lanebase + off + x * 256u;
+#endif
+    asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
     return r;
 }
 

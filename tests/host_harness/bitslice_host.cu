@@ -1,0 +1,45 @@
+// bitslice_host.cu -- TEST INFRASTRUCTURE: runs the host compilation of uaes_bitslice.cuh (the
+// bitsliced co-runner of ctr_kernel) for one 1024-counter pass on the CPU, so that
+// tests/test_bitslice_host.py can compare it with the oracle without a GPU.
+// Build: nvcc -O1 -shared -Xcompiler -fPIC -I micro-aes_b200/csrc -o tests/host_harness/libbitslice_host.so ...
+#include <stdint.h>
+#include <string.h>
+#include "uaes_tables.cuh"
+#include "uaes_bitslice.cuh"
+
+using namespace uaes;
+
+static const WordTable kTe0 = make_te0();
+
+static uint32_t te_host(int tbl, uint32_t x)
+{
+    const uint32_t v = kTe0.v[x & 255];
+    return tbl ? (v << (8 * tbl)) | (v >> (32 - 8 * tbl)) : v;
+}
+
+// rk: expanded key words (little-endian words of the byte schedule), block0: the 16 counter-block
+// bytes of the pass base (counter value multiple of 1024 in bytes 9..15), out: 1024 keystream blocks
+extern "C" int bs_host_pass(const uint32_t *rk, int rounds, const uint8_t *block0, uint8_t *out)
+{
+    static BsKeyPlanes kp;
+    bs_make_key_planes(rk, rounds, &kp);
+    uint32_t w[4];
+    memcpy(w, block0, 16);
+    uint32_t uw[6], um[kBsUniformMasks];
+    bs_uniform_words(te_host, w[0] ^ rk[0], w[1] ^ rk[1], w[2] ^ rk[2], w[3] ^ rk[3], rk, uw);
+    for (int i = 0; i < kBsUniformMasks; ++i) um[i] = bs_mask(uw[i / 32], i % 32);
+    const uint32_t c14 = block0[14];
+    if ((block0[14] & 3) || block0[15]) return 1;
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+        uint32_t s[128];
+        bs_first_rounds(s, lane, c14, kp.k0, um);
+        for (int r = 3; r < rounds; ++r) bs_round(s, kp.k[r - 3]);
+        bs_last_round(s, kp.k[rounds - 3]);
+        for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+        for (int t = 0; t < 32; ++t)
+            for (int c = 0; c < 4; ++c) memcpy(out + 16 * (32 * t + lane) + 4 * c, &s[32 * c + t], 4);
+    }
+    return 0;
+}
+
+extern "C" int bs_host_sbox_lut3_count(void) { return kSboxLut3Count; }

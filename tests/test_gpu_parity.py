@@ -162,6 +162,29 @@ def test_ctr_ecb_sizes(uaes, orc, bits):
         assert a.AES_ECB_decrypt(key, data) == orc.ecb_decrypt(key, data), n
 
 
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_ctr_bitsliced_corunner(uaes, orc, torch, bits):
+    """the CTR kernel's ALU co-runner warps (bitsliced AES, csrc/uaes_bitslice.cuh) forced on for
+    small calls, at every split between the two kinds of warps, with ragged ends, counter offsets
+    that are not multiples of 1024 and the carries into counter bytes 13, 12 and 9"""
+    key, iv = rnd(f"bs-k{bits}", bits // 8), rnd(f"bs-i{bits}", 12)
+    try:
+        for threads in (384, 385):               # 385 = two blocks per table-driven thread in flight
+            for share, n, first in ((1024, 16 * 5000 + 3, 0), (512, 16 * 70001, 1), (300, (1 << 21) + 9, 1000),
+                                    (1024, 16 * 3000, (1 << 16) - 1500), (700, 16 * 4100 + 15, (1 << 24) - 2050),
+                                    (1024, 16 * 2500, (1 << 32) - 1200), (900, 16 * 2048, (1 << 56) - 1024 - 2),
+                                    (1, 16 * 9000, 7), (1024, 16 * 1023, 1), (1024, 16, 0)):
+                uaes.ctr_tuning(threads, share, 0)
+                data = rnd(f"bs-d{bits}{n}", n)
+                src, dst = dev(torch, data), dev(torch, b"", pad=n)
+                uaes.ctr_crypt_range(bits, key, iv, first, src, n, dst)
+                torch.cuda.synchronize()
+                assert host(dst, 0, n) == orc.ctr(key, iv, data, first_block=first), (threads, share, n, first)
+                assert host(dst, n, n + 16) == bytes(16)
+    finally:
+        uaes.ctr_tuning(385, 190, 1 << 20)
+
+
 @pytest.mark.parametrize("bits", [128, 256])
 def test_xts_sizes(uaes, orc, bits):
     a = uaes.MicroAES(bits)
