@@ -1,7 +1,6 @@
 set -x
-mkdir -p gpurun_out
-timeout 1700 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-python bench.py > gpurun_out/bench_default.jsonl 2> gpurun_out/bench_default.err
-ncu --set full --clock-control none --import-source on -k regex:ctr_kernel -s 3 -c 1 -o gpurun_out/prof_ctr_hybrid_r1 -f python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_ctr16GiB.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_list.log 2>&1
+mkdir -p gpurun_out; rm -f gpurun_out/bench_bs7.jsonl
+for c in "256 0" "256 170" "256 200" "256 230" "256 260" "256 300"; do set -- $c
+  echo "ctr128 threads=$1 share=$2" >> gpurun_out/bench_bs7.jsonl
+  UAES_CTR_THREADS=$1 UAES_CTR_BS_PERMILLE=$2 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --workload ctr128 >> gpurun_out/bench_bs7.jsonl 2>> gpurun_out/bench_err.log
+done
