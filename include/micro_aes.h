@@ -4,7 +4,7 @@
  *
  * This header declares, with the reference's names, argument order and return
  * codes, the entry points the reference exports when only ECB, CTR (CTR_NA),
- * XEX/XTS, GCM, GCM_SIV and OCB are enabled:
+ * XEX/XTS, GCM, GCM_SIV, OCB and CCM are enabled:
  *
  *     function            replaces (polfosol/micro-AES)
  *     ------------------  ---------------------------------------------
@@ -20,6 +20,9 @@
  *     GCM_SIV_decrypt     micro_aes.h:394-400, micro_aes.c:1499-1516
  *     AES_OCB_encrypt     micro_aes.h:336-342, micro_aes.c:1779-1789   (SURVEY 8f "next" row 3)
  *     AES_OCB_decrypt     micro_aes.h:344-350, micro_aes.c:1802-1813
+ *     AES_CCM_encrypt     micro_aes.h:315-321, micro_aes.c:1268-1282   (SURVEY 8f "next" row 4; one
+ *     AES_CCM_decrypt     micro_aes.h:323-329, micro_aes.c:1295-1314    GPU lane per message: use the
+ *                                                                        batch call of uaes_b200.h for speed)
  *
  * A program written against the reference keeps its `#include "micro_aes.h"`,
  * drops micro_aes.c from its build and links one of
@@ -59,7 +62,7 @@
 #define KWA             0
 #define FPE             0
 #define CMAC            0
-#define CCM             0
+#define CCM             1
 #define EAX             0
 #define EAXP            0
 #define SIV             0
@@ -81,6 +84,8 @@ enum constant_parameters_of_modes
     GCM_TAG_LEN     = 16,       /* micro_aes.h:109 */
     SIVGCM_NONCE_LEN = 12,      /* micro_aes.h:112 */
     SIVGCM_TAG_LEN  = 16,       /* micro_aes.h:113 */
+    CCM_NONCE_LEN   = 11,       /* micro_aes.h:104 */
+    CCM_TAG_LEN     = 16,       /* micro_aes.h:105 */
     OCB_NONCE_LEN   = 12,       /* micro_aes.h:116 */
     OCB_TAG_LEN     = 16,       /* micro_aes.h:117 */
 #if AES___ != 256 && AES___ != 192
@@ -147,6 +152,15 @@ void AES_OCB_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *pntxt, const size_t ptextLen, void *crtxt);
 char AES_OCB_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* CCM: 11-byte nonce; crtxt holds ptextLen + CCM_TAG_LEN bytes */
+void AES_CCM_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+/* decrypts, then authenticates (micro_aes.c:1304-1312) */
+char AES_CCM_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 

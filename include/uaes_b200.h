@@ -160,6 +160,36 @@ int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
                      const uaes_u8 *partials, const uaes_u64 *blocks_after, int nshards,
                      uaes_u64 total_len, uaes_u8 *tag);
 
+/* ---- many independent messages per call ------------------------ */
+/* The MAC of CCM is a serial CBC-MAC chain inside one message (micro_aes.c:1222-1256), so one
+ * message cannot fill a GPU but a batch can: one message per GPU lane, all under one key.
+ * Message i is described by msgs[i]; offsets are relative to the three base pointers and have no
+ * alignment requirement (16-byte aligned offsets are fastest).  msgs, aad, in and out may each
+ * be host or device memory (when msgs is device memory the other three must be, too).
+ *   encrypt: out + out_off holds len + 16 bytes (ciphertext || tag), result = 0
+ *   decrypt: in + in_off holds len + 16 bytes; the plaintext is written, then the tag is checked
+ *            (micro_aes.c:1304-1312); result = 0 or UAES_AUTH_ERROR per message
+ * Return value: 0, or UAES_AUTH_ERROR when at least one message failed, or a negative UAES_E_*. */
+typedef struct uaes_msg {
+    uaes_u64 in_off, out_off, aad_off;
+    unsigned int len, aad_len;         /* payload bytes (without the tag), associated-data bytes */
+    uaes_u8  nonce[16];                /* CCM: the first CCM_NONCE_LEN = 11 bytes */
+    int      result;
+    unsigned int reserved;
+} uaes_msg;
+
+int uaes_ccm_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+int uaes_ccm_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+/* one message with the reference's argument list (micro_aes.c:1268-1314; 11-byte nonce, 16-byte
+ * tag): a batch of one, i.e. ONE GPU lane -- correct and table-driven, but no faster than a CPU
+ * core; use the batch calls for throughput */
+int uaes_ccm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+int uaes_ccm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
 /* ---- synthetic data (bench / tests) ----------------------------------------- */
 /* 64-bit word w of dst (little-endian) = splitmix64(seed + first_word + w); dst is DEVICE memory */
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords);

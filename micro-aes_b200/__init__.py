@@ -57,6 +57,10 @@ UAES_ABI = {
     "uaes_gcmsiv_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_gcm_shard": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp, _int, _vp]),
     "uaes_gcm_combine": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _vp, _int, _u64, _vp]),
+    "uaes_ccm_encrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_ccm_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_ccm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_ccm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_fill_splitmix64": (_int, [_u64, _u64, _vp, _sz]),
     "uaes_xor_fold64": (_int, [_vp, _sz, ctypes.POINTER(_u64)]),
 }
@@ -73,6 +77,8 @@ MICRO_AES_ABI = {
     "AES_GCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_OCB_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_OCB_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_CCM_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_CCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_CBC_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
     "AES_CFB_decrypt": (None, [_cp, _cp, _vp, _sz, _vp]),
     "GCM_SIV_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
@@ -216,6 +222,19 @@ class MicroAES:
         self._after()
         return rc, out.raw[:n]
 
+    def AES_CCM_encrypt(self, key, nonce, aData, pntxt):
+        out = ctypes.create_string_buffer(len(pntxt) + 16)
+        self.lib.AES_CCM_encrypt(key, nonce, aData, len(aData), pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:len(pntxt) + 16]
+
+    def AES_CCM_decrypt(self, key, nonce, aData, crtxt_and_tag):
+        n = len(crtxt_and_tag) - 16
+        out = ctypes.create_string_buffer(max(n, 1))
+        rc = ord(self.lib.AES_CCM_decrypt(key, nonce, aData, len(aData), crtxt_and_tag, n, out))
+        self._after()
+        return rc, out.raw[:n]
+
     def AES_CBC_decrypt(self, key, iVec, crtxt):
         out = ctypes.create_string_buffer(b"\xcc" * max(len(crtxt), 1), max(len(crtxt), 1))
         rc = ord(self.lib.AES_CBC_decrypt(key, iVec, crtxt, len(crtxt), out))
@@ -323,6 +342,23 @@ def set_stream(stream_handle):
 
 def set_async(flag):
     core().uaes_set_async(1 if flag else 0)
+
+
+class Msg(ctypes.Structure):
+    """uaes_msg of include/uaes_b200.h: one message of a batch"""
+    _fields_ = [("in_off", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("aad_off", ctypes.c_uint64),
+                ("len", ctypes.c_uint32), ("aad_len", ctypes.c_uint32), ("nonce", ctypes.c_uint8 * 16),
+                ("result", ctypes.c_int32), ("reserved", ctypes.c_uint32)]
+
+
+def ccm_batch(bits, key, msgs, n, aad, src, dst, decrypt=False):
+    """uaes_ccm_{en,de}crypt_batch; msgs = ctypes array of Msg or a device pointer.  Returns the
+    call's result code (0, or 0x1A when a message failed authentication); raises on UAES_E_*."""
+    f = core().uaes_ccm_decrypt_batch if decrypt else core().uaes_ccm_encrypt_batch
+    rc = f(bits, key, _ptr(msgs), n, _ptr(aad), _ptr(src), _ptr(dst))
+    if rc < 0:
+        check(rc)
+    return rc
 
 
 def kernel_launches():

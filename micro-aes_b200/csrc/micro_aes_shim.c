@@ -111,3 +111,18 @@ char AES_OCB_decrypt(const uint8_t *key, const uint8_t *nonce,
     return code(uaes_ocb_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
                 M_DECRYPTION_ERROR);
 }
+
+void AES_CCM_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_ccm_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+}
+
+char AES_CCM_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_ccm_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+                M_DECRYPTION_ERROR);
+}

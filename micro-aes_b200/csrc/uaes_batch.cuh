@@ -1,0 +1,191 @@
+// uaes_batch.cuh -- many independent messages per launch, ONE MESSAGE PER LANE.
+//
+// CCM's CBC-MAC (micro_aes.c:1222-1256: M <- E(M ^ X_i), xMac with rijndaelEncrypt) is a serial
+// chain inside one message, so a single message can never fill a GPU; thousands of messages can.
+// Lane l of a warp walks message l's chain with the same lane-private T-tables as every other
+// kernel (each lane's lookups stay in its own bank, so 32 unrelated chains cost exactly what 32
+// blocks of one ECB row cost), and produces the message's CTR keystream in the same loop, so the
+// payload is read once and written once.  Messages are described by uaes_msg records
+// (include/uaes_b200.h); offsets and lengths are arbitrary (16-byte aligned rows take 128-bit
+// accesses, anything else goes word- or byte-wise).
+#pragma once
+#include "uaes_core.cuh"
+
+namespace uaes {
+
+struct BatchMsg {                 // = uaes_msg of include/uaes_b200.h
+    uint64_t in_off, out_off, aad_off;
+    uint32_t len, aad_len;
+    uint8_t nonce[16];
+    int32_t result;
+    uint32_t reserved;
+};
+
+struct BatchArgs {
+    uaes_keysched ks;
+    BatchMsg *msgs;
+    uint64_t n;
+    const uint8_t *aad;
+    const uint8_t *in;
+    uint8_t *out;
+    int decrypt;
+};
+
+struct Blk { uint32_t w[4]; };
+
+constexpr int kBatchThreads = 512;        // 128 registers per lane: two cipher states + descriptors, no spills
+
+// up to 16 bytes from p (n <= 16), zero padded; p has no alignment
+__device__ __forceinline__ Blk load_bytes(const uint8_t *p, uint32_t n)
+{
+    Blk b = {{0, 0, 0, 0}};
+    if (n >= 16 && ((size_t)p & 15) == 0) {
+        const uint4 v = *(const uint4 *)p;
+        b.w[0] = v.x; b.w[1] = v.y; b.w[2] = v.z; b.w[3] = v.w;
+    } else if (n >= 16 && ((size_t)p & 3) == 0) {
+        const uint32_t *q = (const uint32_t *)p;
+        b.w[0] = q[0]; b.w[1] = q[1]; b.w[2] = q[2]; b.w[3] = q[3];
+    } else {
+        for (uint32_t i = 0; i < n && i < 16; ++i) b.w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+    }
+    return b;
+}
+
+__device__ __forceinline__ void store_bytes(uint8_t *p, const Blk &b, uint32_t n)
+{
+    if (n >= 16 && ((size_t)p & 15) == 0) {
+        *(uint4 *)p = make_uint4(b.w[0], b.w[1], b.w[2], b.w[3]);
+    } else if (n >= 16 && ((size_t)p & 3) == 0) {
+        uint32_t *q = (uint32_t *)p;
+        q[0] = b.w[0]; q[1] = b.w[1]; q[2] = b.w[2]; q[3] = b.w[3];
+    } else {
+        for (uint32_t i = 0; i < n && i < 16; ++i) p[i] = (uint8_t)(b.w[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// M <- E(M ^ X)
+template <int NR>
+__device__ __forceinline__ void mac_step(uint32_t lb, const uint32_t *rk, Blk &m, const Blk &x)
+{
+    m.w[0] ^= x.w[0]; m.w[1] ^= x.w[1]; m.w[2] ^= x.w[2]; m.w[3] ^= x.w[3];
+    enc_block<NR>(lb, m.w[0], m.w[1], m.w[2], m.w[3], rk);
+}
+
+// ---------------------------------------------------------------- CCM (micro_aes.c:1219-1315)
+// CCM_NONCE_LEN = 11, CCM_TAG_LEN = 16 (micro_aes.h:104-105): iv = 03 || nonce || 00000000
+template <int NR>
+__global__ void __launch_bounds__(kBatchThreads, 1) ccm_batch_kernel(const __grid_constant__ BatchArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.ks.w;
+    const uint64_t stride = (uint64_t)gridDim.x * kBatchThreads;
+
+    for (uint64_t mi = (uint64_t)blockIdx.x * kBatchThreads + threadIdx.x; mi < a.n; mi += stride) {
+        const BatchMsg d = a.msgs[mi];
+        const uint8_t *src = a.in + d.in_off;
+        uint8_t *dst = a.out + d.out_off;
+        const uint8_t *aad = a.aad + d.aad_off;
+
+        Blk iv;                                       // micro_aes.c:1273-1275
+        iv.w[0] = 3u | (uint32_t)d.nonce[0] << 8 | (uint32_t)d.nonce[1] << 16 | (uint32_t)d.nonce[2] << 24;
+        iv.w[1] = (uint32_t)d.nonce[3] | (uint32_t)d.nonce[4] << 8 | (uint32_t)d.nonce[5] << 16 | (uint32_t)d.nonce[6] << 24;
+        iv.w[2] = (uint32_t)d.nonce[7] | (uint32_t)d.nonce[8] << 8 | (uint32_t)d.nonce[9] << 16 | (uint32_t)d.nonce[10] << 24;
+        iv.w[3] = 0;
+
+        // ---- CCMtag, header part (micro_aes.c:1228-1251)
+        Blk m = iv;
+        m.w[0] |= (16 - 2) << 2;                      // :1229
+        m.w[3] ^= bswap32(d.len);                     // xorBEint(M, ptextLen, LAST), :1230
+        Blk A = {{0, 0, 0, 0}};
+        uint32_t head = 0;
+        if (d.aad_len) {
+            m.w[0] |= 0x40;
+            enc_block<NR>(lb, m.w[0], m.w[1], m.w[2], m.w[3], rk);          // :1235
+            uint32_t p;
+            if (d.aad_len > 0xFEFFu) {                // :1236-1240: FF FE || BE32(aDataLen)
+                A.w[0] = 0xFEFFu | (d.aad_len >> 24) << 16 | ((d.aad_len >> 16) & 255u) << 24;
+                A.w[1] = ((d.aad_len >> 8) & 255u) | (d.aad_len & 255u) << 8;
+                p = 6;
+            } else {
+                A.w[0] = (d.aad_len >> 8) | (d.aad_len & 255u) << 8;
+                p = 2;
+            }
+            head = 16 - p < d.aad_len ? 16 - p : d.aad_len;
+            for (uint32_t i = 0; i < head; ++i) A.w[(p + i) >> 2] |= (uint32_t)aad[i] << (8 * ((p + i) & 3));
+        }
+        mac_step<NR>(lb, rk, m, A);                   // :1247 (a zero block when there is no AAD)
+        for (uint32_t o = head; o < d.aad_len; o += 16)
+            mac_step<NR>(lb, rk, m, load_bytes(aad + o, d.aad_len - o));
+
+        // ---- payload: CBC-MAC over the plaintext (:1252) and CTR from iv + 1 (:939-941) in one walk
+        uint32_t ctr = 1;
+        for (uint32_t o = 0; o < d.len; o += 16, ++ctr) {
+            const uint32_t nb = d.len - o < 16 ? d.len - o : 16;
+            Blk x = load_bytes(src + o, nb);
+            Blk ks = iv;
+            ks.w[3] = bswap32(ctr);
+            enc_block<NR>(lb, ks.w[0], ks.w[1], ks.w[2], ks.w[3], rk);
+            Blk y;
+            y.w[0] = x.w[0] ^ ks.w[0]; y.w[1] = x.w[1] ^ ks.w[1]; y.w[2] = x.w[2] ^ ks.w[2]; y.w[3] = x.w[3] ^ ks.w[3];
+            if (a.decrypt) {
+                if (nb < 16) {                        // the MAC sees the plaintext zero padded
+                    const uint32_t keep = nb & 3 ? (1u << (8 * (nb & 3))) - 1 : 0;
+                    for (uint32_t i = 0; i < 4; ++i)
+                        if (i > (nb >> 2)) y.w[i] = 0; else if (i == (nb >> 2)) y.w[i] &= keep;
+                }
+                mac_step<NR>(lb, rk, m, y);
+            } else {
+                mac_step<NR>(lb, rk, m, x);
+            }
+            store_bytes(dst + o, y, nb);
+        }
+
+        // ---- tag = E(iv) ^ CBC-MAC (:1254-1255)
+        Blk s0 = iv;
+        enc_block<NR>(lb, s0.w[0], s0.w[1], s0.w[2], s0.w[3], rk);
+        Blk tag;
+        for (int i = 0; i < 4; ++i) tag.w[i] = m.w[i] ^ s0.w[i];
+        if (a.decrypt) {                              // :1308-1313; the plaintext stays (SABOTAGE is off)
+            const Blk got = load_bytes(src + d.len, 16);
+            const uint32_t diff = (got.w[0] ^ tag.w[0]) | (got.w[1] ^ tag.w[1]) | (got.w[2] ^ tag.w[2]) | (got.w[3] ^ tag.w[3]);
+            a.msgs[mi].result = diff ? 0x1A : 0;
+        } else {
+            store_bytes(dst + d.len, tag, 16);
+            a.msgs[mi].result = 0;
+        }
+    }
+}
+
+template <int NR>
+static cudaError_t launch_ccm_batch_nr(const BatchArgs &a, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(ccm_batch_kernel<NR>);
+    if (e != cudaSuccess) return e;
+    const uint64_t need = (a.n + kBatchThreads - 1) / kBatchThreads, sms = (uint64_t)sm_count();
+    ccm_batch_kernel<NR><<<(unsigned)(need < sms ? need : sms), kBatchThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace uaes
+
+extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void *msgs_dev, u64 n,
+                                     const void *aad, const void *in, void *out, void *stream)
+{
+    if (n == 0) return 0;
+    uaes::BatchArgs a;
+    a.ks = *ks;
+    a.msgs = (uaes::BatchMsg *)msgs_dev; a.n = n;
+    a.aad = (const uint8_t *)aad; a.in = (const uint8_t *)in; a.out = (uint8_t *)out;
+    a.decrypt = decrypt;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ks->rounds) {
+    case 10: return (int)uaes::launch_ccm_batch_nr<10>(a, st);
+    case 12: return (int)uaes::launch_ccm_batch_nr<12>(a, st);
+    case 14: return (int)uaes::launch_ccm_batch_nr<14>(a, st);
+    }
+    return (int)cudaErrorInvalidValue;
+}

@@ -861,6 +861,110 @@ int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
     return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
 }
 
+/* ------------------------------------------------------------------ CCM, batched */
+
+/* One launch for n messages.  Host-side work is bookkeeping only: where the descriptors and the
+ * three byte ranges live, staging whatever is host memory through the grow-only device buffers. */
+static int ccm_batch(int keybits, const u8 *key, uaes_msg *msgs, size_t n,
+                     const void *aad, const void *in, void *out, int decrypt)
+{
+    devctx *c;
+    uaes_keysched ks;
+    int rc = 0, msgs_dev;
+    size_t i, in_ext = 0, out_ext = 0, aad_ext = 0, off;
+    const void *din, *daad;
+    void *dout, *dmsgs;
+    cudaStream_t st;
+    struct cudaPointerAttributes at;
+
+    if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (n == 0) return 0;
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    msgs_dev = cudaPointerGetAttributes(&at, msgs) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (msgs_dev) {
+        if (!is_direct(out) || !is_direct(in) || (aad && !is_direct(aad))) {
+            rc = fail(UAES_E_BAD_ARGUMENT, "device descriptors need device (16-byte aligned) aad/in/out", 0);
+            goto done;
+        }
+        st = (cudaStream_t)tls_stream;
+        LAUNCH(uaes_launch_ccm_batch(&ks, decrypt, msgs, n, aad, in, out, st));
+        if (!tls_async) CU(cudaStreamSynchronize(st));
+        goto done;                                   /* per-message results stay on the device */
+    }
+    for (i = 0; i < n; ++i) {
+        const size_t tag_in = decrypt ? 16 : 0, tag_out = decrypt ? 0 : 16;
+        if (msgs[i].in_off + msgs[i].len + tag_in > in_ext) in_ext = msgs[i].in_off + msgs[i].len + tag_in;
+        if (msgs[i].out_off + msgs[i].len + tag_out > out_ext) out_ext = msgs[i].out_off + msgs[i].len + tag_out;
+        if (msgs[i].aad_len && msgs[i].aad_off + msgs[i].aad_len > aad_ext) aad_ext = msgs[i].aad_off + msgs[i].aad_len;
+    }
+    st = c->st[0];
+    CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+    /* work area: descriptors, then (if host) the associated data; big: input and output ranges */
+    off = (n * sizeof(uaes_msg) + 255) & ~(size_t)255;
+    if ((rc = grow(&c->work, &c->work_bytes, off + aad_ext + 64, "cudaMalloc(batch descriptors)")) != 0) goto done;
+    dmsgs = c->work;
+    CU(cudaMemcpyAsync(dmsgs, msgs, n * sizeof(uaes_msg), cudaMemcpyDefault, st));
+    daad = aad;
+    if (aad_ext && !is_direct(aad)) {
+        CU(cudaMemcpyAsync((u8 *)c->work + off, aad, aad_ext, cudaMemcpyDefault, st));
+        daad = (u8 *)c->work + off;
+    }
+    din = in; dout = out;
+    if (!is_direct(in) || !is_direct(out)) {
+        const size_t ioff = (in_ext + 255) & ~(size_t)255;
+        if ((rc = grow(&c->big, &c->big_bytes, ioff + out_ext + 64, "cudaMalloc(batch staging)")) != 0) goto done;
+        if (in_ext) CU(cudaMemcpyAsync(c->big, in, in_ext, cudaMemcpyDefault, st));
+        din = c->big; dout = (u8 *)c->big + ioff;
+        /* bytes of the output range that no message covers must survive the copy back */
+        if (out_ext) CU(cudaMemcpyAsync(dout, out, out_ext, cudaMemcpyDefault, st));
+    }
+    LAUNCH(uaes_launch_ccm_batch(&ks, decrypt, dmsgs, n, daad, din, dout, st));
+    if (dout != out && out_ext) CU(cudaMemcpyAsync(out, dout, out_ext, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(msgs, dmsgs, n * sizeof(uaes_msg), cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    for (i = 0; i < n; ++i) if (msgs[i].result) rc = UAES_AUTH_ERROR;
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_ccm_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out)
+{
+    return ccm_batch(keybits, key, msgs, n, aad, in, out, 0);
+}
+
+int uaes_ccm_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out)
+{
+    return ccm_batch(keybits, key, msgs, n, aad, in, out, 1);
+}
+
+static int ccm_single(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
+                      const void *in, size_t len, void *out, int decrypt)
+{
+    uaes_msg m;
+    if (len > 0xFFFFFFFFu || aadlen > 0xFFFFFFFFu) return fail(UAES_E_BAD_ARGUMENT, "CCM with a 4-byte length field", 0);
+    memset(&m, 0, sizeof m);
+    m.len = (unsigned int)len; m.aad_len = (unsigned int)aadlen;
+    memcpy(m.nonce, nonce, 11);
+    return ccm_batch(keybits, key, &m, 1, aad, in, out, decrypt);
+}
+
+int uaes_ccm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return ccm_single(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+}
+
+int uaes_ccm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return ccm_single(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords)

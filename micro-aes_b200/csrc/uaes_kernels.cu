@@ -503,6 +503,7 @@ using namespace uaes;
 #include "uaes_gcm.cuh"
 #include "uaes_chain.cuh"
 #include "uaes_ocb.cuh"
+#include "uaes_batch.cuh"
 
 extern "C" {
 

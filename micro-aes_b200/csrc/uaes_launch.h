@@ -102,6 +102,11 @@ int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int enc
                     const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
                     const void *in, void *out, u64 len, void *tag_out, void *work, void *stream);
 
+/* CCM over a batch of independent messages, one per lane (uaes_batch.cuh); msgs_dev = device array
+ * of uaes_msg records, result fields are written by the kernel */
+int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void *msgs_dev, u64 n,
+                          const void *aad, const void *in, void *out, void *stream);
+
 /* synthetic data + checksum helpers */
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
 int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);

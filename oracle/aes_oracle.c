@@ -832,6 +832,98 @@ int oracle_ocb_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
 }
 
 /* ------------------------------------------------------------------------ */
+/* CCM (micro_aes.c:1219-1315)                              */
+/* ------------------------------------------------------------------------ */
+
+/* CBC-MAC absorb of `len` bytes, the last partial block zero-padded: the
+ * rijndaelEncrypt instance of xMac (micro_aes.c:551-570) */
+static void cbcmac_absorb(const aes_ctx *c, const uint8_t *x, size_t len, uint8_t m[16])
+{
+    size_t i;
+    for (; len >= 16; len -= 16, x += 16) {
+        xor16(m, x);
+        encrypt_block(c, m, m);
+    }
+    if (len) {
+        for (i = 0; i < len; ++i) m[i] ^= x[i];
+        encrypt_block(c, m, m);
+    }
+}
+
+/* CCMtag (micro_aes.c:1222-1256) with CCM_NONCE_LEN = 11, CCM_TAG_LEN = 16
+ * (micro_aes.h:104-105): iv = 03 || nonce || 00000000 */
+static void ccm_tag(const aes_ctx *c, const uint8_t iv[16], const uint8_t *aad, size_t aadlen,
+                    const uint8_t *pt, size_t len, uint8_t tag[16])
+{
+    uint8_t m[16], a[16] = {0}, s0[16];
+    size_t head = 0, i;
+    memcpy(m, iv, 16);
+    m[0] |= (16 - 2) << 2;                       /* :1229 */
+    for (i = 0; i < 8 && i < sizeof len; ++i)    /* xorBEint(M, ptextLen, LAST), :1230 */
+        m[15 - i] ^= (uint8_t)(len >> (8 * i));
+    if (aadlen) {
+        size_t p;
+        m[0] |= 0x40;
+        encrypt_block(c, m, m);                  /* :1235 */
+        if (aadlen > 0xFEFF) {                   /* :1236-1240 */
+            a[0] = 0xFF; a[1] = 0xFE;
+            a[2] = (uint8_t)(aadlen >> 24); a[3] = (uint8_t)(aadlen >> 16);
+            a[4] = (uint8_t)(aadlen >> 8);  a[5] = (uint8_t)aadlen;
+            p = 6;
+        } else {
+            a[0] = (uint8_t)(aadlen >> 8); a[1] = (uint8_t)aadlen;
+            p = 2;
+        }
+        head = 16 - p;
+        if (head > aadlen) head = aadlen;
+        memcpy(a + p, aad, head);                /* :1243 */
+    }
+    cbcmac_absorb(c, a, 16, m);                  /* :1247 (an all-zero block when there is no AAD) */
+    if (aadlen > head) cbcmac_absorb(c, aad + head, aadlen - head, m);
+    cbcmac_absorb(c, pt, len, m);                /* :1252 */
+    encrypt_block(c, iv, s0);                    /* :1254 */
+    for (i = 0; i < 16; ++i) tag[i] = m[i] ^ s0[i];
+}
+
+static void ccm_iv(const uint8_t nonce[11], uint8_t iv[16])
+{
+    memset(iv, 0, 16);
+    iv[0] = 14 - 11;                             /* :1273 */
+    memcpy(iv + 1, nonce, 11);
+}
+
+/* micro_aes.c:1268-1282; out holds len + 16 */
+void oracle_ccm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t iv[16], ctr[16], tag[16];
+    key_setup(&c, keybits, key);
+    ccm_iv(nonce, iv);
+    ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, tag);
+    memcpy(ctr, iv, 16);
+    ctr_add(ctr, 1);                             /* CCM_GCM pre-increment, :939-941 */
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+    memcpy((uint8_t *)out + len, tag, 16);
+}
+
+/* micro_aes.c:1295-1314: the plaintext is produced BEFORE the tag is checked and stays
+ * in `out` on failure (SABOTAGE is off by default, micro_aes.c:31,376-384) */
+int oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t iv[16], ctr[16], tag[16];
+    key_setup(&c, keybits, key);
+    ccm_iv(nonce, iv);
+    memcpy(ctr, iv, 16);
+    ctr_add(ctr, 1);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+    ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, tag);
+    return memcmp(tag, (const uint8_t *)in + len, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
 /* synthetic data                                                           */
 /* ------------------------------------------------------------------------ */
 

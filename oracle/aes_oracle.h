@@ -115,6 +115,13 @@ void oracle_ocb_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12]
 int  oracle_ocb_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
                         const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* CCM with the reference's default parameters: 11-byte nonce, 16-byte tag
+ * (micro_aes.c:1268-1314, micro_aes.h:104-105); out holds len + 16 on encrypt */
+void oracle_ccm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+int  oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
 /* splitmix64 synthetic-data generator shared by tests and bench: 64-bit word w of
  * the buffer (byte offset 8w, little-endian) = splitmix64(seed + first_word + w) */
 void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords);

@@ -74,6 +74,8 @@ def main_c_vectors():
         "xts128": xts128, "xts256": xts256, "gcm128": gcm128, "gcm256": gcm256,
         # OCB, main.c:69-71 (same inputs as GCM) and the RFC 7253 case main.c:262-274
         "ocb128": s["ocbcipher"][0],
+        # CCM, main.c:55-57, 198-204 (nonce = first 11 bytes of iVec, same AAD)
+        "ccm128": s["ccmcipher"][0],
         "ocb_rfc7253": {"key": "000102030405060708090a0b0c0d0e0f", "iv": "bbaa99887766554433221107",
                         "aad": "000102030405060708090a0b0c0d0e0f1011121314151617",
                         "pt": "000102030405060708090a0b0c0d0e0f1011121314151617",
@@ -163,6 +165,44 @@ def parse_ocb(path, keybits):
             k, _, v = line.partition(" =")
             cur[k.strip()] = v.strip()
     return cases
+
+
+def parse_ccm(path, keybits):
+    """testvectors/VNT{128,192,256}.rsp (CAVS CCM variable-nonce test): kept when the nonce has the
+    build's CCM_NONCE_LEN = 11 bytes and the tag CCM_TAG_LEN = 16 (aes_testvectors_CCM.h:97)"""
+    cases, key, cur = [], None, {}
+    for line in open(path):
+        line = line.strip()
+        if line.startswith("Key = "):
+            key = line.split(" = ")[1].lower()
+        for name in ("Nonce", "Adata", "Payload", "CT"):
+            if line.startswith(name + " = "):
+                cur[name] = line.split(" = ")[1].lower()
+        if "Payload" in cur and "CT" in cur:
+            if len(key) == keybits // 4 and len(cur["Nonce"]) == 22 and len(cur["CT"]) == len(cur["Payload"]) + 32:
+                cases.append({"key": key, "nonce": cur["Nonce"], "aad": cur["Adata"], "pt": cur["Payload"], "ct": cur["CT"]})
+            cur = {}
+    return cases
+
+
+def row4_samples():
+    """SURVEY 8f row 4 (CCM now): outputs of the unmodified reference on inputs no in-tree vector
+    covers -- empty/ragged payloads, AAD around the 14-byte first block and the 0xFEFF length-encoding
+    switch (micro_aes.c:1236-1240), all key sizes"""
+    libs = {b: ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libref{b}.so")) for b in (128, 192, 256)}
+    sha = lambda b: hashlib.sha256(b).hexdigest()
+    out = {"source": "oracle/_ref/libref*.so = unmodified /root/reference/micro_aes.c; inputs = rnd()", "ccm": []}
+    for bits, lib in libs.items():
+        for n, a in ((0, 0), (0, 9), (1, 0), (15, 13), (16, 14), (17, 15), (57, 31), (1000, 20), (4096 + 3, 129),
+                     (100, 65279), (33, 65280), (64, 70000 + 5), (1 << 16, 7)):
+            key, nonce = rnd(f"cck{bits}{n}", bits // 8), rnd(f"ccn{bits}{n}", 11)
+            aad, pt = rnd(f"cca{bits}{n}{a}", a), rnd(f"ccp{bits}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.AES_CCM_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            out["ccm"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                               "aad_tag": f"cca{bits}{n}{a}", "pt_tag": f"ccp{bits}{n}",
+                               "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    return out
 
 
 def rnd(tag, n):
@@ -322,6 +362,12 @@ def main():
                       "cases": c})
     print(f"ocb128: {len(c)} cases")
     w("oracle_ref_samples.json", ref_samples())
+    for bits in (128, 192, 256):
+        c = parse_ccm(os.path.join(tv, f"VNT{bits}.rsp"), bits)
+        w(f"ccm{bits}.json", {"source": f"testvectors/VNT{bits}.rsp, filter of aes_testvectors_CCM.h:97 (11-byte nonce, 16-byte tag)",
+                              "cases": c})
+        print(f"ccm{bits}: {len(c)} cases")
+    w("oracle_ref_samples_row4.json", row4_samples())
     print("ok")
 
 

@@ -24,3 +24,4 @@ def test_reference_main_c_passes_against_our_library(bits, modes):
     if bits == 128:      # the header enables OCB and GCM_SIV too: main.c:204-224 and the RFC extras :262-299
         assert out.count("OCB encryption: PASSED!") == 2 and out.count("OCB decryption: PASSED!") == 2, out
         assert out.count("GCMSIV encrypt: PASSED!") == 3 and out.count("GCMSIV decrypt: PASSED!") == 3, out
+        assert "CCM encryption: PASSED!" in out and "CCM decryption: PASSED!" in out, out     # main.c:198-204

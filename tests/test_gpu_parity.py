@@ -506,3 +506,87 @@ def test_ocb(uaes, orc, torch):
     assert host(buf, 0, n + 16) == want
     assert uaes.ocb(128, key, nonce, aad, buf, n, buf, False) == 0
     assert host(buf, 0, n) == data
+
+
+# ---------------------------------------------------------------- CCM, batched
+
+def test_ccm_reference_vectors(uaes, orc):
+    m = golden("main_c.json")
+    a = uaes.MicroAES(128)
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"])[:11], H(m["aad"]), H(m["plaintext"])
+    assert a.AES_CCM_encrypt(key, nonce, aad, pt) == H(m["ccm128"])                  # main.c:198-204
+    assert a.AES_CCM_decrypt(key, nonce, aad, H(m["ccm128"])) == (0, pt)
+    for bits in (128, 192, 256):
+        a = uaes.MicroAES(bits)
+        for c in golden(f"ccm{bits}.json")["cases"]:                                 # testvectors/VNT*.rsp
+            assert a.AES_CCM_encrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+            assert a.AES_CCM_decrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"])), c
+        for c in [x for x in golden("oracle_ref_samples_row4.json")["ccm"] if x["bits"] == bits]:
+            out = a.AES_CCM_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+            assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+
+
+def _ccm_batch_case(uaes, seed, n, max_len, max_aad, align):
+    """n messages with seeded lengths packed at `align`-byte aligned offsets (align = 1: none)"""
+    import random
+    r = random.Random(seed)
+    msgs = (uaes.Msg * n)()
+    in_pos = out_pos = aad_pos = 0
+    up = lambda v: (v + align - 1) // align * align
+    for i in range(n):
+        ln = r.choice([0, 1, 15, 16, 17, 31, 32, 33, max_len]) if r.random() < 0.3 else r.randrange(max_len + 1)
+        al = r.choice([0, 0, 1, 13, 14, 15, 16, 30, max_aad]) if r.random() < 0.5 else r.randrange(max_aad + 1)
+        in_pos, out_pos, aad_pos = up(in_pos + r.randrange(3)), up(out_pos + r.randrange(5)), up(aad_pos + r.randrange(2))
+        msgs[i].in_off, msgs[i].out_off, msgs[i].aad_off = in_pos, out_pos, aad_pos
+        msgs[i].len, msgs[i].aad_len = ln, al
+        nonce = rnd(f"ccmb-n{seed}-{i}", 11)
+        for j in range(11):
+            msgs[i].nonce[j] = nonce[j]
+        in_pos += ln + 16; out_pos += ln + 16; aad_pos += al        # room for the tag on both sides
+    return msgs, in_pos, out_pos, aad_pos
+
+
+@pytest.mark.parametrize("bits,seed,n,max_len,max_aad,align", [(128, 1, 700, 300, 40, 1), (256, 2, 3000, 100, 20, 16),
+                                                               (192, 3, 64, 5000, 70000, 4), (128, 4, 1, 1000, 10, 1)])
+def test_ccm_batch_matches_oracle(uaes, orc, torch, bits, seed, n, max_len, max_aad, align):
+    key = rnd(f"ccmb-k{bits}", bits // 8)
+    msgs, in_sz, out_sz, aad_sz = _ccm_batch_case(uaes, seed, n, max_len, max_aad, align)
+    pt, aad = bytearray(rnd(f"ccmb-p{seed}", in_sz)), rnd(f"ccmb-a{seed}", max(aad_sz, 1))
+    want = bytearray(b"\xee" * out_sz)
+    for m in msgs:
+        want[m.out_off:m.out_off + m.len + 16] = orc.ccm_encrypt(key, bytes(m.nonce[:11]), aad[m.aad_off:m.aad_off + m.aad_len],
+                                                                 bytes(pt[m.in_off:m.in_off + m.len]))
+    # host buffers
+    out = bytearray(b"\xee" * out_sz)
+    assert uaes.ccm_batch(bits, key, msgs, n, aad, pt, out) == 0
+    assert out == want                                   # bytes between messages untouched
+    assert all(m.result == 0 for m in msgs)
+    # device buffers (descriptors stay on the host), then everything on the device
+    d_in, d_out, d_aad = dev(torch, bytes(pt)), dev(torch, b"", pad=out_sz), dev(torch, aad)
+    assert uaes.ccm_batch(bits, key, msgs, n, d_aad, d_in, d_out) == 0
+    got = bytearray(host(d_out, 0, out_sz))
+    for m in msgs:
+        assert got[m.out_off:m.out_off + m.len + 16] == want[m.out_off:m.out_off + m.len + 16]
+    d_msgs = dev(torch, bytes(msgs))
+    d_out2 = dev(torch, b"", pad=out_sz)
+    assert uaes.ccm_batch(bits, key, d_msgs, n, d_aad, d_in, d_out2) == 0
+    torch.cuda.synchronize()
+    assert host(d_out2, 0, out_sz) == host(d_out, 0, out_sz)
+
+    # decrypt: swap the roles of the offsets, forge every 7th tag
+    dec = (uaes.Msg * n)()
+    for i, m in enumerate(msgs):
+        dec[i].in_off, dec[i].out_off, dec[i].aad_off = m.out_off, m.in_off, m.aad_off
+        dec[i].len, dec[i].aad_len = m.len, m.aad_len
+        for j in range(11):
+            dec[i].nonce[j] = m.nonce[j]
+    ct = bytearray(want)
+    forged = set(range(0, n, 7)) if n > 1 else set()
+    for i in forged:
+        ct[msgs[i].out_off + msgs[i].len + 5] ^= 0x40
+    back = bytearray(b"\xdd" * in_sz)
+    rc = uaes.ccm_batch(bits, key, dec, n, aad, ct, back, decrypt=True)
+    assert rc == (0x1A if forged else 0)
+    for i, m in enumerate(msgs):
+        assert dec[i].result == (0x1A if i in forged else 0), i
+        assert back[m.in_off:m.in_off + m.len] == pt[m.in_off:m.in_off + m.len], i    # produced either way (micro_aes.c:1304-1312)

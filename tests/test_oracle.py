@@ -224,6 +224,29 @@ def test_ocb_vectors_and_recorded_reference(orc):
         assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
 
 
+# ---------------------------------------------------------------- CCM
+
+def test_ccm_vectors_and_recorded_reference(orc):
+    m = golden("main_c.json")
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"])[:11], H(m["aad"]), H(m["plaintext"])
+    out = orc.ccm_encrypt(key, nonce, aad, pt)                      # main.c:198-204
+    assert out == H(m["ccm128"])
+    assert orc.ccm_decrypt(key, nonce, aad, out) == (0, pt)
+    for bits in (128, 192, 256):
+        cases = golden(f"ccm{bits}.json")["cases"]
+        assert len(cases) == 10
+        for c in cases:
+            assert orc.ccm_encrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+            assert orc.ccm_decrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"]))
+    for c in golden("oracle_ref_samples_row4.json")["ccm"]:
+        out = orc.ccm_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+    # a wrong tag is reported, the plaintext is still produced (micro_aes.c:1304-1312, SABOTAGE off)
+    bad = bytearray(out); bad[-1] ^= 1
+    rc, got = orc.ccm_decrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), bytes(bad))
+    assert rc == 0x1A and got == rnd(c["pt_tag"], c["n"])
+
+
 # ---------------------------------------------------------------- edge cases
 
 def test_edge_cases(orc):
@@ -269,6 +292,9 @@ def test_live_reference_differential(orc, bits):
         enc = ref.gcm_encrypt(key, iv, aad, data)
         assert orc.gcm_encrypt(key, iv, aad, data) == enc
         assert orc.gcm_decrypt(key, iv, aad, enc) == ref.gcm_decrypt(key, iv, aad, enc) == (0, data)
+        enc = ref.ccm_encrypt(key, iv[:11], aad, data)
+        assert orc.ccm_encrypt(key, iv[:11], aad, data) == enc
+        assert orc.ccm_decrypt(key, iv[:11], aad, enc) == ref.ccm_decrypt(key, iv[:11], aad, enc) == (0, data)
         if bits != 192 and n >= 16:
             keys, tw = rnd(f"lx{bits}{i}", 2 * ks), rnd(f"lt{bits}{i}", 16)
             e = ref.xts(keys, tw, data)

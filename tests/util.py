@@ -58,6 +58,8 @@ class Oracle:
         L.oracle_polyval.argtypes = [_u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_ocb_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_ocb_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_ccm_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_ccm_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         for f in (L.oracle_cbc_decrypt, L.oracle_cbc_encrypt, L.oracle_cfb_decrypt, L.oracle_cfb_encrypt):
             f.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
         L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
@@ -154,6 +156,18 @@ class Oracle:
         rc = self.lib.oracle_ocb_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
         return rc, o.raw[:n]
 
+    def ccm_encrypt(self, key, nonce, aad, pt):
+        o = self._buf(len(pt) + 16)
+        self.lib.oracle_ccm_encrypt(len(key) * 8, key, nonce, aad, len(aad), pt, len(pt), o)
+        return o.raw[:len(pt) + 16]
+
+    def ccm_decrypt(self, key, nonce, aad, ct_and_tag):
+        """(rc, plaintext): the plaintext is produced even when rc = 0x1A (micro_aes.c:1304-1312)"""
+        n = len(ct_and_tag) - 16
+        o = self._buf(n)
+        rc = self.lib.oracle_ccm_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
+        return rc, o.raw[:n]
+
     def polyval(self, H, aad, pt):
         o = self._buf(16)
         self.lib.oracle_polyval(H, aad, len(aad), pt, len(pt), o)
@@ -203,7 +217,7 @@ class Reference:
         self.bits = bits
         self.lib = ctypes.CDLL(self.path)
         for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt", "GCM_SIV_decrypt",
-                  "AES_CBC_encrypt", "AES_CBC_decrypt", "AES_OCB_decrypt"):
+                  "AES_CBC_encrypt", "AES_CBC_decrypt", "AES_OCB_decrypt", "AES_CCM_decrypt"):
             getattr(self.lib, f).restype = ctypes.c_char
 
     @staticmethod
@@ -247,6 +261,17 @@ class Reference:
         n = len(ct_and_tag) - 16
         o = ctypes.create_string_buffer(n + 16)
         rc = self.lib.AES_OCB_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
+        return ord(rc), o.raw[:n]
+
+    def ccm_encrypt(self, key, nonce, aad, pt):
+        o = ctypes.create_string_buffer(len(pt) + 16)
+        self.lib.AES_CCM_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
+        return o.raw[:len(pt) + 16]
+
+    def ccm_decrypt(self, key, nonce, aad, ct_and_tag):
+        n = len(ct_and_tag) - 16
+        o = ctypes.create_string_buffer(n + 16)
+        rc = self.lib.AES_CCM_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
         return ord(rc), o.raw[:n]
 
     def cbc(self, key, iv, data, encrypt=False):

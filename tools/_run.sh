@@ -1,6 +1,6 @@
 set -x
-mkdir -p gpurun_out; rm -f gpurun_out/bench_bs7.jsonl
-for c in "256 0" "256 170" "256 200" "256 230" "256 260" "256 300"; do set -- $c
-  echo "ctr128 threads=$1 share=$2" >> gpurun_out/bench_bs7.jsonl
-  UAES_CTR_THREADS=$1 UAES_CTR_BS_PERMILLE=$2 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --workload ctr128 >> gpurun_out/bench_bs7.jsonl 2>> gpurun_out/bench_err.log
-done
+mkdir -p gpurun_out; rm -f gpurun_out/bench_ccm.jsonl
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -x -q -k "ccm or dropin" > gpurun_out/pytest_ccm.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_ccm.log
+tail -30 gpurun_out/pytest_ccm.log
+python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --workload ccm128batch --gib-per-gpu 4 >> gpurun_out/bench_ccm.jsonl 2>> gpurun_out/bench_err.log
+tail -3 gpurun_out/bench_err.log
