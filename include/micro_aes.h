@@ -4,7 +4,7 @@
  *
  * This header declares, with the reference's names, argument order and return
  * codes, the entry points the reference exports when only ECB, CTR (CTR_NA),
- * XEX/XTS, GCM, GCM_SIV, OCB and CCM are enabled:
+ * XEX/XTS, GCM, GCM_SIV, OCB, CCM, EAX and SIV are enabled:
  *
  *     function            replaces (polfosol/micro-AES)
  *     ------------------  ---------------------------------------------
@@ -23,6 +23,10 @@
  *     AES_CCM_encrypt     micro_aes.h:315-321, micro_aes.c:1268-1282   (SURVEY 8f "next" row 4; one
  *     AES_CCM_decrypt     micro_aes.h:323-329, micro_aes.c:1295-1314    GPU lane per message: use the
  *                                                                        batch call of uaes_b200.h for speed)
+ *     AES_EAX_encrypt     micro_aes.h:357-367, micro_aes.c:1564-1598   (likewise)
+ *     AES_EAX_decrypt     micro_aes.h:369-379, micro_aes.c:1613-1648
+ *     AES_SIV_encrypt     micro_aes.h:273-279, micro_aes.c:1372-1382   (likewise)
+ *     AES_SIV_decrypt     micro_aes.h:281-287, micro_aes.c:1394-1410
  *
  * A program written against the reference keeps its `#include "micro_aes.h"`,
  * drops micro_aes.c from its build and links one of
@@ -63,9 +67,9 @@
 #define FPE             0
 #define CMAC            0
 #define CCM             1
-#define EAX             0
+#define EAX             1
 #define EAXP            0
-#define SIV             0
+#define SIV             1
 #define GCM_SIV         1
 #define OCB             1
 #define POLY1305        0
@@ -86,6 +90,8 @@ enum constant_parameters_of_modes
     SIVGCM_TAG_LEN  = 16,       /* micro_aes.h:113 */
     CCM_NONCE_LEN   = 11,       /* micro_aes.h:104 */
     CCM_TAG_LEN     = 16,       /* micro_aes.h:105 */
+    EAX_NONCE_LEN   = 16,       /* micro_aes.h:120 */
+    EAX_TAG_LEN     = 16,       /* micro_aes.h:121 */
     OCB_NONCE_LEN   = 12,       /* micro_aes.h:116 */
     OCB_TAG_LEN     = 16,       /* micro_aes.h:117 */
 #if AES___ != 256 && AES___ != 192
@@ -161,6 +167,24 @@ void AES_CCM_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *pntxt, const size_t ptextLen, void *crtxt);
 /* decrypts, then authenticates (micro_aes.c:1304-1312) */
 char AES_CCM_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* EAX (not EAX'): 16-byte nonce; crtxt holds ptextLen + EAX_TAG_LEN bytes */
+void AES_EAX_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt);
+/* authenticates, then decrypts: pntxt is untouched on M_AUTHENTICATION_ERROR */
+char AES_EAX_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt);
+
+/* SIV (RFC 5297): keys = two keys of AES_KEYLENGTH bytes; iv = the 16-byte synthetic IV */
+void AES_SIV_encrypt(const uint8_t *keys,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen,
+                     uint8_t iv[16], void *crtxt);
+char AES_SIV_decrypt(const uint8_t *keys, const uint8_t iv[16],
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 

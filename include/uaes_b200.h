@@ -161,8 +161,9 @@ int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
                      uaes_u64 total_len, uaes_u8 *tag);
 
 /* ---- many independent messages per call ------------------------ */
-/* The MAC of CCM is a serial CBC-MAC chain inside one message (micro_aes.c:1222-1256), so one
- * message cannot fill a GPU but a batch can: one message per GPU lane, all under one key.
+/* The MACs of CCM, EAX and SIV are serial chains inside one message (CBC-MAC micro_aes.c:1222-1256,
+ * OMAC :1531-1550, S2V :1325-1359), so one message cannot fill a GPU but a batch can: one message
+ * per GPU lane, all under one key.
  * Message i is described by msgs[i]; offsets are relative to the three base pointers and have no
  * alignment requirement (16-byte aligned offsets are fastest).  msgs, aad, in and out may each
  * be host or device memory (when msgs is device memory the other three must be, too).
@@ -173,7 +174,7 @@ int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
 typedef struct uaes_msg {
     uaes_u64 in_off, out_off, aad_off;
     unsigned int len, aad_len;         /* payload bytes (without the tag), associated-data bytes */
-    uaes_u8  nonce[16];                /* CCM: the first CCM_NONCE_LEN = 11 bytes */
+    uaes_u8  nonce[16];                /* CCM: the first 11 bytes; EAX: 16 bytes; SIV: unused */
     int      result;
     unsigned int reserved;
 } uaes_msg;
@@ -182,9 +183,32 @@ int uaes_ccm_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size
                            const void *aad, const void *in, void *out);
 int uaes_ccm_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
                            const void *aad, const void *in, void *out);
-/* one message with the reference's argument list (micro_aes.c:1268-1314; 11-byte nonce, 16-byte
- * tag): a batch of one, i.e. ONE GPU lane -- correct and table-driven, but no faster than a CPU
- * core; use the batch calls for throughput */
+/* EAX (not EAX'; 16-byte nonce, 16-byte tag, micro_aes.c:1564-1648): same layout as CCM; decrypt
+ * authenticates first and leaves out untouched on UAES_AUTH_ERROR (:1637-1645) */
+int uaes_eax_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+int uaes_eax_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+/* SIV (RFC 5297, one AAD unit, micro_aes.c:1372-1410): key = K1 || K2 (2 x keybits/8 bytes).
+ *   encrypt: out + out_off holds 16 + len bytes: synthetic IV || ciphertext
+ *   decrypt: in + in_off holds IV || ciphertext; the plaintext is written, then the IV is checked
+ * in and out ranges of a message must not overlap when encrypting (the output is 16 bytes longer
+ * and shifted). */
+int uaes_siv_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+int uaes_siv_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+/* one message with the reference's argument lists (micro_aes.c:1268-1314, 1564-1648, 1372-1410):
+ * a batch of one, i.e. ONE GPU lane -- correct and table-driven, but no faster than a CPU core;
+ * use the batch calls for throughput */
+int uaes_eax_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+int uaes_eax_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                     const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+int uaes_siv_encrypt(int keybits, const uaes_u8 *keys, const void *aad, size_t aadlen,
+                     const void *in, size_t len, uaes_u8 *iv, void *out);
+int uaes_siv_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *iv, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out);
 int uaes_ccm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                      const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 int uaes_ccm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,

@@ -61,6 +61,14 @@ UAES_ABI = {
     "uaes_ccm_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
     "uaes_ccm_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_ccm_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_eax_encrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_eax_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_siv_encrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_siv_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_eax_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_eax_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_siv_encrypt": (_int, [_int, _cp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "uaes_siv_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_fill_splitmix64": (_int, [_u64, _u64, _vp, _sz]),
     "uaes_xor_fold64": (_int, [_vp, _sz, ctypes.POINTER(_u64)]),
 }
@@ -79,6 +87,10 @@ MICRO_AES_ABI = {
     "AES_OCB_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_CCM_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_CCM_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_EAX_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_EAX_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "AES_SIV_encrypt": (None, [_cp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "AES_SIV_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "AES_CBC_decrypt": (ctypes.c_char, [_cp, _cp, _vp, _sz, _vp]),
     "AES_CFB_decrypt": (None, [_cp, _cp, _vp, _sz, _vp]),
     "GCM_SIV_encrypt": (None, [_cp, _cp, _vp, _sz, _vp, _sz, _vp]),
@@ -235,6 +247,33 @@ class MicroAES:
         self._after()
         return rc, out.raw[:n]
 
+    def AES_EAX_encrypt(self, key, nonce, aData, pntxt):
+        out = ctypes.create_string_buffer(len(pntxt) + 16)
+        self.lib.AES_EAX_encrypt(key, nonce, aData, len(aData), pntxt, len(pntxt), out)
+        self._after()
+        return out.raw[:len(pntxt) + 16]
+
+    def AES_EAX_decrypt(self, key, nonce, aData, crtxt_and_tag):
+        n = len(crtxt_and_tag) - 16
+        out = ctypes.create_string_buffer(b"\xcc" * max(n, 1), max(n, 1))
+        rc = ord(self.lib.AES_EAX_decrypt(key, nonce, aData, len(aData), crtxt_and_tag, n, out))
+        self._after()
+        return rc, out.raw[:n]
+
+    def AES_SIV_encrypt(self, keys, aData, pntxt):
+        """returns IV || ciphertext (main.c:214 passes output and output + 16)"""
+        iv, out = ctypes.create_string_buffer(16), ctypes.create_string_buffer(max(len(pntxt), 1))
+        self.lib.AES_SIV_encrypt(keys, aData, len(aData), pntxt, len(pntxt), iv, out)
+        self._after()
+        return iv.raw[:16] + out.raw[:len(pntxt)]
+
+    def AES_SIV_decrypt(self, keys, aData, iv_and_crtxt):
+        n = len(iv_and_crtxt) - 16
+        out = ctypes.create_string_buffer(max(n, 1))
+        rc = ord(self.lib.AES_SIV_decrypt(keys, iv_and_crtxt[:16], aData, len(aData), iv_and_crtxt[16:], n, out))
+        self._after()
+        return rc, out.raw[:n]
+
     def AES_CBC_decrypt(self, key, iVec, crtxt):
         out = ctypes.create_string_buffer(b"\xcc" * max(len(crtxt), 1), max(len(crtxt), 1))
         rc = ord(self.lib.AES_CBC_decrypt(key, iVec, crtxt, len(crtxt), out))
@@ -351,10 +390,10 @@ class Msg(ctypes.Structure):
                 ("result", ctypes.c_int32), ("reserved", ctypes.c_uint32)]
 
 
-def ccm_batch(bits, key, msgs, n, aad, src, dst, decrypt=False):
-    """uaes_ccm_{en,de}crypt_batch; msgs = ctypes array of Msg or a device pointer.  Returns the
-    call's result code (0, or 0x1A when a message failed authentication); raises on UAES_E_*."""
-    f = core().uaes_ccm_decrypt_batch if decrypt else core().uaes_ccm_encrypt_batch
+def ccm_batch(bits, key, msgs, n, aad, src, dst, decrypt=False, mode="ccm"):
+    """uaes_{ccm,eax,siv}_{en,de}crypt_batch; msgs = ctypes array of Msg or a device pointer.  Returns
+    the call's result code (0, or 0x1A when a message failed authentication); raises on UAES_E_*."""
+    f = getattr(core(), f"uaes_{mode}_{'decrypt' if decrypt else 'encrypt'}_batch")
     rc = f(bits, key, _ptr(msgs), n, _ptr(aad), _ptr(src), _ptr(dst))
     if rc < 0:
         check(rc)

@@ -126,3 +126,34 @@ char AES_CCM_decrypt(const uint8_t *key, const uint8_t *nonce,
     return code(uaes_ccm_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
                 M_DECRYPTION_ERROR);
 }
+
+void AES_EAX_encrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen, void *crtxt)
+{
+    uaes_eax_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+}
+
+char AES_EAX_decrypt(const uint8_t *key, const uint8_t *nonce,
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_eax_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+                M_DECRYPTION_ERROR);
+}
+
+void AES_SIV_encrypt(const uint8_t *keys,
+                     const void *aData, const size_t aDataLen,
+                     const void *pntxt, const size_t ptextLen,
+                     uint8_t iv[16], void *crtxt)
+{
+    uaes_siv_encrypt(BITS, keys, aData, aDataLen, pntxt, ptextLen, iv, crtxt);
+}
+
+char AES_SIV_decrypt(const uint8_t *keys, const uint8_t iv[16],
+                     const void *aData, const size_t aDataLen,
+                     const void *crtxt, const size_t crtxtLen, void *pntxt)
+{
+    return code(uaes_siv_decrypt(BITS, keys, iv, aData, aDataLen, crtxt, crtxtLen, pntxt),
+                M_DECRYPTION_ERROR);
+}

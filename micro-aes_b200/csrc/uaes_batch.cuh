@@ -1,7 +1,9 @@
-// uaes_batch.cuh -- many independent messages per launch, ONE MESSAGE PER LANE.
+// uaes_batch.cuh -- many independent messages per launch, ONE MESSAGE PER LANE:
+// CCM, EAX and SIV.
 //
-// CCM's CBC-MAC (micro_aes.c:1222-1256: M <- E(M ^ X_i), xMac with rijndaelEncrypt) is a serial
-// chain inside one message, so a single message can never fill a GPU; thousands of messages can.
+// Their MACs -- CCM's CBC-MAC (micro_aes.c:1222-1256), the OMACs of EAX (:1531-1550) and the CMACs
+// inside SIV's S2V (:1325-1359) -- are serial chains M <- E(M ^ X_i) inside one message (xMac with
+// rijndaelEncrypt, :551-570), so a single message can never fill a GPU; thousands of messages can.
 // Lane l of a warp walks message l's chain with the same lane-private T-tables as every other
 // kernel (each lane's lookups stay in its own bank, so 32 unrelated chains cost exactly what 32
 // blocks of one ECB row cost), and produces the message's CTR keystream in the same loop, so the
@@ -22,7 +24,8 @@ struct BatchMsg {                 // = uaes_msg of include/uaes_b200.h
 };
 
 struct BatchArgs {
-    uaes_keysched ks;
+    uaes_keysched ks;             // CCM / EAX key; SIV: first key half (S2V)
+    uaes_keysched ks2;            // SIV: second key half (CTR)
     BatchMsg *msgs;
     uint64_t n;
     const uint8_t *aad;
@@ -159,6 +162,206 @@ __global__ void __launch_bounds__(kBatchThreads, 1) ccm_batch_kernel(const __gri
     }
 }
 
+// ---------------------------------------------------------------- CMAC pieces for EAX and SIV
+
+// big-endian 128-bit value times x with the 0x87 fold: doubleBblock, micro_aes.c:434-444
+__device__ __forceinline__ Blk dbl_be(const Blk &b)
+{
+    const uint32_t a0 = bswap32(b.w[0]), a1 = bswap32(b.w[1]), a2 = bswap32(b.w[2]), a3 = bswap32(b.w[3]);
+    Blk r;
+    r.w[0] = bswap32(a0 << 1 | a1 >> 31); r.w[1] = bswap32(a1 << 1 | a2 >> 31);
+    r.w[2] = bswap32(a2 << 1 | a3 >> 31); r.w[3] = bswap32((a3 << 1) ^ ((a0 >> 31) * 0x87u));
+    return r;
+}
+
+__device__ __forceinline__ void xor_blk(Blk &a, const Blk &b)
+{
+    a.w[0] ^= b.w[0]; a.w[1] ^= b.w[1]; a.w[2] ^= b.w[2]; a.w[3] ^= b.w[3];
+}
+
+// the block as a little-endian 128-bit integer shifted by whole bytes (0..16); byte j moves to
+// byte j + n (left) or j - n (right).  Rare (once per SIV message): plain loops.
+__device__ inline Blk shift_bytes(const Blk &a, int n, bool left)
+{
+    Blk r = {{0, 0, 0, 0}};
+    for (int j = 0; j < 16; ++j) {
+        const int t = left ? j + n : j - n;
+        if (t >= 0 && t < 16) r.w[t >> 2] |= ((a.w[j >> 2] >> (8 * (j & 3))) & 255u) << (8 * (t & 3));
+    }
+    return r;
+}
+
+// getSubkeys with quad = 1 (micro_aes.c:593-604): K1 = 2 E(0), K2 = 4 E(0)
+template <int NR>
+__device__ __forceinline__ void cmac_subkeys(uint32_t lb, const uint32_t *rk, Blk &k1, Blk &k2)
+{
+    Blk l = {{0, 0, 0, 0}};
+    enc_block<NR>(lb, l.w[0], l.w[1], l.w[2], l.w[3], rk);
+    k1 = dbl_be(l);
+    k2 = dbl_be(k1);
+}
+
+// cMac (micro_aes.c:576-590): CMAC of data[0..n) continued from state m.  `fix` is XORed into the
+// message's last 16 bytes on the fly (SIV's xorend; pass zero otherwise; needs n >= 16 if nonzero).
+template <int NR>
+__device__ __forceinline__ void cmac_continue(uint32_t lb, const uint32_t *rk, const Blk &k1, const Blk &k2,
+                                              const uint8_t *data, uint32_t n, Blk &m, const Blk &fix, bool has_fix)
+{
+    const uint32_t s = n ? (n - 1) % 16 + 1 : 0;               // bytes in the last block
+    const uint32_t body = n - s;                                // multiple of 16
+    for (uint32_t o = 0; o < body; o += 16) {
+        Blk x = load_bytes(data + o, 16);
+        if (has_fix && s < 16 && o + 16 == body) xor_blk(x, shift_bytes(fix, (int)s, true));
+        mac_step<NR>(lb, rk, m, x);
+    }
+    Blk last = s ? load_bytes(data + body, s) : Blk{{0, 0, 0, 0}};
+    if (has_fix) xor_blk(last, s < 16 ? shift_bytes(fix, 16 - (int)s, false) : fix);
+    if (s < 16) { last.w[s >> 2] ^= 0x80u << (8 * (s & 3)); xor_blk(last, k2); }
+    else xor_blk(last, k1);
+    mac_step<NR>(lb, rk, m, last);
+}
+
+// oMac without EAXP (micro_aes.c:1531-1550): CMAC([t]_128 || data)
+template <int NR>
+__device__ __forceinline__ Blk omac(uint32_t lb, const uint32_t *rk, const Blk &k1, const Blk &k2, uint32_t t,
+                                    const uint8_t *data, uint32_t n)
+{
+    Blk m = {{0, 0, 0, 0}};
+    if (n == 0) m = k1;
+    m.w[3] ^= t << 24;
+    enc_block<NR>(lb, m.w[0], m.w[1], m.w[2], m.w[3], rk);
+    if (n) cmac_continue<NR>(lb, rk, k1, k2, data, n, m, Blk{{0, 0, 0, 0}}, false);
+    return m;
+}
+
+// out = in ^ E(ctr0 + k), the counter a 56-bit big-endian integer in bytes 9..15 (incBlock with
+// index LAST, micro_aes.c:421-427), no pre-increment (CTR_DEFAULT / SIV_CTR, :931-942)
+template <int NR>
+__device__ __forceinline__ void ctr_walk(uint32_t lb, const uint32_t *rk, const Blk &c0, const uint8_t *src,
+                                         uint8_t *dst, uint32_t n)
+{
+    const uint64_t v0 = ((uint64_t)(bswap32(c0.w[2]) & 0x00ffffffu) << 32) | bswap32(c0.w[3]);
+    uint64_t k = 0;
+    for (uint32_t o = 0; o < n; o += 16, ++k) {
+        const uint32_t nb = n - o < 16 ? n - o : 16;
+        const Blk x = load_bytes(src + o, nb);
+        Blk ks;
+        ks.w[0] = c0.w[0]; ks.w[1] = c0.w[1];
+        ctr_words(c0.w[2] & 255u, (v0 + k) & kMask56, ks.w[2], ks.w[3]);
+        enc_block<NR>(lb, ks.w[0], ks.w[1], ks.w[2], ks.w[3], rk, x.w[0], x.w[1], x.w[2], x.w[3]);
+        store_bytes(dst + o, ks, nb);
+    }
+}
+
+// ---------------------------------------------------------------- EAX (micro_aes.c:1518-1649)
+// EAX_NONCE_LEN = 16, EAX_TAG_LEN = 16 (micro_aes.h:119-121), not EAX'
+template <int NR>
+__global__ void __launch_bounds__(kBatchThreads, 1) eax_batch_kernel(const __grid_constant__ BatchArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.ks.w;
+    const uint64_t stride = (uint64_t)gridDim.x * kBatchThreads;
+    Blk k1, k2;
+    cmac_subkeys<NR>(lb, rk, k1, k2);
+
+    for (uint64_t mi = (uint64_t)blockIdx.x * kBatchThreads + threadIdx.x; mi < a.n; mi += stride) {
+        const BatchMsg d = a.msgs[mi];
+        const uint8_t *src = a.in + d.in_off;
+        uint8_t *dst = a.out + d.out_off;
+        const Blk N = omac<NR>(lb, rk, k1, k2, 0, d.nonce, 16);                   // :1578
+        Blk tag = omac<NR>(lb, rk, k1, k2, 1, a.aad + d.aad_off, d.aad_len);        // :1591
+        xor_blk(tag, N);
+        if (!a.decrypt) {
+            ctr_walk<NR>(lb, rk, N, src, dst, d.len);                             // :1584, counter starts AT N
+            xor_blk(tag, omac<NR>(lb, rk, k1, k2, 2, dst, d.len));                // :1593, over the ciphertext
+            store_bytes(dst + d.len, tag, 16);
+            a.msgs[mi].result = 0;
+        } else {                                                                  // :1625-1647: verify, then decrypt
+            xor_blk(tag, omac<NR>(lb, rk, k1, k2, 2, src, d.len));
+            const Blk got = load_bytes(src + d.len, 16);
+            const uint32_t diff = (got.w[0] ^ tag.w[0]) | (got.w[1] ^ tag.w[1]) | (got.w[2] ^ tag.w[2]) | (got.w[3] ^ tag.w[3]);
+            a.msgs[mi].result = diff ? 0x1A : 0;
+            if (!diff) ctr_walk<NR>(lb, rk, N, src, dst, d.len);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- SIV (micro_aes.c:1317-1411)
+// RFC 5297 with one AAD unit.  Layout of a message: IV (16 bytes) || ciphertext.
+
+// S2V, micro_aes.c:1325-1359
+template <int NR>
+__device__ __forceinline__ Blk s2v(uint32_t lb, const uint32_t *rk, const Blk &k1, const Blk &k2,
+                                   const uint8_t *aad, uint32_t aad_len, const uint8_t *pt, uint32_t n)
+{
+    Blk y = k1;                                                   // Y_0 = CMAC(0^128) = E(K1), :1332
+    enc_block<NR>(lb, y.w[0], y.w[1], y.w[2], y.w[3], rk);
+    if (aad_len) {                                                // :1338-1344
+        Blk t = {{0, 0, 0, 0}};
+        cmac_continue<NR>(lb, rk, k1, k2, aad, aad_len, t, Blk{{0, 0, 0, 0}}, false);
+        y = dbl_be(y);
+        xor_blk(y, t);
+    }
+    Blk v = {{0, 0, 0, 0}};
+    if (n >= 16) {                                                // CMAC(pt xorend Y), :1350-1358
+        cmac_continue<NR>(lb, rk, k1, k2, pt, n, v, y, true);
+    } else {                                                      // CMAC(dbl(Y) ^ pad(pt)), :1345-1349
+        y = dbl_be(y);
+        xor_blk(y, load_bytes(pt, n));
+        y.w[n >> 2] ^= 0x80u << (8 * (n & 3));
+        xor_blk(y, k1);
+        mac_step<NR>(lb, rk, v, y);
+    }
+    return v;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kBatchThreads, 1) siv_batch_kernel(const __grid_constant__ BatchArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk1 = a.ks.w, *rk2 = a.ks2.w;
+    const uint64_t stride = (uint64_t)gridDim.x * kBatchThreads;
+    Blk k1, k2;
+    cmac_subkeys<NR>(lb, rk1, k1, k2);
+
+    for (uint64_t mi = (uint64_t)blockIdx.x * kBatchThreads + threadIdx.x; mi < a.n; mi += stride) {
+        const BatchMsg d = a.msgs[mi];
+        const uint8_t *src = a.in + d.in_off;
+        uint8_t *dst = a.out + d.out_off;
+        const uint8_t *aad = a.aad + d.aad_off;
+        if (!a.decrypt) {                                         // :1372-1382
+            const Blk v = s2v<NR>(lb, rk1, k1, k2, aad, d.aad_len, src, d.len);
+            Blk q = v;
+            q.w[2] &= ~0x80u; q.w[3] &= ~0x80u;                   // c[8] &= 0x7F, c[12] &= 0x7F, :931-934
+            ctr_walk<NR>(lb, rk2, q, src, dst + 16, d.len);
+            store_bytes(dst, v, 16);                              // written last: in == out stays correct
+            a.msgs[mi].result = 0;
+        } else {                                                  // :1394-1410: decrypt, then compare
+            const Blk iv = load_bytes(src, 16);
+            Blk q = iv;
+            q.w[2] &= ~0x80u; q.w[3] &= ~0x80u;
+            ctr_walk<NR>(lb, rk2, q, src + 16, dst, d.len);
+            const Blk v = s2v<NR>(lb, rk1, k1, k2, aad, d.aad_len, dst, d.len);
+            const uint32_t diff = (iv.w[0] ^ v.w[0]) | (iv.w[1] ^ v.w[1]) | (iv.w[2] ^ v.w[2]) | (iv.w[3] ^ v.w[3]);
+            a.msgs[mi].result = diff ? 0x1A : 0;
+        }
+    }
+}
+
+template <int NR, int MODE>
+static cudaError_t launch_batch_nr(const BatchArgs &a, cudaStream_t st)
+{
+    auto kernel = MODE == 1 ? eax_batch_kernel<NR> : siv_batch_kernel<NR>;
+    cudaError_t e = opt_in_smem(kernel);
+    if (e != cudaSuccess) return e;
+    const uint64_t need = (a.n + kBatchThreads - 1) / kBatchThreads, sms = (uint64_t)sm_count();
+    kernel<<<(unsigned)(need < sms ? need : sms), kBatchThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 template <int NR>
 static cudaError_t launch_ccm_batch_nr(const BatchArgs &a, cudaStream_t st)
 {
@@ -177,7 +380,7 @@ extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void 
 {
     if (n == 0) return 0;
     uaes::BatchArgs a;
-    a.ks = *ks;
+    a.ks = *ks; a.ks2 = *ks;
     a.msgs = (uaes::BatchMsg *)msgs_dev; a.n = n;
     a.aad = (const uint8_t *)aad; a.in = (const uint8_t *)in; a.out = (uint8_t *)out;
     a.decrypt = decrypt;
@@ -186,6 +389,28 @@ extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void 
     case 10: return (int)uaes::launch_ccm_batch_nr<10>(a, st);
     case 12: return (int)uaes::launch_ccm_batch_nr<12>(a, st);
     case 14: return (int)uaes::launch_ccm_batch_nr<14>(a, st);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+// mode: 1 = EAX (ks), 2 = SIV (ks = S2V key, ks2 = CTR key)
+extern "C" int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt,
+                                     void *msgs_dev, u64 n, const void *aad, const void *in, void *out, void *stream)
+{
+    if (n == 0) return 0;
+    uaes::BatchArgs a;
+    a.ks = *ks; a.ks2 = ks2 ? *ks2 : *ks;
+    a.msgs = (uaes::BatchMsg *)msgs_dev; a.n = n;
+    a.aad = (const uint8_t *)aad; a.in = (const uint8_t *)in; a.out = (uint8_t *)out;
+    a.decrypt = decrypt;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ks->rounds * 4 + mode) {
+    case 41: return (int)uaes::launch_batch_nr<10, 1>(a, st);
+    case 49: return (int)uaes::launch_batch_nr<12, 1>(a, st);
+    case 57: return (int)uaes::launch_batch_nr<14, 1>(a, st);
+    case 42: return (int)uaes::launch_batch_nr<10, 2>(a, st);
+    case 50: return (int)uaes::launch_batch_nr<12, 2>(a, st);
+    case 58: return (int)uaes::launch_batch_nr<14, 2>(a, st);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -865,11 +865,22 @@ int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
 
 /* One launch for n messages.  Host-side work is bookkeeping only: where the descriptors and the
  * three byte ranges live, staging whatever is host memory through the grow-only device buffers. */
-static int ccm_batch(int keybits, const u8 *key, uaes_msg *msgs, size_t n,
+#define BATCH_CCM 0
+#define BATCH_EAX 1
+#define BATCH_SIV 2
+
+static int launch_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt, void *msgs_dev,
+                        u64 n, const void *aad, const void *in, void *out, void *stream)
+{
+    if (mode == BATCH_CCM) return uaes_launch_ccm_batch(ks, decrypt, msgs_dev, n, aad, in, out, stream);
+    return uaes_launch_mac_batch(mode, ks, ks2, decrypt, msgs_dev, n, aad, in, out, stream);
+}
+
+static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_t n,
                      const void *aad, const void *in, void *out, int decrypt)
 {
     devctx *c;
-    uaes_keysched ks;
+    uaes_keysched ks, ks2;
     int rc = 0, msgs_dev;
     size_t i, in_ext = 0, out_ext = 0, aad_ext = 0, off;
     const void *din, *daad;
@@ -878,6 +889,8 @@ static int ccm_batch(int keybits, const u8 *key, uaes_msg *msgs, size_t n,
     struct cudaPointerAttributes at;
 
     if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    ks2 = ks;
+    if (mode == BATCH_SIV) expand_key(keybits, key + keybits / 8, &ks2);     /* keys = K1 || K2, micro_aes.c:1378 */
     if (n == 0) return 0;
     pthread_mutex_lock(&g_lock);
     if ((rc = get_ctx(&c)) != 0) goto done;
@@ -889,7 +902,7 @@ static int ccm_batch(int keybits, const u8 *key, uaes_msg *msgs, size_t n,
             goto done;
         }
         st = (cudaStream_t)tls_stream;
-        LAUNCH(uaes_launch_ccm_batch(&ks, decrypt, msgs, n, aad, in, out, st));
+        LAUNCH(launch_batch(mode, &ks, &ks2, decrypt, msgs, n, aad, in, out, st));
         if (!tls_async) CU(cudaStreamSynchronize(st));
         goto done;                                   /* per-message results stay on the device */
     }
@@ -920,7 +933,7 @@ static int ccm_batch(int keybits, const u8 *key, uaes_msg *msgs, size_t n,
         /* bytes of the output range that no message covers must survive the copy back */
         if (out_ext) CU(cudaMemcpyAsync(dout, out, out_ext, cudaMemcpyDefault, st));
     }
-    LAUNCH(uaes_launch_ccm_batch(&ks, decrypt, dmsgs, n, daad, din, dout, st));
+    LAUNCH(launch_batch(mode, &ks, &ks2, decrypt, dmsgs, n, daad, din, dout, st));
     if (dout != out && out_ext) CU(cudaMemcpyAsync(out, dout, out_ext, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(msgs, dmsgs, n * sizeof(uaes_msg), cudaMemcpyDefault, st));
     CU(cudaStreamSynchronize(st));
@@ -930,39 +943,84 @@ done:
     return rc;
 }
 
-int uaes_ccm_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
-                           const void *aad, const void *in, void *out)
-{
-    return ccm_batch(keybits, key, msgs, n, aad, in, out, 0);
-}
+#define BATCH_ENTRY(name, mode, dec) \
+    int name(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n, const void *aad, const void *in, void *out) \
+    { return mac_batch(mode, keybits, key, msgs, n, aad, in, out, dec); }
+BATCH_ENTRY(uaes_ccm_encrypt_batch, BATCH_CCM, 0)
+BATCH_ENTRY(uaes_ccm_decrypt_batch, BATCH_CCM, 1)
+BATCH_ENTRY(uaes_eax_encrypt_batch, BATCH_EAX, 0)
+BATCH_ENTRY(uaes_eax_decrypt_batch, BATCH_EAX, 1)
+BATCH_ENTRY(uaes_siv_encrypt_batch, BATCH_SIV, 0)
+BATCH_ENTRY(uaes_siv_decrypt_batch, BATCH_SIV, 1)
 
-int uaes_ccm_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
-                           const void *aad, const void *in, void *out)
-{
-    return ccm_batch(keybits, key, msgs, n, aad, in, out, 1);
-}
-
-static int ccm_single(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
-                      const void *in, size_t len, void *out, int decrypt)
+/* one message with the reference's argument list = a batch of one */
+static int mac_single(int mode, int keybits, const u8 *key, const u8 *nonce, size_t noncelen, const void *aad,
+                      size_t aadlen, const void *in, size_t len, void *out, int decrypt)
 {
     uaes_msg m;
-    if (len > 0xFFFFFFFFu || aadlen > 0xFFFFFFFFu) return fail(UAES_E_BAD_ARGUMENT, "CCM with a 4-byte length field", 0);
+    if (len > 0xFFFFFFFFu - 16 || aadlen > 0xFFFFFFFFu) return fail(UAES_E_BAD_ARGUMENT, "message longer than 4 GiB", 0);
     memset(&m, 0, sizeof m);
     m.len = (unsigned int)len; m.aad_len = (unsigned int)aadlen;
-    memcpy(m.nonce, nonce, 11);
-    return ccm_batch(keybits, key, &m, 1, aad, in, out, decrypt);
+    if (noncelen) memcpy(m.nonce, nonce, noncelen);
+    return mac_batch(mode, keybits, key, &m, 1, aad, in, out, decrypt);
 }
 
 int uaes_ccm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return ccm_single(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 0);
 }
 
 int uaes_ccm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return ccm_single(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 1);
+}
+
+int uaes_eax_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 0);
+}
+
+int uaes_eax_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 1);
+}
+
+/* The reference keeps the synthetic IV and the ciphertext in separate buffers (micro_aes.c:1372,
+ * 1394); the batch layout is IV || ciphertext.  A host temporary bridges the two. */
+int uaes_siv_encrypt(int keybits, const uaes_u8 *keys, const void *aad, size_t aadlen,
+                     const void *in, size_t len, uaes_u8 *iv, void *out)
+{
+    int rc;
+    u8 *tmp = (u8 *)malloc(len + 16);
+    if (!tmp) return fail(UAES_E_NO_MEMORY, "malloc(SIV temporary)", 0);
+    rc = mac_single(BATCH_SIV, keybits, keys, NULL, 0, aad, aadlen, in, len, tmp, 0);
+    if (rc == 0) {
+        memcpy(iv, tmp, 16);
+        if (len && cudaMemcpy(out, tmp + 16, len, cudaMemcpyDefault) != cudaSuccess)
+            rc = fail(UAES_E_CUDA, "cudaMemcpy(SIV ciphertext)", (int)cudaGetLastError());
+    }
+    free(tmp);
+    return rc;
+}
+
+int uaes_siv_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *iv, const void *aad, size_t aadlen,
+                     const void *in, size_t len, void *out)
+{
+    int rc;
+    u8 *tmp = (u8 *)malloc(len + 16);
+    if (!tmp) return fail(UAES_E_NO_MEMORY, "malloc(SIV temporary)", 0);
+    memcpy(tmp, iv, 16);
+    if (len && cudaMemcpy(tmp + 16, in, len, cudaMemcpyDefault) != cudaSuccess) {
+        free(tmp);
+        return fail(UAES_E_CUDA, "cudaMemcpy(SIV ciphertext)", (int)cudaGetLastError());
+    }
+    rc = mac_single(BATCH_SIV, keybits, keys, NULL, 0, aad, aadlen, tmp, len, out, 1);
+    free(tmp);
+    return rc;
 }
 
 /* ------------------------------------------------------------------ synthetic data */

@@ -107,6 +107,10 @@ int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int enc
 int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void *msgs_dev, u64 n,
                           const void *aad, const void *in, void *out, void *stream);
 
+/* EAX (mode 1) and SIV (mode 2; ks = S2V key, ks2 = CTR key) over a batch, one message per lane */
+int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt,
+                          void *msgs_dev, u64 n, const void *aad, const void *in, void *out, void *stream);
+
 /* synthetic data + checksum helpers */
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
 int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);

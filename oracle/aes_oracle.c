@@ -8,6 +8,7 @@
  * taken are a run-time key length and no static state.
  */
 #include "aes_oracle.h"
+#include <stdlib.h>
 #include <string.h>
 
 /* ------------------------------------------------------------------------ */
@@ -921,6 +922,155 @@ int oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
     ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
     ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, tag);
     return memcmp(tag, (const uint8_t *)in + len, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
+/* CMAC helpers, EAX and SIV                              */
+/* ------------------------------------------------------------------------ */
+
+/* doubleBblock, micro_aes.c:434-444: big-endian 128-bit value times x, 0x87 fold */
+static void dbl_be(uint8_t b[16])
+{
+    const int carry = b[0] >> 7;
+    int i;
+    for (i = 0; i < 15; ++i) b[i] = (uint8_t)(b[i] << 1 | b[i + 1] >> 7);
+    b[15] = (uint8_t)(b[15] << 1) ^ (uint8_t)(carry * 0x87);
+}
+
+/* getSubkeys with quad = 1, micro_aes.c:593-604: K1 = 2 E(0), K2 = 4 E(0) */
+static void cmac_subkeys(const aes_ctx *c, uint8_t k1[16], uint8_t k2[16])
+{
+    memset(k1, 0, 16);
+    encrypt_block(c, k1, k1);
+    dbl_be(k1);
+    memcpy(k2, k1, 16);
+    dbl_be(k2);
+}
+
+/* cMac, micro_aes.c:576-590: CMAC continued from the running state `mac` */
+static void cmac_continue(const aes_ctx *c, const uint8_t k1[16], const uint8_t k2[16],
+                          const uint8_t *data, size_t n, uint8_t mac[16])
+{
+    const size_t s = n ? (n - 1) % 16 + 1 : 0;         /* bytes in the last block */
+    uint8_t last[16] = {0};
+    cbcmac_absorb(c, data, n - s, mac);
+    if (s) memcpy(last, data + n - s, s);
+    if (s < 16) { last[s] = 0x80; xor16(last, k2); }
+    else xor16(last, k1);
+    xor16(mac, last);
+    encrypt_block(c, mac, mac);
+}
+
+/* oMac without EAXP, micro_aes.c:1531-1550: OMAC^t(data) = CMAC([t]_128 || data) */
+static void omac(const aes_ctx *c, int t, const uint8_t k1[16], const uint8_t k2[16],
+                 const uint8_t *data, size_t n, uint8_t out[16])
+{
+    memset(out, 0, 16);
+    if (n == 0) memcpy(out, k1, 16);
+    out[15] ^= (uint8_t)t;
+    encrypt_block(c, out, out);
+    if (n) cmac_continue(c, k1, k2, data, n, out);
+}
+
+static void eax_tag(const aes_ctx *c, const uint8_t nonce[16], const uint8_t *aad, size_t aadlen,
+                    const uint8_t *ct, size_t len, uint8_t N[16], uint8_t tag[16])
+{
+    uint8_t k1[16], k2[16], h[16], m[16];
+    int i;
+    cmac_subkeys(c, k1, k2);
+    omac(c, 0, k1, k2, nonce, 16, N);                  /* :1578 */
+    omac(c, 1, k1, k2, aad, aadlen, h);                /* :1591 */
+    omac(c, 2, k1, k2, ct, len, m);                    /* :1593 */
+    for (i = 0; i < 16; ++i) tag[i] = N[i] ^ h[i] ^ m[i];
+}
+
+/* micro_aes.c:1564-1598 (EAX_NONCE_LEN = 16, EAX_TAG_LEN = 16); out holds len + 16 */
+void oracle_eax_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t k1[16], k2[16], N[16], ctr[16], tag[16];
+    key_setup(&c, keybits, key);
+    cmac_subkeys(&c, k1, k2);
+    omac(&c, 0, k1, k2, nonce, 16, N);
+    memcpy(ctr, N, 16);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);    /* CTR_DEFAULT: starts AT N, :1584 */
+    eax_tag(&c, nonce, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, N, tag);
+    memcpy((uint8_t *)out + len, tag, 16);
+}
+
+/* micro_aes.c:1613-1648: authenticate, then decrypt; `out` is untouched on failure */
+int oracle_eax_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t N[16], tag[16];
+    key_setup(&c, keybits, key);
+    eax_tag(&c, nonce, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, N, tag);
+    if (memcmp(tag, (const uint8_t *)in + len, 16)) return ORACLE_AUTHENTICATION_ERROR;
+    ctr_stream(&c, N, (const uint8_t *)in, len, (uint8_t *)out);
+    return ORACLE_SUCCESS;
+}
+
+/* S2V for one AAD unit, micro_aes.c:1325-1359, written the way RFC 5297 states it (xorend for
+ * messages of 16 bytes and more, dbl + pad below that); c = first key half */
+static void s2v(const aes_ctx *c, const uint8_t *aad, size_t aadlen, const uint8_t *pt, size_t len, uint8_t v[16])
+{
+    uint8_t k1[16], k2[16], y[16], t[16];
+    size_t i;
+    cmac_subkeys(c, k1, k2);
+    encrypt_block(c, k1, y);                           /* Y_0 = CMAC(0^128) = E(K1), :1332 */
+    if (aadlen) {                                      /* :1338-1344 */
+        memset(t, 0, 16);
+        cmac_continue(c, k1, k2, aad, aadlen, t);
+        dbl_be(y);
+        xor16(y, t);
+    }
+    memset(v, 0, 16);
+    if (len >= 16) {                                   /* CMAC(pt xorend Y), :1350-1358 */
+        uint8_t *tmp = (uint8_t *)malloc(len);
+        memcpy(tmp, pt, len);
+        for (i = 0; i < 16; ++i) tmp[len - 16 + i] ^= y[i];
+        cmac_continue(c, k1, k2, tmp, len, v);
+        free(tmp);
+    } else {                                           /* CMAC(dbl(Y) ^ pad(pt)), :1345-1349 */
+        dbl_be(y);
+        for (i = 0; i < len; ++i) y[i] ^= pt[i];
+        y[len] ^= 0x80;
+        cmac_continue(c, k1, k2, y, 16, v);
+    }
+}
+
+static void siv_ctr(const aes_ctx *c2, const uint8_t v[16], const uint8_t *x, size_t len, uint8_t *y)
+{
+    uint8_t ctr[16];
+    memcpy(ctr, v, 16);
+    ctr[8] &= 0x7F; ctr[12] &= 0x7F;                   /* SIV_CTR, micro_aes.c:931-934 */
+    ctr_stream(c2, ctr, x, len, y);
+}
+
+/* micro_aes.c:1372-1382: keys = K1 || K2, iv = synthetic IV (16 bytes out), out holds len */
+void oracle_siv_encrypt(int keybits, const uint8_t *keys, const void *aad, size_t aadlen,
+                        const void *in, size_t len, uint8_t iv[16], void *out)
+{
+    aes_ctx c1, c2;
+    key_setup(&c1, keybits, keys);
+    key_setup(&c2, keybits, keys + keybits / 8);
+    s2v(&c1, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, iv);
+    siv_ctr(&c2, iv, (const uint8_t *)in, len, (uint8_t *)out);
+}
+
+/* micro_aes.c:1394-1410: decrypts first, then compares the recomputed IV (plaintext stays) */
+int oracle_siv_decrypt(int keybits, const uint8_t *keys, const uint8_t iv[16], const void *aad, size_t aadlen,
+                       const void *in, size_t len, void *out)
+{
+    aes_ctx c1, c2;
+    uint8_t v[16];
+    key_setup(&c1, keybits, keys);
+    key_setup(&c2, keybits, keys + keybits / 8);
+    siv_ctr(&c2, iv, (const uint8_t *)in, len, (uint8_t *)out);
+    s2v(&c1, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, v);
+    return memcmp(v, iv, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
 }
 
 /* ------------------------------------------------------------------------ */

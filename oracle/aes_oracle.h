@@ -122,6 +122,18 @@ void oracle_ccm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[11]
 int  oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
                         const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* EAX (not EAX'): 16-byte nonce, 16-byte tag (micro_aes.c:1564-1648, micro_aes.h:119-121) */
+void oracle_eax_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+int  oracle_eax_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
+/* SIV (RFC 5297) with one AAD unit: keys = K1 || K2 (micro_aes.c:1372-1410) */
+void oracle_siv_encrypt(int keybits, const uint8_t *keys, const void *aad, size_t aadlen,
+                        const void *in, size_t len, uint8_t iv[16], void *out);
+int  oracle_siv_decrypt(int keybits, const uint8_t *keys, const uint8_t iv[16], const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out);
+
 /* splitmix64 synthetic-data generator shared by tests and bench: 64-bit word w of
  * the buffer (byte offset 8w, little-endian) = splitmix64(seed + first_word + w) */
 void oracle_fill_splitmix64(uint64_t seed, uint64_t first_word, void *dst, size_t nwords);

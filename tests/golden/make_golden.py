@@ -76,6 +76,16 @@ def main_c_vectors():
         "ocb128": s["ocbcipher"][0],
         # CCM, main.c:55-57, 198-204 (nonce = first 11 bytes of iVec, same AAD)
         "ccm128": s["ccmcipher"][0],
+        # EAX (not EAX'): main.c:68-70, 225-237 (nonce = iVec, 16 bytes); SIV: main.c:52-54, 212-218 (keys = first
+        # 32 bytes of the key pool, output = IV || ciphertext) and the two extra cases main.c:300-321
+        "eax128": s["eaxcipher"][0], "siv128": s["sivcipher"][0],
+        "siv_extra": [
+            {"keys": "fffefdfcfbfaf9f8f7f6f5f4f3f2f1f0f0f1f2f3f4f5f6f7f8f9fafbfcfdfeff",
+             "aad": "101112131415161718191a1b1c1d1e1f2021222324252627", "pt": "112233445566778899aabbccddee",
+             "out": "85632d07c6e8f37f950acd320a2ecc9340c02b9690c4dc04daef7f6afe5c"},
+            {"keys": "fffefdfcfbfaf9f8f7f6f5f4f3f2f1f0f0f1f2f3f4f5f6f7f8f9fafbfcfdfeff", "aad": "",
+             "pt": "00112233445566778899aabbccddeeff",
+             "out": "f304f912863e303d5b540e5057c7010c942ffaf45b0e5ca5fb9a56a5263bb065"}],
         "ocb_rfc7253": {"key": "000102030405060708090a0b0c0d0e0f", "iv": "bbaa99887766554433221107",
                         "aad": "000102030405060708090a0b0c0d0e0f1011121314151617",
                         "pt": "000102030405060708090a0b0c0d0e0f1011121314151617",
@@ -185,6 +195,22 @@ def parse_ccm(path, keybits):
     return cases
 
 
+def parse_eax(path, keybits):
+    """testvectors/EAX_AES128.tv (Bellare-Rogaway-Wagner): MSG/KEY/NONCE/HEADER/CIPHER groups, kept when
+    key and nonce have the build's sizes (aes_testvectors_EAX.h:83)"""
+    cases, cur = [], {}
+    for line in open(path):
+        line = line.strip()
+        for name in ("MSG", "KEY", "NONCE", "HEADER", "CIPHER"):
+            if line.startswith(name + ":"):
+                cur[name] = line.split(":", 1)[1].strip().lower()
+        if "CIPHER" in cur:
+            if len(cur["KEY"]) == keybits // 4 and len(cur["NONCE"]) == 32 and len(cur["CIPHER"]) == len(cur["MSG"]) + 32:
+                cases.append({"key": cur["KEY"], "nonce": cur["NONCE"], "aad": cur["HEADER"], "pt": cur["MSG"], "ct": cur["CIPHER"]})
+            cur = {}
+    return cases
+
+
 def row4_samples():
     """SURVEY 8f row 4 (CCM now): outputs of the unmodified reference on inputs no in-tree vector
     covers -- empty/ragged payloads, AAD around the 14-byte first block and the 0xFEFF length-encoding
@@ -202,6 +228,21 @@ def row4_samples():
             out["ccm"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
                                "aad_tag": f"cca{bits}{n}{a}", "pt_tag": f"ccp{bits}{n}",
                                "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    out["eax"], out["siv"] = [], []
+    for bits, lib in libs.items():
+        for n, a in ((0, 0), (0, 9), (1, 0), (15, 13), (16, 16), (17, 15), (32, 0), (57, 31), (1000, 20), (4096 + 3, 129), (1 << 16, 7)):
+            key, nonce = rnd(f"eak{bits}{n}", bits // 8), rnd(f"ean{bits}{n}", 16)
+            aad, pt = rnd(f"eaa{bits}{n}{a}", a), rnd(f"eap{bits}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.AES_EAX_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            out["eax"].append({"bits": bits, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                               "aad_tag": f"eaa{bits}{n}{a}", "pt_tag": f"eap{bits}{n}",
+                               "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+            keys = rnd(f"sik{bits}{n}", bits // 4)
+            iv, ct = ctypes.create_string_buffer(16), ctypes.create_string_buffer(n + 16)
+            lib.AES_SIV_encrypt(keys, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), iv, ct)
+            out["siv"].append({"bits": bits, "n": n, "aadlen": a, "keys": keys.hex(), "aad_tag": f"eaa{bits}{n}{a}",
+                               "pt_tag": f"eap{bits}{n}", "iv": iv.raw.hex(), "ct_sha256": sha(ct.raw[:n])})
     return out
 
 
@@ -367,6 +408,9 @@ def main():
         w(f"ccm{bits}.json", {"source": f"testvectors/VNT{bits}.rsp, filter of aes_testvectors_CCM.h:97 (11-byte nonce, 16-byte tag)",
                               "cases": c})
         print(f"ccm{bits}: {len(c)} cases")
+    c = parse_eax(os.path.join(tv, "EAX_AES128.tv"), 128)
+    w("eax128.json", {"source": "testvectors/EAX_AES128.tv, filter of aes_testvectors_EAX.h:83", "cases": c})
+    print(f"eax128: {len(c)} cases")
     w("oracle_ref_samples_row4.json", row4_samples())
     print("ok")
 

@@ -25,3 +25,5 @@ def test_reference_main_c_passes_against_our_library(bits, modes):
         assert out.count("OCB encryption: PASSED!") == 2 and out.count("OCB decryption: PASSED!") == 2, out
         assert out.count("GCMSIV encrypt: PASSED!") == 3 and out.count("GCMSIV decrypt: PASSED!") == 3, out
         assert "CCM encryption: PASSED!" in out and "CCM decryption: PASSED!" in out, out     # main.c:198-204
+        assert "EAX encryption: PASSED!" in out and "EAX decryption: PASSED!" in out, out     # main.c:225-237
+        assert out.count("SIV encryption: PASSED!") == 3 and out.count("SIV decryption: PASSED!") == 3, out   # :212-218, 300-321

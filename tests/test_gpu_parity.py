@@ -590,3 +590,77 @@ def test_ccm_batch_matches_oracle(uaes, orc, torch, bits, seed, n, max_len, max_
     for i, m in enumerate(msgs):
         assert dec[i].result == (0x1A if i in forged else 0), i
         assert back[m.in_off:m.in_off + m.len] == pt[m.in_off:m.in_off + m.len], i    # produced either way (micro_aes.c:1304-1312)
+
+
+def test_eax_siv_reference_vectors(uaes, orc):
+    m = golden("main_c.json")
+    a = uaes.MicroAES(128)
+    key, aad, pt = H(m["key_pool"])[:16], H(m["aad"]), H(m["plaintext"])
+    assert a.AES_EAX_encrypt(key, H(m["iv16"]), aad, pt) == H(m["eax128"])           # main.c:225-237
+    assert a.AES_EAX_decrypt(key, H(m["iv16"]), aad, H(m["eax128"])) == (0, pt)
+    for c in golden("eax128.json")["cases"]:                                         # testvectors/EAX_AES128.tv
+        assert a.AES_EAX_encrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+        assert a.AES_EAX_decrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"])), c
+    keys = H(m["key_pool"])[:32]
+    assert a.AES_SIV_encrypt(keys, aad, pt) == H(m["siv128"])                        # main.c:212-218
+    assert a.AES_SIV_decrypt(keys, aad, H(m["siv128"])) == (0, pt)
+    for v in m["siv_extra"]:                                                         # main.c:300-321
+        assert a.AES_SIV_encrypt(H(v["keys"]), H(v["aad"]), H(v["pt"])) == H(v["out"])
+        assert a.AES_SIV_decrypt(H(v["keys"]), H(v["aad"]), H(v["out"])) == (0, H(v["pt"]))
+    for bits in (128, 192, 256):
+        a = uaes.MicroAES(bits)
+        for c in [x for x in golden("oracle_ref_samples_row4.json")["eax"] if x["bits"] == bits]:
+            out = a.AES_EAX_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+            assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+        for c in [x for x in golden("oracle_ref_samples_row4.json")["siv"] if x["bits"] == bits]:
+            out = a.AES_SIV_encrypt(H(c["keys"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+            assert out[:16].hex() == c["iv"] and sha256(out[16:]) == c["ct_sha256"], c
+    # EAX authenticates before it decrypts: the output stays as it was (micro_aes.c:1637-1645)
+    enc = bytearray(orc.eax_encrypt(key, H(m["iv16"]), aad, pt)); enc[0] ^= 1
+    assert a.__class__(128).AES_EAX_decrypt(key, H(m["iv16"]), aad, bytes(enc)) == (0x1A, b"\xcc" * len(pt))
+
+
+@pytest.mark.parametrize("mode", ["eax", "siv"])
+@pytest.mark.parametrize("bits,seed,n,max_len,max_aad,align", [(128, 11, 600, 300, 40, 1), (256, 12, 2000, 100, 20, 16),
+                                                               (192, 13, 48, 5000, 3000, 4)])
+def test_eax_siv_batch_matches_oracle(uaes, orc, torch, mode, bits, seed, n, max_len, max_aad, align):
+    key = rnd(f"{mode}b-k{bits}", bits // 8 * (2 if mode == "siv" else 1))
+    msgs, in_sz, out_sz, aad_sz = _ccm_batch_case(uaes, seed, n, max_len, max_aad, align)
+    for i in range(n):                                   # EAX uses all 16 nonce bytes
+        nonce = rnd(f"{mode}b-n{seed}-{i}", 16)
+        for j in range(16):
+            msgs[i].nonce[j] = nonce[j]
+    pt, aad = bytearray(rnd(f"{mode}b-p{seed}", in_sz)), rnd(f"{mode}b-a{seed}", max(aad_sz, 1))
+    enc1 = (lambda m: orc.eax_encrypt(key, bytes(m.nonce), aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len]))) \
+        if mode == "eax" else (lambda m: orc.siv_encrypt(key, aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len])))
+    want = bytearray(b"\xee" * out_sz)
+    for m in msgs:
+        want[m.out_off:m.out_off + m.len + 16] = enc1(m)
+    out = bytearray(b"\xee" * out_sz)
+    assert uaes.ccm_batch(bits, key, msgs, n, aad, pt, out, mode=mode) == 0
+    assert out == want
+    d_in, d_aad, d_msgs, d_out = dev(torch, bytes(pt)), dev(torch, aad), dev(torch, bytes(msgs)), dev(torch, b"", pad=out_sz)
+    assert uaes.ccm_batch(bits, key, d_msgs, n, d_aad, d_in, d_out, mode=mode) == 0
+    torch.cuda.synchronize()
+    got = host(d_out, 0, out_sz)
+    for m in msgs:
+        assert got[m.out_off:m.out_off + m.len + 16] == want[m.out_off:m.out_off + m.len + 16]
+
+    dec = (uaes.Msg * n)()
+    for i, m in enumerate(msgs):
+        dec[i].in_off, dec[i].out_off, dec[i].aad_off = m.out_off, m.in_off, m.aad_off
+        dec[i].len, dec[i].aad_len = m.len, m.aad_len
+        for j in range(16):
+            dec[i].nonce[j] = m.nonce[j]
+    ct = bytearray(want)
+    forged = set(range(0, n, 5))
+    for i in forged:                                      # EAX: the tag at the end; SIV: the IV in front
+        ct[msgs[i].out_off + (msgs[i].len + 7 if mode == "eax" else 3)] ^= 0x04
+    back = bytearray(b"\xdd" * in_sz)
+    assert uaes.ccm_batch(bits, key, dec, n, aad, ct, back, decrypt=True, mode=mode) == 0x1A
+    for i, m in enumerate(msgs):
+        assert dec[i].result == (0x1A if i in forged else 0), i
+        if i not in forged:
+            assert back[m.in_off:m.in_off + m.len] == pt[m.in_off:m.in_off + m.len], i
+        elif mode == "eax":                               # untouched on failure
+            assert back[m.in_off:m.in_off + m.len] == b"\xdd" * m.len, i

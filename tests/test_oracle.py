@@ -247,6 +247,42 @@ def test_ccm_vectors_and_recorded_reference(orc):
     assert rc == 0x1A and got == rnd(c["pt_tag"], c["n"])
 
 
+def test_eax_vectors_and_recorded_reference(orc):
+    m = golden("main_c.json")
+    key, nonce, aad, pt = H(m["key_pool"])[:16], H(m["iv16"]), H(m["aad"]), H(m["plaintext"])
+    out = orc.eax_encrypt(key, nonce, aad, pt)                      # main.c:225-237
+    assert out == H(m["eax128"])
+    assert orc.eax_decrypt(key, nonce, aad, out) == (0, pt)
+    cases = golden("eax128.json")["cases"]
+    assert len(cases) == 10
+    for c in cases:
+        assert orc.eax_encrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["pt"])) == H(c["ct"]), c
+        assert orc.eax_decrypt(H(c["key"]), H(c["nonce"]), H(c["aad"]), H(c["ct"])) == (0, H(c["pt"]))
+    for c in golden("oracle_ref_samples_row4.json")["eax"]:
+        out = orc.eax_encrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+        assert sha256(out[:-16]) == c["ct_sha256"] and out[-16:].hex() == c["tag"], c
+    bad = bytearray(out); bad[3] ^= 1                               # authenticate-then-decrypt, :1637-1645
+    rc, got = orc.eax_decrypt(H(c["key"]), H(c["nonce"]), rnd(c["aad_tag"], c["aadlen"]), bytes(bad))
+    assert rc == 0x1A and got == b"\xcc" * c["n"]
+
+
+def test_siv_vectors_and_recorded_reference(orc):
+    m = golden("main_c.json")
+    keys, aad, pt = H(m["key_pool"])[:32], H(m["aad"]), H(m["plaintext"])
+    out = orc.siv_encrypt(keys, aad, pt)                            # main.c:212-218
+    assert out == H(m["siv128"])
+    assert orc.siv_decrypt(keys, aad, out) == (0, pt)
+    for v in m["siv_extra"]:                                        # RFC 5297 A.1 and miscreant, main.c:300-321
+        assert orc.siv_encrypt(H(v["keys"]), H(v["aad"]), H(v["pt"])) == H(v["out"])
+        assert orc.siv_decrypt(H(v["keys"]), H(v["aad"]), H(v["out"])) == (0, H(v["pt"]))
+    for c in golden("oracle_ref_samples_row4.json")["siv"]:
+        out = orc.siv_encrypt(H(c["keys"]), rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]))
+        assert out[:16].hex() == c["iv"] and sha256(out[16:]) == c["ct_sha256"], c
+    bad = bytearray(out); bad[-1] ^= 1                              # decrypts first, then compares, :1399-1408
+    rc, got = orc.siv_decrypt(H(c["keys"]), rnd(c["aad_tag"], c["aadlen"]), bytes(bad))
+    assert rc == 0x1A and got[:-1] == rnd(c["pt_tag"], c["n"])[:-1]
+
+
 # ---------------------------------------------------------------- edge cases
 
 def test_edge_cases(orc):
@@ -295,6 +331,14 @@ def test_live_reference_differential(orc, bits):
         enc = ref.ccm_encrypt(key, iv[:11], aad, data)
         assert orc.ccm_encrypt(key, iv[:11], aad, data) == enc
         assert orc.ccm_decrypt(key, iv[:11], aad, enc) == ref.ccm_decrypt(key, iv[:11], aad, enc) == (0, data)
+        n16 = rnd(f"ln{bits}{i}", 16)
+        enc = ref.eax_encrypt(key, n16, aad, data)
+        assert orc.eax_encrypt(key, n16, aad, data) == enc
+        assert orc.eax_decrypt(key, n16, aad, enc) == ref.eax_decrypt(key, n16, aad, enc) == (0, data)
+        k2 = rnd(f"lk2{bits}{i}", 2 * ks)
+        enc = ref.siv_encrypt(k2, aad, data)
+        assert orc.siv_encrypt(k2, aad, data) == enc
+        assert orc.siv_decrypt(k2, aad, enc) == ref.siv_decrypt(k2, aad, enc) == (0, data)
         if bits != 192 and n >= 16:
             keys, tw = rnd(f"lx{bits}{i}", 2 * ks), rnd(f"lt{bits}{i}", 16)
             e = ref.xts(keys, tw, data)

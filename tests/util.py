@@ -60,6 +60,10 @@ class Oracle:
         L.oracle_ocb_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_ccm_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         L.oracle_ccm_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_eax_encrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_eax_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
+        L.oracle_siv_encrypt.argtypes = [_int, _u8p, _u8p, _sz, _u8p, _sz, _u8p, _u8p]
+        L.oracle_siv_decrypt.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p]
         for f in (L.oracle_cbc_decrypt, L.oracle_cbc_encrypt, L.oracle_cfb_decrypt, L.oracle_cfb_encrypt):
             f.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
         L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
@@ -168,6 +172,30 @@ class Oracle:
         rc = self.lib.oracle_ccm_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
         return rc, o.raw[:n]
 
+    def eax_encrypt(self, key, nonce, aad, pt):
+        o = self._buf(len(pt) + 16)
+        self.lib.oracle_eax_encrypt(len(key) * 8, key, nonce, aad, len(aad), pt, len(pt), o)
+        return o.raw[:len(pt) + 16]
+
+    def eax_decrypt(self, key, nonce, aad, ct_and_tag):
+        """(rc, plaintext); the output buffer (0xCC filled here) is untouched when rc = 0x1A"""
+        n = len(ct_and_tag) - 16
+        o = ctypes.create_string_buffer(b"\xcc" * max(n, 1), max(n, 1))
+        rc = self.lib.oracle_eax_decrypt(len(key) * 8, key, nonce, aad, len(aad), ct_and_tag, n, o)
+        return rc, o.raw[:n]
+
+    def siv_encrypt(self, keys, aad, pt):
+        """IV || ciphertext, the layout main.c:214 uses"""
+        iv, o = self._buf(16), self._buf(len(pt))
+        self.lib.oracle_siv_encrypt(len(keys) * 4, keys, aad, len(aad), pt, len(pt), iv, o)
+        return iv.raw[:16] + o.raw[:len(pt)]
+
+    def siv_decrypt(self, keys, aad, iv_and_ct):
+        n = len(iv_and_ct) - 16
+        o = self._buf(n)
+        rc = self.lib.oracle_siv_decrypt(len(keys) * 4, keys, iv_and_ct[:16], aad, len(aad), iv_and_ct[16:], n, o)
+        return rc, o.raw[:n]
+
     def polyval(self, H, aad, pt):
         o = self._buf(16)
         self.lib.oracle_polyval(H, aad, len(aad), pt, len(pt), o)
@@ -217,7 +245,8 @@ class Reference:
         self.bits = bits
         self.lib = ctypes.CDLL(self.path)
         for f in ("AES_ECB_decrypt", "AES_XTS_encrypt", "AES_XTS_decrypt", "AES_GCM_decrypt", "GCM_SIV_decrypt",
-                  "AES_CBC_encrypt", "AES_CBC_decrypt", "AES_OCB_decrypt", "AES_CCM_decrypt"):
+                  "AES_CBC_encrypt", "AES_CBC_decrypt", "AES_OCB_decrypt", "AES_CCM_decrypt",
+                  "AES_EAX_decrypt", "AES_SIV_decrypt"):
             getattr(self.lib, f).restype = ctypes.c_char
 
     @staticmethod
@@ -272,6 +301,28 @@ class Reference:
         n = len(ct_and_tag) - 16
         o = ctypes.create_string_buffer(n + 16)
         rc = self.lib.AES_CCM_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
+        return ord(rc), o.raw[:n]
+
+    def eax_encrypt(self, key, nonce, aad, pt):
+        o = ctypes.create_string_buffer(len(pt) + 16)
+        self.lib.AES_EAX_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
+        return o.raw[:len(pt) + 16]
+
+    def eax_decrypt(self, key, nonce, aad, ct_and_tag):
+        n = len(ct_and_tag) - 16
+        o = ctypes.create_string_buffer(b"\xcc" * (n + 16), n + 16)
+        rc = self.lib.AES_EAX_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
+        return ord(rc), o.raw[:n]
+
+    def siv_encrypt(self, keys, aad, pt):
+        iv, o = ctypes.create_string_buffer(16), ctypes.create_string_buffer(len(pt) + 16)
+        self.lib.AES_SIV_encrypt(keys, aad, _sz(len(aad)), pt, _sz(len(pt)), iv, o)
+        return iv.raw[:16] + o.raw[:len(pt)]
+
+    def siv_decrypt(self, keys, aad, iv_and_ct):
+        n = len(iv_and_ct) - 16
+        o = ctypes.create_string_buffer(n + 16)
+        rc = self.lib.AES_SIV_decrypt(keys, iv_and_ct[:16], aad, _sz(len(aad)), iv_and_ct[16:], _sz(n), o)
         return ord(rc), o.raw[:n]
 
     def cbc(self, key, iv, data, encrypt=False):
