@@ -214,6 +214,21 @@ int uaes_ccm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
 int uaes_ccm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                      const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* ---- streaming: init / update / final (the reference has none) ------ */
+/* One message fed in pieces.  Every update but the last must be a multiple of 16 bytes; buffers may
+ * be host or device memory as everywhere else.  CTR keeps the keystream position; GCM runs one fused
+ * CTR+GHASH pass per update and folds the 16-byte contributions on the device, so the number of
+ * updates is unbounded.  A decrypting GCM stream hands out plaintext before it is authenticated:
+ * discard it when uaes_stream_final returns UAES_AUTH_ERROR. */
+typedef struct uaes_stream uaes_stream;
+uaes_stream *uaes_stream_ctr(int keybits, const uaes_u8 *key, const uaes_u8 *iv);
+uaes_stream *uaes_stream_gcm(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                             const void *aad, size_t aadlen, int decrypt);
+int  uaes_stream_update(uaes_stream *s, const void *in, size_t len, void *out);
+/* GCM encrypt: writes tag[16]; GCM decrypt: compares with tag[16]; CTR: no-op */
+int  uaes_stream_final(uaes_stream *s, uaes_u8 *tag);
+void uaes_stream_free(uaes_stream *s);
+
 /* ---- synthetic data (bench / tests) ----------------------------------------- */
 /* 64-bit word w of dst (little-endian) = splitmix64(seed + first_word + w); dst is DEVICE memory */
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords);

@@ -69,6 +69,11 @@ UAES_ABI = {
     "uaes_eax_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_siv_encrypt": (_int, [_int, _cp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "uaes_siv_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
+    "uaes_stream_ctr": (_vp, [_int, _cp, _cp]),
+    "uaes_stream_gcm": (_vp, [_int, _cp, _cp, _vp, _sz, _int]),
+    "uaes_stream_update": (_int, [_vp, _vp, _sz, _vp]),
+    "uaes_stream_final": (_int, [_vp, _vp]),
+    "uaes_stream_free": (None, [_vp]),
     "uaes_fill_splitmix64": (_int, [_u64, _u64, _vp, _sz]),
     "uaes_xor_fold64": (_int, [_vp, _sz, ctypes.POINTER(_u64)]),
 }
@@ -398,6 +403,33 @@ def ccm_batch(bits, key, msgs, n, aad, src, dst, decrypt=False, mode="ccm"):
     if rc < 0:
         check(rc)
     return rc
+
+
+class Stream:
+    """uaes_stream_* of include/uaes_b200.h: one CTR or GCM message fed in pieces"""
+
+    def __init__(self, bits, key, nonce, aad=None, decrypt=False, gcm=True):
+        c = core()
+        self.h = c.uaes_stream_gcm(bits, key, nonce, _ptr(aad) if aad else None, len(aad) if aad else 0,
+                                   1 if decrypt else 0) if gcm else c.uaes_stream_ctr(bits, key, nonce)
+        if not self.h:
+            raise UaesError(core().uaes_last_error_string().decode())
+
+    def update(self, src, nbytes, dst):
+        return check(core().uaes_stream_update(self.h, _ptr(src), nbytes, _ptr(dst)))
+
+    def final(self, tag=None):
+        """encrypt: returns the 16-byte tag; decrypt: pass the received tag, returns 0 or 0x1A"""
+        if tag is None:
+            t = ctypes.create_string_buffer(16)
+            check(core().uaes_stream_final(self.h, ctypes.addressof(t)))
+            return t.raw
+        return check(core().uaes_stream_final(self.h, _ptr(tag)))
+
+    def close(self):
+        if self.h:
+            core().uaes_stream_free(self.h)
+            self.h = None
 
 
 def kernel_launches():

@@ -479,6 +479,7 @@ struct GcmCombineArgs {
     uint32_t nshards;
     uint64_t total_blocks;       // ceil(len / 16)
     uint8_t *tag_out;
+    uint32_t fold_only;          // 1: write sum_r Z_r * H^after[r] and stop (streaming: many shards -> one)
 };
 
 __global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
@@ -497,7 +498,7 @@ __global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
     if (lane < a.nshards) {
         const uint4 z = load_block_bytes(a.partials + 16 * lane, 16);
         term = gf_mul_fast(gf_load(z), gf_pow_fast(H, a.after[lane]));
-    } else if (lane == 31) {                                  // the AAD rides in front of block 0
+    } else if (lane == 31 && !a.fold_only) {                  // the AAD rides in front of block 0
         Gf g{0, 0};
         for (uint64_t off = 0; off < a.aadlen; off += 16) {
             const uint64_t left = a.aadlen - off;
@@ -513,9 +514,11 @@ __global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
     }
     if (lane) return;
     Gf S = term;
-    S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
-    S = gf_mul_fast(H, S);
-    S.hi ^= sh_ej0.hi; S.lo ^= sh_ej0.lo;
+    if (!a.fold_only) {
+        S.hi ^= a.aadlen * 8; S.lo ^= a.len * 8;
+        S = gf_mul_fast(H, S);
+        S.hi ^= sh_ej0.hi; S.lo ^= sh_ej0.lo;
+    }
     const uint4 t = gf_store(S);
     const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
     for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
@@ -610,6 +613,25 @@ extern "C" int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned c
     a.aad = (const uint8_t *)aad_dev; a.aadlen = aadlen; a.len = len;
     a.partials = (const uint8_t *)partials_dev; a.after = (const uint64_t *)after_dev;
     a.nshards = nshards; a.total_blocks = (len + 15) / 16; a.tag_out = (uint8_t *)tag_out;
+    a.fold_only = 0;
+    gcm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+// streaming: fold up to 31 shard contributions into the contribution of their union
+extern "C" int uaes_launch_gcm_fold(const uaes_keysched *ks, const void *partials_dev, const void *after_dev,
+                                    unsigned nshards, void *out_dev, void *stream)
+{
+    using namespace uaes;
+    if (nshards > 31) return (int)cudaErrorInvalidValue;
+    GcmCombineArgs a;
+    a.ks = *ks;
+    a.j0[0] = a.j0[1] = a.j0[2] = a.j0[3] = 0;
+    a.aad = nullptr; a.aadlen = 0; a.len = 0;
+    a.partials = (const uint8_t *)partials_dev; a.after = (const uint64_t *)after_dev;
+    a.nshards = nshards; a.total_blocks = 0; a.tag_out = (uint8_t *)out_dev;
+    a.fold_only = 1;
     gcm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
     return (int)cudaGetLastError();

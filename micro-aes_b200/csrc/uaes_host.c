@@ -1023,6 +1023,138 @@ int uaes_siv_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *iv, const 
     return rc;
 }
 
+/* ------------------------------------------------------------------ streaming */
+
+/* init / update / final on top of the range primitives: CTR is position bookkeeping around
+ * uaes_ctr_crypt_range; GCM runs one fused CTR+GHASH shard pass per update and keeps the 16-byte
+ * contributions, folding them on the device whenever 30 have piled up, so any number of updates
+ * costs O(1) host memory.  The reference has no streaming API. */
+#define STREAM_CTR 1
+#define STREAM_GCM 2
+#define STREAM_MAX_PENDING 30
+
+struct uaes_stream {
+    int kind, keybits, decrypt, ragged, npending;
+    u8 key[32], nonce[12];
+    u8 *aad; size_t aadlen;
+    u64 pos_blocks, total_len;
+    u8 partial[STREAM_MAX_PENDING + 1][16];
+    u64 end_block[STREAM_MAX_PENDING + 1];
+};
+
+static uaes_stream *stream_new(int kind, int keybits, const u8 *key, const u8 *nonce)
+{
+    uaes_stream *s;
+    uaes_keysched ks;
+    if (expand_key(keybits, key, &ks)) { fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0); return NULL; }
+    s = (uaes_stream *)calloc(1, sizeof *s);
+    if (!s) { fail(UAES_E_NO_MEMORY, "calloc(stream)", 0); return NULL; }
+    s->kind = kind; s->keybits = keybits;
+    memcpy(s->key, key, (size_t)keybits / 8);
+    memcpy(s->nonce, nonce, 12);
+    return s;
+}
+
+uaes_stream *uaes_stream_ctr(int keybits, const uaes_u8 *key, const uaes_u8 *iv)
+{
+    return stream_new(STREAM_CTR, keybits, key, iv);
+}
+
+uaes_stream *uaes_stream_gcm(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
+                             const void *aad, size_t aadlen, int decrypt)
+{
+    uaes_stream *s = stream_new(STREAM_GCM, keybits, key, nonce);
+    if (!s) return NULL;
+    s->decrypt = decrypt;
+    if (aadlen) {
+        s->aad = (u8 *)malloc(aadlen);
+        if (!s->aad || cudaMemcpy(s->aad, aad, aadlen, cudaMemcpyDefault) != cudaSuccess) {
+            cudaGetLastError();
+            fail(UAES_E_NO_MEMORY, "stream AAD copy", 0);
+            free(s->aad); free(s);
+            return NULL;
+        }
+        s->aadlen = aadlen;
+    }
+    return s;
+}
+
+void uaes_stream_free(uaes_stream *s)
+{
+    if (!s) return;
+    free(s->aad);
+    memset(s, 0, sizeof *s);
+    free(s);
+}
+
+/* sum_r partial[r] * H^(end_last - end_r) -> one pending entry */
+static int stream_fold(uaes_stream *s)
+{
+    devctx *c;
+    uaes_keysched ks;
+    int rc = 0, i;
+    u64 after[STREAM_MAX_PENDING + 1];
+    u8 *w;
+    cudaStream_t st = (cudaStream_t)tls_stream;
+    const u64 end = s->end_block[s->npending - 1];
+
+    expand_key(s->keybits, s->key, &ks);
+    for (i = 0; i < s->npending; ++i) after[i] = end - s->end_block[i];
+    pthread_mutex_lock(&g_lock);
+    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + 32 * 24 + 64, "cudaMalloc(GCM work)")) != 0) goto done;
+    w = (u8 *)c->work;
+    CU(cudaMemcpyAsync(w + 64, s->partial, (size_t)s->npending * 16, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(w + 64 + 32 * 16, after, (size_t)s->npending * 8, cudaMemcpyDefault, st));
+    LAUNCH(uaes_launch_gcm_fold(&ks, w + 64, w + 64 + 32 * 16, (unsigned)s->npending, w, st));
+    CU(cudaMemcpyAsync(s->partial[0], w, 16, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    s->end_block[0] = end;
+    s->npending = 1;
+done:
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+int uaes_stream_update(uaes_stream *s, const void *in, size_t len, void *out)
+{
+    int rc;
+    const u64 nb = ((u64)len + 15) / 16;
+    if (!s) return fail(UAES_E_BAD_ARGUMENT, "null stream", 0);
+    if (len == 0) return 0;
+    if (s->ragged) return fail(UAES_E_BAD_ARGUMENT, "only the last update may have a length that is not a multiple of 16", 0);
+    if (s->kind == STREAM_CTR) {
+        rc = uaes_ctr_crypt_range(s->keybits, s->key, s->nonce, s->pos_blocks, in, len, out);
+    } else {
+        if (s->npending == STREAM_MAX_PENDING && (rc = stream_fold(s)) != 0) return rc;
+        rc = uaes_gcm_shard(s->keybits, s->key, s->nonce, s->pos_blocks, in, len, out, s->decrypt,
+                            s->partial[s->npending]);
+        if (rc == 0) { s->end_block[s->npending] = s->pos_blocks + nb; ++s->npending; }
+    }
+    if (rc) return rc;
+    s->pos_blocks += nb;
+    s->total_len += len;
+    if (len % 16) s->ragged = 1;
+    return 0;
+}
+
+/* GCM encrypt: writes the 16-byte tag.  GCM decrypt: tag = the received tag; UAES_AUTH_ERROR means
+ * everything the updates produced must be discarded.  CTR: nothing to do (tag may be NULL). */
+int uaes_stream_final(uaes_stream *s, uaes_u8 *tag)
+{
+    int rc, i;
+    u64 after[STREAM_MAX_PENDING + 1];
+    u8 t[16];
+    if (!s) return fail(UAES_E_BAD_ARGUMENT, "null stream", 0);
+    if (s->kind == STREAM_CTR) return 0;
+    for (i = 0; i < s->npending; ++i) after[i] = s->pos_blocks - s->end_block[i];
+    rc = uaes_gcm_combine(s->keybits, s->key, s->nonce, s->aad, s->aadlen, &s->partial[0][0], after,
+                          s->npending, s->total_len, t);
+    if (rc) return rc;
+    if (!s->decrypt) { memcpy(tag, t, 16); return 0; }
+    return memcmp(t, tag, 16) ? UAES_AUTH_ERROR : 0;
+}
+
 /* ------------------------------------------------------------------ synthetic data */
 
 int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t nwords)

@@ -102,6 +102,10 @@ int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int enc
                     const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
                     const void *in, void *out, u64 len, void *tag_out, void *work, void *stream);
 
+/* streaming GCM: sum_r partial[r] * H^after[r] (16 bytes, device) for up to 31 shard contributions */
+int uaes_launch_gcm_fold(const uaes_keysched *ks, const void *partials_dev, const void *after_dev,
+                         unsigned nshards, void *out_dev, void *stream);
+
 /* CCM over a batch of independent messages, one per lane (uaes_batch.cuh); msgs_dev = device array
  * of uaes_msg records, result fields are written by the kernel */
 int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void *msgs_dev, u64 n,

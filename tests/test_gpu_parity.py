@@ -664,3 +664,62 @@ def test_eax_siv_batch_matches_oracle(uaes, orc, torch, mode, bits, seed, n, max
             assert back[m.in_off:m.in_off + m.len] == pt[m.in_off:m.in_off + m.len], i
         elif mode == "eax":                               # untouched on failure
             assert back[m.in_off:m.in_off + m.len] == b"\xdd" * m.len, i
+
+
+# ---------------------------------------------------------------- streaming
+
+@pytest.mark.parametrize("bits", [128, 256])
+def test_streaming_gcm_and_ctr_match_one_shot(uaes, orc, torch, bits):
+    import random
+    r = random.Random(bits)
+    key, nonce, aad = rnd(f"st-k{bits}", bits // 8), rnd(f"st-n{bits}", 12), rnd(f"st-a{bits}", 45)
+    n = 3 * (1 << 20) + 37
+    data = rnd(f"st-d{bits}", n)
+    want = orc.gcm_encrypt(key, nonce, aad, data)
+    # 70 pieces (more than the 30 contributions kept before a fold), all but the last multiples of 16
+    cuts = sorted(r.sample(range(1, n // 16), 69))
+    edges = [0] + [16 * c for c in cuts] + [n]
+    st = uaes.Stream(bits, key, nonce, aad)
+    out = bytearray(n)
+    src = dev(torch, data)
+    dst = dev(torch, b"", pad=n)
+    for i, (a, b) in enumerate(zip(edges, edges[1:])):
+        if i % 2:                                        # alternate host and device buffers
+            piece = ctypes.create_string_buffer(b - a)
+            st.update(data[a:b], b - a, piece)
+            out[a:b] = piece.raw
+        else:
+            st.update(src[a:], b - a, dst[a:])
+            torch.cuda.synchronize()
+            out[a:b] = host(dst, a, b)
+    tag = st.final()
+    st.close()
+    assert bytes(out) == want[:-16] and tag == want[-16:]
+    # decrypting stream: right tag, wrong tag
+    for forged in (False, True):
+        st = uaes.Stream(bits, key, nonce, aad, decrypt=True)
+        back = bytearray(n)
+        for a, b in zip(edges, edges[1:]):
+            piece = ctypes.create_string_buffer(b - a)
+            st.update(want[a:b], b - a, piece)
+            back[a:b] = piece.raw
+        t = bytearray(want[-16:])
+        t[0] ^= forged
+        assert st.final(bytes(t)) == (0x1A if forged else 0)
+        st.close()
+        assert bytes(back) == data
+    # only the last piece may be ragged
+    st = uaes.Stream(bits, key, nonce, aad)
+    st.update(data[:20], 20, ctypes.create_string_buffer(20))
+    with pytest.raises(uaes.UaesError):
+        st.update(data[20:36], 16, ctypes.create_string_buffer(16))
+    st.close()
+    # CTR
+    st = uaes.Stream(bits, key, nonce, gcm=False)
+    out = bytearray(n)
+    for a, b in zip(edges, edges[1:]):
+        piece = ctypes.create_string_buffer(b - a)
+        st.update(data[a:b], b - a, piece)
+        out[a:b] = piece.raw
+    st.close()
+    assert bytes(out) == orc.ctr(key, nonce, data)
