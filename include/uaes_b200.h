@@ -174,7 +174,7 @@ int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
 typedef struct uaes_msg {
     uaes_u64 in_off, out_off, aad_off;
     unsigned int len, aad_len;         /* payload bytes (without the tag), associated-data bytes */
-    uaes_u8  nonce[16];                /* CCM: the first 11 bytes; EAX: 16 bytes; SIV: unused */
+    uaes_u8  nonce[16];                /* CCM: the first 11 bytes; GCM: 12; EAX: 16; SIV: unused */
     int      result;
     unsigned int reserved;
 } uaes_msg;
@@ -197,6 +197,12 @@ int uaes_eax_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size
 int uaes_siv_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
                            const void *aad, const void *in, void *out);
 int uaes_siv_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+/* small-packet GCM (12-byte nonces, micro_aes.c:1164-1212): same layout as CCM; decrypt authenticates
+ * first and leaves out untouched on UAES_AUTH_ERROR.  For few large messages use uaes_gcm_encrypt. */
+int uaes_gcm_encrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
+                           const void *aad, const void *in, void *out);
+int uaes_gcm_decrypt_batch(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n,
                            const void *aad, const void *in, void *out);
 /* one message with the reference's argument lists (micro_aes.c:1268-1314, 1564-1648, 1372-1410):
  * a batch of one, i.e. ONE GPU lane -- correct and table-driven, but no faster than a CPU core;

@@ -65,6 +65,8 @@ UAES_ABI = {
     "uaes_eax_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
     "uaes_siv_encrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
     "uaes_siv_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_gcm_encrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
+    "uaes_gcm_decrypt_batch": (_int, [_int, _cp, _vp, _sz, _vp, _vp, _vp]),
     "uaes_eax_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_eax_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp]),
     "uaes_siv_encrypt": (_int, [_int, _cp, _vp, _sz, _vp, _sz, _vp, _vp]),

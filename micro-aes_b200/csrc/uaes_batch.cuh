@@ -1,5 +1,5 @@
 // uaes_batch.cuh -- many independent messages per launch, ONE MESSAGE PER LANE:
-// CCM, EAX and SIV.
+// CCM, EAX, SIV and small-packet GCM.
 //
 // Their MACs -- CCM's CBC-MAC (micro_aes.c:1222-1256), the OMACs of EAX (:1531-1550) and the CMACs
 // inside SIV's S2V (:1325-1359) -- are serial chains M <- E(M ^ X_i) inside one message (xMac with
@@ -12,6 +12,7 @@
 // accesses, anything else goes word- or byte-wise).
 #pragma once
 #include "uaes_core.cuh"
+#include "uaes_gf128.cuh"
 
 namespace uaes {
 
@@ -350,10 +351,90 @@ __global__ void __launch_bounds__(kBatchThreads, 1) siv_batch_kernel(const __gri
     }
 }
 
+// ---------------------------------------------------------------- GCM (micro_aes.c:1124-1213)
+// Small-packet GCM: the lane runs the message's CTR and its GHASH chain G <- H * (G ^ X_i)
+// (xMac with mulGF128, :551-570, 476-493).  The per-block product is the carry-less multiply built
+// from integer multiplies (gf_mul_fast, uaes_gf128.cuh): its 144 multiplies run on the FMA pipe
+// next to the cipher's lookups, and no GHASH table has to be built per message.
+__device__ __forceinline__ void ghash_step(Gf &g, const Gf &H, const Blk &x)
+{
+    const Gf v = gf_from_words(x.w[0], x.w[1], x.w[2], x.w[3]);
+    g.hi ^= v.hi; g.lo ^= v.lo;
+    g = gf_mul_fast(g, H);
+}
+
+__device__ __forceinline__ void ghash_bytes(Gf &g, const Gf &H, const uint8_t *p, uint32_t n)
+{
+    for (uint32_t o = 0; o < n; o += 16) ghash_step(g, H, load_bytes(p + o, n - o < 16 ? n - o : 16));
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kBatchThreads, 1) gcm_batch_kernel(const __grid_constant__ BatchArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.ks.w;
+    const uint64_t stride = (uint64_t)gridDim.x * kBatchThreads;
+    Blk h = {{0, 0, 0, 0}};
+    enc_block<NR>(lb, h.w[0], h.w[1], h.w[2], h.w[3], rk);        // H = E(0), :1144
+    const Gf H = gf_from_words(h.w[0], h.w[1], h.w[2], h.w[3]);
+
+    for (uint64_t mi = (uint64_t)blockIdx.x * kBatchThreads + threadIdx.x; mi < a.n; mi += stride) {
+        const BatchMsg d = a.msgs[mi];
+        const uint8_t *src = a.in + d.in_off;
+        uint8_t *dst = a.out + d.out_off;
+        Blk j0;                                                   // nonce || 00000001, :1150-1151
+        j0.w[0] = (uint32_t)d.nonce[0] | (uint32_t)d.nonce[1] << 8 | (uint32_t)d.nonce[2] << 16 | (uint32_t)d.nonce[3] << 24;
+        j0.w[1] = (uint32_t)d.nonce[4] | (uint32_t)d.nonce[5] << 8 | (uint32_t)d.nonce[6] << 16 | (uint32_t)d.nonce[7] << 24;
+        j0.w[2] = (uint32_t)d.nonce[8] | (uint32_t)d.nonce[9] << 8 | (uint32_t)d.nonce[10] << 16 | (uint32_t)d.nonce[11] << 24;
+        j0.w[3] = 0x01000000u;
+        Gf g{0, 0};
+        ghash_bytes(g, H, a.aad + d.aad_off, d.aad_len);          // gHash, :1134
+        if (a.decrypt) ghash_bytes(g, H, src, d.len);             // :1199: over the received ciphertext
+        else {
+            uint32_t ctr = 2;                                     // CCM_GCM pre-increment: J0 + 1, :939-941
+            for (uint32_t o = 0; o < d.len; o += 16, ++ctr) {
+                const uint32_t nb = d.len - o < 16 ? d.len - o : 16;
+                const Blk x = load_bytes(src + o, nb);
+                Blk y = j0;
+                y.w[3] = bswap32(ctr);
+                enc_block<NR>(lb, y.w[0], y.w[1], y.w[2], y.w[3], rk, x.w[0], x.w[1], x.w[2], x.w[3]);
+                if (nb < 16) {                                    // GHASH sees the ciphertext zero padded
+                    const uint32_t keep = nb & 3 ? (1u << (8 * (nb & 3))) - 1 : 0;
+                    for (uint32_t i = 0; i < 4; ++i)
+                        if (i > (nb >> 2)) y.w[i] = 0; else if (i == (nb >> 2)) y.w[i] &= keep;
+                }
+                store_bytes(dst + o, y, nb);
+                ghash_step(g, H, y);
+            }
+        }
+        g.hi ^= (uint64_t)d.aad_len * 8; g.lo ^= (uint64_t)d.len * 8;      // length block, :1130-1132
+        g = gf_mul_fast(g, H);
+        Blk tag = j0;
+        enc_block<NR>(lb, tag.w[0], tag.w[1], tag.w[2], tag.w[3], rk);    // E(J0), :1173
+        Blk gw;
+        gf_to_words(g, gw.w[0], gw.w[1], gw.w[2], gw.w[3]);
+        xor_blk(tag, gw);
+        if (!a.decrypt) {
+            store_bytes(dst + d.len, tag, 16);
+            a.msgs[mi].result = 0;
+        } else {                                                  // :1204-1209: verify, then decrypt
+            const Blk got = load_bytes(src + d.len, 16);
+            const uint32_t diff = (got.w[0] ^ tag.w[0]) | (got.w[1] ^ tag.w[1]) | (got.w[2] ^ tag.w[2]) | (got.w[3] ^ tag.w[3]);
+            a.msgs[mi].result = diff ? 0x1A : 0;
+            if (!diff) {
+                Blk c0 = j0;
+                c0.w[3] = 0x02000000u;                            // J0 + 1
+                ctr_walk<NR>(lb, rk, c0, src, dst, d.len);
+            }
+        }
+    }
+}
+
 template <int NR, int MODE>
 static cudaError_t launch_batch_nr(const BatchArgs &a, cudaStream_t st)
 {
-    auto kernel = MODE == 1 ? eax_batch_kernel<NR> : siv_batch_kernel<NR>;
+    auto kernel = MODE == 1 ? eax_batch_kernel<NR> : MODE == 2 ? siv_batch_kernel<NR> : gcm_batch_kernel<NR>;
     cudaError_t e = opt_in_smem(kernel);
     if (e != cudaSuccess) return e;
     const uint64_t need = (a.n + kBatchThreads - 1) / kBatchThreads, sms = (uint64_t)sm_count();
@@ -393,7 +474,7 @@ extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void 
     return (int)cudaErrorInvalidValue;
 }
 
-// mode: 1 = EAX (ks), 2 = SIV (ks = S2V key, ks2 = CTR key)
+// mode: 1 = EAX (ks), 2 = SIV (ks = S2V key, ks2 = CTR key), 3 = GCM (ks)
 extern "C" int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt,
                                      void *msgs_dev, u64 n, const void *aad, const void *in, void *out, void *stream)
 {
@@ -411,6 +492,9 @@ extern "C" int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const ua
     case 42: return (int)uaes::launch_batch_nr<10, 2>(a, st);
     case 50: return (int)uaes::launch_batch_nr<12, 2>(a, st);
     case 58: return (int)uaes::launch_batch_nr<14, 2>(a, st);
+    case 43: return (int)uaes::launch_batch_nr<10, 3>(a, st);
+    case 51: return (int)uaes::launch_batch_nr<12, 3>(a, st);
+    case 59: return (int)uaes::launch_batch_nr<14, 3>(a, st);
     }
     return (int)cudaErrorInvalidValue;
 }

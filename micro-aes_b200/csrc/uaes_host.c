@@ -868,6 +868,7 @@ int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
 #define BATCH_CCM 0
 #define BATCH_EAX 1
 #define BATCH_SIV 2
+#define BATCH_GCM 3
 
 static int launch_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt, void *msgs_dev,
                         u64 n, const void *aad, const void *in, void *out, void *stream)
@@ -952,6 +953,8 @@ BATCH_ENTRY(uaes_eax_encrypt_batch, BATCH_EAX, 0)
 BATCH_ENTRY(uaes_eax_decrypt_batch, BATCH_EAX, 1)
 BATCH_ENTRY(uaes_siv_encrypt_batch, BATCH_SIV, 0)
 BATCH_ENTRY(uaes_siv_decrypt_batch, BATCH_SIV, 1)
+BATCH_ENTRY(uaes_gcm_encrypt_batch, BATCH_GCM, 0)
+BATCH_ENTRY(uaes_gcm_decrypt_batch, BATCH_GCM, 1)
 
 /* one message with the reference's argument list = a batch of one */
 static int mac_single(int mode, int keybits, const u8 *key, const u8 *nonce, size_t noncelen, const void *aad,

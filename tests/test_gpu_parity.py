@@ -620,7 +620,7 @@ def test_eax_siv_reference_vectors(uaes, orc):
     assert a.__class__(128).AES_EAX_decrypt(key, H(m["iv16"]), aad, bytes(enc)) == (0x1A, b"\xcc" * len(pt))
 
 
-@pytest.mark.parametrize("mode", ["eax", "siv"])
+@pytest.mark.parametrize("mode", ["eax", "siv", "gcm"])
 @pytest.mark.parametrize("bits,seed,n,max_len,max_aad,align", [(128, 11, 600, 300, 40, 1), (256, 12, 2000, 100, 20, 16),
                                                                (192, 13, 48, 5000, 3000, 4)])
 def test_eax_siv_batch_matches_oracle(uaes, orc, torch, mode, bits, seed, n, max_len, max_aad, align):
@@ -631,8 +631,12 @@ def test_eax_siv_batch_matches_oracle(uaes, orc, torch, mode, bits, seed, n, max
         for j in range(16):
             msgs[i].nonce[j] = nonce[j]
     pt, aad = bytearray(rnd(f"{mode}b-p{seed}", in_sz)), rnd(f"{mode}b-a{seed}", max(aad_sz, 1))
-    enc1 = (lambda m: orc.eax_encrypt(key, bytes(m.nonce), aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len]))) \
-        if mode == "eax" else (lambda m: orc.siv_encrypt(key, aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len])))
+    if mode == "eax":
+        enc1 = lambda m: orc.eax_encrypt(key, bytes(m.nonce), aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len]))
+    elif mode == "gcm":
+        enc1 = lambda m: orc.gcm_encrypt(key, bytes(m.nonce[:12]), aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len]))
+    else:
+        enc1 = lambda m: orc.siv_encrypt(key, aad[m.aad_off:m.aad_off + m.aad_len], bytes(pt[m.in_off:m.in_off + m.len]))
     want = bytearray(b"\xee" * out_sz)
     for m in msgs:
         want[m.out_off:m.out_off + m.len + 16] = enc1(m)
@@ -654,15 +658,15 @@ def test_eax_siv_batch_matches_oracle(uaes, orc, torch, mode, bits, seed, n, max
             dec[i].nonce[j] = m.nonce[j]
     ct = bytearray(want)
     forged = set(range(0, n, 5))
-    for i in forged:                                      # EAX: the tag at the end; SIV: the IV in front
-        ct[msgs[i].out_off + (msgs[i].len + 7 if mode == "eax" else 3)] ^= 0x04
+    for i in forged:                                      # EAX, GCM: the tag at the end; SIV: the IV in front
+        ct[msgs[i].out_off + (3 if mode == "siv" else msgs[i].len + 7)] ^= 0x04
     back = bytearray(b"\xdd" * in_sz)
     assert uaes.ccm_batch(bits, key, dec, n, aad, ct, back, decrypt=True, mode=mode) == 0x1A
     for i, m in enumerate(msgs):
         assert dec[i].result == (0x1A if i in forged else 0), i
         if i not in forged:
             assert back[m.in_off:m.in_off + m.len] == pt[m.in_off:m.in_off + m.len], i
-        elif mode == "eax":                               # untouched on failure
+        elif mode in ("eax", "gcm"):                      # untouched on failure
             assert back[m.in_off:m.in_off + m.len] == b"\xdd" * m.len, i
 
 
