@@ -727,3 +727,32 @@ def test_streaming_gcm_and_ctr_match_one_shot(uaes, orc, torch, bits):
         out[a:b] = piece.raw
     st.close()
     assert bytes(out) == orc.ctr(key, nonce, data)
+
+
+def test_streaming_edge_cases(uaes, orc):
+    key, nonce, aad = rnd("ste-k", 16), rnd("ste-n", 12), rnd("ste-a", 20)
+    # no update at all: the tag of the empty message (with and without AAD)
+    for a in (aad, b""):
+        st = uaes.Stream(128, key, nonce, a)
+        assert st.final() == orc.gcm_encrypt(key, nonce, a, b"")
+        st.close()
+    # one ragged update, zero-length updates in between
+    data = rnd("ste-d", 1000 + 7)
+    st = uaes.Stream(128, key, nonce, aad)
+    out = ctypes.create_string_buffer(len(data))
+    st.update(b"", 0, out)
+    st.update(data, len(data), out)
+    st.update(b"", 0, out)
+    assert out.raw + st.final() == orc.gcm_encrypt(key, nonce, aad, data)
+    st.close()
+    # exactly 31 and 61 pieces: the fold boundary of the pending contributions
+    for pieces in (30, 31, 61):
+        data = rnd(f"ste-p{pieces}", 16 * pieces * 3)
+        st = uaes.Stream(128, key, nonce, aad)
+        got = b""
+        for i in range(pieces):
+            o = ctypes.create_string_buffer(48)
+            st.update(data[48 * i:48 * i + 48], 48, o)
+            got += o.raw
+        assert got + st.final() == orc.gcm_encrypt(key, nonce, aad, data), pieces
+        st.close()
