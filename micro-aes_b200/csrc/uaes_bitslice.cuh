@@ -204,6 +204,31 @@ UAES_HD void bs_uniform_words(TE te, uint32_t s0, uint32_t s1, uint32_t s2, uint
     w[5] = te(0, C3 & 255) ^ te(3, C2 >> 24) ^ rk[11];
 }
 
+// ---- the general form: any 32 blocks (ECB-like modes with data-dependent input, e.g. XTS) ------
+// All NR + 1 round keys as planes; the state comes from four 32x32 transposes of the blocks' words.
+struct BsKeyPlanesFull {
+    uint32_t k[kBsMaxRounds + 1][128];      // round keys 0..NR
+};
+
+// rijndaelEncrypt (micro_aes.c:242-259) on 32 blocks held as planes
+template <int NR>
+UAES_HD void bs_encrypt_planes(uint32_t s[128], const BsKeyPlanesFull &kp)
+{
+#pragma unroll
+    for (int p = 0; p < 128; ++p) s[p] ^= kp.k[0][p];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 1; r < NR; ++r) bs_round(s, kp.k[r]);
+    bs_last_round(s, kp.k[NR]);
+}
+
+UAES_HD void bs_make_key_planes_full(const uint32_t *rk, int rounds, BsKeyPlanesFull *kp)
+{
+    for (int r = 0; r <= rounds; ++r)
+        for (int p = 0; p < 128; ++p) kp->k[r][p] = bs_mask(rk[4 * r + p / 32], p % 32);
+}
+
 // host-side (uaes_host.c does the same in C): key planes from the expanded key
 UAES_HD void bs_make_key_planes(const uint32_t *rk, int rounds, BsKeyPlanes *kp)
 {

@@ -202,6 +202,154 @@ static cudaError_t launch_xts_sectors_nr(const XtsSectorArgs &a, cudaStream_t st
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- batched sectors, with the co-runner
+//
+// Encryption of 512-byte sectors (32 blocks): the same two-kinds-of-warps kernel as ctr_kernel.
+// 12 table-driven warps (two sectors in flight each) keep the lookup pipe at its roof; one warpgroup
+// of bitsliced warps (uaes_bitslice.cuh, general form) encrypts tiles of 32 sectors on the ALU pipe:
+// lane l, slot t <-> block l of sector t, so every load / store of a slot is the sector's coalesced
+// 512-byte row.  The tweaks stay in the ordinary layout: T_0 of sector t is one table-driven
+// encryption on lane t, T_0 * alpha^l is a shift, and the XEX whitening happens on the blocks'
+// words before the transposes into planes and after the transposes back.
+struct XtsHybridArgs {
+    XtsSectorArgs x;             // sector_blocks == 32
+    uint64_t tt_tiles;           // tiles [0, tt_tiles) of 32 sectors: table-driven warps
+    uint64_t ntiles;             // the rest: bitsliced warps
+    BsKeyPlanesFull bs;          // K1 as planes
+};
+
+template <int NR>
+__device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint32_t lb, uint64_t t0, uint64_t t1)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t tile = t0; tile < t1; ++tile) {
+        const uint64_t sec0 = tile * 32;
+        const uint64_t left = a.x.nsectors - sec0;
+        const int nsec = left < 32 ? (int)left : 32;
+        // T_0 of sector sec0 + lane (micro_aes.c:1017-1027)
+        const uint64_t sec = a.x.first_sector + sec0 + lane;
+        uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
+        enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        auto tweak_of = [&](int t, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+            Tweak tw;
+            tw.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, t) << 32 | __shfl_sync(0xffffffffu, e0, t);
+            tw.hi = (uint64_t)__shfl_sync(0xffffffffu, e3, t) << 32 | __shfl_sync(0xffffffffu, e2, t);
+            tweak_words(xts_shl(tw, lane), w0, w1, w2, w3);
+        };
+        const uint4 *src = a.x.in + sec0 * 32 + lane;
+        uint4 *dst = a.x.out + sec0 * 32 + lane;
+        uint32_t s[128];
+#pragma unroll
+        for (int tb = 0; tb < 32; tb += 8) {                     // loads in batches of 8 rows
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tb + i < nsec ? ld_stream(src + (tb + i) * 32) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t w0, w1, w2, w3;
+                tweak_of(tb + i, w0, w1, w2, w3);
+                s[tb + i] = v[i].x ^ w0; s[32 + tb + i] = v[i].y ^ w1;
+                s[64 + tb + i] = v[i].z ^ w2; s[96 + tb + i] = v[i].w ^ w3;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+        bs_encrypt_planes<NR>(s, a.bs);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            uint32_t w0, w1, w2, w3;
+            tweak_of(t, w0, w1, w2, w3);
+            if (t < nsec) st_stream(dst + t * 32, make_uint4(s[t] ^ w0, s[32 + t] ^ w1, s[64 + t] ^ w2, s[96 + t] ^ w3));
+        }
+    }
+}
+
+constexpr int kXtsTtThreads = 384;
+constexpr int kXtsDefaultShare = 148;
+
+template <int NR>
+__global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_xts_tables<true>(dyn);
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kTtWarps = kXtsTtThreads / 32;
+    constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;      // 128
+    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;   // 200
+
+    if (threadIdx.x >= kXtsTtThreads) {
+        reg_inc<kBsRegs>();
+        const uint64_t nbs = a.ntiles - a.tt_tiles;
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        const uint64_t per = (nbs + nw - 1) / nw;
+        const uint64_t p0 = gw * per < nbs ? gw * per : nbs;
+        const uint64_t p1 = p0 + per < nbs ? p0 + per : nbs;
+        xts_bitsliced_warp<NR>(a, lb, a.tt_tiles + p0, a.tt_tiles + p1);
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    // table-driven warps: a contiguous run of tiles each, two sectors in flight
+    const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+    const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
+    const uint64_t per = (a.tt_tiles + nw - 1) / nw;
+    const uint64_t q0 = gw * per < a.tt_tiles ? gw * per : a.tt_tiles;
+    const uint64_t q1 = q0 + per < a.tt_tiles ? q0 + per : a.tt_tiles;
+    const uint32_t *k1 = a.x.k1.w;
+    for (uint64_t tile = q0; tile < q1; ++tile) {
+        const uint64_t sec0 = tile * 32;
+        const uint64_t left = a.x.nsectors - sec0;
+        const int nsec = left < 32 ? (int)left : 32;
+        const uint64_t sec = a.x.first_sector + sec0 + lane;
+        uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
+        enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        const uint4 *src = a.x.in + sec0 * 32 + lane;
+        uint4 *dst = a.x.out + sec0 * 32 + lane;
+        uint4 cur[2], nxt[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) cur[i] = i < nsec ? ld_stream(src + i * 32) : make_uint4(0, 0, 0, 0);
+        for (int sct = 0; sct < nsec; sct += 2) {
+            uint32_t st[2][4];
+            uint4 tw[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                nxt[i] = sct + 2 + i < nsec ? ld_stream(src + (sct + 2 + i) * 32) : make_uint4(0, 0, 0, 0);
+                Tweak t;
+                t.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, (sct + i) & 31) << 32 | __shfl_sync(0xffffffffu, e0, (sct + i) & 31);
+                t.hi = (uint64_t)__shfl_sync(0xffffffffu, e3, (sct + i) & 31) << 32 | __shfl_sync(0xffffffffu, e2, (sct + i) & 31);
+                tweak_words(xts_shl(t, lane), tw[i].x, tw[i].y, tw[i].z, tw[i].w);
+                st[i][0] = cur[i].x ^ tw[i].x ^ k1[0]; st[i][1] = cur[i].y ^ tw[i].y ^ k1[1];
+                st[i][2] = cur[i].z ^ tw[i].z ^ k1[2]; st[i][3] = cur[i].w ^ tw[i].w ^ k1[3];
+            }
+            enc_finish_n<NR, 1, 2>(lb, st, k1, tw);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (sct + i < nsec) st_stream(dst + (sct + i) * 32, make_uint4(st[i][0], st[i][1], st[i][2], st[i][3]));
+                cur[i] = nxt[i];
+            }
+        }
+    }
+}
+
+template <int NR>
+static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tiles, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(xts_sectors_hybrid_kernel<NR>);
+    if (e != cudaSuccess) return e;
+    static XtsHybridArgs a;                              // 8 KB of planes: keep it off the stack
+    a.x = x;
+    a.ntiles = (x.nsectors + 31) / 32;
+    a.tt_tiles = a.ntiles - bs_tiles;
+    bs_make_key_planes_full(x.k1.w, NR, &a.bs);
+    const uint64_t need = (a.ntiles + 15) / 16, sms = (uint64_t)sm_count();
+    xts_sectors_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 template <int NR, bool ENC>
 static cudaError_t launch_xts_unit_nr(const XtsUnitArgs &a, cudaStream_t st)
 {
@@ -226,6 +374,20 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
     a.first_sector = first_sector; a.sector_blocks = sector_blocks; a.nsectors = nsectors;
     a.in = (const uint4 *)in; a.out = (uint4 *)out;
     cudaStream_t st = (cudaStream_t)stream;
+    // 512-byte sectors, encryption, enough of them: table-driven warps + bitsliced co-runner
+    // (threshold and on/off are the CTR kernel's knobs, uaes_ctr_tuning; the share is XTS's own:
+    // measured 549 / 565 / 577 / 584 / 566 / 519 GiB/s at 0 / 60 / 100 / 140 / 180 / 220 per 1024 for
+    // AES-256, profiles/r1_xts_hybrid_sweep.txt; a non-default CTR share, as the tests set, wins)
+    ctr_tuning_init();
+    if (encrypt && sector_blocks == 32 && g_ctr_share > 0 && (long long)(nsectors * 32) >= g_ctr_bs_min) {
+        const uint64_t ntiles = (nsectors + 31) / 32;
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_XTS_BS_PERMILLE", kXtsDefaultShare);
+        const uint64_t bs_tiles = ntiles * (uint64_t)share / 1024;
+        if (bs_tiles > 0) {
+            if (ks1->rounds == 10) return (int)launch_xts_hybrid_nr<10>(a, bs_tiles, st);
+            if (ks1->rounds == 14) return (int)launch_xts_hybrid_nr<14>(a, bs_tiles, st);
+        }
+    }
     switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
     case 21: return (int)launch_xts_sectors_nr<10, true>(a, st);
     case 20: return (int)launch_xts_sectors_nr<10, false>(a, st);

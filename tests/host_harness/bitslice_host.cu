@@ -42,4 +42,31 @@ extern "C" int bs_host_pass(const uint32_t *rk, int rounds, const uint8_t *block
     return 0;
 }
 
+// 32 arbitrary blocks (512 bytes) through the general bitsliced path: words -> planes (four 32x32
+// transposes), all rounds, planes -> words.  in/out: block t at byte 16*t.
+template <int NR>
+static void ecb32(const BsKeyPlanesFull &kp, const uint8_t *in, uint8_t *out)
+{
+    uint32_t s[128];
+    for (int t = 0; t < 32; ++t)
+        for (int c = 0; c < 4; ++c) memcpy(&s[32 * c + t], in + 16 * t + 4 * c, 4);
+    for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+    bs_encrypt_planes<NR>(s, kp);
+    for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+    for (int t = 0; t < 32; ++t)
+        for (int c = 0; c < 4; ++c) memcpy(out + 16 * t + 4 * c, &s[32 * c + t], 4);
+}
+
+extern "C" int bs_host_ecb32(const uint32_t *rk, int rounds, const uint8_t *in, uint8_t *out)
+{
+    static BsKeyPlanesFull kp;
+    bs_make_key_planes_full(rk, rounds, &kp);
+    switch (rounds) {
+    case 10: ecb32<10>(kp, in, out); return 0;
+    case 12: ecb32<12>(kp, in, out); return 0;
+    case 14: ecb32<14>(kp, in, out); return 0;
+    }
+    return 1;
+}
+
 extern "C" int bs_host_sbox_lut3_count(void) { return kSboxLut3Count; }

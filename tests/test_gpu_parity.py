@@ -211,6 +211,25 @@ def test_xts_sectors(uaes, orc, bits):
         assert back.raw == data
 
 
+@pytest.mark.parametrize("bits", [128, 256])
+def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
+    """512-byte sector encryption with the ALU co-runner warps forced on for small calls, at several
+    splits between table-driven and bitsliced tiles, ragged last tiles, sector numbers across 2^32"""
+    try:
+        for share, first, ns in ((1024, 0, 33), (512, 5, 100), (300, (1 << 32) - 40, 1000), (1024, 1 << 40, 64),
+                                 (700, 9, 4096 + 7), (1, 3, 2048), (1024, 0, 1)):
+            uaes.ctr_tuning(-1, share, 0)
+            keys, data = rnd(f"xh-k{bits}{first}", bits // 4), rnd(f"xh-d{bits}{first}{ns}", 512 * ns)
+            out = ctypes.create_string_buffer(len(data))
+            uaes.xts_sectors(bits, keys, first, 512, data, len(data), out, True)
+            assert (0, out.raw) == orc.xts_sectors(keys, first, 512, data), (share, first, ns)
+            back = ctypes.create_string_buffer(len(data))
+            uaes.xts_sectors(bits, keys, first, 512, out.raw, len(data), back, False)
+            assert back.raw == data
+    finally:
+        uaes.ctr_tuning(385, 190, 1 << 20)
+
+
 @pytest.mark.parametrize("bits", [128, 192, 256])
 def test_gcm_sizes(uaes, orc, bits):
     a = uaes.MicroAES(bits)

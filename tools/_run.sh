@@ -1,4 +1,7 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "streaming" > gpurun_out/pytest_stream.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_stream.log
-tail -25 gpurun_out/pytest_stream.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
+mkdir -p gpurun_out; rm -f gpurun_out/bench_xtsh2.jsonl
+for r in 120 130 150 160; do
+  echo "xts256 share=$r" >> gpurun_out/bench_xtsh2.jsonl
+  UAES_XTS_BS_PERMILLE=$r python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --workload xts256 >> gpurun_out/bench_xtsh2.jsonl 2>> gpurun_out/bench_err.log
+done
+timeout 1700 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
