@@ -223,6 +223,78 @@ UAES_HD void bs_encrypt_planes(uint32_t s[128], const BsKeyPlanesFull &kp)
     bs_last_round(s, kp.k[NR]);
 }
 
+// ---- decryption: the equivalent inverse cipher on planes ---------------------------------------
+// dk = the schedule the table-driven decrypt kernels use (uaes_host.c invert_schedule): dk[0] =
+// round key NR, dk[r] = InvMixColumns(round key NR - r), dk[NR] = round key 0; with it every round is
+// InvShiftRows, InvSubBytes, InvMixColumns, AddRoundKey -- the same result as the reference's
+// straight inverse cipher (micro_aes.c:315-332; FIPS-197 5.3.5).
+// InvMixColumns = MixColumns after the pre-mix  a0 ^= u, a2 ^= u, a1 ^= v, a3 ^= v  with
+// u = 4 (a0 ^ a2), v = 4 (a1 ^ a3)  (the {0e,0b,0d,09} circulant = {02,03,01,01} x {05,00,04,00});
+// times-4 on planes: [x6, x6^x7, x0^x7, x1^x6, x2^x6^x7, x3^x7, x4, x5].
+UAES_HD void bs_times4(const uint32_t x[8], uint32_t y[8])
+{
+    const uint32_t w = x[6] ^ x[7];
+    y[0] = x[6]; y[1] = w; y[2] = x[0] ^ x[7]; y[3] = x[1] ^ x[6];
+    y[4] = x[2] ^ w; y[5] = x[3] ^ x[7]; y[6] = x[4]; y[7] = x[5];
+}
+
+UAES_HD void bs_inv_mix_column(const uint32_t *a0, const uint32_t *a1, const uint32_t *a2,
+                               const uint32_t *a3, const uint32_t *k, uint32_t *out)
+{
+    uint32_t e[8], o[8], u[8], v[8], b[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] = a0[i] ^ a2[i]; o[i] = a1[i] ^ a3[i]; }
+    bs_times4(e, u);
+    bs_times4(o, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        b[0][i] = a0[i] ^ u[i]; b[1][i] = a1[i] ^ v[i]; b[2][i] = a2[i] ^ u[i]; b[3][i] = a3[i] ^ v[i];
+    }
+    bs_mix_column<0>(b[0], b[1], b[2], b[3], k, out);
+}
+
+UAES_HD void bs_inv_round(uint32_t s[128], const uint32_t *kp)
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sbox_inv_bitsliced(s + 8 * i);
+    uint32_t o[128];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)       // InvShiftRows: row r of column c comes from column c - r
+        bs_inv_mix_column(s + 8 * (4 * c), s + 8 * (4 * ((c + 3) & 3) + 1), s + 8 * (4 * ((c + 2) & 3) + 2),
+                          s + 8 * (4 * ((c + 1) & 3) + 3), kp + 32 * c, o + 32 * c);
+#pragma unroll
+    for (int p = 0; p < 128; ++p) s[p] = o[p];
+}
+
+UAES_HD void bs_inv_last_round(uint32_t s[128], const uint32_t *kp)
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sbox_inv_bitsliced(s + 8 * i);
+    uint32_t o[128];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                o[8 * (4 * c + r) + b] = s[8 * (4 * ((c + 4 - r) & 3) + r) + b] ^ kp[8 * (4 * c + r) + b];
+#pragma unroll
+    for (int p = 0; p < 128; ++p) s[p] = o[p];
+}
+
+// rijndaelDecrypt (micro_aes.c:315-332) on 32 blocks held as planes; kp = planes of dk[0..NR]
+template <int NR>
+UAES_HD void bs_decrypt_planes(uint32_t s[128], const BsKeyPlanesFull &kp)
+{
+#pragma unroll
+    for (int p = 0; p < 128; ++p) s[p] ^= kp.k[0][p];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 1; r < NR; ++r) bs_inv_round(s, kp.k[r]);
+    bs_inv_last_round(s, kp.k[NR]);
+}
+
 UAES_HD void bs_make_key_planes_full(const uint32_t *rk, int rounds, BsKeyPlanesFull *kp)
 {
     for (int r = 0; r <= rounds; ++r)

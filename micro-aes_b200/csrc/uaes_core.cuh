@@ -128,6 +128,26 @@ __device__ __forceinline__ void dec_block(uint32_t lb, uint32_t &s0, uint32_t &s
     s0 = o0; s1 = o1; s2 = o2; s3 = o3;
 }
 
+// N independent blocks, rounds interleaved (see enc_finish_n): out_i = D_K(s_i) ^ x_i
+template <int NR, int N>
+__device__ __forceinline__ void dec_block_n(uint32_t lb, uint32_t (&s)[N][4], const uint32_t *dk, const uint4 (&x)[N])
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) { s[i][0] ^= dk[0]; s[i][1] ^= dk[1]; s[i][2] ^= dk[2]; s[i][3] ^= dk[3]; }
+#pragma unroll
+    for (int r = 1; r < NR; ++r)
+#pragma unroll
+        for (int i = 0; i < N; ++i) dec_round(lb, s[i][0], s[i][1], s[i][2], s[i][3], dk + 4 * r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t o0 = dec_last_col(lb, s[i][0], s[i][3], s[i][2], s[i][1]) ^ dk[4 * NR + 0] ^ x[i].x;
+        const uint32_t o1 = dec_last_col(lb, s[i][1], s[i][0], s[i][3], s[i][2]) ^ dk[4 * NR + 1] ^ x[i].y;
+        const uint32_t o2 = dec_last_col(lb, s[i][2], s[i][1], s[i][0], s[i][3]) ^ dk[4 * NR + 2] ^ x[i].z;
+        const uint32_t o3 = dec_last_col(lb, s[i][3], s[i][2], s[i][1], s[i][0]) ^ dk[4 * NR + 3] ^ x[i].w;
+        s[i][0] = o0; s[i][1] = o1; s[i][2] = o2; s[i][3] = o3;
+    }
+}
+
 // ---------------------------------------------------------------- one-off blocks (no smem)
 
 // Byte-wise AES for the handful of blocks that run on ONE thread (GCM subkey H and E_K(J0), the

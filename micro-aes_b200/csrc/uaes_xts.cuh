@@ -204,7 +204,7 @@ static cudaError_t launch_xts_sectors_nr(const XtsSectorArgs &a, cudaStream_t st
 
 // ---------------------------------------------------------------- batched sectors, with the co-runner
 //
-// Encryption of 512-byte sectors (32 blocks): the same two-kinds-of-warps kernel as ctr_kernel.
+// 512-byte sectors (32 blocks), both directions: the same two-kinds-of-warps kernel as ctr_kernel.
 // 12 table-driven warps (two sectors in flight each) keep the lookup pipe at its roof; one warpgroup
 // of bitsliced warps (uaes_bitslice.cuh, general form) encrypts tiles of 32 sectors on the ALU pipe:
 // lane l, slot t <-> block l of sector t, so every load / store of a slot is the sector's coalesced
@@ -215,10 +215,10 @@ struct XtsHybridArgs {
     XtsSectorArgs x;             // sector_blocks == 32
     uint64_t tt_tiles;           // tiles [0, tt_tiles) of 32 sectors: table-driven warps
     uint64_t ntiles;             // the rest: bitsliced warps
-    BsKeyPlanesFull bs;          // K1 as planes
+    BsKeyPlanesFull bs;          // x.k1 (encryption schedule, or the inverse schedule) as planes
 };
 
-template <int NR>
+template <int NR, bool ENC>
 __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint32_t lb, uint64_t t0, uint64_t t1)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -229,7 +229,8 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
         // T_0 of sector sec0 + lane (micro_aes.c:1017-1027)
         const uint64_t sec = a.x.first_sector + sec0 + lane;
         uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
-        enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        else     enc_block_te0<NR, kOffT3>(lb, e0, e1, e2, e3, a.x.k2.w);
         auto tweak_of = [&](int t, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
             Tweak tw;
             tw.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, t) << 32 | __shfl_sync(0xffffffffu, e0, t);
@@ -254,7 +255,7 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
-        bs_encrypt_planes<NR>(s, a.bs);
+        if (ENC) bs_encrypt_planes<NR>(s, a.bs); else bs_decrypt_planes<NR>(s, a.bs);
 #pragma unroll
         for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
 #pragma unroll
@@ -269,11 +270,11 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
 constexpr int kXtsTtThreads = 384;
 constexpr int kXtsDefaultShare = 148;
 
-template <int NR>
+template <int NR, bool ENC>
 __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
-    const uint32_t lb = setup_xts_tables<true>(dyn);
+    const uint32_t lb = setup_xts_tables<ENC>(dyn);
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kXtsTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;      // 128
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
         const uint64_t per = (nbs + nw - 1) / nw;
         const uint64_t p0 = gw * per < nbs ? gw * per : nbs;
         const uint64_t p1 = p0 + per < nbs ? p0 + per : nbs;
-        xts_bitsliced_warp<NR>(a, lb, a.tt_tiles + p0, a.tt_tiles + p1);
+        xts_bitsliced_warp<NR, ENC>(a, lb, a.tt_tiles + p0, a.tt_tiles + p1);
         return;
     }
     reg_dec<kTtRegs>();
@@ -305,7 +306,8 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
         const int nsec = left < 32 ? (int)left : 32;
         const uint64_t sec = a.x.first_sector + sec0 + lane;
         uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
-        enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        else     enc_block_te0<NR, kOffT3>(lb, e0, e1, e2, e3, a.x.k2.w);
         const uint4 *src = a.x.in + sec0 * 32 + lane;
         uint4 *dst = a.x.out + sec0 * 32 + lane;
         uint4 cur[2], nxt[2];
@@ -321,10 +323,11 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
                 t.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, (sct + i) & 31) << 32 | __shfl_sync(0xffffffffu, e0, (sct + i) & 31);
                 t.hi = (uint64_t)__shfl_sync(0xffffffffu, e3, (sct + i) & 31) << 32 | __shfl_sync(0xffffffffu, e2, (sct + i) & 31);
                 tweak_words(xts_shl(t, lane), tw[i].x, tw[i].y, tw[i].z, tw[i].w);
-                st[i][0] = cur[i].x ^ tw[i].x ^ k1[0]; st[i][1] = cur[i].y ^ tw[i].y ^ k1[1];
-                st[i][2] = cur[i].z ^ tw[i].z ^ k1[2]; st[i][3] = cur[i].w ^ tw[i].w ^ k1[3];
+                st[i][0] = cur[i].x ^ tw[i].x; st[i][1] = cur[i].y ^ tw[i].y;
+                st[i][2] = cur[i].z ^ tw[i].z; st[i][3] = cur[i].w ^ tw[i].w;
+                if (ENC) { st[i][0] ^= k1[0]; st[i][1] ^= k1[1]; st[i][2] ^= k1[2]; st[i][3] ^= k1[3]; }
             }
-            enc_finish_n<NR, 1, 2>(lb, st, k1, tw);
+            if (ENC) enc_finish_n<NR, 1, 2>(lb, st, k1, tw); else dec_block_n<NR, 2>(lb, st, k1, tw);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (sct + i < nsec) st_stream(dst + (sct + i) * 32, make_uint4(st[i][0], st[i][1], st[i][2], st[i][3]));
@@ -334,10 +337,10 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
     }
 }
 
-template <int NR>
+template <int NR, bool ENC>
 static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tiles, cudaStream_t st)
 {
-    cudaError_t e = opt_in_smem(xts_sectors_hybrid_kernel<NR>);
+    cudaError_t e = opt_in_smem(xts_sectors_hybrid_kernel<NR, ENC>);
     if (e != cudaSuccess) return e;
     static XtsHybridArgs a;                              // 8 KB of planes: keep it off the stack
     a.x = x;
@@ -345,7 +348,7 @@ static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tile
     a.tt_tiles = a.ntiles - bs_tiles;
     bs_make_key_planes_full(x.k1.w, NR, &a.bs);
     const uint64_t need = (a.ntiles + 15) / 16, sms = (uint64_t)sm_count();
-    xts_sectors_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    xts_sectors_hybrid_kernel<NR, ENC><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -374,18 +377,27 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
     a.first_sector = first_sector; a.sector_blocks = sector_blocks; a.nsectors = nsectors;
     a.in = (const uint4 *)in; a.out = (uint4 *)out;
     cudaStream_t st = (cudaStream_t)stream;
-    // 512-byte sectors, encryption, enough of them: table-driven warps + bitsliced co-runner
+    // 512-byte sectors, enough of them: table-driven warps + bitsliced co-runner
     // (threshold and on/off are the CTR kernel's knobs, uaes_ctr_tuning; the share is XTS's own:
     // measured 549 / 565 / 577 / 584 / 566 / 519 GiB/s at 0 / 60 / 100 / 140 / 180 / 220 per 1024 for
     // AES-256, profiles/r1_xts_hybrid_sweep.txt; a non-default CTR share, as the tests set, wins)
     ctr_tuning_init();
-    if (encrypt && sector_blocks == 32 && g_ctr_share > 0 && (long long)(nsectors * 32) >= g_ctr_bs_min) {
+    if (sector_blocks == 32 && g_ctr_share > 0 && (long long)(nsectors * 32) >= g_ctr_bs_min) {
         const uint64_t ntiles = (nsectors + 31) / 32;
-        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_XTS_BS_PERMILLE", kXtsDefaultShare);
+        // Decryption: the bitsliced inverse cipher is correct (tests force it on) but does not pay: the
+        // table-driven decrypt rounds rotate half of their lookups on the ALU pipe (Td2/Td3 from
+        // Td0/Td1), so less of that pipe is idle and the co-runner costs more than it adds
+        // (558 -> 523 / 480 GiB/s at 30 / 100 per 1024).  Off unless asked for.
+        const int dflt = encrypt ? env_int("UAES_XTS_BS_PERMILLE", kXtsDefaultShare) : env_int("UAES_XTS_DEC_BS_PERMILLE", 0);
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : dflt;
         const uint64_t bs_tiles = ntiles * (uint64_t)share / 1024;
         if (bs_tiles > 0) {
-            if (ks1->rounds == 10) return (int)launch_xts_hybrid_nr<10>(a, bs_tiles, st);
-            if (ks1->rounds == 14) return (int)launch_xts_hybrid_nr<14>(a, bs_tiles, st);
+            switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
+            case 21: return (int)launch_xts_hybrid_nr<10, true>(a, bs_tiles, st);
+            case 20: return (int)launch_xts_hybrid_nr<10, false>(a, bs_tiles, st);
+            case 29: return (int)launch_xts_hybrid_nr<14, true>(a, bs_tiles, st);
+            case 28: return (int)launch_xts_hybrid_nr<14, false>(a, bs_tiles, st);
+            }
         }
     }
     switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {

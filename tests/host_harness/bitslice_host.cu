@@ -69,4 +69,49 @@ extern "C" int bs_host_ecb32(const uint32_t *rk, int rounds, const uint8_t *in, 
     return 1;
 }
 
+// decryption: dk = equivalent-inverse-cipher schedule built here from the encryption schedule
+static uint8_t gmul8(uint8_t a, uint8_t b)
+{
+    uint8_t r = 0;
+    for (int i = 0; i < 8; ++i) { if (b & 1) r ^= a; a = (uint8_t)((a << 1) ^ ((a >> 7) * 0x1b)); b >>= 1; }
+    return r;
+}
+
+static uint32_t inv_mix_word(uint32_t w)
+{
+    uint8_t a[4] = {(uint8_t)w, (uint8_t)(w >> 8), (uint8_t)(w >> 16), (uint8_t)(w >> 24)}, o[4];
+    for (int r = 0; r < 4; ++r)
+        o[r] = gmul8(a[r], 14) ^ gmul8(a[(r + 1) & 3], 11) ^ gmul8(a[(r + 2) & 3], 13) ^ gmul8(a[(r + 3) & 3], 9);
+    return (uint32_t)o[0] | (uint32_t)o[1] << 8 | (uint32_t)o[2] << 16 | (uint32_t)o[3] << 24;
+}
+
+template <int NR>
+static void ecb32_dec(const BsKeyPlanesFull &kp, const uint8_t *in, uint8_t *out)
+{
+    uint32_t s[128];
+    for (int t = 0; t < 32; ++t)
+        for (int c = 0; c < 4; ++c) memcpy(&s[32 * c + t], in + 16 * t + 4 * c, 4);
+    for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+    bs_decrypt_planes<NR>(s, kp);
+    for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+    for (int t = 0; t < 32; ++t)
+        for (int c = 0; c < 4; ++c) memcpy(out + 16 * t + 4 * c, &s[32 * c + t], 4);
+}
+
+extern "C" int bs_host_ecb32_decrypt(const uint32_t *rk, int rounds, const uint8_t *in, uint8_t *out)
+{
+    static BsKeyPlanesFull kp;
+    uint32_t dk[60];
+    for (int c = 0; c < 4; ++c) { dk[c] = rk[4 * rounds + c]; dk[4 * rounds + c] = rk[c]; }
+    for (int r = 1; r < rounds; ++r)
+        for (int c = 0; c < 4; ++c) dk[4 * r + c] = inv_mix_word(rk[4 * (rounds - r) + c]);
+    bs_make_key_planes_full(dk, rounds, &kp);
+    switch (rounds) {
+    case 10: ecb32_dec<10>(kp, in, out); return 0;
+    case 12: ecb32_dec<12>(kp, in, out); return 0;
+    case 14: ecb32_dec<14>(kp, in, out); return 0;
+    }
+    return 1;
+}
+
 extern "C" int bs_host_sbox_lut3_count(void) { return kSboxLut3Count; }

@@ -66,6 +66,11 @@ def test_general_32_block_path_matches_oracle(harness, bits):
         out = ctypes.create_string_buffer(512)
         assert harness.bs_host_ecb32(rk, len(rk) // 16 - 1, data, out) == 0
         assert out.raw == orc.ecb_encrypt(key, data), (bits, trial)
+        # and back through the bitsliced inverse cipher (derived inverse S-box, equivalent inverse schedule)
+        harness.bs_host_ecb32_decrypt.argtypes = harness.bs_host_ecb32.argtypes
+        back = ctypes.create_string_buffer(512)
+        assert harness.bs_host_ecb32_decrypt(rk, len(rk) // 16 - 1, data, back) == 0
+        assert (0, back.raw) == orc.ecb_decrypt(key, data), (bits, trial)
 
 
 def test_generated_sbox_is_current(harness):

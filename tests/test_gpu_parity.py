@@ -226,6 +226,9 @@ def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
             back = ctypes.create_string_buffer(len(data))
             uaes.xts_sectors(bits, keys, first, 512, out.raw, len(data), back, False)
             assert back.raw == data
+            # the decrypting co-runner (bitsliced inverse cipher) against the oracle on unrelated input
+            uaes.xts_sectors(bits, keys, first, 512, data, len(data), back, False)
+            assert (0, back.raw) == orc.xts_sectors(keys, first, 512, data, encrypt=False), (share, first, ns)
     finally:
         uaes.ctr_tuning(385, 190, 1 << 20)
 

@@ -157,7 +157,7 @@ def evalc(g,x):
     v={f"U{i}":(x>>(7-i))&1 for i in range(8)}
     for d,op,a,b in g:
         A,B=v[a],v[b]
-        v[d]= A^B if op=='^' else A&B if op=='&' else 1^A^B
+        v[d]= A^B if op=='^' else A&B if op=='&' else 1^A if op=='~' else 1^A^B
     return sum(v[f"S{i}"]<<(7-i) for i in range(8))
 
 K = 3
@@ -235,7 +235,7 @@ def lut_immediates(nodes, order, choice, outs):
     def ev(n, env):
         if n in env: return env[n]
         op, a, b = nodes[n]; A = ev(a, env); B = ev(b, env)
-        return A ^ B if op == '^' else A & B if op == '&' else 1 ^ A ^ B
+        return A ^ B if op == '^' else A & B if op == '&' else 1 ^ A if op == '~' else 1 ^ A ^ B
     luts = []
     for n in order:
         if n not in need: continue
@@ -249,16 +249,113 @@ def lut_immediates(nodes, order, choice, outs):
         luts.append((n, leaves, imm))
     return luts
 
-def verify(luts):
-    S = sbox_table()
+def verify(luts, S=None):
+    S = S or sbox_table()
     for x in range(256):
         v = {f"U{i}": (x >> (7 - i)) & 1 for i in range(8)}
         for n, l, imm in luts:
             v[n] = (imm >> ((v[l[0]] << 2) | (v[l[1]] << 1) | v[l[2]])) & 1
         assert sum(v[f"S{i}"] << (7 - i) for i in range(8)) == S[x], x
 
-def emit(luts, path):
+def emit_function(L, luts, fname, comment):
     name = {f"U{i}": f"x[{7 - i}]" for i in range(8)}
+    L.append(comment)
+    L.append(f"UAES_HD void {fname}(uint32_t x[8])")
+    L.append("{")
+    for n, l, imm in luts:
+        args = ", ".join(name[z] for z in l)
+        v = f"o{n[1:]}" if n.startswith("S") else n
+        name[n] = v
+        L.append(f"    const uint32_t {v} = lut3<0x{imm:02x}>({args});")
+    for i in range(8):
+        L.append(f"    x[{7 - i}] = o{i};")
+    L.append("}")
+
+
+# ---------------------------------------------------------------- the inverse S-box, derived
+#
+# The forward circuit is  S(u) = Bottom(Middle(Top u)) ^ 0x63  with linear Top (8 -> 22 signals) and
+# Bottom (18 products -> 8 bits) around the shared non-linear Middle (the GF(2^8) inversion in a tower
+# basis).  With the affine map A of FIPS-197 5.1.1 (S = A Inv ^ 0x63):
+#     Inv(u)   = A^-1 (S(u) ^ 0x63)           = (A^-1 Bottom) Middle(Top u)
+#     S^-1(x)  = Inv(A^-1 (x ^ 0x63))          = (A^-1 Bottom) Middle(Top A^-1 x  ^  Top A^-1 0x63)
+# so the inverse S-box (micro_aes.c:53-65, 268-275) re-uses Middle with a new top layer Top A^-1 (plus
+# constant complements) and a new bottom layer A^-1 Bottom, both obtained numerically below and
+# re-synthesised as XOR networks by greedy common-subexpression elimination (Paar).
+def paar(rows, in_names, prefix):
+    """rows: list of sets of input names; returns (gates, out_signal_per_row)"""
+    rows = [set(r) for r in rows]
+    gates, k = [], 0
+    while True:
+        best, cnt = None, 1
+        sigs = sorted(set().union(*rows))
+        for i, a in enumerate(sigs):
+            for b in sigs[i + 1:]:
+                c = sum(1 for r in rows if a in r and b in r)
+                if c > cnt: best, cnt = (a, b), c
+        if best is None: break
+        n = f"{prefix}{k}"; k += 1
+        gates.append((n, '^', best[0], best[1]))
+        for r in rows:
+            if best[0] in r and best[1] in r:
+                r -= {best[0], best[1]}; r.add(n)
+    outs = []
+    for r in rows:                      # what is left shares nothing: chain it
+        r = sorted(r)
+        acc = r[0]
+        for x in r[1:]:
+            n = f"{prefix}{k}"; k += 1
+            gates.append((n, '^', acc, x)); acc = n
+        outs.append(acc)
+    return gates, outs
+
+
+def inverse_network(g):
+    first_mid = next(i for i, x in enumerate(g) if x[0] == 't2')
+    first_bot = next(i for i, x in enumerate(g) if x[0] == 't46')
+    TOP, MID, BOT = g[:first_mid], g[first_mid:first_bot], g[first_bot:]
+    mid_sigs = [f"y{i}" for i in range(1, 22)] + ["U7"]
+    zs = [f"z{i}" for i in range(18)]
+
+    def run(gates, env):
+        v = dict(env)
+        for d, op, a, b in gates:
+            A, B = v[a], v[b]
+            v[d] = A ^ B if op == '^' else A & B if op == '&' else 1 ^ A if op == '~' else 1 ^ A ^ B
+        return v
+    bits = lambda x: [(x >> (7 - i)) & 1 for i in range(8)]
+    frombits = lambda b: sum(v << (7 - i) for i, v in enumerate(b))
+    top_of = lambda u: [run(TOP, {f"U{i}": (u >> (7 - i)) & 1 for i in range(8)})[s] for s in mid_sigs]
+    bot_of = lambda z: [run(BOT, dict(zip(zs, z)))[f"S{i}"] for i in range(8)]
+    unit = lambda n, j: [1 if i == j else 0 for i in range(n)]
+    c0 = bot_of([0] * 18)
+    assert frombits(c0) == 0x63
+    Bm = [frombits([a ^ b for a, b in zip(bot_of(unit(18, j)), c0)]) for j in range(18)]
+    rotl = lambda q, s: ((q << s) | (q >> (8 - s))) & 0xff
+    Ainv = {q ^ rotl(q, 1) ^ rotl(q, 2) ^ rotl(q, 3) ^ rotl(q, 4): q for q in range(256)}
+    newtop = lambda x: top_of(Ainv[x ^ 0x63])
+    t0 = newtop(0)
+    Tp = [[a ^ b for a, b in zip(newtop(1 << (7 - j)), t0)] for j in range(8)]
+    Bp = [bits(Ainv[Bm[j]]) for j in range(18)]
+    # XOR networks.  New top: signal k = XOR of inputs X_j with Tp[j][k], complemented when t0[k].
+    tg, touts = paar([{f"U{j}" for j in range(8) if Tp[j][k]} for k in range(22)], None, "a")
+    gates = list(tg)
+    ren = {}
+    for k, sname in enumerate(mid_sigs):
+        src = touts[k]
+        if t0[k]:
+            gates.append((f"n{k}", '~', src, src)); src = f"n{k}"
+        ren[sname] = src
+    for d, op, a, b in MID:                                  # the shared middle, inputs renamed
+        gates.append((d, op, ren.get(a, a), ren.get(b, b)))
+    bg, bouts = paar([{zs[j] for j in range(18) if Bp[j][i]} for i in range(8)], None, "b")
+    gates += bg
+    out_name = {bouts[i]: f"S{i}" for i in range(8)}         # the rows' final signals are the outputs
+    assert len(out_name) == 8
+    return [(out_name.get(d, d), op, out_name.get(a, a), out_name.get(b, b)) for d, op, a, b in gates]
+
+
+def emit(luts, luts_inv, path):
     L = []
     L.append("// uaes_sbox_lut3.cuh -- GENERATED by tools/gen_sbox_lut3.py, do not edit.")
     L.append("// Bitsliced AES S-box (SubBytes, micro_aes.c:187-194, on 32 blocks at once): x[b] holds bit b")
@@ -281,20 +378,11 @@ def emit(luts, path):
     L.append("#endif")
     L.append("}")
     L.append(f"constexpr int kSboxLut3Count = {len(luts)};")
-    L.append("UAES_HD void sbox_bitsliced(uint32_t x[8])")
-    L.append("{")
-    outmap = {}
-    for n, l, imm in luts:
-        args = ", ".join(name[z] for z in l)
-        if n.startswith("S"):
-            v = f"o{n[1:]}"; outmap[n] = v
-        else:
-            v = n
-        name[n] = v
-        L.append(f"    const uint32_t {v} = lut3<0x{imm:02x}>({args});")
-    for i in range(8):
-        L.append(f"    x[{7 - i}] = o{i};")
-    L.append("}")
+    L.append(f"constexpr int kInvSboxLut3Count = {len(luts_inv)};")
+    emit_function(L, luts, "sbox_bitsliced", "// SubBytes, micro_aes.c:187-194")
+    emit_function(L, luts_inv, "sbox_inv_bitsliced",
+                  "// InvSubBytes, micro_aes.c:268-275: the forward circuit's non-linear middle between a top and a bottom\n"
+                  "// linear layer derived by the generator (Top A^-1 and A^-1 Bottom), verified on all 256 inputs")
     L.append("}  // namespace uaes")
     open(path, "w").write("\n".join(L) + "\n")
 
@@ -310,7 +398,20 @@ if __name__ == "__main__":
         if res is None or b[0] < res[0]: res = b
     luts = lut_immediates(nodes, order, res[1], outs)
     verify(luts)
+    # inverse S-box
+    gi = inverse_network(g)
+    Sinv = [0] * 256
+    for i, v in enumerate(S): Sinv[v] = i
+    assert all(evalc(gi, x) == Sinv[x] for x in range(256)), "derived network is not the inverse S-box"
+    nodes_i, order_i = build(gi); cuts_i = enum_cuts(nodes_i, order_i)
+    res_i = None
+    for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
+        b = optimize(nodes_i, order_i, cuts_i, outs, iters=30000, seed=seed)
+        if res_i is None or b[0] < res_i[0]: res_i = b
+    luts_i = lut_immediates(nodes_i, order_i, res_i[1], outs)
+    verify(luts_i, Sinv)
     here = os.path.dirname(os.path.abspath(__file__))
     out = os.path.join(here, "..", "micro-aes_b200", "csrc", "uaes_sbox_lut3.cuh")
-    emit(luts, out)
-    print(f"{len(g)} gates -> {len(luts)} LOP3, verified on 256 inputs; wrote {os.path.normpath(out)}")
+    emit(luts, luts_i, out)
+    print(f"S-box: {len(g)} gates -> {len(luts)} LOP3; inverse S-box: {len(gi)} gates -> {len(luts_i)} LOP3; "
+          f"both verified on 256 inputs; wrote {os.path.normpath(out)}")
