@@ -1,4 +1,6 @@
-// uaes_bitslice.cuh -- bitsliced AES-CTR keystream for the ALU co-runner warps of ctr_kernel.
+// uaes_bitslice.cuh -- bitsliced AES for the ALU co-runner warps: the CTR-specialised form used by
+// ctr_kernel (first half of this file), the general form for data-dependent modes used by
+// xts_sectors_hybrid_kernel (bs_encrypt_planes) and the inverse cipher (bs_decrypt_planes).
 //
 // The table-driven warps of ctr_kernel saturate the shared-memory lookup pipe (32 lookups / clk /
 // SM) and leave roughly half of the integer ALU pipe idle once their lookup addresses are built on
