@@ -425,28 +425,88 @@ struct Ctr32Args {
 };
 
 // CTR_cipher with mode SIVGCM_CTR (micro_aes.c:935-938): bit 7 of byte 15 forced, the counter is
-// the little-endian 32-bit word in bytes 0..3 and wraps modulo 2^32
+// the little-endian 32-bit word in bytes 0..3 and wraps modulo 2^32.
+//
+// Same round-1/2 hoisting as ctr_kernel, for a counter that lives in COLUMN 0: inside a group of 256
+// consecutive counter values only byte 0 changes, so round 1 column 0 = K0 ^ Te0[byte 0] and the
+// other three columns are group constants (C3 follows counter byte 1, C2 byte 2, C1 byte 3); round 2
+// column j = D_j ^ Te_x[a byte of column 0] with the Te_x terms a function of byte 0 alone, kept in
+// registers per lane for the whole launch.  128 lookups per AES-128 block instead of 160.
+constexpr int kCtr32Threads = 768;
+
 template <int NR>
-__global__ void __launch_bounds__(kThreads, 1) ctr32_kernel(const __grid_constant__ Ctr32Args a)
+__global__ void __launch_bounds__(kCtr32Threads, 1) ctr32_kernel(const __grid_constant__ Ctr32Args a)
 {
+    constexpr int kWarps = kCtr32Threads / 32;
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_tables<true>(dyn);
     const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
     const uint4 c = load_block_bytes(a.tag, 16);
-    const uint32_t c3 = c.w | 0x80000000u;
-    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-    uint64_t k = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const uint32_t s1 = c.y ^ rk[1], s2 = c.z ^ rk[2], s3 = (c.w | 0x80000000u) ^ rk[3];
 
-    uint4 cur = k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
-    for (; k < a.nblocks; k += stride) {
-        const uint4 nxt = k + stride < a.nblocks ? ld_stream(a.in + k + stride) : make_uint4(0, 0, 0, 0);
-        uint32_t s0 = c.x + (uint32_t)k, s1 = c.y, s2 = c.z, s3 = c3;
-        enc_block<NR>(lb, s0, s1, s2, s3, rk, cur.x, cur.y, cur.z, cur.w);
-        st_stream(a.out + k, make_uint4(s0, s1, s2, s3));
-        cur = nxt;
+    // counter value of block k = (c.x + k) mod 2^32; u = c.x + k unreduced, group = u >> 8
+    const uint64_t u0 = c.x;
+    const uint32_t lowoff = c.x & 255u;
+    const uint64_t g0 = u0 >> 8;
+    const uint64_t ngroups = (lowoff + a.nblocks + 255) >> 8;
+    const uint64_t wg = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t half = (uint32_t)wg & 1u;
+    const uint64_t npairs = (uint64_t)gridDim.x * (kWarps / 2);
+    const uint64_t per = (ngroups + npairs - 1) / npairs;
+    const uint64_t j0 = (wg >> 1) * per;
+    const uint64_t j1 = j0 + per < ngroups ? j0 + per : ngroups;
+    const uint32_t b0 = half * 128 + lane;                        // counter byte 0, + 32 * it
+
+    auto kof = [&](uint64_t grp, int it) -> int64_t {
+        return (int64_t)(grp << 8) + (int64_t)(b0 + 32 * it) - (int64_t)lowoff;
+    };
+    auto fetch = [&](uint64_t grp, int it) -> uint4 {
+        const int64_t k = kof(grp, it);
+        if (grp < j1 && k >= 0 && (uint64_t)k < a.nblocks) return ld_stream(a.in + k);
+        return make_uint4(0, 0, 0, 0);
+    };
+
+    // launch constants: K0 and the byte-0 terms of round 2
+    const uint32_t K0 = lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ lut<3, kOffT3>(lb, s3) ^ rk[4];
+    uint32_t U[4][4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const uint32_t c0 = K0 ^ lut<0, kOffT0>(lb, (b0 + 32 * it) ^ (rk[0] & 255u));
+        U[it][0] = lut<0, kOffT0>(lb, c0); U[it][1] = lut<3, kOffT3>(lb, c0);
+        U[it][2] = lut<2, kOffT2>(lb, c0); U[it][3] = lut<1, kOffT1>(lb, c0);
+    }
+    uint64_t tag16 = ~0ull;
+    uint32_t E0 = 0, E1 = 0, E2 = 0, E3 = 0;
+
+    uint4 cur = fetch(j0, 0);
+    for (uint64_t j = j0; j < j1; ++j) {
+        const uint32_t s0 = (uint32_t)((g0 + j) << 8) ^ rk[0];   // counter word with byte 0 = 0, wraps mod 2^32
+        if (((g0 + j) >> 8) != tag16) {                           // counter bytes 2..3 changed: every 256 groups
+            tag16 = (g0 + j) >> 8;
+            const uint32_t C1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<2, kOffT2>(lb, s3) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
+            const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
+            E0 = lut<1, kOffT1>(lb, C1) ^ lut<2, kOffT2>(lb, C2) ^ rk[8];
+            E1 = lut<0, kOffT0>(lb, C1) ^ lut<1, kOffT1>(lb, C2) ^ rk[9];
+            E2 = lut<0, kOffT0>(lb, C2) ^ lut<3, kOffT3>(lb, C1) ^ rk[10];
+            E3 = lut<2, kOffT2>(lb, C1) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+        }
+        // per group: counter byte 1 enters through column 3 of round 1
+        const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
+        const uint32_t D0 = E0 ^ lut<3, kOffT3>(lb, C3), D1 = E1 ^ lut<2, kOffT2>(lb, C3);
+        const uint32_t D2 = E2 ^ lut<1, kOffT1>(lb, C3), D3 = E3 ^ lut<0, kOffT0>(lb, C3);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const uint4 nxt = it < 3 ? fetch(j, it + 1) : fetch(j + 1, 0);
+            const int64_t k = kof(j, it);
+            uint32_t t0 = D0 ^ U[it][0], t1 = D1 ^ U[it][1], t2 = D2 ^ U[it][2], t3 = D3 ^ U[it][3];
+            enc_finish<NR, 3>(lb, t0, t1, t2, t3, rk, cur.x, cur.y, cur.z, cur.w);
+            if (k >= 0 && (uint64_t)k < a.nblocks) st_stream(a.out + k, make_uint4(t0, t1, t2, t3));
+            cur = nxt;
+        }
     }
     if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
-        uint32_t s[4] = {c.x + (uint32_t)a.nblocks, c.y, c.z, c3};
+        uint32_t s[4] = {c.x + (uint32_t)a.nblocks, c.y, c.z, c.w | 0x80000000u};
         enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
         const uint8_t *x = (const uint8_t *)(a.in + a.nblocks);
         uint8_t *y = (uint8_t *)(a.out + a.nblocks);
@@ -459,7 +519,10 @@ static cudaError_t launch_ctr32_nr(const Ctr32Args &a, cudaStream_t st)
 {
     cudaError_t e = opt_in_smem(ctr32_kernel<NR>);
     if (e != cudaSuccess) return e;
-    ctr32_kernel<NR><<<grid_for((a.nblocks + 31) / 32), kThreads, kDynSmem, st>>>(a);
+    constexpr int kWarps = kCtr32Threads / 32;
+    const uint64_t ngroups = (a.nblocks + 255 + 255) >> 8;      // upper bound (the offset is in device memory)
+    const uint64_t ctas = (ngroups + 4 * (kWarps / 2) - 1) / (4 * (kWarps / 2)), sms = (uint64_t)sm_count();
+    ctr32_kernel<NR><<<(unsigned)(ctas < 1 ? 1 : ctas < sms ? ctas : sms), kCtr32Threads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
