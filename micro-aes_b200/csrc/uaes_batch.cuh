@@ -77,6 +77,39 @@ __device__ __forceinline__ void mac_step(uint32_t lb, const uint32_t *rk, Blk &m
     enc_block<NR>(lb, m.w[0], m.w[1], m.w[2], m.w[3], rk);
 }
 
+// Keystream block E(counter block) ^ x with the CTR hoisting of ctr_kernel, per lane: while bytes
+// 0..14 of the counter block stay the same (256 consecutive blocks of ONE message), round 1 is one
+// lookup and round 2 four, the rest coming from five cached words; a change of the upper bytes
+// recomputes them (19 lookups per 256 blocks).  16 * (NR - 2) + 5 lookups per block instead of 16 * NR.
+template <int NR>
+struct LaneCtr {
+    uint32_t K0, D0, D1, D2, D3, k0, k1, k2, k3;
+    bool valid;
+    __device__ __forceinline__ LaneCtr() : valid(false) {}
+    __device__ __forceinline__ void block(uint32_t lb, const uint32_t *rk, uint32_t w0, uint32_t w1, uint32_t w2,
+                                          uint32_t w3, const Blk &x, Blk &out)
+    {
+        const uint32_t s3 = w3 ^ rk[3];
+        if (!valid || w0 != k0 || w1 != k1 || w2 != k2 || (w3 & 0x00ffffffu) != k3) {
+            valid = true; k0 = w0; k1 = w1; k2 = w2; k3 = w3 & 0x00ffffffu;
+            const uint32_t s0 = w0 ^ rk[0], s1 = w1 ^ rk[1], s2 = w2 ^ rk[2];
+            K0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ rk[4];
+            const uint32_t C1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<2, kOffT2>(lb, s3) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
+            const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
+            const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
+            D0 = lut<1, kOffT1>(lb, C1) ^ lut<2, kOffT2>(lb, C2) ^ lut<3, kOffT3>(lb, C3) ^ rk[8];
+            D1 = lut<0, kOffT0>(lb, C1) ^ lut<1, kOffT1>(lb, C2) ^ lut<2, kOffT2>(lb, C3) ^ rk[9];
+            D2 = lut<0, kOffT0>(lb, C2) ^ lut<1, kOffT1>(lb, C3) ^ lut<3, kOffT3>(lb, C1) ^ rk[10];
+            D3 = lut<0, kOffT0>(lb, C3) ^ lut<2, kOffT2>(lb, C1) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+        }
+        const uint32_t c0 = K0 ^ lut<3, kOffT3>(lb, s3);
+        uint32_t t0 = D0 ^ lut<0, kOffT0>(lb, c0), t1 = D1 ^ lut<3, kOffT3>(lb, c0);
+        uint32_t t2 = D2 ^ lut<2, kOffT2>(lb, c0), t3 = D3 ^ lut<1, kOffT1>(lb, c0);
+        enc_finish<NR, 3>(lb, t0, t1, t2, t3, rk, x.w[0], x.w[1], x.w[2], x.w[3]);
+        out.w[0] = t0; out.w[1] = t1; out.w[2] = t2; out.w[3] = t3;
+    }
+};
+
 // ---------------------------------------------------------------- CCM (micro_aes.c:1219-1315)
 // CCM_NONCE_LEN = 11, CCM_TAG_LEN = 16 (micro_aes.h:104-105): iv = 03 || nonce || 00000000
 template <int NR>
@@ -126,14 +159,12 @@ __global__ void __launch_bounds__(kBatchThreads, 1) ccm_batch_kernel(const __gri
 
         // ---- payload: CBC-MAC over the plaintext (:1252) and CTR from iv + 1 (:939-941) in one walk
         uint32_t ctr = 1;
+        LaneCtr<NR> lc;
         for (uint32_t o = 0; o < d.len; o += 16, ++ctr) {
             const uint32_t nb = d.len - o < 16 ? d.len - o : 16;
             Blk x = load_bytes(src + o, nb);
-            Blk ks = iv;
-            ks.w[3] = bswap32(ctr);
-            enc_block<NR>(lb, ks.w[0], ks.w[1], ks.w[2], ks.w[3], rk);
             Blk y;
-            y.w[0] = x.w[0] ^ ks.w[0]; y.w[1] = x.w[1] ^ ks.w[1]; y.w[2] = x.w[2] ^ ks.w[2]; y.w[3] = x.w[3] ^ ks.w[3];
+            lc.block(lb, rk, iv.w[0], iv.w[1], iv.w[2], bswap32(ctr), x, y);
             if (a.decrypt) {
                 if (nb < 16) {                        // the MAC sees the plaintext zero padded
                     const uint32_t keep = nb & 3 ? (1u << (8 * (nb & 3))) - 1 : 0;
@@ -243,13 +274,14 @@ __device__ __forceinline__ void ctr_walk(uint32_t lb, const uint32_t *rk, const 
 {
     const uint64_t v0 = ((uint64_t)(bswap32(c0.w[2]) & 0x00ffffffu) << 32) | bswap32(c0.w[3]);
     uint64_t k = 0;
+    LaneCtr<NR> lc;
     for (uint32_t o = 0; o < n; o += 16, ++k) {
         const uint32_t nb = n - o < 16 ? n - o : 16;
         const Blk x = load_bytes(src + o, nb);
         Blk ks;
-        ks.w[0] = c0.w[0]; ks.w[1] = c0.w[1];
-        ctr_words(c0.w[2] & 255u, (v0 + k) & kMask56, ks.w[2], ks.w[3]);
-        enc_block<NR>(lb, ks.w[0], ks.w[1], ks.w[2], ks.w[3], rk, x.w[0], x.w[1], x.w[2], x.w[3]);
+        uint32_t w2, w3;
+        ctr_words(c0.w[2] & 255u, (v0 + k) & kMask56, w2, w3);
+        lc.block(lb, rk, c0.w[0], c0.w[1], w2, w3, x, ks);
         store_bytes(dst + o, ks, nb);
     }
 }
@@ -393,12 +425,12 @@ __global__ void __launch_bounds__(kBatchThreads, 1) gcm_batch_kernel(const __gri
         if (a.decrypt) ghash_bytes(g, H, src, d.len);             // :1199: over the received ciphertext
         else {
             uint32_t ctr = 2;                                     // CCM_GCM pre-increment: J0 + 1, :939-941
+            LaneCtr<NR> lc;
             for (uint32_t o = 0; o < d.len; o += 16, ++ctr) {
                 const uint32_t nb = d.len - o < 16 ? d.len - o : 16;
                 const Blk x = load_bytes(src + o, nb);
-                Blk y = j0;
-                y.w[3] = bswap32(ctr);
-                enc_block<NR>(lb, y.w[0], y.w[1], y.w[2], y.w[3], rk, x.w[0], x.w[1], x.w[2], x.w[3]);
+                Blk y;
+                lc.block(lb, rk, j0.w[0], j0.w[1], j0.w[2], bswap32(ctr), x, y);
                 if (nb < 16) {                                    // GHASH sees the ciphertext zero padded
                     const uint32_t keep = nb & 3 ? (1u << (8 * (nb & 3))) - 1 : 0;
                     for (uint32_t i = 0; i < 4; ++i)
