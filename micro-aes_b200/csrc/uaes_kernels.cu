@@ -357,6 +357,93 @@ __global__ void __launch_bounds__(kThreads, 1) ecb_kernel(const __grid_constant_
     }
 }
 
+// ---- ECB encryption with the co-runner: 12 table-driven warps (two rows in flight) + one warpgroup
+// of bitsliced warps in the general form (uaes_bitslice.cuh); tile = 1024 blocks, lane l, slot t <->
+// block 32 t + l of the tile, so every access is a coalesced 512-byte row.
+struct EcbHybridArgs {
+    EcbArgs e;
+    uint64_t tt_blocks;          // blocks [0, tt_blocks): table-driven warps; a multiple of 1024
+    BsKeyPlanesFull bs;
+};
+
+constexpr int kEcbTtThreads = 384;
+
+template <int NR>
+__global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kernel(const __grid_constant__ EcbHybridArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.e.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kTtWarps = kEcbTtThreads / 32;
+    constexpr int kLaunchRegs = (65536 / (kEcbTtThreads + kBsThreads)) / 8 * 8;
+    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbTtThreads / kBsThreads;
+
+    if (threadIdx.x >= kEcbTtThreads) {
+        reg_inc<kBsRegs>();
+        const uint64_t ntiles = (a.e.nblocks - a.tt_blocks + 1023) / 1024;
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kEcbTtThreads) >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        const uint64_t per = (ntiles + nw - 1) / nw;
+        const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
+        const uint64_t p1 = p0 + per < ntiles ? p0 + per : ntiles;
+        for (uint64_t tile = p0; tile < p1; ++tile) {
+            const uint64_t kb = a.tt_blocks + tile * 1024 + lane;
+            uint32_t s[128];
+#pragma unroll
+            for (int tb = 0; tb < 32; tb += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < a.e.nblocks ? ld_stream(a.e.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[tb + i] = v[i].x; s[32 + tb + i] = v[i].y; s[64 + tb + i] = v[i].z; s[96 + tb + i] = v[i].w; }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+            bs_encrypt_planes<NR>(s, a.bs);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+                if (kb + 32 * t < a.e.nblocks) st_stream(a.e.out + kb + 32 * t, make_uint4(s[t], s[32 + t], s[64 + t], s[96 + t]));
+        }
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    const uint64_t npairs = a.tt_blocks / 64;                    // pairs of 32-block rows
+    const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+    const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
+    const uint64_t per = (npairs + nw - 1) / nw;
+    const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
+    const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
+    const uint4 zero[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    uint4 cur[2], nxt[2];
+    if (q0 < q1) { cur[0] = ld_stream(a.e.in + q0 * 64 + lane); cur[1] = ld_stream(a.e.in + q0 * 64 + 32 + lane); }
+    for (uint64_t q = q0; q < q1; ++q) {
+        const uint64_t k = q * 64 + lane;
+        if (q + 1 < q1) { nxt[0] = ld_stream(a.e.in + k + 64); nxt[1] = ld_stream(a.e.in + k + 96); }
+        uint32_t st[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            st[i][0] = cur[i].x ^ rk[0]; st[i][1] = cur[i].y ^ rk[1]; st[i][2] = cur[i].z ^ rk[2]; st[i][3] = cur[i].w ^ rk[3];
+        }
+        enc_finish_n<NR, 1, 2>(lb, st, rk, zero);
+        st_stream(a.e.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
+        st_stream(a.e.out + k + 32, make_uint4(st[1][0], st[1][1], st[1][2], st[1][3]));
+        cur[0] = nxt[0]; cur[1] = nxt[1];
+    }
+
+    if (a.e.tail && blockIdx.x == 0 && threadIdx.x == 0) {       // padBlock, micro_aes.c:610-621 (zero padding)
+        const uint8_t *x = (const uint8_t *)(a.e.in + a.e.nblocks);
+        uint8_t *y = (uint8_t *)(a.e.out + a.e.nblocks);
+        uint32_t s[4] = {0, 0, 0, 0};
+        for (uint32_t i = 0; i < a.e.tail; ++i) s[i >> 2] |= (uint32_t)x[i] << (8 * (i & 3));
+        enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
+        for (uint32_t i = 0; i < 16; ++i) y[i] = (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
 // ---------------------------------------------------------------- synthetic data, checksum
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z)
@@ -485,9 +572,34 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     }
 }
 
+constexpr int kEcbDefaultShare = 185;   // 791 / 830 / 849 / 864 / 814 GiB/s at 0 / 100 / 140 / 180 / 220 (AES-128, profiles/r1_ecb_hybrid_sweep.txt)
+
+template <int NR>
+static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(ecb_hybrid_kernel<NR>);
+    if (e != cudaSuccess) return e;
+    static EcbHybridArgs a;                              // 8 KB of planes: not on the stack (callers hold the library lock)
+    a.e = e0;
+    a.tt_blocks = (e0.nblocks - bs_blocks) & ~1023ull;
+    bs_make_key_planes_full(e0.ks.w, NR, &a.bs);
+    const uint64_t need = (e0.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
+    ecb_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kEcbTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 template <int NR, bool ENC>
 static cudaError_t launch_ecb_nr(const EcbArgs &a, cudaStream_t st)
 {
+    if (ENC) {                                           // encryption of enough data: with the co-runner
+        ctr_tuning_init();
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_ECB_BS_PERMILLE", kEcbDefaultShare);
+        if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048) {
+            const uint64_t bs_blocks = a.nblocks / 1024 * (uint64_t)share;
+            if (bs_blocks) return launch_ecb_hybrid_nr<NR>(a, bs_blocks, st);
+        }
+    }
     cudaError_t e = opt_in_smem(ecb_kernel<NR, ENC>);
     if (e != cudaSuccess) return e;
     ecb_kernel<NR, ENC><<<grid_for((a.nblocks + 31) / 32), kThreads, kDynSmem, st>>>(a);

@@ -211,6 +211,19 @@ def test_xts_sectors(uaes, orc, bits):
         assert back.raw == data
 
 
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_ecb_bitsliced_corunner(uaes, orc, bits):
+    """ECB encryption with the co-runner forced on for small calls: all splits, ragged tiles, padded tail"""
+    a = uaes.MicroAES(bits)
+    try:
+        for share, n in ((1024, 16 * 2048), (512, 16 * 5000 + 7), (300, 16 * 70001), (1024, 16 * 3071 + 15), (1, 16 * 4096)):
+            uaes.ctr_tuning(-1, share, 0)
+            key, data = rnd(f"eh-k{bits}{n}", bits // 8), rnd(f"eh-d{bits}{n}", n)
+            assert a.AES_ECB_encrypt(key, data) == orc.ecb_encrypt(key, data), (share, n)
+    finally:
+        uaes.ctr_tuning(385, 190, 1 << 20)
+
+
 @pytest.mark.parametrize("bits", [128, 256])
 def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
     """512-byte sector encryption with the ALU co-runner warps forced on for small calls, at several
