@@ -87,6 +87,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_dec_kernel(const __grid_con
 template <int NR, bool CBC>
 static cudaError_t launch_chain_nr(const ChainArgs &a, cudaStream_t st)
 {
+    if (!CBC) {                                          // CFB decryption of enough data: ECB-shaped, with the co-runner
+        ctr_tuning_init();
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_ECB_BS_PERMILLE", kEcbDefaultShare);
+        if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048) {
+            EcbArgs e0;
+            e0.ks = a.ks; e0.in = a.in; e0.out = a.out; e0.nblocks = a.nblocks; e0.tail = a.tail;
+            return launch_ecb_hybrid_nr<NR, true>(e0, a.nblocks / 1024 * (uint64_t)share, st, a.iv);
+        }
+    }
     cudaError_t e = opt_in_smem(chain_dec_kernel<NR, CBC>);
     if (e != cudaSuccess) return e;
     chain_dec_kernel<NR, CBC><<<grid_for((a.nblocks + 31) / 32), kThreads, kDynSmem, st>>>(a);

@@ -360,17 +360,23 @@ __global__ void __launch_bounds__(kThreads, 1) ecb_kernel(const __grid_constant_
 // ---- ECB encryption with the co-runner: 12 table-driven warps (two rows in flight) + one warpgroup
 // of bitsliced warps in the general form (uaes_bitslice.cuh); tile = 1024 blocks, lane l, slot t <->
 // block 32 t + l of the tile, so every access is a coalesced 512-byte row.
+// CFB = true turns it into CFB decryption (micro_aes.c:799-845): P_k = E(C_(k-1)) ^ C_k, C_(-1) = IV --
+// the same cipher calls on the input shifted by one block, the ciphertext XORed in at the end.
 struct EcbHybridArgs {
     EcbArgs e;
     uint64_t tt_blocks;          // blocks [0, tt_blocks): table-driven warps; a multiple of 1024
+    uint32_t iv[4];              // CFB only
     BsKeyPlanesFull bs;
 };
 
 constexpr int kEcbTtThreads = 384;
 
-template <int NR>
+template <int NR, bool CFB>
 __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kernel(const __grid_constant__ EcbHybridArgs a)
 {
+    const uint4 iv = make_uint4(a.iv[0], a.iv[1], a.iv[2], a.iv[3]);
+    // cipher input of block k: the block itself (ECB) or its predecessor (CFB)
+    auto cin = [&](uint64_t k) -> uint4 { return !CFB ? ld_stream(a.e.in + k) : k ? a.e.in[k - 1] : iv; };
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_tables<true>(dyn);
     const uint32_t *rk = a.e.ks.w;
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
             for (int tb = 0; tb < 32; tb += 8) {
                 uint4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < a.e.nblocks ? ld_stream(a.e.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < a.e.nblocks ? cin(kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { s[tb + i] = v[i].x; s[32 + tb + i] = v[i].y; s[64 + tb + i] = v[i].z; s[96 + tb + i] = v[i].w; }
             }
@@ -404,8 +410,18 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
 #pragma unroll
             for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
 #pragma unroll
-            for (int t = 0; t < 32; ++t)
-                if (kb + 32 * t < a.e.nblocks) st_stream(a.e.out + kb + 32 * t, make_uint4(s[t], s[32 + t], s[64 + t], s[96 + t]));
+            for (int tb = 0; tb < 32; tb += 4) {
+                uint4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    x[i] = CFB && kb + 32 * (tb + i) < a.e.nblocks ? ld_stream(a.e.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = tb + i;
+                    if (kb + 32 * t < a.e.nblocks)
+                        st_stream(a.e.out + kb + 32 * t, make_uint4(s[t] ^ x[i].x, s[32 + t] ^ x[i].y, s[64 + t] ^ x[i].z, s[96 + t] ^ x[i].w));
+                }
+            }
         }
         return;
     }
@@ -417,12 +433,13 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
     const uint64_t per = (npairs + nw - 1) / nw;
     const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
     const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
-    const uint4 zero[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     uint4 cur[2], nxt[2];
-    if (q0 < q1) { cur[0] = ld_stream(a.e.in + q0 * 64 + lane); cur[1] = ld_stream(a.e.in + q0 * 64 + 32 + lane); }
+    if (q0 < q1) { cur[0] = cin(q0 * 64 + lane); cur[1] = cin(q0 * 64 + 32 + lane); }
     for (uint64_t q = q0; q < q1; ++q) {
         const uint64_t k = q * 64 + lane;
-        if (q + 1 < q1) { nxt[0] = ld_stream(a.e.in + k + 64); nxt[1] = ld_stream(a.e.in + k + 96); }
+        if (q + 1 < q1) { nxt[0] = cin(k + 64); nxt[1] = cin(k + 96); }
+        uint4 zero[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (CFB) { zero[0] = ld_stream(a.e.in + k); zero[1] = ld_stream(a.e.in + k + 32); }     // the ciphertext XORed in at the end
         uint32_t st[2][4];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -434,13 +451,20 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
         cur[0] = nxt[0]; cur[1] = nxt[1];
     }
 
-    if (a.e.tail && blockIdx.x == 0 && threadIdx.x == 0) {       // padBlock, micro_aes.c:610-621 (zero padding)
+    if (a.e.tail && blockIdx.x == 0 && threadIdx.x == 0) {
         const uint8_t *x = (const uint8_t *)(a.e.in + a.e.nblocks);
         uint8_t *y = (uint8_t *)(a.e.out + a.e.nblocks);
-        uint32_t s[4] = {0, 0, 0, 0};
-        for (uint32_t i = 0; i < a.e.tail; ++i) s[i >> 2] |= (uint32_t)x[i] << (8 * (i & 3));
-        enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
-        for (uint32_t i = 0; i < 16; ++i) y[i] = (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
+        if (!CFB) {                                              // padBlock, micro_aes.c:610-621 (zero padding)
+            uint32_t s[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < a.e.tail; ++i) s[i >> 2] |= (uint32_t)x[i] << (8 * (i & 3));
+            enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
+            for (uint32_t i = 0; i < 16; ++i) y[i] = (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
+        } else {                                                 // ragged last block: E(C_(m-1)) ^ C_m, micro_aes.c:840-845
+            const uint4 ch = cin(a.e.nblocks);
+            uint32_t s[4] = {ch.x, ch.y, ch.z, ch.w};
+            enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
+            for (uint32_t i = 0; i < a.e.tail; ++i) y[i] = x[i] ^ (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
+        }
     }
 }
 
@@ -574,17 +598,18 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
 
 constexpr int kEcbDefaultShare = 185;   // 791 / 830 / 849 / 864 / 814 GiB/s at 0 / 100 / 140 / 180 / 220 (AES-128, profiles/r1_ecb_hybrid_sweep.txt)
 
-template <int NR>
-static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, cudaStream_t st)
+template <int NR, bool CFB = false>
+static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, cudaStream_t st, const uint32_t *iv = nullptr)
 {
-    cudaError_t e = opt_in_smem(ecb_hybrid_kernel<NR>);
+    cudaError_t e = opt_in_smem(ecb_hybrid_kernel<NR, CFB>);
     if (e != cudaSuccess) return e;
     static EcbHybridArgs a;                              // 8 KB of planes: not on the stack (callers hold the library lock)
     a.e = e0;
+    for (int c = 0; c < 4; ++c) a.iv[c] = iv ? iv[c] : 0;
     a.tt_blocks = (e0.nblocks - bs_blocks) & ~1023ull;
     bs_make_key_planes_full(e0.ks.w, NR, &a.bs);
     const uint64_t need = (e0.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
-    ecb_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kEcbTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ecb_hybrid_kernel<NR, CFB><<<(unsigned)(need < sms ? need : sms), kEcbTtThreads + kBsThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -220,6 +220,10 @@ def test_ecb_bitsliced_corunner(uaes, orc, bits):
             uaes.ctr_tuning(-1, share, 0)
             key, data = rnd(f"eh-k{bits}{n}", bits // 8), rnd(f"eh-d{bits}{n}", n)
             assert a.AES_ECB_encrypt(key, data) == orc.ecb_encrypt(key, data), (share, n)
+            iv = rnd(f"eh-i{bits}{n}", 16)                       # CFB decryption rides the same kernel
+            o = ctypes.create_string_buffer(max(n, 1))
+            orc.lib.oracle_cfb_decrypt(bits, key, iv, data, n, o)
+            assert a.AES_CFB_decrypt(key, iv, data) == o.raw[:n], (share, n)
     finally:
         uaes.ctr_tuning(385, 190, 1 << 20)
 
