@@ -134,6 +134,143 @@ __global__ void __launch_bounds__(kThreads, 1) ocb_bulk_kernel(const __grid_cons
     }
 }
 
+// ---- OCB encryption with the co-runner (the shape of ecb_hybrid_kernel): 12 table-driven warps with
+// two rows in flight + one warpgroup of bitsliced warps (general form).  Offsets stay in the word
+// layout on both sides: a lane jumps to its first Delta through the Gray code and steps 32 blocks at
+// a time; the bitsliced warps walk the 32 rows of a tile twice (whitening in, whitening out) from the
+// saved first Delta instead of keeping 32 of them.  The checksum is the XOR of the plaintext words as
+// they are loaded.
+struct OcbHybridArgs {
+    OcbBulkArgs o;
+    uint64_t tt_blocks;          // blocks [0, tt_blocks): table-driven warps; a multiple of 1024
+    BsKeyPlanesFull bs;
+};
+
+constexpr int kOcbTtThreads = 384;
+
+// D_(i+32) = D_i ^ L_4 ^ L_(5 + ntz((i >> 5) + 1)),  i = k + 1 (1-based index of the block just done)
+__device__ __forceinline__ void ocb_step32(uint4 &delta, const uint4 *Ls, const uint4 &L4, uint64_t k)
+{
+    const uint32_t m = 5 + (uint32_t)__ffsll((long long)(((k + 1) >> 5) + 1)) - 1;
+    xor4(delta, L4);
+    xor4(delta, Ls[m]);
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kernel(const __grid_constant__ OcbHybridArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    uint4 *Ls = (uint4 *)(dyn + dyn_smem_size() - 1024);
+    if (threadIdx.x < 64) Ls[threadIdx.x] = a.o.work->L[threadIdx.x];
+    const uint32_t lb = setup_tables<true>(dyn);                // contains __syncthreads()
+    const uint32_t *rk = a.o.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kTtWarps = kOcbTtThreads / 32;
+    constexpr int kLaunchRegs = (65536 / (kOcbTtThreads + kBsThreads)) / 8 * 8;
+    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kOcbTtThreads / kBsThreads;
+    const uint4 L4 = Ls[4];
+    const uint64_t nblocks = a.o.nblocks;
+    uint4 sum = make_uint4(0, 0, 0, 0);
+
+    if (threadIdx.x >= kOcbTtThreads) {
+        reg_inc<kBsRegs>();
+        const uint64_t ntiles = (nblocks - a.tt_blocks + 1023) / 1024;
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kOcbTtThreads) >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        const uint64_t per = (ntiles + nw - 1) / nw;
+        const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
+        const uint64_t p1 = p0 + per < ntiles ? p0 + per : ntiles;
+        for (uint64_t tile = p0; tile < p1; ++tile) {
+            const uint64_t kb = a.tt_blocks + tile * 1024 + lane;
+            uint4 d0 = a.o.work->off0;
+            xor4(d0, ocb_gray_sum(Ls, kb + 1));
+            uint4 delta = d0;
+            uint32_t s[128];
+#pragma unroll
+            for (int tb = 0; tb < 32; tb += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < nblocks ? ld_stream(a.o.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xor4(sum, v[i]);                                 // out-of-range rows are zero
+                    s[tb + i] = v[i].x ^ delta.x; s[32 + tb + i] = v[i].y ^ delta.y;
+                    s[64 + tb + i] = v[i].z ^ delta.z; s[96 + tb + i] = v[i].w ^ delta.w;
+                    ocb_step32(delta, Ls, L4, kb + 32 * (tb + i));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+            bs_encrypt_planes<NR>(s, a.bs);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+            delta = d0;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                if (kb + 32 * t < nblocks)
+                    st_stream(a.o.out + kb + 32 * t, make_uint4(s[t] ^ delta.x, s[32 + t] ^ delta.y, s[64 + t] ^ delta.z, s[96 + t] ^ delta.w));
+                ocb_step32(delta, Ls, L4, kb + 32 * t);
+            }
+        }
+    } else {
+        reg_dec<kTtRegs>();
+        const uint64_t npairs = a.tt_blocks / 64;
+        const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
+        const uint64_t per = (npairs + nw - 1) / nw;
+        const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
+        const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
+        if (q0 < q1) {
+            uint4 cur[2], nxt[2], dl[2];
+            dl[0] = a.o.work->off0;
+            xor4(dl[0], ocb_gray_sum(Ls, q0 * 64 + lane + 1));
+            cur[0] = ld_stream(a.o.in + q0 * 64 + lane); cur[1] = ld_stream(a.o.in + q0 * 64 + 32 + lane);
+            for (uint64_t q = q0; q < q1; ++q) {
+                const uint64_t k = q * 64 + lane;
+                if (q + 1 < q1) { nxt[0] = ld_stream(a.o.in + k + 64); nxt[1] = ld_stream(a.o.in + k + 96); }
+                dl[1] = dl[0];
+                ocb_step32(dl[1], Ls, L4, k);
+                uint32_t st[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    xor4(sum, cur[i]);
+                    st[i][0] = cur[i].x ^ dl[i].x ^ rk[0]; st[i][1] = cur[i].y ^ dl[i].y ^ rk[1];
+                    st[i][2] = cur[i].z ^ dl[i].z ^ rk[2]; st[i][3] = cur[i].w ^ dl[i].w ^ rk[3];
+                }
+                enc_finish_n<NR, 1, 2>(lb, st, rk, dl);
+                st_stream(a.o.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
+                st_stream(a.o.out + k + 32, make_uint4(st[1][0], st[1][1], st[1][2], st[1][3]));
+                dl[0] = dl[1];
+                ocb_step32(dl[0], Ls, L4, k + 32);
+                cur[0] = nxt[0]; cur[1] = nxt[1];
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        sum.x ^= __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y ^= __shfl_xor_sync(0xffffffffu, sum.y, o);
+        sum.z ^= __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w ^= __shfl_xor_sync(0xffffffffu, sum.w, o);
+    }
+    if (lane == 0 && (sum.x | sum.y | sum.z | sum.w)) {
+        atomicXor(&a.o.work->checksum[0], sum.x); atomicXor(&a.o.work->checksum[1], sum.y);
+        atomicXor(&a.o.work->checksum[2], sum.z); atomicXor(&a.o.work->checksum[3], sum.w);
+    }
+}
+
+template <int NR>
+static cudaError_t launch_ocb_hybrid_nr(const OcbBulkArgs &o, uint64_t bs_blocks, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(ocb_hybrid_kernel<NR>);
+    if (e != cudaSuccess) return e;
+    static OcbHybridArgs a;                              // 8 KB of planes: not on the stack (callers hold the library lock)
+    a.o = o;
+    a.tt_blocks = (o.nblocks - bs_blocks) & ~1023ull;
+    bs_make_key_planes_full(o.ks.w, NR, &a.bs);
+    const uint64_t need = (o.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
+    ocb_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kOcbTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 struct OcbFinishArgs {
     uaes_keysched ks;            // encryption schedule
     const uint8_t *in;
@@ -224,6 +361,12 @@ __global__ void __launch_bounds__(kThreads, 1) ocb_finish_kernel(const __grid_co
 template <int NR, bool ENC>
 static cudaError_t launch_ocb_bulk_nr(const OcbBulkArgs &a, cudaStream_t st)
 {
+    if (ENC) {                                           // encryption of enough data: with the co-runner
+        ctr_tuning_init();
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_OCB_BS_PERMILLE", kEcbDefaultShare);
+        if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048)
+            return launch_ocb_hybrid_nr<NR>(a, a.nblocks / 1024 * (uint64_t)share, st);
+    }
     cudaError_t e = opt_in_smem(ocb_bulk_kernel<NR, ENC>);
     if (e != cudaSuccess) return e;
     ocb_bulk_kernel<NR, ENC><<<grid_for((a.nblocks + 255) / 256), kThreads, kDynSmem, st>>>(a);

@@ -229,6 +229,25 @@ def test_ecb_bitsliced_corunner(uaes, orc, bits):
 
 
 @pytest.mark.parametrize("bits", [128, 256])
+def test_ocb_bitsliced_corunner(uaes, orc, bits):
+    """OCB encryption with the co-runner forced on for small calls: offsets, checksum and tag must not
+    depend on which kind of warp handled a block"""
+    a = uaes.MicroAES(bits)
+    try:
+        for share, n, alen in ((1024, 16 * 2048, 0), (512, 16 * 5000 + 7, 20), (300, 16 * 70001, 5), (1024, 16 * 3071 + 15, 0),
+                               (1, 16 * 4096, 33)):
+            uaes.ctr_tuning(-1, share, 0)
+            key, nonce = rnd(f"oh-k{bits}{n}", bits // 8), rnd(f"oh-n{bits}{n}", 12)
+            aad, data = rnd(f"oh-a{bits}{n}", alen), rnd(f"oh-d{bits}{n}", n)
+            want = orc.ocb_encrypt(key, nonce, aad, data)
+            got = a.AES_OCB_encrypt(key, nonce, aad, data)
+            assert got[-16:] == want[-16:] and got == want, (share, n)
+            assert a.AES_OCB_decrypt(key, nonce, aad, want) == (0, data)
+    finally:
+        uaes.ctr_tuning(385, 190, 1 << 20)
+
+
+@pytest.mark.parametrize("bits", [128, 256])
 def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
     """512-byte sector encryption with the ALU co-runner warps forced on for small calls, at several
     splits between table-driven and bitsliced tiles, ragged last tiles, sector numbers across 2^32"""
