@@ -96,6 +96,14 @@ __device__ __forceinline__ void dec_round(uint32_t lb, uint32_t &s0, uint32_t &s
                                           uint32_t &s3, const uint32_t *dk)
 {
     // InvShiftRows: column j takes row r from column j - r
+#ifndef UAES_LUT_PRMT
+    const uint32_t u0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s2) ^ lut<3, kOffT3>(lb, s1) ^ dk[0];
+    const uint32_t u1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s3) ^ lut<3, kOffT3>(lb, s2) ^ dk[1];
+    const uint32_t u2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s3) ^ dk[2];
+    const uint32_t u3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s2) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s0) ^ dk[3];
+    s0 = u0; s1 = u1; s2 = u2; s3 = u3;
+    return;
+#endif
     const uint32_t t0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s3) ^ rot16(lut<2, kOffT0>(lb, s2) ^ lut<3, kOffT1>(lb, s1)) ^ dk[0];
     const uint32_t t1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s0) ^ rot16(lut<2, kOffT0>(lb, s3) ^ lut<3, kOffT1>(lb, s2)) ^ dk[1];
     const uint32_t t2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s1) ^ rot16(lut<2, kOffT0>(lb, s0) ^ lut<3, kOffT1>(lb, s3)) ^ dk[2];
@@ -107,8 +115,8 @@ __device__ __forceinline__ uint32_t dec_last_col(uint32_t lb, uint32_t a, uint32
                                                  uint32_t d)
 {
     // Td4 holds Si(x) in all four bytes
-    const uint32_t u0 = lut<0, kOffT2>(lb, a), u1 = lut<1, kOffT2>(lb, b);
-    const uint32_t u2 = lut<2, kOffT2>(lb, c), u3 = lut<3, kOffT2>(lb, d);
+    const uint32_t u0 = lut<0, kOffTd4>(lb, a), u1 = lut<1, kOffTd4>(lb, b);
+    const uint32_t u2 = lut<2, kOffTd4>(lb, c), u3 = lut<3, kOffTd4>(lb, d);
     return bsel(bsel(u0, u1, 0x00ff00ffu), bsel(u2, u3, 0x00ff00ffu), 0x0000ffffu);
 }
 

@@ -60,8 +60,8 @@ __device__ __forceinline__ uint32_t dyn_smem_size()
 template <bool ENC>
 __device__ __forceinline__ uint32_t setup_tables(const void *dyn)
 {
-    const uint32_t base = align_table_base(dyn);
-    if (base + kEncTableBytes > smem_u32(dyn) + dyn_smem_size()) __trap();
+    const uint32_t base = ENC ? align_table_base(dyn) : dec_table_base(dyn);
+    if (base + (ENC ? kEncTableBytes : kDecTableBytes) > smem_u32(dyn) + dyn_smem_size()) __trap();
     if (ENC) init_enc_tables(base); else init_dec_tables(base);
     __syncthreads();
     uint32_t lanebase = base + (threadIdx.x & 31) * 4;

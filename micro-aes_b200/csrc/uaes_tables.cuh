@@ -119,7 +119,16 @@ constexpr uint32_t kOffT0 = 0, kOffT1 = 32768, kOffT2 = kTablePairBytes, kOffT3 
 constexpr uint32_t kOffT0 = 0, kOffT1 = 128, kOffT2 = kTablePairBytes, kOffT3 = kTablePairBytes + 128;
 #endif
 constexpr uint32_t kEncTableBytes  = 2 * kTablePairBytes;   // Te0|Te1, Te2|Te3
-constexpr uint32_t kDecTableBytes  = 2 * kTablePairBytes;   // Td0|Td1, Td4|(unused)
+#ifndef UAES_LUT_PRMT
+// decryption keeps all four Td tables, the inverse S-box and (for XTS tweaks) Te0: three pair regions.
+// They fit because IDP.4A addressing needs no 64 KiB alignment of the base (uaes_dec_table_base).
+constexpr uint32_t kDecTableBytes  = 3 * kTablePairBytes;   // Td0|Td1, Td2|Td3, Td4|Te0
+constexpr uint32_t kOffT4 = 2 * kTablePairBytes, kOffT5 = 2 * kTablePairBytes + 32768;
+constexpr uint32_t kOffTd4 = kOffT4, kOffDecTe0 = kOffT5;
+#else
+constexpr uint32_t kDecTableBytes  = 2 * kTablePairBytes;   // Td0|Td1, Td4|Te0 (Td2/Td3 by a 16-bit rotate)
+constexpr uint32_t kOffTd4 = kOffT2, kOffDecTe0 = kOffT3;
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -166,12 +175,28 @@ __device__ __forceinline__ void init_enc_tables(uint32_t base)
     fill_pair(base + kTablePairBytes, c_te0, 16, c_te0, 24);
 }
 
-// decryption keeps Td0|Td1 and derives Td2/Td3 by a 16-bit rotate of the looked-up word, so
-// that the second pair region can hold Td4 (inverse S-box) for the last round
+// base of the decryption tables inside the dynamic window
+__device__ __forceinline__ uint32_t dec_table_base(const void *dyn_smem)
+{
+#ifndef UAES_LUT_PRMT
+    return (smem_u32(dyn_smem) + 127u) & ~127u;
+#else
+    return align_table_base(dyn_smem);
+#endif
+}
+
+// Td0..Td3, the inverse S-box (Td4, last round) and Te0 (XTS decryption encrypts its tweaks).  With
+// PRMT addressing only two pair regions fit behind the aligned base: Td2/Td3 are then Td0/Td1 rotated
+// by 16 bits after the lookup (extra ALU work, which is why that layout is not the default).
 __device__ __forceinline__ void init_dec_tables(uint32_t base)
 {
     fill_pair(base, c_td0, 0, c_td0, 8);
-    fill_pair(base + kTablePairBytes, c_td4, 0, c_td4, 0);
+#ifndef UAES_LUT_PRMT
+    fill_pair(base + kTablePairBytes, c_td0, 16, c_td0, 24);
+    fill_pair(base + 2 * kTablePairBytes, c_td4, 0, c_te0, 0);
+#else
+    fill_pair(base + kTablePairBytes, c_td4, 0, c_te0, 0);
+#endif
 }
 
 // ---------------------------------------------------------------- the lookup primitive

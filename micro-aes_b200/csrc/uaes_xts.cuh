@@ -33,19 +33,13 @@ __device__ __forceinline__ void enc_block_te0(uint32_t lb, uint32_t &s0, uint32_
     s0 = o0; s1 = o1; s2 = o2; s3 = o3;
 }
 
-// decrypt kernels: pair 0 = Td0|Td1, pair 1 = Td4|Te0
-__device__ __forceinline__ void init_xts_dec_tables(uint32_t base)
-{
-    fill_pair(base, c_td0, 0, c_td0, 8);
-    fill_pair(base + kTablePairBytes, c_td4, 0, c_te0, 0);
-}
-
+// decrypt kernels use init_dec_tables (uaes_tables.cuh): the Td tables, Td4 and Te0 for the tweaks
 template <bool ENC>
 __device__ __forceinline__ uint32_t setup_xts_tables(const void *dyn)
 {
-    const uint32_t base = align_table_base(dyn);
-    if (base + kEncTableBytes > smem_u32(dyn) + dyn_smem_size()) __trap();
-    if (ENC) init_enc_tables(base); else init_xts_dec_tables(base);
+    const uint32_t base = ENC ? align_table_base(dyn) : dec_table_base(dyn);
+    if (base + (ENC ? kEncTableBytes : kDecTableBytes) > smem_u32(dyn) + dyn_smem_size()) __trap();
+    if (ENC) init_enc_tables(base); else init_dec_tables(base);
     __syncthreads();
     uint32_t lanebase = base + (threadIdx.x & 31) * 4;
     asm volatile("" : "+r"(lanebase)::"memory");
@@ -92,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) xts_sectors_kernel(const __grid_c
         const uint64_t sec = a.first_sector + tile * 32 + lane;
         uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
         if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.k2.w);
-        else     enc_block_te0<NR, kOffT3>(lb, e0, e1, e2, e3, a.k2.w);
+        else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.k2.w);
 
         const uint64_t left = a.nsectors - tile * 32;
         const int nsec = left < 32 ? (int)left : 32;
@@ -230,7 +224,7 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
         const uint64_t sec = a.x.first_sector + sec0 + lane;
         uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
         if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
-        else     enc_block_te0<NR, kOffT3>(lb, e0, e1, e2, e3, a.x.k2.w);
+        else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.x.k2.w);
         auto tweak_of = [&](int t, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
             Tweak tw;
             tw.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, t) << 32 | __shfl_sync(0xffffffffu, e0, t);
@@ -307,7 +301,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
         const uint64_t sec = a.x.first_sector + sec0 + lane;
         uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
         if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
-        else     enc_block_te0<NR, kOffT3>(lb, e0, e1, e2, e3, a.x.k2.w);
+        else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.x.k2.w);
         const uint4 *src = a.x.in + sec0 * 32 + lane;
         uint4 *dst = a.x.out + sec0 * 32 + lane;
         uint4 cur[2], nxt[2];
