@@ -100,6 +100,31 @@ UAES_HD void bs_round(uint32_t s[128], const uint32_t *kp)
     for (int p = 0; p < 128; ++p) s[p] = o[p];
 }
 
+// one round, middle or last (no MixColumns), chosen at run time: lets the caller keep ALL rounds in one
+// loop body (instruction-cache footprint: one S-box layer instead of two)
+UAES_HD void bs_round_or_last(uint32_t s[128], const uint32_t *kp, bool last)
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sbox_bitsliced(s + 8 * i);
+    uint32_t o[128];
+    if (!last) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            bs_mix_column<0>(s + 8 * (4 * c), s + 8 * (4 * ((c + 1) & 3) + 1), s + 8 * (4 * ((c + 2) & 3) + 2),
+                             s + 8 * (4 * ((c + 3) & 3) + 3), kp + 32 * c, o + 32 * c);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    o[8 * (4 * c + r) + b] = s[8 * (4 * ((c + r) & 3) + r) + b] ^ kp[8 * (4 * c + r) + b];
+    }
+#pragma unroll
+    for (int p = 0; p < 128; ++p) s[p] = o[p];
+}
+
 // last round: SubBytes, ShiftRows, AddRoundKey(kp)
 UAES_HD void bs_last_round(uint32_t s[128], const uint32_t *kp)
 {
@@ -212,17 +237,26 @@ struct BsKeyPlanesFull {
     uint32_t k[kBsMaxRounds + 1][128];      // round keys 0..NR
 };
 
-// rijndaelEncrypt (micro_aes.c:242-259) on 32 blocks held as planes
-template <int NR>
+// rijndaelEncrypt (micro_aes.c:242-259) on 32 blocks held as planes.  MERGED: all rounds in one loop body
+// (smaller instruction footprint; measured better for CTR / ECB / XTS / CFB, worse for OCB, whose
+// co-runner keeps more values live across the rounds).
+template <int NR, bool MERGED = true>
 UAES_HD void bs_encrypt_planes(uint32_t s[128], const BsKeyPlanesFull &kp)
 {
 #pragma unroll
     for (int p = 0; p < 128; ++p) s[p] ^= kp.k[0][p];
+    if (MERGED) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int r = 1; r < NR; ++r) bs_round(s, kp.k[r]);
-    bs_last_round(s, kp.k[NR]);
+        for (int r = 1; r <= NR; ++r) bs_round_or_last(s, kp.k[r], r == NR);    // one loop body, see ctr_kernel
+    } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int r = 1; r < NR; ++r) bs_round(s, kp.k[r]);
+        bs_last_round(s, kp.k[NR]);
+    }
 }
 
 // ---- decryption: the equivalent inverse cipher on planes ---------------------------------------

@@ -156,9 +156,10 @@ __device__ __forceinline__ void ctr_bitsliced_warp(const CtrArgs &a, uint32_t lb
         }
         uint32_t s[128];
         bs_first_rounds(s, lane, (uint32_t)(vc >> 8) & 0xfcu, a.bs.k0, um);
+        // all rounds in ONE loop body (the last one skips MixColumns): a second copy of the S-box layer
+        // for the last round cost 1.2 % through the instruction cache (1008 -> 1020 GiB/s)
 #pragma unroll 1
-        for (int r = 3; r < NR; ++r) bs_round(s, a.bs.k[r - 3]);
-        bs_last_round(s, a.bs.k[NR - 3]);
+        for (int r = 3; r <= NR; ++r) bs_round_or_last(s, a.bs.k[r - 3], r == NR);
         // XOR with the data: slot t of all lanes = one coalesced 512-byte row.  The loads are
         // software-pipelined one batch ahead (the first batch goes out before the transposes).
         const int64_t k0 = (int64_t)(u0 - a.v0) + lane;      // block index of slot 0; >= tt_blocks
@@ -201,7 +202,10 @@ __global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_ke
         // launch allocation is 65536 / threads rounded down to 8; hand the table warps' surplus to
         // the bitsliced warpgroup (whose 128-plane state needs it)
         constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
-        constexpr int kTtRegs = ILP == 1 ? 80 : 104;
+#ifndef UAES_TT_REGS
+#define UAES_TT_REGS 104
+#endif
+        constexpr int kTtRegs = ILP == 1 ? 80 : UAES_TT_REGS;
         constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
         constexpr int kBsRegs = (kBsRegs0 > 232 ? 232 : kBsRegs0) / 8 * 8;
         if (threadIdx.x >= kCtrThreads) {
@@ -560,7 +564,7 @@ static long long g_ctr_bs_min = 1ll << 20;
 //   385  = the same with two blocks per thread in flight (default; the co-runner's instructions
 //          lengthen every lookup round trip, the second block hides it: 968 -> 1006 GiB/s)
 //   512 / 768 / 1024 = table-driven warps only
-constexpr int kCtrDefaultGeometry = 385, kCtrDefaultShare = 190;
+constexpr int kCtrDefaultGeometry = 385, kCtrDefaultShare = 195;
 
 static void ctr_tuning_init()
 {
@@ -596,7 +600,7 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     }
 }
 
-constexpr int kEcbDefaultShare = 185;   // 791 / 830 / 849 / 864 / 814 GiB/s at 0 / 100 / 140 / 180 / 220 (AES-128, profiles/r1_ecb_hybrid_sweep.txt)
+constexpr int kEcbDefaultShare = 195;   // 791 / 830 / 849 / 864 / 814 GiB/s at 0 / 100 / 140 / 180 / 220 (AES-128, profiles/r1_ecb_hybrid_sweep.txt)
 
 template <int NR, bool CFB = false>
 static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, cudaStream_t st, const uint32_t *iv = nullptr)

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
     constexpr int kTtWarps = kOcbTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kOcbTtThreads + kBsThreads)) / 8 * 8;
     constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kOcbTtThreads / kBsThreads;
-    const uint4 L4 = Ls[4];
     const uint64_t nblocks = a.o.nblocks;
     uint4 sum = make_uint4(0, 0, 0, 0);
 
@@ -182,34 +181,44 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
         const uint64_t p1 = p0 + per < ntiles ? p0 + per : ntiles;
         for (uint64_t tile = p0; tile < p1; ++tile) {
             const uint64_t kb = a.tt_blocks + tile * 1024 + lane;
-            uint4 d0 = a.o.work->off0;
-            xor4(d0, ocb_gray_sum(Ls, kb + 1));
-            uint4 delta = d0;
             uint32_t s[128];
+            {   // whitening in; nothing of this phase but the checksum stays live across the rounds
+                const uint4 L4 = Ls[4];
+                uint4 delta = a.o.work->off0;
+                xor4(delta, ocb_gray_sum(Ls, kb + 1));
 #pragma unroll
-            for (int tb = 0; tb < 32; tb += 8) {
-                uint4 v[8];
+                for (int tb = 0; tb < 32; tb += 8) {
+                    uint4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < nblocks ? ld_stream(a.o.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+                    for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < nblocks ? ld_stream(a.o.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    xor4(sum, v[i]);                                 // out-of-range rows are zero
-                    s[tb + i] = v[i].x ^ delta.x; s[32 + tb + i] = v[i].y ^ delta.y;
-                    s[64 + tb + i] = v[i].z ^ delta.z; s[96 + tb + i] = v[i].w ^ delta.w;
-                    ocb_step32(delta, Ls, L4, kb + 32 * (tb + i));
+                    for (int i = 0; i < 8; ++i) {
+                        xor4(sum, v[i]);                             // out-of-range rows are zero
+                        s[tb + i] = v[i].x ^ delta.x; s[32 + tb + i] = v[i].y ^ delta.y;
+                        s[64 + tb + i] = v[i].z ^ delta.z; s[96 + tb + i] = v[i].w ^ delta.w;
+                        ocb_step32(delta, Ls, L4, kb + 32 * (tb + i));
+                    }
                 }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
-            bs_encrypt_planes<NR>(s, a.bs);
+            bs_encrypt_planes<NR, false>(s, a.bs);
 #pragma unroll
             for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
-            delta = d0;
+            {   // whitening out: the offsets are walked again from the block index (opaque to the compiler,
+                // so that the first walk's values are not kept in registers across the rounds)
+                uint64_t kb2 = kb;
+                uint32_t four = 4;
+                asm volatile("" : "+l"(kb2), "+r"(four));
+                const uint4 L4 = Ls[four];
+                uint4 delta = a.o.work->off0;
+                xor4(delta, ocb_gray_sum(Ls, kb2 + 1));
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                if (kb + 32 * t < nblocks)
-                    st_stream(a.o.out + kb + 32 * t, make_uint4(s[t] ^ delta.x, s[32 + t] ^ delta.y, s[64 + t] ^ delta.z, s[96 + t] ^ delta.w));
-                ocb_step32(delta, Ls, L4, kb + 32 * t);
+                for (int t = 0; t < 32; ++t) {
+                    if (kb2 + 32 * t < nblocks)
+                        st_stream(a.o.out + kb2 + 32 * t, make_uint4(s[t] ^ delta.x, s[32 + t] ^ delta.y, s[64 + t] ^ delta.z, s[96 + t] ^ delta.w));
+                    ocb_step32(delta, Ls, L4, kb2 + 32 * t);
+                }
             }
         }
     } else {
@@ -221,6 +230,7 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
         const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
         const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
         if (q0 < q1) {
+            const uint4 L4 = Ls[4];
             uint4 cur[2], nxt[2], dl[2];
             dl[0] = a.o.work->off0;
             xor4(dl[0], ocb_gray_sum(Ls, q0 * 64 + lane + 1));
@@ -363,7 +373,7 @@ static cudaError_t launch_ocb_bulk_nr(const OcbBulkArgs &a, cudaStream_t st)
 {
     if (ENC) {                                           // encryption of enough data: with the co-runner
         ctr_tuning_init();
-        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_OCB_BS_PERMILLE", kEcbDefaultShare);
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_OCB_BS_PERMILLE", 185);
         if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048)
             return launch_ocb_hybrid_nr<NR>(a, a.nblocks / 1024 * (uint64_t)share, st);
     }

@@ -262,7 +262,7 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
 }
 
 constexpr int kXtsTtThreads = 384;
-constexpr int kXtsDefaultShare = 148;
+constexpr int kXtsDefaultShare = 165;
 
 template <int NR, bool ENC>
 __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
