@@ -80,6 +80,7 @@ uaes_u64 uaes_kernel_launches(void);
  *   bs_permille      share of the blocks, in 1/1024, given to the bitsliced ALU co-runner warps
  *                    (0 = co-runner off)
  *   bs_min_blocks    calls shorter than this many 16-byte blocks never use the co-runner
+ *                    (default 2^23 = 128 MiB; the same threshold serves ECB, XTS, OCB and CFB)
  * A negative value leaves that setting unchanged.  Results do not depend on any of them. */
 void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks);
 

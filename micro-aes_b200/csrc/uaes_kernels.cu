@@ -555,7 +555,8 @@ static int env_int(const char *name, int dflt)
 }
 
 static int g_ctr_threads = 0, g_ctr_share = -1;
-static long long g_ctr_bs_min = 1ll << 20;
+static long long g_ctr_bs_min = 1ll << 23;    // 128 MiB: below it the co-runner's whole passes (1024 blocks x 592 warps)
+                                               // quantise badly: 606 vs 659 GiB/s at 32 MiB, 716 vs 782 at 64 MiB, 879 vs 863 at 128 MiB
 
 // Measured on B200, AES-128, 16 GiB (profiles/r1_ctr_hybrid_sweep.txt): table-driven warps alone
 // 942-946 GiB/s; with the co-runner 1000 / 1006 / 1004 / 980 GiB/s at 170 / 185 / 200 / 215 per

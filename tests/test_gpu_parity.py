@@ -182,7 +182,7 @@ def test_ctr_bitsliced_corunner(uaes, orc, torch, bits):
                 assert host(dst, 0, n) == orc.ctr(key, iv, data, first_block=first), (threads, share, n, first)
                 assert host(dst, n, n + 16) == bytes(16)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 20)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -225,7 +225,7 @@ def test_ecb_bitsliced_corunner(uaes, orc, bits):
             orc.lib.oracle_cfb_decrypt(bits, key, iv, data, n, o)
             assert a.AES_CFB_decrypt(key, iv, data) == o.raw[:n], (share, n)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 20)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -244,7 +244,7 @@ def test_ocb_bitsliced_corunner(uaes, orc, bits):
             assert got[-16:] == want[-16:] and got == want, (share, n)
             assert a.AES_OCB_decrypt(key, nonce, aad, want) == (0, data)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 20)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -266,7 +266,7 @@ def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
             uaes.xts_sectors(bits, keys, first, 512, data, len(data), back, False)
             assert (0, back.raw) == orc.xts_sectors(keys, first, 512, data, encrypt=False), (share, first, ns)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 20)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 192, 256])
