@@ -202,10 +202,7 @@ __global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_ke
         // launch allocation is 65536 / threads rounded down to 8; hand the table warps' surplus to
         // the bitsliced warpgroup (whose 128-plane state needs it)
         constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
-#ifndef UAES_TT_REGS
-#define UAES_TT_REGS 104
-#endif
-        constexpr int kTtRegs = ILP == 1 ? 80 : UAES_TT_REGS;
+        constexpr int kTtRegs = ILP == 1 ? 80 : 104;       // 96 and 112 measured worse (profiles/r1_ctr_hybrid_sweep.txt)
         constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
         constexpr int kBsRegs = (kBsRegs0 > 232 ? 232 : kBsRegs0) / 8 * 8;
         if (threadIdx.x >= kCtrThreads) {
