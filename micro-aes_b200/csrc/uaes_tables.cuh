@@ -151,15 +151,18 @@ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int n)   // n in {0,8,16,
 __device__ __forceinline__ void fill_pair(uint32_t region, const WordTable &srcA, int rotA,
                                           const WordTable &srcB, int rotB)
 {
-    // 256 rows x 64 words; consecutive threads write consecutive words (conflict free)
-    for (uint32_t w = threadIdx.x; w < 256u * 64u; w += blockDim.x) {
-        const uint32_t row = w >> 6, col = w & 63;
-        const uint32_t v = col < 32 ? rotl32(srcA.v[row], rotA) : rotl32(srcB.v[row], rotB);
+    // 256 rows x 2 tables x 32 replicas = 4096 16-byte stores (four replicas each); consecutive
+    // threads write consecutive 16-byte slots (conflict free).  The fill is the fixed cost of every
+    // launch (a few microseconds), which is what short calls are made of.
+    for (uint32_t q = threadIdx.x; q < 4096u; q += blockDim.x) {
+        const uint32_t row = q >> 4, tbl = (q >> 3) & 1u, quad = q & 7u;
+        const uint32_t v = tbl ? rotl32(srcB.v[row], rotB) : rotl32(srcA.v[row], rotA);
 #ifndef UAES_LUT_PRMT
-        sts32(region + (col >> 5) * 32768 + row * 128 + (col & 31) * 4, v);
+        const uint32_t ad = region + tbl * 32768u + row * 128u + quad * 16u;
 #else
-        sts32(region + row * 256 + col * 4, v);
+        const uint32_t ad = region + row * 256u + tbl * 128u + quad * 16u;
 #endif
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(ad), "r"(v) : "memory");
     }
 }
 
