@@ -5,6 +5,7 @@ import ctypes
 import os
 import struct
 import subprocess
+import sys
 
 import pytest
 
@@ -73,6 +74,10 @@ def test_general_32_block_path_matches_oracle(harness, bits):
         assert (0, back.raw) == orc.ecb_decrypt(key, data), (bits, trial)
 
 
-def test_generated_sbox_is_current(harness):
-    """the committed header is what tools/gen_sbox_lut3.py emits for its verified mapping"""
+def test_generated_sbox_is_current(harness, tmp_path):
+    """the committed header is exactly what tools/gen_sbox_lut3.py emits (the generator checks both
+    networks against the S-box tables on all 256 inputs before it writes anything)"""
     assert harness.bs_host_sbox_lut3_count() <= 80
+    out = tmp_path / "uaes_sbox_lut3.cuh"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_sbox_lut3.py"), "4", str(out)])
+    assert out.read_text() == open(os.path.join(CSRC, "uaes_sbox_lut3.cuh")).read()

@@ -7,7 +7,8 @@ restated below and checked exhaustively against an S-box computed from the FIPS-
 Step 2 maps the gate network onto 3-input look-up tables (one LOP3.LUT instruction each on
 sm_100a): 3-feasible cut enumeration, area-flow start, annealed local search on the cut choice.
 Step 3 simulates the mapped network on all 256 inputs and writes
-micro-aes_b200/csrc/uaes_sbox_lut3.cuh.   Run:  python tools/gen_sbox_lut3.py [seeds]
+micro-aes_b200/csrc/uaes_sbox_lut3.cuh.   Run:  python tools/gen_sbox_lut3.py [seeds [output]]
+(the committed header is the output of the default, 4 seeds; tests/test_bitslice_host.py regenerates it)
 """
 import itertools, math, os, random, sys
 
@@ -179,7 +180,7 @@ def enum_cuts(nodes,order):
             for c2 in get(b):
                 u=c1|c2
                 if len(u)<=K: cs.add(u)
-        cs=list(cs)
+        cs=sorted(cs, key=lambda c: sorted(c))       # deterministic order (string hashes vary per process)
         # drop dominated cuts (superset of another cut)
         cs=[c for c in cs if not any(o<c for o in cs)]
         cuts[n]=cs+[frozenset([n])]
@@ -218,7 +219,7 @@ def optimize(nodes,order,cuts,outs,iters=20000,seed=0):
     import math
     for it in range(iters):
         need=mapping_area(nodes,outs,choice)
-        n=rnd.choice(list(need))
+        n=rnd.choice(sorted(need))
         c=rnd.choice(nontriv[n])
         if c==choice[n]: continue
         old=choice[n]; choice[n]=c
@@ -393,7 +394,8 @@ if __name__ == "__main__":
     nodes, order = build(g); cuts = enum_cuts(nodes, order)
     outs = [f"S{i}" for i in range(8)]
     res = None
-    for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
+    seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    for seed in range(seeds):
         b = optimize(nodes, order, cuts, outs, iters=30000, seed=seed)
         if res is None or b[0] < res[0]: res = b
     luts = lut_immediates(nodes, order, res[1], outs)
@@ -405,13 +407,13 @@ if __name__ == "__main__":
     assert all(evalc(gi, x) == Sinv[x] for x in range(256)), "derived network is not the inverse S-box"
     nodes_i, order_i = build(gi); cuts_i = enum_cuts(nodes_i, order_i)
     res_i = None
-    for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
+    for seed in range(seeds):
         b = optimize(nodes_i, order_i, cuts_i, outs, iters=30000, seed=seed)
         if res_i is None or b[0] < res_i[0]: res_i = b
     luts_i = lut_immediates(nodes_i, order_i, res_i[1], outs)
     verify(luts_i, Sinv)
     here = os.path.dirname(os.path.abspath(__file__))
-    out = os.path.join(here, "..", "micro-aes_b200", "csrc", "uaes_sbox_lut3.cuh")
+    out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(here, "..", "micro-aes_b200", "csrc", "uaes_sbox_lut3.cuh")
     emit(luts, luts_i, out)
     print(f"S-box: {len(g)} gates -> {len(luts)} LOP3; inverse S-box: {len(gi)} gates -> {len(luts_i)} LOP3; "
           f"both verified on 256 inputs; wrote {os.path.normpath(out)}")
