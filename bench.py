@@ -254,6 +254,8 @@ def run_gpu(args):
             uaes.ecb(128, key, src, nbytes, dst, True)
         elif wl == "ecb128dec":
             uaes.ecb(128, key, src, nbytes, dst, False)
+        elif wl == "xts256unit":    # the reference's AES_XTS_encrypt: the whole shard is ONE data unit
+            uaes.xts_unit(256, keys64, IV + bytes(4), src, nbytes, dst, True)
         elif wl == "xts256dec":
             uaes.xts_sectors(256, keys64, first_block // 32, 512, src, nbytes, dst, False)
         elif wl == "ocb128":
@@ -395,7 +397,7 @@ def run_gpu(args):
                                     "xts256": "uaes::xts_sectors_kernel<14,true>", "gcm128": "uaes::gcm_bulk_kernel<10,0>",
                                     "ecb128dec": "uaes::ecb_kernel<10,false>", "xts256dec": "uaes::xts_sectors_kernel<14,false>",
                                     "gcmsiv128": "uaes::gcm_bulk_kernel<10,1,true> + uaes::ctr32_kernel<10>",
-                                    "ocb128": "uaes::ocb_bulk_kernel<10,true>", "ccm128batch": "uaes::ccm_batch_kernel<10> (1 KiB messages, one per lane)", "eax128batch": "uaes::eax_batch_kernel<10> (1 KiB messages, one per lane)", "siv128batch": "uaes::siv_batch_kernel<10> (1 KiB messages, one per lane)", "gcm128batch": "uaes::gcm_batch_kernel<10> (1 KiB messages, one per lane)", "cbc128dec": "uaes::chain_dec_kernel<10,true>", "cfb128dec": "uaes::chain_dec_kernel<10,false>"}[wl],
+                                    "ocb128": "uaes::ocb_bulk_kernel<10,true>", "xts256unit": "uaes::xts_unit_hybrid_kernel<14>", "ccm128batch": "uaes::ccm_batch_kernel<10> (1 KiB messages, one per lane)", "eax128batch": "uaes::eax_batch_kernel<10> (1 KiB messages, one per lane)", "siv128batch": "uaes::siv_batch_kernel<10> (1 KiB messages, one per lane)", "gcm128batch": "uaes::gcm_batch_kernel<10> (1 KiB messages, one per lane)", "cbc128dec": "uaes::chain_dec_kernel<10,true>", "cfb128dec": "uaes::chain_dec_kernel<10,false>"}[wl],
                          "kernel_ms": round(kernel_ms, 4),
                          "algorithmic_bytes_per_launch": 2 * nbytes},
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -416,7 +418,7 @@ def main():
     ap.add_argument("--e2e-gib", type=float, default=0.0, help="host buffer for the e2e leg (default: auto)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-slice-mib", type=int, default=256)
-    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "ecb128dec", "xts256", "xts256dec", "gcm128", "gcmsiv128", "cbc128dec", "cfb128dec", "ocb128", "ccm128batch", "eax128batch", "siv128batch", "gcm128batch"],
+    ap.add_argument("--workload", default="ctr128", choices=["ctr128", "ctr256", "ecb128", "ecb128dec", "xts256", "xts256dec", "gcm128", "gcmsiv128", "cbc128dec", "cfb128dec", "ocb128", "ccm128batch", "eax128batch", "siv128batch", "gcm128batch", "xts256unit"],
                     help="ctr128 is the headline (BASELINE.json metric); the others are the secondary configs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")

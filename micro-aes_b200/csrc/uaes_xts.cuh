@@ -7,6 +7,10 @@
 
 namespace uaes {
 
+// geometry of the kernels with the bitsliced co-runner (table-driven threads; share of the work, per 1024)
+constexpr int kXtsTtThreads = 384;
+constexpr int kXtsDefaultShare = 165;
+
 // Encryption with ONLY Te0 available at table offset OFF (decrypt kernels keep Te0 next to the
 // inverse tables so that they can still encrypt sector tweaks): Te_k = Te0 rotated by 8k bits.
 template <int NR, uint32_t OFF>
@@ -117,6 +121,36 @@ struct XtsUnitArgs {
     uint32_t tail;               // len % 16 (stealing when non-zero)
 };
 
+// ciphertext stealing (micro_aes.c:1037-1053) on one thread with the byte-wise cipher
+template <bool ENC>
+__device__ inline void xts_steal_tail(const XtsUnitArgs &a, const Tweak &T0)
+{
+    const uint64_t m = a.nblocks;                              // index of the last full block
+    const Tweak Tm = xts_jump(T0, m), Tn = xts_shl(Tm, 1);
+    const uint8_t *x = (const uint8_t *)(a.in + m);
+    uint8_t *y = (uint8_t *)(a.out + m);
+    uint8_t first[16], part[16];
+    for (int i = 0; i < 16; ++i) first[i] = x[i];
+    for (uint32_t i = 0; i < a.tail; ++i) part[i] = x[16 + i];
+    auto xex = [&](uint8_t b[16], Tweak t) {
+        uint32_t tw[4], s[4];
+        tweak_words(t, tw[0], tw[1], tw[2], tw[3]);
+        for (int c = 0; c < 4; ++c)
+            s[c] = ((uint32_t)b[4 * c] | (uint32_t)b[4 * c + 1] << 8 | (uint32_t)b[4 * c + 2] << 16 | (uint32_t)b[4 * c + 3] << 24) ^ tw[c];
+        if (ENC) small_encrypt(a.k1e.w, a.k1e.rounds, s); else small_decrypt(a.k1e.w, a.k1e.rounds, s);
+        for (int c = 0; c < 4; ++c) {
+            s[c] ^= tw[c];
+            for (int i = 0; i < 4; ++i) b[4 * c + i] = (uint8_t)(s[c] >> (8 * i));
+        }
+    };
+    // encrypt: block m under T_m, the stolen block under alpha*T_m; decrypt: the other way round
+    xex(first, ENC ? Tm : Tn);
+    for (uint32_t i = a.tail; i < 16; ++i) part[i] = first[i];
+    xex(part, ENC ? Tn : Tm);
+    for (int i = 0; i < 16; ++i) y[i] = part[i];
+    for (uint32_t i = 0; i < a.tail; ++i) y[16 + i] = first[i];
+}
+
 // The unit is cut into rows of 32 blocks; every warp owns a contiguous run of rows, jumps to
 // T_0 * alpha^(first block) once (ladder of squarings of alpha^128) and then steps alpha^32 per row.
 template <int NR, bool ENC>
@@ -157,33 +191,115 @@ __global__ void __launch_bounds__(kThreads, 1) xts_unit_kernel(const __grid_cons
         }
     }
 
-    // ciphertext stealing (micro_aes.c:1037-1053) on one thread with the byte-wise cipher
-    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
-        const uint64_t m = a.nblocks;                          // index of the last full block
-        const Tweak Tm = xts_jump(T0, m), Tn = xts_shl(Tm, 1);
-        const uint8_t *x = (const uint8_t *)(a.in + m);
-        uint8_t *y = (uint8_t *)(a.out + m);
-        uint8_t first[16], part[16];
-        for (int i = 0; i < 16; ++i) first[i] = x[i];
-        for (uint32_t i = 0; i < a.tail; ++i) part[i] = x[16 + i];
-        auto xex = [&](uint8_t b[16], Tweak t) {
-            uint32_t tw[4], s[4];
-            tweak_words(t, tw[0], tw[1], tw[2], tw[3]);
-            for (int c = 0; c < 4; ++c)
-                s[c] = ((uint32_t)b[4 * c] | (uint32_t)b[4 * c + 1] << 8 | (uint32_t)b[4 * c + 2] << 16 | (uint32_t)b[4 * c + 3] << 24) ^ tw[c];
-            if (ENC) small_encrypt(a.k1e.w, a.k1e.rounds, s); else small_decrypt(a.k1e.w, a.k1e.rounds, s);
-            for (int c = 0; c < 4; ++c) {
-                s[c] ^= tw[c];
-                for (int i = 0; i < 4; ++i) b[4 * c + i] = (uint8_t)(s[c] >> (8 * i));
-            }
-        };
-        // encrypt: block m under T_m, the stolen block under alpha*T_m; decrypt: the other way round
-        xex(first, ENC ? Tm : Tn);
-        for (uint32_t i = a.tail; i < 16; ++i) part[i] = first[i];
-        xex(part, ENC ? Tn : Tm);
-        for (int i = 0; i < 16; ++i) y[i] = part[i];
-        for (uint32_t i = 0; i < a.tail; ++i) y[16 + i] = first[i];
+    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) xts_steal_tail<ENC>(a, T0);
+}
+
+// ---- one data unit, encryption, with the co-runner (the reference's AES_XTS_encrypt on a large
+// buffer): rows of 32 blocks; table-driven warps own runs of row pairs, bitsliced warps runs of
+// 32-row tiles; every warp jumps to its first tweak once and then steps alpha^32 per row.
+struct XtsUnitHybridArgs {
+    XtsUnitArgs u;
+    uint64_t tt_blocks;          // blocks [0, tt_blocks): table-driven warps; a multiple of 1024
+    BsKeyPlanesFull bs;
+};
+
+template <int NR>
+__global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid_kernel(const __grid_constant__ XtsUnitHybridArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    volatile uint32_t *t0s = (volatile uint32_t *)(dyn + dyn_smem_size() - 16);
+    if (threadIdx.x == 0) {                                   // T_0 = E_K2(tweak), micro_aes.c:1026-1027
+        uint32_t s[4] = {a.u.tweak[0], a.u.tweak[1], a.u.tweak[2], a.u.tweak[3]};
+        small_encrypt(a.u.k2.w, a.u.k2.rounds, s);
+        t0s[0] = s[0]; t0s[1] = s[1]; t0s[2] = s[2]; t0s[3] = s[3];
     }
+    const uint32_t lb = setup_xts_tables<true>(dyn);          // contains __syncthreads()
+    const uint32_t lane = threadIdx.x & 31;
+    Tweak T0;
+    T0.lo = (uint64_t)t0s[1] << 32 | t0s[0];
+    T0.hi = (uint64_t)t0s[3] << 32 | t0s[2];
+    constexpr int kTtWarps = kXtsTtThreads / 32;
+    constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;
+    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
+    const uint64_t nblocks = a.u.nblocks;
+
+    if (threadIdx.x >= kXtsTtThreads) {
+        reg_inc<kBsRegs>();
+        const uint64_t ntiles = (nblocks - a.tt_blocks + 1023) / 1024;
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        const uint64_t per = (ntiles + nw - 1) / nw;
+        const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
+        const uint64_t p1 = p0 + per < ntiles ? p0 + per : ntiles;
+        if (p0 >= p1) return;
+        Tweak tstart = xts_jump(T0, a.tt_blocks + p0 * 1024 + lane);
+        for (uint64_t tile = p0; tile < p1; ++tile) {
+            const uint64_t kb = a.tt_blocks + tile * 1024 + lane;
+            Tweak t = tstart;                                  // only tstart stays live across the rounds
+            uint32_t s[128];
+#pragma unroll
+            for (int tb = 0; tb < 32; tb += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < nblocks ? ld_stream(a.u.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t w0, w1, w2, w3;
+                    tweak_words(t, w0, w1, w2, w3);
+                    s[tb + i] = v[i].x ^ w0; s[32 + tb + i] = v[i].y ^ w1; s[64 + tb + i] = v[i].z ^ w2; s[96 + tb + i] = v[i].w ^ w3;
+                    t = xts_shl(t, 32);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+            bs_encrypt_planes<NR>(s, a.bs);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+            Tweak u = tstart;
+#pragma unroll
+            for (int tt = 0; tt < 32; ++tt) {
+                uint32_t w0, w1, w2, w3;
+                tweak_words(u, w0, w1, w2, w3);
+                if (kb + 32 * tt < nblocks)
+                    st_stream(a.u.out + kb + 32 * tt, make_uint4(s[tt] ^ w0, s[32 + tt] ^ w1, s[64 + tt] ^ w2, s[96 + tt] ^ w3));
+                u = xts_shl(u, 32);
+            }
+            tstart = u;                                        // alpha^1024 further: the next tile's first tweak
+        }
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    const uint32_t *k1 = a.u.k1.w;
+    const uint64_t npairs = a.tt_blocks / 64;
+    const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+    const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
+    const uint64_t per = (npairs + nw - 1) / nw;
+    const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
+    const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
+    if (q0 < q1) {
+        Tweak t = xts_jump(T0, q0 * 64 + lane);
+        uint4 cur[2], nxt[2];
+        cur[0] = ld_stream(a.u.in + q0 * 64 + lane); cur[1] = ld_stream(a.u.in + q0 * 64 + 32 + lane);
+        for (uint64_t q = q0; q < q1; ++q) {
+            const uint64_t k = q * 64 + lane;
+            if (q + 1 < q1) { nxt[0] = ld_stream(a.u.in + k + 64); nxt[1] = ld_stream(a.u.in + k + 96); }
+            uint32_t st[2][4];
+            uint4 tw[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                tweak_words(t, tw[i].x, tw[i].y, tw[i].z, tw[i].w);
+                t = xts_shl(t, 32);
+                st[i][0] = cur[i].x ^ tw[i].x ^ k1[0]; st[i][1] = cur[i].y ^ tw[i].y ^ k1[1];
+                st[i][2] = cur[i].z ^ tw[i].z ^ k1[2]; st[i][3] = cur[i].w ^ tw[i].w ^ k1[3];
+            }
+            enc_finish_n<NR, 1, 2>(lb, st, k1, tw);
+            st_stream(a.u.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
+            st_stream(a.u.out + k + 32, make_uint4(st[1][0], st[1][1], st[1][2], st[1][3]));
+            cur[0] = nxt[0]; cur[1] = nxt[1];
+        }
+    }
+    if (a.u.tail && blockIdx.x == 0 && threadIdx.x == 0) xts_steal_tail<true>(a.u, T0);
 }
 
 template <int NR, bool ENC>
@@ -261,8 +377,6 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
     }
 }
 
-constexpr int kXtsTtThreads = 384;
-constexpr int kXtsDefaultShare = 165;
 
 template <int NR, bool ENC>
 __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
@@ -347,9 +461,33 @@ static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tile
     return cudaGetLastError();
 }
 
+template <int NR>
+static cudaError_t launch_xts_unit_hybrid_nr(const XtsUnitArgs &u, uint64_t bs_blocks, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(xts_unit_hybrid_kernel<NR>);
+    if (e != cudaSuccess) return e;
+    static XtsUnitHybridArgs a;                          // 8 KB of planes: not on the stack (callers hold the library lock)
+    a.u = u;
+    a.tt_blocks = (u.nblocks - bs_blocks) & ~1023ull;
+    bs_make_key_planes_full(u.k1.w, NR, &a.bs);
+    const uint64_t need = (u.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
+    xts_unit_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 template <int NR, bool ENC>
 static cudaError_t launch_xts_unit_nr(const XtsUnitArgs &a, cudaStream_t st)
 {
+    if (ENC) {
+        // A large unit with the co-runner: correct (tests force it on) but not a gain yet -- the 64-bit
+        // tweak stepping next to the 128 planes spills inside the bitsliced rounds: 574 GiB/s without,
+        // 535 with (profiles/r1_xts_hybrid_sweep.txt).  Off unless asked for.
+        ctr_tuning_init();
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_XTS_UNIT_BS_PERMILLE", 0);
+        if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048)
+            return launch_xts_unit_hybrid_nr<NR>(a, a.nblocks / 1024 * (uint64_t)share, st);
+    }
     cudaError_t e = opt_in_smem(xts_unit_kernel<NR, ENC>);
     if (e != cudaSuccess) return e;
     // at least 8 rows per warp so that the jump-ahead amortises

@@ -269,6 +269,22 @@ def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
         uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
 
 
+@pytest.mark.parametrize("bits", [128, 256])
+def test_xts_unit_bitsliced_corunner(uaes, orc, bits):
+    """one large data unit (the reference's AES_XTS_encrypt) with the co-runner forced on: all splits,
+    ragged last tile, ciphertext stealing"""
+    a = uaes.MicroAES(bits)
+    try:
+        for share, n in ((1024, 16 * 2048), (512, 16 * 5000 + 7), (300, 16 * 70001 + 15), (1024, 16 * 3071 + 1), (1, 16 * 4096)):
+            uaes.ctr_tuning(-1, share, 0)
+            keys, tw, data = rnd(f"xu-k{bits}{n}", bits // 4), rnd(f"xu-t{bits}{n}", 16), rnd(f"xu-d{bits}{n}", n)
+            want = orc.xts(keys, tw, data)
+            assert a.AES_XTS_encrypt(keys, tw, data) == want, (share, n)
+            assert a.AES_XTS_decrypt(keys, tw, want[1]) == (0, data)
+    finally:
+        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+
+
 @pytest.mark.parametrize("bits", [128, 192, 256])
 def test_gcm_sizes(uaes, orc, bits):
     a = uaes.MicroAES(bits)
