@@ -127,35 +127,45 @@ struct GcmBulkArgs {
     GcmWork *work;
 };
 
-constexpr uint32_t kGhashRegion = 32768;                 // M table and R table, 32 KiB each
-constexpr int kGcmThreads = 768;                         // 85 registers per thread: no spills; the
-constexpr int kGcmWarps = kGcmThreads / 32;              // lookup pipe saturates from 16 warps up
+constexpr uint32_t kGhashRegion = 32768;                 // M table: 256 x 16 B, replicated 8x
+#ifndef UAES_GCM_THREADS
+#define UAES_GCM_THREADS 768                             // 80 registers per thread; the lookup pipe
+#endif                                                   // saturates from 16 warps up
+constexpr int kGcmThreads = UAES_GCM_THREADS;
+constexpr int kGcmWarps = kGcmThreads / 32;
 
-// y <- y * C, y as four memory-order words; mb = M base | (lane&7)*16, rb = R base | lane*4
-__device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t rb, uint32_t &y0, uint32_t &y1,
-                                                uint32_t &y2, uint32_t &y3)
+// y <- y * C.  y and the table entries are held as BIG-endian words (W0 = bytes 0..3 of the block,
+// x^0 = bit 31 of W0), so that "times x^k" is a right shift of the string W0:W1:W2:W3:...
+//   y * C = sum_i M[y_i] * x^(8i),  i = 4q + r:  byte r of word q.
+// The 16 lookups depend on y alone (no serial chain).  Terms with the same r are XORed word-aligned
+// at word offset q into an UNREDUCED 8-word string; the three byte shifts are Horner steps over r;
+// the 120 bits beyond x^127 are folded once with x^128 = 1 + x + x^2 + x^7 (O*x^7 still fits, so
+// one fold is exact).  mb = M base | (lane&7)*16; the index is one IDP.4A on the FMA pipe.
+__device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t &y0, uint32_t &y1, uint32_t &y2, uint32_t &y3)
 {
-    auto m_at = [&](uint32_t word, int byte) -> uint4 {
-        const int sh = 8 * byte - 7;                         // ((word >> 8*byte) & 0xff) << 7
-        const uint32_t idx = (sh >= 0 ? word >> sh : word << -sh) & 0x7f80u;
-        uint4 v;
-        asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(idx | mb));
-        return v;
-    };
-    uint4 acc = m_at(y3, 3);                                 // byte 15 first
     const uint32_t yw[4] = {y0, y1, y2, y3};
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int i = 14; i >= 0; --i) {
-        uint32_t r;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(((acc.w >> 17) & 0x7f80u) | rb));
-        const uint4 m = m_at(yw[i >> 2], i & 3);
-        // acc <- acc * x^8 (bytes move one place up), reduce the byte that fell off, add M[z_i]
-        acc.w = __byte_perm(acc.z, acc.w, 0x6543) ^ m.w;
-        acc.z = __byte_perm(acc.y, acc.z, 0x6543) ^ m.z;
-        acc.y = __byte_perm(acc.x, acc.y, 0x6543) ^ m.y;
-        acc.x = (acc.x << 8) ^ r ^ m.x;
+    for (int r = 3; r >= 0; --r) {
+        if (r != 3) {                                        // acc <- acc * x^8
+#pragma unroll
+            for (int j = 7; j >= 1; --j) acc[j] = __funnelshift_r(acc[j], acc[j - 1], 8);
+            acc[0] >>= 8;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t ad = __dp4a(yw[q], 0x80u << (8 * (3 - r)), mb);   // byte * 128 + mb
+            uint4 m;
+            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(ad));
+            acc[q] ^= m.x; acc[q + 1] ^= m.y; acc[q + 2] ^= m.z; acc[q + 3] ^= m.w;
+        }
     }
-    y0 = acc.x; y1 = acc.y; y2 = acc.z; y3 = acc.w;
+    // fold O = acc[4..7] (x^128 .. x^247): y = lo ^ O ^ O*x ^ O*x^2 ^ O*x^7
+    const uint32_t o0 = acc[4], o1 = acc[5], o2 = acc[6], o3 = acc[7];
+    y0 = acc[0] ^ o0 ^ (o0 >> 1) ^ (o0 >> 2) ^ (o0 >> 7);
+    y1 = acc[1] ^ o1 ^ __funnelshift_r(o1, o0, 1) ^ __funnelshift_r(o1, o0, 2) ^ __funnelshift_r(o1, o0, 7);
+    y2 = acc[2] ^ o2 ^ __funnelshift_r(o2, o1, 1) ^ __funnelshift_r(o2, o1, 2) ^ __funnelshift_r(o2, o1, 7);
+    y3 = acc[3] ^ o3 ^ __funnelshift_r(o3, o2, 1) ^ __funnelshift_r(o3, o2, 2) ^ __funnelshift_r(o3, o2, 7);
 }
 
 // MODE 0: encrypt (CTR, hash the OUTPUT)   MODE 1: hash only (GCM decrypt's verify pass)
@@ -169,10 +179,8 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
     // ---- shared memory map: AES tables 64 KiB aligned, GHASH tables in the 32 KiB-aligned gaps
     const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
     const uint32_t tbase = align_table_base(dyn);
-    uint32_t mbase, rbase;
-    if (tbase >= win0 + kGhashRegion) { mbase = tbase - kGhashRegion; rbase = tbase + kEncTableBytes; }
-    else                              { mbase = tbase + kEncTableBytes; rbase = mbase + kGhashRegion; }
-    if (rbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1) __trap();
+    const uint32_t mbase = tbase >= win0 + kGhashRegion ? tbase - kGhashRegion : tbase + kEncTableBytes;
+    if (mbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1) __trap();
 
     if (MODE != 1) init_enc_tables(tbase);
     {
@@ -184,24 +192,25 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
                 if (threadIdx.x & (0x80u >> j)) { acc.hi ^= t.hi; acc.lo ^= t.lo; }
                 t = gf_mulx(t);
             }
-            const uint4 v = gf_store(acc);
+            // big-endian words (see ghash_mul_const)
+            const uint4 v = make_uint4((uint32_t)(acc.hi >> 32), (uint32_t)acc.hi, (uint32_t)(acc.lo >> 32), (uint32_t)acc.lo);
             for (int rep = 0; rep < 8; ++rep) {
                 const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
             }
         }
-        for (uint32_t w = threadIdx.x; w < 256u * 32u; w += blockDim.x)
-            sts32(rbase + w * 4, c_ghash_reduce.v[w >> 5]);
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4), rb = rbase | (lane << 2);
-    asm volatile("" : "+r"(lb), "+r"(mb), "+r"(rb)::"memory");
+    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4);
+    asm volatile("" : "+r"(lb), "+r"(mb)::"memory");
 
     const uint32_t *rk = a.ks.w;
     const uint64_t CB = a.chunk_blocks;
     const uint64_t nwarps = (uint64_t)gridDim.x * kGcmWarps;
-    const uint4 aad_state = a.work->aad_state;
+    uint4 aad_be = a.work->aad_state;                    // the GHASH state lives in big-endian words
+    aad_be = make_uint4(__byte_perm(aad_be.x, 0, 0x0123), __byte_perm(aad_be.y, 0, 0x0123),
+                        __byte_perm(aad_be.z, 0, 0x0123), __byte_perm(aad_be.w, 0, 0x0123));
 
     uint64_t cur_group = ~0ull;
     uint32_t s3 = 0, K0 = 0, D0 = 0, D1 = 0, D2 = 0, D3 = 0;
@@ -251,10 +260,17 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
                 if (MODE == 0) { o0 = t0; o1 = t1; o2 = t2; o3 = t3; }     // GHASH runs over ciphertext
             }
             if (ok) {
-                if (REV) { const uint4 r = rev_block(make_uint4(o0, o1, o2, o3)); o0 = r.x; o1 = r.y; o2 = r.z; o3 = r.w; }
-                if (k == 0) { o0 ^= aad_state.x; o1 ^= aad_state.y; o2 ^= aad_state.z; o3 ^= aad_state.w; }
-                if (any) ghash_mul_const(mb, rb, y0, y1, y2, y3);
-                y0 ^= o0; y1 ^= o1; y2 ^= o2; y3 ^= o3;
+                // to big-endian words; for POLYVAL the byte reversal of the block (rev_block) and the
+                // word swap cancel into a plain reversal of the word order
+                uint32_t e0, e1, e2, e3;
+                if (REV) { e0 = o3; e1 = o2; e2 = o1; e3 = o0; }
+                else {
+                    e0 = __byte_perm(o0, 0, 0x0123); e1 = __byte_perm(o1, 0, 0x0123);
+                    e2 = __byte_perm(o2, 0, 0x0123); e3 = __byte_perm(o3, 0, 0x0123);
+                }
+                if (k == 0) { e0 ^= aad_be.x; e1 ^= aad_be.y; e2 ^= aad_be.z; e3 ^= aad_be.w; }
+                if (any) ghash_mul_const(mb, y0, y1, y2, y3);
+                y0 ^= e0; y1 ^= e1; y2 ^= e2; y3 ^= e3;
                 any = true;
                 klast = k;
             }
@@ -263,7 +279,8 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
 
         // lane l holds sum_j X_(l+32j) * C^(J-j); scale by H^(b1 - klast) and reduce over the warp
         Gf z{0, 0};
-        if (any) z = gf_mul_fast(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]), gf_from_words(y0, y1, y2, y3));
+        if (any) z = gf_mul_fast(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]),
+                                 Gf{(uint64_t)y0 << 32 | y1, (uint64_t)y2 << 32 | y3});
         for (int o = 16; o; o >>= 1) {
             z.hi ^= __shfl_xor_sync(0xffffffffu, z.hi, o);
             z.lo ^= __shfl_xor_sync(0xffffffffu, z.lo, o);

@@ -188,26 +188,4 @@ __device__ inline Gf gf_pow_fast(Gf x, uint64_t e)
     return r;
 }
 
-// R[d] = d(x) * x^128 mod p as the first two bytes of a block (little-endian 16-bit value):
-// what falls off the end when a block is multiplied by x^8.  Key independent.
-struct GhashReduce { uint16_t v[256]; };
-constexpr GhashReduce make_ghash_reduce()
-{
-    GhashReduce t{};
-    for (int d = 0; d < 256; ++d) {
-        // d's MSB is the coefficient of x^120 -> x^128 after the byte shift
-        Gf acc{0, 0};
-        Gf term{0xE100000000000000ull, 0};              // x^128 mod p
-        for (int j = 0; j < 8; ++j) {
-            if (d & (0x80 >> j)) { acc.hi ^= term.hi; acc.lo ^= term.lo; }
-            term = gf_mulx(term);
-        }
-        // bytes 0 and 1 of the block are the top 16 bits of acc.hi
-        const uint32_t b0 = (uint32_t)(acc.hi >> 56) & 0xff, b1 = (uint32_t)(acc.hi >> 48) & 0xff;
-        t.v[d] = (uint16_t)(b0 | b1 << 8);
-    }
-    return t;
-}
-__constant__ GhashReduce c_ghash_reduce = make_ghash_reduce();
-
 }  // namespace uaes
