@@ -9,9 +9,10 @@
 //   END of the message (a short first chunk is a full one with leading zeros).
 //   Inside a chunk lane l of the warp owns blocks = l (mod 32) in counter space and runs
 //   Horner with the fixed multiplier C = H^32:   y_l <- y_l * C ^ X.
-//   The multiply-by-constant is a byte-serial table walk (Shoup): 16 lookups of M[b] = b(x)*C
-//   (256 x 16 B, replicated 8x so the 8 lanes of a quarter-warp hit 8 different bank groups)
-//   and 15 lookups of the key-independent reduction R[d] = d(x)*x^128 (lane replicated).
+//   The multiply-by-constant is 16 INDEPENDENT lookups of M[b] = b(x)*C, one per byte of y
+//   (256 x 16 B, replicated 8x so the 8 lanes of a quarter-warp hit 8 different bank groups),
+//   summed word-aligned into an unreduced 248-bit string and folded once (ghash_mul_const);
+//   the block of row r is absorbed while the rounds of row r+1 run.
 //   At the end of a chunk lane l scales y_l by H^(distance to the chunk end) in 1..32 (one
 //   generic product per chunk) and the warp XOR-reduces by shuffle into one 16-byte partial.
 //   A last small kernel folds the partials pairwise with P = H^CB, P^2, P^4, ... (carry-less
@@ -129,8 +130,8 @@ struct GcmBulkArgs {
 
 constexpr uint32_t kGhashRegion = 32768;                 // M table: 256 x 16 B, replicated 8x
 #ifndef UAES_GCM_THREADS
-#define UAES_GCM_THREADS 768                             // 80 registers per thread; the lookup pipe
-#endif                                                   // saturates from 16 warps up
+#define UAES_GCM_THREADS 640                             // 96 registers per thread, no spills (768 spills
+#endif                                                   // and is slower); the lookup pipe saturates from 16 warps up
 constexpr int kGcmThreads = UAES_GCM_THREADS;
 constexpr int kGcmWarps = kGcmThreads / 32;
 
@@ -176,7 +177,7 @@ template <int NR, int MODE, bool REV = false>
 __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
-    // ---- shared memory map: AES tables 64 KiB aligned, GHASH tables in the 32 KiB-aligned gaps
+    // ---- shared memory map: AES tables 64 KiB aligned, the GHASH table in a 32 KiB-aligned gap
     const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
     const uint32_t tbase = align_table_base(dyn);
     const uint32_t mbase = tbase >= win0 + kGhashRegion ? tbase - kGhashRegion : tbase + kEncTableBytes;
@@ -223,6 +224,8 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
         uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
         uint64_t klast = 0;
         bool any = false;
+        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;             // previous row's block, not yet absorbed
+        bool pend = false;
 
         auto valid_k = [&](uint64_t vrow, uint64_t &k) -> bool {
             const uint64_t v = vrow + lane;
@@ -236,6 +239,11 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
             const bool ok = valid_k(vrow, k);
             const uint4 nxt = (vrow + 32 < vend && valid_k(vrow + 32, kn)) ? ld_stream(a.in + kn) : make_uint4(0, 0, 0, 0);
             uint32_t o0 = cur.x, o1 = cur.y, o2 = cur.z, o3 = cur.w;
+            // absorb the PREVIOUS row's block while this row's rounds run: the two are independent, so
+            // their lookups interleave in one basic block (0 * C = 0: no branch on the first row)
+            uint32_t m0 = y0, m1 = y1, m2 = y2, m3 = y3;
+            ghash_mul_const(mb, m0, m1, m2, m3);
+            y0 = pend ? m0 ^ p0 : y0; y1 = pend ? m1 ^ p1 : y1; y2 = pend ? m2 ^ p2 : y2; y3 = pend ? m3 ^ p3 : y3;
             if (MODE != 1) {
                 if ((vrow >> 8) != cur_group) {              // same hoisting as ctr_kernel
                     cur_group = vrow >> 8;
@@ -269,13 +277,14 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
                     e2 = __byte_perm(o2, 0, 0x0123); e3 = __byte_perm(o3, 0, 0x0123);
                 }
                 if (k == 0) { e0 ^= aad_be.x; e1 ^= aad_be.y; e2 ^= aad_be.z; e3 ^= aad_be.w; }
-                if (any) ghash_mul_const(mb, y0, y1, y2, y3);
-                y0 ^= e0; y1 ^= e1; y2 ^= e2; y3 ^= e3;
+                p0 = e0; p1 = e1; p2 = e2; p3 = e3;
                 any = true;
                 klast = k;
             }
+            pend = ok;
             cur = nxt;
         }
+        if (pend) { ghash_mul_const(mb, y0, y1, y2, y3); y0 ^= p0; y1 ^= p1; y2 ^= p2; y3 ^= p3; }
 
         // lane l holds sum_j X_(l+32j) * C^(J-j); scale by H^(b1 - klast) and reduce over the warp
         Gf z{0, 0};
