@@ -135,38 +135,17 @@ constexpr uint32_t kGhashRegion = 32768;                 // M table: 256 x 16 B,
 constexpr int kGcmThreads = UAES_GCM_THREADS;
 constexpr int kGcmWarps = kGcmThreads / 32;
 
-// y <- y * C.  y and the table entries are held as BIG-endian words (W0 = bytes 0..3 of the block,
-// x^0 = bit 31 of W0), so that "times x^k" is a right shift of the string W0:W1:W2:W3:...
-//   y * C = sum_i M[y_i] * x^(8i),  i = 4q + r:  byte r of word q.
-// The 16 lookups depend on y alone (no serial chain).  Terms with the same r are XORed word-aligned
-// at word offset q into an UNREDUCED 8-word string; the three byte shifts are Horner steps over r;
-// the 120 bits beyond x^127 are folded once with x^128 = 1 + x + x^2 + x^7 (O*x^7 still fits, so
-// one fold is exact).  mb = M base | (lane&7)*16; the index is one IDP.4A on the FMA pipe.
+// y <- y * C on the device: ghash_mul_table (uaes_gf128.cuh) with the entry fetched from the 8x
+// replicated shared-memory table.  mb = M base | (lane&7)*16; the index byte*128 + mb is one IDP.4A
+// on the FMA pipe (one-hot selector), the fetch one LDS.128.
 __device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t &y0, uint32_t &y1, uint32_t &y2, uint32_t &y3)
 {
-    const uint32_t yw[4] = {y0, y1, y2, y3};
-    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int r = 3; r >= 0; --r) {
-        if (r != 3) {                                        // acc <- acc * x^8
-#pragma unroll
-            for (int j = 7; j >= 1; --j) acc[j] = __funnelshift_r(acc[j], acc[j - 1], 8);
-            acc[0] >>= 8;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t ad = __dp4a(yw[q], 0x80u << (8 * (3 - r)), mb);   // byte * 128 + mb
-            uint4 m;
-            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(ad));
-            acc[q] ^= m.x; acc[q + 1] ^= m.y; acc[q + 2] ^= m.z; acc[q + 3] ^= m.w;
-        }
-    }
-    // fold O = acc[4..7] (x^128 .. x^247): y = lo ^ O ^ O*x ^ O*x^2 ^ O*x^7
-    const uint32_t o0 = acc[4], o1 = acc[5], o2 = acc[6], o3 = acc[7];
-    y0 = acc[0] ^ o0 ^ (o0 >> 1) ^ (o0 >> 2) ^ (o0 >> 7);
-    y1 = acc[1] ^ o1 ^ __funnelshift_r(o1, o0, 1) ^ __funnelshift_r(o1, o0, 2) ^ __funnelshift_r(o1, o0, 7);
-    y2 = acc[2] ^ o2 ^ __funnelshift_r(o2, o1, 1) ^ __funnelshift_r(o2, o1, 2) ^ __funnelshift_r(o2, o1, 7);
-    y3 = acc[3] ^ o3 ^ __funnelshift_r(o3, o2, 1) ^ __funnelshift_r(o3, o2, 2) ^ __funnelshift_r(o3, o2, 7);
+    ghash_mul_table([mb](uint32_t word, int byte) -> uint4 {
+        const uint32_t ad = __dp4a(word, 0x80u << (8 * byte), mb);
+        uint4 m;
+        asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(ad));
+        return m;
+    }, y0, y1, y2, y3);
 }
 
 // MODE 0: encrypt (CTR, hash the OUTPUT)   MODE 1: hash only (GCM decrypt's verify pass)
@@ -188,13 +167,7 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
         // M[b] = b(x) * C: bit 7 of b is the coefficient of x^0 (micro_aes.c:476-493 bit order)
         const Gf C = gf_load(a.work->C32);
         if (threadIdx.x < 256) {
-            Gf acc{0, 0}, t = C;
-            for (int j = 0; j < 8; ++j) {
-                if (threadIdx.x & (0x80u >> j)) { acc.hi ^= t.hi; acc.lo ^= t.lo; }
-                t = gf_mulx(t);
-            }
-            // big-endian words (see ghash_mul_const)
-            const uint4 v = make_uint4((uint32_t)(acc.hi >> 32), (uint32_t)acc.hi, (uint32_t)(acc.lo >> 32), (uint32_t)acc.lo);
+            const uint4 v = ghash_table_entry(C, threadIdx.x);
             for (int rep = 0; rep < 8; ++rep) {
                 const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

@@ -188,4 +188,62 @@ __device__ inline Gf gf_pow_fast(Gf x, uint64_t e)
     return r;
 }
 
+// ---------------------------------------------------------------- GHASH: y <- y * C by table
+//
+// The multiplier of the GCM hot loop is a per-call constant C, so y * C = sum_i M[y_i] * x^(8i) over
+// the 16 bytes of y with M[b] = b(x) * C (bit 7 of b = coefficient of x^0, micro_aes.c:476-493).
+// y and the table entries are held as BIG-endian words (W0 = bytes 0..3 of the block, x^0 = bit 31
+// of W0), so that "times x^k" is a right shift of the string W0:W1:W2:W3:...; i = 4q + r is byte r
+// of word q.  The 16 lookups depend on y alone (no serial chain).  Entries with the same r are
+// XORed word-aligned at word offset q into an UNREDUCED 8-word string; the three byte shifts are
+// Horner steps over r; the 120 bits beyond x^127 are folded once with x^128 = 1 + x + x^2 + x^7
+// (O * x^7 still fits in 128 bits, so one fold is exact).
+// fetch(word, k) returns M[byte k of word] (k = register byte, 3 - r).  Host + device: the host
+// instance is checked against the oracle's mulGF128 in tests/test_ghash_host.py.
+__host__ __device__ __forceinline__ uint32_t shr_pair(uint32_t lo, uint32_t hi, int n)   // low word of (hi:lo) >> n
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, n);
+#else
+    return lo >> n | hi << (32 - n);
+#endif
+}
+
+template <class Fetch>
+__host__ __device__ __forceinline__ void ghash_mul_table(Fetch fetch, uint32_t &y0, uint32_t &y1, uint32_t &y2, uint32_t &y3)
+{
+    const uint32_t yw[4] = {y0, y1, y2, y3};
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int r = 3; r >= 0; --r) {
+        if (r != 3) {                                        // acc <- acc * x^8
+#pragma unroll
+            for (int j = 7; j >= 1; --j) acc[j] = shr_pair(acc[j], acc[j - 1], 8);
+            acc[0] >>= 8;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 m = fetch(yw[q], 3 - r);
+            acc[q] ^= m.x; acc[q + 1] ^= m.y; acc[q + 2] ^= m.z; acc[q + 3] ^= m.w;
+        }
+    }
+    // fold O = acc[4..7] (x^128 .. x^247): y = lo ^ O ^ O*x ^ O*x^2 ^ O*x^7
+    const uint32_t o0 = acc[4], o1 = acc[5], o2 = acc[6], o3 = acc[7];
+    y0 = acc[0] ^ o0 ^ (o0 >> 1) ^ (o0 >> 2) ^ (o0 >> 7);
+    y1 = acc[1] ^ o1 ^ shr_pair(o1, o0, 1) ^ shr_pair(o1, o0, 2) ^ shr_pair(o1, o0, 7);
+    y2 = acc[2] ^ o2 ^ shr_pair(o2, o1, 1) ^ shr_pair(o2, o1, 2) ^ shr_pair(o2, o1, 7);
+    y3 = acc[3] ^ o3 ^ shr_pair(o3, o2, 1) ^ shr_pair(o3, o2, 2) ^ shr_pair(o3, o2, 7);
+}
+
+// M[b] = b(x) * C as big-endian words (the layout ghash_mul_table reads)
+__host__ __device__ inline uint4 ghash_table_entry(Gf C, uint32_t b)
+{
+    Gf acc{0, 0}, t = C;
+    for (int j = 0; j < 8; ++j) {
+        if (b & (0x80u >> j)) { acc.hi ^= t.hi; acc.lo ^= t.lo; }
+        t = gf_mulx(t);
+    }
+    return make_uint4((uint32_t)(acc.hi >> 32), (uint32_t)acc.hi, (uint32_t)(acc.lo >> 32), (uint32_t)acc.lo);
+}
+
 }  // namespace uaes
