@@ -300,6 +300,26 @@ def test_gcm_sizes(uaes, orc, bits):
         assert a.AES_GCM_decrypt(key, nonce, aad, want) == (0, data), (n, alen)
 
 
+def test_gcm_multirow_chunks_ragged(uaes, orc):
+    """The bulk kernel cuts GHASH into one chunk per warp of the grid (R rows of 32 blocks each) and
+    absorbs the block of row r while the rounds of row r+1 run: messages with 2..5 rows per chunk,
+    a first row and a last row that are only partly inside the message, and a ragged tail."""
+    a = uaes.MicroAES(128)
+    for rows_total, extra_blocks, tail in [(2 * 2960, 17, 5), (3 * 2960 - 1, 31, 0), (5 * 2960 + 7, 1, 15),
+                                           (2 * 3552 + 3, 9, 1), (4 * 2960, 0, 0)]:
+        n = 16 * (32 * rows_total + extra_blocks) + tail
+        key, nonce = rnd(f"mr-k{n}", 16), rnd(f"mr-n{n}", 12)
+        aad, data = rnd(f"mr-a{n}", 21), rnd(f"mr-d{n}", n)
+        want = orc.gcm_encrypt(key, nonce, aad, data)
+        got = a.AES_GCM_encrypt(key, nonce, aad, data)
+        assert got[-16:] == want[-16:], n
+        assert got == want, n
+        assert a.AES_GCM_decrypt(key, nonce, aad, want) == (0, data), n
+        wsiv = orc.gcmsiv_encrypt(key, nonce, aad, data)
+        assert a.GCM_SIV_encrypt(key, nonce, aad, data) == wsiv, n
+        assert a.GCM_SIV_decrypt(key, nonce, aad, wsiv) == (0, data), n
+
+
 def test_gcm_auth_failure_leaves_output_untouched(uaes, orc):
     a = uaes.MicroAES(128)
     key, nonce, aad, data = rnd("af-k", 16), rnd("af-n", 12), rnd("af-a", 20), rnd("af-d", 1000)
