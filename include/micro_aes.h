@@ -60,8 +60,10 @@
 #define XEX             1
 #define XTS             1
 #define GCM             1
-#define CBC             0
+#define CBC             0       /* the serial ENcrypt directions of CBC / CFB are not provided ...  */
 #define CFB             0
+#define CBC_DECRYPT     1       /* ... their block-parallel DEcrypt directions are */
+#define CFB_DECRYPT     1
 #define OFB             0
 #define KWA             0
 #define FPE             0
@@ -73,19 +75,42 @@
 #define GCM_SIV         1
 #define OCB             1
 #define POLY1305        0
-#define CTS             0
 #define MICRO_RJNDL     0
 
-#define AES_PADDING     0       /* ECB tail block is zero padded (micro_aes.h:78-80) */
+/* Compile-time variants of the reference (micro_aes.h:56, 78-80, 97-110).  The reference is
+ * configured by editing these lines of its header; here the same names may also be set with -D
+ * (for the enum constants: -DUAES_GCM_NONCE_LEN=..., -DUAES_GCM_TAG_LEN=...).  The application and
+ * the shim library must be built with the same values, exactly as the application and micro_aes.c
+ * share one header in the reference; `make shim VARIANT=... DEFS=...` (csrc/Makefile) builds a shim
+ * for any combination. */
+#ifndef CTS
+#define CTS             1       /* CBC: CS3 ciphertext stealing (micro_aes.h:56); 0 = whole blocks only */
+#endif
+#ifndef AES_PADDING
+#define AES_PADDING     0       /* ECB tail: 0 zeros, 1 PKCS#7, 2 ISO/IEC 7816-4 (micro_aes.h:78-80) */
+#endif
 #define DECRYPTION      1
-#define PRESET_COUNTER  0       /* CTR takes a 12-byte IV, counter field starts at 1 */
+#ifndef PRESET_COUNTER
+#define PRESET_COUNTER  0       /* 0: CTR takes a 12-byte IV, counter field starts at 1;
+                                   1: iv[16] is the first counter block verbatim (micro_aes.h:100) */
+#endif
+#ifndef UAES_GCM_NONCE_LEN
+#define UAES_GCM_NONCE_LEN 12
+#endif
+#ifndef UAES_GCM_TAG_LEN
+#define UAES_GCM_TAG_LEN   16
+#endif
 
 enum constant_parameters_of_modes
 {
     CTR_START_VALUE = 1,        /* micro_aes.h:98  */
+#if PRESET_COUNTER
+    CTR_IV_LENGTH   = 16,       /* micro_aes.h:99-100: the whole counter block */
+#else
     CTR_IV_LENGTH   = 12,       /* micro_aes.h:99  */
-    GCM_NONCE_LEN   = 12,       /* micro_aes.h:108 */
-    GCM_TAG_LEN     = 16,       /* micro_aes.h:109 */
+#endif
+    GCM_NONCE_LEN   = UAES_GCM_NONCE_LEN,   /* micro_aes.h:108: 12 is the recommended value, others are supported */
+    GCM_TAG_LEN     = UAES_GCM_TAG_LEN,     /* micro_aes.h:109 */
     SIVGCM_NONCE_LEN = 12,      /* micro_aes.h:112 */
     SIVGCM_TAG_LEN  = 16,       /* micro_aes.h:113 */
     CCM_NONCE_LEN   = 11,       /* micro_aes.h:104 */
@@ -113,14 +138,15 @@ typedef unsigned char uint8_t;
 extern "C" {
 #endif
 
-/* ECB: output holds ceil16(ptextLen) bytes, the tail block is zero padded */
+/* ECB: output holds ceil16(ptextLen) bytes, the tail block is zero padded; with AES_PADDING 1 / 2
+ * a padding block is always added: (ptextLen / 16 + 1) * 16 bytes (micro_aes.c:610-621) */
 void AES_ECB_encrypt(const uint8_t *key, const void *pntxt, const size_t ptextLen, void *crtxt);
 /* returns M_DECRYPTION_ERROR when crtxtLen is not a multiple of 16 (full blocks are
  * still decrypted, tail bytes copied through) */
 char AES_ECB_decrypt(const uint8_t *key, const void *crtxt, const size_t crtxtLen, void *pntxt);
 
-/* CTR: iv = CTR_IV_LENGTH bytes; counter block = iv || BE32(1), incremented as a
- * 56-bit big-endian integer in bytes 9..15 (micro_aes.c:421-427) */
+/* CTR: iv = CTR_IV_LENGTH bytes; counter block = iv || BE32(1) (or iv[16] itself when
+ * PRESET_COUNTER), incremented as a 56-bit big-endian integer in bytes 9..15 (micro_aes.c:421-427) */
 void AES_CTR_encrypt(const uint8_t *key, const uint8_t *iv,
                      const void *pntxt, const size_t ptextLen, void *crtxt);
 void AES_CTR_decrypt(const uint8_t *key, const uint8_t *iv,
@@ -134,7 +160,7 @@ char AES_XTS_encrypt(const uint8_t *keys, const uint8_t *tweak,
 char AES_XTS_decrypt(const uint8_t *keys, const uint8_t *tweak,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 
-/* GCM: 12-byte nonce; crtxt holds ptextLen + GCM_TAG_LEN bytes (tag appended) */
+/* GCM: GCM_NONCE_LEN-byte nonce; crtxt holds ptextLen + GCM_TAG_LEN bytes (tag appended) */
 void AES_GCM_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *pntxt, const size_t ptextLen, void *crtxt);
@@ -144,9 +170,11 @@ char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt);
 
-/* only the block-parallel DEcrypt directions of CBC (CS3 stealing, as with the
- * reference's CTS = 1) and CFB exist on the GPU; CBC / CFB stay 0 above because the serial
- * encrypt directions (micro_aes.c:697-733, 826-830) are not provided.
+/* only the block-parallel DEcrypt directions of CBC and CFB exist on the GPU
+ * (CBC_DECRYPT / CFB_DECRYPT above); CBC / CFB stay 0 because the serial encrypt directions
+ * (micro_aes.c:697-733, 826-830) are not provided.  CBC follows CTS like the reference: CS3
+ * stealing with CTS = 1 (any length >= 16), whole blocks only with CTS = 0 (M_DATALENGTH_ERROR
+ * otherwise).
  * Replaces micro_aes.h:194-198 / micro_aes.c:746-782 and micro_aes.h:211-215 / micro_aes.c:840-845. */
 char AES_CBC_decrypt(const uint8_t *key, const uint8_t iVec[16],
                      const void *crtxt, const size_t crtxtLen, void *pntxt);

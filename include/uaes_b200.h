@@ -17,8 +17,9 @@
  *
  * Every data pointer may be host memory (pageable or pinned) or CUDA device /
  * managed memory; the library classifies it per call.  Device buffers are processed
- * in HBM with no copies; host buffers are staged through pinned chunks with copies
- * overlapped against the kernels.  key / iv / nonce / tweak / aad are always small
+ * in HBM with no copies; host buffers are staged in chunks with copies overlapped
+ * against the kernels (pageable memory through the library's own pinned bounce
+ * chunks), on one GPU or -- uaes_set_devices -- spread over all of them.  key / iv / nonce / tweak / aad are always small
  * HOST arrays, as in the reference.
  *
  * All functions return 0 (UAES_OK) or a micro_aes.h result code (1, 0x1A, 0x1D) or
@@ -48,7 +49,7 @@ enum uaes_status
     UAES_DECRYPTION_ERROR   = 0x1D,   /* = M_DECRYPTION_ERROR     (micro_aes.h:472) */
     UAES_E_NO_DEVICE        = -1,     /* no CUDA device / driver: nothing was computed */
     UAES_E_CUDA             = -2,     /* a CUDA runtime call or kernel failed */
-    UAES_E_BAD_ARGUMENT     = -3,     /* key size not 128/192/256, XTS-192, ragged sectors */
+    UAES_E_BAD_ARGUMENT     = -3,     /* key size not 128/192/256, ragged sectors, tag length */
     UAES_E_NO_MEMORY        = -4
 };
 
@@ -71,6 +72,38 @@ void uaes_set_async(int enable);
 /* pinned host memory, for callers that want full-speed host<->device staging */
 void *uaes_host_alloc(size_t bytes);
 void  uaes_host_free(void *p);
+/* page-lock / release a buffer the caller already owns (cudaHostRegister): worth it for buffers
+ * that are used more than once; pageable buffers work too, through the library's own bounce chunks */
+int   uaes_host_register(void *p, size_t bytes);
+int   uaes_host_unregister(void *p);
+
+/* ---- multi-GPU context (extension 5) --------------------------- */
+/* Number of GPUs a call on HOST buffers may be spread over (n <= 0: all of them).  The byte range
+ * is cut into one contiguous part per device -- blocks, sectors, tweak positions and GCM shards are
+ * independent (micro_aes.c:943-948, 1030-1036) -- and each part runs the staging
+ * pipeline of its device on its own host thread, so every PCIe link of the box carries data at
+ * once.  Part 0 stays on the calling thread's current device.  Returns the number in effect
+ * (default 1, or UAES_DEVICES from the environment).  Device-resident buffers are never spread:
+ * shard those yourself with the *_range entry points below. */
+int  uaes_set_devices(int n);
+int  uaes_get_devices(void);
+/* a call is spread only as far as every device still gets this many bytes (default 256 MiB) */
+void uaes_set_fanout_min(size_t bytes_per_device);
+/* helper threads that move PAGEABLE caller memory into / out of the pinned bounce chunks
+ * (default 4; memcpy only -- no cipher work ever runs on the host) */
+void uaes_set_copy_threads(int n);
+
+/* ---- lifecycle --------------------------------------------------------------- */
+/* 1: wipe every staging chunk, work area and host-side key schedule after each call, the
+ * reference's INCREASE_SECURITY / BURN (micro_aes.c:362-364); costs one extra memset per chunk */
+void uaes_set_burn(int enable);
+/* give back the grow-on-demand device memory of all devices (work areas, full-size staging);
+ * streams and staging chunks stay.  Full-size staging above 256 MiB is released after every call
+ * anyway. */
+void uaes_trim(void);
+/* wipe and release everything on all devices; the next call initialises again.  No call may be
+ * in flight. */
+void uaes_shutdown(void);
 /* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
 uaes_u64 uaes_kernel_launches(void);
 /* CTR kernel geometry (tuning and tests; the defaults are the measured optimum on B200):
@@ -85,7 +118,7 @@ uaes_u64 uaes_kernel_launches(void);
 void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks);
 
 /* ---- the hot path, run-time key length ------------------------------------- */
-/* keybits = 128, 192 or 256 everywhere (XTS: 128 or 256, keys = K1 || K2). */
+/* keybits = 128, 192 or 256 everywhere (XTS: keys = K1 || K2, 2 * keybits / 8 bytes). */
 
 /* micro_aes.c:636-653; out holds ceil16(len) */
 int uaes_ecb_encrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out);
@@ -101,11 +134,27 @@ int uaes_ctr_crypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
 int uaes_ctr_crypt_range(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
                          uaes_u64 first_block, const void *in, size_t len, void *out);
 
+/* the reference built with PRESET_COUNTER = 1 (micro_aes.c:964-966, micro_aes.h:100): ctr[16] is
+ * counter block 0 verbatim; keystream block k uses ctr + first_block + k (56-bit add, bytes 9..15) */
+int uaes_ctr_crypt_block(int keybits, const uaes_u8 *key, const uaes_u8 *ctr, uaes_u64 first_block,
+                         const void *in, size_t len, void *out);
+/* the reference built with AES_PADDING = 1 (PKCS#7) or 2 (ISO/IEC 7816-4), micro_aes.c:610-621:
+ * the last block is always padded, out holds (len / 16 + 1) * 16 bytes; padding = 0 is
+ * uaes_ecb_encrypt.  (Like the reference, decryption does not strip or check the padding.) */
+int uaes_ecb_encrypt_padded(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out, int padding);
+
 /* micro_aes.c:1066-1093: one data unit, tweak = 16 bytes or NULL (sector 0), stealing */
 int uaes_xts_encrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak,
                      const void *in, size_t len, void *out);
 int uaes_xts_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak,
                      const void *in, size_t len, void *out);
+/* A block range of ONE data unit ("a single huge data unit also shards"): in[0] is
+ * block first_block of the unit, whose tweak chain T_0 * alpha^k (micro_aes.c:1030-1036) is entered
+ * by jump-ahead.  len is a multiple of 16 except for the range that ends the unit, which applies the
+ * ciphertext stealing of micro_aes.c:1037-1053 to its last two blocks (len >= 16 always).  Ranges
+ * may run on different GPUs or at different times; together they equal one AES_XTS_encrypt call. */
+int uaes_xts_crypt_range(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, uaes_u64 first_block,
+                         const void *in, size_t len, void *out, int encrypt);
 /* len / sector_bytes consecutive data units, unit j tweaked with LE128(first_sector + j);
  * sector_bytes must be a multiple of 16, len a multiple of sector_bytes.  Equals a loop of
  * AES_XTS_encrypt / AES_XTS_decrypt calls over the sectors. */
@@ -118,6 +167,15 @@ int uaes_gcm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
 /* micro_aes.c:1192-1212; in holds len + 16; UAES_AUTH_ERROR leaves out untouched */
 int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                      const void *aad, size_t aadlen, const void *in, size_t len, void *out);
+
+/* the reference built with GCM_NONCE_LEN != 12 and / or GCM_TAG_LEN < 16 (micro_aes.h:107-110):
+ * a nonce of any other length becomes J0 = GHASH_H({}, nonce) (micro_aes.c:1145-1149), the tag is
+ * cut to its first taglen bytes (micro_aes.c:1178, 1204).  out holds len + taglen (encrypt), in holds
+ * len + taglen (decrypt). */
+int uaes_gcm_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, size_t noncelen,
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+int uaes_gcm_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, size_t noncelen,
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
 
 /* ---- AES-GCM-SIV (RFC 8452), micro_aes.c:1474-1516 ------------- */
 /* nonce = 12 bytes; out holds len + 16 (tag appended).  Two passes (POLYVAL, then CTR). */
@@ -134,6 +192,10 @@ int uaes_gcmsiv_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
  * chain and is not provided.)  A staged copy is made when in == out. */
 int uaes_cbc_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
                      const void *in, size_t len, void *out);
+/* cts = 0: the reference built with CTS = 0 (plain CBC: UAES_DATALENGTH_ERROR unless len % 16 == 0,
+ * micro_aes.c:757-759); cts = 1 is uaes_cbc_decrypt */
+int uaes_cbc_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
+                        const void *in, size_t len, void *out, int cts);
 /* micro_aes.c:799-845, any length */
 int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv,
                      const void *in, size_t len, void *out);
@@ -150,11 +212,15 @@ int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
  * starting at block `first_block` of the message; all shards but the last are multiples of 16
  * bytes.  uaes_gcm_shard runs the fused CTR + GHASH pass over the shard (encrypt: GHASH over the
  * output; decrypt: GHASH over the input, plaintext written in the same pass) and returns the
- * shard's 16-byte GHASH contribution in partial[] (host memory).  Gather the contributions (the
- * one 16-byte-per-rank exchange of the path) and let uaes_gcm_combine fold them with the AAD and the
- * lengths into the tag: blocks_after[r] = number of 16-byte blocks of the message after shard r's
- * end (0 for the last shard).  A decrypting caller compares that tag with the received one and
- * discards the shards' output on mismatch (the single-call API does this itself). */
+ * shard's 16-byte GHASH contribution in partial[] -- host memory, or DEVICE memory, in which case
+ * the contribution never leaves the GPU and (in asynchronous mode) the call only enqueues work, so
+ * the gather can run device to device.  Gather the contributions (the one 16-byte-per-rank exchange
+ * of the path) and let uaes_gcm_combine fold them with the AAD and the lengths into the tag:
+ * blocks_after[r] = number of 16-byte blocks of the message after shard r's end (0 for the last
+ * shard); partials, blocks_after and tag may each be host or device memory, nshards is unbounded.
+ * A decrypting caller compares that tag with the received one and discards the shards' output on
+ * mismatch (the single-call API does this itself).  A host-buffer uaes_gcm_encrypt / _decrypt
+ * larger than one staging chunk runs exactly this scheme internally, one shard per chunk. */
 int uaes_gcm_shard(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, uaes_u64 first_block,
                    const void *in, size_t len, void *out, int decrypt, uaes_u8 *partial);
 int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,

@@ -38,12 +38,27 @@ UAES_ABI = {
     "uaes_set_async": (None, [_int]),
     "uaes_host_alloc": (_vp, [_sz]),
     "uaes_host_free": (None, [_vp]),
+    "uaes_host_register": (_int, [_vp, _sz]),
+    "uaes_host_unregister": (_int, [_vp]),
+    "uaes_set_devices": (_int, [_int]),
+    "uaes_get_devices": (_int, []),
+    "uaes_set_fanout_min": (None, [_sz]),
+    "uaes_set_copy_threads": (None, [_int]),
+    "uaes_set_burn": (None, [_int]),
+    "uaes_trim": (None, []),
+    "uaes_shutdown": (None, []),
     "uaes_kernel_launches": (_u64, []),
     "uaes_ctr_tuning": (None, [_int, _int, ctypes.c_longlong]),
     "uaes_ecb_encrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
     "uaes_ecb_decrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
     "uaes_ctr_crypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_ctr_crypt_range": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp]),
+    "uaes_ctr_crypt_block": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp]),
+    "uaes_ecb_encrypt_padded": (_int, [_int, _cp, _vp, _sz, _vp, _int]),
+    "uaes_xts_crypt_range": (_int, [_int, _cp, _cp, _u64, _vp, _sz, _vp, _int]),
+    "uaes_gcm_encrypt_ex": (_int, [_int, _cp, _cp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_gcm_decrypt_ex": (_int, [_int, _cp, _cp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_cbc_decrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _int]),
     "uaes_xts_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_xts_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
@@ -132,7 +147,8 @@ def core():
 
 
 def shim(bits):
-    """libmicro_aes_<bits>.so: the reference's symbol names for one key size."""
+    """libmicro_aes_<bits>.so: the reference's symbol names for one key size; `bits` may also name
+    a compile-time variant built by `make variants` (e.g. "128_pc", "128_iv1", "128_pad1")."""
     if bits not in _shims:
         core()
         _shims[bits] = _bind(ctypes.CDLL(os.path.join(LIBDIR, f"libmicro_aes_{bits}.so")), MICRO_AES_ABI)
@@ -353,23 +369,84 @@ def gcmsiv(bits, key, nonce, aad, src, nbytes, dst, encrypt=True):
     return check(f(bits, key, nonce, _ptr(aad), len(aad) if aad else 0, _ptr(src), nbytes, _ptr(dst)))
 
 
-def gcm_shard(bits, key, nonce, first_block, src, nbytes, dst, decrypt=False):
-    """fused CTR+GHASH over one shard of a message; returns the shard's 16-byte GHASH contribution"""
+def gcm_shard(bits, key, nonce, first_block, src, nbytes, dst, decrypt=False, partial_dev=None):
+    """fused CTR+GHASH over one shard of a message; returns the shard's 16-byte GHASH contribution,
+    or leaves it in `partial_dev` (16 bytes of device memory) when that is given"""
+    if partial_dev is not None:
+        check(core().uaes_gcm_shard(bits, key, nonce, first_block, _ptr(src), nbytes, _ptr(dst),
+                                    1 if decrypt else 0, _ptr(partial_dev)))
+        return None
     part = ctypes.create_string_buffer(16)
     check(core().uaes_gcm_shard(bits, key, nonce, first_block, _ptr(src), nbytes, _ptr(dst),
                                 1 if decrypt else 0, ctypes.addressof(part)))
     return part.raw
 
 
-def gcm_combine(bits, key, nonce, aad, partials, blocks_after, total_len):
-    """tag of a sharded message from the gathered contributions"""
+def gcm_combine(bits, key, nonce, aad, partials, blocks_after, total_len, partials_dev=None):
+    """tag of a sharded message from the gathered contributions (a list of 16-byte strings, or
+    `partials_dev` = device memory holding len(blocks_after) x 16 bytes)"""
     tag = ctypes.create_string_buffer(16)
-    ps = b"".join(partials)
-    after = (ctypes.c_uint64 * max(len(blocks_after), 1))(*blocks_after)
+    ps = b"".join(partials) if partials_dev is None else None
+    n = len(blocks_after)
+    after = (ctypes.c_uint64 * max(n, 1))(*blocks_after)
+    pp = _ptr(partials_dev) if partials_dev is not None else (_ptr(ps) if ps else None)
     check(core().uaes_gcm_combine(bits, key, nonce, _ptr(aad) if aad else None, len(aad) if aad else 0,
-                                  _ptr(ps) if ps else None, ctypes.addressof(after), len(partials), total_len,
-                                  ctypes.addressof(tag)))
+                                  pp, ctypes.addressof(after), n, total_len, ctypes.addressof(tag)))
     return tag.raw
+
+
+def ctr_crypt_block(bits, key, ctr16, first_block, src, nbytes, dst):
+    """PRESET_COUNTER form of CTR: ctr16 is counter block 0 verbatim"""
+    return check(core().uaes_ctr_crypt_block(bits, key, ctr16, first_block, _ptr(src), nbytes, _ptr(dst)))
+
+
+def ecb_encrypt_padded(bits, key, src, nbytes, dst, padding):
+    return check(core().uaes_ecb_encrypt_padded(bits, key, _ptr(src), nbytes, _ptr(dst), padding))
+
+
+def xts_crypt_range(bits, keys, tweak, first_block, src, nbytes, dst, encrypt=True):
+    """a block range of one XTS data unit (tweak chain entered by jump-ahead)"""
+    return check(core().uaes_xts_crypt_range(bits, keys, tweak, first_block, _ptr(src), nbytes, _ptr(dst),
+                                             1 if encrypt else 0))
+
+
+def gcm_encrypt_ex(bits, key, nonce, aad, src, nbytes, dst, taglen=16):
+    return check(core().uaes_gcm_encrypt_ex(bits, key, nonce, len(nonce), _ptr(aad), len(aad) if aad else 0,
+                                            _ptr(src), nbytes, _ptr(dst), taglen))
+
+
+def gcm_decrypt_ex(bits, key, nonce, aad, src, nbytes, dst, taglen=16):
+    return check(core().uaes_gcm_decrypt_ex(bits, key, nonce, len(nonce), _ptr(aad), len(aad) if aad else 0,
+                                            _ptr(src), nbytes, _ptr(dst), taglen))
+
+
+def cbc_decrypt_ex(bits, key, iv, src, nbytes, dst, cts=True):
+    return check(core().uaes_cbc_decrypt_ex(bits, key, iv, _ptr(src), nbytes, _ptr(dst), 1 if cts else 0))
+
+
+def set_devices(n):
+    """GPUs a host-buffer call may be spread over (n <= 0: all); returns the number in effect"""
+    return core().uaes_set_devices(n)
+
+
+def set_fanout_min(nbytes):
+    core().uaes_set_fanout_min(nbytes)
+
+
+def set_copy_threads(n):
+    core().uaes_set_copy_threads(n)
+
+
+def set_burn(flag):
+    core().uaes_set_burn(1 if flag else 0)
+
+
+def trim():
+    core().uaes_trim()
+
+
+def shutdown():
+    core().uaes_shutdown()
 
 
 def fill_splitmix64(seed, first_word, dst, nwords):

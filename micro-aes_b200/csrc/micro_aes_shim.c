@@ -7,6 +7,11 @@
  * of micro_aes.c.  Each function forwards to the run-time-key-length entry point of
  * uaes_b200.h; return codes are the reference's (micro_aes.h:469-476).  The void functions
  * latch failures for uaes_last_error().
+ *
+ * The reference's other compile-time variants select the matching run-time entry point here:
+ * PRESET_COUNTER (micro_aes.c:964-966), GCM_NONCE_LEN / GCM_TAG_LEN (micro_aes.c:1145-1149, 1178,
+ * 1204), AES_PADDING (micro_aes.c:610-621), CTS (micro_aes.c:703-707, 757-759); build a variant with
+ * `make shim VARIANT=<name> DEFS="-D..."`.
  */
 #include "../../include/micro_aes.h"
 #include "../../include/uaes_b200.h"
@@ -23,7 +28,7 @@ static char code(int rc, char fallback)
 
 void AES_ECB_encrypt(const uint8_t *key, const void *pntxt, const size_t ptextLen, void *crtxt)
 {
-    uaes_ecb_encrypt(BITS, key, pntxt, ptextLen, crtxt);
+    uaes_ecb_encrypt_padded(BITS, key, pntxt, ptextLen, crtxt, AES_PADDING);     /* micro_aes.c:610-621 */
 }
 
 char AES_ECB_decrypt(const uint8_t *key, const void *crtxt, const size_t crtxtLen, void *pntxt)
@@ -34,13 +39,17 @@ char AES_ECB_decrypt(const uint8_t *key, const void *crtxt, const size_t crtxtLe
 void AES_CTR_encrypt(const uint8_t *key, const uint8_t *iv,
                      const void *pntxt, const size_t ptextLen, void *crtxt)
 {
+#if PRESET_COUNTER
+    uaes_ctr_crypt_block(BITS, key, iv, 0, pntxt, ptextLen, crtxt);             /* micro_aes.c:964-966 */
+#else
     uaes_ctr_crypt(BITS, key, iv, pntxt, ptextLen, crtxt);
+#endif
 }
 
 void AES_CTR_decrypt(const uint8_t *key, const uint8_t *iv,
                      const void *crtxt, const size_t crtxtLen, void *pntxt)
 {
-    uaes_ctr_crypt(BITS, key, iv, crtxt, crtxtLen, pntxt);     /* micro_aes.c:986-990 */
+    AES_CTR_encrypt(key, iv, crtxt, crtxtLen, pntxt);                           /* micro_aes.c:986-990 */
 }
 
 char AES_XTS_encrypt(const uint8_t *keys, const uint8_t *tweak,
@@ -59,15 +68,15 @@ void AES_GCM_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *pntxt, const size_t ptextLen, void *crtxt)
 {
-    uaes_gcm_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+    uaes_gcm_encrypt_ex(BITS, key, nonce, GCM_NONCE_LEN, aData, aDataLen, pntxt, ptextLen, crtxt, GCM_TAG_LEN);
 }
 
 char AES_GCM_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt)
 {
-    return code(uaes_gcm_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
-                M_DECRYPTION_ERROR);
+    return code(uaes_gcm_decrypt_ex(BITS, key, nonce, GCM_NONCE_LEN, aData, aDataLen, crtxt, crtxtLen, pntxt,
+                                    GCM_TAG_LEN), M_DECRYPTION_ERROR);
 }
 
 void GCM_SIV_encrypt(const uint8_t *key, const uint8_t *nonce,
@@ -88,7 +97,7 @@ char GCM_SIV_decrypt(const uint8_t *key, const uint8_t *nonce,
 char AES_CBC_decrypt(const uint8_t *key, const uint8_t iVec[16],
                      const void *crtxt, const size_t crtxtLen, void *pntxt)
 {
-    return code(uaes_cbc_decrypt(BITS, key, iVec, crtxt, crtxtLen, pntxt), M_DECRYPTION_ERROR);
+    return code(uaes_cbc_decrypt_ex(BITS, key, iVec, crtxt, crtxtLen, pntxt, CTS), M_DECRYPTION_ERROR);
 }
 
 void AES_CFB_decrypt(const uint8_t *key, const uint8_t iVec[16],

@@ -92,7 +92,7 @@ static cudaError_t launch_chain_nr(const ChainArgs &a, cudaStream_t st)
         const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_ECB_BS_PERMILLE", kEcbDefaultShare);
         if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048) {
             EcbArgs e0;
-            e0.ks = a.ks; e0.in = a.in; e0.out = a.out; e0.nblocks = a.nblocks; e0.tail = a.tail;
+            e0.ks = a.ks; e0.in = a.in; e0.out = a.out; e0.nblocks = a.nblocks; e0.tail = a.tail; e0.pad = 0;
             return launch_ecb_hybrid_nr<NR, true>(e0, a.nblocks / 1024 * (uint64_t)share, st, a.iv);
         }
     }

@@ -284,7 +284,8 @@ struct GcmFinishArgs {
     int mode;                    // as gcm_bulk_kernel's MODE
     int partial_only;            // write the GHASH state of this shard instead of a tag
     int siv;                     // POLYVAL + GCM-SIV tag (micro_aes.c:1454-1462); j0[] = nonce words
-    uint8_t *tag_out;            // 16 bytes, any alignment
+    uint8_t *tag_out;            // taglen bytes (16 for a shard's contribution), any alignment
+    uint32_t taglen;             // GCM_TAG_LEN (micro_aes.c:1178): the leading bytes of the tag that are written
     GcmWork *work;
 };
 
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
         const uint4 pv = rev_block(gf_store(S));              // = POLYVAL
         uint32_t t[4] = {pv.x ^ a.w0, pv.y ^ a.w1, pv.z ^ a.b8, pv.w & 0x7fffffffu};   // ^ nonce, clear bit 127
         small_encrypt(a.ks.w, a.ks.rounds, t);
-        for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(t[i >> 2] >> (8 * (i & 3)));
+        for (uint32_t i = 0; i < a.taglen; ++i) a.tag_out[i] = (uint8_t)(t[i >> 2] >> (8 * (i & 3)));
         return;
     }
     // length block: BE64(8*aadlen) || BE64(8*len)   (micro_aes.c:1130-1132)
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
     uint4 tag = gf_store(S);
     tag.x ^= ej0.x; tag.y ^= ej0.y; tag.z ^= ej0.z; tag.w ^= ej0.w;
     const uint32_t tw[4] = {tag.x, tag.y, tag.z, tag.w};
-    for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
+    for (uint32_t i = 0; i < a.taglen; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
 }
 
 static unsigned gcm_grid(uint64_t nchunks)
@@ -530,7 +531,8 @@ static cudaError_t launch_ctr32_nr(const Ctr32Args &a, cudaStream_t st)
 
 // A message sharded over GPUs: shard r returns Z_r = sum over its blocks of
 // X_i * H^(shard end - i).  GHASH of the whole = aad_state * H^(all blocks) ^ sum_r Z_r * H^(blocks
-// after shard r), then the length block and E_K(J0) as usual.  <= 32 shards, one lane each.
+// after shard r), then the length block and E_K(J0) as usual.  Lane l takes contributions l, l+32, ...
+// (a staged host-buffer call leaves one per chunk, a multi-GPU call one per rank).
 struct GcmCombineArgs {
     uaes_keysched ks;
     uint32_t j0[4];
@@ -541,6 +543,7 @@ struct GcmCombineArgs {
     uint32_t nshards;
     uint64_t total_blocks;       // ceil(len / 16)
     uint8_t *tag_out;
+    uint32_t taglen;             // bytes of the tag that are written (16 when fold_only)
     uint32_t fold_only;          // 1: write sum_r Z_r * H^after[r] and stop (streaming: many shards -> one)
 };
 
@@ -557,10 +560,12 @@ __global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
     __syncwarp();
     const Gf H = sh_H;
     Gf term{0, 0};
-    if (lane < a.nshards) {
-        const uint4 z = load_block_bytes(a.partials + 16 * lane, 16);
-        term = gf_mul_fast(gf_load(z), gf_pow_fast(H, a.after[lane]));
-    } else if (lane == 31 && !a.fold_only) {                  // the AAD rides in front of block 0
+    for (uint32_t r = lane; r < a.nshards; r += 32) {
+        const uint4 z = load_block_bytes(a.partials + 16 * (size_t)r, 16);
+        const Gf t = gf_mul_fast(gf_load(z), gf_pow_fast(H, a.after[r]));
+        term.hi ^= t.hi; term.lo ^= t.lo;
+    }
+    if (lane == 31 && !a.fold_only && a.aad && a.aadlen) {    // the AAD rides in front of block 0 (aad == NULL: it came as a shard)
         Gf g{0, 0};
         for (uint64_t off = 0; off < a.aadlen; off += 16) {
             const uint64_t left = a.aadlen - off;
@@ -568,7 +573,8 @@ __global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
             g.hi ^= x.hi; g.lo ^= x.lo;
             g = gf_mul_fast(H, g);
         }
-        term = gf_mul_fast(g, gf_pow_fast(H, a.total_blocks));
+        const Gf t = gf_mul_fast(g, gf_pow_fast(H, a.total_blocks));
+        term.hi ^= t.hi; term.lo ^= t.lo;
     }
     for (int o = 16; o; o >>= 1) {
         term.hi ^= __shfl_xor_sync(0xffffffffu, term.hi, o);
@@ -583,7 +589,36 @@ __global__ void gcm_combine_kernel(const __grid_constant__ GcmCombineArgs a)
     }
     const uint4 t = gf_store(S);
     const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
-    for (uint32_t i = 0; i < 16; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
+    for (uint32_t i = 0; i < a.taglen; ++i) a.tag_out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
+}
+
+// J0 for a nonce that is not 12 bytes long (GCMsetup, micro_aes.c:1145-1149): GHASH_H({}, nonce),
+// i.e. the zero-padded nonce blocks and the length block BE64(0) || BE64(8 * ivlen).  One thread.
+struct GcmJ0Args {
+    uaes_keysched ks;
+    const uint8_t *iv;           // device memory
+    uint64_t ivlen;
+    uint8_t *out;                // 16 bytes, device memory
+};
+
+__global__ void gcm_j0_kernel(const __grid_constant__ GcmJ0Args a)
+{
+    if (threadIdx.x) return;
+    uint32_t s[4] = {0, 0, 0, 0};
+    small_encrypt(a.ks.w, a.ks.rounds, s);
+    const Gf H = gf_from_words(s[0], s[1], s[2], s[3]);
+    Gf g{0, 0};
+    for (uint64_t off = 0; off < a.ivlen; off += 16) {
+        const uint64_t left = a.ivlen - off;
+        const Gf x = gf_load(load_block_bytes(a.iv + off, left < 16 ? (uint32_t)left : 16));
+        g.hi ^= x.hi; g.lo ^= x.lo;
+        g = gf_mul_fast(H, g);
+    }
+    g.lo ^= a.ivlen * 8;
+    g = gf_mul_fast(H, g);
+    const uint4 t = gf_store(g);
+    const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+    for (uint32_t i = 0; i < 16; ++i) a.out[i] = (uint8_t)(tw[i >> 2] >> (8 * (i & 3)));
 }
 
 }  // namespace uaes
@@ -596,10 +631,21 @@ extern "C" size_t uaes_gcm_work_bytes(u64 len)
     return sizeof(GcmWork) + (size_t)nchunks * sizeof(uint4);
 }
 
-extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+extern "C" int uaes_launch_gcm_j0(const uaes_keysched *ks, const void *iv_dev, u64 ivlen, void *out_dev,
+                                  void *stream)
+{
+    using namespace uaes;
+    GcmJ0Args a;
+    a.ks = *ks; a.iv = (const uint8_t *)iv_dev; a.ivlen = ivlen; a.out = (uint8_t *)out_dev;
+    gcm_j0_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char j0b[16], const void *aad_dev,
                                u64 aadlen, const void *aad_state_dev, const void *in, void *out, u64 len,
-                               int mode, u64 first_block, int partial_only, void *tag_out, void *work,
-                               void *stream)
+                               int mode, u64 first_block, int partial_only, void *tag_out, unsigned taglen,
+                               void *work, void *stream)
 {
     using namespace uaes;
     cudaStream_t st = (cudaStream_t)stream;
@@ -607,10 +653,9 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     uint64_t rows_per_chunk, nchunks;
     gcm_plan(nblocks, rows_per_chunk, nchunks);
 
-    uint32_t j0[4];
-    for (int c = 0; c < 3; ++c)
-        j0[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
-    j0[3] = 0x01000000u;                                   // bytes 12..15 = 00 00 00 01
+    uint32_t j0[4];                                        // J0 = nonce || 00000001, or GHASH(nonce)
+    for (int c = 0; c < 4; ++c)
+        j0[c] = (uint32_t)j0b[4 * c] | (uint32_t)j0b[4 * c + 1] << 8 | (uint32_t)j0b[4 * c + 2] << 16 | (uint32_t)j0b[4 * c + 3] << 24;
 
     GcmSetupArgs s;
     s.ks = *ks;
@@ -624,10 +669,11 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
 
-    // counter field of J0 = bytes 9..11 of the nonce, then 00 00 00 01; data starts at J0 + 1
-    // (CCM_GCM pre-increment, micro_aes.c:939-941)
-    const uint64_t vj0 = (uint64_t)nonce[9] << 48 | (uint64_t)nonce[10] << 40 | (uint64_t)nonce[11] << 32 | 1u;
-    const uint32_t b8 = nonce[8];
+    // counter field of J0 = its bytes 9..15 as a 56-bit big-endian integer (micro_aes.c:421-427); data
+    // starts at J0 + 1 (CCM_GCM pre-increment, micro_aes.c:939-941)
+    uint64_t vj0 = 0;
+    for (int i = 9; i < 16; ++i) vj0 = vj0 << 8 | j0b[i];
+    const uint32_t b8 = j0b[8];
 
     if (nchunks) {
         GcmBulkArgs b;
@@ -655,27 +701,25 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonc
     f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1 + first_block) & kMask56;
     f.in = (const uint8_t *)in; f.out = (uint8_t *)out;
     f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.mode = mode; f.partial_only = partial_only; f.siv = 0;
-    f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
+    f.tag_out = (uint8_t *)tag_out; f.taglen = partial_only ? 16 : taglen; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
     ++g_launches;
     return (int)cudaGetLastError();
 }
 
-extern "C" int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+extern "C" int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char j0b[16], const void *aad_dev,
                                        u64 aadlen, u64 len, const void *partials_dev, const void *after_dev,
-                                       unsigned nshards, void *tag_out, void *stream)
+                                       unsigned nshards, void *tag_out, unsigned taglen, void *stream)
 {
     using namespace uaes;
-    if (nshards > 31) return (int)cudaErrorInvalidValue;
     GcmCombineArgs a;
     a.ks = *ks;
-    for (int c = 0; c < 3; ++c)
-        a.j0[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
-    a.j0[3] = 0x01000000u;
+    for (int c = 0; c < 4; ++c)
+        a.j0[c] = (uint32_t)j0b[4 * c] | (uint32_t)j0b[4 * c + 1] << 8 | (uint32_t)j0b[4 * c + 2] << 16 | (uint32_t)j0b[4 * c + 3] << 24;
     a.aad = (const uint8_t *)aad_dev; a.aadlen = aadlen; a.len = len;
     a.partials = (const uint8_t *)partials_dev; a.after = (const uint64_t *)after_dev;
     a.nshards = nshards; a.total_blocks = (len + 15) / 16; a.tag_out = (uint8_t *)tag_out;
-    a.fold_only = 0;
+    a.taglen = taglen; a.fold_only = 0;
     gcm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
     return (int)cudaGetLastError();
@@ -686,14 +730,13 @@ extern "C" int uaes_launch_gcm_fold(const uaes_keysched *ks, const void *partial
                                     unsigned nshards, void *out_dev, void *stream)
 {
     using namespace uaes;
-    if (nshards > 31) return (int)cudaErrorInvalidValue;
     GcmCombineArgs a;
     a.ks = *ks;
     a.j0[0] = a.j0[1] = a.j0[2] = a.j0[3] = 0;
     a.aad = nullptr; a.aadlen = 0; a.len = 0;
     a.partials = (const uint8_t *)partials_dev; a.after = (const uint64_t *)after_dev;
     a.nshards = nshards; a.total_blocks = 0; a.tag_out = (uint8_t *)out_dev;
-    a.fold_only = 1;
+    a.taglen = 16; a.fold_only = 1;
     gcm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     ++g_launches;
     return (int)cudaGetLastError();
@@ -756,7 +799,7 @@ extern "C" int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned c
     f.in = (const uint8_t *)data; f.out = nullptr;
     f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk;
     f.mode = 1; f.partial_only = partial_only; f.siv = 1;
-    f.tag_out = (uint8_t *)tag_out; f.work = (GcmWork *)work;
+    f.tag_out = (uint8_t *)tag_out; f.taglen = 16; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
     ++g_launches;
     return (int)cudaGetLastError();

@@ -10,10 +10,15 @@
  *
  * Buffers are classified per call (cudaPointerGetAttributes):
  *   device / managed, 16-byte aligned  -> kernels run directly on them, zero copies;
- *   anything else (pageable or pinned host memory, misaligned device memory) -> staged through
- *   three device chunks on three streams so that H2D, kernel and D2H of consecutive chunks
- *   overlap (CTR, ECB, XTS sectors), or through one full-size device buffer (GCM, single XTS
- *   data unit, which cannot be cut).
+ *   pinned host memory                 -> staged through three device chunks on three streams so
+ *                                         that H2D, kernel and D2H of consecutive chunks overlap;
+ *   pageable host memory               -> the same pipeline behind pinned bounce chunks that a
+ *                                         few helper threads fill and drain (memcpy only);
+ *   misaligned device memory           -> the same pipeline with device-to-device copies.
+ * Every mode of the hot path is cut into chunks: CTR / ECB / XTS sectors by block or sector
+ * range, one XTS data unit by tweak jump-ahead, GCM as a sequence of shards whose 16-byte GHASH
+ * contributions are folded at the end.  With uaes_set_devices(n) a host-buffer call is spread
+ * over n GPUs, one part and one host thread per device, each under its own device's lock.
  */
 #include <cuda_runtime_api.h>
 #include <pthread.h>
@@ -191,19 +196,91 @@ static void make_ctrblock(const u8 *iv, u64 start, u64 first, uaes_ctrblock *cb)
     cb->v0 = (v + first) & (((u64)1 << 56) - 1);  /* 56-bit carry, micro_aes.c:421-427 */
 }
 
+/* a caller-supplied 16-byte counter block (PRESET_COUNTER, micro_aes.c:964-966; GCM's J0) advanced
+ * by `add` blocks: bytes 9..15 are the 56-bit big-endian counter (micro_aes.c:421-427) */
+static void block_to_ctrblock(const u8 *blk, u64 add, uaes_ctrblock *cb)
+{
+    u64 v = 0;
+    int i;
+    for (i = 9; i < 16; ++i) v = v << 8 | blk[i];
+    cb->w0 = (u32)blk[0] | (u32)blk[1] << 8 | (u32)blk[2] << 16 | (u32)blk[3] << 24;
+    cb->w1 = (u32)blk[4] | (u32)blk[5] << 8 | (u32)blk[6] << 16 | (u32)blk[7] << 24;
+    cb->b8 = blk[8];
+    cb->v0 = (v + add) & (((u64)1 << 56) - 1);
+}
+
 /* ------------------------------------------------------------------ per-device resources */
 
+/* One devctx per CUDA device, each with its OWN lock: threads driving different GPUs never wait for
+ * each other.  The lock covers what is shared per device -- the staging slots (a staged call owns
+ * them for its whole H2D / kernel / D2H pipeline), the full-size staging buffer and the
+ * bookkeeping of the scratch pool.  Calls on device-resident buffers take it only while they pick a
+ * scratch block; plain CTR / ECB / XTS launches on device memory take no lock at all. */
+#define MAX_SCRATCH 16
+
 typedef struct {
-    int ready;
-    void *slot[MAX_SLOT];
+    void *p; size_t bytes;
+    cudaEvent_t ev;                     /* recorded after the last kernel that used the block */
+    cudaStream_t last;                  /* ... on this stream */
+    int busy, used, have_ev;
+} scratch;
+
+typedef struct {
+    int ready, dev;
+    pthread_mutex_t lock;               /* staging: slots, streams st[], big */
+    pthread_mutex_t plock;              /* scratch pool bookkeeping (taken briefly, may nest inside lock) */
+    void *slot[MAX_SLOT];               /* device chunks of the staging pipeline */
+    void *hslot[MAX_SLOT];              /* pinned host chunks: bounce buffers for PAGEABLE caller memory */
     cudaStream_t st[MAX_SLOT];
-    void *big;  size_t big_bytes;       /* grow-only full-size staging (GCM / XTS unit) */
-    void *work; size_t work_bytes;      /* grow-only GCM scratch + AAD copy */
+    cudaEvent_t ev[MAX_SLOT];
+    void *big;  size_t big_bytes;       /* full-size staging (GCM decrypt, CBC/CFB, batches); trimmed after use */
+    scratch pool[MAX_SCRATCH];          /* GCM / OCB / batch work areas: one block per call in flight */
 } devctx;
 
 static devctx g_dev[MAX_DEV];
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_once_t g_dev_once = PTHREAD_ONCE_INIT;
+static pthread_mutex_t g_cfg_lock = PTHREAD_MUTEX_INITIALIZER;     /* first-use initialisation only */
+static int g_cfg_ready;
 
+/* process-wide settings (uaes_set_devices, uaes_set_burn, ...) */
+static int    g_fan_devices = 1;                      /* devices a host-buffer call may be spread over */
+static size_t g_fan_min = (size_t)256 << 20;          /* ... when every device gets at least this much */
+static int    g_burn;                                 /* wipe staging memory and scratch after each call */
+static size_t g_big_keep = (size_t)256 << 20;         /* full-size staging above this is freed after the call */
+static int    g_copy_threads = 4;                     /* helpers that move pageable memory to / from the pinned chunks */
+
+static void dev_locks_init(void)
+{
+    int i;
+    for (i = 0; i < MAX_DEV; ++i) {
+        pthread_mutex_init(&g_dev[i].lock, NULL);
+        pthread_mutex_init(&g_dev[i].plock, NULL);
+        g_dev[i].dev = i;
+    }
+}
+
+static void cfg_init(void)
+{
+    const char *e;
+    pthread_mutex_lock(&g_cfg_lock);
+    if (!g_cfg_ready) {
+        if ((e = getenv("UAES_STAGE_SLOTS")) != NULL && atoi(e) >= 1 && atoi(e) <= MAX_SLOT) g_nslot = atoi(e);
+        if ((e = getenv("UAES_STAGE_CHUNK_MIB")) != NULL && atoi(e) >= 1 && (size_t)atoi(e) <= (MAX_CHUNK >> 20))
+            g_chunk = (size_t)atoi(e) << 20;
+        if ((e = getenv("UAES_DEVICES")) != NULL) {
+            int n = atoi(e), have = uaes_device_count();
+            g_fan_devices = (n <= 0 || n > have) ? have : n;
+            if (g_fan_devices < 1) g_fan_devices = 1;
+        }
+        if ((e = getenv("UAES_FANOUT_MIN_MIB")) != NULL && atoi(e) >= 1) g_fan_min = (size_t)atoi(e) << 20;
+        if ((e = getenv("UAES_BURN")) != NULL) g_burn = atoi(e) != 0;
+        if ((e = getenv("UAES_COPY_THREADS")) != NULL && atoi(e) >= 1 && atoi(e) <= 32) g_copy_threads = atoi(e);
+        g_cfg_ready = 1;
+    }
+    pthread_mutex_unlock(&g_cfg_lock);
+}
+
+/* context of the calling thread's current device; creates its streams on first use */
 static int get_ctx(devctx **out)
 {
     int dev = 0, i, n = 0;
@@ -214,30 +291,40 @@ static int get_ctx(devctx **out)
     }
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV)
         return fail(UAES_E_NO_DEVICE, "cudaGetDevice failed", (int)cudaGetLastError());
+    pthread_once(&g_dev_once, dev_locks_init);
+    if (!g_cfg_ready) cfg_init();
     c = &g_dev[dev];
     if (!c->ready) {
-        const char *e;
-        if ((e = getenv("UAES_STAGE_SLOTS")) != NULL && atoi(e) >= 1 && atoi(e) <= MAX_SLOT) g_nslot = atoi(e);
-        if ((e = getenv("UAES_STAGE_CHUNK_MIB")) != NULL && atoi(e) >= 1 && (size_t)atoi(e) <= (MAX_CHUNK >> 20))
-            g_chunk = (size_t)atoi(e) << 20;
-        for (i = 0; i < MAX_SLOT; ++i)
-            if (cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking) != cudaSuccess)
-                return fail(UAES_E_CUDA, "cudaStreamCreate", (int)cudaGetLastError());
-        c->ready = 1;
+        pthread_mutex_lock(&c->lock);
+        if (!c->ready) {
+            for (i = 0; i < MAX_SLOT; ++i)
+                if (cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                    pthread_mutex_unlock(&c->lock);
+                    return fail(UAES_E_CUDA, "cudaStreamCreate", (int)cudaGetLastError());
+                }
+            c->ready = 1;
+        }
+        pthread_mutex_unlock(&c->lock);
     }
     *out = c;
     return 0;
 }
 
-static int need_slots(devctx *c)
+/* lock held */
+static int need_slots(devctx *c, int pinned_too)
 {
     int i;
-    for (i = 0; i < NSLOT; ++i)
-        if (!c->slot[i] && cudaMalloc(&c->slot[i], CHUNK_BYTES + 16) != cudaSuccess)
+    for (i = 0; i < NSLOT; ++i) {
+        if (!c->slot[i] && cudaMalloc(&c->slot[i], CHUNK_BYTES + 32) != cudaSuccess)
             return fail(UAES_E_NO_MEMORY, "cudaMalloc(staging chunk)", (int)cudaGetLastError());
+        if (pinned_too && !c->hslot[i] && cudaHostAlloc(&c->hslot[i], CHUNK_BYTES + 32, cudaHostAllocDefault) != cudaSuccess)
+            return fail(UAES_E_NO_MEMORY, "cudaHostAlloc(bounce chunk)", (int)cudaGetLastError());
+    }
     return 0;
 }
 
+/* lock held */
 static int grow(void **p, size_t *have, size_t want, const char *what)
 {
     if (*have >= want) return 0;
@@ -248,14 +335,95 @@ static int grow(void **p, size_t *have, size_t want, const char *what)
     return 0;
 }
 
-/* device (or managed) memory that the kernels may touch directly with 128-bit accesses */
-static int is_direct(const void *p)
+/* lock held, all work on `big` complete: a multi-GiB staging buffer does not outlive its call
+ * (one 16 GiB host GCM call used to pin 16 GiB of HBM for the life of the process) */
+static void big_done(devctx *c)
+{
+    if (c->big && g_burn) cudaMemset(c->big, 0, c->big_bytes);
+    if (c->big && c->big_bytes > g_big_keep) { cudaFree(c->big); c->big = NULL; c->big_bytes = 0; }
+}
+
+/* A work area for ONE call: never shared by two calls in flight.  A block is handed out again only
+ * to the stream that used it last (stream order protects it) or once its event has completed, so
+ * asynchronous calls on different user streams cannot trample each other's H, E(J0), partials or
+ * tag scratch. */
+static int scratch_get_locked(devctx *c, size_t want, cudaStream_t st, scratch **out)
+{
+    int i, pick = -1, idle = -1, empty = -1, waitable = -1;
+    for (i = 0; i < MAX_SCRATCH; ++i) {
+        scratch *s = &c->pool[i];
+        if (s->busy) continue;
+        if (!s->p) { if (empty < 0) empty = i; continue; }
+        if (!s->used || s->last == st || cudaEventQuery(s->ev) == cudaSuccess) {
+            if (s->bytes >= want) { pick = i; break; }
+            if (idle < 0) idle = i;
+        } else if (waitable < 0) waitable = i;
+    }
+    cudaGetLastError();                                   /* cudaErrorNotReady from the queries */
+    if (pick < 0) {
+        scratch *s;
+        if (empty >= 0) pick = empty;
+        else if (idle >= 0) pick = idle;
+        else if (waitable >= 0) { pick = waitable; cudaEventSynchronize(c->pool[pick].ev); }
+        else return fail(UAES_E_NO_MEMORY, "more than 16 calls in flight on one device", 0);
+        s = &c->pool[pick];
+        if (s->p && s->bytes < want) {
+            if (s->used && s->last == st) cudaStreamSynchronize(st);      /* still queued work may read it */
+            cudaFree(s->p); s->p = NULL; s->bytes = 0;
+        }
+        if (!s->p) {
+            const size_t b = want + want / 8 + 4096;
+            if (cudaMalloc(&s->p, b) != cudaSuccess) return fail(UAES_E_NO_MEMORY, "cudaMalloc(work area)", (int)cudaGetLastError());
+            s->bytes = b; s->used = 0;
+        }
+        if (!s->have_ev) {
+            if (cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming) != cudaSuccess)
+                return fail(UAES_E_CUDA, "cudaEventCreate", (int)cudaGetLastError());
+            s->have_ev = 1;
+        }
+    }
+    c->pool[pick].busy = 1;
+    *out = &c->pool[pick];
+    return 0;
+}
+
+static int scratch_get(devctx *c, size_t want, cudaStream_t st, scratch **out)
+{
+    int rc;
+    pthread_mutex_lock(&c->plock);
+    rc = scratch_get_locked(c, want, st, out);
+    pthread_mutex_unlock(&c->plock);
+    return rc;
+}
+
+/* everything that uses the block has been enqueued on st */
+static void scratch_put(devctx *c, scratch *s, cudaStream_t st)
+{
+    if (!s) return;
+    pthread_mutex_lock(&c->plock);
+    if (g_burn) cudaMemsetAsync(s->p, 0, s->bytes, st);   /* H, E(J0), derived keys, tag scratch */
+    cudaEventRecord(s->ev, st);
+    s->last = st; s->used = 1; s->busy = 0;
+    pthread_mutex_unlock(&c->plock);
+}
+
+#define PTR_DEVICE   0   /* device or managed memory, 16-byte aligned: kernels touch it directly */
+#define PTR_PINNED   1   /* page-locked host memory (cudaHostAlloc / cudaHostRegister): DMA at full speed */
+#define PTR_PAGEABLE 2   /* plain malloc'd memory: moved through pinned bounce chunks by helper threads */
+#define PTR_OTHER    3   /* misaligned device memory: staged with device-to-device copies */
+
+static int ptr_class(const void *p)
 {
     struct cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return 0;
-    return ((size_t)p & 15) == 0;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return PTR_PAGEABLE; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)
+        return ((size_t)p & 15) == 0 ? PTR_DEVICE : PTR_OTHER;
+    if (at.type == cudaMemoryTypeHost) return PTR_PINNED;
+    return PTR_PAGEABLE;
 }
+
+/* device (or managed) memory that the kernels may touch directly with 128-bit accesses */
+static int is_direct(const void *p) { return ptr_class(p) == PTR_DEVICE; }
 
 static int finish_direct(void)
 {
@@ -266,77 +434,331 @@ static int finish_direct(void)
     return 0;
 }
 
+/* ------------------------------------------------------------------ helpers for pageable memory */
+
+/* cudaMemcpyAsync on pageable memory is synchronous and single-threaded inside the driver, which
+ * serialises the whole pipeline (H2D of chunk k+1 cannot overlap D2H of chunk k).  For pageable
+ * caller buffers the library therefore owns pinned bounce chunks and moves the bytes itself with a
+ * few helper threads: memcpy into the pinned chunk, DMA, kernel, DMA, memcpy out -- the memcpys of
+ * neighbouring chunks overlap each other and the DMA.  This is data movement only; no cipher work
+ * happens on the host. */
+typedef struct { u8 *dst; const u8 *src; size_t n; int *left; } copy_piece;
+
+#define COPY_QUEUE 128
+typedef struct copy_pool {
+    pthread_mutex_t m;
+    pthread_cond_t work, done;
+    copy_piece q[COPY_QUEUE];
+    unsigned head, tail;
+    int nthreads;
+    pthread_t th[32];
+} copy_pool;
+
+static copy_pool g_cp = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+                          {{0, 0, 0, 0}}, 0, 0, 0, {0} };
+
+static void *copy_worker(void *arg)
+{
+    copy_pool *p = (copy_pool *)arg;
+    pthread_mutex_lock(&p->m);
+    for (;;) {
+        copy_piece w;
+        while (p->head == p->tail) pthread_cond_wait(&p->work, &p->m);
+        w = p->q[p->head % COPY_QUEUE]; ++p->head;
+        pthread_mutex_unlock(&p->m);
+        memcpy(w.dst, w.src, w.n);
+        pthread_mutex_lock(&p->m);
+        --*w.left;
+        pthread_cond_broadcast(&p->done);
+    }
+    return NULL;
+}
+
+/* copy n bytes with the helper threads (shared by all devices' pipelines) and return when all of
+ * it has arrived; the calling thread copies one share itself */
+static void copy_parallel(void *dst, const void *src, size_t n)
+{
+    copy_pool *p = &g_cp;
+    int parts, i, left = 0;
+    size_t per, own;
+    if (n < ((size_t)1 << 20) || g_copy_threads <= 1) { memcpy(dst, src, n); return; }
+    pthread_mutex_lock(&p->m);
+    while (p->nthreads < g_copy_threads - 1) {
+        pthread_attr_t at;
+        pthread_attr_init(&at);
+        pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+        if (pthread_create(&p->th[p->nthreads], &at, copy_worker, p) != 0) { pthread_attr_destroy(&at); break; }
+        pthread_attr_destroy(&at);
+        ++p->nthreads;
+    }
+    parts = p->nthreads + 1;
+    per = ((n + (size_t)parts - 1) / (size_t)parts + 4095) & ~(size_t)4095;
+    while ((int)(p->tail - p->head) + parts > COPY_QUEUE) pthread_cond_wait(&p->done, &p->m);
+    for (i = 1; i < parts; ++i) {
+        const size_t off = per * (size_t)i;
+        copy_piece *q;
+        if (off >= n) break;
+        q = &p->q[p->tail % COPY_QUEUE];
+        q->dst = (u8 *)dst + off; q->src = (const u8 *)src + off; q->n = n - off < per ? n - off : per; q->left = &left;
+        ++p->tail; ++left;
+    }
+    pthread_cond_broadcast(&p->work);
+    pthread_mutex_unlock(&p->m);
+    own = n < per ? n : per;
+    memcpy(dst, src, own);
+    pthread_mutex_lock(&p->m);
+    while (left) pthread_cond_wait(&p->done, &p->m);
+    pthread_mutex_unlock(&p->m);
+}
+
 /* ------------------------------------------------------------------ chunked staging pipeline */
 
-typedef int (*chunk_fn)(void *user, u64 offset, void *dev, size_t bytes, size_t out_bytes, void *stream);
+/* one chunk, resident in a device slot: offset = byte offset inside the WHOLE call (not the part),
+ * index = number of the chunk inside this device's part, slot = which slot / work area it uses */
+typedef int (*chunk_fn)(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t out_bytes,
+                        void *stream);
 
-/* in/out may be any mix of host and device memory.  `unit` = granularity a chunk must respect.
- * out_extra = bytes the LAST chunk writes beyond its input size (ECB padding). */
-static int run_chunked(devctx *c, const void *in, void *out, size_t len, size_t unit, size_t out_extra,
-                       chunk_fn fn, void *user)
+typedef struct {
+    const u8 *in; u8 *out;       /* this part's first byte (host or device memory, any mix) */
+    size_t len;                  /* bytes of this part */
+    u64 base;                    /* offset of the part inside the whole call */
+    size_t unit;                 /* a chunk is a multiple of this */
+    size_t out_extra;            /* bytes the LAST chunk writes beyond its input size (ECB padding) */
+    size_t absorb_tail;          /* a final piece of fewer than this many bytes joins the chunk before it
+                                    (XTS stealing needs the last full block and the ragged tail together) */
+    u8 *resident;                /* non-NULL: chunk k stays at resident + offset (device memory holding the whole
+                                    part) instead of a slot, and nothing is copied back (out is NULL) */
+    chunk_fn fn; void *user;     /* fn may be NULL: a pure copy */
+} pipe_part;
+
+static size_t pipe_chunk_bytes(const pipe_part *p) { return CHUNK_BYTES - CHUNK_BYTES % p->unit; }
+
+static size_t pipe_nchunks(const pipe_part *p)
+{
+    const size_t chunk = pipe_chunk_bytes(p);
+    size_t n;
+    if (p->len == 0 || chunk == 0) return 0;
+    n = (p->len + chunk - 1) / chunk;
+    if (n > 1 && p->len - (n - 1) * chunk < p->absorb_tail) --n;
+    return n;
+}
+
+/* Runs one part through the device's slots.  Caller holds c->lock and has made `c` current. */
+static int run_chunked(devctx *c, const pipe_part *p)
 {
     int rc = 0, i;
-    size_t off = 0, chunk = CHUNK_BYTES - CHUNK_BYTES % unit;
-    unsigned n = 0;
+    const size_t chunk = pipe_chunk_bytes(p), nchunks = pipe_nchunks(p);
+    const int bounce_in = ptr_class(p->in) == PTR_PAGEABLE, bounce_out = p->out && ptr_class(p->out) == PTR_PAGEABLE;
+    size_t k, off = 0;
+    size_t pend_off[MAX_SLOT], pend_bytes[MAX_SLOT];        /* bounce mode: chunks whose copy-out is due */
+    int pend[MAX_SLOT];
 
-    if ((rc = need_slots(c)) != 0) return rc;
-    /* inputs produced on the caller's stream (mixed host/device calls) must be complete */
-    CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
-    while (off < len) {
-        const size_t bytes = len - off < chunk ? len - off : chunk;
-        const size_t obytes = bytes + (off + bytes == len ? out_extra : 0);
-        const int s = (int)(n++ % NSLOT);
-        CU(cudaMemcpyAsync(c->slot[s], (const u8 *)in + off, bytes, cudaMemcpyDefault, c->st[s]));
-        rc = fn(user, off, c->slot[s], bytes, obytes, c->st[s]);
-        if (rc) goto done;
-        CU(cudaMemcpyAsync((u8 *)out + off, c->slot[s], obytes, cudaMemcpyDefault, c->st[s]));
+    if (chunk == 0) return fail(UAES_E_BAD_ARGUMENT, "unit larger than the staging chunk", 0);
+    if ((rc = need_slots(c, bounce_in || bounce_out)) != 0) return rc;
+    for (i = 0; i < MAX_SLOT; ++i) pend[i] = 0;
+
+    for (k = 0; k < nchunks; ++k) {
+        const size_t bytes = k + 1 == nchunks ? p->len - off : chunk;
+        const size_t obytes = bytes + (k + 1 == nchunks ? p->out_extra : 0);
+        const int s = (int)(k % (size_t)NSLOT);
+        u8 *d = p->resident ? p->resident + off : (u8 *)c->slot[s];
+        /* the slot's previous chunk must have left it (and, in bounce mode, its pinned chunk) */
+        if (pend[s]) {
+            CU(cudaEventSynchronize(c->ev[s]));
+            copy_parallel(p->out + pend_off[s], c->hslot[s], pend_bytes[s]);
+            pend[s] = 0;
+        }
+        if (bounce_in) {
+            if (!bounce_out && k >= (size_t)NSLOT) CU(cudaStreamSynchronize(c->st[s]));   /* pinned chunk still being read */
+            copy_parallel(c->hslot[s], p->in + off, bytes);
+            CU(cudaMemcpyAsync(d, c->hslot[s], bytes, cudaMemcpyHostToDevice, c->st[s]));
+        } else {
+            CU(cudaMemcpyAsync(d, p->in + off, bytes, cudaMemcpyDefault, c->st[s]));
+        }
+        if (p->fn && (rc = p->fn(p->user, p->base + off, k, s, d, bytes, obytes, c->st[s])) != 0) goto done;
+        if (!p->out) {
+            /* resident part: the result stays on the device */
+        } else if (bounce_out) {
+            CU(cudaMemcpyAsync(c->hslot[s], d, obytes, cudaMemcpyDeviceToHost, c->st[s]));
+            CU(cudaEventRecord(c->ev[s], c->st[s]));
+            pend[s] = 1; pend_off[s] = off; pend_bytes[s] = obytes;
+        } else {
+            CU(cudaMemcpyAsync(p->out + off, d, obytes, cudaMemcpyDefault, c->st[s]));
+        }
+        if (g_burn && !p->resident) CU(cudaMemsetAsync(c->slot[s], 0, CHUNK_BYTES, c->st[s]));
         off += bytes;
+    }
+    /* drain in chunk order */
+    for (k = nchunks > (size_t)NSLOT ? nchunks - (size_t)NSLOT : 0; k < nchunks; ++k) {
+        const int s = (int)(k % (size_t)NSLOT);
+        if (pend[s]) {
+            CU(cudaEventSynchronize(c->ev[s]));
+            copy_parallel(p->out + pend_off[s], c->hslot[s], pend_bytes[s]);
+            pend[s] = 0;
+        }
     }
 done:
     for (i = 0; i < NSLOT; ++i) {
         cudaError_t e = cudaStreamSynchronize(c->st[i]);
         if (e != cudaSuccess && !rc) rc = fail(UAES_E_CUDA, "cudaStreamSynchronize(staging)", (int)e);
     }
+    if (g_burn && (bounce_in || bounce_out))
+        for (i = 0; i < NSLOT; ++i) if (c->hslot[i]) memset(c->hslot[i], 0, CHUNK_BYTES);
     return rc;
+}
+
+/* ------------------------------------------------------------------ spreading a call over devices */
+
+/* A host-buffer call may use every GPU of the box (extension 5): the byte range is cut
+ * into one contiguous part per device (block / sector ranges are independent), each part
+ * runs the staging pipeline of ITS device on its own host thread, with that device's lock only.
+ * uaes_set_devices(n) (or UAES_DEVICES) turns it on; a call is spread only as far as every device
+ * still gets uaes_set_fanout_min() bytes. */
+typedef struct {
+    int dev, rc, err;
+    char msg[160];
+    pipe_part part;
+    int (*before)(devctx *c, void *user, const pipe_part *p);    /* per-device set-up under the lock (may be NULL) */
+    int (*after)(devctx *c, void *user, const pipe_part *p);     /* per-device wrap-up, pipeline drained (may be NULL) */
+    pthread_t th;
+    int threaded;
+} fan_part;
+
+static int fan_run_one(fan_part *f)
+{
+    devctx *c;
+    int rc;
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    pthread_mutex_lock(&c->lock);
+    rc = f->before ? f->before(c, f->part.user, &f->part) : 0;
+    if (!rc) rc = run_chunked(c, &f->part);
+    if (!rc && f->after) rc = f->after(c, f->part.user, &f->part);
+    pthread_mutex_unlock(&c->lock);
+    return rc;
+}
+
+static void *fan_thread(void *arg)
+{
+    fan_part *f = (fan_part *)arg;
+    cudaError_t e = cudaSetDevice(f->dev);
+    tls_stream = NULL; tls_async = 0;
+    f->rc = e == cudaSuccess ? fan_run_one(f) : fail(UAES_E_CUDA, "cudaSetDevice", (int)e);
+    f->err = tls_err;
+    memcpy(f->msg, tls_msg, sizeof f->msg);
+    return NULL;
+}
+
+/* number of devices a staged call of `len` bytes is spread over */
+static int fan_width(size_t len, const void *in, const void *out)
+{
+    int n;
+    if (!g_cfg_ready) cfg_init();
+    n = g_fan_devices;
+    /* device-resident data stays on its device: only host memory is worth spreading */
+    if (n <= 1 || ptr_class(in) == PTR_DEVICE || ptr_class(in) == PTR_OTHER ||
+        ptr_class(out) == PTR_DEVICE || ptr_class(out) == PTR_OTHER) return 1;
+    while (n > 1 && len / (size_t)n < g_fan_min) --n;
+    return n;
+}
+
+/* Cuts `whole` into n parts at multiples of `align` bytes: part 0 for the calling thread's current
+ * device, part i for device (current + i) mod count.  Returns the number of parts. */
+static int fan_plan(const pipe_part *whole, int n, size_t align, fan_part f[MAX_DEV])
+{
+    int i, cur = 0, count = uaes_device_count();
+    size_t per, off = 0;
+    if (n > count) n = count;
+    if (n > MAX_DEV) n = MAX_DEV;
+    if (n < 1) n = 1;
+    if (n > 1 && cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); n = 1; }
+    per = (whole->len / (size_t)n + align - 1) / align * align;
+    for (i = 0; i < n; ++i) {
+        const size_t bytes = i + 1 == n ? whole->len - off : (whole->len - off < per ? whole->len - off : per);
+        memset(&f[i], 0, sizeof f[i]);
+        f[i].dev = count ? (cur + i) % count : 0;
+        f[i].part = *whole;
+        f[i].part.in = whole->in + off;
+        f[i].part.out = whole->out ? whole->out + off : NULL;
+        f[i].part.len = bytes; f[i].part.base = whole->base + off;
+        f[i].part.out_extra = i + 1 == n ? whole->out_extra : 0;
+        f[i].part.absorb_tail = i + 1 == n ? whole->absorb_tail : 0;
+        off += bytes;
+    }
+    return n;
+}
+
+/* part 0 on the calling thread, every other non-empty part on a thread of its own */
+static int fan_exec(fan_part f[], int n)
+{
+    int i, rc;
+    for (i = 1; i < n; ++i) {
+        f[i].threaded = 0; f[i].rc = 0;
+        if (f[i].part.len == 0) continue;
+        if (pthread_create(&f[i].th, NULL, fan_thread, &f[i]) == 0) f[i].threaded = 1;
+        else { f[i].rc = fail(UAES_E_NO_MEMORY, "pthread_create(device worker)", 0); f[i].err = tls_err; memcpy(f[i].msg, tls_msg, sizeof f[i].msg); }
+    }
+    rc = f[0].rc = f[0].part.len ? fan_run_one(&f[0]) : 0;
+    for (i = 1; i < n; ++i) {
+        if (f[i].threaded) pthread_join(f[i].th, NULL);
+        if (f[i].rc && !rc) {                          /* hand the worker's error to the caller's latch */
+            rc = f[i].rc; tls_err = f[i].err; memcpy(tls_msg, f[i].msg, sizeof tls_msg);
+        }
+    }
+    return rc;
+}
+
+/* the common case: every part shares one read-only job description */
+static int fan_out(const pipe_part *whole, int n, size_t align)
+{
+    fan_part f[MAX_DEV];
+    n = fan_plan(whole, n, align, f);
+    return fan_exec(f, n);
 }
 
 /* ------------------------------------------------------------------ CTR */
 
-typedef struct { uaes_keysched ks; const u8 *iv; u64 first; } ctr_job;
+typedef struct { uaes_keysched ks; uaes_ctrblock cb0; } ctr_job;    /* cb0 = counter block of byte 0 of the call */
 
-static int ctr_chunk(void *user, u64 offset, void *dev, size_t bytes, size_t obytes, void *stream)
+static int ctr_chunk(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t obytes, void *stream)
 {
     ctr_job *j = (ctr_job *)user;
-    uaes_ctrblock cb;
+    uaes_ctrblock cb = j->cb0;
     int e;
-    (void)obytes;
-    make_ctrblock(j->iv, 1, j->first + offset / 16, &cb);
+    (void)obytes; (void)index; (void)slot;
+    cb.v0 = (cb.v0 + offset / 16) & (((u64)1 << 56) - 1);
     e = uaes_launch_ctr(&j->ks, &cb, dev, dev, bytes, stream);
     return e ? fail(UAES_E_CUDA, "ctr kernel launch", e) : 0;
+}
+
+static int ctr_run(ctr_job *j, const void *in, size_t len, void *out)
+{
+    devctx *c;
+    int rc;
+    if (len == 0) return 0;                         /* NULL data is fine when there is none */
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    if (is_direct(in) && is_direct(out)) {
+        LAUNCH(uaes_launch_ctr(&j->ks, &j->cb0, in, out, len, tls_stream));
+        rc = finish_direct();
+    } else {
+        pipe_part p;
+        memset(&p, 0, sizeof p);
+        p.in = (const u8 *)in; p.out = (u8 *)out; p.len = len; p.unit = 16; p.fn = ctr_chunk; p.user = j;
+        /* inputs produced on the caller's stream (mixed host/device calls) must be complete */
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        rc = fan_out(&p, fan_width(len, in, out), 16384);
+    }
+done:
+    if (g_burn) memset(j, 0, sizeof *j);            /* BURN(RoundKey), micro_aes.c:975 */
+    return rc;
 }
 
 int uaes_ctr_crypt_range(int keybits, const uaes_u8 *key, const uaes_u8 *iv, uaes_u64 first_block,
                          const void *in, size_t len, void *out)
 {
-    devctx *c;
     ctr_job j;
-    int rc;
     if (expand_key(keybits, key, &j.ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
-    if (len == 0) return 0;                         /* NULL data is fine when there is none */
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
-    j.iv = iv; j.first = first_block;
-    if (is_direct(in) && is_direct(out)) {
-        uaes_ctrblock cb;
-        make_ctrblock(iv, 1, first_block, &cb);
-        LAUNCH(uaes_launch_ctr(&j.ks, &cb, in, out, len, tls_stream));
-        rc = finish_direct();
-    } else {
-        rc = run_chunked(c, in, out, len, 16, 0, ctr_chunk, &j);
-    }
-done:
-    pthread_mutex_unlock(&g_lock);
-    return rc;
+    make_ctrblock(iv, 1, first_block, &j.cb0);
+    return ctr_run(&j, in, len, out);
 }
 
 int uaes_ctr_crypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out)
@@ -344,76 +766,118 @@ int uaes_ctr_crypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const voi
     return uaes_ctr_crypt_range(keybits, key, iv, 0, in, len, out);
 }
 
+/* the reference built with PRESET_COUNTER = 1 (micro_aes.c:964-966): the caller's 16 bytes ARE
+ * counter block 0; block k adds k to the 56-bit big-endian field in bytes 9..15 */
+int uaes_ctr_crypt_block(int keybits, const uaes_u8 *key, const uaes_u8 *ctr, uaes_u64 first_block,
+                         const void *in, size_t len, void *out)
+{
+    ctr_job j;
+    if (expand_key(keybits, key, &j.ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    block_to_ctrblock(ctr, first_block, &j.cb0);
+    return ctr_run(&j, in, len, out);
+}
+
 /* ------------------------------------------------------------------ ECB */
 
-typedef struct { uaes_keysched ks; int encrypt; } ecb_job;
+typedef struct { uaes_keysched ks; int encrypt, pad; size_t total; } ecb_job;
 
-static int ecb_chunk(void *user, u64 offset, void *dev, size_t bytes, size_t obytes, void *stream)
+static int ecb_chunk(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t obytes, void *stream)
 {
     ecb_job *j = (ecb_job *)user;
     int e;
-    (void)offset; (void)obytes;
-    e = uaes_launch_ecb(&j->ks, j->encrypt, dev, dev, bytes, stream);
+    (void)obytes; (void)index; (void)slot;
+    /* only the chunk that ends the message is padded (PKCS#7 / ISO 7816 always add a block there) */
+    e = uaes_launch_ecb(&j->ks, j->encrypt, offset + bytes == j->total ? j->pad : 0, dev, dev, bytes, stream);
     return e ? fail(UAES_E_CUDA, "ecb kernel launch", e) : 0;
 }
 
-static int ecb_common(int keybits, const u8 *key, const void *in, size_t len, void *out, int encrypt)
+static int ecb_common(int keybits, const u8 *key, const void *in, size_t len, void *out, int encrypt, int pad)
 {
     devctx *c;
     ecb_job j;
     uaes_keysched enc;
     int rc;
     if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (pad < 0 || pad > 2) return fail(UAES_E_BAD_ARGUMENT, "padding must be 0 (zeros), 1 (PKCS#7) or 2 (ISO/IEC 7816-4)", 0);
     if (encrypt) j.ks = enc; else invert_schedule(&enc, &j.ks);
-    j.encrypt = encrypt;
-    if (len == 0) return 0;
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    j.encrypt = encrypt; j.pad = encrypt ? pad : 0; j.total = len;
+    if (len == 0 && !j.pad) return 0;
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    if (len == 0) {
+        /* an empty message still encrypts to one full padding block: stage that block alone */
+        u8 *d;
+        pthread_mutex_lock(&c->lock);
+        if ((rc = need_slots(c, 0)) == 0) {
+            d = (u8 *)c->slot[0];
+            rc = uaes_launch_ecb(&j.ks, 1, j.pad, d, d, 0, c->st[0]);
+            if (rc) rc = fail(UAES_E_CUDA, "ecb kernel launch", rc);
+            else if (cudaMemcpyAsync(out, d, 16, cudaMemcpyDefault, c->st[0]) != cudaSuccess ||
+                     cudaStreamSynchronize(c->st[0]) != cudaSuccess)
+                rc = fail(UAES_E_CUDA, "cudaMemcpy(padding block)", (int)cudaGetLastError());
+        }
+        pthread_mutex_unlock(&c->lock);
+        return rc;
+    }
     if (is_direct(in) && is_direct(out)) {
-        LAUNCH(uaes_launch_ecb(&j.ks, encrypt, in, out, len, tls_stream));
+        LAUNCH(uaes_launch_ecb(&j.ks, encrypt, j.pad, in, out, len, tls_stream));
         rc = finish_direct();
     } else {
-        /* encrypt pads the ragged tail to a whole block: the last chunk returns up to 15 more bytes */
-        const size_t extra = (encrypt && len % 16) ? 16 - len % 16 : 0;
-        rc = run_chunked(c, in, out, len, 16, extra, ecb_chunk, &j);
+        /* encrypt pads the tail to a whole block: the last chunk returns up to 16 more bytes */
+        pipe_part p;
+        memset(&p, 0, sizeof p);
+        p.in = (const u8 *)in; p.out = (u8 *)out; p.len = len; p.unit = 16; p.fn = ecb_chunk; p.user = &j;
+        p.out_extra = !encrypt ? 0 : j.pad ? 16 - len % 16 : (16 - len % 16) % 16;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        rc = fan_out(&p, fan_width(len, in, out), 16384);
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    if (g_burn) { memset(&j, 0, sizeof j); memset(&enc, 0, sizeof enc); }
     return rc;
 }
 
 int uaes_ecb_encrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out)
 {
-    return ecb_common(keybits, key, in, len, out, 1);
+    return ecb_common(keybits, key, in, len, out, 1, 0);
+}
+
+/* AES_PADDING = 1 / 2 of the reference (micro_aes.h:78-80): out holds (len / 16 + 1) * 16 bytes */
+int uaes_ecb_encrypt_padded(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out, int padding)
+{
+    return ecb_common(keybits, key, in, len, out, 1, padding);
 }
 
 int uaes_ecb_decrypt(int keybits, const uaes_u8 *key, const void *in, size_t len, void *out)
 {
-    const int rc = ecb_common(keybits, key, in, len, out, 0);
+    const int rc = ecb_common(keybits, key, in, len, out, 0, 0);
     if (rc) return rc;
     return len % 16 ? UAES_DECRYPTION_ERROR : UAES_OK;       /* micro_aes.c:679 */
 }
 
 /* ------------------------------------------------------------------ XTS */
 
-typedef struct { uaes_keysched k1, k1e, k2; int encrypt; u64 first_sector; size_t sector_bytes; } xts_job;
+typedef struct {
+    uaes_keysched k1, k1e, k2;
+    int encrypt;
+    u64 first_sector; size_t sector_bytes;          /* sector batches */
+    u8 tweak[16]; u64 first_block;                  /* one data unit, or a range of it */
+} xts_job;
 
 static int xts_keys(int keybits, const u8 *keys, int encrypt, xts_job *j)
 {
-    if (keybits != 128 && keybits != 256)
-        return fail(UAES_E_BAD_ARGUMENT, "XTS is defined for 128- and 256-bit keys only", 0);
-    expand_key(keybits, keys, &j->k1e);                       /* key1 = first half: data key   */
+    /* the reference runs XTS with whatever AES___ it was built for, 192 included (two 24-byte keys) */
+    if (expand_key(keybits, keys, &j->k1e))                   /* key1 = first half: data key   */
+        return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
     expand_key(keybits, keys + keybits / 8, &j->k2);          /* key2 = second half: tweak key */
     if (encrypt) j->k1 = j->k1e; else invert_schedule(&j->k1e, &j->k1);
     j->encrypt = encrypt;
     return 0;
 }
 
-static int xts_chunk(void *user, u64 offset, void *dev, size_t bytes, size_t obytes, void *stream)
+static int xts_chunk(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t obytes, void *stream)
 {
     xts_job *j = (xts_job *)user;
     int e;
-    (void)obytes;
+    (void)obytes; (void)index; (void)slot;
     e = uaes_launch_xts_sectors(&j->k1, &j->k2, j->encrypt, j->first_sector + offset / j->sector_bytes,
                                 j->sector_bytes / 16, bytes / j->sector_bytes, dev, dev, stream);
     return e ? fail(UAES_E_CUDA, "xts kernel launch", e) : 0;
@@ -426,61 +890,84 @@ int uaes_xts_sectors(int keybits, const uaes_u8 *keys, uaes_u64 first_sector, si
     xts_job j;
     int rc;
     if ((rc = xts_keys(keybits, keys, encrypt, &j)) != 0) return rc;
-    if (sector_bytes < 16 || sector_bytes % 16 || sector_bytes > CHUNK_BYTES || len % sector_bytes)
+    if (sector_bytes < 16 || sector_bytes % 16 || len % sector_bytes)
         return fail(UAES_E_BAD_ARGUMENT, "sector size must be a multiple of 16 and divide the length", 0);
     if (len == 0) return 0;
     j.first_sector = first_sector; j.sector_bytes = sector_bytes;
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
     if (is_direct(in) && is_direct(out)) {
         LAUNCH(uaes_launch_xts_sectors(&j.k1, &j.k2, encrypt, first_sector, sector_bytes / 16,
                                        len / sector_bytes, in, out, tls_stream));
         rc = finish_direct();
     } else {
-        rc = run_chunked(c, in, out, len, sector_bytes, 0, xts_chunk, &j);
+        pipe_part p;
+        if (sector_bytes > CHUNK_BYTES)
+            return fail(UAES_E_BAD_ARGUMENT, "staged sectors must fit one staging chunk; use uaes_xts_encrypt per unit", 0);
+        memset(&p, 0, sizeof p);
+        p.in = (const u8 *)in; p.out = (u8 *)out; p.len = len; p.unit = sector_bytes; p.fn = xts_chunk; p.user = &j;
+        CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+        rc = fan_out(&p, fan_width(len, in, out), sector_bytes);
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    if (g_burn) memset(&j, 0, sizeof j);
     return rc;
 }
 
-static int xts_unit(int keybits, const u8 *keys, const u8 *tweak, const void *in, size_t len, void *out,
-                    int encrypt)
+static int xts_unit_chunk(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t obytes, void *stream)
 {
-    static const u8 sector0[16] = {0};
+    xts_job *j = (xts_job *)user;
+    int e;
+    (void)obytes; (void)index; (void)slot;
+    e = uaes_launch_xts_unit(&j->k1, &j->k1e, &j->k2, j->encrypt, j->tweak, j->first_block + offset / 16,
+                             dev, dev, bytes, stream);
+    return e ? fail(UAES_E_CUDA, "xts kernel launch", e) : 0;
+}
+
+/* One data unit or a block range of it.  The tweak chain of the reference (micro_aes.c:1030-1036) is
+ * T_0 * alpha^k by jump-ahead, so a unit can be cut anywhere at a block boundary: staged in chunks,
+ * or spread over GPUs.  Only the range that ends the unit may be ragged (stealing). */
+static int xts_unit(int keybits, const u8 *keys, const u8 *tweak, u64 first_block, const void *in, size_t len,
+                    void *out, int encrypt)
+{
     devctx *c;
     xts_job j;
     int rc;
     if (len < 16) return UAES_DATALENGTH_ERROR;               /* micro_aes.c:1069, 1088 */
     if ((rc = xts_keys(keybits, keys, encrypt, &j)) != 0) return rc;
-    if (!tweak) tweak = sector0;                              /* micro_aes.c:1017-1021 */
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    memset(j.tweak, 0, 16);                                   /* NULL = sector 0, micro_aes.c:1017-1021 */
+    if (tweak) memcpy(j.tweak, tweak, 16);
+    j.first_block = first_block;
+    if ((rc = get_ctx(&c)) != 0) return rc;
     if (is_direct(in) && is_direct(out)) {
-        LAUNCH(uaes_launch_xts_unit(&j.k1, &j.k1e, &j.k2, encrypt, tweak, in, out, len, tls_stream));
+        LAUNCH(uaes_launch_xts_unit(&j.k1, &j.k1e, &j.k2, encrypt, j.tweak, first_block, in, out, len, tls_stream));
         rc = finish_direct();
     } else {
-        /* one data unit cannot be cut at chunk borders without the tweak chain: stage it whole */
-        if ((rc = grow(&c->big, &c->big_bytes, len + 16, "cudaMalloc(XTS unit staging)")) != 0) goto done;
+        pipe_part p;
+        memset(&p, 0, sizeof p);
+        p.in = (const u8 *)in; p.out = (u8 *)out; p.len = len; p.unit = 16; p.fn = xts_unit_chunk; p.user = &j;
+        p.absorb_tail = 32;                       /* a last piece of < 32 bytes joins the chunk before it */
         CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
-        CU(cudaMemcpyAsync(c->big, in, len, cudaMemcpyDefault, c->st[0]));
-        LAUNCH(uaes_launch_xts_unit(&j.k1, &j.k1e, &j.k2, encrypt, tweak, c->big, c->big, len, c->st[0]));
-        CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, c->st[0]));
-        CU(cudaStreamSynchronize(c->st[0]));
+        rc = fan_out(&p, fan_width(len, in, out), 16384);
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    if (g_burn) memset(&j, 0, sizeof j);
     return rc;
 }
 
 int uaes_xts_encrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, const void *in, size_t len, void *out)
 {
-    return xts_unit(keybits, keys, tweak, in, len, out, 1);
+    return xts_unit(keybits, keys, tweak, 0, in, len, out, 1);
 }
 
 int uaes_xts_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, const void *in, size_t len, void *out)
 {
-    return xts_unit(keybits, keys, tweak, in, len, out, 0);
+    return xts_unit(keybits, keys, tweak, 0, in, len, out, 0);
+}
+
+int uaes_xts_crypt_range(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, uaes_u64 first_block,
+                         const void *in, size_t len, void *out, int encrypt)
+{
+    return xts_unit(keybits, keys, tweak, first_block, in, len, out, encrypt);
 }
 
 /* ------------------------------------------------------------------ GCM */
@@ -489,36 +976,241 @@ int uaes_xts_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *tweak, con
 #define AAD_STATE_OFF 128    /* 16 bytes inside the head: GHASH state of a bulk-hashed AAD */
 #define AAD_BULK_MIN  4096   /* larger AADs are hashed by the bulk kernel instead of one lane */
 
-/* common part: returns with data resident on the device (din/dout), AAD on the device, work ready */
-static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
-                      const void *in, size_t len, void *out, int decrypt)
+/* J0 (micro_aes.c:1140-1152): nonce || 00000001 for the recommended 12-byte nonce; any other length
+ * is GHASH_H({}, nonce), computed on the device and read back (16 bytes) because the launch
+ * arguments of the bulk kernel are derived from it */
+static int gcm_j0(devctx *c, const uaes_keysched *ks, const u8 *nonce, size_t noncelen, u8 j0[16])
+{
+    int rc = 0;
+    scratch *w = NULL;
+    cudaStream_t st = (cudaStream_t)tls_stream;
+    if (noncelen == 12) {
+        memcpy(j0, nonce, 12);
+        j0[12] = j0[13] = j0[14] = 0; j0[15] = 1;
+        return 0;
+    }
+    if (noncelen == 0) return fail(UAES_E_BAD_ARGUMENT, "GCM nonce must not be empty", 0);
+    if ((rc = scratch_get(c, noncelen + 64, st, &w)) != 0) return rc;
+    CU(cudaMemcpyAsync((u8 *)w->p + 32, nonce, noncelen, cudaMemcpyDefault, st));
+    LAUNCH(uaes_launch_gcm_j0(ks, (u8 *)w->p + 32, noncelen, w->p, st));
+    CU(cudaMemcpyAsync(j0, w->p, 16, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+done:
+    scratch_put(c, w, st);
+    return rc;
+}
+
+/* ---- staged GCM: the message goes through the chunk pipeline as a sequence of shards ------------
+ * Every chunk is one fused CTR+GHASH pass that leaves its 16-byte contribution on the device; the
+ * contributions of all chunks (of all devices) are folded with powers of H into the tag at the end
+ * (gcm_combine_kernel).  H2D, kernel and D2H of neighbouring chunks overlap exactly as for CTR.
+ * Decryption must not hand out plaintext before the tag is checked (micro_aes.c:1204-1208): its
+ * chunks decrypt into a device-resident copy of the part, and only a matching tag starts the copy
+ * back to the caller. */
+typedef struct {
+    uaes_keysched ks;
+    u8 j0[16];
+    int mode;                    /* 0 encrypt; 2 decrypt (CTR + GHASH of the input) */
+    u64 total_len;
+    size_t chunk;                /* pipeline chunk of this call */
+    scratch *w;                  /* NSLOT work areas + the part's contribution array (device) */
+    size_t work_stride, nchunks;
+    u8 *host_parts;              /* where this part's contributions go on the host (16 B per chunk) */
+    u64 *host_after;             /* ... and the number of GHASH blocks after each chunk */
+    u8 *keep;                    /* decrypt: the part's plaintext on the device until the tag is checked */
+} gcm_part;
+
+static int gcm_part_before(devctx *c, void *user, const pipe_part *p)
+{
+    gcm_part *g = (gcm_part *)user;
+    g->nchunks = pipe_nchunks(p);
+    g->work_stride = (uaes_gcm_work_bytes(g->chunk) + 255) & ~(size_t)255;
+    return scratch_get(c, (size_t)NSLOT * g->work_stride + g->nchunks * 16 + 64, c->st[0], &g->w);
+}
+
+static int gcm_part_chunk(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t obytes, void *stream)
+{
+    gcm_part *g = (gcm_part *)user;
+    u8 *work = (u8 *)g->w->p + (size_t)slot * g->work_stride;
+    u8 *dpart = (u8 *)g->w->p + (size_t)NSLOT * g->work_stride + index * 16;
+    int e;
+    (void)obytes;
+    e = uaes_launch_gcm(&g->ks, g->j0, NULL, 0, NULL, dev, dev, bytes, g->mode, offset / 16, 1, dpart, 16, work, stream);
+    if (e) return fail(UAES_E_CUDA, "gcm kernel launch", e);
+    g->host_after[index] = (g->total_len + 15) / 16 - (offset + bytes + 15) / 16;
+    return 0;
+}
+
+static int gcm_part_after(devctx *c, void *user, const pipe_part *p)
+{
+    gcm_part *g = (gcm_part *)user;
+    int rc = 0;
+    (void)p;
+    /* the pipeline is drained: the contributions are complete */
+    if (g->nchunks &&
+        cudaMemcpy(g->host_parts, (u8 *)g->w->p + (size_t)NSLOT * g->work_stride, g->nchunks * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(UAES_E_CUDA, "cudaMemcpy(GHASH contributions)", (int)cudaGetLastError());
+    scratch_put(c, g->w, c->st[0]);
+    g->w = NULL;
+    return rc;
+}
+
+static int gcm_keep_free(devctx *c, void *user, const pipe_part *p)
+{
+    gcm_part *g = (gcm_part *)user;
+    (void)c;
+    if (g->keep) {
+        if (g_burn) cudaMemset(g->keep, 0, p->len);
+        cudaFree(g->keep);
+        g->keep = NULL;
+    }
+    return 0;
+}
+
+/* folds contributions (n x 16 B and n x u64, host or device memory) + AAD + lengths into the tag
+ * (taglen bytes written to `tag`, host or device memory) on the current device */
+static int gcm_fold_tag(devctx *c, const uaes_keysched *ks, const u8 j0[16], const void *aad, size_t aadlen,
+                        const void *parts, const void *after, size_t n, u64 total_len, u8 *tag, size_t taglen)
+{
+    int rc = 0, bulk_aad = aadlen >= AAD_BULK_MIN;
+    scratch *w = NULL;
+    u8 *base, *dparts, *dafter, *daad;
+    cudaStream_t st = (cudaStream_t)tls_stream;
+    const size_t aoff = (GCM_WORK_HEAD + (n + 1) * 24 + 255) & ~(size_t)255;
+    const size_t woff = aoff + ((aadlen + 255) & ~(size_t)255);
+
+    if ((rc = scratch_get(c, woff + 64 + (bulk_aad ? uaes_gcm_work_bytes(aadlen) + 256 : 0), st, &w)) != 0) return rc;
+    base = (u8 *)w->p;                   /* [tag 16][pad][parts (n+1) x 16][after (n+1) x 8][aad][aad work] */
+    dparts = base + GCM_WORK_HEAD; dafter = dparts + (n + 1) * 16; daad = base + aoff;
+    if (n) {
+        CU(cudaMemcpyAsync(dparts, parts, n * 16, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(dafter, after, n * 8, cudaMemcpyDefault, st));
+    }
+    if (aadlen) CU(cudaMemcpyAsync(daad, aad, aadlen, cudaMemcpyDefault, st));
+    if (bulk_aad) {
+        /* a large AAD is one more shard: hashed by the bulk kernel, it ends total_blocks before the end */
+        const u64 tb = (total_len + 15) / 16;
+        LAUNCH(uaes_launch_gcm(ks, j0, NULL, 0, NULL, daad, NULL, aadlen, 1, 0, 1, dparts + n * 16, 16, base + woff, st));
+        CU(cudaMemcpyAsync(dafter + n * 8, &tb, 8, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));                          /* tb lives on this stack frame */
+    }
+    LAUNCH(uaes_launch_gcm_combine(ks, j0, bulk_aad || !aadlen ? NULL : daad, aadlen, total_len, dparts, dafter,
+                                   (unsigned)(n + (bulk_aad ? 1 : 0)), base, 16, st));
+    CU(cudaMemcpyAsync(tag, base, taglen, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+done:
+    scratch_put(c, w, st);
+    return rc;
+}
+
+static int gcm_staged(devctx *c, const uaes_keysched *ks, const u8 j0[16], const void *aad, size_t aadlen,
+                      const void *in, size_t len, void *out, size_t taglen, int decrypt)
+{
+    fan_part f[MAX_DEV];
+    gcm_part g[MAX_DEV];
+    pipe_part whole;
+    int rc = 0, n, i;
+    size_t total_chunks = 0, k = 0;
+    u8 *parts = NULL, tag[16], rtag[16];
+    u64 *after = NULL;
+
+    memset(&whole, 0, sizeof whole);
+    whole.in = (const u8 *)in; whole.out = decrypt ? NULL : (u8 *)out; whole.len = len; whole.unit = 16;
+    whole.fn = gcm_part_chunk;
+    n = fan_plan(&whole, fan_width(len, in, out), 16384, f);
+    for (i = 0; i < n; ++i) total_chunks += pipe_nchunks(&f[i].part);
+    parts = (u8 *)malloc(total_chunks * 16 + 16);
+    after = (u64 *)malloc(total_chunks * 8 + 8);
+    if (!parts || !after) { rc = fail(UAES_E_NO_MEMORY, "malloc(GHASH contributions)", 0); goto done; }
+    memset(g, 0, sizeof g);
+    for (i = 0; i < n; ++i) {
+        g[i].ks = *ks; memcpy(g[i].j0, j0, 16);
+        g[i].mode = decrypt ? 2 : 0; g[i].total_len = len; g[i].chunk = pipe_chunk_bytes(&whole);
+        g[i].host_parts = parts + 16 * k; g[i].host_after = after + k;
+        k += pipe_nchunks(&f[i].part);
+        f[i].part.user = &g[i];
+        f[i].before = gcm_part_before; f[i].after = gcm_part_after;
+        if (decrypt && f[i].part.len) {
+            /* the call owns this copy (not the shared staging buffer: the device lock is released
+             * between the two phases) */
+            cudaError_t e = cudaSetDevice(f[i].dev);
+            if (e == cudaSuccess) e = cudaMalloc((void **)&g[i].keep, f[i].part.len + 32);
+            if (e != cudaSuccess) { rc = fail(UAES_E_NO_MEMORY, "cudaMalloc(GCM decrypt copy)", (int)e); break; }
+            f[i].part.resident = g[i].keep;
+        }
+    }
+    if (decrypt) cudaSetDevice(f[0].dev);
+    if (rc) goto cleanup;
+    CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+    if ((rc = fan_exec(f, n)) != 0) goto cleanup;
+    if ((rc = gcm_fold_tag(c, ks, j0, aad, aadlen, parts, after, total_chunks, len, tag, 16)) != 0) goto cleanup;
+    if (!decrypt) {
+        /* tag appended at out + len (micro_aes.c:1168, 1178) */
+        if (cudaMemcpy((u8 *)out + len, tag, taglen, cudaMemcpyDefault) != cudaSuccess)
+            rc = fail(UAES_E_CUDA, "cudaMemcpy(tag)", (int)cudaGetLastError());
+        goto cleanup;
+    }
+    if (cudaMemcpy(rtag, (const u8 *)in + len, taglen, cudaMemcpyDefault) != cudaSuccess) {
+        rc = fail(UAES_E_CUDA, "cudaMemcpy(received tag)", (int)cudaGetLastError());
+        goto cleanup;
+    }
+    if (memcmp(tag, rtag, taglen)) { rc = UAES_AUTH_ERROR; goto cleanup; }   /* out untouched, micro_aes.c:1204-1208 */
+    /* phase 2: the verified plaintext leaves the devices */
+    for (i = 0; i < n; ++i) {
+        f[i].part.in = g[i].keep; f[i].part.out = (u8 *)out + (f[i].part.base - whole.base);
+        f[i].part.resident = NULL; f[i].part.fn = NULL;
+        f[i].before = NULL; f[i].after = gcm_keep_free;
+    }
+    rc = fan_exec(f, n);
+cleanup:
+    for (i = 0; i < n; ++i)
+        if (g[i].keep) { if (g_burn) cudaMemset(g[i].keep, 0, f[i].part.len); cudaFree(g[i].keep); g[i].keep = NULL; }
+done:
+    free(parts); free(after);
+    if (g_burn) memset(g, 0, sizeof g);
+    return rc;
+}
+
+/* The whole message on one device: device-resident buffers (zero copies), or a host message of at
+ * most one staging chunk. */
+static int gcm_common(int keybits, const u8 *key, const u8 *nonce, size_t noncelen, const void *aad, size_t aadlen,
+                      const void *in, size_t len, void *out, size_t taglen, int decrypt)
 {
     devctx *c;
     uaes_keysched ks;
-    int rc, direct;
+    int rc, direct, locked = 0;
     const void *din, *daad;
     void *dout;
-    u8 *work, *dtag, *dstate;
+    u8 *work, *dtag, *dstate, j0[16];
     size_t wbytes;
-    cudaStream_t st;
+    scratch *w = NULL;
+    cudaStream_t st = NULL;
 
     if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if (taglen < 1 || taglen > 16) return fail(UAES_E_BAD_ARGUMENT, "GCM tag length must be 1..16 bytes", 0);
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    if ((rc = gcm_j0(c, &ks, nonce, noncelen, j0)) != 0) return rc;
 
     /* the kernels write ciphertext and tag through `out` and read `in`: both must be device memory
      * for the zero-copy path (an empty message still has a tag to write when encrypting) */
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
     else         direct = is_direct(out) && (len == 0 || is_direct(in));
+    if (!direct && len > CHUNK_BYTES) {
+        rc = gcm_staged(c, &ks, j0, aad, aadlen, in, len, out, taglen, decrypt);
+        goto wipe;
+    }
+    if (!direct) { pthread_mutex_lock(&c->lock); locked = 1; }     /* the staged path owns big and st[0] */
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
     wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len > aadlen ? len : aadlen) + aadlen + 64;
-    if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM work)")) != 0) goto done;
-    dtag = (u8 *)c->work;
-    work = (u8 *)c->work + GCM_WORK_HEAD;
+    if ((rc = scratch_get(c, wbytes, st, &w)) != 0) goto done;
+    dtag = (u8 *)w->p;
+    work = (u8 *)w->p + GCM_WORK_HEAD;
     daad = NULL;
     if (aadlen) {
         u8 *a = work + uaes_gcm_work_bytes(len > aadlen ? len : aadlen);
         a += (16 - ((size_t)a & 15)) & 15;
+        /* a staged call's AAD copy runs on st[0]: order it after the caller's stream first */
+        if (!direct) CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
         CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
         daad = a;
     }
@@ -527,75 +1219,96 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, const void *a
     } else {
         if ((rc = grow(&c->big, &c->big_bytes, len + 32, "cudaMalloc(GCM staging)")) != 0) goto done;
         CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
-        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? taglen : 0), cudaMemcpyDefault, st));
         din = c->big; dout = c->big;
     }
     dstate = NULL;
     if (aadlen >= AAD_BULK_MIN) {                             /* xMac over the AAD (micro_aes.c:1134) in bulk */
-        dstate = (u8 *)c->work + AAD_STATE_OFF;
-        LAUNCH(uaes_launch_gcm(&ks, nonce, NULL, 0, NULL, daad, NULL, aadlen, 1, 0, 1, dstate, work, st));
+        dstate = (u8 *)w->p + AAD_STATE_OFF;
+        LAUNCH(uaes_launch_gcm(&ks, j0, NULL, 0, NULL, daad, NULL, aadlen, 1, 0, 1, dstate, 16, work, st));
     }
 
     if (!decrypt) {
         /* one fused pass: CTR + GHASH, tag appended at out + len (micro_aes.c:1168,1178) */
-        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, dstate, din, dout, len, 0, 0, 0, (u8 *)dout + len, work, st));
-        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
+        LAUNCH(uaes_launch_gcm(&ks, j0, daad, aadlen, dstate, din, dout, len, 0, 0, 0, (u8 *)dout + len, (unsigned)taglen, work, st));
+        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + taglen, cudaMemcpyDefault, st));
         if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
     } else {
         /* verify first, decrypt only on success; `out` stays untouched otherwise (micro_aes.c:1199-1209) */
         u8 t1[16], t2[16];
         uaes_ctrblock cb;
-        LAUNCH(uaes_launch_gcm(&ks, nonce, daad, aadlen, dstate, din, NULL, len, 1, 0, 0, dtag, work, st));
+        LAUNCH(uaes_launch_gcm(&ks, j0, daad, aadlen, dstate, din, NULL, len, 1, 0, 0, dtag, 16, work, st));
         CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
-        CU(cudaMemcpyAsync(t2, (const u8 *)din + len, 16, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(t2, (const u8 *)din + len, taglen, cudaMemcpyDefault, st));
         CU(cudaStreamSynchronize(st));
-        if (memcmp(t1, t2, 16)) { rc = UAES_AUTH_ERROR; goto done; }
+        if (memcmp(t1, t2, taglen)) { rc = UAES_AUTH_ERROR; goto done; }
         if (len) {
-            make_ctrblock(nonce, 1, 1, &cb);                  /* J0 = nonce || 1, data from J0 + 1 */
+            block_to_ctrblock(j0, 1, &cb);                    /* data from J0 + 1 (micro_aes.c:939-941) */
             LAUNCH(uaes_launch_ctr(&ks, &cb, din, dout, len, st));
             if (!direct) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
             if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
         }
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, w, st);
+    if (locked) { big_done(c); pthread_mutex_unlock(&c->lock); }
+wipe:
+    if (g_burn) { memset(&ks, 0, sizeof ks); memset(j0, 0, sizeof j0); }
     return rc;
 }
 
 int uaes_gcm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return gcm_common(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+    return gcm_common(keybits, key, nonce, 12, aad, aadlen, in, len, out, 16, 0);
 }
 
 int uaes_gcm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return gcm_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+    return gcm_common(keybits, key, nonce, 12, aad, aadlen, in, len, out, 16, 1);
+}
+
+/* the reference's compile-time GCM_NONCE_LEN / GCM_TAG_LEN (micro_aes.h:107-110) as run-time arguments */
+int uaes_gcm_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, size_t noncelen,
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
+{
+    return gcm_common(keybits, key, nonce, noncelen, aad, aadlen, in, len, out, taglen, 0);
+}
+
+int uaes_gcm_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, size_t noncelen,
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
+{
+    return gcm_common(keybits, key, nonce, noncelen, aad, aadlen, in, len, out, taglen, 1);
 }
 
 /* ---- a GCM message sharded over several GPUs / calls ---------------------------
  * Every shard runs the fused CTR+GHASH pass over its own byte range and returns 16 bytes; one
- * caller gathers them (an all-gather of 16 B per rank) and folds them into the tag. */
+ * caller gathers them (an all-gather of 16 B per rank) and folds them into the tag.  `partial` may
+ * be DEVICE memory: the contribution then stays on the GPU (ready for a device-to-device gather)
+ * and, in asynchronous mode, the call only enqueues work. */
 int uaes_gcm_shard(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, uaes_u64 first_block,
                    const void *in, size_t len, void *out, int decrypt, uaes_u8 *partial)
 {
     devctx *c;
     uaes_keysched ks;
-    int rc, direct;
+    int rc, direct, locked = 0, part_dev;
     const void *din;
     void *dout;
-    u8 *work, *dpart;
-    cudaStream_t st;
+    u8 *work, *dpart, j0[16];
+    scratch *w = NULL;
+    cudaStream_t st = NULL;
 
     if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    memcpy(j0, nonce, 12); j0[12] = j0[13] = j0[14] = 0; j0[15] = 1;
     direct = len == 0 || (is_direct(in) && is_direct(out));
+    part_dev = ptr_class(partial) == PTR_DEVICE || ptr_class(partial) == PTR_OTHER;
+    if (!direct) { pthread_mutex_lock(&c->lock); locked = 1; }
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
-    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + 64, "cudaMalloc(GCM work)")) != 0) goto done;
-    dpart = (u8 *)c->work;
-    work = (u8 *)c->work + GCM_WORK_HEAD;
+    if ((rc = scratch_get(c, GCM_WORK_HEAD + uaes_gcm_work_bytes(len) + 64, st, &w)) != 0) goto done;
+    dpart = part_dev ? partial : (u8 *)w->p;
+    work = (u8 *)w->p + GCM_WORK_HEAD;
     if (direct) {
         din = in; dout = out;
     } else {
@@ -604,15 +1317,18 @@ int uaes_gcm_shard(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, uaes_u
         CU(cudaMemcpyAsync(c->big, in, len, cudaMemcpyDefault, st));
         din = c->big; dout = c->big;
     }
-    LAUNCH(uaes_launch_gcm(&ks, nonce, NULL, 0, NULL, din, dout, len, decrypt ? 2 : 0, first_block, 1, dpart, work, st));
+    LAUNCH(uaes_launch_gcm(&ks, j0, NULL, 0, NULL, din, dout, len, decrypt ? 2 : 0, first_block, 1, dpart, 16, work, st));
     if (!direct) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
-    CU(cudaMemcpyAsync(partial, dpart, 16, cudaMemcpyDefault, st));
-    CU(cudaStreamSynchronize(st));                            /* the 16 bytes are a host result */
+    if (!part_dev) CU(cudaMemcpyAsync(partial, dpart, 16, cudaMemcpyDefault, st));
+    if (!part_dev || !direct || !tls_async) CU(cudaStreamSynchronize(st));     /* host results are complete on return */
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, w, st);
+    if (locked) { big_done(c); pthread_mutex_unlock(&c->lock); }
+    if (g_burn) memset(&ks, 0, sizeof ks);
     return rc;
 }
 
+/* partials (nshards x 16 B), blocks_after (nshards x u64) and tag may each be host or device memory */
 int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const uaes_u8 *partials, const uaes_u64 *blocks_after, int nshards,
                      uaes_u64 total_len, uaes_u8 *tag)
@@ -620,26 +1336,13 @@ int uaes_gcm_combine(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
     devctx *c;
     uaes_keysched ks;
     int rc;
-    u8 *w;
-    cudaStream_t st = (cudaStream_t)tls_stream;
-
+    u8 j0[16];
     if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
-    if (nshards < 0 || nshards > 31) return fail(UAES_E_BAD_ARGUMENT, "at most 31 shards", 0);
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
-    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + 32 * 24 + aadlen + 64, "cudaMalloc(GCM work)")) != 0) goto done;
-    w = (u8 *)c->work;                                        /* [tag 16][pad][partials][after][aad] */
-    if (nshards) {
-        CU(cudaMemcpyAsync(w + 64, partials, (size_t)nshards * 16, cudaMemcpyDefault, st));
-        CU(cudaMemcpyAsync(w + 64 + 32 * 16, blocks_after, (size_t)nshards * 8, cudaMemcpyDefault, st));
-    }
-    if (aadlen) CU(cudaMemcpyAsync(w + GCM_WORK_HEAD, aad, aadlen, cudaMemcpyDefault, st));
-    LAUNCH(uaes_launch_gcm_combine(&ks, nonce, aadlen ? w + GCM_WORK_HEAD : NULL, aadlen, total_len,
-                                   w + 64, w + 64 + 32 * 16, (unsigned)nshards, w, st));
-    CU(cudaMemcpyAsync(tag, w, 16, cudaMemcpyDefault, st));
-    CU(cudaStreamSynchronize(st));
-done:
-    pthread_mutex_unlock(&g_lock);
+    if (nshards < 0) return fail(UAES_E_BAD_ARGUMENT, "negative shard count", 0);
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    memcpy(j0, nonce, 12); j0[12] = j0[13] = j0[14] = 0; j0[15] = 1;
+    rc = gcm_fold_tag(c, &ks, j0, aad, aadlen, partials, blocks_after, (size_t)nshards, total_len, tag, 16);
+    if (g_burn) memset(&ks, 0, sizeof ks);
     return rc;
 }
 
@@ -653,25 +1356,26 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
 {
     devctx *c;
     uaes_keysched master, enc;
-    int rc, direct;
+    int rc, direct, locked = 0;
     const void *din, *daad;
     void *dout;
     u8 *work, *dtag, *dderived, *dstate, derived[48];
     size_t wbytes;
+    scratch *w = NULL;
     cudaStream_t st;
 
     if (expand_key(keybits, key, &master)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
 
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
     else         direct = is_direct(out) && (len == 0 || is_direct(in));
+    if (!direct) { pthread_mutex_lock(&c->lock); locked = 1; }     /* the staged path owns big and st[0] */
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
     wbytes = GCM_WORK_HEAD + uaes_gcm_work_bytes(len > aadlen ? len : aadlen) + aadlen + 64;
-    if ((rc = grow(&c->work, &c->work_bytes, wbytes, "cudaMalloc(GCM-SIV work)")) != 0) goto done;
-    dtag = (u8 *)c->work;                 /* [0,16) computed tag, [64,112) derived key material */
-    dderived = (u8 *)c->work + 64;
-    work = (u8 *)c->work + GCM_WORK_HEAD;
+    if ((rc = scratch_get(c, wbytes, st, &w)) != 0) goto done;
+    dtag = (u8 *)w->p;                    /* [0,16) computed tag, [64,112) derived key material */
+    dderived = (u8 *)w->p + 64;
+    work = (u8 *)w->p + GCM_WORK_HEAD;
 
     /* message keys: E_K(LE32(i) || nonce) on the device, KeyExpansion of the result on the host */
     LAUNCH(uaes_launch_gcmsiv_derive(&master, nonce, dderived, st));
@@ -683,6 +1387,7 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
     if (aadlen) {
         u8 *a = work + uaes_gcm_work_bytes(len > aadlen ? len : aadlen);
         a += (16 - ((size_t)a & 15)) & 15;
+        if (!direct) CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
         CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
         daad = a;
     }
@@ -696,7 +1401,7 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
     }
     dstate = NULL;
     if (aadlen >= AAD_BULK_MIN) {                             /* POLYVAL state of a large AAD, in bulk */
-        dstate = (u8 *)c->work + AAD_STATE_OFF;
+        dstate = (u8 *)w->p + AAD_STATE_OFF;
         LAUNCH(uaes_launch_gcmsiv_tag(&enc, derived, nonce, NULL, 0, NULL, daad, aadlen, 1, dstate, work, st));
     }
 
@@ -722,7 +1427,9 @@ static int gcmsiv_common(int keybits, const u8 *key, const u8 *nonce, const void
         if (memcmp(t1, t2, 16)) rc = UAES_AUTH_ERROR;         /* micro_aes.c:1510-1514 */
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, w, st);
+    if (locked) { big_done(c); pthread_mutex_unlock(&c->lock); }
+    if (g_burn) { memset(&master, 0, sizeof master); memset(&enc, 0, sizeof enc); memset(derived, 0, sizeof derived); }
     return rc;
 }
 
@@ -742,31 +1449,35 @@ int uaes_gcmsiv_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, c
 
 /* Both directions read two input blocks per output block, so in and out must be different
  * buffers on the device: the staged path uses the two halves of the full-size staging area. */
-static int chain_common(int keybits, const u8 *key, const u8 *iv, const void *in, size_t len, void *out, int cbc)
+static int chain_common(int keybits, const u8 *key, const u8 *iv, const void *in, size_t len, void *out, int cbc, int cts)
 {
     devctx *c;
     uaes_keysched enc, dec;
-    int rc;
+    int rc, locked = 0;
     size_t n = len / 16, r = len % 16;
     cudaStream_t st;
 
     if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
-    if (cbc) {                                                /* CS3 rules of micro_aes.c:751-760 */
+    if (cbc && cts) {                                         /* CS3 rules of micro_aes.c:751-760 */
         if (n > 1 && !r) { --n; r = 16; }
         if (n == 0) return UAES_DATALENGTH_ERROR;
         n -= r > 0;
         invert_schedule(&enc, &dec);
+    } else if (cbc) {                                         /* built with CTS = 0: whole blocks only, micro_aes.c:757-759 */
+        if (r) return UAES_DATALENGTH_ERROR;
+        if (n == 0) return 0;
+        invert_schedule(&enc, &dec);
     } else if (len == 0) {
         return 0;
     }
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
     if (is_direct(in) && is_direct(out) && in != out) {
         LAUNCH(uaes_launch_chain_dec(cbc ? &dec : &enc, &enc, cbc, iv, in, out, n, (unsigned)r, tls_stream));
         rc = finish_direct();
     } else {
         const size_t half = (len + 255) & ~(size_t)255;
         u8 *din, *dout;
+        pthread_mutex_lock(&c->lock); locked = 1;
         if ((rc = grow(&c->big, &c->big_bytes, 2 * half + 32, "cudaMalloc(CBC/CFB staging)")) != 0) goto done;
         din = (u8 *)c->big; dout = din + half;
         st = c->st[0];
@@ -777,18 +1488,26 @@ static int chain_common(int keybits, const u8 *key, const u8 *iv, const void *in
         CU(cudaStreamSynchronize(st));
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    if (locked) { big_done(c); pthread_mutex_unlock(&c->lock); }
+    if (g_burn) { memset(&enc, 0, sizeof enc); memset(&dec, 0, sizeof dec); }
     return rc;
 }
 
 int uaes_cbc_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out)
 {
-    return chain_common(keybits, key, iv, in, len, out, 1);
+    return chain_common(keybits, key, iv, in, len, out, 1, 1);
+}
+
+/* cts = 0: the reference built with CTS = 0 -- plain CBC, UAES_DATALENGTH_ERROR unless len % 16 == 0
+ * (micro_aes.c:757-759) */
+int uaes_cbc_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out, int cts)
+{
+    return chain_common(keybits, key, iv, in, len, out, 1, cts);
 }
 
 int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const void *in, size_t len, void *out)
 {
-    return chain_common(keybits, key, iv, in, len, out, 0);
+    return chain_common(keybits, key, iv, in, len, out, 0, 0);
 }
 
 /* ------------------------------------------------------------------ OCB */
@@ -800,26 +1519,27 @@ static int ocb_common(int keybits, const u8 *key, const u8 *nonce, const void *a
 {
     devctx *c;
     uaes_keysched enc, dec;
-    int rc, direct;
+    int rc, direct, locked = 0;
     const void *din, *daad;
     void *dout;
     u8 *work, *dtag;
+    scratch *w = NULL;
     cudaStream_t st;
 
     if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
     if (decrypt) invert_schedule(&enc, &dec);
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
     else         direct = is_direct(out) && (len == 0 || is_direct(in));
+    if (!direct) { pthread_mutex_lock(&c->lock); locked = 1; }
     st = direct ? (cudaStream_t)tls_stream : c->st[0];
-    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + uaes_ocb_work_bytes() + aadlen + 64,
-                   "cudaMalloc(OCB work)")) != 0) goto done;
-    dtag = (u8 *)c->work;
-    work = (u8 *)c->work + GCM_WORK_HEAD;
+    if ((rc = scratch_get(c, GCM_WORK_HEAD + uaes_ocb_work_bytes() + aadlen + 64, st, &w)) != 0) goto done;
+    dtag = (u8 *)w->p;
+    work = (u8 *)w->p + GCM_WORK_HEAD;
     daad = NULL;
     if (aadlen) {
         u8 *a = work + ((uaes_ocb_work_bytes() + 15) & ~(size_t)15);
+        if (!direct) CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
         CU(cudaMemcpyAsync(a, aad, aadlen, cudaMemcpyDefault, st));
         daad = a;
     }
@@ -845,7 +1565,9 @@ static int ocb_common(int keybits, const u8 *key, const u8 *nonce, const void *a
         if (memcmp(t1, t2, 16)) rc = UAES_AUTH_ERROR;
     }
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, w, st);
+    if (locked) { big_done(c); pthread_mutex_unlock(&c->lock); }
+    if (g_burn) { memset(&enc, 0, sizeof enc); memset(&dec, 0, sizeof dec); }
     return rc;
 }
 
@@ -882,19 +1604,19 @@ static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_
 {
     devctx *c;
     uaes_keysched ks, ks2;
-    int rc = 0, msgs_dev;
+    int rc = 0, msgs_dev, locked = 0;
     size_t i, in_ext = 0, out_ext = 0, aad_ext = 0, off;
     const void *din, *daad;
     void *dout, *dmsgs;
-    cudaStream_t st;
+    scratch *w = NULL;
+    cudaStream_t st = NULL;
     struct cudaPointerAttributes at;
 
     if (expand_key(keybits, key, &ks)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
     ks2 = ks;
     if (mode == BATCH_SIV) expand_key(keybits, key + keybits / 8, &ks2);     /* keys = K1 || K2, micro_aes.c:1378 */
     if (n == 0) return 0;
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
     msgs_dev = cudaPointerGetAttributes(&at, msgs) == cudaSuccess && at.type == cudaMemoryTypeDevice;
     cudaGetLastError();
     if (msgs_dev) {
@@ -913,17 +1635,18 @@ static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_
         if (msgs[i].out_off + msgs[i].len + tag_out > out_ext) out_ext = msgs[i].out_off + msgs[i].len + tag_out;
         if (msgs[i].aad_len && msgs[i].aad_off + msgs[i].aad_len > aad_ext) aad_ext = msgs[i].aad_off + msgs[i].aad_len;
     }
+    pthread_mutex_lock(&c->lock); locked = 1;                 /* the staged path owns big and st[0] */
     st = c->st[0];
     CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
     /* work area: descriptors, then (if host) the associated data; big: input and output ranges */
     off = (n * sizeof(uaes_msg) + 255) & ~(size_t)255;
-    if ((rc = grow(&c->work, &c->work_bytes, off + aad_ext + 64, "cudaMalloc(batch descriptors)")) != 0) goto done;
-    dmsgs = c->work;
+    if ((rc = scratch_get(c, off + aad_ext + 64, st, &w)) != 0) goto done;
+    dmsgs = w->p;
     CU(cudaMemcpyAsync(dmsgs, msgs, n * sizeof(uaes_msg), cudaMemcpyDefault, st));
     daad = aad;
     if (aad_ext && !is_direct(aad)) {
-        CU(cudaMemcpyAsync((u8 *)c->work + off, aad, aad_ext, cudaMemcpyDefault, st));
-        daad = (u8 *)c->work + off;
+        CU(cudaMemcpyAsync((u8 *)w->p + off, aad, aad_ext, cudaMemcpyDefault, st));
+        daad = (u8 *)w->p + off;
     }
     din = in; dout = out;
     if (!is_direct(in) || !is_direct(out)) {
@@ -940,7 +1663,9 @@ static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_
     CU(cudaStreamSynchronize(st));
     for (i = 0; i < n; ++i) if (msgs[i].result) rc = UAES_AUTH_ERROR;
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, w, st);
+    if (locked) { big_done(c); pthread_mutex_unlock(&c->lock); }
+    if (g_burn) { memset(&ks, 0, sizeof ks); memset(&ks2, 0, sizeof ks2); }
     return rc;
 }
 
@@ -1098,15 +1823,15 @@ static int stream_fold(uaes_stream *s)
     int rc = 0, i;
     u64 after[STREAM_MAX_PENDING + 1];
     u8 *w;
+    scratch *sc = NULL;
     cudaStream_t st = (cudaStream_t)tls_stream;
     const u64 end = s->end_block[s->npending - 1];
 
     expand_key(s->keybits, s->key, &ks);
     for (i = 0; i < s->npending; ++i) after[i] = end - s->end_block[i];
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
-    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD + 32 * 24 + 64, "cudaMalloc(GCM work)")) != 0) goto done;
-    w = (u8 *)c->work;
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    if ((rc = scratch_get(c, GCM_WORK_HEAD + 32 * 24 + 64, st, &sc)) != 0) return rc;
+    w = (u8 *)sc->p;
     CU(cudaMemcpyAsync(w + 64, s->partial, (size_t)s->npending * 16, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(w + 64 + 32 * 16, after, (size_t)s->npending * 8, cudaMemcpyDefault, st));
     LAUNCH(uaes_launch_gcm_fold(&ks, w + 64, w + 64 + 32 * 16, (unsigned)s->npending, w, st));
@@ -1115,7 +1840,8 @@ static int stream_fold(uaes_stream *s)
     s->end_block[0] = end;
     s->npending = 1;
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, sc, st);
+    if (g_burn) memset(&ks, 0, sizeof ks);
     return rc;
 }
 
@@ -1164,12 +1890,10 @@ int uaes_fill_splitmix64(uaes_u64 seed, uaes_u64 first_word, void *dst, size_t n
 {
     devctx *c;
     int rc;
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
+    if ((rc = get_ctx(&c)) != 0) return rc;
     LAUNCH(uaes_launch_fill(seed, first_word, dst, nwords, tls_stream));
     rc = finish_direct();
 done:
-    pthread_mutex_unlock(&g_lock);
     return rc;
 }
 
@@ -1177,13 +1901,114 @@ int uaes_xor_fold64(const void *src, size_t nwords, uaes_u64 *result)
 {
     devctx *c;
     int rc;
-    pthread_mutex_lock(&g_lock);
-    if ((rc = get_ctx(&c)) != 0) goto done;
-    if ((rc = grow(&c->work, &c->work_bytes, GCM_WORK_HEAD, "cudaMalloc(work)")) != 0) goto done;
-    LAUNCH(uaes_launch_xor_fold(src, nwords, c->work, tls_stream));
-    CU(cudaMemcpyAsync(result, c->work, 8, cudaMemcpyDefault, (cudaStream_t)tls_stream));
-    CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
+    scratch *w = NULL;
+    cudaStream_t st = (cudaStream_t)tls_stream;
+    if ((rc = get_ctx(&c)) != 0) return rc;
+    if ((rc = scratch_get(c, 64, st, &w)) != 0) return rc;
+    LAUNCH(uaes_launch_xor_fold(src, nwords, w->p, st));
+    CU(cudaMemcpyAsync(result, w->p, 8, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
 done:
-    pthread_mutex_unlock(&g_lock);
+    scratch_put(c, w, st);
     return rc;
+}
+
+/* ------------------------------------------------------------------ library state, lifecycle */
+
+int uaes_set_devices(int n)
+{
+    const int have = uaes_device_count();
+    if (!g_cfg_ready) cfg_init();
+    g_fan_devices = (n <= 0 || n > have) ? have : n;
+    if (g_fan_devices < 1) g_fan_devices = 1;
+    return g_fan_devices;
+}
+
+int uaes_get_devices(void)
+{
+    if (!g_cfg_ready) cfg_init();
+    return g_fan_devices;
+}
+
+void uaes_set_fanout_min(size_t bytes_per_device)
+{
+    if (!g_cfg_ready) cfg_init();
+    g_fan_min = bytes_per_device ? bytes_per_device : 1;
+}
+
+void uaes_set_burn(int enable)
+{
+    if (!g_cfg_ready) cfg_init();
+    g_burn = enable != 0;
+}
+
+void uaes_set_copy_threads(int n)
+{
+    if (!g_cfg_ready) cfg_init();
+    if (n >= 1 && n <= 32) g_copy_threads = n;
+}
+
+int uaes_host_register(void *p, size_t bytes)
+{
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess)
+        return fail(UAES_E_CUDA, "cudaHostRegister", (int)cudaGetLastError());
+    return 0;
+}
+
+int uaes_host_unregister(void *p)
+{
+    if (cudaHostUnregister(p) != cudaSuccess) return fail(UAES_E_CUDA, "cudaHostUnregister", (int)cudaGetLastError());
+    return 0;
+}
+
+/* frees what the library holds on one device; all = 0 keeps the streams and the staging chunks */
+static void dev_release(devctx *c, int all)
+{
+    int i, cur = 0;
+    if (!c->ready) return;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(c->dev) != cudaSuccess) { cudaGetLastError(); return; }
+    pthread_mutex_lock(&c->lock);
+    cudaDeviceSynchronize();
+    if (c->big) { if (g_burn) cudaMemset(c->big, 0, c->big_bytes); cudaFree(c->big); c->big = NULL; c->big_bytes = 0; }
+    pthread_mutex_lock(&c->plock);
+    for (i = 0; i < MAX_SCRATCH; ++i) {
+        scratch *s = &c->pool[i];
+        if (s->busy) continue;
+        if (s->p) { if (g_burn) cudaMemset(s->p, 0, s->bytes); cudaFree(s->p); s->p = NULL; s->bytes = 0; s->used = 0; }
+        if (all && s->have_ev) { cudaEventDestroy(s->ev); s->have_ev = 0; }
+    }
+    pthread_mutex_unlock(&c->plock);
+    for (i = 0; i < MAX_SLOT; ++i) {
+        if (c->slot[i] && (all || g_burn)) cudaMemset(c->slot[i], 0, CHUNK_BYTES);
+        if (c->hslot[i] && (all || g_burn)) memset(c->hslot[i], 0, CHUNK_BYTES);
+        if (all) {
+            if (c->slot[i]) { cudaFree(c->slot[i]); c->slot[i] = NULL; }
+            if (c->hslot[i]) { cudaFreeHost(c->hslot[i]); c->hslot[i] = NULL; }
+            cudaStreamDestroy(c->st[i]);
+            cudaEventDestroy(c->ev[i]);
+        }
+    }
+    if (all) c->ready = 0;
+    pthread_mutex_unlock(&c->lock);
+    cudaSetDevice(cur);
+    cudaGetLastError();
+}
+
+/* gives back the grow-on-demand device memory (full-size staging, work areas) of every device;
+ * staging chunks and streams stay for the next call */
+void uaes_trim(void)
+{
+    int i;
+    pthread_once(&g_dev_once, dev_locks_init);
+    for (i = 0; i < MAX_DEV; ++i) dev_release(&g_dev[i], 0);
+}
+
+/* releases everything, wiping staging memory first: the library is back in its initial state and
+ * initialises again on the next call.  No call may be in flight. */
+void uaes_shutdown(void)
+{
+    int i;
+    pthread_once(&g_dev_once, dev_locks_init);
+    for (i = 0; i < MAX_DEV; ++i) dev_release(&g_dev[i], 1);
 }

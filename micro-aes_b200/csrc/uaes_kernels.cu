@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <atomic>
 
 #include "uaes_core.cuh"
 #include "uaes_gf128.cuh"
@@ -22,7 +23,7 @@ constexpr int kThreads = 1024;
 constexpr int kWarpsPerCta = kThreads / 32;
 constexpr uint32_t kDynSmem = 227 * 1024;          // everything an SM has; tables are aligned inside
 
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};     // host threads of several devices launch concurrently
 
 // ---------------------------------------------------------------- small device helpers
 
@@ -324,7 +325,20 @@ struct EcbArgs {
     uint4 *out;
     uint64_t nblocks;
     uint32_t tail;               // encrypt: zero-padded extra block; decrypt: bytes copied through
+    uint32_t pad;                // encrypt: 0 = zero padding of a ragged tail only, 1 = PKCS#7, 2 = ISO/IEC 7816-4
+                                 // (the reference's AES_PADDING: the last two ALWAYS add a block, micro_aes.c:610-621)
 };
+
+// padBlock (micro_aes.c:610-621): the last block of an ECB encryption from `tail` input bytes
+__device__ inline void ecb_pad_block(const uint8_t *x, uint32_t tail, uint32_t pad, uint32_t s[4])
+{
+    const uint32_t n = 16 - tail;
+    s[0] = s[1] = s[2] = s[3] = 0;
+    for (uint32_t i = 0; i < 16; ++i) {
+        const uint32_t b = i < tail ? x[i] : pad == 1 ? n : (pad == 2 && i == tail) ? 0x80u : 0u;
+        s[i >> 2] |= b << (8 * (i & 3));
+    }
+}
 
 template <int NR, bool ENC>
 __global__ void __launch_bounds__(kThreads, 1) ecb_kernel(const __grid_constant__ EcbArgs a)
@@ -344,12 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) ecb_kernel(const __grid_constant_
         cur = nxt;
     }
 
-    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+    if ((a.tail || (ENC && a.pad)) && blockIdx.x == 0 && threadIdx.x == 0) {
         const uint8_t *x = (const uint8_t *)(a.in + a.nblocks);
         uint8_t *y = (uint8_t *)(a.out + a.nblocks);
-        if (ENC) {                                    // padBlock, micro_aes.c:610-621 (zero padding)
-            uint32_t s[4] = {0, 0, 0, 0};
-            for (uint32_t i = 0; i < a.tail; ++i) s[i >> 2] |= (uint32_t)x[i] << (8 * (i & 3));
+        if (ENC) {                                    // padBlock, micro_aes.c:610-621
+            uint32_t s[4];
+            ecb_pad_block(x, a.tail, a.pad, s);
             enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
             for (uint32_t i = 0; i < 16; ++i) y[i] = (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
         } else {                                      // the memcpy of micro_aes.c:667 leaves them as is
@@ -452,12 +466,12 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
         cur[0] = nxt[0]; cur[1] = nxt[1];
     }
 
-    if (a.e.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+    if ((a.e.tail || (!CFB && a.e.pad)) && blockIdx.x == 0 && threadIdx.x == 0) {
         const uint8_t *x = (const uint8_t *)(a.e.in + a.e.nblocks);
         uint8_t *y = (uint8_t *)(a.e.out + a.e.nblocks);
-        if (!CFB) {                                              // padBlock, micro_aes.c:610-621 (zero padding)
-            uint32_t s[4] = {0, 0, 0, 0};
-            for (uint32_t i = 0; i < a.e.tail; ++i) s[i >> 2] |= (uint32_t)x[i] << (8 * (i & 3));
+        if (!CFB) {                                              // padBlock, micro_aes.c:610-621
+            uint32_t s[4];
+            ecb_pad_block(x, a.e.tail, a.e.pad, s);
             enc_block<NR>(lb, s[0], s[1], s[2], s[3], rk);
             for (uint32_t i = 0; i < 16; ++i) y[i] = (uint8_t)(s[i >> 2] >> (8 * (i & 3)));
         } else {                                                 // ragged last block: E(C_(m-1)) ^ C_m, micro_aes.c:840-845
@@ -605,7 +619,7 @@ static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, c
 {
     cudaError_t e = opt_in_smem(ecb_hybrid_kernel<NR, CFB>);
     if (e != cudaSuccess) return e;
-    static EcbHybridArgs a;                              // 8 KB of planes: not on the stack (callers hold the library lock)
+    static thread_local EcbHybridArgs a;                 // 8 KB of planes: off the stack, one per calling thread
     a.e = e0;
     for (int c = 0; c < 4; ++c) a.iv[c] = iv ? iv[c] : 0;
     a.tt_blocks = (e0.nblocks - bs_blocks) & ~1023ull;
@@ -674,14 +688,14 @@ int uaes_launch_ctr(const uaes_keysched *ks, const uaes_ctrblock *cb, const void
     return (int)cudaErrorInvalidValue;
 }
 
-int uaes_launch_ecb(const uaes_keysched *ks, int encrypt, const void *in, void *out, u64 len,
+int uaes_launch_ecb(const uaes_keysched *ks, int encrypt, int pad, const void *in, void *out, u64 len,
                     void *stream)
 {
-    if (len == 0) return 0;
+    if (len == 0 && !(encrypt && pad)) return 0;
     EcbArgs a;
     a.ks = *ks;
     a.in = (const uint4 *)in; a.out = (uint4 *)out;
-    a.nblocks = len / 16; a.tail = (uint32_t)(len % 16);
+    a.nblocks = len / 16; a.tail = (uint32_t)(len % 16); a.pad = encrypt ? (uint32_t)pad : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ks->rounds * 2 + (encrypt ? 1 : 0)) {
     case 21: return (int)launch_ecb_nr<10, true>(a, st);

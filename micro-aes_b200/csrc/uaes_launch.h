@@ -38,8 +38,10 @@ typedef struct {
 int uaes_launch_ctr(const uaes_keysched *ks, const uaes_ctrblock *cb, const void *in, void *out,
                     u64 len, void *stream);
 
-/* ECB over len/16 full blocks; encrypt additionally zero-pads and encrypts a len%16 tail */
-int uaes_launch_ecb(const uaes_keysched *ks, int encrypt, const void *in, void *out, u64 len,
+/* ECB over len/16 full blocks; encrypt additionally pads and encrypts the last block: pad = 0 zero
+ * padding of a len%16 tail (nothing added when len%16 == 0), 1 = PKCS#7, 2 = ISO/IEC 7816-4 (both
+ * always add a block; micro_aes.c:610-621) */
+int uaes_launch_ecb(const uaes_keysched *ks, int encrypt, int pad, const void *in, void *out, u64 len,
                     void *stream);
 
 /* XTS over nsectors data units of sector_blocks*16 bytes; unit j uses tweak LE128(first_sector+j).
@@ -48,12 +50,14 @@ int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keysched *ks2, 
                             u64 first_sector, u64 sector_blocks, u64 nsectors, const void *in,
                             void *out, void *stream);
 
-/* XTS over ONE data unit of len bytes (len >= 16) with an explicit 16-byte tweak, including
- * ciphertext stealing.  ks1e = data key encryption schedule (needed by the stealing path and
- * the small cipher), ks1 = schedule for the bulk direction. */
+/* XTS over ONE data unit with an explicit 16-byte tweak, or over a RANGE of it: in[0] is block
+ * `first_block` of the unit (tweak T_0 * alpha^(first_block + k) for block k of the range), len >= 16
+ * bytes; a ragged len applies ciphertext stealing to the last two blocks of the range, so only the
+ * range that ends the unit may be ragged.  ks1e = data key encryption schedule (needed by the
+ * stealing path and the small cipher), ks1 = schedule for the bulk direction. */
 int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysched *ks1e,
                          const uaes_keysched *ks2, int encrypt, const unsigned char tweak[16],
-                         const void *in, void *out, u64 len, void *stream);
+                         u64 first_block, const void *in, void *out, u64 len, void *stream);
 
 /* GCM.  `work` is a device scratch area of at least uaes_gcm_work_bytes(len) bytes.
  * mode 0: CTR over in -> out, GHASH over aad and out;  mode 1: GHASH over aad and in only;
@@ -65,15 +69,21 @@ size_t uaes_gcm_work_bytes(u64 len);
 /* aad_state_dev: NULL, or 16 bytes of device memory holding the GHASH state after the AAD (from a
  * mode-1 partial_only pass over a large AAD); aad_dev is then not read, aadlen still feeds the
  * length block */
-int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+/* j0 = the pre-counter block J0: nonce || 00000001 for a 12-byte nonce, else GHASH_H(nonce)
+ * (uaes_launch_gcm_j0).  taglen = bytes of the tag written to tag_out (GCM_TAG_LEN). */
+int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char j0[16], const void *aad_dev,
                     u64 aadlen, const void *aad_state_dev, const void *in, void *out, u64 len,
-                    int mode, u64 first_block, int partial_only, void *tag_out, void *work,
-                    void *stream);
+                    int mode, u64 first_block, int partial_only, void *tag_out, unsigned taglen,
+                    void *work, void *stream);
+/* J0 = GHASH_H({}, iv) for a nonce of ivlen != 12 bytes (micro_aes.c:1145-1149); iv_dev and out_dev
+ * (16 bytes) are device memory */
+int uaes_launch_gcm_j0(const uaes_keysched *ks, const void *iv_dev, u64 ivlen, void *out_dev, void *stream);
 /* tag of a sharded message from the shards' contributions: partials_dev = nshards x 16 B,
- * after_dev = nshards x u64 (GHASH blocks after the end of each shard), both device memory */
-int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char nonce[12], const void *aad_dev,
+ * after_dev = nshards x u64 (GHASH blocks after the end of each shard), both device memory; any
+ * number of shards */
+int uaes_launch_gcm_combine(const uaes_keysched *ks, const unsigned char j0[16], const void *aad_dev,
                             u64 aadlen, u64 len, const void *partials_dev, const void *after_dev,
-                            unsigned nshards, void *tag_out, void *stream);
+                            unsigned nshards, void *tag_out, unsigned taglen, void *stream);
 
 /* GCM-SIV (micro_aes.c:1418-1516): key derivation blocks (8 bytes each, 2 + Nk/2 of them) into
  * device memory; POLYVAL + tag; CTR with the 32-bit little-endian counter seeded by a tag that
@@ -102,7 +112,7 @@ int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int enc
                     const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
                     const void *in, void *out, u64 len, void *tag_out, void *work, void *stream);
 
-/* streaming GCM: sum_r partial[r] * H^after[r] (16 bytes, device) for up to 31 shard contributions */
+/* sum_r partial[r] * H^after[r] (16 bytes, device): many contributions folded into the one of their union */
 int uaes_launch_gcm_fold(const uaes_keysched *ks, const void *partials_dev, const void *after_dev,
                          unsigned nshards, void *out_dev, void *stream);
 

@@ -271,7 +271,7 @@ static cudaError_t launch_ocb_hybrid_nr(const OcbBulkArgs &o, uint64_t bs_blocks
 {
     cudaError_t e = opt_in_smem(ocb_hybrid_kernel<NR>);
     if (e != cudaSuccess) return e;
-    static OcbHybridArgs a;                              // 8 KB of planes: not on the stack (callers hold the library lock)
+    static thread_local OcbHybridArgs a;                 // 8 KB of planes: off the stack, one per calling thread
     a.o = o;
     a.tt_blocks = (o.nblocks - bs_blocks) & ~1023ull;
     bs_make_key_planes_full(o.ks.w, NR, &a.bs);

@@ -118,7 +118,9 @@ struct XtsUnitArgs {
     const uint4 *in;
     uint4 *out;
     uint64_t nblocks;            // blocks handled by the plain loop: len/16 - (len%16 != 0)
-    uint32_t tail;               // len % 16 (stealing when non-zero)
+    uint64_t first_block;        // position of in[0] inside the data unit (a range of a larger unit: a
+                                 // staged chunk, or one GPU's share); tweak of block k = T_0 * alpha^(first_block + k)
+    uint32_t tail;               // len % 16 (stealing when non-zero; only the range that ends the unit has one)
 };
 
 // ciphertext stealing (micro_aes.c:1037-1053) on one thread with the byte-wise cipher
@@ -126,7 +128,7 @@ template <bool ENC>
 __device__ inline void xts_steal_tail(const XtsUnitArgs &a, const Tweak &T0)
 {
     const uint64_t m = a.nblocks;                              // index of the last full block
-    const Tweak Tm = xts_jump(T0, m), Tn = xts_shl(Tm, 1);
+    const Tweak Tm = xts_jump(T0, a.first_block + m), Tn = xts_shl(Tm, 1);
     const uint8_t *x = (const uint8_t *)(a.in + m);
     uint8_t *y = (uint8_t *)(a.out + m);
     uint8_t first[16], part[16];
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) xts_unit_kernel(const __grid_cons
     const uint64_t r0 = warp * rpw, r1 = r0 + rpw < rows ? r0 + rpw : rows;
 
     if (r0 < r1) {
-        Tweak t = xts_jump(T0, r0 * 32 + lane);
+        Tweak t = xts_jump(T0, a.first_block + r0 * 32 + lane);
         uint64_t k = r0 * 32 + lane;
         uint4 cur = k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
         for (uint64_t r = r0; r < r1; ++r, k += 32) {
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid
         const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
         const uint64_t p1 = p0 + per < ntiles ? p0 + per : ntiles;
         if (p0 >= p1) return;
-        Tweak tstart = xts_jump(T0, a.tt_blocks + p0 * 1024 + lane);
+        Tweak tstart = xts_jump(T0, a.u.first_block + a.tt_blocks + p0 * 1024 + lane);
         for (uint64_t tile = p0; tile < p1; ++tile) {
             const uint64_t kb = a.tt_blocks + tile * 1024 + lane;
             Tweak t = tstart;                                  // only tstart stays live across the rounds
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid
     const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
     const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
     if (q0 < q1) {
-        Tweak t = xts_jump(T0, q0 * 64 + lane);
+        Tweak t = xts_jump(T0, a.u.first_block + q0 * 64 + lane);
         uint4 cur[2], nxt[2];
         cur[0] = ld_stream(a.u.in + q0 * 64 + lane); cur[1] = ld_stream(a.u.in + q0 * 64 + 32 + lane);
         for (uint64_t q = q0; q < q1; ++q) {
@@ -450,7 +452,7 @@ static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tile
 {
     cudaError_t e = opt_in_smem(xts_sectors_hybrid_kernel<NR, ENC>);
     if (e != cudaSuccess) return e;
-    static XtsHybridArgs a;                              // 8 KB of planes: keep it off the stack
+    static thread_local XtsHybridArgs a;                 // 8 KB of planes: off the stack, one per calling thread
     a.x = x;
     a.ntiles = (x.nsectors + 31) / 32;
     a.tt_tiles = a.ntiles - bs_tiles;
@@ -466,7 +468,7 @@ static cudaError_t launch_xts_unit_hybrid_nr(const XtsUnitArgs &u, uint64_t bs_b
 {
     cudaError_t e = opt_in_smem(xts_unit_hybrid_kernel<NR>);
     if (e != cudaSuccess) return e;
-    static XtsUnitHybridArgs a;                          // 8 KB of planes: not on the stack (callers hold the library lock)
+    static thread_local XtsUnitHybridArgs a;                 // 8 KB of planes: off the stack, one per calling thread
     a.u = u;
     a.tt_blocks = (u.nblocks - bs_blocks) & ~1023ull;
     bs_make_key_planes_full(u.k1.w, NR, &a.bs);
@@ -527,6 +529,8 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
             switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
             case 21: return (int)launch_xts_hybrid_nr<10, true>(a, bs_tiles, st);
             case 20: return (int)launch_xts_hybrid_nr<10, false>(a, bs_tiles, st);
+            case 25: return (int)launch_xts_hybrid_nr<12, true>(a, bs_tiles, st);
+            case 24: return (int)launch_xts_hybrid_nr<12, false>(a, bs_tiles, st);
             case 29: return (int)launch_xts_hybrid_nr<14, true>(a, bs_tiles, st);
             case 28: return (int)launch_xts_hybrid_nr<14, false>(a, bs_tiles, st);
             }
@@ -535,6 +539,8 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
     switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
     case 21: return (int)launch_xts_sectors_nr<10, true>(a, st);
     case 20: return (int)launch_xts_sectors_nr<10, false>(a, st);
+    case 25: return (int)launch_xts_sectors_nr<12, true>(a, st);
+    case 24: return (int)launch_xts_sectors_nr<12, false>(a, st);
     case 29: return (int)launch_xts_sectors_nr<14, true>(a, st);
     case 28: return (int)launch_xts_sectors_nr<14, false>(a, st);
     }
@@ -543,7 +549,7 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
 
 extern "C" int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysched *ks1e,
                                     const uaes_keysched *ks2, int encrypt, const unsigned char tweak[16],
-                                    const void *in, void *out, u64 len, void *stream)
+                                    u64 first_block, const void *in, void *out, u64 len, void *stream)
 {
     using namespace uaes;
     if (len < 16) return (int)cudaErrorInvalidValue;
@@ -554,10 +560,13 @@ extern "C" int uaes_launch_xts_unit(const uaes_keysched *ks1, const uaes_keysche
     a.in = (const uint4 *)in; a.out = (uint4 *)out;
     a.tail = (uint32_t)(len % 16);
     a.nblocks = len / 16 - (a.tail ? 1 : 0);
+    a.first_block = first_block;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
     case 21: return (int)launch_xts_unit_nr<10, true>(a, st);
     case 20: return (int)launch_xts_unit_nr<10, false>(a, st);
+    case 25: return (int)launch_xts_unit_nr<12, true>(a, st);
+    case 24: return (int)launch_xts_unit_nr<12, false>(a, st);
     case 29: return (int)launch_xts_unit_nr<14, true>(a, st);
     case 28: return (int)launch_xts_unit_nr<14, false>(a, st);
     }
