@@ -89,6 +89,9 @@ int  uaes_set_devices(int n);
 int  uaes_get_devices(void);
 /* a call is spread only as far as every device still gets this many bytes (default 256 MiB) */
 void uaes_set_fanout_min(size_t bytes_per_device);
+/* staging pipeline geometry for host buffers: bytes per chunk (default 64 MiB) and chunks in flight
+ * per device (default 3); 0 keeps a value.  Implies uaes_shutdown(): no call may be in flight. */
+void uaes_set_staging(size_t chunk_bytes, int slots);
 /* helper threads that move PAGEABLE caller memory into / out of the pinned bounce chunks
  * (default 4; memcpy only -- no cipher work ever runs on the host) */
 void uaes_set_copy_threads(int n);
@@ -107,15 +110,20 @@ void uaes_shutdown(void);
 /* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
 uaes_u64 uaes_kernel_launches(void);
 /* CTR kernel geometry (tuning and tests; the defaults are the measured optimum on B200):
- *   tt_threads       geometry code: 385 (default) = 384 table-driven threads with two blocks in
- *                    flight each + 128 bitsliced co-runner threads; 384 = the same with one block
- *                    in flight; 512 / 768 / 1024 = table-driven warps only
+ *   tt_threads       geometry code: 386 (default) = 384 table-driven threads with two blocks in
+ *                    flight each + 128 bitsliced co-runner threads sharing the counter range through a
+ *                    two-ended work queue; 385 = the same warps with a static split (bs_permille);
+ *                    384 = static split, one block in flight; 512 / 768 / 1024 = table-driven warps only
  *   bs_permille      share of the blocks, in 1/1024, given to the bitsliced ALU co-runner warps
  *                    (0 = co-runner off)
  *   bs_min_blocks    calls shorter than this many 16-byte blocks never use the co-runner
  *                    (default 2^23 = 128 MiB; the same threshold serves ECB, XTS, OCB and CFB)
  * A negative value leaves that setting unchanged.  Results do not depend on any of them. */
 void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks);
+/* how the calling thread's most recent work-queue CTR launch (geometry 386) was shared out: units
+ * served by the table-driven warps, by the bitsliced warps, and 16-byte blocks per unit.  Waits for
+ * the device.  (bench.py derives the shared-memory-lookup roofline from it.) */
+int uaes_ctr_queue_stats(uaes_u64 *tt_units, uaes_u64 *bs_units, uaes_u64 *unit_blocks);
 
 /* ---- the hot path, run-time key length ------------------------------------- */
 /* keybits = 128, 192 or 256 everywhere (XTS: keys = K1 || K2, 2 * keybits / 8 bytes). */

@@ -44,11 +44,13 @@ UAES_ABI = {
     "uaes_get_devices": (_int, []),
     "uaes_set_fanout_min": (None, [_sz]),
     "uaes_set_copy_threads": (None, [_int]),
+    "uaes_set_staging": (None, [_sz, _int]),
     "uaes_set_burn": (None, [_int]),
     "uaes_trim": (None, []),
     "uaes_shutdown": (None, []),
     "uaes_kernel_launches": (_u64, []),
     "uaes_ctr_tuning": (None, [_int, _int, ctypes.c_longlong]),
+    "uaes_ctr_queue_stats": (_int, [ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "uaes_ecb_encrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
     "uaes_ecb_decrypt": (_int, [_int, _cp, _vp, _sz, _vp]),
     "uaes_ctr_crypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
@@ -433,6 +435,11 @@ def set_fanout_min(nbytes):
     core().uaes_set_fanout_min(nbytes)
 
 
+def set_staging(chunk_bytes=0, slots=0):
+    """staging chunk size / slots per device for host buffers (releases the current ones first)"""
+    core().uaes_set_staging(chunk_bytes, slots)
+
+
 def set_copy_threads(n):
     core().uaes_set_copy_threads(n)
 
@@ -513,6 +520,14 @@ class Stream:
 
 def kernel_launches():
     return core().uaes_kernel_launches()
+
+
+def ctr_queue_stats():
+    """(units served by table-driven warps, by bitsliced warps, blocks per unit) of this thread's last
+    work-queue CTR launch"""
+    a, b, c = _u64(0), _u64(0), _u64(0)
+    check(core().uaes_ctr_queue_stats(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
 
 
 def ctr_tuning(tt_threads=-1, bs_permille=-1, bs_min_blocks=-1):

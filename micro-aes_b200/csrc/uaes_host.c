@@ -76,6 +76,12 @@ void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks)
     uaes_launch_ctr_tuning(tt_threads, bs_permille, bs_min_blocks);
 }
 
+int uaes_ctr_queue_stats(uaes_u64 *tt_units, uaes_u64 *bs_units, uaes_u64 *unit_blocks)
+{
+    const int e = uaes_launch_ctr_queue_stats(tt_units, bs_units, unit_blocks);
+    return e ? fail(UAES_E_CUDA, "no work-queue CTR launch on this thread yet", 0) : 0;
+}
+
 int uaes_device_count(void)
 {
     int n = 0;
@@ -245,6 +251,7 @@ static int g_cfg_ready;
 /* process-wide settings (uaes_set_devices, uaes_set_burn, ...) */
 static int    g_fan_devices = 1;                      /* devices a host-buffer call may be spread over */
 static size_t g_fan_min = (size_t)256 << 20;          /* ... when every device gets at least this much */
+static int    g_fan_oversubscribe;                    /* tests: more parts than devices (UAES_FANOUT_OVERSUBSCRIBE) */
 static int    g_burn;                                 /* wipe staging memory and scratch after each call */
 static size_t g_big_keep = (size_t)256 << 20;         /* full-size staging above this is freed after the call */
 static int    g_copy_threads = 4;                     /* helpers that move pageable memory to / from the pinned chunks */
@@ -267,9 +274,12 @@ static void cfg_init(void)
         if ((e = getenv("UAES_STAGE_SLOTS")) != NULL && atoi(e) >= 1 && atoi(e) <= MAX_SLOT) g_nslot = atoi(e);
         if ((e = getenv("UAES_STAGE_CHUNK_MIB")) != NULL && atoi(e) >= 1 && (size_t)atoi(e) <= (MAX_CHUNK >> 20))
             g_chunk = (size_t)atoi(e) << 20;
+        /* more parts than devices: the parts share devices and run one after the other there -- no
+         * gain, but the whole splitting / threading path runs on a one-GPU box (tests) */
+        if ((e = getenv("UAES_FANOUT_OVERSUBSCRIBE")) != NULL) g_fan_oversubscribe = atoi(e) != 0;
         if ((e = getenv("UAES_DEVICES")) != NULL) {
             int n = atoi(e), have = uaes_device_count();
-            g_fan_devices = (n <= 0 || n > have) ? have : n;
+            g_fan_devices = (n <= 0 || (n > have && !g_fan_oversubscribe)) ? have : n;
             if (g_fan_devices < 1) g_fan_devices = 1;
         }
         if ((e = getenv("UAES_FANOUT_MIN_MIB")) != NULL && atoi(e) >= 1) g_fan_min = (size_t)atoi(e) << 20;
@@ -667,7 +677,7 @@ static int fan_plan(const pipe_part *whole, int n, size_t align, fan_part f[MAX_
 {
     int i, cur = 0, count = uaes_device_count();
     size_t per, off = 0;
-    if (n > count) n = count;
+    if (n > count && !g_fan_oversubscribe) n = count;
     if (n > MAX_DEV) n = MAX_DEV;
     if (n < 1) n = 1;
     if (n > 1 && cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); n = 1; }
@@ -1915,11 +1925,14 @@ done:
 
 /* ------------------------------------------------------------------ library state, lifecycle */
 
+void uaes_shutdown(void);
+
 int uaes_set_devices(int n)
 {
     const int have = uaes_device_count();
     if (!g_cfg_ready) cfg_init();
-    g_fan_devices = (n <= 0 || n > have) ? have : n;
+    g_fan_devices = (n <= 0 || (n > have && !g_fan_oversubscribe)) ? have : n;
+    if (g_fan_devices > MAX_DEV) g_fan_devices = MAX_DEV;
     if (g_fan_devices < 1) g_fan_devices = 1;
     return g_fan_devices;
 }
@@ -1934,6 +1947,21 @@ void uaes_set_fanout_min(size_t bytes_per_device)
 {
     if (!g_cfg_ready) cfg_init();
     g_fan_min = bytes_per_device ? bytes_per_device : 1;
+}
+
+/* staging geometry: chunk bytes (rounded down to 64 KiB, 64 KiB .. 256 MiB) and number of slots
+ * (1 .. 8); 0 keeps a value.  Releases the current chunks first, so no call may be in flight. */
+void uaes_set_staging(size_t chunk_bytes, int slots)
+{
+    if (!g_cfg_ready) cfg_init();
+    uaes_shutdown();
+    if (chunk_bytes) {
+        chunk_bytes &= ~(size_t)65535;
+        if (chunk_bytes < 65536) chunk_bytes = 65536;
+        if (chunk_bytes > MAX_CHUNK) chunk_bytes = MAX_CHUNK;
+        g_chunk = chunk_bytes;
+    }
+    if (slots >= 1 && slots <= MAX_SLOT) g_nslot = slots;
 }
 
 void uaes_set_burn(int enable)

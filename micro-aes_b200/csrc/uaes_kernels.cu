@@ -97,6 +97,12 @@ struct CtrArgs {
     uint64_t bs_u0;              // v0 + tt_blocks: first counter (not reduced mod 2^56) of the
                                  // bitsliced range, a multiple of 1024 unless bs_passes == 0
     uint64_t bs_passes;          // 1024-counter passes covering blocks [tt_blocks, nblocks)
+    // work-queue form (ctr_queue_kernel): the counter range in units of kQUnit blocks, handed out
+    // from the front to the table-driven warps and from the back to the bitsliced warps
+    unsigned long long *q;       // device: [0] front | back << 32, [1] units done by table-driven warps, [2] by bitsliced warps
+    uint64_t q_u0;               // counter (not reduced mod 2^56) where unit 0 starts: v0 rounded down to a unit
+    uint64_t q_units;            // units covering [v0, v0 + nblocks)
+    uint32_t q_bs_on;            // 0: the bitsliced warps take no work (short calls)
     BsKeyPlanes bs;
 };
 
@@ -126,68 +132,73 @@ constexpr int kBsThreads = 128;
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// one pass = 1024 consecutive counters starting at u0 (a multiple of 1024, not reduced mod 2^56);
+// tag16 remembers for which counter bytes <= 13 the uniform masks `um` were built
+template <int NR, int BATCH>
+__device__ __forceinline__ void ctr_bs_pass(const CtrArgs &a, uint32_t lb, uint32_t *um, uint64_t u0, uint64_t &tag16)
+{
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t vc = u0 & kMask56;
+    {   // pull this pass's 16 KiB of input towards L2 while the rounds run (4 lines per lane)
+        const uint64_t kb = u0 - a.v0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint64_t k = kb + (uint64_t)(lane * 4 + i) * 8;
+            if (k < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + k));
+        }
+    }
+    if ((vc >> 16) != tag16) {              // counter bytes <= 13 changed: every 64 passes
+        tag16 = vc >> 16;
+        uint32_t w2, w3, uw[6];
+        ctr_words(a.b8, vc, w2, w3);
+        bs_uniform_words([&](int t, uint32_t x) { return lut_index(lb, t == 0 ? kOffT0 : t == 1 ? kOffT1 : t == 2 ? kOffT2 : kOffT3, x); },
+                         a.w0 ^ rk[0], a.w1 ^ rk[1], w2 ^ rk[2], w3 ^ rk[3], rk, uw);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 6; ++j) um[32 * j + lane] = bs_mask(uw[j], (int)lane);
+        __syncwarp();
+    }
+    uint32_t s[128];
+    bs_first_rounds(s, lane, (uint32_t)(vc >> 8) & 0xfcu, a.bs.k0, um);
+    // all rounds in ONE loop body (the last one skips MixColumns): a second copy of the S-box layer
+    // for the last round cost 1.2 % through the instruction cache (1008 -> 1020 GiB/s)
+#pragma unroll 1
+    for (int r = 3; r <= NR; ++r) bs_round_or_last(s, a.bs.k[r - 3], r == NR);
+    // XOR with the data: slot t of all lanes = one coalesced 512-byte row.  The loads are
+    // software-pipelined one batch ahead (the first batch goes out before the transposes).
+    const int64_t k0 = (int64_t)(u0 - a.v0) + lane;          // block index of slot 0 (may be < 0 in the first unit)
+    auto load_batch = [&](int t0, uint4 (&x)[BATCH]) {
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int64_t k = k0 + 32 * (t0 + i);
+            x[i] = (uint64_t)k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    uint4 x[BATCH], y[BATCH];
+    load_batch(0, x);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+#pragma unroll
+    for (int t0 = 0; t0 < 32; t0 += BATCH) {
+        if (t0 + BATCH < 32) load_batch(t0 + BATCH, y);
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const int64_t k = k0 + 32 * (t0 + i);
+            const int t = t0 + i;
+            x[i].x ^= s[t]; x[i].y ^= s[32 + t]; x[i].z ^= s[64 + t]; x[i].w ^= s[96 + t];
+            if ((uint64_t)k < a.nblocks) st_stream(a.out + k, x[i]);
+            x[i] = y[i];
+        }
+    }
+}
+
 template <int NR, int BATCH>
 __device__ __forceinline__ void ctr_bitsliced_warp(const CtrArgs &a, uint32_t lb, uint32_t *um,
                                                    uint64_t p0, uint64_t p1)
 {
-    const uint32_t *rk = a.ks.w;
-    const uint32_t lane = threadIdx.x & 31;
     uint64_t tag16 = ~0ull;
-    for (uint64_t p = p0; p < p1; ++p) {
-        const uint64_t u0 = a.bs_u0 + (p << 10);
-        const uint64_t vc = u0 & kMask56;
-        {   // pull this pass's 16 KiB of input towards L2 while the rounds run (4 lines per lane)
-            const uint64_t kb = u0 - a.v0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint64_t k = kb + (uint64_t)(lane * 4 + i) * 8;
-                if (k < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + k));
-            }
-        }
-        if ((vc >> 16) != tag16) {              // counter bytes <= 13 changed: every 64 passes
-            tag16 = vc >> 16;
-            uint32_t w2, w3, uw[6];
-            ctr_words(a.b8, vc, w2, w3);
-            bs_uniform_words([&](int t, uint32_t x) { return lut_index(lb, t == 0 ? kOffT0 : t == 1 ? kOffT1 : t == 2 ? kOffT2 : kOffT3, x); },
-                             a.w0 ^ rk[0], a.w1 ^ rk[1], w2 ^ rk[2], w3 ^ rk[3], rk, uw);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 6; ++j) um[32 * j + lane] = bs_mask(uw[j], (int)lane);
-            __syncwarp();
-        }
-        uint32_t s[128];
-        bs_first_rounds(s, lane, (uint32_t)(vc >> 8) & 0xfcu, a.bs.k0, um);
-        // all rounds in ONE loop body (the last one skips MixColumns): a second copy of the S-box layer
-        // for the last round cost 1.2 % through the instruction cache (1008 -> 1020 GiB/s)
-#pragma unroll 1
-        for (int r = 3; r <= NR; ++r) bs_round_or_last(s, a.bs.k[r - 3], r == NR);
-        // XOR with the data: slot t of all lanes = one coalesced 512-byte row.  The loads are
-        // software-pipelined one batch ahead (the first batch goes out before the transposes).
-        const int64_t k0 = (int64_t)(u0 - a.v0) + lane;      // block index of slot 0; >= tt_blocks
-        auto load_batch = [&](int t0, uint4 (&x)[BATCH]) {
-#pragma unroll
-            for (int i = 0; i < BATCH; ++i) {
-                const int64_t k = k0 + 32 * (t0 + i);
-                x[i] = (uint64_t)k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
-            }
-        };
-        uint4 x[BATCH], y[BATCH];
-        load_batch(0, x);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
-#pragma unroll
-        for (int t0 = 0; t0 < 32; t0 += BATCH) {
-            if (t0 + BATCH < 32) load_batch(t0 + BATCH, y);
-#pragma unroll
-            for (int i = 0; i < BATCH; ++i) {
-                const int64_t k = k0 + 32 * (t0 + i);
-                const int t = t0 + i;
-                x[i].x ^= s[t]; x[i].y ^= s[32 + t]; x[i].z ^= s[64 + t]; x[i].w ^= s[96 + t];
-                if ((uint64_t)k < a.nblocks) st_stream(a.out + k, x[i]);
-                x[i] = y[i];
-            }
-        }
-    }
+    for (uint64_t p = p0; p < p1; ++p) ctr_bs_pass<NR, BATCH>(a, lb, um, a.bs_u0 + (p << 10), tag16);
 }
 
 template <int NR, int kCtrThreads, bool BS, int ILP>
@@ -311,6 +322,194 @@ __global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_ke
         uint32_t s0 = a.w0, s1 = a.w1, s2 = w2, s3 = w3;
         enc_block<NR>(lb, s0, s1, s2, s3, rk);
         const uint32_t ksw[4] = {s0, s1, s2, s3};
+        const uint8_t *x = (const uint8_t *)(a.in + a.nblocks);
+        uint8_t *y = (uint8_t *)(a.out + a.nblocks);
+        for (uint32_t i = 0; i < a.tail; ++i) y[i] = x[i] ^ (uint8_t)(ksw[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
+// ---- CTR with a two-ended work queue ---------------------------------------------------------------
+// Same two kinds of warps as ctr_kernel, but no static split: the counter range is cut into units of
+// kQUnit blocks; table-driven warps claim units from the FRONT, bitsliced warps from the BACK, through
+// one 64-bit atomic add on a packed (front, back) word.  A claim sees both counts at its own place in
+// the atomic order, so "front + back < units" decides exactly and without a retry loop whether the
+// unit is still free: the two kinds of warps meet wherever their actual speeds on THIS GPU put the
+// border, nobody waits for the other kind (the static 195/1024 split was tuned on one box; the pool
+// spreads 982..1026 GiB/s), and short calls need no special case.
+// A table-driven warp serves both halves of its unit one after the other (rows 0..3, then rows 4..7 of
+// every group), re-deriving the 16 register-resident round-2 words when the half changes; its next
+// unit is claimed a unit ahead so that neither the atomic nor the first loads of that unit are
+// waited for.
+#ifndef UAES_BS_BATCH
+#define UAES_BS_BATCH 4                          // rows of a bitsliced pass loaded ahead of the XOR / store
+#endif
+#ifndef UAES_Q_UNIT_SHIFT
+#define UAES_Q_UNIT_SHIFT 11                     // 2048 blocks = 32 KiB = 8 groups = 2 bitsliced passes
+#endif
+constexpr int kQUnitShift = UAES_Q_UNIT_SHIFT;
+constexpr uint64_t kQUnit = 1ull << kQUnitShift;
+constexpr uint64_t kQNone = ~0ull;
+
+// front claim (table-driven): returns the unit or kQNone; all lanes get the same answer
+__device__ __forceinline__ uint64_t q_claim_front(unsigned long long *q, uint64_t units)
+{
+    unsigned long long old = 0;
+    if ((threadIdx.x & 31) == 0) old = atomicAdd(q, 1ull);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const uint64_t f = old & 0xffffffffull, b = old >> 32;
+    return f + b < units ? f : kQNone;
+}
+
+__device__ __forceinline__ uint64_t q_claim_back(unsigned long long *q, uint64_t units)
+{
+    unsigned long long old = 0;
+    if ((threadIdx.x & 31) == 0) old = atomicAdd(q, 1ull << 32);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const uint64_t f = old & 0xffffffffull, b = old >> 32;
+    return f + b < units ? units - 1 - b : kQNone;
+}
+
+template <int NR, int kCtrThreads, int ILP>
+__global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(const __grid_constant__ CtrArgs a)
+{
+    static_assert(ILP == 2, "two rows in flight per table-driven thread");
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
+#ifndef UAES_Q_TT_REGS
+#define UAES_Q_TT_REGS 104
+#endif
+    constexpr int kTtRegs = UAES_Q_TT_REGS;
+    constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
+    constexpr int kBsRegs = (kBsRegs0 > 232 ? 232 : kBsRegs0) / 8 * 8;
+
+    if (threadIdx.x >= kCtrThreads) {
+        reg_inc<kBsRegs>();
+        const uint32_t tbase = align_table_base(dyn);
+        const uint32_t bw = (threadIdx.x - kCtrThreads) >> 5;
+        const uint32_t off = tbase + kEncTableBytes + bw * (kBsUniformMasks * 4) - smem_u32(dyn);
+        if (off + kBsUniformMasks * 4 > dyn_smem_size()) __trap();
+        if (!a.q_bs_on) return;
+        uint32_t *um = (uint32_t *)(dyn + off);
+        uint64_t tag16 = ~0ull, done = 0;
+        for (;;) {
+            const uint64_t u = q_claim_back(a.q, a.q_units);
+            if (u == kQNone) break;
+            const uint64_t c0 = a.q_u0 + (u << kQUnitShift);
+#pragma unroll 1
+            for (uint32_t p = 0; p < (uint32_t)(kQUnit >> 10); ++p)
+                ctr_bs_pass<NR, UAES_BS_BATCH>(a, lb, um, c0 + ((uint64_t)p << 10), tag16);
+            ++done;
+        }
+        if (lane == 0 && done) atomicAdd(a.q + 2, (unsigned long long)done);
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    // absolute group index G = counter >> 8 (counter space not reduced mod 2^56); block index of
+    // (G, row r = 4 * half + it, lane) = 256 G + 32 r + lane - v0
+    constexpr uint32_t kGroupsPerUnit = (uint32_t)(kQUnit >> 8);
+    const uint64_t Gfirst = a.q_u0 >> 8;
+    auto kof = [&](uint64_t G, uint32_t r) -> int64_t {
+        return (int64_t)((G << 8) + 32 * r + lane) - (int64_t)a.v0;
+    };
+    auto fetch = [&](bool ok, uint64_t G, uint32_t r) -> uint4 {
+        const int64_t k = kof(G, r);
+        if (ok && k >= 0 && (uint64_t)k < a.nblocks) return ld_stream(a.in + k);
+        return make_uint4(0, 0, 0, 0);
+    };
+
+    uint64_t tag40 = ~0ull, tag16 = ~0ull, done = 0;
+    uint32_t U[4][4], K0 = 0, Cp1 = 0, E0 = 0, E1 = 0, E2 = 0, E3 = 0;
+    const uint32_t s0 = a.w0 ^ rk[0], s1 = a.w1 ^ rk[1];
+
+    uint64_t ucur = q_claim_front(a.q, a.q_units);
+    uint4 cur[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) cur[i] = fetch(ucur != kQNone, Gfirst + ucur * kGroupsPerUnit, (uint32_t)i);
+    while (ucur != kQNone) {
+        const uint64_t unext = q_claim_front(a.q, a.q_units);          // a unit ahead: its latency hides behind this unit
+        const uint64_t Gu = Gfirst + ucur * kGroupsPerUnit;
+#pragma unroll 1
+        for (uint32_t half = 0; half < 2; ++half) {
+            const uint32_t b15 = half * 128 + lane;                   // + 32 * it
+            bool fresh = true;                                        // U belongs to (K0, half)
+#pragma unroll 1
+            for (uint32_t jj = 0; jj < kGroupsPerUnit; ++jj) {
+                const uint64_t G = Gu + jj;
+                const uint64_t vg = (G << 8) & kMask56;
+                uint32_t w2, w3;
+                ctr_words(a.b8, vg, w2, w3);
+                const uint32_t s2 = w2 ^ rk[2], s3 = w3 ^ rk[3];     // byte 15 of the counter is 0 here
+                if ((vg >> 40) != tag40) {                            // once per launch in practice
+                    tag40 = vg >> 40;
+                    K0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ rk[4];
+                    Cp1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
+                    tag16 = ~0ull;
+                    fresh = true;
+                }
+                if (fresh) {                                          // per unit half: 20 lookups for 8192
+                    fresh = false;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const uint32_t c0 = K0 ^ lut<3, kOffT3>(lb, s3 ^ ((b15 + 32 * it) << 24));
+                        U[it][0] = lut<0, kOffT0>(lb, c0); U[it][1] = lut<3, kOffT3>(lb, c0);
+                        U[it][2] = lut<2, kOffT2>(lb, c0); U[it][3] = lut<1, kOffT1>(lb, c0);
+                    }
+                }
+                if ((vg >> 16) != tag16) {                            // every 256 groups, and on every new unit
+                    tag16 = vg >> 16;
+                    const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
+                    const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
+                    E0 = lut<2, kOffT2>(lb, C2) ^ lut<3, kOffT3>(lb, C3) ^ rk[8];
+                    E1 = lut<1, kOffT1>(lb, C2) ^ lut<2, kOffT2>(lb, C3) ^ rk[9];
+                    E2 = lut<0, kOffT0>(lb, C2) ^ lut<1, kOffT1>(lb, C3) ^ rk[10];
+                    E3 = lut<0, kOffT0>(lb, C3) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+                }
+                // per group: counter byte 14 enters through column 1 of round 1
+                const uint32_t C1 = Cp1 ^ lut<2, kOffT2>(lb, s3);
+                const uint32_t D0 = E0 ^ lut<1, kOffT1>(lb, C1), D1 = E1 ^ lut<0, kOffT0>(lb, C1);
+                const uint32_t D2 = E2 ^ lut<3, kOffT3>(lb, C1), D3 = E3 ^ lut<2, kOffT2>(lb, C1);
+                const bool last_group = jj + 1 == kGroupsPerUnit;
+#pragma unroll
+                for (int it = 0; it < 4; it += ILP) {
+                    uint4 nxt[ILP];
+                    uint32_t t[ILP][4];
+#pragma unroll
+                    for (int i = 0; i < ILP; ++i) {
+                        // the rows after these: same group; next group of this half; first group of the
+                        // other half; first group of the unit claimed ahead
+                        if (it + ILP < 4)      nxt[i] = fetch(true, G, 4 * half + it + ILP + i);
+                        else if (!last_group)  nxt[i] = fetch(true, G + 1, 4 * half + i);
+                        else if (half == 0)    nxt[i] = fetch(true, Gu, 4 + i);
+                        else                   nxt[i] = fetch(unext != kQNone, Gfirst + unext * kGroupsPerUnit, (uint32_t)i);
+                        t[i][0] = D0 ^ U[it + i][0]; t[i][1] = D1 ^ U[it + i][1];
+                        t[i][2] = D2 ^ U[it + i][2]; t[i][3] = D3 ^ U[it + i][3];
+                    }
+                    enc_finish_n<NR, 3, ILP>(lb, t, rk, cur);
+#pragma unroll
+                    for (int i = 0; i < ILP; ++i) {
+                        const int64_t k = kof(G, 4 * half + it + i);
+                        if (k >= 0 && (uint64_t)k < a.nblocks) st_stream(a.out + k, make_uint4(t[i][0], t[i][1], t[i][2], t[i][3]));
+                        cur[i] = nxt[i];
+                    }
+                }
+            }
+        }
+        ++done;
+        ucur = unext;
+    }
+    if (lane == 0 && done) atomicAdd(a.q + 1, (unsigned long long)done);
+
+    // ragged tail: Y[0..n) = E(ctr)[0..n) ^ X[0..n)  (mixThenXor, micro_aes.c:534-544)
+    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t w2, w3;
+        ctr_words(a.b8, (a.v0 + a.nblocks) & kMask56, w2, w3);
+        uint32_t t0 = a.w0, t1 = a.w1, t2 = w2, t3 = w3;
+        enc_block<NR>(lb, t0, t1, t2, t3, rk);
+        const uint32_t ksw[4] = {t0, t1, t2, t3};
         const uint8_t *x = (const uint8_t *)(a.in + a.nblocks);
         uint8_t *y = (uint8_t *)(a.out + a.nblocks);
         for (uint32_t i = 0; i < a.tail; ++i) y[i] = x[i] ^ (uint8_t)(ksw[i >> 2] >> (8 * (i & 3)));
@@ -576,7 +775,43 @@ static long long g_ctr_bs_min = 1ll << 23;    // 128 MiB: below it the co-runner
 //   385  = the same with two blocks per thread in flight (default; the co-runner's instructions
 //          lengthen every lookup round trip, the second block hides it: 968 -> 1006 GiB/s)
 //   512 / 768 / 1024 = table-driven warps only
-constexpr int kCtrDefaultGeometry = 385, kCtrDefaultShare = 195;
+//   386  = the work-queue kernel (ctr_queue_kernel): 384 table-driven threads, two rows in flight,
+//          + 128 co-runner threads; no static split, bs_permille only switches the co-runner on / off
+#ifndef UAES_CTR_DEFAULT_GEOMETRY
+#define UAES_CTR_DEFAULT_GEOMETRY 386
+#endif
+constexpr int kCtrDefaultGeometry = UAES_CTR_DEFAULT_GEOMETRY, kCtrDefaultShare = 195;
+
+// ---- queue words: one 32-byte slot per launch, from a per-device ring (a slot comes round again
+// after kQRing launches on that device; far more than can be in flight)
+constexpr int kQRing = 4096;
+static unsigned long long *g_qring[64];
+static std::atomic<unsigned> g_qnext[64];
+static std::atomic_flag g_qlock = ATOMIC_FLAG_INIT;
+static thread_local unsigned long long *tls_last_q = nullptr;
+
+static cudaError_t q_slot(cudaStream_t st, unsigned long long **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!g_qring[dev]) {
+        while (g_qlock.test_and_set(std::memory_order_acquire)) { }
+        if (!g_qring[dev]) {
+            void *p = nullptr;
+            e = cudaMalloc(&p, (size_t)kQRing * 32);
+            if (e == cudaSuccess) g_qring[dev] = (unsigned long long *)p;
+        }
+        g_qlock.clear(std::memory_order_release);
+        if (e != cudaSuccess) return e;
+    }
+    unsigned long long *q = g_qring[dev] + 4 * (size_t)(g_qnext[dev].fetch_add(1) % kQRing);
+    e = cudaMemsetAsync(q, 0, 32, st);
+    *out = q;
+    tls_last_q = q;
+    return e;
+}
 
 static void ctr_tuning_init()
 {
@@ -591,6 +826,24 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     ctr_tuning_init();
     const int threads = g_ctr_threads, share = g_ctr_share;
     a.tt_blocks = a.nblocks; a.bs_u0 = 0; a.bs_passes = 0;
+    a.q = nullptr; a.q_u0 = 0; a.q_units = 0; a.q_bs_on = 0;
+    if (threads == 386) {
+        // work queue: units of kQUnit counters, aligned in counter space; both kinds of warps clip to
+        // [v0, v0 + nblocks).  Short calls keep the co-runner out (a bitsliced unit takes longer than a
+        // table-driven one, which shows when there are fewer units than warps).
+        a.q_u0 = a.v0 & ~(kQUnit - 1);
+        a.q_units = (a.v0 - a.q_u0 + a.nblocks + kQUnit - 1) >> kQUnitShift;
+        a.q_bs_on = share > 0 && (long long)a.nblocks >= g_ctr_bs_min;
+        if (a.q_bs_on) bs_make_key_planes(a.ks.w, NR, &a.bs);
+        cudaError_t e = opt_in_smem(ctr_queue_kernel<NR, 384, 2>);
+        if (e != cudaSuccess) return e;
+        if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
+        // one CTA per SM; fewer when there are not even 2 units per table-driven warp
+        const uint64_t sms = (uint64_t)sm_count(), want = (a.q_units + 2 * 12 - 1) / (2 * 12);
+        ctr_queue_kernel<NR, 384, 2><<<(unsigned)(want < 1 ? 1 : want < sms ? want : sms), 384 + kBsThreads, kDynSmem, st>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
     if (share > 0 && (threads == 384 || threads == 385) && (long long)a.nblocks >= g_ctr_bs_min) {
         // bitsliced range = [S, v0 + nblocks) with S a multiple of 1024 in counter space
         const uint64_t want = a.nblocks / 1024 * (uint64_t)share;           // blocks for the co-runner
@@ -661,6 +914,17 @@ using namespace uaes;
 extern "C" {
 
 u64 uaes_launch_count(void) { return g_launches; }
+
+/* units the two kinds of warps of the calling thread's most recent work-queue CTR launch ended up
+ * with (synchronises the device); unit_blocks = blocks per unit */
+int uaes_launch_ctr_queue_stats(u64 *tt_units, u64 *bs_units, u64 *unit_blocks)
+{
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (!tls_last_q) return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaMemcpy(h, tls_last_q, 32, cudaMemcpyDeviceToHost);
+    *tt_units = h[1]; *bs_units = h[2]; *unit_blocks = kQUnit;
+    return (int)e;
+}
 
 void uaes_launch_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks)
 {

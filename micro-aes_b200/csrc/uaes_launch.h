@@ -129,6 +129,9 @@ int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched
 int uaes_launch_fill(u64 seed, u64 first_word, void *dst, u64 nwords, void *stream);
 int uaes_launch_xor_fold(const void *src, u64 nwords, void *result_dev, void *stream);
 
+/* how the calling thread's last work-queue CTR launch was shared: units served by the table-driven
+ * warps and by the bitsliced warps, blocks per unit (bench bookkeeping; synchronises) */
+int uaes_launch_ctr_queue_stats(u64 *tt_units, u64 *bs_units, u64 *unit_blocks);
 /* kernels launched so far by this process */
 u64 uaes_launch_count(void);
 /* CTR kernel geometry, see uaes_ctr_tuning() in uaes_b200.h */

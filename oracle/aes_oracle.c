@@ -219,6 +219,24 @@ void oracle_ecb_encrypt(int keybits, const uint8_t *key, const void *in, size_t 
 
 /* micro_aes.c:663-680: full blocks are decrypted, the tail bytes are copied
  * through untouched (the initial memcpy), and a ragged length is an error */
+/* micro_aes.c:610-621 (padBlock) with AES_PADDING = 1 (PKCS#7) or 2 (ISO/IEC 7816-4): the last block
+ * is ALWAYS padded, so out holds (len / 16 + 1) * 16 bytes; padding = 0 is oracle_ecb_encrypt */
+void oracle_ecb_encrypt_padded(int keybits, const uint8_t *key, const void *in, size_t len, void *out,
+                               int padding)
+{
+    aes_ctx c;
+    const uint8_t *x = (const uint8_t *)in;
+    uint8_t *y = (uint8_t *)out, last[16];
+    size_t n = len / 16, tail = len % 16, i;
+
+    if (!padding) { oracle_ecb_encrypt(keybits, key, in, len, out); return; }
+    key_setup(&c, keybits, key);
+    for (; n--; x += 16, y += 16) encrypt_block(&c, x, y);
+    for (i = 0; i < 16; ++i)
+        last[i] = i < tail ? x[i] : padding == 1 ? (uint8_t)(16 - tail) : i == tail ? 0x80 : 0;
+    encrypt_block(&c, last, y);
+}
+
 int oracle_ecb_decrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out)
 {
     aes_ctx c;
@@ -284,6 +302,18 @@ void oracle_ctr_crypt(int keybits, const uint8_t *key, const uint8_t iv[12],
     oracle_ctr_crypt_at(keybits, key, iv, 0, in, len, out);
 }
 
+/* micro_aes.c:962-976 with PRESET_COUNTER == 1 (:964-966): the caller's 16 bytes are counter block 0 */
+void oracle_ctr_crypt_block(int keybits, const uint8_t *key, const uint8_t ctr0[16],
+                            uint64_t first_block, const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    uint8_t ctr[16];
+    memcpy(ctr, ctr0, 16);
+    ctr_add(ctr, first_block);
+    key_setup(&c, keybits, key);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+}
+
 /* ------------------------------------------------------------------------ */
 /* XTS                                                                      */
 /* ------------------------------------------------------------------------ */
@@ -342,6 +372,46 @@ static int xts_unit(int keybits, const uint8_t *keys, const uint8_t *tweak,
         xex_block(&k1, encrypt, encrypt ? T : Tn, first, cc);
         for (i = 0; i < 16; ++i) pp[i] = i < r ? x[16 + i] : cc[i];
         for (i = 0; i < r; ++i) first[i] = cc[i];       /* keep before y is written */
+        xex_block(&k1, encrypt, encrypt ? Tn : T, pp, y);
+        memcpy(y + 16, first, r);
+    }
+    return ORACLE_SUCCESS;
+}
+
+/* A block range of one data unit: the blocks [first_block, first_block + len/16) of the chain of
+ * micro_aes.c:1030-1036, entered by doubling T_0 first_block times (the reference has no such entry
+ * point; this IS its loop started late).  A ragged len steals like the end of a unit. */
+int oracle_xts_range(int keybits, const uint8_t *keys, const uint8_t *tweak, uint64_t first_block,
+                     const void *in, size_t len, void *out, int encrypt)
+{
+    const int keysize = keybits / 8;
+    const uint8_t *x = (const uint8_t *)in;
+    uint8_t *y = (uint8_t *)out;
+    aes_ctx k1, k2;
+    uint8_t T[16] = {0};
+    size_t r = len % 16, n;
+    uint64_t j;
+
+    if (len < 16) return ORACLE_DATALENGTH_ERROR;
+    n = len / 16 - (r > 0);
+    if (tweak) memcpy(T, tweak, 16);
+    key_setup(&k2, keybits, keys + keysize);
+    key_setup(&k1, keybits, keys);
+    encrypt_block(&k2, T, T);
+    for (j = 0; j < first_block; ++j) oracle_xts_double(T);
+    for (; n--; x += 16, y += 16) {
+        xex_block(&k1, encrypt, T, x, y);
+        oracle_xts_double(T);
+    }
+    if (r) {
+        uint8_t Tn[16], first[16], cc[16], pp[16];
+        size_t i;
+        memcpy(Tn, T, 16);
+        oracle_xts_double(Tn);
+        memcpy(first, x, 16);
+        xex_block(&k1, encrypt, encrypt ? T : Tn, first, cc);
+        for (i = 0; i < 16; ++i) pp[i] = i < r ? x[16 + i] : cc[i];
+        for (i = 0; i < r; ++i) first[i] = cc[i];
         xex_block(&k1, encrypt, encrypt ? Tn : T, pp, y);
         memcpy(y + 16, first, r);
     }
@@ -464,6 +534,50 @@ void oracle_gcm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12]
     oracle_ghash(H, aad, aadlen, out, len, g);
     xor16(g, ekj0);
     memcpy((uint8_t *)out + len, g, 16);
+}
+
+/* micro_aes.c:1140-1152 with any GCM_NONCE_LEN: 12 bytes -> nonce || 00000001, otherwise
+ * J0 = GHASH_H({}, nonce) (:1145-1149) */
+static void gcm_setup_ex(aes_ctx *c, int keybits, const uint8_t *key, const uint8_t *nonce, size_t noncelen,
+                         uint8_t H[16], uint8_t j0[16])
+{
+    if (noncelen == 12) { gcm_setup(c, keybits, key, nonce, H, j0); return; }
+    key_setup(c, keybits, key);
+    memset(H, 0, 16);
+    encrypt_block(c, H, H);
+    oracle_ghash(H, NULL, 0, nonce, noncelen, j0);
+}
+
+/* micro_aes.c:1164-1179 with GCM_NONCE_LEN = noncelen, GCM_TAG_LEN = taglen: out holds len + taglen */
+void oracle_gcm_encrypt_ex(int keybits, const uint8_t *key, const uint8_t *nonce, size_t noncelen,
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
+{
+    aes_ctx c;
+    uint8_t H[16], j0[16], ctr[16], ekj0[16], g[16];
+    gcm_setup_ex(&c, keybits, key, nonce, noncelen, H, j0);
+    memcpy(ctr, j0, 16);
+    ctr_add(ctr, 1);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+    encrypt_block(&c, j0, ekj0);
+    oracle_ghash(H, aad, aadlen, out, len, g);
+    xor16(g, ekj0);
+    memcpy((uint8_t *)out + len, g, taglen);                  /* :1178 */
+}
+
+int oracle_gcm_decrypt_ex(int keybits, const uint8_t *key, const uint8_t *nonce, size_t noncelen,
+                          const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
+{
+    aes_ctx c;
+    uint8_t H[16], j0[16], ctr[16], ekj0[16], g[16];
+    gcm_setup_ex(&c, keybits, key, nonce, noncelen, H, j0);
+    oracle_ghash(H, aad, aadlen, in, len, g);
+    encrypt_block(&c, j0, ekj0);
+    xor16(g, ekj0);
+    if (memcmp(g, (const uint8_t *)in + len, taglen)) return ORACLE_AUTHENTICATION_ERROR;   /* :1204 */
+    memcpy(ctr, j0, 16);
+    ctr_add(ctr, 1);
+    ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
+    return ORACLE_SUCCESS;
 }
 
 /* micro_aes.c:1192-1212: verify first, leave `out` untouched on failure */
@@ -643,6 +757,24 @@ int oracle_cbc_encrypt(int keybits, const uint8_t *key, const uint8_t iv[16],
         xor16(last, head);
         encrypt_block(&c, last, y - 16);
         memcpy(y, head, r);
+    }
+    return ORACLE_SUCCESS;
+}
+
+/* micro_aes.c:746-782 built with CTS == 0: whole blocks only (:757-759), plain chain */
+int oracle_cbc_decrypt_nocts(int keybits, const uint8_t *key, const uint8_t iv[16],
+                             const void *in, size_t len, void *out)
+{
+    aes_ctx c;
+    const uint8_t *x = (const uint8_t *)in, *chain = iv;
+    uint8_t *y = (uint8_t *)out;
+    size_t n = len / 16;
+    if (len % 16) return ORACLE_DATALENGTH_ERROR;
+    key_setup(&c, keybits, key);
+    for (; n--; x += 16, y += 16) {
+        decrypt_block(&c, x, y);
+        xor16(y, chain);
+        chain = x;
     }
     return ORACLE_SUCCESS;
 }

@@ -46,6 +46,23 @@ int  oracle_key_expansion(int keybits, const uint8_t *key, uint8_t *roundkeys);
 void oracle_ecb_encrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out);
 int  oracle_ecb_decrypt(int keybits, const uint8_t *key, const void *in, size_t len, void *out);
 
+/* the reference's compile-time variants of this path as run-time arguments (micro_aes.h:56, 78-80,
+ * 97-110): AES_PADDING 1 / 2, PRESET_COUNTER, GCM_NONCE_LEN / GCM_TAG_LEN, CTS = 0; each is pinned on
+ * a build of the unmodified reference with the same macro (oracle/Makefile, _ref/libref128*.so) */
+void oracle_ecb_encrypt_padded(int keybits, const uint8_t *key, const void *in, size_t len, void *out,
+                               int padding);
+void oracle_ctr_crypt_block(int keybits, const uint8_t *key, const uint8_t ctr0[16],
+                            uint64_t first_block, const void *in, size_t len, void *out);
+void oracle_gcm_encrypt_ex(int keybits, const uint8_t *key, const uint8_t *nonce, size_t noncelen,
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+int  oracle_gcm_decrypt_ex(int keybits, const uint8_t *key, const uint8_t *nonce, size_t noncelen,
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+int  oracle_cbc_decrypt_nocts(int keybits, const uint8_t *key, const uint8_t iv[16],
+                              const void *in, size_t len, void *out);
+/* blocks [first_block, ...) of one XTS data unit: the chain of micro_aes.c:1030-1036 started late */
+int  oracle_xts_range(int keybits, const uint8_t *keys, const uint8_t *tweak, uint64_t first_block,
+                      const void *in, size_t len, void *out, int encrypt);
+
 /* CTR, 12-byte IV, counter starts at 1, 56-bit big-endian carry (micro_aes.c:919-976).
  * first_block skips that many keystream blocks (counter-range extension). */
 void oracle_ctr_crypt(int keybits, const uint8_t *key, const uint8_t iv[12],

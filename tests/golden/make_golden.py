@@ -139,6 +139,96 @@ def parse_gcm(path, keybits):
     return cases
 
 
+def parse_gcm_variants(path, keybits, per_group=2):
+    """the groups of GcmEncryptExtIV*.rsp the default build skips: IVlen = 8 / 1024 bits (J0 = GHASH of
+    the nonce, micro_aes.c:1145-1149) and Taglen < 128 (truncated tag, micro_aes.c:1178); the first and
+    last case of every [Keylen, IVlen, PTlen, AADlen, Taglen] group"""
+    groups, cur, hdr = [], {}, {}
+    for line in open(path):
+        line = line.strip()
+        m = re.match(r"\[(\w+) = (\d+)\]", line)
+        if m:
+            if m.group(1) == "Keylen":
+                groups.append([])
+            hdr[m.group(1)] = int(m.group(2))
+        elif " = " in line or line.endswith(" ="):
+            k, _, v = line.partition(" =")
+            cur[k.strip()] = v.strip()
+            if "Tag" in cur:
+                if hdr["Keylen"] == keybits and (hdr["IVlen"] != 96 or hdr["Taglen"] != 128):
+                    groups[-1].append({"key": cur["Key"], "iv": cur["IV"], "pt": cur["PT"],
+                                       "aad": cur["AAD"], "ct": cur["CT"], "tag": cur["Tag"]})
+                cur = {}
+    cases = []
+    for g in groups:
+        pick = g[:1] + (g[-1:] if len(g) > 1 and per_group > 1 else [])
+        cases += pick
+    return cases
+
+
+def variant_samples():
+    """outputs of the unmodified reference BUILT WITH ITS OTHER COMPILE-TIME SETTINGS
+    (oracle/_ref/libref128{pc,iv1,iv128,tag12,pad1,pad2,cts0}.so, see oracle/Makefile) on seeded inputs"""
+    L = lambda v: ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", f"libref128{v}.so"))
+    sha = lambda b: hashlib.sha256(b).hexdigest()
+    out = {"source": "oracle/_ref/libref128<variant>.so = unmodified micro_aes.c with one edited header line each",
+           "ctr_preset_counter": [], "gcm_nonce": [], "gcm_tag12": [], "ecb_padding": [], "cbc_nocts": []}
+    pc = L("pc")
+    for n in (0, 1, 16, 57, 4096 + 5, 1 << 18):
+        key, ctr, pt = rnd(f"vpk{n}", 16), rnd(f"vpc{n}", 16), rnd(f"vpp{n}", n)
+        ct = ctypes.create_string_buffer(n + 16)
+        pc.AES_CTR_encrypt(key, ctr, pt, ctypes.c_size_t(n), ct)
+        out["ctr_preset_counter"].append({"n": n, "key": key.hex(), "counter0": ctr.hex(), "pt_tag": f"vpp{n}",
+                                          "ct_sha256": sha(ct.raw[:n])})
+    for v, ivlen in (("iv1", 1), ("iv128", 128)):
+        lib = L(v)
+        lib.AES_GCM_decrypt.restype = ctypes.c_char
+        for n, a in ((0, 0), (1, 0), (16, 16), (57, 31), (4096 + 3, 129), (1 << 18, 7)):
+            key, nonce = rnd(f"vgk{v}{n}", 16), rnd(f"vgn{v}{n}", ivlen)
+            aad, pt = rnd(f"vga{v}{n}", a), rnd(f"vgp{v}{n}", n)
+            ct = ctypes.create_string_buffer(n + 16)
+            lib.AES_GCM_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            back = ctypes.create_string_buffer(n + 16)
+            assert ord(lib.AES_GCM_decrypt(key, nonce, aad, ctypes.c_size_t(a), ct, ctypes.c_size_t(n), back)) == 0
+            assert back.raw[:n] == pt
+            out["gcm_nonce"].append({"noncelen": ivlen, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                                     "aad_tag": f"vga{v}{n}", "pt_tag": f"vgp{v}{n}",
+                                     "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 16].hex()})
+    t12 = L("tag12")
+    t12.AES_GCM_decrypt.restype = ctypes.c_char
+    for n, a in ((0, 0), (1, 5), (57, 31), (4096 + 3, 129)):
+        key, nonce = rnd(f"vtk{n}", 16), rnd(f"vtn{n}", 12)
+        aad, pt = rnd(f"vta{n}", a), rnd(f"vtp{n}", n)
+        ct = ctypes.create_string_buffer(b"\xee" * (n + 16), n + 16)
+        t12.AES_GCM_encrypt(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+        assert ct.raw[n + 12:n + 16] == b"\xee" * 4          # only 12 tag bytes are written
+        bad = bytearray(ct.raw[:n + 12]); bad[-1] ^= 1
+        rc_bad = ord(t12.AES_GCM_decrypt(key, nonce, aad, ctypes.c_size_t(a), bytes(bad), ctypes.c_size_t(n),
+                                         ctypes.create_string_buffer(n + 16)))
+        out["gcm_tag12"].append({"n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(), "aad_tag": f"vta{n}",
+                                 "pt_tag": f"vtp{n}", "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 12].hex(),
+                                 "rc_forged": rc_bad})
+    for v, mode in (("pad1", 1), ("pad2", 2)):
+        lib = L(v)
+        for n in (0, 1, 15, 16, 17, 32, 57, 4096, 4096 + 7):
+            key, pt = rnd(f"vek{v}{n}", 16), rnd(f"vep{v}{n}", n)
+            m = (n // 16 + 1) * 16
+            ct = ctypes.create_string_buffer(b"\xee" * (m + 16), m + 16)
+            lib.AES_ECB_encrypt(key, pt, ctypes.c_size_t(n), ct)
+            assert ct.raw[m:m + 16] == b"\xee" * 16
+            out["ecb_padding"].append({"padding": mode, "n": n, "key": key.hex(), "pt_tag": f"vep{v}{n}",
+                                       "ct_sha256": sha(ct.raw[:m])})
+    c0 = L("cts0")
+    c0.AES_CBC_decrypt.restype = ctypes.c_char
+    for n in (0, 15, 16, 17, 32, 48, 57, 4096, 1 << 18):
+        key, iv, ct = rnd(f"vck{n}", 16), rnd(f"vci{n}", 16), rnd(f"vcc{n}", n)
+        o = ctypes.create_string_buffer(n + 16)
+        rc = ord(c0.AES_CBC_decrypt(key, iv, ct, ctypes.c_size_t(n), o))
+        out["cbc_nocts"].append({"n": n, "key": key.hex(), "iv": iv.hex(), "ct_tag": f"vcc{n}", "rc": rc,
+                                 "pt_sha256": sha(o.raw[:n]) if rc == 0 else None})
+    return out
+
+
 def parse_gcmsiv(path, keybits):
     """testvectors/SIV_GCM_ACVP.tv, kept when the key has the build's size
     (aes_testvectors_GCMSIV.h:84)"""
@@ -412,6 +502,15 @@ def main():
     w("eax128.json", {"source": "testvectors/EAX_AES128.tv, filter of aes_testvectors_EAX.h:83", "cases": c})
     print(f"eax128: {len(c)} cases")
     w("oracle_ref_samples_row4.json", row4_samples())
+    import gzip
+    allv = {"source": "testvectors/GcmEncryptExtIV{128,192,256}.rsp: the groups with IVlen != 96 or Taglen != 128 "
+                      "(GCM_NONCE_LEN / GCM_TAG_LEN variants, micro_aes.c:1145-1149, 1178), first and last case of each group"}
+    for bits in (128, 192, 256):
+        allv[str(bits)] = parse_gcm_variants(os.path.join(tv, f"GcmEncryptExtIV{bits}.rsp"), bits)
+        print(f"gcm variants {bits}: {len(allv[str(bits)])} cases")
+    with gzip.GzipFile(os.path.join(HERE, "gcm_variants.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(allv, separators=(",", ":")).encode())
+    w("oracle_ref_variant_samples.json", variant_samples())
     print("ok")
 
 

@@ -137,6 +137,26 @@ def test_xts256_16gib_sectors(uaes, orc, torch):
     uaes.xts_unit(256, keys, tw, src, m, dst, True)
     head = orc.xts(keys, tw, orc.splitmix(seed, 0, (1 << 20) // 8))[1]
     assert host(dst, 0, 1 << 20) == head
+    # far offsets against the oracle: a wrong entry of the jump-ahead ladder
+    # x^(128 * 2^i) above bit 18 of the block index would survive a round trip but not this.  The oracle
+    # walks the reference's own chain T_(j+1) = alpha * T_j (micro_aes.c:1030-1036) from T_0 to the window.
+    nblk = m // 16
+    for k in (1 << 20, (1 << 20) - 1, 1 << 24, (1 << 24) + 12345, (1 << 25) + (1 << 22) + 7, (1 << 26) - 4096, nblk - 4096):
+        pt = orc.splitmix(seed, k * 2, 4096 * 2)
+        assert host(dst, 16 * k, 16 * (k + 4096)) == orc.xts_range(keys, tw, k, pt)[1], k
+    # the last blocks with the stolen pair (micro_aes.c:1037-1053): window [nblk - 64, end)
+    k = nblk - 64
+    tail = orc.splitmix(seed, k * 2, (m - 16 * k + 7) // 8)[:m - 16 * k]
+    assert host(dst, 16 * k, m) == orc.xts_range(keys, tw, k, tail)[1]
+    whole = uaes.xor_fold64(dst, GIB // 8)
+    # the same unit as 3 ranges (the multi-GPU / staged decomposition, uaes_xts_crypt_range) == one call
+    tmp = torch.zeros(GIB + 4096, dtype=torch.uint8, device="cuda")
+    cut1, cut2 = 16 * ((1 << 24) + 1000), 16 * ((1 << 25) + (1 << 23))
+    for a, b in ((cut2, m), (0, cut1), (cut1, cut2)):
+        uaes.xts_crypt_range(256, keys, tw, a // 16, src[a:], b - a, tmp[a:], True)
+    assert uaes.xor_fold64(tmp, GIB // 8) == whole and torch.equal(tmp[GIB - 4096:m], dst[GIB - 4096:m])
+    assert torch.equal(tmp[cut1 - 4096:cut1 + 4096], dst[cut1 - 4096:cut1 + 4096])
+    del tmp
     uaes.xts_unit(256, keys, tw, dst, m, dst, False)
     assert torch.equal(dst[:m], src[:m])
 
@@ -183,3 +203,62 @@ def test_gcm128_4gib_tag(uaes, orc, torch):
     dst[n // 2 + 5] ^= 4
     assert uaes.gcm_decrypt(128, key, nonce, aad, dst, n, out) == 0
     assert torch.equal(out, src)
+
+
+def test_ctr128_4gib_pageable_host_buffer(uaes, orc, torch):
+    """what a drop-in caller really passes: a malloc'd (pageable) 4 GiB buffer, in place (VERDICT r1,
+    weak #4).  Every byte against the device-resident result (same kernels, no staging), oracle
+    windows at both ends and around staging-chunk borders."""
+    n, seed = 4 * GIB + 16 * 3 + 5, 0x5EED0007
+    key, iv = rnd("pg-key", 16), rnd("pg-iv", 12)
+    src = torch.empty(n + 11, dtype=torch.uint8, device="cuda")
+    uaes.fill_splitmix64(seed, 0, src, (n + 11) // 8)
+    import numpy as np
+    hostbuf = np.empty(n + 64, dtype=np.uint8)                      # pageable
+    hostbuf[:n] = src[:n].cpu().numpy()
+    hostbuf[n:] = 0xCC
+    uaes.ctr_crypt_range(128, key, iv, 0, hostbuf.ctypes.data, n, hostbuf.ctypes.data)
+    assert uaes.core().uaes_last_error() == 0
+    assert hostbuf[n:].tobytes() == b"\xcc" * 64
+    dst = torch.empty(n + 11, dtype=torch.uint8, device="cuda")
+    uaes.ctr_crypt_range(128, key, iv, 0, src, n, dst)
+    got = torch.from_numpy(hostbuf[:n])
+    step = 1 << 30
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        assert torch.equal(got[a:b].cuda(), dst[a:b]), a
+    chunk = 64 << 20
+    for off in windows(n - 5, extra=(chunk, 2 * chunk, 37 * chunk, n - 65536), count=4, tag="pg"):
+        pt = orc.splitmix(seed, off // 8, 65536 // 8)
+        assert hostbuf[off:off + 65536].tobytes() == orc.ctr(key, iv, pt, first_block=off // 16), off
+
+
+def test_gcm128_4gib_host_buffer_pipelined(uaes, orc, torch):
+    """BASELINE config 4 through the reference-facing call on a HOST buffer: the message runs through
+    the chunk pipeline as 64 shards; the tag must equal the one-launch device result (itself checked
+    against the oracle's GHASH in test_gcm128_4gib_tag)"""
+    n, seed = 4 * GIB, 0x5EED0005
+    key, nonce, aad = rnd("c5-key", 16), rnd("c5-nonce", 12), rnd("c5-aad", 20)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    uaes.fill_splitmix64(seed, 0, src, n // 8)
+    uaes.gcm_encrypt(128, key, nonce, aad, src, n, dst)
+    h = torch.empty(n + 16, dtype=torch.uint8, pin_memory=True)
+    h[:n].copy_(src)
+    shim = uaes.shim(128)
+    shim.AES_GCM_encrypt(key, nonce, aad, len(aad), ctypes.c_void_p(h.data_ptr()), n, ctypes.c_void_p(h.data_ptr()))
+    assert uaes.core().uaes_last_error() == 0
+    assert bytes(h[n:].numpy()) == host(dst, n, n + 16)
+    for a in range(0, n, GIB):
+        assert torch.equal(h[a:a + GIB].cuda(), dst[a:a + GIB]), a
+    # decrypt in place: verified on the device first, then copied back
+    rc = shim.AES_GCM_decrypt(key, nonce, aad, len(aad), ctypes.c_void_p(h.data_ptr()), n, ctypes.c_void_p(h.data_ptr()))
+    assert ord(rc) == 0
+    for a in range(0, n, GIB):
+        assert torch.equal(h[a:a + GIB].cuda(), src[a:a + GIB]), a
+    # a forged tag: M_AUTHENTICATION_ERROR and the caller's buffer keeps the ciphertext
+    shim.AES_GCM_encrypt(key, nonce, aad, len(aad), ctypes.c_void_p(h.data_ptr()), n, ctypes.c_void_p(h.data_ptr()))
+    h[n + 3] ^= 1
+    rc = shim.AES_GCM_decrypt(key, nonce, aad, len(aad), ctypes.c_void_p(h.data_ptr()), n, ctypes.c_void_p(h.data_ptr()))
+    assert ord(rc) == 0x1A
+    assert torch.equal(h[:GIB].cuda(), dst[:GIB]) and torch.equal(h[n - GIB:n].cuda(), dst[n - GIB:n])

@@ -354,3 +354,98 @@ def test_live_reference_gcm_auth_failure(orc):
     enc[5] ^= 0x40
     assert ref.gcm_decrypt(key, nonce, aad, bytes(enc))[0] == 0x1A
     assert orc.gcm_decrypt(key, nonce, aad, bytes(enc))[0] == 0x1A
+
+
+# ---------------------------------------------------------------- compile-time variants (row b2)
+
+def _gcm_variant_cases():
+    import gzip
+    import json
+    import os
+    from util import GOLDEN
+    with gzip.open(os.path.join(GOLDEN, "gcm_variants.json.gz")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_gcm_rsp_other_nonce_and_tag_lengths(orc, bits):
+    """the groups of GcmEncryptExtIV*.rsp the default build skips: 1-byte and 128-byte IVs (J0 = GHASH of
+    the nonce, micro_aes.c:1145-1149), tags of 4..15 bytes (micro_aes.c:1178)"""
+    cases = _gcm_variant_cases()[str(bits)]
+    assert len(cases) == 1000
+    seen = set()
+    for c in cases:
+        key, iv, pt, aad, tag = H(c["key"]), H(c["iv"]), H(c["pt"]), H(c["aad"]), H(c["tag"])
+        seen.add((len(iv), len(tag)))
+        out = orc.gcm_encrypt_ex(key, iv, aad, pt, taglen=len(tag))
+        assert out == H(c["ct"]) + tag, c
+        assert orc.gcm_decrypt_ex(key, iv, aad, out, taglen=len(tag)) == (0, pt)
+    assert {l for l, _ in seen} == {1, 12, 128} and {t for _, t in seen} == {4, 8, 12, 13, 14, 15, 16}
+
+
+def test_variant_recorded_reference_outputs(orc):
+    v = golden("oracle_ref_variant_samples.json")
+    for c in v["ctr_preset_counter"]:
+        pt = rnd(c["pt_tag"], c["n"])
+        assert sha256(orc.ctr_block(H(c["key"]), H(c["counter0"]), pt)) == c["ct_sha256"], c
+    for c in v["gcm_nonce"]:
+        aad, pt = rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"])
+        out = orc.gcm_encrypt_ex(H(c["key"]), H(c["nonce"]), aad, pt)
+        assert sha256(out[:c["n"]]) == c["ct_sha256"] and out[c["n"]:].hex() == c["tag"], c
+    for c in v["gcm_tag12"]:
+        aad, pt = rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"])
+        out = orc.gcm_encrypt_ex(H(c["key"]), H(c["nonce"]), aad, pt, taglen=12)
+        assert len(out) == c["n"] + 12 and sha256(out[:c["n"]]) == c["ct_sha256"] and out[c["n"]:].hex() == c["tag"], c
+        bad = bytearray(out); bad[-1] ^= 1
+        assert orc.gcm_decrypt_ex(H(c["key"]), H(c["nonce"]), aad, bytes(bad), taglen=12)[0] == c["rc_forged"] == 0x1A
+    for c in v["ecb_padding"]:
+        pt = rnd(c["pt_tag"], c["n"])
+        out = orc.ecb_encrypt_padded(H(c["key"]), pt, c["padding"])
+        assert len(out) == (c["n"] // 16 + 1) * 16 and sha256(out) == c["ct_sha256"], c
+    for c in v["cbc_nocts"]:
+        rc, out = orc.cbc_nocts(H(c["key"]), H(c["iv"]), rnd(c["ct_tag"], c["n"]))
+        assert rc == c["rc"] and (rc != 0 or sha256(out) == c["pt_sha256"]), c
+    assert [c["rc"] for c in v["cbc_nocts"]] == [0, 1, 0, 1, 0, 0, 1, 0, 0]
+
+
+def test_xts_range_equals_the_unit(orc):
+    """oracle_xts_range over pieces of a unit = oracle_xts_encrypt over the whole (incl. stealing)"""
+    keys, tw = rnd("xr-k", 64), rnd("xr-t", 16)
+    data = rnd("xr-d", 16 * 300 + 9)
+    rc, whole = orc.xts(keys, tw, data)
+    cut = 16 * 117
+    a = orc.xts_range(keys, tw, 0, data[:cut])[1]
+    b = orc.xts_range(keys, tw, 117, data[cut:])[1]
+    assert rc == 0 and a + b == whole
+    assert orc.xts_range(keys, tw, 117, b, encrypt=False)[1] == data[cut:]
+
+
+@pytest.mark.skipif(not Reference.available(128, variant="iv1"), reason="oracle/_ref variants not built")
+def test_live_reference_variants(orc):
+    for v, ivlen in (("iv1", 1), ("iv128", 128)):
+        ref = Reference(128, variant=v)
+        for i, n in enumerate([0, 1, 16, 33, 1000, 70001]):
+            key, iv, aad, pt = rnd(f"lvk{v}{i}", 16), rnd(f"lvn{v}{i}", ivlen), rnd(f"lva{v}{i}", (11 * i) % 40), rnd(f"lvp{v}{i}", n)
+            enc = ref.gcm_encrypt_v(key, iv, aad, pt)
+            assert orc.gcm_encrypt_ex(key, iv, aad, pt) == enc
+            assert orc.gcm_decrypt_ex(key, iv, aad, enc) == ref.gcm_decrypt_v(key, iv, aad, enc) == (0, pt)
+    ref = Reference(128, variant="tag12")
+    for i, n in enumerate([0, 5, 64, 4099]):
+        key, iv, aad, pt = rnd(f"ltk{i}", 16), rnd(f"ltn{i}", 12), rnd(f"lta{i}", 3 * i), rnd(f"ltp{i}", n)
+        enc = ref.gcm_encrypt_v(key, iv, aad, pt, taglen=12)
+        assert orc.gcm_encrypt_ex(key, iv, aad, pt, taglen=12) == enc
+        assert orc.gcm_decrypt_ex(key, iv, aad, enc, taglen=12) == ref.gcm_decrypt_v(key, iv, aad, enc, taglen=12) == (0, pt)
+    for mode in (1, 2):
+        ref = Reference(128, variant=f"pad{mode}")
+        for i, n in enumerate([0, 1, 15, 16, 31, 32, 1000]):
+            key, pt = rnd(f"lpk{i}", 16), rnd(f"lpp{i}", n)
+            assert orc.ecb_encrypt_padded(key, pt, mode) == ref.ecb_encrypt_padded(key, pt)
+    ref = Reference(128, variant="cts0")
+    for i, n in enumerate([0, 16, 17, 160, 4096]):
+        key, iv, ct = rnd(f"lck{i}", 16), rnd(f"lci{i}", 16), rnd(f"lcc{i}", n)
+        rc, out = ref.cbc(key, iv, ct)
+        assert orc.cbc_nocts(key, iv, ct)[0] == rc and (rc or orc.cbc_nocts(key, iv, ct)[1] == out)
+    ref = Reference(128, preset_counter=True)
+    for i, n in enumerate([0, 1, 16, 100, 4099]):
+        key, ctr, pt = rnd(f"lbk{i}", 16), rnd(f"lbc{i}", 16), rnd(f"lbp{i}", n)
+        assert orc.ctr_block(key, ctr, pt) == ref.ctr(key, ctr, pt)

@@ -67,6 +67,13 @@ class Oracle:
         for f in (L.oracle_cbc_decrypt, L.oracle_cbc_encrypt, L.oracle_cfb_decrypt, L.oracle_cfb_encrypt):
             f.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
         L.oracle_fill_splitmix64.argtypes = [_u64, _u64, ctypes.c_void_p, _sz]
+        # compile-time variants of the reference as run-time arguments
+        L.oracle_ecb_encrypt_padded.argtypes = [_int, _u8p, _u8p, _sz, _u8p, _int]
+        L.oracle_ctr_crypt_block.argtypes = [_int, _u8p, _u8p, _u64, _u8p, _sz, _u8p]
+        L.oracle_gcm_encrypt_ex.argtypes = [_int, _u8p, _u8p, _sz, _u8p, _sz, _u8p, _sz, _u8p, _sz]
+        L.oracle_gcm_decrypt_ex.argtypes = [_int, _u8p, _u8p, _sz, _u8p, _sz, _u8p, _sz, _u8p, _sz]
+        L.oracle_cbc_decrypt_nocts.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
+        L.oracle_xts_range.argtypes = [_int, _u8p, _u8p, _u64, _u8p, _sz, _u8p, _int]
 
     @staticmethod
     def _buf(n):
@@ -107,6 +114,39 @@ class Oracle:
         o = self._buf(len(data))
         f = self.lib.oracle_xts_encrypt if encrypt else self.lib.oracle_xts_decrypt
         rc = f(len(keys) * 4, keys, tweak, data, len(data), o)
+        return rc, o.raw[:len(data)]
+
+    def ecb_encrypt_padded(self, key, pt, padding):
+        m = (len(pt) // 16 + 1) * 16 if padding else (len(pt) + 15) // 16 * 16
+        o = self._buf(m)
+        self.lib.oracle_ecb_encrypt_padded(len(key) * 8, key, pt, len(pt), o, padding)
+        return o.raw[:m]
+
+    def ctr_block(self, key, ctr16, data, first_block=0):
+        o = self._buf(len(data))
+        self.lib.oracle_ctr_crypt_block(len(key) * 8, key, ctr16, first_block, data, len(data), o)
+        return o.raw[:len(data)]
+
+    def gcm_encrypt_ex(self, key, nonce, aad, pt, taglen=16):
+        o = self._buf(len(pt) + 16)
+        self.lib.oracle_gcm_encrypt_ex(len(key) * 8, key, nonce, len(nonce), aad, len(aad), pt, len(pt), o, taglen)
+        return o.raw[:len(pt) + taglen]
+
+    def gcm_decrypt_ex(self, key, nonce, aad, ct_and_tag, taglen=16):
+        n = len(ct_and_tag) - taglen
+        o = self._buf(n)
+        rc = self.lib.oracle_gcm_decrypt_ex(len(key) * 8, key, nonce, len(nonce), aad, len(aad), ct_and_tag, n, o, taglen)
+        return rc, o.raw[:n]
+
+    def cbc_nocts(self, key, iv, data):
+        o = self._buf(len(data))
+        rc = self.lib.oracle_cbc_decrypt_nocts(len(key) * 8, key, iv, data, len(data), o)
+        return rc, o.raw[:len(data)]
+
+    def xts_range(self, keys, tweak, first_block, data, encrypt=True):
+        """blocks [first_block, ...) of one data unit; walks the tweak chain from T_0 (slow for far offsets)"""
+        o = self._buf(len(data))
+        rc = self.lib.oracle_xts_range(len(keys) * 4, keys, tweak, first_block, data, len(data), o, 1 if encrypt else 0)
         return rc, o.raw[:len(data)]
 
     def xts_sectors(self, keys, first_sector, sector_bytes, data, encrypt=True):
@@ -239,8 +279,8 @@ class Reference:
     """ctypes binding of oracle/_ref/libref<bits>.so: the UNMODIFIED micro_aes.c.  The key
     length is baked into each library (AES___, micro_aes.h:17)."""
 
-    def __init__(self, bits, preset_counter=False):
-        name = f"libref{bits}{'pc' if preset_counter else ''}.so"
+    def __init__(self, bits, preset_counter=False, variant=""):
+        name = f"libref{bits}{'pc' if preset_counter else variant}.so"
         self.path = os.path.join(ROOT, "oracle", "_ref", name)
         self.bits = bits
         self.lib = ctypes.CDLL(self.path)
@@ -250,9 +290,27 @@ class Reference:
             getattr(self.lib, f).restype = ctypes.c_char
 
     @staticmethod
-    def available(bits=128, preset_counter=False):
+    def available(bits=128, preset_counter=False, variant=""):
         return os.path.exists(os.path.join(ROOT, "oracle", "_ref",
-                                           f"libref{bits}{'pc' if preset_counter else ''}.so"))
+                                           f"libref{bits}{'pc' if preset_counter else variant}.so"))
+
+    # ---- builds with other compile-time settings (variant = "iv1", "iv128", "tag12", "pad1", "pad2", "cts0")
+    def gcm_encrypt_v(self, key, nonce, aad, pt, taglen=16):
+        o = ctypes.create_string_buffer(len(pt) + 16)
+        self.lib.AES_GCM_encrypt(key, nonce, aad, _sz(len(aad)), pt, _sz(len(pt)), o)
+        return o.raw[:len(pt) + taglen]
+
+    def gcm_decrypt_v(self, key, nonce, aad, ct_and_tag, taglen=16):
+        n = len(ct_and_tag) - taglen
+        o = ctypes.create_string_buffer(b"\xcc" * (n + 16), n + 16)
+        rc = self.lib.AES_GCM_decrypt(key, nonce, aad, _sz(len(aad)), ct_and_tag, _sz(n), o)
+        return ord(rc), o.raw[:n]
+
+    def ecb_encrypt_padded(self, key, pt):
+        m = (len(pt) // 16 + 1) * 16
+        o = ctypes.create_string_buffer(m + 16)
+        self.lib.AES_ECB_encrypt(key, pt, _sz(len(pt)), o)
+        return o.raw[:m]
 
     def ecb_encrypt(self, key, pt):
         m = (len(pt) + 15) // 16 * 16
