@@ -103,6 +103,7 @@ struct CtrArgs {
     uint64_t q_u0;               // counter (not reduced mod 2^56) where unit 0 starts: v0 rounded down to a unit
     uint64_t q_units;            // units covering [v0, v0 + nblocks)
     uint32_t q_bs_on;            // 0: the bitsliced warps take no work (short calls)
+    uint32_t q_zero;             // 0 (see q_post)
     BsKeyPlanes bs;
 };
 
@@ -350,21 +351,33 @@ constexpr int kQUnitShift = UAES_Q_UNIT_SHIFT;
 constexpr uint64_t kQUnit = 1ull << kQUnitShift;
 constexpr uint64_t kQNone = ~0ull;
 
-// front claim (table-driven): returns the unit or kQNone; all lanes get the same answer
-__device__ __forceinline__ uint64_t q_claim_front(unsigned long long *q, uint64_t units)
+// A claim is split in two so that nobody waits for the atomic: q_post() issues it from lane 0 (the
+// result is not touched), q_front() / q_back() broadcast and decode it a unit later.
+__device__ __forceinline__ unsigned long long q_post(unsigned long long *q, unsigned long long inc, uint32_t zero)
 {
+    // ptxas turns an atomic on a warp-uniform address into its aggregated form (VOTE, POPC, ATOMG,
+    // SHFL), whose shuffle reads the result straight away.  An address it cannot prove uniform
+    // (q + 0 * %laneid, the zero being a kernel argument) keeps the plain ATOMG, issued and left alone.
     unsigned long long old = 0;
-    if ((threadIdx.x & 31) == 0) old = atomicAdd(q, 1ull);
-    old = __shfl_sync(0xffffffffu, old, 0);
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t lid;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lid));
+        asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(q + zero * lid), "l"(inc) : "memory");
+    }
+    return old;
+}
+
+// front claim (table-driven): the unit or kQNone; all lanes get the same answer
+__device__ __forceinline__ uint64_t q_front(unsigned long long posted, uint64_t units)
+{
+    const unsigned long long old = __shfl_sync(0xffffffffu, posted, 0);
     const uint64_t f = old & 0xffffffffull, b = old >> 32;
     return f + b < units ? f : kQNone;
 }
 
-__device__ __forceinline__ uint64_t q_claim_back(unsigned long long *q, uint64_t units)
+__device__ __forceinline__ uint64_t q_back(unsigned long long posted, uint64_t units)
 {
-    unsigned long long old = 0;
-    if ((threadIdx.x & 31) == 0) old = atomicAdd(q, 1ull << 32);
-    old = __shfl_sync(0xffffffffu, old, 0);
+    const unsigned long long old = __shfl_sync(0xffffffffu, posted, 0);
     const uint64_t f = old & 0xffffffffull, b = old >> 32;
     return f + b < units ? units - 1 - b : kQNone;
 }
@@ -394,14 +407,15 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
         if (!a.q_bs_on) return;
         uint32_t *um = (uint32_t *)(dyn + off);
         uint64_t tag16 = ~0ull, done = 0;
-        for (;;) {
-            const uint64_t u = q_claim_back(a.q, a.q_units);
-            if (u == kQNone) break;
+        uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.q_units);
+        while (u != kQNone) {
+            const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);      // the next unit, a unit ahead
             const uint64_t c0 = a.q_u0 + (u << kQUnitShift);
 #pragma unroll 1
             for (uint32_t p = 0; p < (uint32_t)(kQUnit >> 10); ++p)
                 ctr_bs_pass<NR, UAES_BS_BATCH>(a, lb, um, c0 + ((uint64_t)p << 10), tag16);
             ++done;
+            u = q_back(posted, a.q_units);
         }
         if (lane == 0 && done) atomicAdd(a.q + 2, (unsigned long long)done);
         return;
@@ -425,17 +439,21 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
     uint32_t U[4][4], K0 = 0, Cp1 = 0, E0 = 0, E1 = 0, E2 = 0, E3 = 0;
     const uint32_t s0 = a.w0 ^ rk[0], s1 = a.w1 ^ rk[1];
 
-    uint64_t ucur = q_claim_front(a.q, a.q_units);
+    uint64_t ucur = q_front(q_post(a.q, 1ull, a.q_zero), a.q_units);
     uint4 cur[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; ++i) cur[i] = fetch(ucur != kQNone, Gfirst + ucur * kGroupsPerUnit, (uint32_t)i);
     while (ucur != kQNone) {
-        const uint64_t unext = q_claim_front(a.q, a.q_units);          // a unit ahead: its latency hides behind this unit
+        // the next unit is claimed a unit ahead: the atomic is issued here, its answer is read when the
+        // second half starts, the first loads of that unit go out with the last rows of this one
+        const unsigned long long posted = q_post(a.q, 1ull, a.q_zero);
+        uint64_t unext = kQNone;
         const uint64_t Gu = Gfirst + ucur * kGroupsPerUnit;
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
             const uint32_t b15 = half * 128 + lane;                   // + 32 * it
             bool fresh = true;                                        // U belongs to (K0, half)
+            if (half) unext = q_front(posted, a.q_units);
 #pragma unroll 1
             for (uint32_t jj = 0; jj < kGroupsPerUnit; ++jj) {
                 const uint64_t G = Gu + jj;
@@ -472,19 +490,20 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
                 const uint32_t C1 = Cp1 ^ lut<2, kOffT2>(lb, s3);
                 const uint32_t D0 = E0 ^ lut<1, kOffT1>(lb, C1), D1 = E1 ^ lut<0, kOffT0>(lb, C1);
                 const uint32_t D2 = E2 ^ lut<3, kOffT3>(lb, C1), D3 = E3 ^ lut<2, kOffT2>(lb, C1);
+                // where this warp's rows continue after the group (warp-uniform selects, no branches): the next
+                // group of this half; the first group of the other half; the first group of the unit claimed ahead
                 const bool last_group = jj + 1 == kGroupsPerUnit;
+                const uint64_t Gn = !last_group ? G + 1 : half == 0 ? Gu : Gfirst + unext * kGroupsPerUnit;
+                const uint32_t rn = !last_group ? 4 * half : half == 0 ? 4u : 0u;
+                const bool okn = !last_group || half == 0 || unext != kQNone;
 #pragma unroll
                 for (int it = 0; it < 4; it += ILP) {
                     uint4 nxt[ILP];
                     uint32_t t[ILP][4];
 #pragma unroll
                     for (int i = 0; i < ILP; ++i) {
-                        // the rows after these: same group; next group of this half; first group of the
-                        // other half; first group of the unit claimed ahead
-                        if (it + ILP < 4)      nxt[i] = fetch(true, G, 4 * half + it + ILP + i);
-                        else if (!last_group)  nxt[i] = fetch(true, G + 1, 4 * half + i);
-                        else if (half == 0)    nxt[i] = fetch(true, Gu, 4 + i);
-                        else                   nxt[i] = fetch(unext != kQNone, Gfirst + unext * kGroupsPerUnit, (uint32_t)i);
+                        if (it + ILP < 4) nxt[i] = fetch(true, G, 4 * half + it + ILP + i);
+                        else              nxt[i] = fetch(okn, Gn, rn + i);
                         t[i][0] = D0 ^ U[it + i][0]; t[i][1] = D1 ^ U[it + i][1];
                         t[i][2] = D2 ^ U[it + i][2]; t[i][3] = D3 ^ U[it + i][3];
                     }
@@ -826,7 +845,7 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     ctr_tuning_init();
     const int threads = g_ctr_threads, share = g_ctr_share;
     a.tt_blocks = a.nblocks; a.bs_u0 = 0; a.bs_passes = 0;
-    a.q = nullptr; a.q_u0 = 0; a.q_units = 0; a.q_bs_on = 0;
+    a.q = nullptr; a.q_u0 = 0; a.q_units = 0; a.q_bs_on = 0; a.q_zero = 0;
     if (threads == 386) {
         // work queue: units of kQUnit counters, aligned in counter space; both kinds of warps clip to
         // [v0, v0 + nblocks).  Short calls keep the co-runner out (a bitsliced unit takes longer than a

@@ -141,7 +141,7 @@ def test_xts256_16gib_sectors(uaes, orc, torch):
     # x^(128 * 2^i) above bit 18 of the block index would survive a round trip but not this.  The oracle
     # walks the reference's own chain T_(j+1) = alpha * T_j (micro_aes.c:1030-1036) from T_0 to the window.
     nblk = m // 16
-    for k in (1 << 20, (1 << 20) - 1, 1 << 24, (1 << 24) + 12345, (1 << 25) + (1 << 22) + 7, (1 << 26) - 4096, nblk - 4096):
+    for k in (1 << 20, (1 << 20) - 1, 1 << 24, (1 << 24) + 12345, (1 << 25) + (1 << 22) + 7, (1 << 26) - 4096, nblk - 8192):
         pt = orc.splitmix(seed, k * 2, 4096 * 2)
         assert host(dst, 16 * k, 16 * (k + 4096)) == orc.xts_range(keys, tw, k, pt)[1], k
     # the last blocks with the stolen pair (micro_aes.c:1037-1053): window [nblk - 64, end)

@@ -46,6 +46,13 @@ def orc():
     return Oracle()
 
 
+@pytest.fixture(autouse=True)
+def _fresh_error_latch(uaes):
+    """the latch keeps the most recent failure of the thread: earlier tests provoke failures on purpose"""
+    uaes.core().uaes_clear_error()
+    yield
+
+
 @pytest.fixture(scope="module")
 def torch():
     return pytest.importorskip("torch")
