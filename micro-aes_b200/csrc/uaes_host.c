@@ -20,11 +20,13 @@
  * contributions are folded at the end.  With uaes_set_devices(n) a host-buffer call is spread
  * over n GPUs, one part and one host thread per device, each under its own device's lock.
  */
+#define _POSIX_C_SOURCE 200809L      /* clock_gettime, pthread_cond_timedwait under -std=c99 */
 #include <cuda_runtime_api.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/uaes_b200.h"
 #include "uaes_launch.h"
@@ -239,6 +241,7 @@ typedef struct {
     void *hslot[MAX_SLOT];              /* pinned host chunks: bounce buffers for PAGEABLE caller memory */
     cudaStream_t st[MAX_SLOT];
     cudaEvent_t ev[MAX_SLOT];
+    cudaEvent_t rev[16]; int rev_ok[16];  /* one event per ring slot of the pageable (bounce) pipeline */
     void *big;  size_t big_bytes;       /* full-size staging (GCM decrypt, CBC/CFB, batches); trimmed after use */
     scratch pool[MAX_SCRATCH];          /* GCM / OCB / batch work areas: one block per call in flight */
 } devctx;
@@ -254,7 +257,8 @@ static size_t g_fan_min = (size_t)256 << 20;          /* ... when every device g
 static int    g_fan_oversubscribe;                    /* tests: more parts than devices (UAES_FANOUT_OVERSUBSCRIBE) */
 static int    g_burn;                                 /* wipe staging memory and scratch after each call */
 static size_t g_big_keep = (size_t)256 << 20;         /* full-size staging above this is freed after the call */
-static int    g_copy_threads = 4;                     /* helpers that move pageable memory to / from the pinned chunks */
+static int    g_copy_threads = 8;
+static int    g_in_ahead = 2;                         /* chunks of pageable input copied ahead of the GPU stage */                     /* helpers that move pageable memory to / from the pinned chunks */
 
 static void dev_locks_init(void)
 {
@@ -284,6 +288,7 @@ static void cfg_init(void)
         }
         if ((e = getenv("UAES_FANOUT_MIN_MIB")) != NULL && atoi(e) >= 1) g_fan_min = (size_t)atoi(e) << 20;
         if ((e = getenv("UAES_BURN")) != NULL) g_burn = atoi(e) != 0;
+        if ((e = getenv("UAES_IN_AHEAD")) != NULL && atoi(e) >= 1) g_in_ahead = atoi(e);
         if ((e = getenv("UAES_COPY_THREADS")) != NULL && atoi(e) >= 1 && atoi(e) <= 32) g_copy_threads = atoi(e);
         g_cfg_ready = 1;
     }
@@ -454,7 +459,8 @@ static int finish_direct(void)
  * happens on the host. */
 typedef struct { u8 *dst; const u8 *src; size_t n; int *left; } copy_piece;
 
-#define COPY_QUEUE 128
+#define COPY_QUEUE 1024
+#define COPY_PIECE ((size_t)1 << 20)
 typedef struct copy_pool {
     pthread_mutex_t m;
     pthread_cond_t work, done;
@@ -484,16 +490,14 @@ static void *copy_worker(void *arg)
     return NULL;
 }
 
-/* copy n bytes with the helper threads (shared by all devices' pipelines) and return when all of
- * it has arrived; the calling thread copies one share itself */
-static void copy_parallel(void *dst, const void *src, size_t n)
+/* queue a copy of n bytes for the helper threads (shared by all devices' pipelines) in pieces of
+ * 1 MiB; *left counts the pieces still to arrive (read it with copy_left / copy_wait) */
+static void copy_async(void *dst, const void *src, size_t n, int *left)
 {
     copy_pool *p = &g_cp;
-    int parts, i, left = 0;
-    size_t per, own;
-    if (n < ((size_t)1 << 20) || g_copy_threads <= 1) { memcpy(dst, src, n); return; }
+    size_t off;
     pthread_mutex_lock(&p->m);
-    while (p->nthreads < g_copy_threads - 1) {
+    while (p->nthreads < g_copy_threads && p->nthreads < 32) {
         pthread_attr_t at;
         pthread_attr_init(&at);
         pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
@@ -501,24 +505,41 @@ static void copy_parallel(void *dst, const void *src, size_t n)
         pthread_attr_destroy(&at);
         ++p->nthreads;
     }
-    parts = p->nthreads + 1;
-    per = ((n + (size_t)parts - 1) / (size_t)parts + 4095) & ~(size_t)4095;
-    while ((int)(p->tail - p->head) + parts > COPY_QUEUE) pthread_cond_wait(&p->done, &p->m);
-    for (i = 1; i < parts; ++i) {
-        const size_t off = per * (size_t)i;
-        copy_piece *q;
-        if (off >= n) break;
-        q = &p->q[p->tail % COPY_QUEUE];
-        q->dst = (u8 *)dst + off; q->src = (const u8 *)src + off; q->n = n - off < per ? n - off : per; q->left = &left;
-        ++p->tail; ++left;
+    if (p->nthreads == 0) {                               /* no helper could be started: copy here */
+        pthread_mutex_unlock(&p->m);
+        memcpy(dst, src, n);
+        return;
     }
-    pthread_cond_broadcast(&p->work);
+    for (off = 0; off < n; off += COPY_PIECE) {
+        copy_piece *q;
+        while (p->tail - p->head >= COPY_QUEUE) pthread_cond_wait(&p->done, &p->m);
+        q = &p->q[p->tail % COPY_QUEUE];
+        q->dst = (u8 *)dst + off; q->src = (const u8 *)src + off; q->n = n - off < COPY_PIECE ? n - off : COPY_PIECE; q->left = left;
+        ++p->tail; ++*left;
+        pthread_cond_signal(&p->work);
+    }
     pthread_mutex_unlock(&p->m);
-    own = n < per ? n : per;
-    memcpy(dst, src, own);
-    pthread_mutex_lock(&p->m);
-    while (left) pthread_cond_wait(&p->done, &p->m);
-    pthread_mutex_unlock(&p->m);
+}
+
+static int copy_left(int *left)
+{
+    int v;
+    pthread_mutex_lock(&g_cp.m);
+    v = *left;
+    pthread_mutex_unlock(&g_cp.m);
+    return v;
+}
+
+/* wait until some piece of anybody has arrived, or for 200 us at most */
+static void copy_wait_any(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    ts.tv_nsec += 200000;
+    if (ts.tv_nsec >= 1000000000L) { ts.tv_nsec -= 1000000000L; ++ts.tv_sec; }
+    pthread_mutex_lock(&g_cp.m);
+    pthread_cond_timedwait(&g_cp.done, &g_cp.m, &ts);
+    pthread_mutex_unlock(&g_cp.m);
 }
 
 /* ------------------------------------------------------------------ chunked staging pipeline */
@@ -541,7 +562,40 @@ typedef struct {
     chunk_fn fn; void *user;     /* fn may be NULL: a pure copy */
 } pipe_part;
 
-static size_t pipe_chunk_bytes(const pipe_part *p) { return CHUNK_BYTES - CHUNK_BYTES % p->unit; }
+/* Geometry of one part's pipeline.  Pinned or device memory: NSLOT chunks of CHUNK_BYTES, DMA straight
+ * from / to the caller's buffer.  Pageable memory on either side: the same device and pinned chunks
+ * are cut into a ring of smaller pieces (BOUNCE_BYTES) so that the helper threads' memcpy in, the DMA
+ * both ways, the kernel and the memcpy out of different pieces all overlap (measured on the B200 box,
+ * profiles/r2_hostmem_probe.txt: cudaMemcpy of pageable memory 10.7 / 20.1 GiB/s, cudaHostRegister
+ * 10.9 GiB/s, 8 memcpy threads 74 GiB/s). */
+#define BOUNCE_BYTES ((size_t)8 << 20)
+#define MAX_RING 16                   /* NSLOT <= 8: at least 2 pieces per chunk */
+
+static int pipe_bounces(const pipe_part *p)
+{
+    return ptr_class(p->in) == PTR_PAGEABLE || (p->out && ptr_class(p->out) == PTR_PAGEABLE);
+}
+
+static size_t pipe_chunk_bytes(const pipe_part *p)
+{
+    size_t chunk = CHUNK_BYTES - CHUNK_BYTES % p->unit;
+    if (pipe_bounces(p) && chunk > BOUNCE_BYTES && BOUNCE_BYTES >= p->unit) chunk = BOUNCE_BYTES - BOUNCE_BYTES % p->unit;
+    return chunk;
+}
+
+/* pieces per staging chunk: 1 for pinned / device memory */
+static size_t pipe_per(const pipe_part *p)
+{
+    const size_t chunk = pipe_chunk_bytes(p);
+    size_t per;
+    if (!pipe_bounces(p) || chunk == 0) return 1;
+    per = (CHUNK_BYTES + 32) / (chunk + 32);               /* 32 bytes of slack behind each piece */
+    if (per > (size_t)MAX_RING / (size_t)NSLOT) per = (size_t)MAX_RING / (size_t)NSLOT;
+    return per < 1 ? 1 : per;
+}
+
+/* ring slots (= chunks in flight, = work areas a chunk function may index with `slot`) */
+static int pipe_slots(const pipe_part *p) { return (int)(pipe_per(p) * (size_t)NSLOT); }
 
 static size_t pipe_nchunks(const pipe_part *p)
 {
@@ -553,68 +607,120 @@ static size_t pipe_nchunks(const pipe_part *p)
     return n;
 }
 
-/* Runs one part through the device's slots.  Caller holds c->lock and has made `c` current. */
+/* Runs one part through the device's ring.  Caller holds c->lock and has made `c` current.
+ * Four stages per chunk, each started as soon as its predecessor has finished and a ring slot is free:
+ *   IN   helper threads copy pageable input into the slot's pinned piece     (skipped: pinned / device input)
+ *   GPU  H2D, the mode's kernel(s), D2H, an event -- all on the slot's stream
+ *   OUT  helper threads copy the pinned piece to pageable output             (skipped: pinned / device output)
+ *   retire: the slot may be used again */
 static int run_chunked(devctx *c, const pipe_part *p)
 {
     int rc = 0, i;
-    const size_t chunk = pipe_chunk_bytes(p), nchunks = pipe_nchunks(p);
+    const size_t chunk = pipe_chunk_bytes(p), n = pipe_nchunks(p);
+    const int R = pipe_slots(p);
     const int bounce_in = ptr_class(p->in) == PTR_PAGEABLE, bounce_out = p->out && ptr_class(p->out) == PTR_PAGEABLE;
-    size_t k, off = 0;
-    size_t pend_off[MAX_SLOT], pend_bytes[MAX_SLOT];        /* bounce mode: chunks whose copy-out is due */
-    int pend[MAX_SLOT];
+    const int bounce = bounce_in || bounce_out;
+    const size_t per = pipe_per(p);                          /* ring slots per staging chunk */
+    size_t kin = 0, kgpu = 0, kout = 0, kdone = 0;
+    int in_left[MAX_RING], out_left[MAX_RING];
 
     if (chunk == 0) return fail(UAES_E_BAD_ARGUMENT, "unit larger than the staging chunk", 0);
-    if ((rc = need_slots(c, bounce_in || bounce_out)) != 0) return rc;
-    for (i = 0; i < MAX_SLOT; ++i) pend[i] = 0;
+    if ((rc = need_slots(c, bounce)) != 0) return rc;
+    for (i = 0; i < MAX_RING; ++i) in_left[i] = out_left[i] = 0;
+    if (bounce)
+        for (i = 0; i < R; ++i)
+            if (!c->rev_ok[i]) {
+                CU(cudaEventCreateWithFlags(&c->rev[i], cudaEventDisableTiming));
+                c->rev_ok[i] = 1;
+            }
 
-    for (k = 0; k < nchunks; ++k) {
-        const size_t bytes = k + 1 == nchunks ? p->len - off : chunk;
-        const size_t obytes = bytes + (k + 1 == nchunks ? p->out_extra : 0);
-        const int s = (int)(k % (size_t)NSLOT);
-        u8 *d = p->resident ? p->resident + off : (u8 *)c->slot[s];
-        /* the slot's previous chunk must have left it (and, in bounce mode, its pinned chunk) */
-        if (pend[s]) {
-            CU(cudaEventSynchronize(c->ev[s]));
-            copy_parallel(p->out + pend_off[s], c->hslot[s], pend_bytes[s]);
-            pend[s] = 0;
+#define SLOT_OF(k)   ((int)((k) % (size_t)R))
+#define DEV_OF(r)    ((u8 *)c->slot[(size_t)(r) / per] + ((size_t)(r) % per) * (chunk + 32))
+#define HOST_OF(r)   ((u8 *)c->hslot[(size_t)(r) / per] + ((size_t)(r) % per) * (chunk + 32))
+#define STREAM_OF(r) (c->st[(r) % NSLOT])
+#define OFF_OF(k)    ((k) * chunk)
+#define BYTES_OF(k)  ((k) + 1 == n ? p->len - OFF_OF(k) : chunk)
+
+    if (!bounce) {
+        /* pinned / device memory: everything is stream ordered, nothing to wait for on the host */
+        size_t k;
+        for (k = 0; k < n; ++k) {
+            const size_t off = OFF_OF(k), bytes = BYTES_OF(k), obytes = bytes + (k + 1 == n ? p->out_extra : 0);
+            const int r = SLOT_OF(k);
+            u8 *d = p->resident ? p->resident + off : (u8 *)c->slot[r];
+            CU(cudaMemcpyAsync(d, p->in + off, bytes, cudaMemcpyDefault, c->st[r]));
+            if (p->fn && (rc = p->fn(p->user, p->base + off, k, r, d, bytes, obytes, c->st[r])) != 0) goto done;
+            if (p->out) CU(cudaMemcpyAsync(p->out + off, d, obytes, cudaMemcpyDefault, c->st[r]));
+            if (g_burn && !p->resident) CU(cudaMemsetAsync(c->slot[r], 0, CHUNK_BYTES, c->st[r]));
         }
-        if (bounce_in) {
-            if (!bounce_out && k >= (size_t)NSLOT) CU(cudaStreamSynchronize(c->st[s]));   /* pinned chunk still being read */
-            copy_parallel(c->hslot[s], p->in + off, bytes);
-            CU(cudaMemcpyAsync(d, c->hslot[s], bytes, cudaMemcpyHostToDevice, c->st[s]));
-        } else {
-            CU(cudaMemcpyAsync(d, p->in + off, bytes, cudaMemcpyDefault, c->st[s]));
-        }
-        if (p->fn && (rc = p->fn(p->user, p->base + off, k, s, d, bytes, obytes, c->st[s])) != 0) goto done;
-        if (!p->out) {
-            /* resident part: the result stays on the device */
-        } else if (bounce_out) {
-            CU(cudaMemcpyAsync(c->hslot[s], d, obytes, cudaMemcpyDeviceToHost, c->st[s]));
-            CU(cudaEventRecord(c->ev[s], c->st[s]));
-            pend[s] = 1; pend_off[s] = off; pend_bytes[s] = obytes;
-        } else {
-            CU(cudaMemcpyAsync(p->out + off, d, obytes, cudaMemcpyDefault, c->st[s]));
-        }
-        if (g_burn && !p->resident) CU(cudaMemsetAsync(c->slot[s], 0, CHUNK_BYTES, c->st[s]));
-        off += bytes;
+        goto done;
     }
-    /* drain in chunk order */
-    for (k = nchunks > (size_t)NSLOT ? nchunks - (size_t)NSLOT : 0; k < nchunks; ++k) {
-        const int s = (int)(k % (size_t)NSLOT);
-        if (pend[s]) {
-            CU(cudaEventSynchronize(c->ev[s]));
-            copy_parallel(p->out + pend_off[s], c->hslot[s], pend_bytes[s]);
-            pend[s] = 0;
+
+    while (kdone < n) {
+        int progressed = 0;
+        /* IN: a ring slot must be free; pageable input is copied only a little ahead of the GPU stage, or the
+         * helpers would fill the whole ring first and the copies out (which free slots) would queue behind */
+        if (kin < n && kin - kdone < (size_t)R && (!bounce_in || kin - kgpu < (size_t)g_in_ahead)) {
+            const int r = SLOT_OF(kin);
+            if (bounce_in) copy_async(HOST_OF(r), p->in + OFF_OF(kin), BYTES_OF(kin), &in_left[r]);
+            ++kin; progressed = 1;
+        }
+        if (kgpu < kin && (!bounce_in || copy_left(&in_left[SLOT_OF(kgpu)]) == 0)) {      /* GPU */
+            const size_t k = kgpu, off = OFF_OF(k), bytes = BYTES_OF(k), obytes = bytes + (k + 1 == n ? p->out_extra : 0);
+            const int r = SLOT_OF(k);
+            u8 *d = p->resident ? p->resident + off : DEV_OF(r);
+            cudaStream_t st = STREAM_OF(r);
+            if (bounce_in) CU(cudaMemcpyAsync(d, HOST_OF(r), bytes, cudaMemcpyHostToDevice, st));
+            else           CU(cudaMemcpyAsync(d, p->in + off, bytes, cudaMemcpyDefault, st));
+            if (p->fn && (rc = p->fn(p->user, p->base + off, k, r, d, bytes, obytes, st)) != 0) goto done;
+            if (p->out) {
+                if (bounce_out) CU(cudaMemcpyAsync(HOST_OF(r), d, obytes, cudaMemcpyDeviceToHost, st));
+                else            CU(cudaMemcpyAsync(p->out + off, d, obytes, cudaMemcpyDefault, st));
+            }
+            if (g_burn && !p->resident) CU(cudaMemsetAsync(d, 0, chunk, st));
+            CU(cudaEventRecord(c->rev[r], st));
+            ++kgpu; progressed = 1;
+        }
+        if (kout < kgpu) {                                                  /* OUT */
+            const int r = SLOT_OF(kout);
+            const cudaError_t q = cudaEventQuery(c->rev[r]);
+            if (q == cudaSuccess) {
+                const size_t k = kout, obytes = BYTES_OF(k) + (k + 1 == n ? p->out_extra : 0);
+                if (bounce_out && p->out) copy_async(p->out + OFF_OF(k), HOST_OF(r), obytes, &out_left[r]);
+                ++kout; progressed = 1;
+            } else if (q != cudaErrorNotReady) {
+                rc = fail(UAES_E_CUDA, "staging pipeline", (int)q);
+                goto done;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (kdone < kout && (!bounce_out || copy_left(&out_left[SLOT_OF(kdone)]) == 0)) {    /* retire */
+            ++kdone; progressed = 1;
+        }
+        if (!progressed) {
+            /* waiting for helper threads (IN of kgpu, OUT of kdone) or for the GPU (event of kout) */
+            if ((kgpu < kin && bounce_in) || (kdone < kout && bounce_out)) copy_wait_any();
+            else if (kout < kgpu) CU(cudaEventSynchronize(c->rev[SLOT_OF(kout)]));
         }
     }
 done:
+    /* on an error pieces may still be queued for the helpers: they must land before the ring is reused */
+    for (i = 0; i < MAX_RING; ++i)
+        while (copy_left(&in_left[i]) || copy_left(&out_left[i])) copy_wait_any();
     for (i = 0; i < NSLOT; ++i) {
         cudaError_t e = cudaStreamSynchronize(c->st[i]);
         if (e != cudaSuccess && !rc) rc = fail(UAES_E_CUDA, "cudaStreamSynchronize(staging)", (int)e);
     }
-    if (g_burn && (bounce_in || bounce_out))
+    if (g_burn && bounce)
         for (i = 0; i < NSLOT; ++i) if (c->hslot[i]) memset(c->hslot[i], 0, CHUNK_BYTES);
     return rc;
+#undef SLOT_OF
+#undef DEV_OF
+#undef HOST_OF
+#undef STREAM_OF
+#undef OFF_OF
+#undef BYTES_OF
 }
 
 /* ------------------------------------------------------------------ spreading a call over devices */
@@ -1024,7 +1130,7 @@ typedef struct {
     u64 total_len;
     size_t chunk;                /* pipeline chunk of this call */
     scratch *w;                  /* NSLOT work areas + the part's contribution array (device) */
-    size_t work_stride, nchunks;
+    size_t work_stride, nchunks, nslots;
     u8 *host_parts;              /* where this part's contributions go on the host (16 B per chunk) */
     u64 *host_after;             /* ... and the number of GHASH blocks after each chunk */
     u8 *keep;                    /* decrypt: the part's plaintext on the device until the tag is checked */
@@ -1034,15 +1140,16 @@ static int gcm_part_before(devctx *c, void *user, const pipe_part *p)
 {
     gcm_part *g = (gcm_part *)user;
     g->nchunks = pipe_nchunks(p);
-    g->work_stride = (uaes_gcm_work_bytes(g->chunk) + 255) & ~(size_t)255;
-    return scratch_get(c, (size_t)NSLOT * g->work_stride + g->nchunks * 16 + 64, c->st[0], &g->w);
+    g->work_stride = (uaes_gcm_work_bytes(pipe_chunk_bytes(p)) + 255) & ~(size_t)255;
+    g->nslots = (size_t)pipe_slots(p);
+    return scratch_get(c, g->nslots * g->work_stride + g->nchunks * 16 + 64, c->st[0], &g->w);
 }
 
 static int gcm_part_chunk(void *user, u64 offset, size_t index, int slot, void *dev, size_t bytes, size_t obytes, void *stream)
 {
     gcm_part *g = (gcm_part *)user;
     u8 *work = (u8 *)g->w->p + (size_t)slot * g->work_stride;
-    u8 *dpart = (u8 *)g->w->p + (size_t)NSLOT * g->work_stride + index * 16;
+    u8 *dpart = (u8 *)g->w->p + g->nslots * g->work_stride + index * 16;
     int e;
     (void)obytes;
     e = uaes_launch_gcm(&g->ks, g->j0, NULL, 0, NULL, dev, dev, bytes, g->mode, offset / 16, 1, dpart, 16, work, stream);
@@ -1058,7 +1165,7 @@ static int gcm_part_after(devctx *c, void *user, const pipe_part *p)
     (void)p;
     /* the pipeline is drained: the contributions are complete */
     if (g->nchunks &&
-        cudaMemcpy(g->host_parts, (u8 *)g->w->p + (size_t)NSLOT * g->work_stride, g->nchunks * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+        cudaMemcpy(g->host_parts, (u8 *)g->w->p + g->nslots * g->work_stride, g->nchunks * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
         rc = fail(UAES_E_CUDA, "cudaMemcpy(GHASH contributions)", (int)cudaGetLastError());
     scratch_put(c, g->w, c->st[0]);
     g->w = NULL;

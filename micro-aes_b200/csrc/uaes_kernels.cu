@@ -129,6 +129,10 @@ struct CtrArgs {
 // keystream with no lookups at all (uaes_bitslice.cuh).  Register budgets differ by 2x, so the two
 // roles re-balance the CTA's register file with setmaxnreg right after the table fill.
 constexpr int kBsThreads = 128;
+#ifndef UAES_HYB_TT_REGS
+#define UAES_HYB_TT_REGS 104
+#endif
+constexpr int kHybridTtRegs = UAES_HYB_TT_REGS;  // register budget of the table-driven threads in the ECB / XTS / OCB kernels with a co-runner
 
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -342,7 +346,8 @@ __global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_ke
 // unit is claimed a unit ahead so that neither the atomic nor the first loads of that unit are
 // waited for.
 #ifndef UAES_BS_BATCH
-#define UAES_BS_BATCH 4                          // rows of a bitsliced pass loaded ahead of the XOR / store
+#define UAES_BS_BATCH 2                          // rows of a bitsliced pass loaded ahead of the XOR / store (4: 16 more
+                                                 // registers, spills: 996 -> 1036 GiB/s going from 4 to 2, profiles/r2_ctr_queue_sweep*.txt)
 #endif
 #ifndef UAES_Q_UNIT_SHIFT
 #define UAES_Q_UNIT_SHIFT 11                     // 2048 blocks = 32 KiB = 8 groups = 2 bitsliced passes
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
 #ifndef UAES_Q_TT_REGS
-#define UAES_Q_TT_REGS 104
+#define UAES_Q_TT_REGS 96                        // table-driven threads; the co-runner gets 224 (104 / 200: -0.8 .. -1.8 %)
 #endif
     constexpr int kTtRegs = UAES_Q_TT_REGS;
     constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kEcbTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kEcbTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbTtThreads / kBsThreads;
+    constexpr int kTtRegs = kHybridTtRegs, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbTtThreads / kBsThreads;
 
     if (threadIdx.x >= kEcbTtThreads) {
         reg_inc<kBsRegs>();

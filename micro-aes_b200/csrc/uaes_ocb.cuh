@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kOcbTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kOcbTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kOcbTtThreads / kBsThreads;
+    constexpr int kTtRegs = kHybridTtRegs, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kOcbTtThreads / kBsThreads;
     const uint64_t nblocks = a.o.nblocks;
     uint4 sum = make_uint4(0, 0, 0, 0);
 

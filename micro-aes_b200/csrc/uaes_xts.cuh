@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid
     T0.hi = (uint64_t)t0s[3] << 32 | t0s[2];
     constexpr int kTtWarps = kXtsTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
+    constexpr int kTtRegs = kHybridTtRegs, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
     const uint64_t nblocks = a.u.nblocks;
 
     if (threadIdx.x >= kXtsTtThreads) {
@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kXtsTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;      // 128
-    constexpr int kTtRegs = 104, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;   // 200
+    // 96 / 224: 582 -> 596 GiB/s for AES-256 (profiles/r2_sweep_hybrid_regs.txt); ECB and OCB keep 104 / 200
+    constexpr int kTtRegs = kHybridTtRegs - 8, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
 
     if (threadIdx.x >= kXtsTtThreads) {
         reg_inc<kBsRegs>();
