@@ -55,6 +55,19 @@ def main():
     print("\n# per-opcode totals from the source page: warp-instructions, shared wavefronts, ideal shared wavefronts")
     for op, (n, w, i) in sorted(agg.items()):
         print(f"{op:24s} {n:14d} {w:14d} {i:14d}")
+    # warp-state sampling split by role: the bitsliced warps' code lies between the two USETMAXREG
+    # instructions (setmaxnreg.inc ... setmaxnreg.dec), the table-driven warps' code after the second
+    marks = [i for i, r in enumerate(src[2:]) if len(r) >= len(hdr) and 'USETMAXREG' in r[ix['Source']]]
+    stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+    if len(marks) >= 2 and stalls:
+        body = [r for r in src[2:] if len(r) >= len(hdr)]
+        for name, rows_ in (('bitsliced co-runner warps', body[marks[0]:marks[-1]]), ('table-driven warps', body[marks[-1]:])):
+            tot = {h: sum(int(r[ix[h]] or 0) for r in rows_) for h in stalls}
+            n = sum(tot.values()) or 1
+            inst = sum(int(r[ix['Instructions Executed']] or 0) for r in rows_)
+            top = sorted(tot.items(), key=lambda kv: -kv[1])[:9]
+            print(f"\n# {name}: static {len(rows_)} instructions, executed {inst} warp-instructions, {n} samples; "
+                  + " ".join(f"{k[6:]}={v / n:.2f}" for k, v in top))
     if blocks:
         rows32 = blocks / 32
         cyc = float(d['sm__cycles_active.avg'][1])
