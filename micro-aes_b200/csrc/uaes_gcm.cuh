@@ -148,40 +148,15 @@ __device__ __forceinline__ void ghash_mul_const(uint32_t mb, uint32_t &y0, uint3
     }, y0, y1, y2, y3);
 }
 
-// MODE 0: encrypt (CTR, hash the OUTPUT)   MODE 1: hash only (GCM decrypt's verify pass)
-// MODE 2: decrypt shard (CTR, hash the INPUT in the same pass; multi-GPU shards, where the caller
-//         compares the combined tag afterwards)
-// REV: absorb byte-reversed blocks (POLYVAL)
-template <int NR, int MODE, bool REV = false>
-__global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
+// The table-driven warps' part of the pass: chunks first_chunk, first_chunk + nwarps, ... of the range
+// [0, region_blocks) (the whole message, or what is left in front of the bitsliced warps' region).
+template <int NR, int MODE, bool REV>
+__device__ __forceinline__ void gcm_tt_chunks(const GcmBulkArgs &a, uint64_t region_blocks, uint32_t lb, uint32_t mb,
+                                              uint64_t first_chunk, uint64_t nwarps)
 {
-    extern __shared__ __align__(16) uint8_t dyn[];
-    // ---- shared memory map: AES tables 64 KiB aligned, the GHASH table in a 32 KiB-aligned gap
-    const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
-    const uint32_t tbase = align_table_base(dyn);
-    const uint32_t mbase = tbase >= win0 + kGhashRegion ? tbase - kGhashRegion : tbase + kEncTableBytes;
-    if (mbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1) __trap();
-
-    if (MODE != 1) init_enc_tables(tbase);
-    {
-        // M[b] = b(x) * C: bit 7 of b is the coefficient of x^0 (micro_aes.c:476-493 bit order)
-        const Gf C = gf_load(a.work->C32);
-        if (threadIdx.x < 256) {
-            const uint4 v = ghash_table_entry(C, threadIdx.x);
-            for (int rep = 0; rep < 8; ++rep) {
-                const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-            }
-        }
-    }
-    __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4);
-    asm volatile("" : "+r"(lb), "+r"(mb)::"memory");
-
     const uint32_t *rk = a.ks.w;
     const uint64_t CB = a.chunk_blocks;
-    const uint64_t nwarps = (uint64_t)gridDim.x * kGcmWarps;
     uint4 aad_be = a.work->aad_state;                    // the GHASH state lives in big-endian words
     aad_be = make_uint4(__byte_perm(aad_be.x, 0, 0x0123), __byte_perm(aad_be.y, 0, 0x0123),
                         __byte_perm(aad_be.z, 0, 0x0123), __byte_perm(aad_be.w, 0, 0x0123));
@@ -189,9 +164,9 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
     uint64_t cur_group = ~0ull;
     uint32_t s3 = 0, K0 = 0, D0 = 0, D1 = 0, D2 = 0, D3 = 0;
 
-    for (uint64_t c = (uint64_t)blockIdx.x * kGcmWarps + (threadIdx.x >> 5); c < a.nchunks; c += nwarps) {
+    for (uint64_t c = first_chunk; c < a.nchunks; c += nwarps) {
         // chunk c ends (NC-1-c) chunks before the end of the message
-        const uint64_t b1 = a.nblocks - (a.nchunks - 1 - c) * CB;
+        const uint64_t b1 = region_blocks - (a.nchunks - 1 - c) * CB;
         const uint64_t b0 = b1 > CB ? b1 - CB : 0;
         const uint64_t vfirst = (a.v0 + b0) & ~31ull, vend = a.v0 + b1;      // counter space rows
         uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
@@ -271,6 +246,181 @@ __global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_c
     }
 }
 
+
+// MODE 0: encrypt (CTR, hash the OUTPUT)   MODE 1: hash only (GCM decrypt's verify pass)
+// MODE 2: decrypt shard (CTR, hash the INPUT in the same pass; multi-GPU shards, where the caller
+//         compares the combined tag afterwards)
+// REV: absorb byte-reversed blocks (POLYVAL)
+template <int NR, int MODE, bool REV = false>
+__global__ void __launch_bounds__(kGcmThreads, 1) gcm_bulk_kernel(const __grid_constant__ GcmBulkArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    // ---- shared memory map: AES tables 64 KiB aligned, the GHASH table in a 32 KiB-aligned gap
+    const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
+    const uint32_t tbase = align_table_base(dyn);
+    const uint32_t mbase = tbase >= win0 + kGhashRegion ? tbase - kGhashRegion : tbase + kEncTableBytes;
+    if (mbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1) __trap();
+
+    if (MODE != 1) init_enc_tables(tbase);
+    {
+        // M[b] = b(x) * C: bit 7 of b is the coefficient of x^0 (micro_aes.c:476-493 bit order)
+        const Gf C = gf_load(a.work->C32);
+        if (threadIdx.x < 256) {
+            const uint4 v = ghash_table_entry(C, threadIdx.x);
+            for (int rep = 0; rep < 8; ++rep) {
+                const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4);
+    asm volatile("" : "+r"(lb), "+r"(mb)::"memory");
+
+    gcm_tt_chunks<NR, MODE, REV>(a, a.nblocks, lb, mb, (uint64_t)blockIdx.x * kGcmWarps + (threadIdx.x >> 5),
+                                 (uint64_t)gridDim.x * kGcmWarps);
+}
+
+// ---- GCM with the co-runner (AES-GCM encryption / decrypting shards of >= 128 MiB) -----------------
+// The bulk kernel above sits at the shared-memory lookup roof with 192 wavefronts per block (128 AES +
+// 64 GHASH) and half of the ALU pipe idle.  Here one warpgroup of bitsliced warps (uaes_bitslice.cuh,
+// the CTR-specialised form of ctr_kernel) produces the keystream of the LAST part of the message on
+// the ALU pipe; those blocks cost the lookup pipe only their 64 GHASH wavefronts.  After the 32 x 32
+// transposes lane l of a bitsliced warp holds the blocks = l (mod 32) of 1024 consecutive counters --
+// exactly the lane ownership of the GHASH Horner with multiplier H^32 -- so the warp XORs, stores and
+// absorbs its 32 slots in order with ghash_mul_const.  A bitsliced warp owns a contiguous run of
+// passes (= one GHASH chunk); it scales its partial to the END of the message itself (one power of H
+// per launch), so the finish kernel only XORs those partials onto the folded table-driven region.
+// 3 table-driven warpgroups at 96 registers + 1 bitsliced warpgroup at 224 (setmaxnreg works on whole
+// warpgroups only: a 2-warp co-runner next to 16 table-driven warps hangs, profiles/r2_setmaxnreg_partial.txt).
+struct GcmHybridArgs {
+    GcmBulkArgs b;               // b.nblocks = all full blocks; b.chunk_blocks / b.nchunks plan [0, a_blocks)
+    uint64_t a_blocks;           // blocks [0, a_blocks): table-driven warps; v0 + a_blocks is a multiple of 1024
+    uint64_t bs_passes;          // 1024-counter passes covering [a_blocks, nblocks)
+    uint64_t bs_per;             // passes per bitsliced warp
+    uint64_t nchunks_b;          // bitsliced chunks: partials[b.nchunks + j], already scaled to the end of the range
+    BsKeyPlanes bs;
+};
+
+constexpr int kGcmHybTtThreads = 384;
+constexpr int kGcmHybTtWarps = kGcmHybTtThreads / 32;
+
+template <int NR, int MODE>
+__device__ __forceinline__ void gcm_bs_chunk(const GcmHybridArgs &h, uint32_t lb, uint32_t mb, uint32_t *um, uint64_t j)
+{
+    const GcmBulkArgs &a = h.b;
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t p0 = j * h.bs_per, p1 = p0 + h.bs_per < h.bs_passes ? p0 + h.bs_per : h.bs_passes;
+    const uint64_t ubase = a.v0 + h.a_blocks;                   // counter of the region's first block (not reduced mod 2^56)
+    uint64_t tag16 = ~0ull, klast = 0;
+    uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    bool any = false;
+
+    for (uint64_t p = p0; p < p1; ++p) {
+        const uint64_t u0 = ubase + (p << 10);
+        const uint64_t vc = u0 & kMask56;
+        const uint64_t kb = h.a_blocks + (p << 10);              // block index of (slot 0, lane 0)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                            // this pass's 16 KiB towards L2 while the rounds run
+            const uint64_t k = kb + (uint64_t)(lane * 4 + i) * 8;
+            if (k < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + k));
+        }
+        if ((vc >> 16) != tag16) {                               // counter bytes <= 13 changed: every 64 passes
+            tag16 = vc >> 16;
+            uint32_t w2, w3, uw[6];
+            ctr_words(a.b8, vc, w2, w3);
+            bs_uniform_words([&](int t, uint32_t x) { return lut_index(lb, t == 0 ? kOffT0 : t == 1 ? kOffT1 : t == 2 ? kOffT2 : kOffT3, x); },
+                             a.w0 ^ rk[0], a.w1 ^ rk[1], w2 ^ rk[2], w3 ^ rk[3], rk, uw);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 6; ++q) um[32 * q + lane] = bs_mask(uw[q], (int)lane);
+            __syncwarp();
+        }
+        uint32_t s[128];
+        bs_first_rounds(s, lane, (uint32_t)(vc >> 8) & 0xfcu, h.bs.k0, um);
+#pragma unroll 1
+        for (int r = 3; r <= NR; ++r) bs_round_or_last(s, h.bs.k[r - 3], r == NR);
+        const uint64_t k0 = kb + lane;
+        uint4 x = k0 < a.nblocks ? ld_stream(a.in + k0) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const uint64_t k = k0 + 32 * t;
+            const uint4 nx = (t + 1 < 32 && k + 32 < a.nblocks) ? ld_stream(a.in + k + 32) : make_uint4(0, 0, 0, 0);
+            if (k < a.nblocks) {
+                const uint4 o = make_uint4(x.x ^ s[t], x.y ^ s[32 + t], x.z ^ s[64 + t], x.w ^ s[96 + t]);
+                st_stream(a.out + k, o);
+                const uint4 g = MODE == 0 ? o : x;               // GHASH runs over the ciphertext
+                ghash_mul_const(mb, y0, y1, y2, y3);
+                y0 ^= __byte_perm(g.x, 0, 0x0123); y1 ^= __byte_perm(g.y, 0, 0x0123);
+                y2 ^= __byte_perm(g.z, 0, 0x0123); y3 ^= __byte_perm(g.w, 0, 0x0123);
+                klast = k; any = true;
+            }
+            x = nx;
+        }
+    }
+    // chunk end b1; lane l holds sum_j X_(l+32j) * C^(J-j): scale by H^(b1 - klast), reduce over the warp,
+    // then move the partial to the end of the range: * H^(nblocks - b1)
+    const uint64_t b1 = h.a_blocks + (p1 << 10) < a.nblocks ? h.a_blocks + (p1 << 10) : a.nblocks;
+    Gf z{0, 0};
+    if (any) z = gf_mul_fast(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]),
+                             Gf{(uint64_t)y0 << 32 | y1, (uint64_t)y2 << 32 | y3});
+    for (int o = 16; o; o >>= 1) {
+        z.hi ^= __shfl_xor_sync(0xffffffffu, z.hi, o);
+        z.lo ^= __shfl_xor_sync(0xffffffffu, z.lo, o);
+    }
+    if (lane == 0) {
+        if (a.nblocks > b1) z = gf_mul_fast(z, gf_pow_fast(gf_load(a.work->H), a.nblocks - b1));
+        a.work->partials[a.nchunks + j] = gf_store(z);
+    }
+}
+
+template <int NR, int MODE>
+__global__ void __launch_bounds__(kGcmHybTtThreads + kBsThreads, 1) gcm_bulk_hybrid_kernel(const __grid_constant__ GcmHybridArgs h)
+{
+    static_assert(MODE == 0 || MODE == 2, "the co-runner produces keystream: encrypt or decrypting shard");
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
+    const uint32_t tbase = align_table_base(dyn);
+    const uint32_t mbase = tbase >= win0 + kGhashRegion ? tbase - kGhashRegion : tbase + kEncTableBytes;
+    const uint32_t after = mbase > tbase ? mbase + kGhashRegion : tbase + kEncTableBytes;   // uniform masks of the bitsliced warps
+    if (mbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1 || after + 4 * kBsUniformMasks * 4 > win1) __trap();
+
+    init_enc_tables(tbase);
+    {
+        const Gf C = gf_load(h.b.work->C32);
+        if (threadIdx.x < 256) {
+            const uint4 v = ghash_table_entry(C, threadIdx.x);
+            for (int rep = 0; rep < 8; ++rep) {
+                const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4);
+    asm volatile("" : "+r"(lb), "+r"(mb)::"memory");
+
+    constexpr int kLaunchRegs = (65536 / (kGcmHybTtThreads + kBsThreads)) / 8 * 8;     // 128
+    constexpr int kTtRegs = 96, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kGcmHybTtThreads / kBsThreads;   // 224
+    if (threadIdx.x >= kGcmHybTtThreads) {
+        reg_inc<kBsRegs>();
+        const uint32_t bw = (threadIdx.x - kGcmHybTtThreads) >> 5;
+        uint32_t *um = (uint32_t *)(dyn + (after - win0)) + bw * kBsUniformMasks;
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        for (uint64_t j = (uint64_t)blockIdx.x * (kBsThreads / 32) + bw; j < h.nchunks_b; j += nw)
+            gcm_bs_chunk<NR, MODE>(h, lb, mb, um, j);
+        return;
+    }
+    reg_dec<kTtRegs>();
+    gcm_tt_chunks<NR, MODE, false>(h.b, h.a_blocks, lb, mb, (uint64_t)blockIdx.x * kGcmHybTtWarps + (threadIdx.x >> 5),
+                                   (uint64_t)gridDim.x * kGcmHybTtWarps);
+}
+
 // ---------------------------------------------------------------- fold, tail, tag
 
 struct GcmFinishArgs {
@@ -280,7 +430,9 @@ struct GcmFinishArgs {
     const uint8_t *in;
     uint8_t *out;
     uint64_t len, aadlen;
-    uint64_t nparts, chunk_rows; // partials left by the bulk kernel; neighbours are H^(32*rows) apart
+    uint64_t nparts, chunk_rows; // partials left by the table-driven warps; neighbours are H^(32*rows) apart
+    uint64_t nparts_b, blocks_b; // co-runner: partials [nparts, nparts + nparts_b), already scaled to the end of the
+                                 // full-block range, which lies blocks_b blocks behind the table-driven region
     int mode;                    // as gcm_bulk_kernel's MODE
     int partial_only;            // write the GHASH state of this shard instead of a tag
     int siv;                     // POLYVAL + GCM-SIV tag (micro_aes.c:1454-1462); j0[] = nonce words
@@ -321,6 +473,13 @@ __global__ void __launch_bounds__(kFinThreads, 1) gcm_finish_kernel(const __grid
     if (threadIdx.x != 0) return;
     const Gf H = gf_load(a.work->H);
     Gf S = a.nparts ? gf_load(slot[0]) : gf_load(a.work->aad_state);
+    if (a.nparts_b) {                                         // the bitsliced warps' region follows
+        S = gf_mul_fast(S, gf_pow_fast(H, a.blocks_b));
+        for (uint64_t j = 0; j < a.nparts_b; ++j) {
+            const Gf z = gf_load(slot[a.nparts + j]);
+            S.hi ^= z.hi; S.lo ^= z.lo;
+        }
+    }
 
     const uint64_t nfull = a.len / 16;
     const uint32_t tail = (uint32_t)(a.len % 16);
@@ -387,12 +546,26 @@ static cudaError_t launch_gcm_bulk_nr(const GcmBulkArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+constexpr int kGcmDefaultShare = 170;    // of 1024: blocks given to the bitsliced warps; 632 / 661 / 671 / 680 / 648 / 568 GiB/s at
+                                         // 0 / 120 / 150 / 180 / 200 / 250 for AES-128, 4 GiB (profiles/r2_sweep_gcm*.txt): the static split
+                                         // falls off quickly once the bitsliced warps finish last, so stay left of the peak
+
+template <int NR, int MODE>
+static cudaError_t launch_gcm_hybrid_nr(const GcmHybridArgs &h, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(gcm_bulk_hybrid_kernel<NR, MODE>);
+    if (e != cudaSuccess) return e;
+    gcm_bulk_hybrid_kernel<NR, MODE><<<(unsigned)sm_count(), kGcmHybTtThreads + kBsThreads, kDynSmem, st>>>(h);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 // One chunk per warp of the persistent grid: R rows each, so that all warps get the same share
 // (the first chunk in message order is the short one).  Small messages get one row per chunk.
-static void gcm_plan(uint64_t nblocks, uint64_t &rows_per_chunk, uint64_t &nchunks)
+static void gcm_plan(uint64_t nblocks, uint64_t &rows_per_chunk, uint64_t &nchunks, int warps_per_cta = kGcmWarps)
 {
     const uint64_t rows = (nblocks + 31) / 32;
-    const uint64_t warps = (uint64_t)sm_count() * kGcmWarps;
+    const uint64_t warps = (uint64_t)sm_count() * (uint64_t)warps_per_cta;
     rows_per_chunk = rows ? (rows + warps - 1) / warps : 1;
     nchunks = rows ? (nblocks + 32 * rows_per_chunk - 1) / (32 * rows_per_chunk) : 0;
 }
@@ -628,7 +801,8 @@ extern "C" size_t uaes_gcm_work_bytes(u64 len)
     using namespace uaes;
     uint64_t rows_per_chunk, nchunks;
     gcm_plan(len / 16, rows_per_chunk, nchunks);
-    return sizeof(GcmWork) + (size_t)nchunks * sizeof(uint4);
+    // + one partial per bitsliced warp of the co-runner form (4 per SM)
+    return sizeof(GcmWork) + ((size_t)nchunks + 4 * (size_t)sm_count() + 8) * sizeof(uint4);
 }
 
 extern "C" int uaes_launch_gcm_j0(const uaes_keysched *ks, const void *iv_dev, u64 ivlen, void *out_dev,
@@ -675,7 +849,43 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char j0b[
     for (int i = 9; i < 16; ++i) vj0 = vj0 << 8 | j0b[i];
     const uint32_t b8 = j0b[8];
 
-    if (nchunks) {
+    uint64_t nparts_b = 0, blocks_b = 0;
+    // the co-runner form: the last `share` of the blocks goes to bitsliced warps (region B starts on a
+    // 1024-counter boundary); the on/off knobs are the CTR kernel's (uaes_ctr_tuning)
+    ctr_tuning_init();
+    const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_GCM_BS_PERMILLE", kGcmDefaultShare);
+    if ((mode == 0 || mode == 2) && g_ctr_share > 0 && share > 0 && (long long)nblocks >= g_ctr_bs_min && nblocks >= 4096) {
+        static thread_local GcmHybridArgs h;                 // 6 KB of planes: off the stack
+        const uint64_t v0 = (vj0 + 1 + first_block) & kMask56;
+        const uint64_t uend = v0 + nblocks, want = nblocks / 1024 * (uint64_t)share;
+        const uint64_t ub = (uend - want) & ~1023ull;
+        if (ub > v0 + 1024 && ub < uend) {
+            h.a_blocks = ub - v0;
+            h.bs_passes = (uend - ub + 1023) >> 10;
+            const uint64_t nw = (uint64_t)sm_count() * (kBsThreads / 32);
+            h.bs_per = (h.bs_passes + nw - 1) / nw;
+            h.nchunks_b = (h.bs_passes + h.bs_per - 1) / h.bs_per;
+            gcm_plan(h.a_blocks, rows_per_chunk, nchunks, kGcmHybTtWarps);
+            GcmBulkArgs &b = h.b;
+            b.ks = *ks;
+            b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = v0;
+            b.in = (const uint4 *)in; b.out = (uint4 *)out;
+            b.nblocks = nblocks; b.chunk_blocks = 32 * rows_per_chunk; b.nchunks = nchunks; b.work = (GcmWork *)work;
+            bs_make_key_planes(ks->w, ks->rounds, &h.bs);
+            nparts_b = h.nchunks_b; blocks_b = nblocks - h.a_blocks;
+            switch (ks->rounds * 4 + mode) {
+            case 40: e = launch_gcm_hybrid_nr<10, 0>(h, st); break;
+            case 42: e = launch_gcm_hybrid_nr<10, 2>(h, st); break;
+            case 48: e = launch_gcm_hybrid_nr<12, 0>(h, st); break;
+            case 50: e = launch_gcm_hybrid_nr<12, 2>(h, st); break;
+            case 56: e = launch_gcm_hybrid_nr<14, 0>(h, st); break;
+            case 58: e = launch_gcm_hybrid_nr<14, 2>(h, st); break;
+            default: e = cudaErrorInvalidValue;
+            }
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (nchunks && !nparts_b) {
         GcmBulkArgs b;
         b.ks = *ks;
         b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = (vj0 + 1 + first_block) & kMask56;
@@ -701,6 +911,7 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char j0b[
     f.w0 = j0[0]; f.w1 = j0[1]; f.b8 = b8; f.v0 = (vj0 + 1 + first_block) & kMask56;
     f.in = (const uint8_t *)in; f.out = (uint8_t *)out;
     f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk; f.mode = mode; f.partial_only = partial_only; f.siv = 0;
+    f.nparts_b = nparts_b; f.blocks_b = blocks_b;
     f.tag_out = (uint8_t *)tag_out; f.taglen = partial_only ? 16 : taglen; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);
     ++g_launches;
@@ -798,6 +1009,7 @@ extern "C" int uaes_launch_gcmsiv_tag(const uaes_keysched *enc, const unsigned c
     f.w0 = nw[0]; f.w1 = nw[1]; f.b8 = nw[2]; f.v0 = 0;      // the nonce words ride in the counter fields
     f.in = (const uint8_t *)data; f.out = nullptr;
     f.len = len; f.aadlen = aadlen; f.nparts = nchunks; f.chunk_rows = rows_per_chunk;
+    f.nparts_b = 0; f.blocks_b = 0;
     f.mode = 1; f.partial_only = partial_only; f.siv = 1;
     f.tag_out = (uint8_t *)tag_out; f.taglen = 16; f.work = (GcmWork *)work;
     gcm_finish_kernel<<<1, kFinThreads, 0, st>>>(f);

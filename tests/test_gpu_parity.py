@@ -164,12 +164,13 @@ def test_ctr_ecb_sizes(uaes, orc, bits):
 
 @pytest.mark.parametrize("bits", [128, 192, 256])
 def test_ctr_bitsliced_corunner(uaes, orc, torch, bits):
-    """the CTR kernel's ALU co-runner warps (bitsliced AES, csrc/uaes_bitslice.cuh) forced on for
-    small calls, at every split between the two kinds of warps, with ragged ends, counter offsets
-    that are not multiples of 1024 and the carries into counter bytes 13, 12 and 9"""
+    """the CTR kernels' ALU co-runner warps (bitsliced AES, csrc/uaes_bitslice.cuh) forced on for
+    small calls, at every static split between the two kinds of warps and through the work queue, with
+    ragged ends, counter offsets that are not multiples of 1024 (or of a queue unit) and the carries
+    into counter bytes 13, 12 and 9"""
     key, iv = rnd(f"bs-k{bits}", bits // 8), rnd(f"bs-i{bits}", 12)
     try:
-        for threads in (384, 385):               # 385 = two blocks per table-driven thread in flight
+        for threads in (384, 385, 386):          # 385 = two blocks per table-driven thread in flight; 386 = the work-queue kernel
             for share, n, first in ((1024, 16 * 5000 + 3, 0), (512, 16 * 70001, 1), (300, (1 << 21) + 9, 1000),
                                     (1024, 16 * 3000, (1 << 16) - 1500), (700, 16 * 4100 + 15, (1 << 24) - 2050),
                                     (1024, 16 * 2500, (1 << 32) - 1200), (900, 16 * 2048, (1 << 56) - 1024 - 2),
@@ -182,7 +183,7 @@ def test_ctr_bitsliced_corunner(uaes, orc, torch, bits):
                 assert host(dst, 0, n) == orc.ctr(key, iv, data, first_block=first), (threads, share, n, first)
                 assert host(dst, n, n + 16) == bytes(16)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -225,7 +226,7 @@ def test_ecb_bitsliced_corunner(uaes, orc, bits):
             orc.lib.oracle_cfb_decrypt(bits, key, iv, data, n, o)
             assert a.AES_CFB_decrypt(key, iv, data) == o.raw[:n], (share, n)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -244,7 +245,7 @@ def test_ocb_bitsliced_corunner(uaes, orc, bits):
             assert got[-16:] == want[-16:] and got == want, (share, n)
             assert a.AES_OCB_decrypt(key, nonce, aad, want) == (0, data)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -266,7 +267,7 @@ def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
             uaes.xts_sectors(bits, keys, first, 512, data, len(data), back, False)
             assert (0, back.raw) == orc.xts_sectors(keys, first, 512, data, encrypt=False), (share, first, ns)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -282,7 +283,7 @@ def test_xts_unit_bitsliced_corunner(uaes, orc, bits):
             assert a.AES_XTS_encrypt(keys, tw, data) == want, (share, n)
             assert a.AES_XTS_decrypt(keys, tw, want[1]) == (0, data)
     finally:
-        uaes.ctr_tuning(385, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultShare)
+        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 192, 256])

@@ -214,6 +214,38 @@ def test_cbc_without_cts(uaes, orc, torch):
     assert uaes.cbc_decrypt_ex(192, key, iv, ct, 100, out, cts=True) == 0 and out.raw[:100] == orc.cbc(key, iv, ct)[1]
 
 
+@pytest.mark.parametrize("bits", [128, 256])
+def test_gcm_bitsliced_corunner(uaes, orc, torch, bits):
+    """gcm_bulk_hybrid_kernel forced on for small messages: the last part of the message is encrypted by
+    bitsliced warps that also run their share of the GHASH; every split, ragged ends, AAD, shards whose
+    first block is not a multiple of 1024, both hash directions (encrypt / decrypting shard)"""
+    key, nonce = rnd(f"gb-k{bits}", bits // 8), rnd("gb-n", 12)
+    try:
+        for share, n, alen in ((200, 16 * 9000 + 3, 20), (512, 16 * 70001, 0), (900, (1 << 21) + 9, 4500), (100, 16 * 4096, 7),
+                               (1000, 16 * 5000 + 15, 1), (300, 3 * MIB, 0)):
+            uaes.ctr_tuning(-1, share, 0)
+            aad, pt = rnd(f"gb-a{alen}", alen), rnd(f"gb-p{bits}{n}", n)
+            want = orc.gcm_encrypt(key, nonce, aad, pt)
+            src, dst = dev(torch, pt), dev(torch, b"", pad=n + 32)
+            uaes.gcm_encrypt(bits, key, nonce, aad, src, n, dst)
+            assert host(dst, n, n + 16) == want[n:], (share, n, alen)
+            assert host(dst, 0, n) == want[:n], (share, n, alen)
+            back = dev(torch, b"", pad=n + 16)
+            assert uaes.gcm_decrypt(bits, key, nonce, aad, dst, n, back) == 0 and host(back, 0, n) == pt
+            # as two shards (the second starts at a block that is not a multiple of 1024), encrypting and
+            # decrypting (MODE 2: CTR + GHASH of the input)
+            cut = (n // 3) // 16 * 16 + 16 * 33                 # a block that is not a multiple of 1024
+            for decrypt, data, ref in ((False, pt, want[:n]), (True, want[:n], pt)):
+                s_in, s_out = dev(torch, data), dev(torch, b"", pad=n + 16)
+                z0 = uaes.gcm_shard(bits, key, nonce, 0, s_in, cut, s_out, decrypt=decrypt)
+                z1 = uaes.gcm_shard(bits, key, nonce, cut // 16, s_in[cut:], n - cut, s_out[cut:], decrypt=decrypt)
+                assert host(s_out, 0, n) == ref, (share, n, decrypt)
+                tag = uaes.gcm_combine(bits, key, nonce, aad, [z0, z1], [(n + 15) // 16 - cut // 16, 0], n)
+                assert tag == want[n:], (share, n, decrypt)
+    finally:
+        uaes.ctr_tuning(386, 195, 1 << 23)
+
+
 # ---------------------------------------------------------------- XTS: ranges of a unit, XTS-192
 
 def test_xts_192(uaes, orc, torch):
