@@ -132,6 +132,10 @@ constexpr int kBsThreads = 128;
 #ifndef UAES_HYB_TT_REGS
 #define UAES_HYB_TT_REGS 104
 #endif
+#ifndef UAES_BS_LOAD_BATCH
+#define UAES_BS_LOAD_BATCH 8
+#endif
+constexpr int kBsLoadBatch = UAES_BS_LOAD_BATCH;   // rows a general-form bitsliced warp loads at a time
 constexpr int kHybridTtRegs = UAES_HYB_TT_REGS;  // register budget of the table-driven threads in the ECB / XTS / OCB kernels with a co-runner
 
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -635,12 +639,12 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
             const uint64_t kb = a.tt_blocks + tile * 1024 + lane;
             uint32_t s[128];
 #pragma unroll
-            for (int tb = 0; tb < 32; tb += 8) {
-                uint4 v[8];
+            for (int tb = 0; tb < 32; tb += kBsLoadBatch) {
+                uint4 v[kBsLoadBatch];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = kb + 32 * (tb + i) < a.e.nblocks ? cin(kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < kBsLoadBatch; ++i) v[i] = kb + 32 * (tb + i) < a.e.nblocks ? cin(kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { s[tb + i] = v[i].x; s[32 + tb + i] = v[i].y; s[64 + tb + i] = v[i].z; s[96 + tb + i] = v[i].w; }
+                for (int i = 0; i < kBsLoadBatch; ++i) { s[tb + i] = v[i].x; s[32 + tb + i] = v[i].y; s[64 + tb + i] = v[i].z; s[96 + tb + i] = v[i].w; }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);

@@ -353,12 +353,12 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
         uint4 *dst = a.x.out + sec0 * 32 + lane;
         uint32_t s[128];
 #pragma unroll
-        for (int tb = 0; tb < 32; tb += 8) {                     // loads in batches of 8 rows
-            uint4 v[8];
+        for (int tb = 0; tb < 32; tb += kBsLoadBatch) {          // loads in batches of rows
+            uint4 v[kBsLoadBatch];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = tb + i < nsec ? ld_stream(src + (tb + i) * 32) : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < kBsLoadBatch; ++i) v[i] = tb + i < nsec ? ld_stream(src + (tb + i) * 32) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kBsLoadBatch; ++i) {
                 uint32_t w0, w1, w2, w3;
                 tweak_of(tb + i, w0, w1, w2, w3);
                 s[tb + i] = v[i].x ^ w0; s[32 + tb + i] = v[i].y ^ w1;
