@@ -530,17 +530,40 @@ static int copy_left(int *left)
     return v;
 }
 
-/* wait until some piece of anybody has arrived, or for 200 us at most */
+/* The pipeline's own thread has nothing to enqueue: it copies a queued piece itself (waking a sleeping
+ * helper costs ~200 us on the measured hosts -- more than copying 1 MiB), or, when the queue is empty,
+ * waits until some piece of anybody has arrived, for 200 us at most */
 static void copy_wait_any(void)
 {
-    struct timespec ts;
-    clock_gettime(CLOCK_REALTIME, &ts);
-    ts.tv_nsec += 200000;
-    if (ts.tv_nsec >= 1000000000L) { ts.tv_nsec -= 1000000000L; ++ts.tv_sec; }
-    pthread_mutex_lock(&g_cp.m);
-    pthread_cond_timedwait(&g_cp.done, &g_cp.m, &ts);
-    pthread_mutex_unlock(&g_cp.m);
+    copy_pool *p = &g_cp;
+    pthread_mutex_lock(&p->m);
+    if (p->head != p->tail) {
+        const copy_piece w = p->q[p->head % COPY_QUEUE];
+        ++p->head;
+        pthread_mutex_unlock(&p->m);
+        memcpy(w.dst, w.src, w.n);
+        pthread_mutex_lock(&p->m);
+        --*w.left;
+        pthread_cond_broadcast(&p->done);
+    } else {
+        struct timespec ts;
+        clock_gettime(CLOCK_REALTIME, &ts);
+        ts.tv_nsec += 200000;
+        if (ts.tv_nsec >= 1000000000L) { ts.tv_nsec -= 1000000000L; ++ts.tv_sec; }
+        pthread_cond_timedwait(&p->done, &p->m, &ts);
+    }
+    pthread_mutex_unlock(&p->m);
 }
+
+/* UAES_TRACE=1: timestamps of the pipeline stages on stderr (debugging / tuning only) */
+static int g_trace = -1;
+static double now_us(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
+}
+#define TRACE(...) do { if (g_trace > 0) fprintf(stderr, __VA_ARGS__); } while (0)
 
 /* ------------------------------------------------------------------ chunked staging pipeline */
 
@@ -571,8 +594,12 @@ typedef struct {
 #define BOUNCE_BYTES ((size_t)8 << 20)
 #define MAX_RING 16                   /* NSLOT <= 8: at least 2 pieces per chunk */
 
+#define BOUNCE_MIN ((size_t)64 << 10)  /* smaller pageable calls go through plain cudaMemcpyAsync (one stream, no
+                                         helpers): the fixed costs dominate there */
+
 static int pipe_bounces(const pipe_part *p)
 {
+    if (p->len <= BOUNCE_MIN) return 0;
     return ptr_class(p->in) == PTR_PAGEABLE || (p->out && ptr_class(p->out) == PTR_PAGEABLE);
 }
 
@@ -618,15 +645,19 @@ static int run_chunked(devctx *c, const pipe_part *p)
     int rc = 0, i;
     const size_t chunk = pipe_chunk_bytes(p), n = pipe_nchunks(p);
     const int R = pipe_slots(p);
-    const int bounce_in = ptr_class(p->in) == PTR_PAGEABLE, bounce_out = p->out && ptr_class(p->out) == PTR_PAGEABLE;
-    const int bounce = bounce_in || bounce_out;
+    const int bounce = pipe_bounces(p);
+    const int bounce_in = bounce && ptr_class(p->in) == PTR_PAGEABLE, bounce_out = bounce && p->out && ptr_class(p->out) == PTR_PAGEABLE;
     const size_t per = pipe_per(p);                          /* ring slots per staging chunk */
     size_t kin = 0, kgpu = 0, kout = 0, kdone = 0;
     int in_left[MAX_RING], out_left[MAX_RING];
 
+    double t0;
+    if (g_trace < 0) g_trace = getenv("UAES_TRACE") != NULL;
+    t0 = now_us();
     if (chunk == 0) return fail(UAES_E_BAD_ARGUMENT, "unit larger than the staging chunk", 0);
     if ((rc = need_slots(c, bounce)) != 0) return rc;
     for (i = 0; i < MAX_RING; ++i) in_left[i] = out_left[i] = 0;
+    TRACE("[uaes] run_chunked len %zu chunk %zu n %zu R %d bounce %d/%d  (+%.0f us)\n", p->len, chunk, n, R, bounce_in, bounce_out, now_us() - t0);
     if (bounce)
         for (i = 0; i < R; ++i)
             if (!c->rev_ok[i]) {
@@ -663,6 +694,7 @@ static int run_chunked(devctx *c, const pipe_part *p)
         if (kin < n && kin - kdone < (size_t)R && (!bounce_in || kin - kgpu < (size_t)g_in_ahead)) {
             const int r = SLOT_OF(kin);
             if (bounce_in) copy_async(HOST_OF(r), p->in + OFF_OF(kin), BYTES_OF(kin), &in_left[r]);
+            TRACE("[uaes] %8.0f IN  %zu\n", now_us() - t0, kin);
             ++kin; progressed = 1;
         }
         if (kgpu < kin && (!bounce_in || copy_left(&in_left[SLOT_OF(kgpu)]) == 0)) {      /* GPU */
@@ -679,6 +711,7 @@ static int run_chunked(devctx *c, const pipe_part *p)
             }
             if (g_burn && !p->resident) CU(cudaMemsetAsync(d, 0, chunk, st));
             CU(cudaEventRecord(c->rev[r], st));
+            TRACE("[uaes] %8.0f GPU %zu\n", now_us() - t0, kgpu);
             ++kgpu; progressed = 1;
         }
         if (kout < kgpu) {                                                  /* OUT */
@@ -687,6 +720,7 @@ static int run_chunked(devctx *c, const pipe_part *p)
             if (q == cudaSuccess) {
                 const size_t k = kout, obytes = BYTES_OF(k) + (k + 1 == n ? p->out_extra : 0);
                 if (bounce_out && p->out) copy_async(p->out + OFF_OF(k), HOST_OF(r), obytes, &out_left[r]);
+                TRACE("[uaes] %8.0f OUT %zu\n", now_us() - t0, kout);
                 ++kout; progressed = 1;
             } else if (q != cudaErrorNotReady) {
                 rc = fail(UAES_E_CUDA, "staging pipeline", (int)q);
@@ -696,6 +730,7 @@ static int run_chunked(devctx *c, const pipe_part *p)
             }
         }
         if (kdone < kout && (!bounce_out || copy_left(&out_left[SLOT_OF(kdone)]) == 0)) {    /* retire */
+            TRACE("[uaes] %8.0f RET %zu\n", now_us() - t0, kdone);
             ++kdone; progressed = 1;
         }
         if (!progressed) {
@@ -714,6 +749,7 @@ done:
     }
     if (g_burn && bounce)
         for (i = 0; i < NSLOT; ++i) if (c->hslot[i]) memset(c->hslot[i], 0, CHUNK_BYTES);
+    TRACE("[uaes] %8.0f done rc %d\n", now_us() - t0, rc);
     return rc;
 #undef SLOT_OF
 #undef DEV_OF
@@ -1312,9 +1348,15 @@ static int gcm_common(int keybits, const u8 *key, const u8 *nonce, size_t noncel
      * for the zero-copy path (an empty message still has a tag to write when encrypting) */
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
     else         direct = is_direct(out) && (len == 0 || is_direct(in));
-    if (!direct && len > CHUNK_BYTES) {
-        rc = gcm_staged(c, &ks, j0, aad, aadlen, in, len, out, taglen, decrypt);
-        goto wipe;
+    if (!direct) {
+        /* more than one pipeline chunk (64 MiB pinned, 8 MiB pageable): one shard per chunk, copies overlapped */
+        pipe_part pp;
+        memset(&pp, 0, sizeof pp);
+        pp.in = (const u8 *)in; pp.out = (u8 *)out; pp.len = len; pp.unit = 16;
+        if (len > pipe_chunk_bytes(&pp)) {
+            rc = gcm_staged(c, &ks, j0, aad, aadlen, in, len, out, taglen, decrypt);
+            goto wipe;
+        }
     }
     if (!direct) { pthread_mutex_lock(&c->lock); locked = 1; }     /* the staged path owns big and st[0] */
     st = direct ? (cudaStream_t)tls_stream : c->st[0];

@@ -866,8 +866,9 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
         cudaError_t e = opt_in_smem(ctr_queue_kernel<NR, 384, 2>);
         if (e != cudaSuccess) return e;
         if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
-        // one CTA per SM; fewer when there are not even 2 units per table-driven warp
-        const uint64_t sms = (uint64_t)sm_count(), want = (a.q_units + 2 * 12 - 1) / (2 * 12);
+        // one CTA per SM; fewer when there is not even one unit per table-driven warp (latency of short calls:
+        // a unit takes a warp ~55 us, a CTA's table fill ~10 us)
+        const uint64_t sms = (uint64_t)sm_count(), want = (a.q_units + 12 - 1) / 12;
         ctr_queue_kernel<NR, 384, 2><<<(unsigned)(want < 1 ? 1 : want < sms ? want : sms), 384 + kBsThreads, kDynSmem, st>>>(a);
         ++g_launches;
         return cudaGetLastError();

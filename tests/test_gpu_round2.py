@@ -359,6 +359,15 @@ def test_pageable_and_pinned_host_buffers(uaes, orc, torch, small_chunks):
     uaes.ctr_crypt_range(128, key, iv, 0, reg.ctypes.data, n, reg.ctypes.data)
     assert uaes.core().uaes_host_unregister(reg.ctypes.data) == 0
     assert reg.tobytes() == want
+    # GCM on pageable memory with the DEFAULT staging geometry: 8 MiB ring pieces, one shard each
+    uaes.set_staging(64 * MIB, 3)
+    gp = rnd("pg-g", 1000) * 12600                                      # ~12 MiB
+    gbuf = np.frombuffer(gp + bytes(16), dtype=np.uint8).copy()
+    uaes.gcm_encrypt(128, key, iv, b"aad", gbuf.ctypes.data, len(gp), gbuf.ctypes.data)
+    assert gbuf.tobytes() == orc.gcm_encrypt(key, iv, b"aad", gp)
+    assert uaes.gcm_decrypt(128, key, iv, b"aad", gbuf.ctypes.data, len(gp), gbuf.ctypes.data) == 0
+    assert gbuf[:len(gp)].tobytes() == gp
+    uaes.set_staging(1 * MIB, 3)
     # the other staged modes on pageable memory
     keys = rnd("pg-x", 64)
     sec = np.frombuffer(rnd("pg-s", 4 * MIB), dtype=np.uint8).copy()
