@@ -10,6 +10,10 @@ namespace uaes {
 // geometry of the kernels with the bitsliced co-runner (table-driven threads; share of the work, per 1024)
 constexpr int kXtsTtThreads = 384;
 constexpr int kXtsDefaultShare = 165;
+#ifndef UAES_XTS_QUEUE_DEFAULT
+#define UAES_XTS_QUEUE_DEFAULT 1
+#endif
+constexpr int kXtsQueueDefault = UAES_XTS_QUEUE_DEFAULT;   // 1: work queue instead of the static share (encryption with the co-runner)
 
 // Encryption with ONLY Te0 available at table offset OFF (decrypt kernels keep Te0 next to the
 // inverse tables so that they can still encrypt sector tweaks): Te_k = Te0 rotated by 8k bits.
@@ -325,8 +329,10 @@ static cudaError_t launch_xts_sectors_nr(const XtsSectorArgs &a, cudaStream_t st
 // words before the transposes into planes and after the transposes back.
 struct XtsHybridArgs {
     XtsSectorArgs x;             // sector_blocks == 32
-    uint64_t tt_tiles;           // tiles [0, tt_tiles) of 32 sectors: table-driven warps
+    uint64_t tt_tiles;           // static split: tiles [0, tt_tiles) of 32 sectors: table-driven warps
     uint64_t ntiles;             // the rest: bitsliced warps
+    unsigned long long *q;       // non-null: no static split -- the two-ended work queue of ctr_queue_kernel, unit = one tile
+    uint32_t q_zero;             // 0 (see q_post)
     BsKeyPlanesFull bs;          // x.k1 (encryption schedule, or the inverse schedule) as planes
 };
 
@@ -393,6 +399,15 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
 
     if (threadIdx.x >= kXtsTtThreads) {
         reg_inc<kBsRegs>();
+        if (a.q) {                                   // work queue: tiles from the BACK, the next one claimed a tile ahead
+            uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.ntiles);
+            while (u != kQNone) {
+                const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);
+                xts_bitsliced_warp<NR, ENC>(a, lb, u, u + 1);
+                u = q_back(posted, a.ntiles);
+            }
+            return;
+        }
         const uint64_t nbs = a.ntiles - a.tt_tiles;
         const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
         const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
@@ -404,14 +419,17 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
     }
     reg_dec<kTtRegs>();
 
-    // table-driven warps: a contiguous run of tiles each, two sectors in flight
+    // table-driven warps: a contiguous run of tiles each (static split) or tiles claimed from the FRONT of
+    // the work queue, two sectors in flight
     const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
     const uint64_t per = (a.tt_tiles + nw - 1) / nw;
-    const uint64_t q0 = gw * per < a.tt_tiles ? gw * per : a.tt_tiles;
-    const uint64_t q1 = q0 + per < a.tt_tiles ? q0 + per : a.tt_tiles;
+    const uint64_t q0 = a.q ? q_front(q_post(a.q, 1ull, a.q_zero), a.ntiles) : gw * per < a.tt_tiles ? gw * per : a.tt_tiles;
+    const uint64_t q1 = a.q ? kQNone : q0 + per < a.tt_tiles ? q0 + per : a.tt_tiles;
     const uint32_t *k1 = a.x.k1.w;
-    for (uint64_t tile = q0; tile < q1; ++tile) {
+    unsigned long long posted = 0;
+    for (uint64_t tile = q0; tile < q1; tile = a.q ? q_front(posted, a.ntiles) : tile + 1) {
+        if (a.q) posted = q_post(a.q, 1ull, a.q_zero);       // the next tile, a tile ahead
         const uint64_t sec0 = tile * 32;
         const uint64_t left = a.x.nsectors - sec0;
         const int nsec = left < 32 ? (int)left : 32;
@@ -457,6 +475,10 @@ static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tile
     a.x = x;
     a.ntiles = (x.nsectors + 31) / 32;
     a.tt_tiles = a.ntiles - bs_tiles;
+    a.q = nullptr; a.q_zero = 0;
+    if (ENC && env_int("UAES_XTS_QUEUE", kXtsQueueDefault)) {          // encryption: dynamic split (the static share is ignored)
+        if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
+    }
     bs_make_key_planes_full(x.k1.w, NR, &a.bs);
     const uint64_t need = (a.ntiles + 15) / 16, sms = (uint64_t)sm_count();
     xts_sectors_hybrid_kernel<NR, ENC><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
