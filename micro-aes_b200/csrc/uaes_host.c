@@ -2166,6 +2166,9 @@ static void dev_release(devctx *c, int all)
             cudaEventDestroy(c->ev[i]);
         }
     }
+    if (all)
+        for (i = 0; i < 16; ++i)
+            if (c->rev_ok[i]) { cudaEventDestroy(c->rev[i]); c->rev_ok[i] = 0; }
     if (all) c->ready = 0;
     pthread_mutex_unlock(&c->lock);
     cudaSetDevice(cur);
