@@ -94,6 +94,12 @@
 #define PRESET_COUNTER  0       /* 0: CTR takes a 12-byte IV, counter field starts at 1;
                                    1: iv[16] is the first counter block verbatim (micro_aes.h:100) */
 #endif
+#ifndef UAES_CTR_IV_LENGTH
+#define UAES_CTR_IV_LENGTH 12   /* bytes of iv copied into the counter block (micro_aes.h:99); <= 16 */
+#endif
+#ifndef UAES_CTR_START_VALUE
+#define UAES_CTR_START_VALUE 1  /* XORed big-endian into the end of the block (micro_aes.h:98, micro_aes.c:971) */
+#endif
 #ifndef UAES_GCM_NONCE_LEN
 #define UAES_GCM_NONCE_LEN 12
 #endif
@@ -103,11 +109,11 @@
 
 enum constant_parameters_of_modes
 {
-    CTR_START_VALUE = 1,        /* micro_aes.h:98  */
+    CTR_START_VALUE = UAES_CTR_START_VALUE,     /* micro_aes.h:98  */
 #if PRESET_COUNTER
     CTR_IV_LENGTH   = 16,       /* micro_aes.h:99-100: the whole counter block */
 #else
-    CTR_IV_LENGTH   = 12,       /* micro_aes.h:99  */
+    CTR_IV_LENGTH   = UAES_CTR_IV_LENGTH,       /* micro_aes.h:99  */
 #endif
     GCM_NONCE_LEN   = UAES_GCM_NONCE_LEN,   /* micro_aes.h:108: 12 is the recommended value, others are supported */
     GCM_TAG_LEN     = UAES_GCM_TAG_LEN,     /* micro_aes.h:109 */

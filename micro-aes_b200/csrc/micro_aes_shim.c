@@ -41,8 +41,21 @@ void AES_CTR_encrypt(const uint8_t *key, const uint8_t *iv,
 {
 #if PRESET_COUNTER
     uaes_ctr_crypt_block(BITS, key, iv, 0, pntxt, ptextLen, crtxt);             /* micro_aes.c:964-966 */
-#else
+#elif UAES_CTR_IV_LENGTH == 12 && UAES_CTR_START_VALUE == 1
     uaes_ctr_crypt(BITS, key, iv, pntxt, ptextLen, crtxt);
+#else
+    /* any other CTR_IV_LENGTH / CTR_START_VALUE (micro_aes.c:967-971): ctr = iv || 0.., start value XORed
+     * big-endian into its last bytes; the block then counts like the preset one */
+    uint8_t ctr[16];
+    unsigned long start = (unsigned long)UAES_CTR_START_VALUE;
+    int i;
+    for (i = 0; i < 16; ++i) ctr[i] = i < UAES_CTR_IV_LENGTH ? iv[i] : 0;
+    for (i = 15; ; --i) {                                                       /* xorBEint, micro_aes.c:410-415 */
+        ctr[i] ^= (uint8_t)start;
+        start >>= 8;
+        if (!start || i == 0) break;
+    }
+    uaes_ctr_crypt_block(BITS, key, ctr, 0, pntxt, ptextLen, crtxt);
 #endif
 }
 

@@ -180,6 +180,14 @@ def variant_samples():
         pc.AES_CTR_encrypt(key, ctr, pt, ctypes.c_size_t(n), ct)
         out["ctr_preset_counter"].append({"n": n, "key": key.hex(), "counter0": ctr.hex(), "pt_tag": f"vpp{n}",
                                           "ct_sha256": sha(ct.raw[:n])})
+    civ = L("civ8")                        # CTR_IV_LENGTH = 8, CTR_START_VALUE = 0x01020304 (micro_aes.c:967-971)
+    out["ctr_iv8_start"] = []
+    for n in (0, 1, 16, 57, 4096 + 5, 1 << 18):
+        key, iv, pt = rnd(f"vik{n}", 16), rnd(f"vii{n}", 8), rnd(f"vip{n}", n)
+        ct = ctypes.create_string_buffer(n + 16)
+        civ.AES_CTR_encrypt(key, iv, pt, ctypes.c_size_t(n), ct)
+        out["ctr_iv8_start"].append({"n": n, "key": key.hex(), "iv": iv.hex(), "start": 0x01020304, "pt_tag": f"vip{n}",
+                                     "ct_sha256": sha(ct.raw[:n])})
     for v, ivlen in (("iv1", 1), ("iv128", 128)):
         lib = L(v)
         lib.AES_GCM_decrypt.restype = ctypes.c_char

@@ -137,6 +137,12 @@ def test_shim_variants_match_reference_builds(uaes, orc):
         back = hbuf(c["n"])
         pc.AES_CTR_decrypt(H(c["key"]), H(c["counter0"]), out.raw[:c["n"]], c["n"], back)
         assert back.raw[:c["n"]] == p
+    civ = uaes.shim("128_civ8")                # CTR_IV_LENGTH = 8, CTR_START_VALUE = 0x01020304
+    for c in v["ctr_iv8_start"]:
+        p = rnd(c["pt_tag"], c["n"])
+        out = hbuf(c["n"])
+        civ.AES_CTR_encrypt(H(c["key"]), H(c["iv"]), p, c["n"], out)
+        assert sha256(out.raw[:c["n"]]) == c["ct_sha256"], c
     for c in v["gcm_nonce"]:
         lib = uaes.shim(f"128_iv{c['noncelen']}")
         aad, p = rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"])

@@ -388,6 +388,11 @@ def test_variant_recorded_reference_outputs(orc):
     for c in v["ctr_preset_counter"]:
         pt = rnd(c["pt_tag"], c["n"])
         assert sha256(orc.ctr_block(H(c["key"]), H(c["counter0"]), pt)) == c["ct_sha256"], c
+    for c in v["ctr_iv8_start"]:               # CTR_IV_LENGTH = 8, CTR_START_VALUE = 0x01020304: iv || 0.., start XORed in
+        blk = bytearray(H(c["iv"]) + bytes(8))
+        for i, b in enumerate(c["start"].to_bytes(4, "big")):
+            blk[12 + i] ^= b
+        assert sha256(orc.ctr_block(H(c["key"]), bytes(blk), rnd(c["pt_tag"], c["n"]))) == c["ct_sha256"], c
     for c in v["gcm_nonce"]:
         aad, pt = rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"])
         out = orc.gcm_encrypt_ex(H(c["key"]), H(c["nonce"]), aad, pt)
