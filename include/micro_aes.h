@@ -106,6 +106,15 @@
 #ifndef UAES_GCM_TAG_LEN
 #define UAES_GCM_TAG_LEN   16
 #endif
+#ifndef UAES_CCM_TAG_LEN
+#define UAES_CCM_TAG_LEN   16      /* even, 4..16 (micro_aes.h:105) */
+#endif
+#ifndef UAES_EAX_TAG_LEN
+#define UAES_EAX_TAG_LEN   16
+#endif
+#ifndef UAES_OCB_TAG_LEN
+#define UAES_OCB_TAG_LEN   16
+#endif
 
 enum constant_parameters_of_modes
 {
@@ -120,11 +129,11 @@ enum constant_parameters_of_modes
     SIVGCM_NONCE_LEN = 12,      /* micro_aes.h:112 */
     SIVGCM_TAG_LEN  = 16,       /* micro_aes.h:113 */
     CCM_NONCE_LEN   = 11,       /* micro_aes.h:104 */
-    CCM_TAG_LEN     = 16,       /* micro_aes.h:105 */
+    CCM_TAG_LEN     = UAES_CCM_TAG_LEN,         /* micro_aes.h:105 */
     EAX_NONCE_LEN   = 16,       /* micro_aes.h:120 */
-    EAX_TAG_LEN     = 16,       /* micro_aes.h:121 */
+    EAX_TAG_LEN     = UAES_EAX_TAG_LEN,         /* micro_aes.h:121 */
     OCB_NONCE_LEN   = 12,       /* micro_aes.h:116 */
-    OCB_TAG_LEN     = 16,       /* micro_aes.h:117 */
+    OCB_TAG_LEN     = UAES_OCB_TAG_LEN,         /* micro_aes.h:117 */
 #if AES___ != 256 && AES___ != 192
     AES_KEYLENGTH   = 16
 #else

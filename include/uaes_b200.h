@@ -216,6 +216,23 @@ int uaes_ocb_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
 int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce,
                      const void *aad, size_t aadlen, const void *in, size_t len, void *out);
 
+/* the reference built with OCB_TAG_LEN / CCM_TAG_LEN / EAX_TAG_LEN < 16 (micro_aes.h:105, 117, 121): out holds
+ * len + taglen (encrypt), in holds len + taglen (decrypt).  OCB: 1..16, the length also enters the nonce block
+ * (micro_aes.c:1707); CCM: even, 4..16, it enters the flags of the first MAC block (micro_aes.c:1229); EAX: 1..16,
+ * a plain truncation (micro_aes.c:1594, 1638).  Single messages only; the batch calls use 16-byte tags. */
+int uaes_ocb_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen);
+int uaes_ocb_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen);
+int uaes_ccm_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen);
+int uaes_ccm_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen);
+int uaes_eax_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen);
+int uaes_eax_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen);
+
 /* One GCM message sharded over several GPUs (or calls).  Each shard holds a contiguous byte range
  * starting at block `first_block` of the message; all shards but the last are multiples of 16
  * bytes.  uaes_gcm_shard runs the fused CTR + GHASH pass over the shard (encrypt: GHASH over the

@@ -61,6 +61,12 @@ UAES_ABI = {
     "uaes_gcm_encrypt_ex": (_int, [_int, _cp, _cp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "uaes_gcm_decrypt_ex": (_int, [_int, _cp, _cp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "uaes_cbc_decrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _int]),
+    "uaes_ocb_encrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_ocb_decrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_ccm_encrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_ccm_decrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_eax_encrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "uaes_eax_decrypt_ex": (_int, [_int, _cp, _cp, _vp, _sz, _vp, _sz, _vp, _sz]),
     "uaes_xts_encrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_xts_decrypt": (_int, [_int, _cp, _cp, _vp, _sz, _vp]),
     "uaes_xts_sectors": (_int, [_int, _cp, _u64, _sz, _vp, _sz, _vp, _int]),
@@ -420,6 +426,12 @@ def gcm_encrypt_ex(bits, key, nonce, aad, src, nbytes, dst, taglen=16):
 def gcm_decrypt_ex(bits, key, nonce, aad, src, nbytes, dst, taglen=16):
     return check(core().uaes_gcm_decrypt_ex(bits, key, nonce, len(nonce), _ptr(aad), len(aad) if aad else 0,
                                             _ptr(src), nbytes, _ptr(dst), taglen))
+
+
+def aead_ex(mode, bits, key, nonce, aad, src, nbytes, dst, taglen, encrypt=True):
+    """uaes_{ocb,ccm,eax}_{en,de}crypt_ex: one message with a tag of `taglen` bytes; returns the result code"""
+    f = getattr(core(), f"uaes_{mode}_{'encrypt' if encrypt else 'decrypt'}_ex")
+    return check(f(bits, key, nonce, _ptr(aad) if aad else None, len(aad) if aad else 0, _ptr(src), nbytes, _ptr(dst), taglen))
 
 
 def cbc_decrypt_ex(bits, key, iv, src, nbytes, dst, cts=True):

@@ -123,14 +123,14 @@ void AES_OCB_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *pntxt, const size_t ptextLen, void *crtxt)
 {
-    uaes_ocb_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+    uaes_ocb_encrypt_ex(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt, OCB_TAG_LEN);
 }
 
 char AES_OCB_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt)
 {
-    return code(uaes_ocb_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+    return code(uaes_ocb_decrypt_ex(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt, OCB_TAG_LEN),
                 M_DECRYPTION_ERROR);
 }
 
@@ -138,14 +138,14 @@ void AES_CCM_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *pntxt, const size_t ptextLen, void *crtxt)
 {
-    uaes_ccm_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+    uaes_ccm_encrypt_ex(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt, CCM_TAG_LEN);
 }
 
 char AES_CCM_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt)
 {
-    return code(uaes_ccm_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+    return code(uaes_ccm_decrypt_ex(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt, CCM_TAG_LEN),
                 M_DECRYPTION_ERROR);
 }
 
@@ -153,14 +153,14 @@ void AES_EAX_encrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *pntxt, const size_t ptextLen, void *crtxt)
 {
-    uaes_eax_encrypt(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt);
+    uaes_eax_encrypt_ex(BITS, key, nonce, aData, aDataLen, pntxt, ptextLen, crtxt, EAX_TAG_LEN);
 }
 
 char AES_EAX_decrypt(const uint8_t *key, const uint8_t *nonce,
                      const void *aData, const size_t aDataLen,
                      const void *crtxt, const size_t crtxtLen, void *pntxt)
 {
-    return code(uaes_eax_decrypt(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt),
+    return code(uaes_eax_decrypt_ex(BITS, key, nonce, aData, aDataLen, crtxt, crtxtLen, pntxt, EAX_TAG_LEN),
                 M_DECRYPTION_ERROR);
 }
 

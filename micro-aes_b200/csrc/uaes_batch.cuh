@@ -33,9 +33,22 @@ struct BatchArgs {
     const uint8_t *in;
     uint8_t *out;
     int decrypt;
+    uint32_t taglen;              // CCM_TAG_LEN / EAX_TAG_LEN (micro_aes.h:105, 121): bytes of tag behind each message
 };
 
 struct Blk { uint32_t w[4]; };
+
+// first n bytes of a block differ?  (memcmp_s(tag, computed, TAG_LEN), micro_aes.c:1308, 1638)
+__device__ __forceinline__ uint32_t tag_diff(const Blk &got, const Blk &tag, uint32_t n)
+{
+    uint32_t d = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t keep = n >= 4 * i + 4 ? 0xffffffffu : n > 4 * i ? (1u << (8 * (n - 4 * i))) - 1 : 0u;
+        d |= (got.w[i] ^ tag.w[i]) & keep;
+    }
+    return d;
+}
 
 constexpr int kBatchThreads = 512;        // 128 registers per lane: two cipher states + descriptors, no spills
 
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) ccm_batch_kernel(const __gri
 
         // ---- CCMtag, header part (micro_aes.c:1228-1251)
         Blk m = iv;
-        m.w[0] |= (16 - 2) << 2;                      // :1229
+        m.w[0] |= (a.taglen - 2) << 2;                // :1229: M' = (CCM_TAG_LEN - 2) / 2 in bits 3..5
         m.w[3] ^= bswap32(d.len);                     // xorBEint(M, ptextLen, LAST), :1230
         Blk A = {{0, 0, 0, 0}};
         uint32_t head = 0;
@@ -184,11 +197,10 @@ __global__ void __launch_bounds__(kBatchThreads, 1) ccm_batch_kernel(const __gri
         Blk tag;
         for (int i = 0; i < 4; ++i) tag.w[i] = m.w[i] ^ s0.w[i];
         if (a.decrypt) {                              // :1308-1313; the plaintext stays (SABOTAGE is off)
-            const Blk got = load_bytes(src + d.len, 16);
-            const uint32_t diff = (got.w[0] ^ tag.w[0]) | (got.w[1] ^ tag.w[1]) | (got.w[2] ^ tag.w[2]) | (got.w[3] ^ tag.w[3]);
-            a.msgs[mi].result = diff ? 0x1A : 0;
+            const Blk got = load_bytes(src + d.len, a.taglen);
+            a.msgs[mi].result = tag_diff(got, tag, a.taglen) ? 0x1A : 0;
         } else {
-            store_bytes(dst + d.len, tag, 16);
+            store_bytes(dst + d.len, tag, a.taglen);  // :1281
             a.msgs[mi].result = 0;
         }
     }
@@ -308,12 +320,12 @@ __global__ void __launch_bounds__(kBatchThreads, 1) eax_batch_kernel(const __gri
         if (!a.decrypt) {
             ctr_walk<NR>(lb, rk, N, src, dst, d.len);                             // :1584, counter starts AT N
             xor_blk(tag, omac<NR>(lb, rk, k1, k2, 2, dst, d.len));                // :1593, over the ciphertext
-            store_bytes(dst + d.len, tag, 16);
+            store_bytes(dst + d.len, tag, a.taglen);                              // :1594
             a.msgs[mi].result = 0;
         } else {                                                                  // :1625-1647: verify, then decrypt
             xor_blk(tag, omac<NR>(lb, rk, k1, k2, 2, src, d.len));
-            const Blk got = load_bytes(src + d.len, 16);
-            const uint32_t diff = (got.w[0] ^ tag.w[0]) | (got.w[1] ^ tag.w[1]) | (got.w[2] ^ tag.w[2]) | (got.w[3] ^ tag.w[3]);
+            const Blk got = load_bytes(src + d.len, a.taglen);
+            const uint32_t diff = tag_diff(got, tag, a.taglen);                   // :1638
             a.msgs[mi].result = diff ? 0x1A : 0;
             if (!diff) ctr_walk<NR>(lb, rk, N, src, dst, d.len);
         }
@@ -488,7 +500,7 @@ static cudaError_t launch_ccm_batch_nr(const BatchArgs &a, cudaStream_t st)
 
 }  // namespace uaes
 
-extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void *msgs_dev, u64 n,
+extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, unsigned taglen, void *msgs_dev, u64 n,
                                      const void *aad, const void *in, void *out, void *stream)
 {
     if (n == 0) return 0;
@@ -496,7 +508,7 @@ extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void 
     a.ks = *ks; a.ks2 = *ks;
     a.msgs = (uaes::BatchMsg *)msgs_dev; a.n = n;
     a.aad = (const uint8_t *)aad; a.in = (const uint8_t *)in; a.out = (uint8_t *)out;
-    a.decrypt = decrypt;
+    a.decrypt = decrypt; a.taglen = taglen;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ks->rounds) {
     case 10: return (int)uaes::launch_ccm_batch_nr<10>(a, st);
@@ -508,14 +520,15 @@ extern "C" int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void 
 
 // mode: 1 = EAX (ks), 2 = SIV (ks = S2V key, ks2 = CTR key), 3 = GCM (ks)
 extern "C" int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt,
-                                     void *msgs_dev, u64 n, const void *aad, const void *in, void *out, void *stream)
+                                     unsigned taglen, void *msgs_dev, u64 n, const void *aad, const void *in, void *out,
+                                     void *stream)
 {
     if (n == 0) return 0;
     uaes::BatchArgs a;
     a.ks = *ks; a.ks2 = ks2 ? *ks2 : *ks;
     a.msgs = (uaes::BatchMsg *)msgs_dev; a.n = n;
     a.aad = (const uint8_t *)aad; a.in = (const uint8_t *)in; a.out = (uint8_t *)out;
-    a.decrypt = decrypt;
+    a.decrypt = decrypt; a.taglen = taglen;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ks->rounds * 4 + mode) {
     case 41: return (int)uaes::launch_batch_nr<10, 1>(a, st);

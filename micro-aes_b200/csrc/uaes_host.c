@@ -1674,7 +1674,7 @@ int uaes_cfb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *iv, const v
 /* micro_aes.c:1779-1813.  One pass; decrypt writes the plaintext and then reports the tag
  * comparison, exactly like the reference (micro_aes.c:1806-1812). */
 static int ocb_common(int keybits, const u8 *key, const u8 *nonce, const void *aad, size_t aadlen,
-                      const void *in, size_t len, void *out, int decrypt)
+                      const void *in, size_t len, void *out, size_t taglen, int decrypt)
 {
     devctx *c;
     uaes_keysched enc, dec;
@@ -1686,6 +1686,7 @@ static int ocb_common(int keybits, const u8 *key, const u8 *nonce, const void *a
     cudaStream_t st;
 
     if (expand_key(keybits, key, &enc)) return fail(UAES_E_BAD_ARGUMENT, "key size must be 128, 192 or 256", 0);
+    if (taglen < 1 || taglen > 16) return fail(UAES_E_BAD_ARGUMENT, "OCB tag length must be 1..16 bytes", 0);
     if (decrypt) invert_schedule(&enc, &dec);
     if ((rc = get_ctx(&c)) != 0) return rc;
     if (decrypt) direct = len == 0 || (is_direct(in) && is_direct(out));
@@ -1707,21 +1708,21 @@ static int ocb_common(int keybits, const u8 *key, const u8 *nonce, const void *a
     } else {
         if ((rc = grow(&c->big, &c->big_bytes, len + 32, "cudaMalloc(OCB staging)")) != 0) goto done;
         CU(cudaStreamSynchronize((cudaStream_t)tls_stream));
-        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? 16 : 0), cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(c->big, in, len + (decrypt ? taglen : 0), cudaMemcpyDefault, st));
         din = c->big; dout = c->big;
     }
     if (!decrypt) {
-        LAUNCH(uaes_launch_ocb(&enc, &enc, 1, nonce, daad, aadlen, din, dout, len, (u8 *)dout + len, work, st));
-        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + 16, cudaMemcpyDefault, st));
+        LAUNCH(uaes_launch_ocb(&enc, &enc, 1, nonce, daad, aadlen, din, dout, len, (u8 *)dout + len, (unsigned)taglen, work, st));
+        if (!direct) CU(cudaMemcpyAsync(out, c->big, len + taglen, cudaMemcpyDefault, st));
         if (!direct || !tls_async) CU(cudaStreamSynchronize(st));
     } else {
         u8 t1[16], t2[16];
-        CU(cudaMemcpyAsync(t2, (const u8 *)din + len, 16, cudaMemcpyDefault, st));   /* before it can be overwritten */
-        LAUNCH(uaes_launch_ocb(&enc, &dec, 0, nonce, daad, aadlen, din, dout, len, dtag, work, st));
+        CU(cudaMemcpyAsync(t2, (const u8 *)din + len, taglen, cudaMemcpyDefault, st));   /* before it can be overwritten */
+        LAUNCH(uaes_launch_ocb(&enc, &dec, 0, nonce, daad, aadlen, din, dout, len, dtag, (unsigned)taglen, work, st));
         if (!direct && len) CU(cudaMemcpyAsync(out, c->big, len, cudaMemcpyDefault, st));
-        CU(cudaMemcpyAsync(t1, dtag, 16, cudaMemcpyDefault, st));
+        CU(cudaMemcpyAsync(t1, dtag, taglen, cudaMemcpyDefault, st));
         CU(cudaStreamSynchronize(st));
-        if (memcmp(t1, t2, 16)) rc = UAES_AUTH_ERROR;
+        if (memcmp(t1, t2, taglen)) rc = UAES_AUTH_ERROR;            /* micro_aes.c:1807 */
     }
 done:
     scratch_put(c, w, st);
@@ -1733,13 +1734,27 @@ done:
 int uaes_ocb_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 0);
+    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 16, 0);
 }
 
 int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 1);
+    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, 16, 1);
+}
+
+/* the reference built with OCB_TAG_LEN < 16 (micro_aes.h:117): the length enters the nonce block
+ * (micro_aes.c:1707) and cuts the tag (micro_aes.c:1783, 1807) */
+int uaes_ocb_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen)
+{
+    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, taglen, 0);
+}
+
+int uaes_ocb_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen)
+{
+    return ocb_common(keybits, key, nonce, aad, aadlen, in, len, out, taglen, 1);
 }
 
 /* ------------------------------------------------------------------ CCM, batched */
@@ -1751,15 +1766,15 @@ int uaes_ocb_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, cons
 #define BATCH_SIV 2
 #define BATCH_GCM 3
 
-static int launch_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt, void *msgs_dev,
-                        u64 n, const void *aad, const void *in, void *out, void *stream)
+static int launch_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt, unsigned taglen,
+                        void *msgs_dev, u64 n, const void *aad, const void *in, void *out, void *stream)
 {
-    if (mode == BATCH_CCM) return uaes_launch_ccm_batch(ks, decrypt, msgs_dev, n, aad, in, out, stream);
-    return uaes_launch_mac_batch(mode, ks, ks2, decrypt, msgs_dev, n, aad, in, out, stream);
+    if (mode == BATCH_CCM) return uaes_launch_ccm_batch(ks, decrypt, taglen, msgs_dev, n, aad, in, out, stream);
+    return uaes_launch_mac_batch(mode, ks, ks2, decrypt, taglen, msgs_dev, n, aad, in, out, stream);
 }
 
 static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_t n,
-                     const void *aad, const void *in, void *out, int decrypt)
+                     const void *aad, const void *in, void *out, int decrypt, size_t taglen)
 {
     devctx *c;
     uaes_keysched ks, ks2;
@@ -1784,12 +1799,12 @@ static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_
             goto done;
         }
         st = (cudaStream_t)tls_stream;
-        LAUNCH(launch_batch(mode, &ks, &ks2, decrypt, msgs, n, aad, in, out, st));
+        LAUNCH(launch_batch(mode, &ks, &ks2, decrypt, (unsigned)taglen, msgs, n, aad, in, out, st));
         if (!tls_async) CU(cudaStreamSynchronize(st));
         goto done;                                   /* per-message results stay on the device */
     }
     for (i = 0; i < n; ++i) {
-        const size_t tag_in = decrypt ? 16 : 0, tag_out = decrypt ? 0 : 16;
+        const size_t tag_in = decrypt ? taglen : 0, tag_out = decrypt ? 0 : taglen;
         if (msgs[i].in_off + msgs[i].len + tag_in > in_ext) in_ext = msgs[i].in_off + msgs[i].len + tag_in;
         if (msgs[i].out_off + msgs[i].len + tag_out > out_ext) out_ext = msgs[i].out_off + msgs[i].len + tag_out;
         if (msgs[i].aad_len && msgs[i].aad_off + msgs[i].aad_len > aad_ext) aad_ext = msgs[i].aad_off + msgs[i].aad_len;
@@ -1816,7 +1831,7 @@ static int mac_batch(int mode, int keybits, const u8 *key, uaes_msg *msgs, size_
         /* bytes of the output range that no message covers must survive the copy back */
         if (out_ext) CU(cudaMemcpyAsync(dout, out, out_ext, cudaMemcpyDefault, st));
     }
-    LAUNCH(launch_batch(mode, &ks, &ks2, decrypt, dmsgs, n, daad, din, dout, st));
+    LAUNCH(launch_batch(mode, &ks, &ks2, decrypt, (unsigned)taglen, dmsgs, n, daad, din, dout, st));
     if (dout != out && out_ext) CU(cudaMemcpyAsync(out, dout, out_ext, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(msgs, dmsgs, n * sizeof(uaes_msg), cudaMemcpyDefault, st));
     CU(cudaStreamSynchronize(st));
@@ -1830,7 +1845,7 @@ done:
 
 #define BATCH_ENTRY(name, mode, dec) \
     int name(int keybits, const uaes_u8 *key, uaes_msg *msgs, size_t n, const void *aad, const void *in, void *out) \
-    { return mac_batch(mode, keybits, key, msgs, n, aad, in, out, dec); }
+    { return mac_batch(mode, keybits, key, msgs, n, aad, in, out, dec, 16); }
 BATCH_ENTRY(uaes_ccm_encrypt_batch, BATCH_CCM, 0)
 BATCH_ENTRY(uaes_ccm_decrypt_batch, BATCH_CCM, 1)
 BATCH_ENTRY(uaes_eax_encrypt_batch, BATCH_EAX, 0)
@@ -1842,38 +1857,64 @@ BATCH_ENTRY(uaes_gcm_decrypt_batch, BATCH_GCM, 1)
 
 /* one message with the reference's argument list = a batch of one */
 static int mac_single(int mode, int keybits, const u8 *key, const u8 *nonce, size_t noncelen, const void *aad,
-                      size_t aadlen, const void *in, size_t len, void *out, int decrypt)
+                      size_t aadlen, const void *in, size_t len, void *out, int decrypt, size_t taglen)
 {
     uaes_msg m;
+    if (taglen < 1 || taglen > 16 || (mode == BATCH_CCM && (taglen < 4 || taglen % 2)))
+        return fail(UAES_E_BAD_ARGUMENT, "tag length must be 1..16 bytes (CCM: even, 4..16)", 0);
     if (len > 0xFFFFFFFFu - 16 || aadlen > 0xFFFFFFFFu) return fail(UAES_E_BAD_ARGUMENT, "message longer than 4 GiB", 0);
     memset(&m, 0, sizeof m);
     m.len = (unsigned int)len; m.aad_len = (unsigned int)aadlen;
     if (noncelen) memcpy(m.nonce, nonce, noncelen);
-    return mac_batch(mode, keybits, key, &m, 1, aad, in, out, decrypt);
+    return mac_batch(mode, keybits, key, &m, 1, aad, in, out, decrypt, taglen);
 }
 
 int uaes_ccm_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 0);
+    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 0, 16);
+}
+
+int uaes_ccm_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen)
+{
+    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 0, taglen);
 }
 
 int uaes_ccm_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 1);
+    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 1, 16);
+}
+
+int uaes_ccm_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen)
+{
+    return mac_single(BATCH_CCM, keybits, key, nonce, 11, aad, aadlen, in, len, out, 1, taglen);
 }
 
 int uaes_eax_encrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 0);
+    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 0, 16);
+}
+
+int uaes_eax_encrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen)
+{
+    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 0, taglen);
 }
 
 int uaes_eax_decrypt(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
                      const void *in, size_t len, void *out)
 {
-    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 1);
+    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 1, 16);
+}
+
+int uaes_eax_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, const void *aad, size_t aadlen,
+                        const void *in, size_t len, void *out, size_t taglen)
+{
+    return mac_single(BATCH_EAX, keybits, key, nonce, 16, aad, aadlen, in, len, out, 1, taglen);
 }
 
 /* The reference keeps the synthetic IV and the ciphertext in separate buffers (micro_aes.c:1372,
@@ -1884,7 +1925,7 @@ int uaes_siv_encrypt(int keybits, const uaes_u8 *keys, const void *aad, size_t a
     int rc;
     u8 *tmp = (u8 *)malloc(len + 16);
     if (!tmp) return fail(UAES_E_NO_MEMORY, "malloc(SIV temporary)", 0);
-    rc = mac_single(BATCH_SIV, keybits, keys, NULL, 0, aad, aadlen, in, len, tmp, 0);
+    rc = mac_single(BATCH_SIV, keybits, keys, NULL, 0, aad, aadlen, in, len, tmp, 0, 16);
     if (rc == 0) {
         memcpy(iv, tmp, 16);
         if (len && cudaMemcpy(out, tmp + 16, len, cudaMemcpyDefault) != cudaSuccess)
@@ -1905,7 +1946,7 @@ int uaes_siv_decrypt(int keybits, const uaes_u8 *keys, const uaes_u8 *iv, const 
         free(tmp);
         return fail(UAES_E_CUDA, "cudaMemcpy(SIV ciphertext)", (int)cudaGetLastError());
     }
-    rc = mac_single(BATCH_SIV, keybits, keys, NULL, 0, aad, aadlen, tmp, len, out, 1);
+    rc = mac_single(BATCH_SIV, keybits, keys, NULL, 0, aad, aadlen, tmp, len, out, 1, 16);
     free(tmp);
     return rc;
 }

@@ -110,7 +110,7 @@ int uaes_launch_chain_dec(const uaes_keysched *ks, const uaes_keysched *kse, int
 size_t uaes_ocb_work_bytes(void);
 int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int encrypt,
                     const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
-                    const void *in, void *out, u64 len, void *tag_out, void *work, void *stream);
+                    const void *in, void *out, u64 len, void *tag_out, unsigned taglen, void *work, void *stream);
 
 /* sum_r partial[r] * H^after[r] (16 bytes, device): many contributions folded into the one of their union */
 int uaes_launch_gcm_fold(const uaes_keysched *ks, const void *partials_dev, const void *after_dev,
@@ -118,11 +118,11 @@ int uaes_launch_gcm_fold(const uaes_keysched *ks, const void *partials_dev, cons
 
 /* CCM over a batch of independent messages, one per lane (uaes_batch.cuh); msgs_dev = device array
  * of uaes_msg records, result fields are written by the kernel */
-int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, void *msgs_dev, u64 n,
+int uaes_launch_ccm_batch(const uaes_keysched *ks, int decrypt, unsigned taglen, void *msgs_dev, u64 n,
                           const void *aad, const void *in, void *out, void *stream);
 
 /* EAX (mode 1) and SIV (mode 2; ks = S2V key, ks2 = CTR key) over a batch, one message per lane */
-int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt,
+int uaes_launch_mac_batch(int mode, const uaes_keysched *ks, const uaes_keysched *ks2, int decrypt, unsigned taglen,
                           void *msgs_dev, u64 n, const void *aad, const void *in, void *out, void *stream);
 
 /* synthetic data + checksum helpers */

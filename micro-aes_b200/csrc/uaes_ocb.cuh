@@ -45,6 +45,7 @@ __device__ inline uint4 ocb_gray_sum(const uint4 *L, uint64_t index)
 struct OcbSetupArgs {
     uaes_keysched ks;            // encryption schedule
     uint32_t nonce[3];
+    uint32_t taglen;             // OCB_TAG_LEN: enters the nonce block (micro_aes.c:1707)
     OcbWork *work;
 };
 
@@ -61,7 +62,8 @@ __global__ void ocb_setup_kernel(const __grid_constant__ OcbSetupArgs a)
     for (int k = 0; k < 64; ++k) { L = ocb_double(L); a.work->L[k] = L; }
     // nonce block: 00 00 00 01 || nonce with its last six bits cleared; bottom = those six bits
     const uint32_t bottom = (a.nonce[2] >> 24) & 63;
-    uint32_t kt[4] = {0x01000000u, a.nonce[0], a.nonce[1], a.nonce[2] & 0xc0ffffffu};
+    // byte 0 carries the tag length: kt[0] |= OCB_TAG_LEN << 4 as a uint8_t (micro_aes.c:1707; 16 -> 0)
+    uint32_t kt[4] = {0x01000000u | ((a.taglen << 4) & 0xffu), a.nonce[0], a.nonce[1], a.nonce[2] & 0xc0ffffffu};
     small_encrypt(a.ks.w, a.ks.rounds, kt);
     const Gf K = gf_from_words(kt[0], kt[1], kt[2], kt[3]);
     const uint64_t ext = K.hi ^ (K.hi << 8 | K.lo >> 56);     // Stretch = K_top || (K_top[0..8) ^ K_top[1..9))
@@ -290,6 +292,7 @@ struct OcbFinishArgs {
     uint64_t aadlen;
     int encrypt;
     uint8_t *tag_out;
+    uint32_t taglen;             // OCB_TAG_LEN
     OcbWork *work;
 };
 
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) ocb_finish_kernel(const __grid_co
     enc_block<NR>(lb, sum.x, sum.y, sum.z, sum.w, rk);
     xor4(sum, pmac);
     const uint32_t tw[4] = {sum.x, sum.y, sum.z, sum.w};
-    store_bytes(a.tag_out, tw, 16);
+    store_bytes(a.tag_out, tw, a.taglen);                   // micro_aes.c:1783
 }
 
 template <int NR, bool ENC>
@@ -402,7 +405,7 @@ extern "C" size_t uaes_ocb_work_bytes(void) { return sizeof(uaes::OcbWork); }
 
 extern "C" int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bulk, int encrypt,
                                const unsigned char nonce[12], const void *aad_dev, u64 aadlen,
-                               const void *in, void *out, u64 len, void *tag_out, void *work, void *stream)
+                               const void *in, void *out, u64 len, void *tag_out, unsigned taglen, void *work, void *stream)
 {
     using namespace uaes;
     cudaStream_t st = (cudaStream_t)stream;
@@ -410,6 +413,7 @@ extern "C" int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bu
     s.ks = *enc;
     for (int c = 0; c < 3; ++c)
         s.nonce[c] = (uint32_t)nonce[4 * c] | (uint32_t)nonce[4 * c + 1] << 8 | (uint32_t)nonce[4 * c + 2] << 16 | (uint32_t)nonce[4 * c + 3] << 24;
+    s.taglen = taglen;
     s.work = (OcbWork *)work;
     ocb_setup_kernel<<<1, 32, 0, st>>>(s);
     ++g_launches;
@@ -435,7 +439,7 @@ extern "C" int uaes_launch_ocb(const uaes_keysched *enc, const uaes_keysched *bu
     f.ks = *enc;
     f.in = (const uint8_t *)in; f.out = (uint8_t *)out; f.len = len;
     f.aad = (const uint8_t *)aad_dev; f.aadlen = aadlen; f.encrypt = encrypt;
-    f.tag_out = (uint8_t *)tag_out; f.work = (OcbWork *)work;
+    f.tag_out = (uint8_t *)tag_out; f.taglen = taglen; f.work = (OcbWork *)work;
     switch (enc->rounds) {
     case 10: return (int)launch_ocb_finish_nr<10>(f, st);
     case 12: return (int)launch_ocb_finish_nr<12>(f, st);

@@ -875,7 +875,7 @@ static void ocb_delta(uint64_t index, const uint8_t Ldollar[16], const uint8_t d
 /* micro_aes.c:1693-1767 (OCB_cipher) */
 static void ocb_cipher(int keybits, const uint8_t *key, const uint8_t nonce[12], int encrypt,
                        const uint8_t *aad, size_t aadlen, const uint8_t *x, size_t len,
-                       uint8_t *y, uint8_t tag[16])
+                       uint8_t *y, size_t taglen, uint8_t tag[16])
 {
     aes_ctx c;
     uint8_t Lstar[16] = {0}, Ldollar[16], ktop[16] = {0}, stretch[24], off0[16], delta[16], sum[16] = {0};
@@ -890,6 +890,7 @@ static void ocb_cipher(int keybits, const uint8_t *key, const uint8_t nonce[12],
     /* nonce block: tag length (128 mod 128 = 0) in the top 7 bits, then 0..01, then the nonce with
      * its last six bits cleared (micro_aes.c:1709-1712) */
     memcpy(ktop + 4, nonce, 12);
+    ktop[0] |= (uint8_t)(taglen << 4);                 /* :1707, OCB_TAG_LEN (16 wraps to 0) */
     ktop[3] |= 1;
     ktop[15] &= 0xC0;
     encrypt_block(&c, ktop, ktop);
@@ -946,22 +947,33 @@ static void ocb_cipher(int keybits, const uint8_t *key, const uint8_t nonce[12],
 }
 
 /* micro_aes.c:1779-1789 */
+void oracle_ocb_encrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
+{
+    uint8_t tag[16];
+    ocb_cipher(keybits, key, nonce, 1, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, (uint8_t *)out, taglen, tag);
+    memcpy((uint8_t *)out + len, tag, taglen);         /* :1783 */
+}
+
+int oracle_ocb_decrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                          const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
+{
+    uint8_t tag[16], got[16];
+    memcpy(got, (const uint8_t *)in + len, taglen);
+    ocb_cipher(keybits, key, nonce, 0, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, (uint8_t *)out, taglen, tag);
+    return memcmp(tag, got, taglen) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;   /* :1807 */
+}
+
 void oracle_ocb_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
                         const void *aad, size_t aadlen, const void *in, size_t len, void *out)
 {
-    uint8_t tag[16];
-    ocb_cipher(keybits, key, nonce, 1, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, (uint8_t *)out, tag);
-    memcpy((uint8_t *)out + len, tag, 16);
+    oracle_ocb_encrypt_ex(keybits, key, nonce, aad, aadlen, in, len, out, 16);
 }
 
-/* micro_aes.c:1802-1813 */
 int oracle_ocb_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[12],
                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
 {
-    uint8_t tag[16], got[16];
-    memcpy(got, (const uint8_t *)in + len, 16);
-    ocb_cipher(keybits, key, nonce, 0, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, (uint8_t *)out, tag);
-    return memcmp(tag, got, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
+    return oracle_ocb_decrypt_ex(keybits, key, nonce, aad, aadlen, in, len, out, 16);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -986,12 +998,12 @@ static void cbcmac_absorb(const aes_ctx *c, const uint8_t *x, size_t len, uint8_
 /* CCMtag (micro_aes.c:1222-1256) with CCM_NONCE_LEN = 11, CCM_TAG_LEN = 16
  * (micro_aes.h:104-105): iv = 03 || nonce || 00000000 */
 static void ccm_tag(const aes_ctx *c, const uint8_t iv[16], const uint8_t *aad, size_t aadlen,
-                    const uint8_t *pt, size_t len, uint8_t tag[16])
+                    const uint8_t *pt, size_t len, size_t taglen, uint8_t tag[16])
 {
     uint8_t m[16], a[16] = {0}, s0[16];
     size_t head = 0, i;
     memcpy(m, iv, 16);
-    m[0] |= (16 - 2) << 2;                       /* :1229 */
+    m[0] |= (uint8_t)((taglen - 2) << 2);        /* :1229, CCM_TAG_LEN */
     for (i = 0; i < 8 && i < sizeof len; ++i)    /* xorBEint(M, ptextLen, LAST), :1230 */
         m[15 - i] ^= (uint8_t)(len >> (8 * i));
     if (aadlen) {
@@ -1026,24 +1038,22 @@ static void ccm_iv(const uint8_t nonce[11], uint8_t iv[16])
 }
 
 /* micro_aes.c:1268-1282; out holds len + 16 */
-void oracle_ccm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
-                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+void oracle_ccm_encrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
 {
     aes_ctx c;
     uint8_t iv[16], ctr[16], tag[16];
     key_setup(&c, keybits, key);
     ccm_iv(nonce, iv);
-    ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, tag);
+    ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, taglen, tag);
     memcpy(ctr, iv, 16);
     ctr_add(ctr, 1);                             /* CCM_GCM pre-increment, :939-941 */
     ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
-    memcpy((uint8_t *)out + len, tag, 16);
+    memcpy((uint8_t *)out + len, tag, taglen);   /* :1281 */
 }
 
-/* micro_aes.c:1295-1314: the plaintext is produced BEFORE the tag is checked and stays
- * in `out` on failure (SABOTAGE is off by default, micro_aes.c:31,376-384) */
-int oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
-                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+int oracle_ccm_decrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                          const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
 {
     aes_ctx c;
     uint8_t iv[16], ctr[16], tag[16];
@@ -1052,8 +1062,20 @@ int oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
     memcpy(ctr, iv, 16);
     ctr_add(ctr, 1);
     ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);
-    ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, tag);
-    return memcmp(tag, (const uint8_t *)in + len, 16) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;
+    ccm_tag(&c, iv, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, taglen, tag);
+    return memcmp(tag, (const uint8_t *)in + len, taglen) ? ORACLE_AUTHENTICATION_ERROR : ORACLE_SUCCESS;   /* :1308 */
+}
+
+void oracle_ccm_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    oracle_ccm_encrypt_ex(keybits, key, nonce, aad, aadlen, in, len, out, 16);
+}
+
+int oracle_ccm_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    return oracle_ccm_decrypt_ex(keybits, key, nonce, aad, aadlen, in, len, out, 16);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1117,8 +1139,8 @@ static void eax_tag(const aes_ctx *c, const uint8_t nonce[16], const uint8_t *aa
 }
 
 /* micro_aes.c:1564-1598 (EAX_NONCE_LEN = 16, EAX_TAG_LEN = 16); out holds len + 16 */
-void oracle_eax_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
-                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+void oracle_eax_encrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
 {
     aes_ctx c;
     uint8_t k1[16], k2[16], N[16], ctr[16], tag[16];
@@ -1128,20 +1150,31 @@ void oracle_eax_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[16]
     memcpy(ctr, N, 16);
     ctr_stream(&c, ctr, (const uint8_t *)in, len, (uint8_t *)out);    /* CTR_DEFAULT: starts AT N, :1584 */
     eax_tag(&c, nonce, (const uint8_t *)aad, aadlen, (const uint8_t *)out, len, N, tag);
-    memcpy((uint8_t *)out + len, tag, 16);
+    memcpy((uint8_t *)out + len, tag, taglen);                        /* :1594 */
 }
 
-/* micro_aes.c:1613-1648: authenticate, then decrypt; `out` is untouched on failure */
-int oracle_eax_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
-                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+int oracle_eax_decrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                          const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen)
 {
     aes_ctx c;
     uint8_t N[16], tag[16];
     key_setup(&c, keybits, key);
     eax_tag(&c, nonce, (const uint8_t *)aad, aadlen, (const uint8_t *)in, len, N, tag);
-    if (memcmp(tag, (const uint8_t *)in + len, 16)) return ORACLE_AUTHENTICATION_ERROR;
+    if (memcmp(tag, (const uint8_t *)in + len, taglen)) return ORACLE_AUTHENTICATION_ERROR;   /* :1638 */
     ctr_stream(&c, N, (const uint8_t *)in, len, (uint8_t *)out);
     return ORACLE_SUCCESS;
+}
+
+void oracle_eax_encrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                        const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    oracle_eax_encrypt_ex(keybits, key, nonce, aad, aadlen, in, len, out, 16);
+}
+
+int oracle_eax_decrypt(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                       const void *aad, size_t aadlen, const void *in, size_t len, void *out)
+{
+    return oracle_eax_decrypt_ex(keybits, key, nonce, aad, aadlen, in, len, out, 16);
 }
 
 /* S2V for one AAD unit, micro_aes.c:1325-1359, written the way RFC 5297 states it (xorend for

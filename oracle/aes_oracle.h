@@ -59,6 +59,20 @@ int  oracle_gcm_decrypt_ex(int keybits, const uint8_t *key, const uint8_t *nonce
                            const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
 int  oracle_cbc_decrypt_nocts(int keybits, const uint8_t *key, const uint8_t iv[16],
                               const void *in, size_t len, void *out);
+/* CCM_TAG_LEN (even, 4..16), EAX_TAG_LEN, OCB_TAG_LEN (1..16) as arguments (micro_aes.c:1229, 1281, 1308, 1594,
+ * 1638, 1707, 1783, 1807); pinned on oracle/_ref/libref128atag.so (8 / 10 / 12 bytes) */
+void oracle_ccm_encrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+int  oracle_ccm_decrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[11],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+void oracle_eax_encrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+int  oracle_eax_decrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[16],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+void oracle_ocb_encrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
+int  oracle_ocb_decrypt_ex(int keybits, const uint8_t *key, const uint8_t nonce[12],
+                           const void *aad, size_t aadlen, const void *in, size_t len, void *out, size_t taglen);
 /* blocks [first_block, ...) of one XTS data unit: the chain of micro_aes.c:1030-1036 started late */
 int  oracle_xts_range(int keybits, const uint8_t *keys, const uint8_t *tweak, uint64_t first_block,
                       const void *in, size_t len, void *out, int encrypt);

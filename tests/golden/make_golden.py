@@ -216,6 +216,24 @@ def variant_samples():
         out["gcm_tag12"].append({"n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(), "aad_tag": f"vta{n}",
                                  "pt_tag": f"vtp{n}", "ct_sha256": sha(ct.raw[:n]), "tag": ct.raw[n:n + 12].hex(),
                                  "rc_forged": rc_bad})
+    at = L("atag")                         # CCM_TAG_LEN = 8, EAX_TAG_LEN = 10, OCB_TAG_LEN = 12 in one build
+    out["aead_tags"] = []
+    for name, fn, dfn, nl, tl in (("ccm", at.AES_CCM_encrypt, at.AES_CCM_decrypt, 11, 8), ("eax", at.AES_EAX_encrypt, at.AES_EAX_decrypt, 16, 10),
+                                  ("ocb", at.AES_OCB_encrypt, at.AES_OCB_decrypt, 12, 12)):
+        dfn.restype = ctypes.c_char
+        for n, a in ((0, 0), (1, 7), (16, 16), (57, 31), (4096 + 3, 129)):
+            key, nonce = rnd(f"vak{name}{n}", 16), rnd(f"van{name}{n}", nl)
+            aad, pt = rnd(f"vaa{name}{n}", a), rnd(f"vap{name}{n}", n)
+            ct = ctypes.create_string_buffer(b"\xee" * (n + 16), n + 16)
+            fn(key, nonce, aad, ctypes.c_size_t(a), pt, ctypes.c_size_t(n), ct)
+            assert ct.raw[n + tl:n + 16] == b"\xee" * (16 - tl)
+            back = ctypes.create_string_buffer(n + 16)
+            assert ord(dfn(key, nonce, aad, ctypes.c_size_t(a), ct, ctypes.c_size_t(n), back)) == 0 and back.raw[:n] == pt
+            bad = bytearray(ct.raw[:n + tl]); bad[-1] ^= 2
+            rc_bad = ord(dfn(key, nonce, aad, ctypes.c_size_t(a), bytes(bad), ctypes.c_size_t(n), ctypes.create_string_buffer(n + 16)))
+            out["aead_tags"].append({"mode": name, "taglen": tl, "n": n, "aadlen": a, "key": key.hex(), "nonce": nonce.hex(),
+                                     "aad_tag": f"vaa{name}{n}", "pt_tag": f"vap{name}{n}", "ct_sha256": sha(ct.raw[:n]),
+                                     "tag": ct.raw[n:n + tl].hex(), "rc_forged": rc_bad})
     for v, mode in (("pad1", 1), ("pad2", 2)):
         lib = L(v)
         for n in (0, 1, 15, 16, 17, 32, 57, 4096, 4096 + 7):

@@ -161,6 +161,20 @@ def test_shim_variants_match_reference_builds(uaes, orc):
         assert sha256(out.raw[:c["n"]]) == c["ct_sha256"]
         bad = bytearray(out.raw[:c["n"] + 12]); bad[-1] ^= 1
         assert ord(t12.AES_GCM_decrypt(H(c["key"]), H(c["nonce"]), aad, len(aad), bytes(bad), c["n"], hbuf(c["n"]))) == c["rc_forged"]
+    at = uaes.shim("128_atag")                 # CCM_TAG_LEN = 8, EAX_TAG_LEN = 10, OCB_TAG_LEN = 12
+    for c in v["aead_tags"]:
+        enc = getattr(at, f"AES_{c['mode'].upper()}_encrypt")
+        dec = getattr(at, f"AES_{c['mode'].upper()}_decrypt")
+        aad, p, tl = rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"]), c["taglen"]
+        out = hbuf(c["n"] + 16, fill=0xEE)
+        enc(H(c["key"]), H(c["nonce"]), aad, len(aad), p, c["n"], out)
+        assert sha256(out.raw[:c["n"]]) == c["ct_sha256"] and out.raw[c["n"]:c["n"] + tl].hex() == c["tag"], c
+        assert out.raw[c["n"] + tl:] == b"\xee" * (16 - tl), c
+        back = hbuf(c["n"])
+        assert ord(dec(H(c["key"]), H(c["nonce"]), aad, len(aad), out.raw[:c["n"] + tl], c["n"], back)) == 0
+        assert back.raw[:c["n"]] == p
+        bad = bytearray(out.raw[:c["n"] + tl]); bad[-1] ^= 2
+        assert ord(dec(H(c["key"]), H(c["nonce"]), aad, len(aad), bytes(bad), c["n"], hbuf(c["n"]))) == c["rc_forged"]
     for c in v["ecb_padding"]:
         lib = uaes.shim(f"128_pad{c['padding']}")
         p = rnd(c["pt_tag"], c["n"])
@@ -200,6 +214,31 @@ def test_padding_and_preset_counter_large_and_device(uaes, orc, torch):
         off = 16 * 70001
         uaes.ctr_crypt_block(128, key[:16], ctr, 70001, src[off:], len(pt) - off, dst)
         assert host(dst, 0, len(pt) - off) == orc.ctr_block(key[:16], ctr, pt[off:], first_block=70001)
+
+
+def test_ccm_eax_ocb_tag_lengths(uaes, orc, torch):
+    """CCM_TAG_LEN / EAX_TAG_LEN / OCB_TAG_LEN as run-time arguments: every legal length, device buffers for OCB"""
+    key = rnd("tl-k", 16)
+    for mode, nl, lens in (("ccm", 11, (4, 6, 8, 10, 12, 14, 16)), ("eax", 16, (1, 5, 8, 15, 16)), ("ocb", 12, (1, 4, 8, 12, 15, 16))):
+        for tl in lens:
+            for n, alen in ((0, 3), (57, 31), (16 * 300 + 5, 0)):
+                nonce, aad, pt = rnd(f"tl-n{mode}", nl), rnd(f"tl-a{alen}", alen), rnd(f"tl-p{n}", n)
+                want = orc.aead_ex(mode, key, nonce, aad, pt, tl)
+                out = hbuf(n + 16)
+                uaes.aead_ex(mode, 128, key, nonce, aad, pt, n, out, tl)
+                assert out.raw[:n + tl] == want and out.raw[n + tl:] == b"\xcc" * (16 - tl), (mode, tl, n)
+                back = hbuf(n)
+                assert uaes.aead_ex(mode, 128, key, nonce, aad, want, n, back, tl, encrypt=False) == 0 and back.raw[:n] == pt
+                bad = bytearray(want); bad[-1] ^= 0x10
+                assert uaes.aead_ex(mode, 128, key, nonce, aad, bytes(bad), n, hbuf(n), tl, encrypt=False) == 0x1A
+    nonce, pt = rnd("tl-on", 12), rnd("tl-op", 3 * MIB + 9)
+    src, dst = dev(torch, pt), dev(torch, b"", pad=len(pt) + 32)
+    dst[:] = 0xCC
+    uaes.aead_ex("ocb", 128, key, nonce, b"hdr", src, len(pt), dst, 12)
+    assert host(dst, 0, len(pt) + 12) == orc.aead_ex("ocb", key, nonce, b"hdr", pt, 12) and host(dst, len(pt) + 12, len(pt) + 16) == b"\xcc" * 4
+    # CCM tags are even and at least 4 bytes (micro_aes.h:105); anything else is an argument error
+    assert uaes.core().uaes_ccm_encrypt_ex(128, key, rnd("x", 11), None, 0, pt[:10], 10, hbuf(26), 7) == -3
+    assert uaes.core().uaes_ocb_encrypt_ex(128, key, nonce, None, 0, pt[:10], 10, hbuf(26), 17) == -3
 
 
 def test_cbc_without_cts(uaes, orc, torch):

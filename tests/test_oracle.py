@@ -403,6 +403,13 @@ def test_variant_recorded_reference_outputs(orc):
         assert len(out) == c["n"] + 12 and sha256(out[:c["n"]]) == c["ct_sha256"] and out[c["n"]:].hex() == c["tag"], c
         bad = bytearray(out); bad[-1] ^= 1
         assert orc.gcm_decrypt_ex(H(c["key"]), H(c["nonce"]), aad, bytes(bad), taglen=12)[0] == c["rc_forged"] == 0x1A
+    for c in v["aead_tags"]:                    # CCM 8-, EAX 10-, OCB 12-byte tags (one build of the reference)
+        aad, pt = rnd(c["aad_tag"], c["aadlen"]), rnd(c["pt_tag"], c["n"])
+        out = orc.aead_ex(c["mode"], H(c["key"]), H(c["nonce"]), aad, pt, c["taglen"])
+        assert len(out) == c["n"] + c["taglen"] and sha256(out[:c["n"]]) == c["ct_sha256"] and out[c["n"]:].hex() == c["tag"], c
+        assert orc.aead_ex(c["mode"], H(c["key"]), H(c["nonce"]), aad, out, c["taglen"], encrypt=False) == (0, pt)
+        bad = bytearray(out); bad[-1] ^= 2
+        assert orc.aead_ex(c["mode"], H(c["key"]), H(c["nonce"]), aad, bytes(bad), c["taglen"], encrypt=False)[0] == c["rc_forged"] == 0x1A
     for c in v["ecb_padding"]:
         pt = rnd(c["pt_tag"], c["n"])
         out = orc.ecb_encrypt_padded(H(c["key"]), pt, c["padding"])

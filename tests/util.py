@@ -74,6 +74,9 @@ class Oracle:
         L.oracle_gcm_decrypt_ex.argtypes = [_int, _u8p, _u8p, _sz, _u8p, _sz, _u8p, _sz, _u8p, _sz]
         L.oracle_cbc_decrypt_nocts.argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p]
         L.oracle_xts_range.argtypes = [_int, _u8p, _u8p, _u64, _u8p, _sz, _u8p, _int]
+        for m in ("ccm", "eax", "ocb"):
+            getattr(L, f"oracle_{m}_encrypt_ex").argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p, _sz]
+            getattr(L, f"oracle_{m}_decrypt_ex").argtypes = [_int, _u8p, _u8p, _u8p, _sz, _u8p, _sz, _u8p, _sz]
 
     @staticmethod
     def _buf(n):
@@ -136,6 +139,17 @@ class Oracle:
         n = len(ct_and_tag) - taglen
         o = self._buf(n)
         rc = self.lib.oracle_gcm_decrypt_ex(len(key) * 8, key, nonce, len(nonce), aad, len(aad), ct_and_tag, n, o, taglen)
+        return rc, o.raw[:n]
+
+    def aead_ex(self, mode, key, nonce, aad, data, taglen, encrypt=True):
+        """CCM / EAX / OCB with a tag of `taglen` bytes: encrypt -> ct || tag, decrypt -> (rc, pt)"""
+        if encrypt:
+            o = self._buf(len(data) + 16)
+            getattr(self.lib, f"oracle_{mode}_encrypt_ex")(len(key) * 8, key, nonce, aad, len(aad), data, len(data), o, taglen)
+            return o.raw[:len(data) + taglen]
+        n = len(data) - taglen
+        o = self._buf(n)
+        rc = getattr(self.lib, f"oracle_{mode}_decrypt_ex")(len(key) * 8, key, nonce, aad, len(aad), data, n, o, taglen)
         return rc, o.raw[:n]
 
     def cbc_nocts(self, key, iv, data):
