@@ -104,6 +104,7 @@ struct CtrArgs {
     uint64_t q_units;            // units covering [v0, v0 + nblocks)
     uint32_t q_bs_on;            // 0: the bitsliced warps take no work (short calls)
     uint32_t q_zero;             // 0 (see q_post)
+    uint32_t q_shift;            // log2(blocks per unit): 11, or 10 for calls short enough that the last unit shows
     BsKeyPlanes bs;
 };
 
@@ -419,9 +420,9 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
         uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.q_units);
         while (u != kQNone) {
             const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);      // the next unit, a unit ahead
-            const uint64_t c0 = a.q_u0 + (u << kQUnitShift);
+            const uint64_t c0 = a.q_u0 + (u << a.q_shift);
 #pragma unroll 1
-            for (uint32_t p = 0; p < (uint32_t)(kQUnit >> 10); ++p)
+            for (uint32_t p = 0; p < (1u << (a.q_shift - 10)); ++p)
                 ctr_bs_pass<NR, UAES_BS_BATCH>(a, lb, um, c0 + ((uint64_t)p << 10), tag16);
             ++done;
             u = q_back(posted, a.q_units);
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
 
     // absolute group index G = counter >> 8 (counter space not reduced mod 2^56); block index of
     // (G, row r = 4 * half + it, lane) = 256 G + 32 r + lane - v0
-    constexpr uint32_t kGroupsPerUnit = (uint32_t)(kQUnit >> 8);
+    const uint32_t kGroupsPerUnit = 1u << (a.q_shift - 8);
     const uint64_t Gfirst = a.q_u0 >> 8;
     auto kof = [&](uint64_t G, uint32_t r) -> int64_t {
         return (int64_t)((G << 8) + 32 * r + lane) - (int64_t)a.v0;
@@ -817,6 +818,7 @@ static unsigned long long *g_qring[64];
 static std::atomic<unsigned> g_qnext[64];
 static std::atomic_flag g_qlock = ATOMIC_FLAG_INIT;
 static thread_local unsigned long long *tls_last_q = nullptr;
+static thread_local unsigned long long tls_last_unit = 0;
 
 static cudaError_t q_slot(cudaStream_t st, unsigned long long **out)
 {
@@ -854,13 +856,19 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     ctr_tuning_init();
     const int threads = g_ctr_threads, share = g_ctr_share;
     a.tt_blocks = a.nblocks; a.bs_u0 = 0; a.bs_passes = 0;
-    a.q = nullptr; a.q_u0 = 0; a.q_units = 0; a.q_bs_on = 0; a.q_zero = 0;
+    a.q = nullptr; a.q_u0 = 0; a.q_units = 0; a.q_bs_on = 0; a.q_zero = 0; a.q_shift = kQUnitShift;
     if (threads == 386) {
         // work queue: units of kQUnit counters, aligned in counter space; both kinds of warps clip to
         // [v0, v0 + nblocks).  Short calls keep the co-runner out (a bitsliced unit takes longer than a
         // table-driven one, which shows when there are fewer units than warps).
-        a.q_u0 = a.v0 & ~(kQUnit - 1);
-        a.q_units = (a.v0 - a.q_u0 + a.nblocks + kQUnit - 1) >> kQUnitShift;
+        // units of 2048 blocks; 1024 when a warp gets fewer than ~64 of them (below 4 GiB): the last unit of the
+        // slowest warp is the tail of the launch (1 GiB: 979 -> see profiles/r2_sweep_ctr_unit_small.txt)
+        a.q_shift = (uint32_t)env_int("UAES_CTR_UNIT_SHIFT", a.nblocks >= (1ull << 28) ? kQUnitShift : kQUnitShift - 1);
+        if (a.q_shift < 10 || a.q_shift > 16) a.q_shift = kQUnitShift;
+        const uint64_t unit = 1ull << a.q_shift;
+        a.q_u0 = a.v0 & ~(unit - 1);
+        a.q_units = (a.v0 - a.q_u0 + a.nblocks + unit - 1) >> a.q_shift;
+        tls_last_unit = unit;
         a.q_bs_on = share > 0 && (long long)a.nblocks >= g_ctr_bs_min;
         if (a.q_bs_on) bs_make_key_planes(a.ks.w, NR, &a.bs);
         cudaError_t e = opt_in_smem(ctr_queue_kernel<NR, 384, 2>);
@@ -951,7 +959,7 @@ int uaes_launch_ctr_queue_stats(u64 *tt_units, u64 *bs_units, u64 *unit_blocks)
     unsigned long long h[4] = {0, 0, 0, 0};
     if (!tls_last_q) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaMemcpy(h, tls_last_q, 32, cudaMemcpyDeviceToHost);
-    *tt_units = h[1]; *bs_units = h[2]; *unit_blocks = kQUnit;
+    *tt_units = h[1]; *bs_units = h[2]; *unit_blocks = tls_last_unit;
     return (int)e;
 }
 
