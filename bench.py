@@ -320,7 +320,7 @@ def run_gpu(args):
                 self.allp = torch.zeros(16 * world, dtype=torch.uint8, device="cuda")
                 shards = gcm_shards(n * world, world)
                 self.after = gcm_blocks_after(shards, n * world)
-                self.tag = None
+                self.tag, self.tag_dev = None, torch.zeros(16, dtype=torch.uint8, device="cuda")
 
         def step(self):
             wl, n, fb = self.wl, self.n, self.first_block
@@ -356,8 +356,8 @@ def run_gpu(args):
                 # rank 0 folds the contributions into the tag
                 uaes.gcm_shard(128, key, iv, fb, src, n, dst, partial_dev=self.mine)
                 dist.all_gather_into_tensor(self.allp, self.mine)
-                if rank == 0:
-                    self.tag = uaes.gcm_combine(128, key, iv, b"", None, self.after, n * world, partials_dev=self.allp)
+                if rank == 0:      # the tag stays on the GPU: nothing in the step waits for the host
+                    uaes.gcm_combine(128, key, iv, b"", None, self.after, n * world, partials_dev=self.allp, tag_dev=self.tag_dev)
 
         # ---- parity inside the bench: windows of this rank's shard against the oracle, on EVERY rank
         def check(self):
@@ -409,6 +409,7 @@ def run_gpu(args):
                     allsub = torch.zeros(48 * world, dtype=torch.uint8, device="cuda")
                     dist.all_gather_into_tensor(allsub, sub)
                     if rank == 0:
+                        self.tag = bytes(self.tag_dev.cpu().numpy())
                         tot = (n * world) // 16
                         aft = [tot - (r * (n // 16) + b // 16) for r in range(world) for b in cuts[1:]]
                         t_all = uaes.gcm_combine(128, key, iv, b"", None, aft, n * world, partials_dev=allsub)

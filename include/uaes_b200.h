@@ -242,7 +242,8 @@ int uaes_eax_decrypt_ex(int keybits, const uaes_u8 *key, const uaes_u8 *nonce, c
  * the gather can run device to device.  Gather the contributions (the one 16-byte-per-rank exchange
  * of the path) and let uaes_gcm_combine fold them with the AAD and the lengths into the tag:
  * blocks_after[r] = number of 16-byte blocks of the message after shard r's end (0 for the last
- * shard); partials, blocks_after and tag may each be host or device memory, nshards is unbounded.
+ * shard); partials, blocks_after and tag may each be host or device memory (a device tag in asynchronous mode:
+ * the call only enqueues work), nshards is unbounded.
  * A decrypting caller compares that tag with the received one and discards the shards' output on
  * mismatch (the single-call API does this itself).  A host-buffer uaes_gcm_encrypt / _decrypt
  * larger than one staging chunk runs exactly this scheme internally, one shard per chunk. */

@@ -390,17 +390,19 @@ def gcm_shard(bits, key, nonce, first_block, src, nbytes, dst, decrypt=False, pa
     return part.raw
 
 
-def gcm_combine(bits, key, nonce, aad, partials, blocks_after, total_len, partials_dev=None):
+def gcm_combine(bits, key, nonce, aad, partials, blocks_after, total_len, partials_dev=None, tag_dev=None):
     """tag of a sharded message from the gathered contributions (a list of 16-byte strings, or
-    `partials_dev` = device memory holding len(blocks_after) x 16 bytes)"""
+    `partials_dev` = device memory holding len(blocks_after) x 16 bytes).  With `tag_dev` (16 bytes of device
+    memory) the tag stays on the GPU and, in asynchronous mode, the call only enqueues work; returns None then."""
     tag = ctypes.create_string_buffer(16)
     ps = b"".join(partials) if partials_dev is None else None
     n = len(blocks_after)
     after = (ctypes.c_uint64 * max(n, 1))(*blocks_after)
     pp = _ptr(partials_dev) if partials_dev is not None else (_ptr(ps) if ps else None)
     check(core().uaes_gcm_combine(bits, key, nonce, _ptr(aad) if aad else None, len(aad) if aad else 0,
-                                  pp, ctypes.addressof(after), n, total_len, ctypes.addressof(tag)))
-    return tag.raw
+                                  pp, ctypes.addressof(after), n, total_len,
+                                  _ptr(tag_dev) if tag_dev is not None else ctypes.addressof(tag)))
+    return None if tag_dev is not None else tag.raw
 
 
 def ctr_crypt_block(bits, key, ctr16, first_block, src, nbytes, dst):

@@ -1250,7 +1250,9 @@ static int gcm_fold_tag(devctx *c, const uaes_keysched *ks, const u8 j0[16], con
     LAUNCH(uaes_launch_gcm_combine(ks, j0, bulk_aad || !aadlen ? NULL : daad, aadlen, total_len, dparts, dafter,
                                    (unsigned)(n + (bulk_aad ? 1 : 0)), base, 16, st));
     CU(cudaMemcpyAsync(tag, base, taglen, cudaMemcpyDefault, st));
-    CU(cudaStreamSynchronize(st));
+    /* a tag that stays on the device (and contributions that came from there) needs no host round trip:
+     * in asynchronous mode the call only enqueues, like the shard calls that feed it */
+    if (!(tls_async && (ptr_class(tag) == PTR_DEVICE || ptr_class(tag) == PTR_OTHER))) CU(cudaStreamSynchronize(st));
 done:
     scratch_put(c, w, st);
     return rc;

@@ -532,10 +532,12 @@ def test_gcm_shard_contributions_stay_on_the_device(uaes, orc, torch):
         ln = 65536 if r < nsh - 1 else n - off
         uaes.gcm_shard(128, key, nonce, off // 16, src[off:], ln, dst[off:], partial_dev=parts[16 * r:])
         after.append((n + 15) // 16 - (off + ln + 15) // 16)
+    tag_dev = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    uaes.gcm_combine(128, key, nonce, aad, None, after, n, partials_dev=parts, tag_dev=tag_dev)     # enqueued only
     uaes.set_async(False)
     tag = uaes.gcm_combine(128, key, nonce, aad, None, after, n, partials_dev=parts)
     want = orc.gcm_encrypt(key, nonce, aad, pt)
-    assert host(dst, 0, n) == want[:n] and tag == want[n:]
+    assert host(dst, 0, n) == want[:n] and tag == want[n:] and host(tag_dev, 0, 16) == want[n:]
 
 
 def test_trim_shutdown_burn(uaes, orc, torch):
