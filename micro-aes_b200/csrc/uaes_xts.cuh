@@ -434,14 +434,18 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
         const uint64_t left = a.x.nsectors - sec0;
         const int nsec = left < 32 ? (int)left : 32;
         const uint64_t sec = a.x.first_sector + sec0 + lane;
-        uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
-        if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
-        else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.x.k2.w);
         const uint4 *src = a.x.in + sec0 * 32 + lane;
         uint4 *dst = a.x.out + sec0 * 32 + lane;
         uint4 cur[2], nxt[2];
+        // the tile's first two sectors are requested BEFORE the 32 tweak encryptions: their latency hides
+        // behind those (ncu had the table-driven warps at 12 % long-scoreboard stalls, one cold load per tile):
+        // 591-596 -> 613 GiB/s; an L2 prefetch of the NEXT tile from the middle of this one made it worse (608),
+        // profiles/r2_sweep_xts_loads_first.txt
 #pragma unroll
         for (int i = 0; i < 2; ++i) cur[i] = i < nsec ? ld_stream(src + i * 32) : make_uint4(0, 0, 0, 0);
+        uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
+        if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+        else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.x.k2.w);
         for (int sct = 0; sct < nsec; sct += 2) {
             uint32_t st[2][4];
             uint4 tw[2];
