@@ -303,6 +303,9 @@ struct GcmHybridArgs {
     BsKeyPlanes bs;
 };
 
+#ifndef UAES_GCM_BS_AHEAD
+#define UAES_GCM_BS_AHEAD 1                       // rows a bitsliced warp loads ahead of its XOR / store / absorb loop
+#endif
 constexpr int kGcmHybTtThreads = 384;
 constexpr int kGcmHybTtWarps = kGcmHybTtThreads / 32;
 
@@ -344,12 +347,20 @@ __device__ __forceinline__ void gcm_bs_chunk(const GcmHybridArgs &h, uint32_t lb
         for (int r = 3; r <= NR; ++r) bs_round_or_last(s, h.bs.k[r - 3], r == NR);
         const uint64_t k0 = kb + lane;
         uint4 x = k0 < a.nblocks ? ld_stream(a.in + k0) : make_uint4(0, 0, 0, 0);
+#if UAES_GCM_BS_AHEAD == 2
+        uint4 x1 = k0 + 32 < a.nblocks ? ld_stream(a.in + k0 + 32) : make_uint4(0, 0, 0, 0);
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
             const uint64_t k = k0 + 32 * t;
+#if UAES_GCM_BS_AHEAD == 2
+            const uint4 nx = x1;
+            x1 = (t + 2 < 32 && k + 64 < a.nblocks) ? ld_stream(a.in + k + 64) : make_uint4(0, 0, 0, 0);
+#else
             const uint4 nx = (t + 1 < 32 && k + 32 < a.nblocks) ? ld_stream(a.in + k + 32) : make_uint4(0, 0, 0, 0);
+#endif
             if (k < a.nblocks) {
                 const uint4 o = make_uint4(x.x ^ s[t], x.y ^ s[32 + t], x.z ^ s[64 + t], x.w ^ s[96 + t]);
                 st_stream(a.out + k, o);
