@@ -432,6 +432,159 @@ __global__ void __launch_bounds__(kGcmHybTtThreads + kBsThreads, 1) gcm_bulk_hyb
                                    (uint64_t)gridDim.x * kGcmHybTtWarps);
 }
 
+// ---- the same with NARROW bitsliced warps (uaes_bitslice8.cuh; ctr_queue8_kernel in uaes_kernels.cu) ------
+// 8 blocks per thread: a pass is one group of 256 counters, lane l holds the blocks = l (mod 32) of it, so
+// the GHASH Horner with H^32 runs 8 steps per pass instead of 32 (the absorb code is a quarter of the
+// wide form's 180 KB), the warps need 96 registers like the table-driven ones, and 8 of them fit per SM.
+// The chunk bookkeeping (runs of 1024-counter passes, partial scaled to the end of the range) is unchanged.
+struct GcmHybridArgs8 {
+    GcmBulkArgs b;
+    uint64_t a_blocks, bs_passes, bs_per, nchunks_b;     // as GcmHybridArgs
+    BsKeyPlanes8 bs8;
+};
+
+#ifndef UAES_GCM8_BS
+#define UAES_GCM8_BS 256
+#endif
+#ifndef UAES_GCM8_ROLL
+#define UAES_GCM8_ROLL 1
+#endif
+constexpr uint32_t kGcm8StageWords = UAES_GCM8_ROLL ? 16 * 32 : 0;   // per bitsliced warp: four slots of keystream words, one column per lane
+constexpr int kGcm8BsThreads = UAES_GCM8_BS;
+
+template <int NR, int MODE>
+__device__ __forceinline__ void gcm_bs8_chunk(const GcmHybridArgs8 &h, uint32_t lb, uint32_t mb, uint32_t *ws, uint32_t *stg, uint64_t j)
+{
+    const GcmBulkArgs &a = h.b;
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t *up = ws + lane, *dm = ws + 32 * 32;
+    const uint64_t p0 = j * h.bs_per, p1 = p0 + h.bs_per < h.bs_passes ? p0 + h.bs_per : h.bs_passes;
+    const uint64_t ubase = a.v0 + h.a_blocks;                   // counter of the region's first block (not reduced mod 2^56)
+    uint64_t klast = 0;
+    uint32_t y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    bool any = false;
+    Bs8Hoist hoist;
+
+#pragma unroll 1
+    for (uint64_t g = p0 << 2; g < p1 << 2; ++g) {               // groups of 256 counters
+        const uint64_t kb = h.a_blocks + (g << 8);               // block index of (slot 0, lane 0)
+        if (kb >= a.nblocks) break;
+        {
+            const uint64_t k = kb + 8 * (uint64_t)lane;          // this pass's 4 KiB towards L2 while the rounds run
+            if (k < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + k));
+        }
+        uint32_t s[32];
+        hoist.group(s, lb, rk, a.w0, a.w1, a.b8, (ubase + (g << 8)) & kMask56, up, dm, lane);
+        bs8_finish<NR>(s, h.bs8);
+        const uint64_t k0 = kb + lane;
+        uint4 x = k0 < a.nblocks ? ld_stream(a.in + k0) : make_uint4(0, 0, 0, 0);
+        bs_transpose32(s);                                       // s[8 c + t] = word c of slot t
+#if UAES_GCM8_ROLL
+        // the absorb loop ROLLED: the keystream words go through a lane-private column of shared memory, four
+        // slots at a time, so that the GHASH step exists twice in the code instead of eight times
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) stg[(4 * tt + c) * 32] = s[8 * c + 4 * hf + tt];
+#pragma unroll 1
+            for (int tt = 0; tt < 4; ++tt) {
+                const uint64_t k = k0 + 32 * (4 * hf + tt);
+                const uint4 nx = (4 * hf + tt + 1 < 8 && k + 32 < a.nblocks) ? ld_stream(a.in + k + 32) : make_uint4(0, 0, 0, 0);
+                if (k < a.nblocks) {
+                    const uint32_t *ksw = stg + 128 * tt;
+                    const uint4 o = make_uint4(x.x ^ ksw[0], x.y ^ ksw[32], x.z ^ ksw[64], x.w ^ ksw[96]);
+                    st_stream(a.out + k, o);
+                    const uint4 gh = MODE == 0 ? o : x;          // GHASH runs over the ciphertext
+                    ghash_mul_const(mb, y0, y1, y2, y3);
+                    y0 ^= __byte_perm(gh.x, 0, 0x0123); y1 ^= __byte_perm(gh.y, 0, 0x0123);
+                    y2 ^= __byte_perm(gh.z, 0, 0x0123); y3 ^= __byte_perm(gh.w, 0, 0x0123);
+                    klast = k; any = true;
+                }
+                x = nx;
+            }
+        }
+#else
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const uint64_t k = k0 + 32 * t;
+            const uint4 nx = (t + 1 < 8 && k + 32 < a.nblocks) ? ld_stream(a.in + k + 32) : make_uint4(0, 0, 0, 0);
+            if (k < a.nblocks) {
+                const uint4 o = make_uint4(x.x ^ s[t], x.y ^ s[8 + t], x.z ^ s[16 + t], x.w ^ s[24 + t]);
+                st_stream(a.out + k, o);
+                const uint4 gh = MODE == 0 ? o : x;              // GHASH runs over the ciphertext
+                ghash_mul_const(mb, y0, y1, y2, y3);
+                y0 ^= __byte_perm(gh.x, 0, 0x0123); y1 ^= __byte_perm(gh.y, 0, 0x0123);
+                y2 ^= __byte_perm(gh.z, 0, 0x0123); y3 ^= __byte_perm(gh.w, 0, 0x0123);
+                klast = k; any = true;
+            }
+            x = nx;
+        }
+#endif
+    }
+    // chunk end b1; lane l holds sum_j X_(l+32j) * C^(J-j): scale by H^(b1 - klast), reduce over the warp,
+    // then move the partial to the end of the range: * H^(nblocks - b1)
+    const uint64_t b1 = h.a_blocks + (p1 << 10) < a.nblocks ? h.a_blocks + (p1 << 10) : a.nblocks;
+    Gf z{0, 0};
+    if (any) z = gf_mul_fast(gf_load(a.work->lanepow[(uint32_t)(b1 - klast) - 1]),
+                             Gf{(uint64_t)y0 << 32 | y1, (uint64_t)y2 << 32 | y3});
+    for (int o = 16; o; o >>= 1) {
+        z.hi ^= __shfl_xor_sync(0xffffffffu, z.hi, o);
+        z.lo ^= __shfl_xor_sync(0xffffffffu, z.lo, o);
+    }
+    if (lane == 0) {
+        if (a.nblocks > b1) z = gf_mul_fast(z, gf_pow_fast(gf_load(a.work->H), a.nblocks - b1));
+        a.work->partials[a.nchunks + j] = gf_store(z);
+    }
+}
+
+template <int NR, int MODE>
+__global__ void __launch_bounds__(kGcmHybTtThreads + kGcm8BsThreads, 1) gcm_bulk_hybrid8_kernel(const __grid_constant__ GcmHybridArgs8 h)
+{
+    static_assert(MODE == 0 || MODE == 2, "the co-runner produces keystream: encrypt or decrypting shard");
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t win0 = smem_u32(dyn), win1 = win0 + dyn_smem_size();
+    const uint32_t tbase = align_table_base(dyn);
+    const uint32_t mbase = tbase >= win0 + kGhashRegion ? tbase - kGhashRegion : tbase + kEncTableBytes;
+    const uint32_t after = mbase > tbase ? mbase + kGhashRegion : tbase + kEncTableBytes;   // the bitsliced warps' U planes and D masks
+    constexpr uint32_t kBsWarps = kGcm8BsThreads / 32;
+    if (mbase + kGhashRegion > win1 || tbase + kEncTableBytes > win1 || after + kBsWarps * kBs8WarpWords * 4 > win1) __trap();
+    // staging columns of the rolled absorb loop: in front of the GHASH table when that lies in the gap, else behind the warps' areas
+    const uint32_t sbase = (win0 + 15u) & ~15u;
+    const bool stage_front = mbase < tbase && sbase + kBsWarps * kGcm8StageWords * 4 <= mbase;
+    const uint32_t stage0 = stage_front ? sbase : after + kBsWarps * kBs8WarpWords * 4;
+    if (stage0 + kBsWarps * kGcm8StageWords * 4 > (stage_front ? mbase : win1)) __trap();
+
+    init_enc_tables(tbase);
+    {
+        const Gf C = gf_load(h.b.work->C32);
+        if (threadIdx.x < 256) {
+            const uint4 v = ghash_table_entry(C, threadIdx.x);
+            for (int rep = 0; rep < 8; ++rep) {
+                const uint32_t ad = mbase + threadIdx.x * 128 + rep * 16;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t lb = tbase + lane * 4, mb = mbase | ((lane & 7) << 4);
+    asm volatile("" : "+r"(lb), "+r"(mb)::"memory");
+
+    if (w < kBsWarps) {                          // the bitsliced warps come first (ctr_queue8_kernel: UAES_Q8_MAP)
+        uint32_t *ws = (uint32_t *)(dyn + (after - win0)) + w * kBs8WarpWords;
+        const uint64_t nw = (uint64_t)gridDim.x * kBsWarps;
+        uint32_t *stg = (uint32_t *)(dyn + (stage0 - win0)) + w * kGcm8StageWords + lane;
+        for (uint64_t j = (uint64_t)blockIdx.x * kBsWarps + w; j < h.nchunks_b; j += nw)
+            gcm_bs8_chunk<NR, MODE>(h, lb, mb, ws, stg, j);
+        return;
+    }
+    gcm_tt_chunks<NR, MODE, false>(h.b, h.a_blocks, lb, mb, (uint64_t)blockIdx.x * kGcmHybTtWarps + (w - kBsWarps),
+                                   (uint64_t)gridDim.x * kGcmHybTtWarps);
+}
+
 // ---------------------------------------------------------------- fold, tail, tag
 
 struct GcmFinishArgs {
@@ -560,6 +713,24 @@ static cudaError_t launch_gcm_bulk_nr(const GcmBulkArgs &a, cudaStream_t st)
 constexpr int kGcmDefaultShare = 170;    // of 1024: blocks given to the bitsliced warps; 632 / 661 / 671 / 680 / 648 / 568 GiB/s at
                                          // 0 / 120 / 150 / 180 / 200 / 250 for AES-128, 4 GiB (profiles/r2_sweep_gcm*.txt): the static split
                                          // falls off quickly once the bitsliced warps finish last, so stay left of the peak
+
+#ifndef UAES_GCM_NARROW_DEFAULT
+#define UAES_GCM_NARROW_DEFAULT 0           // measured: 655-666 GiB/s (8 warps, rolled absorb) and 665-670 (4 warps) against 676-678 for the wide form (profiles/r2_sweep_gcm8.txt)
+#endif
+#ifndef UAES_GCM8_DEFAULT_SHARE
+#define UAES_GCM8_DEFAULT_SHARE 200
+#endif
+constexpr int kGcm8DefaultShare = UAES_GCM8_DEFAULT_SHARE;
+
+template <int NR, int MODE>
+static cudaError_t launch_gcm_hybrid8_nr(const GcmHybridArgs8 &h, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(gcm_bulk_hybrid8_kernel<NR, MODE>);
+    if (e != cudaSuccess) return e;
+    gcm_bulk_hybrid8_kernel<NR, MODE><<<(unsigned)sm_count(), kGcmHybTtThreads + kGcm8BsThreads, kDynSmem, st>>>(h);
+    ++g_launches;
+    return cudaGetLastError();
+}
 
 template <int NR, int MODE>
 static cudaError_t launch_gcm_hybrid_nr(const GcmHybridArgs &h, cudaStream_t st)
@@ -812,8 +983,8 @@ extern "C" size_t uaes_gcm_work_bytes(u64 len)
     using namespace uaes;
     uint64_t rows_per_chunk, nchunks;
     gcm_plan(len / 16, rows_per_chunk, nchunks);
-    // + one partial per bitsliced warp of the co-runner form (4 per SM)
-    return sizeof(GcmWork) + ((size_t)nchunks + 4 * (size_t)sm_count() + 8) * sizeof(uint4);
+    // + one partial per bitsliced warp of the co-runner forms (up to 8 per SM)
+    return sizeof(GcmWork) + ((size_t)nchunks + 8 * (size_t)sm_count() + 8) * sizeof(uint4);
 }
 
 extern "C" int uaes_launch_gcm_j0(const uaes_keysched *ks, const void *iv_dev, u64 ivlen, void *out_dev,
@@ -864,16 +1035,18 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char j0b[
     // the co-runner form: the last `share` of the blocks goes to bitsliced warps (region B starts on a
     // 1024-counter boundary); the on/off knobs are the CTR kernel's (uaes_ctr_tuning)
     ctr_tuning_init();
-    const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_GCM_BS_PERMILLE", kGcmDefaultShare);
+    const bool narrow = env_int("UAES_GCM_NARROW", UAES_GCM_NARROW_DEFAULT) != 0;
+    const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_GCM_BS_PERMILLE", narrow ? kGcm8DefaultShare : kGcmDefaultShare);
     if ((mode == 0 || mode == 2) && g_ctr_share > 0 && share > 0 && (long long)nblocks >= g_ctr_bs_min && nblocks >= 4096) {
         static thread_local GcmHybridArgs h;                 // 6 KB of planes: off the stack
+        static thread_local GcmHybridArgs8 h8;
         const uint64_t v0 = (vj0 + 1 + first_block) & kMask56;
         const uint64_t uend = v0 + nblocks, want = nblocks / 1024 * (uint64_t)share;
         const uint64_t ub = (uend - want) & ~1023ull;
         if (ub > v0 + 1024 && ub < uend) {
             h.a_blocks = ub - v0;
             h.bs_passes = (uend - ub + 1023) >> 10;
-            const uint64_t nw = (uint64_t)sm_count() * (kBsThreads / 32);
+            const uint64_t nw = (uint64_t)sm_count() * (narrow ? kGcm8BsThreads / 32 : kBsThreads / 32);
             h.bs_per = (h.bs_passes + nw - 1) / nw;
             h.nchunks_b = (h.bs_passes + h.bs_per - 1) / h.bs_per;
             gcm_plan(h.a_blocks, rows_per_chunk, nchunks, kGcmHybTtWarps);
@@ -882,16 +1055,30 @@ extern "C" int uaes_launch_gcm(const uaes_keysched *ks, const unsigned char j0b[
             b.w0 = j0[0]; b.w1 = j0[1]; b.b8 = b8; b.v0 = v0;
             b.in = (const uint4 *)in; b.out = (uint4 *)out;
             b.nblocks = nblocks; b.chunk_blocks = 32 * rows_per_chunk; b.nchunks = nchunks; b.work = (GcmWork *)work;
-            bs_make_key_planes(ks->w, ks->rounds, &h.bs);
             nparts_b = h.nchunks_b; blocks_b = nblocks - h.a_blocks;
-            switch (ks->rounds * 4 + mode) {
-            case 40: e = launch_gcm_hybrid_nr<10, 0>(h, st); break;
-            case 42: e = launch_gcm_hybrid_nr<10, 2>(h, st); break;
-            case 48: e = launch_gcm_hybrid_nr<12, 0>(h, st); break;
-            case 50: e = launch_gcm_hybrid_nr<12, 2>(h, st); break;
-            case 56: e = launch_gcm_hybrid_nr<14, 0>(h, st); break;
-            case 58: e = launch_gcm_hybrid_nr<14, 2>(h, st); break;
-            default: e = cudaErrorInvalidValue;
+            if (narrow) {
+                h8.b = h.b; h8.a_blocks = h.a_blocks; h8.bs_passes = h.bs_passes; h8.bs_per = h.bs_per; h8.nchunks_b = h.nchunks_b;
+                bs8_make_key_planes(ks->w, ks->rounds, &h8.bs8);
+                switch (ks->rounds * 4 + mode) {
+                case 40: e = launch_gcm_hybrid8_nr<10, 0>(h8, st); break;
+                case 42: e = launch_gcm_hybrid8_nr<10, 2>(h8, st); break;
+                case 48: e = launch_gcm_hybrid8_nr<12, 0>(h8, st); break;
+                case 50: e = launch_gcm_hybrid8_nr<12, 2>(h8, st); break;
+                case 56: e = launch_gcm_hybrid8_nr<14, 0>(h8, st); break;
+                case 58: e = launch_gcm_hybrid8_nr<14, 2>(h8, st); break;
+                default: e = cudaErrorInvalidValue;
+                }
+            } else {
+                bs_make_key_planes(ks->w, ks->rounds, &h.bs);
+                switch (ks->rounds * 4 + mode) {
+                case 40: e = launch_gcm_hybrid_nr<10, 0>(h, st); break;
+                case 42: e = launch_gcm_hybrid_nr<10, 2>(h, st); break;
+                case 48: e = launch_gcm_hybrid_nr<12, 0>(h, st); break;
+                case 50: e = launch_gcm_hybrid_nr<12, 2>(h, st); break;
+                case 56: e = launch_gcm_hybrid_nr<14, 0>(h, st); break;
+                case 58: e = launch_gcm_hybrid_nr<14, 2>(h, st); break;
+                default: e = cudaErrorInvalidValue;
+                }
             }
             if (e != cudaSuccess) return (int)e;
         }

@@ -16,6 +16,7 @@
 #include "uaes_core.cuh"
 #include "uaes_gf128.cuh"
 #include "uaes_bitslice.cuh"
+#include "uaes_bitslice8.cuh"
 
 namespace uaes {
 
@@ -84,7 +85,7 @@ constexpr uint64_t kMask56 = (1ull << 56) - 1;
 
 // ---------------------------------------------------------------- CTR (micro_aes.c:919-950)
 
-struct CtrArgs {
+struct CtrArgsBase {
     uaes_keysched ks;
     uint32_t w0, w1, b8;
     uint64_t v0;                 // counter of block 0
@@ -105,7 +106,12 @@ struct CtrArgs {
     uint32_t q_bs_on;            // 0: the bitsliced warps take no work (short calls)
     uint32_t q_zero;             // 0 (see q_post)
     uint32_t q_shift;            // log2(blocks per unit): 11, or 10 for calls short enough that the last unit shows
-    BsKeyPlanes bs;
+};
+struct CtrArgs : CtrArgsBase {
+    BsKeyPlanes bs;              // wide bitsliced form (uaes_bitslice.cuh): 32 blocks per thread
+};
+struct CtrArgs8 : CtrArgsBase {
+    BsKeyPlanes8 bs8;            // narrow form (uaes_bitslice8.cuh): 8 blocks per thread
 };
 
 // Work unit = a "group": the 256 counter values that share bytes 0..14 of the counter block.
@@ -392,46 +398,16 @@ __device__ __forceinline__ uint64_t q_back(unsigned long long posted, uint64_t u
     return f + b < units ? units - 1 - b : kQNone;
 }
 
-template <int NR, int kCtrThreads, int ILP>
-__global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(const __grid_constant__ CtrArgs a)
+#ifndef UAES_TT_ROLL_ROWS
+#define UAES_TT_ROLL_ROWS 0                     // 1: one copy of the round code for both row pairs of a group; measured -13 % (profiles/r2_sweep_q8.txt)
+#endif
+// the table-driven role of the work-queue kernels: claims units from the front until none is left,
+// then (one thread of the grid) the ragged tail
+template <int NR, int ILP>
+__device__ __forceinline__ void ctr_queue_table_role(const CtrArgsBase &a, uint32_t lb, uint32_t tail_thread = 0)
 {
-    static_assert(ILP == 2, "two rows in flight per table-driven thread");
-    extern __shared__ __align__(16) uint8_t dyn[];
-    const uint32_t lb = setup_tables<true>(dyn);
     const uint32_t *rk = a.ks.w;
     const uint32_t lane = threadIdx.x & 31;
-    constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
-#ifndef UAES_Q_TT_REGS
-#define UAES_Q_TT_REGS 96                        // table-driven threads; the co-runner gets 224 (104 / 200: -0.8 .. -1.8 %)
-#endif
-    constexpr int kTtRegs = UAES_Q_TT_REGS;
-    constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
-    constexpr int kBsRegs = (kBsRegs0 > 232 ? 232 : kBsRegs0) / 8 * 8;
-
-    if (threadIdx.x >= kCtrThreads) {
-        reg_inc<kBsRegs>();
-        const uint32_t tbase = align_table_base(dyn);
-        const uint32_t bw = (threadIdx.x - kCtrThreads) >> 5;
-        const uint32_t off = tbase + kEncTableBytes + bw * (kBsUniformMasks * 4) - smem_u32(dyn);
-        if (off + kBsUniformMasks * 4 > dyn_smem_size()) __trap();
-        if (!a.q_bs_on) return;
-        uint32_t *um = (uint32_t *)(dyn + off);
-        uint64_t tag16 = ~0ull, done = 0;
-        uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.q_units);
-        while (u != kQNone) {
-            const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);      // the next unit, a unit ahead
-            const uint64_t c0 = a.q_u0 + (u << a.q_shift);
-#pragma unroll 1
-            for (uint32_t p = 0; p < (1u << (a.q_shift - 10)); ++p)
-                ctr_bs_pass<NR, UAES_BS_BATCH>(a, lb, um, c0 + ((uint64_t)p << 10), tag16);
-            ++done;
-            u = q_back(posted, a.q_units);
-        }
-        if (lane == 0 && done) atomicAdd(a.q + 2, (unsigned long long)done);
-        return;
-    }
-    reg_dec<kTtRegs>();
-
     // absolute group index G = counter >> 8 (counter space not reduced mod 2^56); block index of
     // (G, row r = 4 * half + it, lane) = 256 G + 32 r + lane - v0
     const uint32_t kGroupsPerUnit = 1u << (a.q_shift - 8);
@@ -506,6 +482,34 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
                 const uint64_t Gn = !last_group ? G + 1 : half == 0 ? Gu : Gfirst + unext * kGroupsPerUnit;
                 const uint32_t rn = !last_group ? 4 * half : half == 0 ? 4u : 0u;
                 const bool okn = !last_group || half == 0 || unext != kQNone;
+#if UAES_TT_ROLL_ROWS
+                // the two row pairs of the group share ONE copy of the round code (the instruction working set of
+                // the two roles together has to fit the 32 KB instruction cache): the pair's U words are selected
+                // into place (8 selects per pair), the pointers of the rows fetched ahead likewise
+                static_assert(ILP == 2, "rolled form: two row pairs");
+#pragma unroll 1
+                for (int it = 0; it < 4; it += ILP) {
+                    uint4 nxt[ILP];
+                    uint32_t t[ILP][4];
+                    const bool second = it != 0;
+                    const uint64_t Gf = second ? Gn : G;
+                    const uint32_t rf = second ? rn : 4 * half + ILP;
+                    const bool okf = second ? okn : true;
+#pragma unroll
+                    for (int i = 0; i < ILP; ++i) {
+                        nxt[i] = fetch(okf, Gf, rf + i);
+                        t[i][0] = D0 ^ (second ? U[2 + i][0] : U[i][0]); t[i][1] = D1 ^ (second ? U[2 + i][1] : U[i][1]);
+                        t[i][2] = D2 ^ (second ? U[2 + i][2] : U[i][2]); t[i][3] = D3 ^ (second ? U[2 + i][3] : U[i][3]);
+                    }
+                    enc_finish_n<NR, 3, ILP>(lb, t, rk, cur);
+#pragma unroll
+                    for (int i = 0; i < ILP; ++i) {
+                        const int64_t k = kof(G, 4 * half + it + i);
+                        if (k >= 0 && (uint64_t)k < a.nblocks) st_stream(a.out + k, make_uint4(t[i][0], t[i][1], t[i][2], t[i][3]));
+                        cur[i] = nxt[i];
+                    }
+                }
+#else
 #pragma unroll
                 for (int it = 0; it < 4; it += ILP) {
                     uint4 nxt[ILP];
@@ -525,6 +529,7 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
                         cur[i] = nxt[i];
                     }
                 }
+#endif
             }
         }
         ++done;
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
     if (lane == 0 && done) atomicAdd(a.q + 1, (unsigned long long)done);
 
     // ragged tail: Y[0..n) = E(ctr)[0..n) ^ X[0..n)  (mixThenXor, micro_aes.c:534-544)
-    if (a.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.tail && blockIdx.x == 0 && threadIdx.x == tail_thread) {
         uint32_t w2, w3;
         ctr_words(a.b8, (a.v0 + a.nblocks) & kMask56, w2, w3);
         uint32_t t0 = a.w0, t1 = a.w1, t2 = w2, t3 = w3;
@@ -543,6 +548,224 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
         uint8_t *y = (uint8_t *)(a.out + a.nblocks);
         for (uint32_t i = 0; i < a.tail; ++i) y[i] = x[i] ^ (uint8_t)(ksw[i >> 2] >> (8 * (i & 3)));
     }
+}
+
+template <int NR, int kCtrThreads, int ILP>
+__global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(const __grid_constant__ CtrArgs a)
+{
+    static_assert(ILP == 2, "two rows in flight per table-driven thread");
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
+#ifndef UAES_Q_TT_REGS
+#define UAES_Q_TT_REGS 96                        // table-driven threads; the co-runner gets 224 (104 / 200: -0.8 .. -1.8 %)
+#endif
+    constexpr int kTtRegs = UAES_Q_TT_REGS;
+    constexpr int kBsRegs0 = kLaunchRegs + (kLaunchRegs - kTtRegs) * kCtrThreads / kBsThreads;
+    constexpr int kBsRegs = (kBsRegs0 > 232 ? 232 : kBsRegs0) / 8 * 8;
+
+    if (threadIdx.x >= kCtrThreads) {
+        reg_inc<kBsRegs>();
+        const uint32_t tbase = align_table_base(dyn);
+        const uint32_t bw = (threadIdx.x - kCtrThreads) >> 5;
+        const uint32_t off = tbase + kEncTableBytes + bw * (kBsUniformMasks * 4) - smem_u32(dyn);
+        if (off + kBsUniformMasks * 4 > dyn_smem_size()) __trap();
+        if (!a.q_bs_on) return;
+        uint32_t *um = (uint32_t *)(dyn + off);
+        uint64_t tag16 = ~0ull, done = 0;
+        uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.q_units);
+        while (u != kQNone) {
+            const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);      // the next unit, a unit ahead
+            const uint64_t c0 = a.q_u0 + (u << a.q_shift);
+#pragma unroll 1
+            for (uint32_t p = 0; p < (1u << (a.q_shift - 10)); ++p)
+                ctr_bs_pass<NR, UAES_BS_BATCH>(a, lb, um, c0 + ((uint64_t)p << 10), tag16);
+            ++done;
+            u = q_back(posted, a.q_units);
+        }
+        if (lane == 0 && done) atomicAdd(a.q + 2, (unsigned long long)done);
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    ctr_queue_table_role<NR, ILP>(a, lb);
+}
+
+// ---- CTR work-queue kernel with NARROW bitsliced warps (uaes_bitslice8.cuh) --------------------------
+// Same queue, same table-driven role; the co-runner warps hold 8 blocks per thread in 32 registers
+// instead of 32 blocks in 128, so they need no more registers than the table-driven warps and
+// several of them fit per scheduler (more warps to pick from when the table-driven ones wait for
+// the lookup pipe), and their round loop is 420 instructions instead of 1 600 (instruction cache).
+// One pass = one group (256 counters, 8 rows): the state entering round 3 is U(byte 15) ^ D(group);
+// the thread's U planes are computed once per 2^40 blocks and parked in shared memory (lane-private
+// words, conflict free), D is expanded into 32 mask words by the 32 lanes of the warp.
+#ifndef UAES_Q8_TT
+#define UAES_Q8_TT 384
+#endif
+#ifndef UAES_Q8_BS
+#define UAES_Q8_BS 256
+#endif
+#ifndef UAES_Q8_TT_REGS
+#define UAES_Q8_TT_REGS 0                        // 0: both roles keep the launch allocation (no setmaxnreg)
+#endif
+#ifndef UAES_Q8_MAP
+#define UAES_Q8_MAP 1                            // bitsliced warps first: 1080.8 vs 1076.3 GiB/s; segregated by scheduler: 952-957
+#endif
+#ifndef UAES_Q8_BATCH
+#define UAES_Q8_BATCH 2                          // rows loaded ahead of the XOR / store
+#endif
+constexpr uint32_t kBs8WarpWords = 32 * 32 + 2 * 32;   // U planes (32 per lane) + two D-mask buffers
+
+// Rounds 0-2 of one group for the narrow bitsliced warps: s[32] = planes of the state entering round 3.
+// K0 / Cp1 / E0..E3 follow the slow counter bytes exactly as in the table-driven role; the thread's U
+// planes (a function of counter byte 15 alone) are rebuilt when counter bits >= 40 change and parked in
+// shared memory: plane j of this thread at up[32 * j]; dm = two buffers of 32 D-mask words per warp.
+struct Bs8Hoist {
+    uint64_t tag40 = ~0ull, tag16 = ~0ull;
+    uint32_t K0 = 0, Cp1 = 0, E0 = 0, E1 = 0, E2 = 0, E3 = 0, flip = 0;
+
+    // vg = counter of the group's first block (byte 15 = 0), reduced mod 2^56
+    __device__ __forceinline__ void group(uint32_t (&s)[32], uint32_t lb, const uint32_t *rk, uint32_t w0, uint32_t w1,
+                                          uint32_t b8, uint64_t vg, uint32_t *up, uint32_t *dm, uint32_t lane)
+    {
+        const uint32_t s0 = w0 ^ rk[0], s1 = w1 ^ rk[1];
+        uint32_t w2, w3;
+        ctr_words(b8, vg, w2, w3);
+        const uint32_t s2 = w2 ^ rk[2], s3 = w3 ^ rk[3];                      // byte 15 of the counter is 0 here
+        if ((vg >> 40) != tag40) {                                            // once per launch in practice
+            tag40 = vg >> 40;
+            K0 = lut<0, kOffT0>(lb, s0) ^ lut<1, kOffT1>(lb, s1) ^ lut<2, kOffT2>(lb, s2) ^ rk[4];
+            Cp1 = lut<0, kOffT0>(lb, s1) ^ lut<1, kOffT1>(lb, s2) ^ lut<3, kOffT3>(lb, s0) ^ rk[5];
+            tag16 = ~0ull;
+            uint32_t m[32];                                                   // m[8 c + t] = U word of column c, slot t
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t c0 = K0 ^ lut<3, kOffT3>(lb, s3 ^ ((32 * t + lane) << 24));
+                m[t] = lut<0, kOffT0>(lb, c0);      m[8 + t] = lut<3, kOffT3>(lb, c0);
+                m[16 + t] = lut<2, kOffT2>(lb, c0); m[24 + t] = lut<1, kOffT1>(lb, c0);
+            }
+            bs_transpose32(m);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) up[32 * j] = m[j];
+        }
+        if ((vg >> 16) != tag16) {                                            // every 256 groups
+            tag16 = vg >> 16;
+            const uint32_t C2 = lut<0, kOffT0>(lb, s2) ^ lut<1, kOffT1>(lb, s3) ^ lut<2, kOffT2>(lb, s0) ^ lut<3, kOffT3>(lb, s1) ^ rk[6];
+            const uint32_t C3 = lut<0, kOffT0>(lb, s3) ^ lut<1, kOffT1>(lb, s0) ^ lut<2, kOffT2>(lb, s1) ^ lut<3, kOffT3>(lb, s2) ^ rk[7];
+            E0 = lut<2, kOffT2>(lb, C2) ^ lut<3, kOffT3>(lb, C3) ^ rk[8];
+            E1 = lut<1, kOffT1>(lb, C2) ^ lut<2, kOffT2>(lb, C3) ^ rk[9];
+            E2 = lut<0, kOffT0>(lb, C2) ^ lut<1, kOffT1>(lb, C3) ^ rk[10];
+            E3 = lut<0, kOffT0>(lb, C3) ^ lut<3, kOffT3>(lb, C2) ^ rk[11];
+        }
+        const uint32_t C1 = Cp1 ^ lut<2, kOffT2>(lb, s3);                     // counter byte 14 enters through column 1 of round 1
+        const uint32_t D0 = E0 ^ lut<1, kOffT1>(lb, C1), D1 = E1 ^ lut<0, kOffT0>(lb, C1);
+        const uint32_t D2 = E2 ^ lut<3, kOffT3>(lb, C1), D3 = E3 ^ lut<2, kOffT2>(lb, C1);
+        uint32_t *d = dm + flip;                                              // double buffered: one __syncwarp per group is enough
+        flip ^= 32;
+        d[lane] = bs8_spread(D0, D1, D2, D3, (int)lane);                      // lane j owns plane j of D
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = up[32 * j] ^ d[j];
+    }
+};
+
+template <int NR>
+__device__ __forceinline__ void ctr_bs8_role(const CtrArgs8 &a, uint32_t lb, uint32_t *ws)
+{
+    constexpr int BATCH = UAES_Q8_BATCH;
+    const uint32_t *rk = a.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t *up = ws + lane;                    // plane j of this thread's U at up[32 * j]
+    uint32_t *dm = ws + 32 * 32;                 // D masks, double buffered
+    const uint32_t kGroupsPerUnit = 1u << (a.q_shift - 8);
+    const uint64_t Gfirst = a.q_u0 >> 8;
+    uint64_t done = 0;
+    Bs8Hoist hoist;
+
+    uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.q_units);
+    while (u != kQNone) {
+        const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);      // the next unit, a unit ahead
+        const uint64_t Gu = Gfirst + u * kGroupsPerUnit;
+#pragma unroll 1
+        for (uint32_t jj = 0; jj < kGroupsPerUnit; ++jj) {
+            const uint64_t G = Gu + jj;
+            const int64_t k0 = (int64_t)((G << 8) + lane) - (int64_t)a.v0;        // block of slot 0 (may be < 0 in the first unit)
+            {   // pull the pass's 4 KiB of input towards L2 while the rounds run: one 128-byte line per lane
+                const int64_t kp = (int64_t)(G << 8) - (int64_t)a.v0 + 8 * (int64_t)lane;
+                if (kp >= 0 && (uint64_t)kp < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + kp));
+            }
+            uint32_t s[32];
+            hoist.group(s, lb, rk, a.w0, a.w1, a.b8, (G << 8) & kMask56, up, dm, lane);
+            bs8_finish<NR>(s, a.bs8);
+            // XOR with the data: slot t of all lanes = one coalesced 512-byte row, loaded BATCH rows ahead
+            auto load_batch = [&](int t0, uint4 (&x)[BATCH]) {
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+                    const int64_t k = k0 + 32 * (t0 + i);
+                    x[i] = (uint64_t)k < a.nblocks ? ld_stream(a.in + k) : make_uint4(0, 0, 0, 0);
+                }
+            };
+            uint4 x[BATCH], y[BATCH];
+            load_batch(0, x);
+            bs_transpose32(s);                                                    // s[8 c + t] = word c of slot t
+#pragma unroll
+            for (int t0 = 0; t0 < 8; t0 += BATCH) {
+                if (t0 + BATCH < 8) load_batch(t0 + BATCH, y);
+#pragma unroll
+                for (int i = 0; i < BATCH; ++i) {
+                    const int64_t k = k0 + 32 * (t0 + i);
+                    const int t = t0 + i;
+                    x[i].x ^= s[t]; x[i].y ^= s[8 + t]; x[i].z ^= s[16 + t]; x[i].w ^= s[24 + t];
+                    if ((uint64_t)k < a.nblocks) st_stream(a.out + k, x[i]);
+                    x[i] = y[i];
+                }
+            }
+        }
+        ++done;
+        u = q_back(posted, a.q_units);
+    }
+    if (lane == 0 && done) atomicAdd(a.q + 2, (unsigned long long)done);
+}
+
+template <int NR, int TT, int BS>
+__global__ void __launch_bounds__(TT + BS, 1) ctr_queue8_kernel(const __grid_constant__ CtrArgs8 a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<true>(dyn);
+    constexpr int kLaunchRegs = (65536 / (TT + BS)) / 8 * 8 > 255 ? 248 : (65536 / (TT + BS)) / 8 * 8;
+    constexpr int kTtRegs = UAES_Q8_TT_REGS;
+    constexpr int kBsRegs = kTtRegs ? (kLaunchRegs + (kLaunchRegs - kTtRegs) * TT / BS) / 8 * 8 : 0;
+    // which warps play which role (UAES_Q8_MAP): 0 = the first TT / 32 warps are table-driven; 1 = the LAST ones are;
+    // 2 = segregated by scheduler (warp w runs on scheduler w % 4): schedulers 0 and 1 host table-driven warps only,
+    // the bitsliced warps share schedulers 2 and 3 with one table-driven warp each (needs TT = 384, BS = 256)
+    const uint32_t w = threadIdx.x >> 5;
+#if UAES_Q8_MAP == 1
+    const bool is_bs = w < BS / 32;
+    const uint32_t bw = w;
+#elif UAES_Q8_MAP == 2
+    static_assert(TT == 384 && BS == 256, "segregated map: 12 + 8 warps");
+    const bool is_bs = (w & 3u) >= 2u && w >= 4u;
+    const uint32_t bw = ((w >> 2) - 1u) * 2u + ((w & 3u) - 2u);
+#else
+    const bool is_bs = w >= TT / 32;
+    const uint32_t bw = w - TT / 32;
+#endif
+    if (is_bs) {
+        if (kTtRegs) { if (kBsRegs > kLaunchRegs) reg_inc<kBsRegs ? kBsRegs : 24>(); else reg_dec<kBsRegs ? kBsRegs : 24>(); }
+        // the warps' areas: in the gap in front of the 64 KiB-aligned tables if it is large enough, else behind them
+        const uint32_t d0 = smem_u32(dyn), tb = align_table_base(dyn);
+        constexpr uint32_t kNeed = (BS / 32) * kBs8WarpWords * 4;
+        uint32_t off = (d0 + 15u & ~15u) - d0;
+        if (off + kNeed > tb - d0) off = tb + kEncTableBytes - d0;
+        if (off + kNeed > dyn_smem_size()) __trap();
+        if (!a.q_bs_on) return;
+        ctr_bs8_role<NR>(a, lb, (uint32_t *)(dyn + off) + bw * kBs8WarpWords);
+        return;
+    }
+    if (kTtRegs) { if (kTtRegs < kLaunchRegs) reg_dec<kTtRegs ? kTtRegs : 24>(); else reg_inc<kTtRegs ? kTtRegs : 24>(); }
+    ctr_queue_table_role<NR, 2>(a, lb, UAES_Q8_MAP == 1 ? BS : 0);
 }
 
 // ---------------------------------------------------------------- ECB (micro_aes.c:636-680)
@@ -806,8 +1029,10 @@ static long long g_ctr_bs_min = 1ll << 23;    // 128 MiB: below it the co-runner
 //   512 / 768 / 1024 = table-driven warps only
 //   386  = the work-queue kernel (ctr_queue_kernel): 384 table-driven threads, two rows in flight,
 //          + 128 co-runner threads; no static split, bs_permille only switches the co-runner on / off
+//   388  = the work-queue kernel with NARROW bitsliced warps (ctr_queue8_kernel, default): 384 table-driven
+//          + 256 co-runner threads of 8 blocks each, 96 registers for everybody
 #ifndef UAES_CTR_DEFAULT_GEOMETRY
-#define UAES_CTR_DEFAULT_GEOMETRY 386
+#define UAES_CTR_DEFAULT_GEOMETRY 388
 #endif
 constexpr int kCtrDefaultGeometry = UAES_CTR_DEFAULT_GEOMETRY, kCtrDefaultShare = 195;
 
@@ -878,6 +1103,26 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
         // a unit takes a warp ~55 us, a CTA's table fill ~10 us)
         const uint64_t sms = (uint64_t)sm_count(), want = (a.q_units + 12 - 1) / 12;
         ctr_queue_kernel<NR, 384, 2><<<(unsigned)(want < 1 ? 1 : want < sms ? want : sms), 384 + kBsThreads, kDynSmem, st>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+    if (threads == 388) {
+        // the work queue with narrow bitsliced warps (ctr_queue8_kernel)
+        a.q_shift = (uint32_t)env_int("UAES_CTR_UNIT_SHIFT", a.nblocks >= (1ull << 28) ? kQUnitShift : kQUnitShift - 1);
+        if (a.q_shift < 10 || a.q_shift > 16) a.q_shift = kQUnitShift;
+        const uint64_t unit = 1ull << a.q_shift;
+        a.q_u0 = a.v0 & ~(unit - 1);
+        a.q_units = (a.v0 - a.q_u0 + a.nblocks + unit - 1) >> a.q_shift;
+        tls_last_unit = unit;
+        a.q_bs_on = share > 0 && (long long)a.nblocks >= g_ctr_bs_min;
+        cudaError_t e = opt_in_smem(ctr_queue8_kernel<NR, UAES_Q8_TT, UAES_Q8_BS>);
+        if (e != cudaSuccess) return e;
+        if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
+        static thread_local CtrArgs8 a8;
+        static_cast<CtrArgsBase &>(a8) = a;
+        if (a.q_bs_on) bs8_make_key_planes(a.ks.w, NR, &a8.bs8);
+        const uint64_t sms = (uint64_t)sm_count(), ttw = UAES_Q8_TT / 32, want = (a.q_units + ttw - 1) / ttw;
+        ctr_queue8_kernel<NR, UAES_Q8_TT, UAES_Q8_BS><<<(unsigned)(want < 1 ? 1 : want < sms ? want : sms), UAES_Q8_TT + UAES_Q8_BS, kDynSmem, st>>>(a8);
         ++g_launches;
         return cudaGetLastError();
     }

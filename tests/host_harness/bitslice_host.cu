@@ -6,6 +6,7 @@
 #include <string.h>
 #include "uaes_tables.cuh"
 #include "uaes_bitslice.cuh"
+#include "uaes_bitslice8.cuh"
 
 using namespace uaes;
 
@@ -110,6 +111,82 @@ extern "C" int bs_host_ecb32_decrypt(const uint32_t *rk, int rounds, const uint8
     case 10: ecb32_dec<10>(kp, in, out); return 0;
     case 12: ecb32_dec<12>(kp, in, out); return 0;
     case 14: ecb32_dec<14>(kp, in, out); return 0;
+    }
+    return 1;
+}
+
+// The narrow form (uaes_bitslice8.cuh): one pass = one group = the 256 counters sharing bytes 0..14.
+// block0: the group's counter block with byte 15 = 0; out: 256 keystream blocks.  Rounds 0-2 are
+// factored exactly as the kernels factor them (state entering round 3 = D_j ^ U_j(byte 15)).
+extern "C" int bs8_host_group(const uint32_t *rk, int rounds, const uint8_t *block0, uint8_t *out)
+{
+    static BsKeyPlanes8 kp;
+    bs8_make_key_planes(rk, rounds, &kp);
+    if (block0[15]) return 1;
+    uint32_t w[4];
+    memcpy(w, block0, 16);
+    const uint32_t s0 = w[0] ^ rk[0], s1 = w[1] ^ rk[1], s2 = w[2] ^ rk[2], s3 = w[3] ^ rk[3];
+    auto B = [](uint32_t x, int i) { return (x >> (8 * i)) & 255u; };
+    const uint32_t K0 = te_host(0, B(s0, 0)) ^ te_host(1, B(s1, 1)) ^ te_host(2, B(s2, 2)) ^ rk[4];
+    const uint32_t C1 = te_host(0, B(s1, 0)) ^ te_host(1, B(s2, 1)) ^ te_host(2, B(s3, 2)) ^ te_host(3, B(s0, 3)) ^ rk[5];
+    const uint32_t C2 = te_host(0, B(s2, 0)) ^ te_host(1, B(s3, 1)) ^ te_host(2, B(s0, 2)) ^ te_host(3, B(s1, 3)) ^ rk[6];
+    const uint32_t C3 = te_host(0, B(s3, 0)) ^ te_host(1, B(s0, 1)) ^ te_host(2, B(s1, 2)) ^ te_host(3, B(s2, 3)) ^ rk[7];
+    const uint32_t D0 = te_host(1, B(C1, 1)) ^ te_host(2, B(C2, 2)) ^ te_host(3, B(C3, 3)) ^ rk[8];
+    const uint32_t D1 = te_host(0, B(C1, 0)) ^ te_host(1, B(C2, 1)) ^ te_host(2, B(C3, 2)) ^ rk[9];
+    const uint32_t D2 = te_host(3, B(C1, 3)) ^ te_host(0, B(C2, 0)) ^ te_host(1, B(C3, 1)) ^ rk[10];
+    const uint32_t D3 = te_host(2, B(C1, 2)) ^ te_host(3, B(C2, 3)) ^ te_host(0, B(C3, 0)) ^ rk[11];
+    uint32_t dm[32];
+    for (int j = 0; j < 32; ++j) dm[j] = bs8_spread(D0, D1, D2, D3, j);
+    for (uint32_t lane = 0; lane < 32; ++lane) {
+        uint32_t up[32], s[32];
+        for (uint32_t t = 0; t < 8; ++t) {
+            const uint32_t c0 = K0 ^ te_host(3, B(s3, 3) ^ (32 * t + lane));
+            up[8 * 0 + t] = te_host(0, B(c0, 0)); up[8 * 1 + t] = te_host(3, B(c0, 3));
+            up[8 * 2 + t] = te_host(2, B(c0, 2)); up[8 * 3 + t] = te_host(1, B(c0, 1));
+        }
+        bs_transpose32(up);
+        for (int j = 0; j < 32; ++j) s[j] = up[j] ^ dm[j];
+        switch (rounds) {
+        case 10: bs8_finish<10>(s, kp); break;
+        case 12: bs8_finish<12>(s, kp); break;
+        case 14: bs8_finish<14>(s, kp); break;
+        default: return 2;
+        }
+        bs_transpose32(s);
+        for (int t = 0; t < 8; ++t)
+            for (int c = 0; c < 4; ++c) memcpy(out + 16 * (32 * t + lane) + 4 * c, &s[8 * c + t], 4);
+    }
+    return 0;
+}
+
+// 8 arbitrary blocks (128 bytes) through the narrow general form, encrypt (dec = 0) or decrypt (dec = 1)
+template <int NR>
+static void ecb8(const BsKeyPlanes8Full &kp, const uint8_t *in, uint8_t *out, int dec)
+{
+    uint32_t s[32];
+    for (int t = 0; t < 8; ++t)
+        for (int c = 0; c < 4; ++c) memcpy(&s[8 * c + t], in + 16 * t + 4 * c, 4);
+    bs_transpose32(s);
+    if (dec) bs8_decrypt_planes<NR>(s, kp); else bs8_encrypt_planes<NR>(s, kp);
+    bs_transpose32(s);
+    for (int t = 0; t < 8; ++t)
+        for (int c = 0; c < 4; ++c) memcpy(out + 16 * t + 4 * c, &s[8 * c + t], 4);
+}
+
+extern "C" int bs8_host_ecb8(const uint32_t *rk, int rounds, const uint8_t *in, uint8_t *out, int dec)
+{
+    static BsKeyPlanes8Full kp;
+    uint32_t dk[60];
+    if (dec) {
+        for (int c = 0; c < 4; ++c) { dk[c] = rk[4 * rounds + c]; dk[4 * rounds + c] = rk[c]; }
+        for (int r = 1; r < rounds; ++r)
+            for (int c = 0; c < 4; ++c) dk[4 * r + c] = inv_mix_word(rk[4 * (rounds - r) + c]);
+    }
+    bs8_make_key_planes_full(dec ? dk : rk, rounds, &kp);
+    switch (rounds) {
+    case 10: ecb8<10>(kp, in, out, dec); return 0;
+    case 12: ecb8<12>(kp, in, out, dec); return 0;
+    case 14: ecb8<14>(kp, in, out, dec); return 0;
     }
     return 1;
 }

@@ -170,7 +170,8 @@ def test_ctr_bitsliced_corunner(uaes, orc, torch, bits):
     into counter bytes 13, 12 and 9"""
     key, iv = rnd(f"bs-k{bits}", bits // 8), rnd(f"bs-i{bits}", 12)
     try:
-        for threads in (384, 385, 386):          # 385 = two blocks per table-driven thread in flight; 386 = the work-queue kernel
+        for threads in (384, 385, 386, 388):     # 385 = two blocks per table-driven thread in flight; 386 = the work-queue kernel;
+                                                 # 388 = the work queue with narrow bitsliced warps (uaes_bitslice8.cuh)
             for share, n, first in ((1024, 16 * 5000 + 3, 0), (512, 16 * 70001, 1), (300, (1 << 21) + 9, 1000),
                                     (1024, 16 * 3000, (1 << 16) - 1500), (700, 16 * 4100 + 15, (1 << 24) - 2050),
                                     (1024, 16 * 2500, (1 << 32) - 1200), (900, 16 * 2048, (1 << 56) - 1024 - 2),

@@ -259,11 +259,14 @@ def test_cbc_without_cts(uaes, orc, torch):
     assert uaes.cbc_decrypt_ex(192, key, iv, ct, 100, out, cts=True) == 0 and out.raw[:100] == orc.cbc(key, iv, ct)[1]
 
 
+@pytest.mark.parametrize("narrow", [1, 0])
 @pytest.mark.parametrize("bits", [128, 256])
-def test_gcm_bitsliced_corunner(uaes, orc, torch, bits):
+def test_gcm_bitsliced_corunner(uaes, orc, torch, bits, narrow, monkeypatch):
     """gcm_bulk_hybrid_kernel forced on for small messages: the last part of the message is encrypted by
     bitsliced warps that also run their share of the GHASH; every split, ragged ends, AAD, shards whose
     first block is not a multiple of 1024, both hash directions (encrypt / decrypting shard)"""
+    # narrow = 1: gcm_bulk_hybrid8_kernel (8 blocks per bitsliced thread, uaes_bitslice8.cuh), 0: the wide form
+    monkeypatch.setenv("UAES_GCM_NARROW", str(narrow))
     key, nonce = rnd(f"gb-k{bits}", bits // 8), rnd("gb-n", 12)
     try:
         for share, n, alen in ((200, 16 * 9000 + 3, 20), (512, 16 * 70001, 0), (900, (1 << 21) + 9, 4500), (100, 16 * 4096, 7),

@@ -59,9 +59,20 @@ def main():
     # instructions (setmaxnreg.inc ... setmaxnreg.dec), the table-driven warps' code after the second
     marks = [i for i, r in enumerate(src[2:]) if len(r) >= len(hdr) and 'USETMAXREG' in r[ix['Source']]]
     stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
-    if len(marks) >= 2 and stalls:
-        body = [r for r in src[2:] if len(r) >= len(hdr)]
-        for name, rows_ in (('bitsliced co-runner warps', body[marks[0]:marks[-1]]), ('table-driven warps', body[marks[-1]:])):
+    body = [r for r in src[2:] if len(r) >= len(hdr)]
+    regions = None
+    if len(marks) >= 2:
+        regions = (('bitsliced co-runner warps', body[marks[0]:marks[-1]]), ('table-driven warps', body[marks[-1]:]))
+    else:
+        # kernels without setmaxnreg (ctr_queue8_kernel): the co-runner role lies between the table fill's barrier and
+        # the first unpredicated EXIT after it, the table-driven role behind that
+        bar = next((i for i, r in enumerate(body) if r[ix['Source']].strip().startswith('BAR.SYNC')), None)
+        if bar is not None:
+            ex = next((i for i in range(bar, len(body)) if body[i][ix['Source']].strip().startswith('EXIT')), None)
+            if ex is not None:
+                regions = (('bitsliced co-runner warps', body[bar:ex + 1]), ('table-driven warps', body[ex + 1:]))
+    if regions and stalls:
+        for name, rows_ in regions:
             tot = {h: sum(int(r[ix[h]] or 0) for r in rows_) for h in stalls}
             n = sum(tot.values()) or 1
             inst = sum(int(r[ix['Instructions Executed']] or 0) for r in rows_)
