@@ -7,7 +7,7 @@ measured HBM roofline, next to micro_aes.c timed on the box's host cores.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        the reference's own CPU code on all host cores
 
-One step = one pass of the hot path (one ctr_queue_kernel launch: table-driven warps plus the bitsliced
+One step = one pass of the hot path (one ctr_queue8_kernel launch: table-driven warps plus the bitsliced
 ALU co-runner warps sharing the range through a work queue) over this rank's 16 GiB shard of the
 N*16 GiB buffer; rank r owns keystream blocks [r*2^30, (r+1)*2^30) (counter-range sharding, no
 data-path collective; the key and IV are broadcast once over NCCL).  Scaling is therefore weak.
@@ -197,8 +197,8 @@ def mem_available_gib():
 
 
 KERNEL_NAMES = {
-    "ctr128": "uaes::ctr_queue_kernel<10,384,2> (384 table-driven + 128 bitsliced threads per CTA, two-ended work queue)",
-    "ctr256": "uaes::ctr_queue_kernel<14,384,2>",
+    "ctr128": "uaes::ctr_queue8_kernel<10,384,256> (384 table-driven + 256 narrow bitsliced threads per CTA, 96 registers each, two-ended work queue)",
+    "ctr256": "uaes::ctr_queue8_kernel<14,384,256>",
     "ecb128": "uaes::ecb_hybrid_kernel<10,false> (table-driven + bitsliced warps)",
     "ecb128dec": "uaes::ecb_kernel<10,false>",
     "xts256": "uaes::xts_sectors_hybrid_kernel<14,true> (table-driven + bitsliced warps)",

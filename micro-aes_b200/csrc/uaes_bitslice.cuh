@@ -177,6 +177,9 @@ UAES_HD void bs_first_rounds(uint32_t s[128], uint32_t lane, uint32_t c14, const
     for (int p = 0; p < 128; ++p) s[p] = o[p];
 }
 
+#ifndef UAES_TRANSPOSE_SELECT
+#define UAES_TRANSPOSE_SELECT 1
+#endif
 // 32 x 32 bit transpose: on return bit q of m[t] = bit t of the old m[q]
 UAES_HD void bs_transpose32(uint32_t m[32])
 {
@@ -207,8 +210,15 @@ UAES_HD void bs_transpose32(uint32_t m[32])
         const uint32_t mask = j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
 #pragma unroll
         for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+#if defined(__CUDA_ARCH__) && UAES_TRANSPOSE_SELECT
+            // the swap as two bit selects (one LOP3 each) on two shifted copies: 4 instructions per pair instead of 5
+            const uint32_t lo = m[k], hi = m[k + j];
+            m[k] = lut3<0xE4>(lo, hi << j, mask);            // (a & c) | (b & ~c)
+            m[k + j] = lut3<0xE4>(lo >> j, hi, mask);
+#else
             const uint32_t t = ((m[k] >> j) ^ m[k + j]) & mask;
             m[k + j] ^= t; m[k] ^= t << j;
+#endif
         }
     }
 }

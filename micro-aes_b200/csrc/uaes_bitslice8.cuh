@@ -33,7 +33,7 @@
 
 namespace uaes {
 
-struct BsKeyPlanes8 {
+struct alignas(16) BsKeyPlanes8 {           // 16-byte aligned inside the kernel parameters: the key words load as LDC.128
     uint32_t k[kBsMaxRounds - 2][32];       // round keys 3..NR: word j, byte c = 0xFF iff bit j of key word c is set
 };
 
@@ -66,13 +66,20 @@ UAES_HD void bs8_round_or_last(uint32_t s[32], const uint32_t *kp, bool last)
         a[0][b] = bs8_shift_row<0>(s[b]);      a[1][b] = bs8_shift_row<1>(s[8 + b]);
         a[2][b] = bs8_shift_row<2>(s[16 + b]); a[3][b] = bs8_shift_row<3>(s[24 + b]);
     }
+    // the round's 32 key words as eight 128-bit loads (the planes are 16-byte aligned inside the kernel parameters)
+    uint32_t kw[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint4 v = reinterpret_cast<const uint4 *>(kp)[q];
+        kw[4 * q] = v.x; kw[4 * q + 1] = v.y; kw[4 * q + 2] = v.z; kw[4 * q + 3] = v.w;
+    }
     if (!last) {
-        bs_mix_column<0>(a[0], a[1], a[2], a[3], kp, o);
+        bs_mix_column<0>(a[0], a[1], a[2], a[3], kw, o);
     } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int b = 0; b < 8; ++b) o[8 * r + b] = a[r][b] ^ kp[8 * r + b];
+            for (int b = 0; b < 8; ++b) o[8 * r + b] = a[r][b] ^ kw[8 * r + b];
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) s[j] = o[j];
@@ -97,7 +104,7 @@ UAES_HD void bs8_finish(uint32_t s[32], const BsKeyPlanes8 &kp)
 // ---- the general form: any 8 blocks (data-dependent modes: XTS, ECB, ...) -------------------------------
 // All NR + 1 round keys as packed plane words; the state comes from ONE 32x32 transpose of
 // M[8 c + t] = word c of block t and goes back the same way.
-struct BsKeyPlanes8Full {
+struct alignas(16) BsKeyPlanes8Full {
     uint32_t k[kBsMaxRounds + 1][32];       // round keys 0..NR (for decryption: the equivalent-inverse schedule dk[0..NR])
 };
 

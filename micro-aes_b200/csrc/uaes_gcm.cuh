@@ -458,7 +458,7 @@ __device__ __forceinline__ void gcm_bs8_chunk(const GcmHybridArgs8 &h, uint32_t 
     const GcmBulkArgs &a = h.b;
     const uint32_t *rk = a.ks.w;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t *up = ws + lane, *dm = ws + 32 * 32;
+    uint32_t *up = ws + 4 * lane, *dm = ws + 32 * 32;
     const uint64_t p0 = j * h.bs_per, p1 = p0 + h.bs_per < h.bs_passes ? p0 + h.bs_per : h.bs_passes;
     const uint64_t ubase = a.v0 + h.a_blocks;                   // counter of the region's first block (not reduced mod 2^56)
     uint64_t klast = 0;

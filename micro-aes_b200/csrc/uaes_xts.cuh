@@ -386,42 +386,15 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
 }
 
 
-template <int NR, bool ENC>
-__global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
+// the table-driven role of the sector kernels with a co-runner; tt_warp = this warp's number among the CTA's table-driven warps
+template <int NR, bool ENC, class ARGS>
+__device__ __forceinline__ void xts_hybrid_tt_role(const ARGS &a, uint32_t lb, uint32_t tt_warp)
 {
-    extern __shared__ __align__(16) uint8_t dyn[];
-    const uint32_t lb = setup_xts_tables<ENC>(dyn);
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kXtsTtThreads / 32;
-    constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;      // 128
-    // 96 / 224: 582 -> 596 GiB/s for AES-256 (profiles/r2_sweep_hybrid_regs.txt); ECB and OCB keep 104 / 200
-    constexpr int kTtRegs = kHybridTtRegs - 8, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
-
-    if (threadIdx.x >= kXtsTtThreads) {
-        reg_inc<kBsRegs>();
-        if (a.q) {                                   // work queue: tiles from the BACK, the next one claimed a tile ahead
-            uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.ntiles);
-            while (u != kQNone) {
-                const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);
-                xts_bitsliced_warp<NR, ENC>(a, lb, u, u + 1);
-                u = q_back(posted, a.ntiles);
-            }
-            return;
-        }
-        const uint64_t nbs = a.ntiles - a.tt_tiles;
-        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
-        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
-        const uint64_t per = (nbs + nw - 1) / nw;
-        const uint64_t p0 = gw * per < nbs ? gw * per : nbs;
-        const uint64_t p1 = p0 + per < nbs ? p0 + per : nbs;
-        xts_bitsliced_warp<NR, ENC>(a, lb, a.tt_tiles + p0, a.tt_tiles + p1);
-        return;
-    }
-    reg_dec<kTtRegs>();
-
     // table-driven warps: a contiguous run of tiles each (static split) or tiles claimed from the FRONT of
     // the work queue, two sectors in flight
-    const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+    const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + tt_warp;
     const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
     const uint64_t per = (a.tt_tiles + nw - 1) / nw;
     const uint64_t q0 = a.q ? q_front(q_post(a.q, 1ull, a.q_zero), a.ntiles) : gw * per < a.tt_tiles ? gw * per : a.tt_tiles;
@@ -468,6 +441,164 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
             }
         }
     }
+}
+
+template <int NR, bool ENC>
+__global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_xts_tables<ENC>(dyn);
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kTtWarps = kXtsTtThreads / 32;
+    constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;      // 128
+    // 96 / 224: 582 -> 596 GiB/s for AES-256 (profiles/r2_sweep_hybrid_regs.txt); ECB and OCB keep 104 / 200
+    constexpr int kTtRegs = kHybridTtRegs - 8, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
+
+    if (threadIdx.x >= kXtsTtThreads) {
+        reg_inc<kBsRegs>();
+        if (a.q) {                                   // work queue: tiles from the BACK, the next one claimed a tile ahead
+            uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.ntiles);
+            while (u != kQNone) {
+                const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);
+                xts_bitsliced_warp<NR, ENC>(a, lb, u, u + 1);
+                u = q_back(posted, a.ntiles);
+            }
+            return;
+        }
+        const uint64_t nbs = a.ntiles - a.tt_tiles;
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        const uint64_t per = (nbs + nw - 1) / nw;
+        const uint64_t p0 = gw * per < nbs ? gw * per : nbs;
+        const uint64_t p1 = p0 + per < nbs ? p0 + per : nbs;
+        xts_bitsliced_warp<NR, ENC>(a, lb, a.tt_tiles + p0, a.tt_tiles + p1);
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    xts_hybrid_tt_role<NR, ENC>(a, lb, threadIdx.x >> 5);
+}
+
+// ---- the same with NARROW bitsliced warps (uaes_bitslice8.cuh, general form): 8 sectors per pass, lane l, slot t
+// <-> block l of sector t.  32 state registers instead of 128: the warps run in 96 registers like the table-driven
+// ones (8 of them per SM, no setmaxnreg) and one round is 440 (forward) / 520 (inverse) instructions, so the
+// round loop -- also the INVERSE one, whose wide form did not fit the instruction cache -- stays cached.
+struct XtsHybridArgs8 {
+    XtsSectorArgs x;             // sector_blocks == 32
+    uint64_t tt_tiles, ntiles;   // as XtsHybridArgs
+    unsigned long long *q;
+    uint32_t q_zero;
+    BsKeyPlanes8Full bs;
+};
+
+#ifndef UAES_XTS8_BS
+#define UAES_XTS8_BS 256
+#endif
+#ifndef UAES_XTS8_DEC_DEFAULT_SHARE
+#define UAES_XTS8_DEC_DEFAULT_SHARE 165          // decryption with the narrow co-runner: on (work queue; the value only has to be > 0)
+#endif
+constexpr int kXts8BsThreads = UAES_XTS8_BS;
+
+template <int NR, bool ENC>
+__device__ __forceinline__ void xts_bs8_tile(const XtsHybridArgs8 &a, uint32_t lb, uint64_t tile)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t sec0 = tile * 32;
+    const uint64_t left = a.x.nsectors - sec0;
+    const int nsec = left < 32 ? (int)left : 32;
+    const uint4 *src = a.x.in + sec0 * 32 + lane;
+    uint4 *dst = a.x.out + sec0 * 32 + lane;
+    if ((int)(lane >> 2) < nsec) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x.in + sec0 * 32 + 8 * lane));   // the first 8 sectors
+    // T_0 of sector sec0 + lane (micro_aes.c:1017-1027)
+    const uint64_t sec = a.x.first_sector + sec0 + lane;
+    uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
+    if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
+    else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.x.k2.w);
+    auto tweak_of = [&](int t, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+        Tweak tw;
+        tw.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, t) << 32 | __shfl_sync(0xffffffffu, e0, t);
+        tw.hi = (uint64_t)__shfl_sync(0xffffffffu, e3, t) << 32 | __shfl_sync(0xffffffffu, e2, t);
+        tweak_words(xts_shl(tw, lane), w0, w1, w2, w3);
+    };
+#pragma unroll 1
+    for (int q = 0; q < 32; q += 8) {
+        if (q >= nsec) break;
+        if (q + 8 + (int)(lane >> 2) < nsec)                     // the next pass's 4 KiB towards L2 while this one's rounds run
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x.in + (sec0 + q + 8) * 32 + 8 * lane));
+        uint32_t s[32];
+        {
+            uint4 v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = q + t < nsec ? ld_stream(src + (q + t) * 32) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                uint32_t w0, w1, w2, w3;
+                tweak_of(q + t, w0, w1, w2, w3);
+                s[t] = v[t].x ^ w0; s[8 + t] = v[t].y ^ w1; s[16 + t] = v[t].z ^ w2; s[24 + t] = v[t].w ^ w3;
+            }
+        }
+        bs_transpose32(s);
+        if (ENC) bs8_encrypt_planes<NR>(s, a.bs); else bs8_decrypt_planes<NR>(s, a.bs);
+        bs_transpose32(s);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            uint32_t w0, w1, w2, w3;
+            tweak_of(q + t, w0, w1, w2, w3);
+            if (q + t < nsec) st_stream(dst + (q + t) * 32, make_uint4(s[t] ^ w0, s[8 + t] ^ w1, s[16 + t] ^ w2, s[24 + t] ^ w3));
+        }
+    }
+}
+
+template <int NR, bool ENC>
+__global__ void __launch_bounds__(kXtsTtThreads + kXts8BsThreads, 1) xts_sectors_hybrid8_kernel(const __grid_constant__ XtsHybridArgs8 a)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_xts_tables<ENC>(dyn);
+    constexpr uint32_t kBsWarps = kXts8BsThreads / 32;
+    const uint32_t w = threadIdx.x >> 5;
+    if (w < kBsWarps) {                              // the bitsliced warps take the low warp numbers (ctr_queue8_kernel: UAES_Q8_MAP)
+        if (a.q) {                                   // work queue: tiles from the BACK, the next one claimed a tile ahead
+            uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.ntiles);
+            while (u != kQNone) {
+                const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);
+                xts_bs8_tile<NR, ENC>(a, lb, u);
+                u = q_back(posted, a.ntiles);
+            }
+            return;
+        }
+        const uint64_t nbs = a.ntiles - a.tt_tiles;
+        const uint64_t gw = (uint64_t)blockIdx.x * kBsWarps + w, nw = (uint64_t)gridDim.x * kBsWarps;
+        const uint64_t per = (nbs + nw - 1) / nw;
+        const uint64_t p0 = gw * per < nbs ? gw * per : nbs;
+        const uint64_t p1 = p0 + per < nbs ? p0 + per : nbs;
+        for (uint64_t tile = a.tt_tiles + p0; tile < a.tt_tiles + p1; ++tile) xts_bs8_tile<NR, ENC>(a, lb, tile);
+        return;
+    }
+    xts_hybrid_tt_role<NR, ENC>(a, lb, w - kBsWarps);
+}
+
+#ifndef UAES_XTS_NARROW_DEFAULT
+#define UAES_XTS_NARROW_DEFAULT 0           // measured: 522 vs 612 GiB/s (encrypt), 490 vs 558 (decrypt against no co-runner): profiles/r2_sweep_xts8.txt
+#endif
+
+template <int NR, bool ENC>
+static cudaError_t launch_xts_hybrid8_nr(const XtsSectorArgs &x, uint64_t bs_tiles, cudaStream_t st)
+{
+    cudaError_t e = opt_in_smem(xts_sectors_hybrid8_kernel<NR, ENC>);
+    if (e != cudaSuccess) return e;
+    static thread_local XtsHybridArgs8 a;
+    a.x = x;
+    a.ntiles = (x.nsectors + 31) / 32;
+    a.tt_tiles = a.ntiles - bs_tiles;
+    a.q = nullptr; a.q_zero = 0;
+    if (env_int("UAES_XTS_QUEUE", kXtsQueueDefault)) {                 // dynamic split, both directions (the static share is ignored)
+        if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
+    }
+    bs8_make_key_planes_full(x.k1.w, NR, &a.bs);
+    const uint64_t need = (a.ntiles + 15) / 16, sms = (uint64_t)sm_count();
+    xts_sectors_hybrid8_kernel<NR, ENC><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kXts8BsThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
 }
 
 template <int NR, bool ENC>
@@ -549,9 +680,21 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
         // table-driven decrypt rounds rotate half of their lookups on the ALU pipe (Td2/Td3 from
         // Td0/Td1), so less of that pipe is idle and the co-runner costs more than it adds
         // (558 -> 523 / 480 GiB/s at 30 / 100 per 1024).  Off unless asked for.
-        const int dflt = encrypt ? env_int("UAES_XTS_BS_PERMILLE", kXtsDefaultShare) : env_int("UAES_XTS_DEC_BS_PERMILLE", 0);
+        const bool narrow = env_int("UAES_XTS_NARROW", UAES_XTS_NARROW_DEFAULT) != 0;
+        const int dflt = encrypt ? env_int("UAES_XTS_BS_PERMILLE", kXtsDefaultShare)
+                                 : env_int("UAES_XTS_DEC_BS_PERMILLE", narrow ? UAES_XTS8_DEC_DEFAULT_SHARE : 0);
         const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : dflt;
         const uint64_t bs_tiles = ntiles * (uint64_t)share / 1024;
+        if (bs_tiles > 0 && narrow) {
+            switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
+            case 21: return (int)launch_xts_hybrid8_nr<10, true>(a, bs_tiles, st);
+            case 20: return (int)launch_xts_hybrid8_nr<10, false>(a, bs_tiles, st);
+            case 25: return (int)launch_xts_hybrid8_nr<12, true>(a, bs_tiles, st);
+            case 24: return (int)launch_xts_hybrid8_nr<12, false>(a, bs_tiles, st);
+            case 29: return (int)launch_xts_hybrid8_nr<14, true>(a, bs_tiles, st);
+            case 28: return (int)launch_xts_hybrid8_nr<14, false>(a, bs_tiles, st);
+            }
+        }
         if (bs_tiles > 0) {
             switch (ks1->rounds * 2 + (encrypt ? 1 : 0)) {
             case 21: return (int)launch_xts_hybrid_nr<10, true>(a, bs_tiles, st);

@@ -249,10 +249,14 @@ def test_ocb_bitsliced_corunner(uaes, orc, bits):
         uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
-@pytest.mark.parametrize("bits", [128, 256])
-def test_xts_sectors_bitsliced_corunner(uaes, orc, bits):
+@pytest.mark.parametrize("narrow", [1, 0])
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_xts_sectors_bitsliced_corunner(uaes, orc, bits, narrow, monkeypatch):
     """512-byte sector encryption with the ALU co-runner warps forced on for small calls, at several
-    splits between table-driven and bitsliced tiles, ragged last tiles, sector numbers across 2^32"""
+    splits between table-driven and bitsliced tiles, ragged last tiles, sector numbers across 2^32;
+    narrow = 1: xts_sectors_hybrid8_kernel (8 sectors per bitsliced pass, uaes_bitslice8.cuh, both directions
+    through the work queue), narrow = 0: the wide form"""
+    monkeypatch.setenv("UAES_XTS_NARROW", str(narrow))
     try:
         for share, first, ns in ((1024, 0, 33), (512, 5, 100), (300, (1 << 32) - 40, 1000), (1024, 1 << 40, 64),
                                  (700, 9, 4096 + 7), (1, 3, 2048), (1024, 0, 1)):
