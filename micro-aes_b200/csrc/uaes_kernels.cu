@@ -601,21 +601,40 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
 // One pass = one group (256 counters, 8 rows): the state entering round 3 is U(byte 15) ^ D(group);
 // the thread's U planes are computed once per 2^40 blocks and parked in shared memory (lane-private
 // words, conflict free), D is expanded into 32 mask words by the 32 lanes of the warp.
+// Geometry (profiles/r2_sweep_q8.txt): 16 table-driven warps with ONE row in flight at 64 registers + 8 bitsliced warps
+// at 112 (setmaxnreg from a launch allocation of 80): 1100-1115 GiB/s; 12 table-driven warps with two rows in flight +
+// 8 bitsliced, 96 registers each, no setmaxnreg: 1080-1090 on the same boxes; 20 + 8 (64 / 88): 1109; 20 + 4: 1078;
+// 16 + 12: 1069; table-driven warps at 56 registers: 1073 (16 + 8), 1105 (20 + 8).
 #ifndef UAES_Q8_TT
-#define UAES_Q8_TT 384
+#define UAES_Q8_TT 512
 #endif
 #ifndef UAES_Q8_BS
 #define UAES_Q8_BS 256
 #endif
 #ifndef UAES_Q8_TT_REGS
-#define UAES_Q8_TT_REGS 0                        // 0: both roles keep the launch allocation (no setmaxnreg)
+#define UAES_Q8_TT_REGS 64                       // 0: both roles keep the launch allocation (no setmaxnreg)
 #endif
 #ifndef UAES_Q8_MAP
 #define UAES_Q8_MAP 1                            // bitsliced warps first: 1080.8 vs 1076.3 GiB/s; segregated by scheduler: 952-957
 #endif
+#ifndef UAES_Q8_ILP
+#define UAES_Q8_ILP 1                            // rows in flight per table-driven thread
+#endif
 #ifndef UAES_Q8_BATCH
 #define UAES_Q8_BATCH 2                          // rows loaded ahead of the XOR / store
 #endif
+// AES-192 / 256 keep 12 table-driven warps with two rows in flight + 8 bitsliced warps at 96 registers each (no
+// setmaxnreg): AES-256 759 GiB/s against 740 in the AES-128 geometry (the longer round loop spills there)
+#ifndef UAES_Q8_TT_LONG
+#define UAES_Q8_TT_LONG 384
+#define UAES_Q8_BS_LONG 256
+#define UAES_Q8_ILP_LONG 2
+#define UAES_Q8_TT_REGS_LONG 0
+#endif
+template <int NR> struct Q8Geom {
+    static constexpr int TT = NR == 10 ? UAES_Q8_TT : UAES_Q8_TT_LONG, BS = NR == 10 ? UAES_Q8_BS : UAES_Q8_BS_LONG;
+    static constexpr int ILP = NR == 10 ? UAES_Q8_ILP : UAES_Q8_ILP_LONG, TTREGS = NR == 10 ? UAES_Q8_TT_REGS : UAES_Q8_TT_REGS_LONG;
+};
 constexpr uint32_t kBs8WarpWords = 32 * 32 + 2 * 32;   // U planes (32 per lane) + two D-mask buffers
 
 // Rounds 0-2 of one group for the narrow bitsliced warps: s[32] = planes of the state entering round 3.
@@ -733,13 +752,13 @@ __device__ __forceinline__ void ctr_bs8_role(const CtrArgs8 &a, uint32_t lb, uin
     if (lane == 0 && done) atomicAdd(a.q + 2, (unsigned long long)done);
 }
 
-template <int NR, int TT, int BS>
+template <int NR, int TT, int BS, int ILP, int TTREGS>
 __global__ void __launch_bounds__(TT + BS, 1) ctr_queue8_kernel(const __grid_constant__ CtrArgs8 a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_tables<true>(dyn);
     constexpr int kLaunchRegs = (65536 / (TT + BS)) / 8 * 8 > 255 ? 248 : (65536 / (TT + BS)) / 8 * 8;
-    constexpr int kTtRegs = UAES_Q8_TT_REGS;
+    constexpr int kTtRegs = TTREGS;
     constexpr int kBsRegs = kTtRegs ? (kLaunchRegs + (kLaunchRegs - kTtRegs) * TT / BS) / 8 * 8 : 0;
     // which warps play which role (UAES_Q8_MAP): 0 = the first TT / 32 warps are table-driven; 1 = the LAST ones are;
     // 2 = segregated by scheduler (warp w runs on scheduler w % 4): schedulers 0 and 1 host table-driven warps only,
@@ -769,7 +788,7 @@ __global__ void __launch_bounds__(TT + BS, 1) ctr_queue8_kernel(const __grid_con
         return;
     }
     if (kTtRegs) { if (kTtRegs < kLaunchRegs) reg_dec<kTtRegs ? kTtRegs : 24>(); else reg_inc<kTtRegs ? kTtRegs : 24>(); }
-    ctr_queue_table_role<NR, 2>(a, lb, UAES_Q8_MAP == 1 ? BS : 0);
+    ctr_queue_table_role<NR, ILP>(a, lb, UAES_Q8_MAP == 1 ? BS : 0);
 }
 
 // ---------------------------------------------------------------- ECB (micro_aes.c:636-680)
@@ -1033,8 +1052,8 @@ static long long g_ctr_bs_min = 1ll << 23;    // 128 MiB: below it the co-runner
 //   512 / 768 / 1024 = table-driven warps only
 //   386  = the work-queue kernel (ctr_queue_kernel): 384 table-driven threads, two rows in flight,
 //          + 128 co-runner threads; no static split, bs_permille only switches the co-runner on / off
-//   388  = the work-queue kernel with NARROW bitsliced warps (ctr_queue8_kernel, default): 384 table-driven
-//          + 256 co-runner threads of 8 blocks each, 96 registers for everybody
+//   388  = the work-queue kernel with NARROW bitsliced warps (ctr_queue8_kernel, default): 512 table-driven threads
+//          with one row in flight (64 registers) + 256 co-runner threads of 8 blocks each (112 registers)
 #ifndef UAES_CTR_DEFAULT_GEOMETRY
 #define UAES_CTR_DEFAULT_GEOMETRY 388
 #endif
@@ -1119,14 +1138,16 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
         a.q_units = (a.v0 - a.q_u0 + a.nblocks + unit - 1) >> a.q_shift;
         tls_last_unit = unit;
         a.q_bs_on = share > 0 && (long long)a.nblocks >= g_ctr_bs_min;
-        cudaError_t e = opt_in_smem(ctr_queue8_kernel<NR, UAES_Q8_TT, UAES_Q8_BS>);
+        using G = Q8Geom<NR>;
+        auto kernel = ctr_queue8_kernel<NR, G::TT, G::BS, G::ILP, G::TTREGS>;
+        cudaError_t e = opt_in_smem(kernel);
         if (e != cudaSuccess) return e;
         if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
         static thread_local CtrArgs8 a8;
         static_cast<CtrArgsBase &>(a8) = a;
         if (a.q_bs_on) bs8_make_key_planes(a.ks.w, NR, &a8.bs8);
-        const uint64_t sms = (uint64_t)sm_count(), ttw = UAES_Q8_TT / 32, want = (a.q_units + ttw - 1) / ttw;
-        ctr_queue8_kernel<NR, UAES_Q8_TT, UAES_Q8_BS><<<(unsigned)(want < 1 ? 1 : want < sms ? want : sms), UAES_Q8_TT + UAES_Q8_BS, kDynSmem, st>>>(a8);
+        const uint64_t sms = (uint64_t)sm_count(), ttw = G::TT / 32, want = (a.q_units + ttw - 1) / ttw;
+        kernel<<<(unsigned)(want < 1 ? 1 : want < sms ? want : sms), G::TT + G::BS, kDynSmem, st>>>(a8);
         ++g_launches;
         return cudaGetLastError();
     }

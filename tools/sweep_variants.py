@@ -28,7 +28,11 @@ for spec in args:
         env[k] = v
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-cpu", "--no-e2e",
            "--no-secondary", "--workload", workload] + (["--gib-per-gpu", gib] if gib else [])
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    except subprocess.TimeoutExpired:
+        print(f"{spec:40s} TIMEOUT", flush=True)
+        continue
     try:
         j = json.loads(r.stdout.strip().splitlines()[-1])
         print(f"{spec:40s} {j['value']:9.2f} GiB/s  kernel {j['roofline']['kernel_ms']:8.4f} ms  parity {j.get('parity_spot_check')}"
