@@ -858,7 +858,17 @@ struct EcbHybridArgs {
     BsKeyPlanesFull bs;
 };
 
-constexpr int kEcbTtThreads = 384;
+// table-driven side: UAES_ECB_TT threads with UAES_ECB_ILP rows in flight at UAES_ECB_TT_REGS registers (profiles/r2_sweep_ecb_ilp.txt)
+#ifndef UAES_ECB_TT
+#define UAES_ECB_TT 384
+#endif
+#ifndef UAES_ECB_ILP
+#define UAES_ECB_ILP 2
+#endif
+#ifndef UAES_ECB_TT_REGS
+#define UAES_ECB_TT_REGS kHybridTtRegs
+#endif
+constexpr int kEcbTtThreads = UAES_ECB_TT;
 
 template <int NR, bool CFB>
 __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kernel(const __grid_constant__ EcbHybridArgs a)
@@ -872,7 +882,7 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kEcbTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kEcbTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = kHybridTtRegs, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbTtThreads / kBsThreads;
+    constexpr int kTtRegs = UAES_ECB_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbTtThreads / kBsThreads) / 8 * 8;
 
     if (threadIdx.x >= kEcbTtThreads) {
         reg_inc<kBsRegs>();
@@ -916,28 +926,34 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
     }
     reg_dec<kTtRegs>();
 
-    const uint64_t npairs = a.tt_blocks / 64;                    // pairs of 32-block rows
+    constexpr int ILP = UAES_ECB_ILP;                            // 32-block rows in flight per thread
+    const uint64_t nsteps = a.tt_blocks / (32 * ILP);            // tt_blocks is a multiple of 1024
     const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
-    const uint64_t per = (npairs + nw - 1) / nw;
-    const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
-    const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
-    uint4 cur[2], nxt[2];
-    if (q0 < q1) { cur[0] = cin(q0 * 64 + lane); cur[1] = cin(q0 * 64 + 32 + lane); }
-    for (uint64_t q = q0; q < q1; ++q) {
-        const uint64_t k = q * 64 + lane;
-        if (q + 1 < q1) { nxt[0] = cin(k + 64); nxt[1] = cin(k + 96); }
-        uint4 zero[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (CFB) { zero[0] = ld_stream(a.e.in + k); zero[1] = ld_stream(a.e.in + k + 32); }     // the ciphertext XORed in at the end
-        uint32_t st[2][4];
+    const uint64_t per = (nsteps + nw - 1) / nw;
+    const uint64_t q0 = gw * per < nsteps ? gw * per : nsteps;
+    const uint64_t q1 = q0 + per < nsteps ? q0 + per : nsteps;
+    uint4 cur[ILP], nxt[ILP];
+    if (q0 < q1) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ILP; ++i) cur[i] = cin(q0 * (32 * ILP) + 32 * i + lane);
+    }
+    for (uint64_t q = q0; q < q1; ++q) {
+        const uint64_t k = q * (32 * ILP) + lane;
+        uint4 zero[ILP];
+        uint32_t st[ILP][4];
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (q + 1 < q1) nxt[i] = cin(k + 32 * ILP + 32 * i);
+            zero[i] = CFB ? ld_stream(a.e.in + k + 32 * i) : make_uint4(0, 0, 0, 0);             // the ciphertext XORed in at the end
             st[i][0] = cur[i].x ^ rk[0]; st[i][1] = cur[i].y ^ rk[1]; st[i][2] = cur[i].z ^ rk[2]; st[i][3] = cur[i].w ^ rk[3];
         }
-        enc_finish_n<NR, 1, 2>(lb, st, rk, zero);
-        st_stream(a.e.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
-        st_stream(a.e.out + k + 32, make_uint4(st[1][0], st[1][1], st[1][2], st[1][3]));
-        cur[0] = nxt[0]; cur[1] = nxt[1];
+        enc_finish_n<NR, 1, ILP>(lb, st, rk, zero);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            st_stream(a.e.out + k + 32 * i, make_uint4(st[i][0], st[i][1], st[i][2], st[i][3]));
+            cur[i] = nxt[i];
+        }
     }
 
     if ((a.e.tail || (!CFB && a.e.pad)) && blockIdx.x == 0 && threadIdx.x == 0) {

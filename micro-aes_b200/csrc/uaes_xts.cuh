@@ -387,13 +387,13 @@ __device__ __forceinline__ void xts_bitsliced_warp(const XtsHybridArgs &a, uint3
 
 
 // the table-driven role of the sector kernels with a co-runner; tt_warp = this warp's number among the CTA's table-driven warps
-template <int NR, bool ENC, class ARGS>
+template <int NR, bool ENC, int ILP, int TTW, class ARGS>
 __device__ __forceinline__ void xts_hybrid_tt_role(const ARGS &a, uint32_t lb, uint32_t tt_warp)
 {
     const uint32_t lane = threadIdx.x & 31;
-    constexpr int kTtWarps = kXtsTtThreads / 32;
+    constexpr int kTtWarps = TTW;                // table-driven warps per CTA
     // table-driven warps: a contiguous run of tiles each (static split) or tiles claimed from the FRONT of
-    // the work queue, two sectors in flight
+    // the work queue, ILP sectors in flight
     const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + tt_warp;
     const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
     const uint64_t per = (a.tt_tiles + nw - 1) / nw;
@@ -409,22 +409,22 @@ __device__ __forceinline__ void xts_hybrid_tt_role(const ARGS &a, uint32_t lb, u
         const uint64_t sec = a.x.first_sector + sec0 + lane;
         const uint4 *src = a.x.in + sec0 * 32 + lane;
         uint4 *dst = a.x.out + sec0 * 32 + lane;
-        uint4 cur[2], nxt[2];
+        uint4 cur[ILP], nxt[ILP];
         // the tile's first two sectors are requested BEFORE the 32 tweak encryptions: their latency hides
         // behind those (ncu had the table-driven warps at 12 % long-scoreboard stalls, one cold load per tile):
         // 591-596 -> 613 GiB/s; an L2 prefetch of the NEXT tile from the middle of this one made it worse (608),
         // profiles/r2_sweep_xts_loads_first.txt
 #pragma unroll
-        for (int i = 0; i < 2; ++i) cur[i] = i < nsec ? ld_stream(src + i * 32) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < ILP; ++i) cur[i] = i < nsec ? ld_stream(src + i * 32) : make_uint4(0, 0, 0, 0);
         uint32_t e0 = (uint32_t)sec, e1 = (uint32_t)(sec >> 32), e2 = 0, e3 = 0;
         if (ENC) enc_block<NR>(lb, e0, e1, e2, e3, a.x.k2.w);
         else     enc_block_te0<NR, kOffDecTe0>(lb, e0, e1, e2, e3, a.x.k2.w);
-        for (int sct = 0; sct < nsec; sct += 2) {
-            uint32_t st[2][4];
-            uint4 tw[2];
+        for (int sct = 0; sct < nsec; sct += ILP) {
+            uint32_t st[ILP][4];
+            uint4 tw[ILP];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                nxt[i] = sct + 2 + i < nsec ? ld_stream(src + (sct + 2 + i) * 32) : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < ILP; ++i) {
+                nxt[i] = sct + ILP + i < nsec ? ld_stream(src + (sct + ILP + i) * 32) : make_uint4(0, 0, 0, 0);
                 Tweak t;
                 t.lo = (uint64_t)__shfl_sync(0xffffffffu, e1, (sct + i) & 31) << 32 | __shfl_sync(0xffffffffu, e0, (sct + i) & 31);
                 t.hi = (uint64_t)__shfl_sync(0xffffffffu, e3, (sct + i) & 31) << 32 | __shfl_sync(0xffffffffu, e2, (sct + i) & 31);
@@ -433,9 +433,9 @@ __device__ __forceinline__ void xts_hybrid_tt_role(const ARGS &a, uint32_t lb, u
                 st[i][2] = cur[i].z ^ tw[i].z; st[i][3] = cur[i].w ^ tw[i].w;
                 if (ENC) { st[i][0] ^= k1[0]; st[i][1] ^= k1[1]; st[i][2] ^= k1[2]; st[i][3] ^= k1[3]; }
             }
-            if (ENC) enc_finish_n<NR, 1, 2>(lb, st, k1, tw); else dec_block_n<NR, 2>(lb, st, k1, tw);
+            if (ENC) enc_finish_n<NR, 1, ILP>(lb, st, k1, tw); else dec_block_n<NR, ILP>(lb, st, k1, tw);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < ILP; ++i) {
                 if (sct + i < nsec) st_stream(dst + (sct + i) * 32, make_uint4(st[i][0], st[i][1], st[i][2], st[i][3]));
                 cur[i] = nxt[i];
             }
@@ -443,18 +443,32 @@ __device__ __forceinline__ void xts_hybrid_tt_role(const ARGS &a, uint32_t lb, u
     }
 }
 
+// geometry of the table-driven side (profiles/r2_sweep_xts_ilp.txt): UAES_XTS_TT threads with UAES_XTS_ILP sectors in flight
+// 16 warps with ONE sector in flight at 64 registers (+ the 4 bitsliced warps at 224): 651.8 GiB/s for AES-256 against 614.7 for
+// 12 warps with two sectors in flight at 96; 20 warps at 56 registers: 646.5; 16 at 72 (co-runner 192): 650.2
+#ifndef UAES_XTS_TT
+#define UAES_XTS_TT 512
+#endif
+#ifndef UAES_XTS_ILP
+#define UAES_XTS_ILP 1
+#endif
+#ifndef UAES_XTS_TT_REGS
+#define UAES_XTS_TT_REGS 64
+#endif
+constexpr int kXtsHybTt = UAES_XTS_TT;
+
 template <int NR, bool ENC>
-__global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
+__global__ void __launch_bounds__(kXtsHybTt + kBsThreads, 1) xts_sectors_hybrid_kernel(const __grid_constant__ XtsHybridArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_xts_tables<ENC>(dyn);
     const uint32_t lane = threadIdx.x & 31;
-    constexpr int kTtWarps = kXtsTtThreads / 32;
-    constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;      // 128
+    constexpr int kTtWarps = kXtsHybTt / 32;
+    constexpr int kLaunchRegs = (65536 / (kXtsHybTt + kBsThreads)) / 8 * 8;          // 128 for 384 + 128 threads
     // 96 / 224: 582 -> 596 GiB/s for AES-256 (profiles/r2_sweep_hybrid_regs.txt); ECB and OCB keep 104 / 200
-    constexpr int kTtRegs = kHybridTtRegs - 8, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
+    constexpr int kTtRegs = UAES_XTS_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsHybTt / kBsThreads) / 8 * 8;
 
-    if (threadIdx.x >= kXtsTtThreads) {
+    if (threadIdx.x >= kXtsHybTt) {
         reg_inc<kBsRegs>();
         if (a.q) {                                   // work queue: tiles from the BACK, the next one claimed a tile ahead
             uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), a.ntiles);
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
             return;
         }
         const uint64_t nbs = a.ntiles - a.tt_tiles;
-        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsHybTt) >> 5);
         const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
         const uint64_t per = (nbs + nw - 1) / nw;
         const uint64_t p0 = gw * per < nbs ? gw * per : nbs;
@@ -476,7 +490,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_sectors_hyb
     }
     reg_dec<kTtRegs>();
 
-    xts_hybrid_tt_role<NR, ENC>(a, lb, threadIdx.x >> 5);
+    xts_hybrid_tt_role<NR, ENC, UAES_XTS_ILP, kTtWarps>(a, lb, threadIdx.x >> 5);
 }
 
 // ---- the same with NARROW bitsliced warps (uaes_bitslice8.cuh, general form): 8 sectors per pass, lane l, slot t
@@ -574,7 +588,7 @@ __global__ void __launch_bounds__(kXtsTtThreads + kXts8BsThreads, 1) xts_sectors
         for (uint64_t tile = a.tt_tiles + p0; tile < a.tt_tiles + p1; ++tile) xts_bs8_tile<NR, ENC>(a, lb, tile);
         return;
     }
-    xts_hybrid_tt_role<NR, ENC>(a, lb, w - kBsWarps);
+    xts_hybrid_tt_role<NR, ENC, 2, kXtsTtThreads / 32>(a, lb, w - kBsWarps);
 }
 
 #ifndef UAES_XTS_NARROW_DEFAULT
@@ -616,7 +630,7 @@ static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tile
     }
     bs_make_key_planes_full(x.k1.w, NR, &a.bs);
     const uint64_t need = (a.ntiles + 15) / 16, sms = (uint64_t)sm_count();
-    xts_sectors_hybrid_kernel<NR, ENC><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    xts_sectors_hybrid_kernel<NR, ENC><<<(unsigned)(need < sms ? need : sms), kXtsHybTt + kBsThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
