@@ -197,17 +197,17 @@ def mem_available_gib():
 
 
 KERNEL_NAMES = {
-    "ctr128": "uaes::ctr_queue8_kernel<10,384,256> (384 table-driven + 256 narrow bitsliced threads per CTA, 96 registers each, two-ended work queue)",
-    "ctr256": "uaes::ctr_queue8_kernel<14,384,256>",
+    "ctr128": "uaes::ctr_queue8_kernel<10,512,256,1,64> (16 table-driven warps, one row in flight, 64 registers + 8 narrow bitsliced warps, 112 registers; two-ended work queue)",
+    "ctr256": "uaes::ctr_queue8_kernel<14,384,256,2,0> (12 table-driven + 8 narrow bitsliced warps, 96 registers each)",
     "ecb128": "uaes::ecb_hybrid_kernel<10,false> (table-driven + bitsliced warps)",
-    "ecb128dec": "uaes::ecb_kernel<10,false>",
-    "xts256": "uaes::xts_sectors_hybrid_kernel<14,true> (table-driven + bitsliced warps)",
-    "xts256dec": "uaes::xts_sectors_kernel<14,false>",
+    "ecb128dec": "uaes::ecb_dec_hybrid_kernel<10,false> (16 table-driven warps + 4 bitsliced inverse-cipher warps, work queue)",
+    "xts256": "uaes::xts_sectors_hybrid_kernel<14,true> (16 table-driven warps, one sector in flight + 4 bitsliced warps, work queue)",
+    "xts256dec": "uaes::xts_sectors_hybrid_kernel<14,false> (16 table-driven warps + 4 bitsliced inverse-cipher warps, work queue)",
     "xts256unit": "uaes::xts_unit_kernel<14,true>",
-    "gcm128": "uaes::gcm_setup_kernel + uaes::gcm_bulk_kernel<10,0> + uaes::gcm_finish_kernel",
+    "gcm128": "uaes::gcm_setup_kernel + uaes::gcm_bulk_hybrid_kernel<10,0> (table-driven + bitsliced warps) + uaes::gcm_finish_kernel",
     "gcmsiv128": "uaes::gcm_bulk_kernel<10,1,true> (POLYVAL) + uaes::ctr32_kernel<10>",
     "ocb128": "uaes::ocb_hybrid_kernel<10> (table-driven + bitsliced warps)",
-    "cbc128dec": "uaes::chain_dec_kernel<10,true>",
+    "cbc128dec": "uaes::ecb_dec_hybrid_kernel<10,true> (CBC form; 16 table-driven warps + 4 bitsliced inverse-cipher warps, work queue)",
     "cfb128dec": "uaes::ecb_hybrid_kernel<10,true> (CFB form)",
     "ccm128batch": "uaes::ccm_batch_kernel<10> (1 KiB messages, one per lane)",
     "eax128batch": "uaes::eax_batch_kernel<10> (1 KiB messages, one per lane)",

@@ -22,6 +22,7 @@ struct ChainArgs {
     uint4 *out;
     uint64_t nblocks;            // blocks handled by the plain loop
     uint32_t tail;               // CBC: r of the CTS pair (1..16, 0 = none); CFB: len % 16
+    uint32_t tail_only;          // the nblocks whole blocks were done by another kernel (ecb_dec_hybrid_kernel): only the tail
 };
 
 __device__ inline void store_bytes(uint8_t *y, const uint32_t w[4], uint32_t n)
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_dec_kernel(const __grid_con
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
     const uint4 iv = make_uint4(a.iv[0], a.iv[1], a.iv[2], a.iv[3]);
 
-    for (uint64_t k = (uint64_t)blockIdx.x * kThreads + threadIdx.x; k < a.nblocks; k += stride) {
+    for (uint64_t k = (uint64_t)blockIdx.x * kThreads + threadIdx.x; k < (a.tail_only ? 0 : a.nblocks); k += stride) {
         const uint4 cur = ld_stream(a.in + k);
         const uint4 prev = k ? a.in[k - 1] : iv;             // the neighbour lane loads it too: L1 hit
         uint32_t s0, s1, s2, s3;
@@ -96,6 +97,22 @@ static cudaError_t launch_chain_nr(const ChainArgs &a, cudaStream_t st)
             return launch_ecb_hybrid_nr<NR, true>(e0, a.nblocks / 1024 * (uint64_t)share, st, a.iv);
         }
     }
+    if (CBC) {                                           // CBC decryption of enough data: ECB-decrypt-shaped, with the inverse-cipher co-runner
+        EcbArgs e0;
+        e0.ks = a.ks; e0.in = a.in; e0.out = a.out; e0.nblocks = a.nblocks; e0.tail = 0; e0.pad = 0;
+        bool done = false;
+        const cudaError_t eh = launch_ecb_dec_hybrid_nr<NR, true>(e0, a.iv, st, done);
+        if (done) {
+            if (eh != cudaSuccess || !a.tail) return eh;
+            ChainArgs t = a;                             // the CS3 pair: one thread of a one-CTA launch
+            t.tail_only = 1;
+            cudaError_t e = opt_in_smem(chain_dec_kernel<NR, CBC>);
+            if (e != cudaSuccess) return e;
+            chain_dec_kernel<NR, CBC><<<1, kThreads, kDynSmem, st>>>(t);
+            ++g_launches;
+            return cudaGetLastError();
+        }
+    }
     cudaError_t e = opt_in_smem(chain_dec_kernel<NR, CBC>);
     if (e != cudaSuccess) return e;
     chain_dec_kernel<NR, CBC><<<grid_for((a.nblocks + 31) / 32), kThreads, kDynSmem, st>>>(a);
@@ -117,7 +134,7 @@ extern "C" int uaes_launch_chain_dec(const uaes_keysched *ks, const uaes_keysche
     a.ks = *ks; a.kse = *kse;
     for (int c = 0; c < 4; ++c)
         a.iv[c] = (uint32_t)iv[4 * c] | (uint32_t)iv[4 * c + 1] << 8 | (uint32_t)iv[4 * c + 2] << 16 | (uint32_t)iv[4 * c + 3] << 24;
-    a.in = (const uint4 *)in; a.out = (uint4 *)out; a.nblocks = nblocks; a.tail = tail;
+    a.in = (const uint4 *)in; a.out = (uint4 *)out; a.nblocks = nblocks; a.tail = tail; a.tail_only = 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (ks->rounds * 2 + (cbc ? 1 : 0)) {
     case 21: return (int)launch_chain_nr<10, true>(a, st);

@@ -854,7 +854,9 @@ __global__ void __launch_bounds__(kThreads, 1) ecb_kernel(const __grid_constant_
 struct EcbHybridArgs {
     EcbArgs e;
     uint64_t tt_blocks;          // blocks [0, tt_blocks): table-driven warps; a multiple of 1024
-    uint32_t iv[4];              // CFB only
+    uint32_t iv[4];              // CFB / CBC only
+    unsigned long long *q;       // ecb_dec_hybrid_kernel: non-null = no static split, the two-ended work queue of ctr_queue_kernel, unit = a tile of 1024 blocks
+    uint32_t q_zero;             // 0 (see q_post)
     BsKeyPlanesFull bs;
 };
 
@@ -1188,6 +1190,160 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     }
 }
 
+// ---- ECB decryption with the co-runner: the shape of xts_sectors_hybrid_kernel's decrypt direction -- 16 table-driven
+// warps with one row in flight at 64 registers (Td tables) + one warpgroup of bitsliced warps running the equivalent
+// inverse cipher (bs_decrypt_planes) on tiles of 1024 blocks at 224.  a.e.ks = the inverse schedule (uaes_host.c).
+#ifndef UAES_ECBDEC_TT
+#define UAES_ECBDEC_TT 512
+#endif
+#ifndef UAES_ECBDEC_ILP
+#define UAES_ECBDEC_ILP 1
+#endif
+#ifndef UAES_ECBDEC_TT_REGS
+#define UAES_ECBDEC_TT_REGS 64
+#endif
+constexpr int kEcbDecTtThreads = UAES_ECBDEC_TT;
+
+// CBC = true turns it into CBC decryption (micro_aes.c:746-782): P_k = D(C_k) ^ C_(k-1), C_(-1) = IV -- the neighbour's
+// ciphertext block is a second, cache-resident load (the CS3 pair at the end is chain_dec_kernel's, uaes_chain.cuh).
+template <int NR, bool CBC>
+__global__ void __launch_bounds__(kEcbDecTtThreads + kBsThreads, 1) ecb_dec_hybrid_kernel(const __grid_constant__ EcbHybridArgs a)
+{
+    const uint4 iv = make_uint4(a.iv[0], a.iv[1], a.iv[2], a.iv[3]);
+    auto prev = [&](uint64_t k) -> uint4 { return !CBC ? make_uint4(0, 0, 0, 0) : k ? a.e.in[k - 1] : iv; };
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const uint32_t lb = setup_tables<false>(dyn);
+    const uint32_t *dk = a.e.ks.w;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kTtWarps = kEcbDecTtThreads / 32;
+    constexpr int kLaunchRegs = (65536 / (kEcbDecTtThreads + kBsThreads)) / 8 * 8;
+    constexpr int kTtRegs = UAES_ECBDEC_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbDecTtThreads / kBsThreads) / 8 * 8;
+
+    const uint64_t nt_all = (a.e.nblocks + 1023) / 1024;         // work-queue mode: tiles of the whole call
+    if (threadIdx.x >= kEcbDecTtThreads) {
+        reg_inc<kBsRegs>();
+        auto do_tile = [&](uint64_t first_block) {
+            const uint64_t kb = first_block + lane;
+            uint32_t s[128];
+#pragma unroll
+            for (int tb = 0; tb < 32; tb += kBsLoadBatch) {
+                uint4 v[kBsLoadBatch];
+#pragma unroll
+                for (int i = 0; i < kBsLoadBatch; ++i) v[i] = kb + 32 * (tb + i) < a.e.nblocks ? ld_stream(a.e.in + kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < kBsLoadBatch; ++i) { s[tb + i] = v[i].x; s[32 + tb + i] = v[i].y; s[64 + tb + i] = v[i].z; s[96 + tb + i] = v[i].w; }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+            bs_decrypt_planes<NR>(s, a.bs);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bs_transpose32(s + 32 * c);
+#pragma unroll
+            for (int tb = 0; tb < 32; tb += 4) {
+                uint4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = kb + 32 * (tb + i) < a.e.nblocks ? prev(kb + 32 * (tb + i)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = tb + i;
+                    if (kb + 32 * t < a.e.nblocks)
+                        st_stream(a.e.out + kb + 32 * t, make_uint4(s[t] ^ x[i].x, s[32 + t] ^ x[i].y, s[64 + t] ^ x[i].z, s[96 + t] ^ x[i].w));
+                }
+            }
+        };
+        if (a.q) {                                   // work queue: tiles from the BACK, the next one claimed a tile ahead
+            uint64_t u = q_back(q_post(a.q, 1ull << 32, a.q_zero), nt_all);
+            while (u != kQNone) {
+                const unsigned long long posted = q_post(a.q, 1ull << 32, a.q_zero);
+                do_tile(u * 1024);
+                u = q_back(posted, nt_all);
+            }
+            return;
+        }
+        const uint64_t ntiles = (a.e.nblocks - a.tt_blocks + 1023) / 1024;
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kEcbDecTtThreads) >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
+        const uint64_t per = (ntiles + nw - 1) / nw;
+        const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
+        const uint64_t p1 = p0 + per < ntiles ? p0 + per : ntiles;
+        for (uint64_t tile = p0; tile < p1; ++tile) do_tile(a.tt_blocks + tile * 1024);
+        return;
+    }
+    reg_dec<kTtRegs>();
+
+    if (a.q) {
+        // work queue: tiles from the FRONT; the next tile is claimed a tile ahead, its answer read half way through
+        // this one, its first row requested with this one's last
+        uint64_t tile = q_front(q_post(a.q, 1ull, a.q_zero), nt_all);
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        if (tile != kQNone && tile * 1024 + lane < a.e.nblocks) cur = ld_stream(a.e.in + tile * 1024 + lane);
+        while (tile != kQNone) {
+            const unsigned long long posted = q_post(a.q, 1ull, a.q_zero);
+            uint64_t next = kQNone;
+            const uint64_t kb = tile * 1024 + lane;
+#pragma unroll 1
+            for (int r = 0; r < 32; ++r) {
+                const uint64_t k = kb + 32 * r;
+                if (r == 16) next = q_front(posted, nt_all);
+                const uint64_t kn = r + 1 < 32 ? k + 32 : next * 1024 + lane;
+                const bool okn = (r + 1 < 32 || next != kQNone) && kn < a.e.nblocks;
+                const uint4 nxt = okn ? ld_stream(a.e.in + kn) : make_uint4(0, 0, 0, 0);
+                const uint4 x[1] = {k < a.e.nblocks ? prev(k) : make_uint4(0, 0, 0, 0)};
+                uint32_t st[1][4] = {{cur.x, cur.y, cur.z, cur.w}};
+                dec_block_n<NR, 1>(lb, st, dk, x);
+                if (k < a.e.nblocks) st_stream(a.e.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
+                cur = nxt;
+            }
+            tile = next;
+        }
+        if (!CBC && a.e.tail && blockIdx.x == 0 && threadIdx.x == 0) {
+            const uint8_t *x = (const uint8_t *)(a.e.in + a.e.nblocks);
+            uint8_t *y = (uint8_t *)(a.e.out + a.e.nblocks);
+            for (uint32_t i = 0; i < a.e.tail; ++i) y[i] = x[i];
+        }
+        return;
+    }
+
+    constexpr int ILP = UAES_ECBDEC_ILP;
+    const uint64_t nsteps = a.tt_blocks / (32 * ILP);            // tt_blocks is a multiple of 1024
+    const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+    const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
+    const uint64_t per = (nsteps + nw - 1) / nw;
+    const uint64_t q0 = gw * per < nsteps ? gw * per : nsteps;
+    const uint64_t q1 = q0 + per < nsteps ? q0 + per : nsteps;
+    uint4 cur[ILP], nxt[ILP];
+    if (q0 < q1) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) cur[i] = ld_stream(a.e.in + q0 * (32 * ILP) + 32 * i + lane);
+    }
+    for (uint64_t q = q0; q < q1; ++q) {
+        const uint64_t k = q * (32 * ILP) + lane;
+        uint4 zero[ILP];
+        uint32_t st[ILP][4];
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (q + 1 < q1) nxt[i] = ld_stream(a.e.in + k + 32 * ILP + 32 * i);
+            zero[i] = prev(k + 32 * i);                          // the neighbour lane loads it too: cache hit
+            st[i][0] = cur[i].x; st[i][1] = cur[i].y; st[i][2] = cur[i].z; st[i][3] = cur[i].w;
+        }
+        dec_block_n<NR, ILP>(lb, st, dk, zero);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            st_stream(a.e.out + k + 32 * i, make_uint4(st[i][0], st[i][1], st[i][2], st[i][3]));
+            cur[i] = nxt[i];
+        }
+    }
+    if (!CBC && a.e.tail && blockIdx.x == 0 && threadIdx.x == 0) {   // the memcpy of micro_aes.c:667 leaves the ragged bytes as they are
+        const uint8_t *x = (const uint8_t *)(a.e.in + a.e.nblocks);
+        uint8_t *y = (uint8_t *)(a.e.out + a.e.nblocks);
+        for (uint32_t i = 0; i < a.e.tail; ++i) y[i] = x[i];
+    }
+}
+
+#ifndef UAES_ECB_DEC_DEFAULT_SHARE
+#define UAES_ECB_DEC_DEFAULT_SHARE 150           // static split: 804 / 903 / 924 / 816 GiB/s at 0 / 130 / 160 / 190; only > 0 matters with the work queue (default)
+#endif
+constexpr int kEcbDecDefaultShare = UAES_ECB_DEC_DEFAULT_SHARE;
 constexpr int kEcbDefaultShare = 195;   // 791 / 830 / 849 / 864 / 814 GiB/s at 0 / 100 / 140 / 180 / 220 (AES-128, profiles/r1_ecb_hybrid_sweep.txt)
 
 template <int NR, bool CFB = false>
@@ -1199,9 +1355,38 @@ static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, c
     a.e = e0;
     for (int c = 0; c < 4; ++c) a.iv[c] = iv ? iv[c] : 0;
     a.tt_blocks = (e0.nblocks - bs_blocks) & ~1023ull;
+    a.q = nullptr; a.q_zero = 0;
     bs_make_key_planes_full(e0.ks.w, NR, &a.bs);
     const uint64_t need = (e0.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
     ecb_hybrid_kernel<NR, CFB><<<(unsigned)(need < sms ? need : sms), kEcbTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// ECB (CBC = false) or CBC (true) decryption of enough data with the co-runner; done = false: not applicable, nothing launched
+template <int NR, bool CBC>
+static cudaError_t launch_ecb_dec_hybrid_nr(const EcbArgs &a, const uint32_t *iv, cudaStream_t st, bool &done)
+{
+    done = false;
+    ctr_tuning_init();
+    const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_ECB_DEC_BS_PERMILLE", kEcbDecDefaultShare);
+    if (!(g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048)) return cudaSuccess;
+    const uint64_t bs_blocks = a.nblocks / 1024 * (uint64_t)share;
+    if (!bs_blocks) return cudaSuccess;
+    done = true;
+    cudaError_t e = opt_in_smem(ecb_dec_hybrid_kernel<NR, CBC>);
+    if (e != cudaSuccess) return e;
+    static thread_local EcbHybridArgs h;
+    h.e = a;
+    for (int c = 0; c < 4; ++c) h.iv[c] = iv ? iv[c] : 0;
+    h.tt_blocks = (a.nblocks - bs_blocks) & ~1023ull;
+    h.q = nullptr; h.q_zero = 0;
+    if (env_int("UAES_ECB_DEC_QUEUE", 1)) {              // dynamic split (the static share is ignored)
+        if ((e = q_slot(st, &h.q)) != cudaSuccess) return e;
+    }
+    bs_make_key_planes_full(a.ks.w, NR, &h.bs);
+    const uint64_t need = (a.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
+    ecb_dec_hybrid_kernel<NR, CBC><<<(unsigned)(need < sms ? need : sms), kEcbDecTtThreads + kBsThreads, kDynSmem, st>>>(h);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -1216,6 +1401,11 @@ static cudaError_t launch_ecb_nr(const EcbArgs &a, cudaStream_t st)
             const uint64_t bs_blocks = a.nblocks / 1024 * (uint64_t)share;
             if (bs_blocks) return launch_ecb_hybrid_nr<NR>(a, bs_blocks, st);
         }
+    }
+    if (!ENC) {                                          // decryption of enough data: with the inverse-cipher co-runner
+        bool done = false;
+        const cudaError_t e = launch_ecb_dec_hybrid_nr<NR, false>(a, nullptr, st, done);
+        if (done) return e;
     }
     cudaError_t e = opt_in_smem(ecb_kernel<NR, ENC>);
     if (e != cudaSuccess) return e;

@@ -10,6 +10,7 @@ namespace uaes {
 // geometry of the kernels with the bitsliced co-runner (table-driven threads; share of the work, per 1024)
 constexpr int kXtsTtThreads = 384;
 constexpr int kXtsDefaultShare = 165;
+constexpr int kXtsDecDefaultShare = 60;      // decryption; only its being > 0 matters when the work queue is on
 #ifndef UAES_XTS_QUEUE_DEFAULT
 #define UAES_XTS_QUEUE_DEFAULT 1
 #endif
@@ -625,7 +626,7 @@ static cudaError_t launch_xts_hybrid_nr(const XtsSectorArgs &x, uint64_t bs_tile
     a.ntiles = (x.nsectors + 31) / 32;
     a.tt_tiles = a.ntiles - bs_tiles;
     a.q = nullptr; a.q_zero = 0;
-    if (ENC && env_int("UAES_XTS_QUEUE", kXtsQueueDefault)) {          // encryption: dynamic split (the static share is ignored)
+    if (env_int(ENC ? "UAES_XTS_QUEUE" : "UAES_XTS_DEC_QUEUE", kXtsQueueDefault)) {   // dynamic split (the static share is ignored)
         if ((e = q_slot(st, &a.q)) != cudaSuccess) return e;
     }
     bs_make_key_planes_full(x.k1.w, NR, &a.bs);
@@ -690,13 +691,12 @@ extern "C" int uaes_launch_xts_sectors(const uaes_keysched *ks1, const uaes_keys
     ctr_tuning_init();
     if (sector_blocks == 32 && g_ctr_share > 0 && (long long)(nsectors * 32) >= g_ctr_bs_min) {
         const uint64_t ntiles = (nsectors + 31) / 32;
-        // Decryption: the bitsliced inverse cipher is correct (tests force it on) but does not pay: the
-        // table-driven decrypt rounds rotate half of their lookups on the ALU pipe (Td2/Td3 from
-        // Td0/Td1), so less of that pipe is idle and the co-runner costs more than it adds
-        // (558 -> 523 / 480 GiB/s at 30 / 100 per 1024).  Off unless asked for.
+        // Decryption: the bitsliced inverse cipher as co-runner did not pay next to 12 table-driven warps with two
+        // sectors in flight (558 -> 523 / 480 GiB/s at 30 / 100 per 1024); next to 16 warps with one sector in flight
+        // it does: 557 -> 589 / 583 at 60 / 100 per 1024 (static split), profiles/r2_sweep_xtsdec_ilp.txt.  On by default.
         const bool narrow = env_int("UAES_XTS_NARROW", UAES_XTS_NARROW_DEFAULT) != 0;
         const int dflt = encrypt ? env_int("UAES_XTS_BS_PERMILLE", kXtsDefaultShare)
-                                 : env_int("UAES_XTS_DEC_BS_PERMILLE", narrow ? UAES_XTS8_DEC_DEFAULT_SHARE : 0);
+                                 : env_int("UAES_XTS_DEC_BS_PERMILLE", narrow ? UAES_XTS8_DEC_DEFAULT_SHARE : kXtsDecDefaultShare);
         const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : dflt;
         const uint64_t bs_tiles = ntiles * (uint64_t)share / 1024;
         if (bs_tiles > 0 && narrow) {

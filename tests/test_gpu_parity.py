@@ -184,7 +184,7 @@ def test_ctr_bitsliced_corunner(uaes, orc, torch, bits):
                 assert host(dst, 0, n) == orc.ctr(key, iv, data, first_block=first), (threads, share, n, first)
                 assert host(dst, n, n + 16) == bytes(16)
     finally:
-        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
+        uaes.ctr_tuning(388, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -222,12 +222,29 @@ def test_ecb_bitsliced_corunner(uaes, orc, bits):
             uaes.ctr_tuning(-1, share, 0)
             key, data = rnd(f"eh-k{bits}{n}", bits // 8), rnd(f"eh-d{bits}{n}", n)
             assert a.AES_ECB_encrypt(key, data) == orc.ecb_encrypt(key, data), (share, n)
+            # decryption: ecb_dec_hybrid_kernel (table-driven Td rounds + the bitsliced equivalent inverse cipher)
+            assert a.AES_ECB_decrypt(key, data) == orc.ecb_decrypt(key, data), (share, n)
             iv = rnd(f"eh-i{bits}{n}", 16)                       # CFB decryption rides the same kernel
             o = ctypes.create_string_buffer(max(n, 1))
             orc.lib.oracle_cfb_decrypt(bits, key, iv, data, n, o)
             assert a.AES_CFB_decrypt(key, iv, data) == o.raw[:n], (share, n)
     finally:
-        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
+        uaes.ctr_tuning(388, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
+
+
+@pytest.mark.parametrize("bits", [128, 192, 256])
+def test_cbc_decrypt_bitsliced_corunner(uaes, orc, bits):
+    """CBC decryption through ecb_dec_hybrid_kernel<NR, true> (table-driven Td rounds + bitsliced inverse cipher, XOR with
+    the previous ciphertext block) forced on for small calls: all splits, whole blocks and CS3 stealing pairs"""
+    a = uaes.MicroAES(bits)
+    try:
+        for share, n in ((1024, 16 * 2048), (512, 16 * 5000 + 7), (300, 16 * 70001), (1024, 16 * 3071 + 15), (1, 16 * 4096 + 1),
+                         (700, 16 * 2049)):
+            uaes.ctr_tuning(-1, share, 0)
+            key, iv, ct = rnd(f"ch-k{bits}{n}", bits // 8), rnd(f"ch-i{bits}{n}", 16), rnd(f"ch-d{bits}{n}", n)
+            assert a.AES_CBC_decrypt(key, iv, ct) == orc.cbc(key, iv, ct), (share, n)
+    finally:
+        uaes.ctr_tuning(388, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -246,7 +263,7 @@ def test_ocb_bitsliced_corunner(uaes, orc, bits):
             assert got[-16:] == want[-16:] and got == want, (share, n)
             assert a.AES_OCB_decrypt(key, nonce, aad, want) == (0, data)
     finally:
-        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
+        uaes.ctr_tuning(388, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("narrow", [1, 0])
@@ -272,7 +289,7 @@ def test_xts_sectors_bitsliced_corunner(uaes, orc, bits, narrow, monkeypatch):
             uaes.xts_sectors(bits, keys, first, 512, data, len(data), back, False)
             assert (0, back.raw) == orc.xts_sectors(keys, first, 512, data, encrypt=False), (share, first, ns)
     finally:
-        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
+        uaes.ctr_tuning(388, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 256])
@@ -288,7 +305,7 @@ def test_xts_unit_bitsliced_corunner(uaes, orc, bits):
             assert a.AES_XTS_encrypt(keys, tw, data) == want, (share, n)
             assert a.AES_XTS_decrypt(keys, tw, want[1]) == (0, data)
     finally:
-        uaes.ctr_tuning(386, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
+        uaes.ctr_tuning(388, 195, 1 << 23)      # library defaults (uaes_kernels.cu kCtrDefaultGeometry / kCtrDefaultShare)
 
 
 @pytest.mark.parametrize("bits", [128, 192, 256])

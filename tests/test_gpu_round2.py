@@ -291,7 +291,7 @@ def test_gcm_bitsliced_corunner(uaes, orc, torch, bits, narrow, monkeypatch):
                 tag = uaes.gcm_combine(bits, key, nonce, aad, [z0, z1], [(n + 15) // 16 - cut // 16, 0], n)
                 assert tag == want[n:], (share, n, decrypt)
     finally:
-        uaes.ctr_tuning(386, 195, 1 << 23)
+        uaes.ctr_tuning(388, 195, 1 << 23)
 
 
 # ---------------------------------------------------------------- XTS: ranges of a unit, XTS-192
