@@ -18,8 +18,9 @@
 // wide form's column routine applied ONCE, because the four columns sit side by side in each
 // register.  Per block the instruction count is that of the wide form plus the 24 PRMTs (+6 %), but a
 // thread needs 32 + 32 + temporaries instead of 128 + 32 + temporaries registers and one round is
-// 420 instructions: two or three such warps fit per scheduler next to the table-driven ones, and
-// the whole round loop stays in the instruction cache.
+// 440 instructions: two such warps fit per scheduler next to the table-driven ones, and the whole
+// round loop stays in the instruction cache.  (Measured, DESIGN.md 5.1: this pays for CTR, whose
+// hoisted rounds 1-2 make a bitsliced block cheap; as GCM or XTS co-runner the wide form stays ahead.)
 //
 // Counter layout of one pass = one GROUP (the 256 counters that share bytes 0..14): lane l, slot t
 // <-> counter byte 15 = 32*t + l, so slot t of all lanes is one coalesced 512-byte row.  Rounds 1-2

@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
 
 // ---- CTR work-queue kernel with NARROW bitsliced warps (uaes_bitslice8.cuh) --------------------------
 // Same queue, same table-driven role; the co-runner warps hold 8 blocks per thread in 32 registers
-// instead of 32 blocks in 128, so they need no more registers than the table-driven warps and
-// several of them fit per scheduler (more warps to pick from when the table-driven ones wait for
-// the lookup pipe), and their round loop is 420 instructions instead of 1 600 (instruction cache).
+// instead of 32 blocks in 128, so they need 96-112 registers instead of 224 and two of them fit per
+// scheduler (more warps to pick from when the table-driven ones wait for the lookup pipe), and
+// their round loop is 440 instructions instead of 1 600 (instruction cache).
 // One pass = one group (256 counters, 8 rows): the state entering round 3 is U(byte 15) ^ D(group);
 // the thread's U planes are computed once per 2^40 blocks and parked in shared memory (lane-private
 // words, conflict free), D is expanded into 32 mask words by the 32 lanes of the warp.

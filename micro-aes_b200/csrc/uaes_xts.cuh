@@ -498,6 +498,9 @@ __global__ void __launch_bounds__(kXtsHybTt + kBsThreads, 1) xts_sectors_hybrid_
 // <-> block l of sector t.  32 state registers instead of 128: the warps run in 96 registers like the table-driven
 // ones (8 of them per SM, no setmaxnreg) and one round is 440 (forward) / 520 (inverse) instructions, so the
 // round loop -- also the INVERSE one, whose wide form did not fit the instruction cache -- stays cached.
+// MEASURED SLOWER than the wide form (522 vs 612 GiB/s encrypt, 490 vs 558 decrypt, profiles/r2_sweep_xts8.txt): without
+// CTR's hoisted rounds a narrow block costs 1.5 x the instructions of a table-driven one.  Selectable (UAES_XTS_NARROW=1),
+// parity-tested, off by default.
 struct XtsHybridArgs8 {
     XtsSectorArgs x;             // sector_blocks == 32
     uint64_t tt_tiles, ntiles;   // as XtsHybridArgs
