@@ -148,7 +148,17 @@ struct OcbHybridArgs {
     BsKeyPlanesFull bs;
 };
 
-constexpr int kOcbTtThreads = 384;
+// table-driven side: UAES_OCB_TT threads with UAES_OCB_ILP rows in flight at UAES_OCB_TT_REGS registers (profiles/r2_sweep_ocb_ilp.txt)
+#ifndef UAES_OCB_TT
+#define UAES_OCB_TT 384
+#endif
+#ifndef UAES_OCB_ILP
+#define UAES_OCB_ILP 2
+#endif
+#ifndef UAES_OCB_TT_REGS
+#define UAES_OCB_TT_REGS kHybridTtRegs
+#endif
+constexpr int kOcbTtThreads = UAES_OCB_TT;
 
 // D_(i+32) = D_i ^ L_4 ^ L_(5 + ntz((i >> 5) + 1)),  i = k + 1 (1-based index of the block just done)
 __device__ __forceinline__ void ocb_step32(uint4 &delta, const uint4 *Ls, const uint4 &L4, uint64_t k)
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kOcbTtThreads / 32;
     constexpr int kLaunchRegs = (65536 / (kOcbTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = kHybridTtRegs, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kOcbTtThreads / kBsThreads;
+    constexpr int kTtRegs = UAES_OCB_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kOcbTtThreads / kBsThreads) / 8 * 8;
     const uint64_t nblocks = a.o.nblocks;
     uint4 sum = make_uint4(0, 0, 0, 0);
 
@@ -225,6 +235,32 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
         }
     } else {
         reg_dec<kTtRegs>();
+#if UAES_OCB_ILP == 1
+        // one row in flight per thread (the 16-warp geometry of xts_sectors_hybrid_kernel / ecb_dec_hybrid_kernel)
+        const uint64_t nrows = a.tt_blocks / 32;
+        const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
+        const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
+        const uint64_t per = (nrows + nw - 1) / nw;
+        const uint64_t q0 = gw * per < nrows ? gw * per : nrows;
+        const uint64_t q1 = q0 + per < nrows ? q0 + per : nrows;
+        if (q0 < q1) {
+            const uint4 L4 = Ls[4];
+            uint4 dl[1];
+            dl[0] = a.o.work->off0;
+            xor4(dl[0], ocb_gray_sum(Ls, q0 * 32 + lane + 1));
+            uint4 cur = ld_stream(a.o.in + q0 * 32 + lane), nxt = make_uint4(0, 0, 0, 0);
+            for (uint64_t q = q0; q < q1; ++q) {
+                const uint64_t k = q * 32 + lane;
+                if (q + 1 < q1) nxt = ld_stream(a.o.in + k + 32);
+                xor4(sum, cur);
+                uint32_t st[1][4] = {{cur.x ^ dl[0].x ^ rk[0], cur.y ^ dl[0].y ^ rk[1], cur.z ^ dl[0].z ^ rk[2], cur.w ^ dl[0].w ^ rk[3]}};
+                enc_finish_n<NR, 1, 1>(lb, st, rk, dl);
+                st_stream(a.o.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
+                ocb_step32(dl[0], Ls, L4, k);
+                cur = nxt;
+            }
+        }
+#else
         const uint64_t npairs = a.tt_blocks / 64;
         const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
         const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
@@ -257,6 +293,7 @@ __global__ void __launch_bounds__(kOcbTtThreads + kBsThreads, 1) ocb_hybrid_kern
                 cur[0] = nxt[0]; cur[1] = nxt[1];
             }
         }
+#endif
     }
     for (int o = 16; o; o >>= 1) {
         sum.x ^= __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y ^= __shfl_xor_sync(0xffffffffu, sum.y, o);
