@@ -398,6 +398,9 @@ __device__ __forceinline__ uint64_t q_back(unsigned long long posted, uint64_t u
     return f + b < units ? units - 1 - b : kQNone;
 }
 
+#ifndef UAES_TT_L2_PREFETCH
+#define UAES_TT_L2_PREFETCH 0
+#endif
 #ifndef UAES_TT_ROLL_ROWS
 #define UAES_TT_ROLL_ROWS 0                     // 1: one copy of the round code for both row pairs of a group; measured -13 % (profiles/r2_sweep_q8.txt)
 #endif
@@ -479,6 +482,14 @@ __device__ __forceinline__ void ctr_queue_table_role(const CtrArgsBase &a, uint3
                 // where this warp's rows continue after the group (warp-uniform selects, no branches): the next
                 // group of this half; the first group of the other half; the first group of the unit claimed ahead
                 const bool last_group = jj + 1 == kGroupsPerUnit;
+#if UAES_TT_L2_PREFETCH
+                // the next group's four rows of this half (2 KiB = 16 lines) towards L2: the loads that fetch a row ahead
+                // into registers then find it there (one row takes a warp about as long as a DRAM access under load)
+                if (!last_group && lane < 16) {
+                    const int64_t kp = (int64_t)(((G + 1) << 8) + 128 * half + 8 * lane) - (int64_t)a.v0;
+                    if (kp >= 0 && (uint64_t)kp < a.nblocks) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + kp));
+                }
+#endif
                 const uint64_t Gn = !last_group ? G + 1 : half == 0 ? Gu : Gfirst + unext * kGroupsPerUnit;
                 const uint32_t rn = !last_group ? 4 * half : half == 0 ? 4u : 0u;
                 const bool okn = !last_group || half == 0 || unext != kQNone;
