@@ -306,7 +306,13 @@ struct GcmHybridArgs {
 #ifndef UAES_GCM_BS_AHEAD
 #define UAES_GCM_BS_AHEAD 1                       // rows a bitsliced warp loads ahead of its XOR / store / absorb loop
 #endif
-constexpr int kGcmHybTtThreads = 384;
+#ifndef UAES_GCM_TT
+#define UAES_GCM_TT 384                           // table-driven threads of the co-runner kernels
+#endif
+#ifndef UAES_GCM_TT_REGS
+#define UAES_GCM_TT_REGS 96
+#endif
+constexpr int kGcmHybTtThreads = UAES_GCM_TT;
 constexpr int kGcmHybTtWarps = kGcmHybTtThreads / 32;
 
 template <int NR, int MODE>
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(kGcmHybTtThreads + kBsThreads, 1) gcm_bulk_hyb
     asm volatile("" : "+r"(lb), "+r"(mb)::"memory");
 
     constexpr int kLaunchRegs = (65536 / (kGcmHybTtThreads + kBsThreads)) / 8 * 8;     // 128
-    constexpr int kTtRegs = 96, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kGcmHybTtThreads / kBsThreads;   // 224
+    constexpr int kTtRegs = UAES_GCM_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kGcmHybTtThreads / kBsThreads) / 8 * 8;   // 224
     if (threadIdx.x >= kGcmHybTtThreads) {
         reg_inc<kBsRegs>();
         const uint32_t bw = (threadIdx.x - kGcmHybTtThreads) >> 5;
