@@ -110,9 +110,11 @@ void uaes_shutdown(void);
 /* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
 uaes_u64 uaes_kernel_launches(void);
 /* CTR kernel geometry (tuning and tests; the defaults are the measured optimum on B200):
- *   tt_threads       geometry code: 386 (default) = 384 table-driven threads with two blocks in
- *                    flight each + 128 bitsliced co-runner threads sharing the counter range through a
- *                    two-ended work queue; 385 = the same warps with a static split (bs_permille);
+ *   tt_threads       geometry code: 388 (default) = ctr_queue8_kernel: table-driven warps + NARROW bitsliced
+ *                    co-runner warps (8 blocks per thread) sharing the counter range through a two-ended
+ *                    work queue (AES-128: 16 + 8 warps); 386 = ctr_queue_kernel: 384 table-driven threads
+ *                    with two blocks in flight each + 128 wide bitsliced threads on the same queue;
+ *                    385 = the same warps with a static split (bs_permille);
  *                    384 = static split, one block in flight; 512 / 768 / 1024 = table-driven warps only
  *   bs_permille      share of the blocks, in 1/1024, given to the bitsliced ALU co-runner warps
  *                    (0 = co-runner off)
@@ -120,7 +122,7 @@ uaes_u64 uaes_kernel_launches(void);
  *                    (default 2^23 = 128 MiB; the same threshold serves ECB, XTS, OCB and CFB)
  * A negative value leaves that setting unchanged.  Results do not depend on any of them. */
 void uaes_ctr_tuning(int tt_threads, int bs_permille, long long bs_min_blocks);
-/* how the calling thread's most recent work-queue CTR launch (geometry 386) was shared out: units
+/* how the calling thread's most recent work-queue CTR launch (geometry 388 / 386) was shared out: units
  * served by the table-driven warps, by the bitsliced warps, and 16-byte blocks per unit.  Waits for
  * the device.  (bench.py derives the shared-memory-lookup roofline from it.) */
 int uaes_ctr_queue_stats(uaes_u64 *tt_units, uaes_u64 *bs_units, uaes_u64 *unit_blocks);

@@ -1,4 +1,4 @@
-"""The two-ended work queue of ctr_queue_kernel / xts_sectors_hybrid_kernel (csrc/uaes_kernels.cu, q_post /
+"""The two-ended work queue of ctr_queue8_kernel / ctr_queue_kernel / xts_sectors_hybrid_kernel / ecb_dec_hybrid_kernel (csrc/uaes_kernels.cu, q_post /
 q_front / q_back), restated in Python and checked on random interleavings: table-driven warps claim units from
 the front, bitsliced warps from the back, through ONE atomic add on a packed (front, back) word; a claim is
 valid iff front + back < units *at its own place in the atomic order*.
