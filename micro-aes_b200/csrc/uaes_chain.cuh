@@ -90,7 +90,7 @@ static cudaError_t launch_chain_nr(const ChainArgs &a, cudaStream_t st)
 {
     if (!CBC) {                                          // CFB decryption of enough data: ECB-shaped, with the co-runner
         ctr_tuning_init();
-        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_ECB_BS_PERMILLE", kEcbDefaultShare);
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_ECB_BS_PERMILLE", kCfbDefaultShare);
         if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048) {
             EcbArgs e0;
             e0.ks = a.ks; e0.in = a.in; e0.out = a.out; e0.nblocks = a.nblocks; e0.tail = a.tail; e0.pad = 0;

@@ -882,9 +882,23 @@ struct EcbHybridArgs {
 #define UAES_ECB_TT_REGS kHybridTtRegs
 #endif
 constexpr int kEcbTtThreads = UAES_ECB_TT;
+// CFB decryption (the same kernel, CFB = true) does gain from the 16-warp geometry: 884 against 854 GiB/s
+#ifndef UAES_CFB_TT
+#define UAES_CFB_TT 512
+#endif
+#ifndef UAES_CFB_ILP
+#define UAES_CFB_ILP 1
+#endif
+#ifndef UAES_CFB_TT_REGS
+#define UAES_CFB_TT_REGS 64
+#endif
+template <bool CFB> struct EcbGeom {
+    static constexpr int TT = CFB ? UAES_CFB_TT : UAES_ECB_TT, ILP = CFB ? UAES_CFB_ILP : UAES_ECB_ILP;
+    static constexpr int TTREGS = CFB ? UAES_CFB_TT_REGS : UAES_ECB_TT_REGS;
+};
 
 template <int NR, bool CFB>
-__global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kernel(const __grid_constant__ EcbHybridArgs a)
+__global__ void __launch_bounds__(EcbGeom<CFB>::TT + kBsThreads, 1) ecb_hybrid_kernel(const __grid_constant__ EcbHybridArgs a)
 {
     const uint4 iv = make_uint4(a.iv[0], a.iv[1], a.iv[2], a.iv[3]);
     // cipher input of block k: the block itself (ECB) or its predecessor (CFB)
@@ -893,14 +907,14 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
     const uint32_t lb = setup_tables<true>(dyn);
     const uint32_t *rk = a.e.ks.w;
     const uint32_t lane = threadIdx.x & 31;
-    constexpr int kTtWarps = kEcbTtThreads / 32;
-    constexpr int kLaunchRegs = (65536 / (kEcbTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = UAES_ECB_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kEcbTtThreads / kBsThreads) / 8 * 8;
+    constexpr int kTt = EcbGeom<CFB>::TT, kTtWarps = kTt / 32;
+    constexpr int kLaunchRegs = (65536 / (kTt + kBsThreads)) / 8 * 8;
+    constexpr int kTtRegs = EcbGeom<CFB>::TTREGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kTt / kBsThreads) / 8 * 8;
 
-    if (threadIdx.x >= kEcbTtThreads) {
+    if (threadIdx.x >= kTt) {
         reg_inc<kBsRegs>();
         const uint64_t ntiles = (a.e.nblocks - a.tt_blocks + 1023) / 1024;
-        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kEcbTtThreads) >> 5);
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kTt) >> 5);
         const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
         const uint64_t per = (ntiles + nw - 1) / nw;
         const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
@@ -939,7 +953,7 @@ __global__ void __launch_bounds__(kEcbTtThreads + kBsThreads, 1) ecb_hybrid_kern
     }
     reg_dec<kTtRegs>();
 
-    constexpr int ILP = UAES_ECB_ILP;                            // 32-block rows in flight per thread
+    constexpr int ILP = EcbGeom<CFB>::ILP;                       // 32-block rows in flight per thread
     const uint64_t nsteps = a.tt_blocks / (32 * ILP);            // tt_blocks is a multiple of 1024
     const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
@@ -1355,6 +1369,7 @@ __global__ void __launch_bounds__(kEcbDecTtThreads + kBsThreads, 1) ecb_dec_hybr
 #define UAES_ECB_DEC_DEFAULT_SHARE 150           // static split: 804 / 903 / 924 / 816 GiB/s at 0 / 130 / 160 / 190; only > 0 matters with the work queue (default)
 #endif
 constexpr int kEcbDecDefaultShare = UAES_ECB_DEC_DEFAULT_SHARE;
+constexpr int kCfbDefaultShare = 170;   // CFB decryption in the 16-warp geometry: 870 / 892 / 883 / 842 GiB/s at 150 / 175 / 195 / 215 (profiles/r2_sweep_cfb_ilp.txt)
 constexpr int kEcbDefaultShare = 195;   // 791 / 830 / 849 / 864 / 814 GiB/s at 0 / 100 / 140 / 180 / 220 (AES-128, profiles/r1_ecb_hybrid_sweep.txt)
 
 template <int NR, bool CFB = false>
@@ -1369,7 +1384,7 @@ static cudaError_t launch_ecb_hybrid_nr(const EcbArgs &e0, uint64_t bs_blocks, c
     a.q = nullptr; a.q_zero = 0;
     bs_make_key_planes_full(e0.ks.w, NR, &a.bs);
     const uint64_t need = (e0.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
-    ecb_hybrid_kernel<NR, CFB><<<(unsigned)(need < sms ? need : sms), kEcbTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    ecb_hybrid_kernel<NR, CFB><<<(unsigned)(need < sms ? need : sms), EcbGeom<CFB>::TT + kBsThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
