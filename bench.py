@@ -203,7 +203,7 @@ KERNEL_NAMES = {
     "ecb128dec": "uaes::ecb_dec_hybrid_kernel<10,false> (16 table-driven warps + 4 bitsliced inverse-cipher warps, work queue)",
     "xts256": "uaes::xts_sectors_hybrid_kernel<14,true> (16 table-driven warps, one sector in flight + 4 bitsliced warps, work queue)",
     "xts256dec": "uaes::xts_sectors_hybrid_kernel<14,false> (16 table-driven warps + 4 bitsliced inverse-cipher warps, work queue)",
-    "xts256unit": "uaes::xts_unit_kernel<14,true>",
+    "xts256unit": "uaes::xts_unit_hybrid_kernel<14> (16 table-driven warps, one row in flight + 4 bitsliced warps, static split)",
     "gcm128": "uaes::gcm_setup_kernel + uaes::gcm_bulk_hybrid_kernel<10,0> (table-driven + bitsliced warps) + uaes::gcm_finish_kernel",
     "gcmsiv128": "uaes::gcm_bulk_kernel<10,1,true> (POLYVAL) + uaes::ctr32_kernel<10>",
     "ocb128": "uaes::ocb_hybrid_kernel<10> (table-driven + bitsliced warps)",

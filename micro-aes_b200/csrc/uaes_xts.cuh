@@ -10,6 +10,7 @@ namespace uaes {
 // geometry of the kernels with the bitsliced co-runner (table-driven threads; share of the work, per 1024)
 constexpr int kXtsTtThreads = 384;
 constexpr int kXtsDefaultShare = 165;
+constexpr int kXtsUnitDefaultShare = 140;    // one large data unit (static split)
 constexpr int kXtsDecDefaultShare = 60;      // decryption; only its being > 0 matters when the work queue is on
 #ifndef UAES_XTS_QUEUE_DEFAULT
 #define UAES_XTS_QUEUE_DEFAULT 1
@@ -210,8 +211,20 @@ struct XtsUnitHybridArgs {
     BsKeyPlanesFull bs;
 };
 
+// table-driven side of the single-unit kernel with a co-runner: as in xts_sectors_hybrid_kernel
+#ifndef UAES_XTSU_TT
+#define UAES_XTSU_TT 512
+#endif
+#ifndef UAES_XTSU_ILP
+#define UAES_XTSU_ILP 1
+#endif
+#ifndef UAES_XTSU_TT_REGS
+#define UAES_XTSU_TT_REGS 64
+#endif
+constexpr int kXtsUnitTt = UAES_XTSU_TT;
+
 template <int NR>
-__global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid_kernel(const __grid_constant__ XtsUnitHybridArgs a)
+__global__ void __launch_bounds__(kXtsUnitTt + kBsThreads, 1) xts_unit_hybrid_kernel(const __grid_constant__ XtsUnitHybridArgs a)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
     volatile uint32_t *t0s = (volatile uint32_t *)(dyn + dyn_smem_size() - 16);
@@ -225,15 +238,15 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid
     Tweak T0;
     T0.lo = (uint64_t)t0s[1] << 32 | t0s[0];
     T0.hi = (uint64_t)t0s[3] << 32 | t0s[2];
-    constexpr int kTtWarps = kXtsTtThreads / 32;
-    constexpr int kLaunchRegs = (65536 / (kXtsTtThreads + kBsThreads)) / 8 * 8;
-    constexpr int kTtRegs = kHybridTtRegs, kBsRegs = kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsTtThreads / kBsThreads;
+    constexpr int kTtWarps = kXtsUnitTt / 32;
+    constexpr int kLaunchRegs = (65536 / (kXtsUnitTt + kBsThreads)) / 8 * 8;
+    constexpr int kTtRegs = UAES_XTSU_TT_REGS, kBsRegs = (kLaunchRegs + (kLaunchRegs - kTtRegs) * kXtsUnitTt / kBsThreads) / 8 * 8;
     const uint64_t nblocks = a.u.nblocks;
 
-    if (threadIdx.x >= kXtsTtThreads) {
+    if (threadIdx.x >= kXtsUnitTt) {
         reg_inc<kBsRegs>();
         const uint64_t ntiles = (nblocks - a.tt_blocks + 1023) / 1024;
-        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsTtThreads) >> 5);
+        const uint64_t gw = (uint64_t)blockIdx.x * (kBsThreads / 32) + ((threadIdx.x - kXtsUnitTt) >> 5);
         const uint64_t nw = (uint64_t)gridDim.x * (kBsThreads / 32);
         const uint64_t per = (ntiles + nw - 1) / nw;
         const uint64_t p0 = gw * per < ntiles ? gw * per : ntiles;
@@ -278,32 +291,36 @@ __global__ void __launch_bounds__(kXtsTtThreads + kBsThreads, 1) xts_unit_hybrid
     reg_dec<kTtRegs>();
 
     const uint32_t *k1 = a.u.k1.w;
-    const uint64_t npairs = a.tt_blocks / 64;
+    constexpr int ILP = UAES_XTSU_ILP;                           // rows in flight per thread
+    const uint64_t nsteps = a.tt_blocks / (32 * ILP);            // tt_blocks is a multiple of 1024
     const uint64_t gw = (uint64_t)blockIdx.x * kTtWarps + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * kTtWarps;
-    const uint64_t per = (npairs + nw - 1) / nw;
-    const uint64_t q0 = gw * per < npairs ? gw * per : npairs;
-    const uint64_t q1 = q0 + per < npairs ? q0 + per : npairs;
+    const uint64_t per = (nsteps + nw - 1) / nw;
+    const uint64_t q0 = gw * per < nsteps ? gw * per : nsteps;
+    const uint64_t q1 = q0 + per < nsteps ? q0 + per : nsteps;
     if (q0 < q1) {
-        Tweak t = xts_jump(T0, a.u.first_block + q0 * 64 + lane);
-        uint4 cur[2], nxt[2];
-        cur[0] = ld_stream(a.u.in + q0 * 64 + lane); cur[1] = ld_stream(a.u.in + q0 * 64 + 32 + lane);
-        for (uint64_t q = q0; q < q1; ++q) {
-            const uint64_t k = q * 64 + lane;
-            if (q + 1 < q1) { nxt[0] = ld_stream(a.u.in + k + 64); nxt[1] = ld_stream(a.u.in + k + 96); }
-            uint32_t st[2][4];
-            uint4 tw[2];
+        Tweak t = xts_jump(T0, a.u.first_block + q0 * (32 * ILP) + lane);
+        uint4 cur[ILP], nxt[ILP];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ILP; ++i) cur[i] = ld_stream(a.u.in + q0 * (32 * ILP) + 32 * i + lane);
+        for (uint64_t q = q0; q < q1; ++q) {
+            const uint64_t k = q * (32 * ILP) + lane;
+            uint32_t st[ILP][4];
+            uint4 tw[ILP];
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                if (q + 1 < q1) nxt[i] = ld_stream(a.u.in + k + 32 * ILP + 32 * i);
                 tweak_words(t, tw[i].x, tw[i].y, tw[i].z, tw[i].w);
                 t = xts_shl(t, 32);
                 st[i][0] = cur[i].x ^ tw[i].x ^ k1[0]; st[i][1] = cur[i].y ^ tw[i].y ^ k1[1];
                 st[i][2] = cur[i].z ^ tw[i].z ^ k1[2]; st[i][3] = cur[i].w ^ tw[i].w ^ k1[3];
             }
-            enc_finish_n<NR, 1, 2>(lb, st, k1, tw);
-            st_stream(a.u.out + k, make_uint4(st[0][0], st[0][1], st[0][2], st[0][3]));
-            st_stream(a.u.out + k + 32, make_uint4(st[1][0], st[1][1], st[1][2], st[1][3]));
-            cur[0] = nxt[0]; cur[1] = nxt[1];
+            enc_finish_n<NR, 1, ILP>(lb, st, k1, tw);
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                st_stream(a.u.out + k + 32 * i, make_uint4(st[i][0], st[i][1], st[i][2], st[i][3]));
+                cur[i] = nxt[i];
+            }
         }
     }
     if (a.u.tail && blockIdx.x == 0 && threadIdx.x == 0) xts_steal_tail<true>(a.u, T0);
@@ -649,7 +666,7 @@ static cudaError_t launch_xts_unit_hybrid_nr(const XtsUnitArgs &u, uint64_t bs_b
     a.tt_blocks = (u.nblocks - bs_blocks) & ~1023ull;
     bs_make_key_planes_full(u.k1.w, NR, &a.bs);
     const uint64_t need = (u.nblocks + 32 * 16 - 1) / (32 * 16), sms = (uint64_t)sm_count();
-    xts_unit_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kXtsTtThreads + kBsThreads, kDynSmem, st>>>(a);
+    xts_unit_hybrid_kernel<NR><<<(unsigned)(need < sms ? need : sms), kXtsUnitTt + kBsThreads, kDynSmem, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -658,11 +675,11 @@ template <int NR, bool ENC>
 static cudaError_t launch_xts_unit_nr(const XtsUnitArgs &a, cudaStream_t st)
 {
     if (ENC) {
-        // A large unit with the co-runner: correct (tests force it on) but not a gain yet -- the 64-bit
-        // tweak stepping next to the 128 planes spills inside the bitsliced rounds: 574 GiB/s without,
-        // 535 with (profiles/r1_xts_hybrid_sweep.txt).  Off unless asked for.
+        // A large unit with the co-runner.  Next to 12 table-driven warps with two rows in flight it lost (574 GiB/s
+        // without, 535 with, profiles/r1_xts_hybrid_sweep.txt); next to 16 warps with one row in flight at 64 registers it
+        // pays: 574 -> 619 / 640 / 618 GiB/s at 100 / 140 / 180 per 1024 (AES-256, profiles/r2_sweep_xtsunit_ilp.txt).
         ctr_tuning_init();
-        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_XTS_UNIT_BS_PERMILLE", 0);
+        const int share = g_ctr_share != kCtrDefaultShare ? g_ctr_share : env_int("UAES_XTS_UNIT_BS_PERMILLE", kXtsUnitDefaultShare);
         if (g_ctr_share > 0 && share > 0 && (long long)a.nblocks >= g_ctr_bs_min && a.nblocks >= 2048)
             return launch_xts_unit_hybrid_nr<NR>(a, a.nblocks / 1024 * (uint64_t)share, st);
     }
