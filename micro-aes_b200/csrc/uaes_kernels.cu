@@ -98,7 +98,7 @@ struct CtrArgsBase {
     uint64_t bs_u0;              // v0 + tt_blocks: first counter (not reduced mod 2^56) of the
                                  // bitsliced range, a multiple of 1024 unless bs_passes == 0
     uint64_t bs_passes;          // 1024-counter passes covering blocks [tt_blocks, nblocks)
-    // work-queue form (ctr_queue_kernel): the counter range in units of kQUnit blocks, handed out
+    // work-queue form (ctr_queue_kernel): the counter range in units of 2^q_shift blocks, handed out
     // from the front to the table-driven warps and from the back to the bitsliced warps
     unsigned long long *q;       // device: [0] front | back << 32, [1] units done by table-driven warps, [2] by bitsliced warps
     uint64_t q_u0;               // counter (not reduced mod 2^56) where unit 0 starts: v0 rounded down to a unit
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_ke
 
 // ---- CTR with a two-ended work queue ---------------------------------------------------------------
 // Same two kinds of warps as ctr_kernel, but no static split: the counter range is cut into units of
-// kQUnit blocks; table-driven warps claim units from the FRONT, bitsliced warps from the BACK, through
+// 2^q_shift blocks; table-driven warps claim units from the FRONT, bitsliced warps from the BACK, through
 // one 64-bit atomic add on a packed (front, back) word.  A claim sees both counts at its own place in
 // the atomic order, so "front + back < units" decides exactly and without a retry loop whether the
 // unit is still free: the two kinds of warps meet wherever their actual speeds on THIS GPU put the
@@ -364,7 +364,6 @@ __global__ void __launch_bounds__(kCtrThreads + (BS ? kBsThreads : 0), 1) ctr_ke
 #define UAES_Q_UNIT_SHIFT 11                     // 2048 blocks = 32 KiB = 8 groups = 2 bitsliced passes
 #endif
 constexpr int kQUnitShift = UAES_Q_UNIT_SHIFT;
-constexpr uint64_t kQUnit = 1ull << kQUnitShift;
 constexpr uint64_t kQNone = ~0ull;
 
 // A claim is split in two so that nobody waits for the atomic: q_post() issues it from lane 0 (the
@@ -567,7 +566,6 @@ __global__ void __launch_bounds__(kCtrThreads + kBsThreads, 1) ctr_queue_kernel(
     static_assert(ILP == 2, "two rows in flight per table-driven thread");
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_tables<true>(dyn);
-    const uint32_t *rk = a.ks.w;
     const uint32_t lane = threadIdx.x & 31;
     constexpr int kLaunchRegs = (65536 / (kCtrThreads + kBsThreads)) / 8 * 8;
 #ifndef UAES_Q_TT_REGS
@@ -881,7 +879,6 @@ struct EcbHybridArgs {
 #ifndef UAES_ECB_TT_REGS
 #define UAES_ECB_TT_REGS kHybridTtRegs
 #endif
-constexpr int kEcbTtThreads = UAES_ECB_TT;
 // CFB decryption (the same kernel, CFB = true) does gain from the 16-warp geometry: 884 against 854 GiB/s
 #ifndef UAES_CFB_TT
 #define UAES_CFB_TT 512
@@ -1149,7 +1146,7 @@ static cudaError_t launch_ctr_nr(CtrArgs &a, cudaStream_t st)
     a.tt_blocks = a.nblocks; a.bs_u0 = 0; a.bs_passes = 0;
     a.q = nullptr; a.q_u0 = 0; a.q_units = 0; a.q_bs_on = 0; a.q_zero = 0; a.q_shift = kQUnitShift;
     if (threads == 386) {
-        // work queue: units of kQUnit counters, aligned in counter space; both kinds of warps clip to
+        // work queue: units of 2^q_shift counters, aligned in counter space; both kinds of warps clip to
         // [v0, v0 + nblocks).  Short calls keep the co-runner out (a bitsliced unit takes longer than a
         // table-driven one, which shows when there are fewer units than warps).
         // units of 2048 blocks; 1024 when a warp gets fewer than ~64 of them (below 4 GiB): the last unit of the

@@ -480,7 +480,6 @@ __global__ void __launch_bounds__(kXtsHybTt + kBsThreads, 1) xts_sectors_hybrid_
 {
     extern __shared__ __align__(16) uint8_t dyn[];
     const uint32_t lb = setup_xts_tables<ENC>(dyn);
-    const uint32_t lane = threadIdx.x & 31;
     constexpr int kTtWarps = kXtsHybTt / 32;
     constexpr int kLaunchRegs = (65536 / (kXtsHybTt + kBsThreads)) / 8 * 8;          // 128 for 384 + 128 threads
     // 96 / 224: 582 -> 596 GiB/s for AES-256 (profiles/r2_sweep_hybrid_regs.txt); ECB and OCB keep 104 / 200
